@@ -1,0 +1,132 @@
+"""Host-side preprocessing that bcf's R wrapper does before and after the native call.
+
+Restates the R code of `bcf::bcf` [bcf-recall; the package is imported
+by the reference at NAMESPACE:9 and called at R/bcf_iv.R:89, R/bcf_itt.R:71].  Plain NumPy: this is
+O(n p) once per call and stays on the CPU (SURVEY 8f-3 lists it as a later row).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+CP_NUM = 10000      # .cp_quantile(num=10000)
+CP_CAT_LEVELS = 8   # .cp_quantile(cat_levels=8)
+
+
+def cp_quantile(x: np.ndarray, num: int = CP_NUM, cat_levels: int = CP_CAT_LEVELS) -> np.ndarray:
+    """Cutpoint grid of one covariate column (bcf's `.cp_quantile`).
+
+    1 distinct value -> that value (with a warning); fewer than `cat_levels` distinct values ->
+    midpoints between them; otherwise `num` points of approxfun(sort(x), quantile(x, 0:(n-1)/n))
+    evaluated on seq(min, max, length.out=num).
+    """
+    x = np.asarray(x, dtype=np.float64)
+    ux = np.unique(x)
+    if ux.size == 1:
+        warnings.warn("A supplied covariate contains a single distinct value.")
+        return x[:1].copy()
+    if ux.size < cat_levels:
+        return ux[:-1] + np.diff(ux) / 2.0
+    n = x.size
+    xs = np.sort(x)
+    qs = np.quantile(xs, np.arange(n) / n)          # R quantile type 7 == numpy 'linear'
+    # approxfun(ties = mean): collapse tied abscissae, averaging their ordinates
+    uxs, inv = np.unique(xs, return_inverse=True)
+    mq = np.bincount(inv, weights=qs) / np.bincount(inv)
+    grid = np.linspace(xs[0], xs[-1], num)
+    return np.interp(grid, uxs, mq)
+
+
+def make_cutpoints(X: np.ndarray):
+    """Per-column cutpoints of an n x p matrix -> list of p sorted float64 vectors."""
+    X = np.asarray(X, dtype=np.float64)
+    return [cp_quantile(X[:, v]) for v in range(X.shape[1])]
+
+
+def pack_cuts(cut_list):
+    """list of per-variable cutpoint vectors -> (flat float64 cuts, int32 offsets[p+1]) as the C-ABI takes them."""
+    off = np.zeros(len(cut_list) + 1, dtype=np.int32)
+    for v, c in enumerate(cut_list):
+        off[v + 1] = off[v] + len(c)
+    flat = np.concatenate([np.asarray(c, dtype=np.float64) for c in cut_list]) if cut_list else np.zeros(0)
+    return np.ascontiguousarray(flat), off
+
+
+def lm_sigma(yscale: np.ndarray, z: np.ndarray, x_c: np.ndarray) -> float:
+    """summary(lm(yscale ~ z + x_c))$sigma via the normal equations (rank-aware)."""
+    n = yscale.size
+    A = np.column_stack([np.ones(n), np.asarray(z, dtype=np.float64), np.asarray(x_c, dtype=np.float64)])
+    G = A.T @ A
+    b = A.T @ yscale
+    beta, _, rank, _ = np.linalg.lstsq(G, b, rcond=None)
+    rss = float(np.sum((yscale - A @ beta) ** 2))
+    dof = max(n - int(rank), 1)
+    return float(np.sqrt(rss / dof))
+
+
+def qchisq(p: float, df: float) -> float:
+    from scipy.stats import chi2
+    return float(chi2.ppf(p, df))
+
+
+class Prepared:
+    """Everything the native sampler needs, in bcf's internal conventions."""
+
+    __slots__ = ("n", "ntrt", "perm", "inv_perm", "muy", "sdy", "yscale", "z", "x_c", "x_m", "cuts_c", "cuts_m",
+                 "sighat", "lambda_", "con_sd", "mod_sd", "sigma_init")
+
+
+def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_control=None, sd_moderate=None,
+            nu=3.0, lambda_=None, sigq=0.9, sighat=None, use_tauscale=True) -> Prepared:
+    """bcf's R-side preamble [bcf-recall, SURVEY A.1].  Returns arrays in the ORIGINAL row order plus `perm`
+    (treated rows first, stable: R's order(z, decreasing=TRUE)); the native library applies the permutation."""
+    y = np.asarray(y, dtype=np.float64).ravel()
+    z = np.asarray(z).ravel()
+    x_control = np.asarray(x_control, dtype=np.float64)
+    x_moderate = np.asarray(x_moderate, dtype=np.float64)
+    if x_control.ndim == 1:
+        x_control = x_control[:, None]
+    if x_moderate.ndim == 1:
+        x_moderate = x_moderate[:, None]
+    pihat = np.asarray(pihat, dtype=np.float64)
+    if pihat.ndim == 1:
+        pihat = pihat[:, None]
+    n = y.size
+    if not (z.size == n and x_control.shape[0] == n and x_moderate.shape[0] == n and pihat.shape[0] == n):
+        raise ValueError("y, z, x_control, x_moderate and pihat must have the same number of rows")
+    if np.any(~np.isfinite(y)) or np.any(~np.isfinite(x_control)) or np.any(~np.isfinite(x_moderate)) \
+            or np.any(~np.isfinite(pihat)):
+        raise ValueError("Missing or non-finite values in y, x_control, x_moderate or pihat")
+    if not np.all((z == 0) | (z == 1)):
+        raise ValueError("z must be a vector of 0's and 1's")
+    if include_pi not in ("control", "moderate", "both", "none"):
+        raise ValueError("include_pi must be one of 'control', 'moderate', 'both', 'none'")
+    if np.unique(y).size < 5:
+        warnings.warn("y appears to be discrete")
+
+    x_c = np.column_stack([x_control, pihat]) if include_pi in ("control", "both") else x_control
+    x_m = np.column_stack([x_moderate, pihat]) if include_pi in ("moderate", "both") else x_moderate
+
+    P = Prepared()
+    P.n = n
+    P.muy = float(np.mean(y))
+    P.sdy = float(np.std(y, ddof=1))
+    P.yscale = (y - P.muy) / P.sdy
+    P.z = z.astype(np.int32)
+    P.x_c, P.x_m = x_c, x_m
+    P.cuts_c = make_cutpoints(x_c)
+    P.cuts_m = make_cutpoints(x_m)
+    P.sighat = float(sighat) if sighat is not None else lm_sigma(P.yscale, z, x_c)
+    P.lambda_ = float(lambda_) if lambda_ is not None else P.sighat ** 2 * qchisq(1.0 - sigq, nu) / nu
+    P.perm = np.argsort(-P.z, kind="stable")          # treated first, ties in original order
+    P.inv_perm = np.empty(n, dtype=np.int64)
+    P.inv_perm[P.perm] = np.arange(n)
+    P.ntrt = int(np.sum(P.z == 1))
+    sdc = 2.0 * P.sdy if sd_control is None else float(sd_control)
+    sdm = P.sdy if sd_moderate is None else float(sd_moderate)
+    P.con_sd = 2.0 if np.isclose(sdc, 2.0 * P.sdy) else sdc / P.sdy
+    mod = 1.0 if np.isclose(sdm, P.sdy) else sdm / P.sdy
+    P.mod_sd = mod / 0.674 if use_tauscale else mod
+    P.sigma_init = float(np.std(P.yscale, ddof=1))
+    return P
