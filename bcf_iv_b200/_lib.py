@@ -1,0 +1,340 @@
+"""ctypes binding of libbcfgpu.so -- exactly the entry points declared in include/bcfgpu.h.
+
+This is the Python stand-in for the R shim (bcf_iv_b200/R/src/r_shim.c): same C-ABI, host buffers in, host
+buffers out.  There is no CPU fallback: if the library is missing it is an ImportError-like failure, and if
+there is no CUDA device every compute call raises BcfGpuError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbcfgpu.so")
+
+MAX_LEAVES = 128
+STATUS = {0: "OK", 1: "BAD_ARG", 2: "CUDA", 3: "NCCL", 4: "NUMERIC", 5: "OOM", 6: "STATE"}
+ENGINE_AUTO, ENGINE_GRAPH, ENGINE_PERSISTENT = 0, 1, 2
+
+# every symbol include/bcfgpu.h declares (tests check the library exports each of them)
+SYMBOLS = [
+    "bcfgpu_abi_version", "bcfgpu_device_count", "bcfgpu_last_error", "bcfgpu_config_init", "bcfgpu_create",
+    "bcfgpu_destroy", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_data", "bcfgpu_run",
+    "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
+    "bcfgpu_get_mu_mean", "bcfgpu_get_yhat_mean", "bcfgpu_get_sigma", "bcfgpu_get_scales", "bcfgpu_get_draws",
+    "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
+    "bcfgpu_get_tree", "bcfgpu_set_tree", "bcfgpu_get_leaf_ids", "bcfgpu_verify_leaf_cache", "bcfgpu_op_bin_column",
+    "bcfgpu_op_suffstats", "bcfgpu_op_hist_all", "bcfgpu_op_lil", "bcfgpu_op_rng_probe",
+]
+
+
+class BcfGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libbcfgpu: {STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("ntree_con", C.c_int32), ("ntree_mod", C.c_int32),
+        ("alpha_con", C.c_double), ("beta_con", C.c_double), ("alpha_mod", C.c_double), ("beta_mod", C.c_double),
+        ("con_sd", C.c_double), ("mod_sd", C.c_double), ("nu", C.c_double), ("lambda_", C.c_double),
+        ("sigma_init", C.c_double), ("use_muscale", C.c_int32), ("use_tauscale", C.c_int32),
+        ("min_leaf", C.c_int32), ("max_leaves", C.c_int32), ("seed", C.c_uint64), ("chain", C.c_uint32),
+        ("device", C.c_int32), ("engine", C.c_int32), ("keep_draws", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """dlopen libbcfgpu.so (building it first if nvcc is there and it is missing).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build
+        build.build_lib()
+    if not os.path.exists(LIB_PATH):
+        raise OSError(f"{LIB_PATH} is missing: build it with `python -m bcf_iv_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int32); up = C.POINTER(C.c_uint32); lp = C.POINTER(C.c_int64)
+    vp = C.c_void_p
+    L.bcfgpu_abi_version.restype = C.c_int
+    L.bcfgpu_device_count.restype = C.c_int
+    L.bcfgpu_last_error.restype = C.c_char_p
+    L.bcfgpu_config_init.argtypes = [C.POINTER(Config)]
+    L.bcfgpu_config_init.restype = None
+    L.bcfgpu_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.bcfgpu_destroy.argtypes = [vp]
+    L.bcfgpu_nccl_unique_id.argtypes = [C.c_char_p]
+    L.bcfgpu_set_shard.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.bcfgpu_set_data.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, dp, ip, dp, dp, dp, ip, dp, ip]
+    L.bcfgpu_run.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    L.bcfgpu_last_run_ms.argtypes = [vp, dp]
+    L.bcfgpu_kernel_launches.argtypes = [vp, lp]
+    L.bcfgpu_num_saved.argtypes = [vp, ip]
+    for nm in ("tau_mean", "tau_var", "mu_mean", "yhat_mean", "sigma"):
+        getattr(L, "bcfgpu_get_" + nm).argtypes = [vp, dp]
+    L.bcfgpu_get_scales.argtypes = [vp, dp, dp]
+    L.bcfgpu_get_draws.argtypes = [vp, C.c_int32, dp]
+    L.bcfgpu_get_scalars.argtypes = [vp, dp]
+    L.bcfgpu_get_fits.argtypes = [vp, dp, dp]
+    L.bcfgpu_get_counters.argtypes = [vp, lp]
+    L.bcfgpu_get_trace.argtypes = [vp, ip, dp]
+    L.bcfgpu_tree_size.argtypes = [vp, C.c_int32, ip]
+    L.bcfgpu_get_tree.argtypes = [vp, C.c_int32, up, ip, ip, dp]
+    L.bcfgpu_set_tree.argtypes = [vp, C.c_int32, C.c_int32, up, ip, ip, dp]
+    L.bcfgpu_get_leaf_ids.argtypes = [vp, C.c_int32, up]
+    L.bcfgpu_verify_leaf_cache.argtypes = [vp, lp]
+    L.bcfgpu_op_bin_column.argtypes = [dp, C.c_int64, dp, C.c_int32, C.POINTER(C.c_uint16)]
+    L.bcfgpu_op_suffstats.argtypes = [vp, C.c_int32, dp, C.c_uint32, C.c_int32, C.c_int32, ip, up, lp, lp, dp, dp, dp]
+    L.bcfgpu_op_hist_all.argtypes = [vp, C.c_int32, ip, C.c_int32, dp, lp, dp, dp]
+    L.bcfgpu_op_lil.argtypes = [dp, dp, dp, C.c_int32, dp]
+    L.bcfgpu_op_rng_probe.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp]
+    for nm in SYMBOLS:
+        f = getattr(L, nm)
+        if nm not in ("bcfgpu_last_error", "bcfgpu_config_init"):
+            f.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+def _up(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def _lp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def check(code):
+    if code != 0:
+        raise BcfGpuError(code, load().bcfgpu_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    return load().bcfgpu_device_count()
+
+
+def default_config() -> Config:
+    c = Config()
+    load().bcfgpu_config_init(C.byref(c))
+    return c
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(load().bcfgpu_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Sampler:
+    """Thin object wrapper over a bcfgpu_handle."""
+
+    def __init__(self, **kw):
+        L = load()
+        c = default_config()
+        for k, v in kw.items():
+            if k == "lambda":
+                k = "lambda_"
+            if not hasattr(c, k):
+                raise TypeError(f"unknown config field {k}")
+            setattr(c, k, v)
+        self.cfg = c
+        self.T = c.ntree_con + c.ntree_mod
+        self._h = C.c_void_p()
+        check(L.bcfgpu_create(C.byref(c), C.byref(self._h)))
+        self.n = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            load().bcfgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_shard(self, rank, nranks, unique_id: bytes | None):
+        check(load().bcfgpu_set_shard(self._h, rank, nranks, unique_id))
+
+    def set_data(self, y, z, x_con, x_mod, cuts_con, off_con, cuts_mod=None, off_mod=None):
+        """x_con / x_mod: n x p arrays (any layout; converted to column-major float64 without copying when they
+        already are Fortran-ordered)."""
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.int32)
+        xc = np.asfortranarray(x_con, dtype=np.float64)
+        n = y.size
+        if self.cfg.ntree_mod > 0:
+            xm = np.asfortranarray(x_mod, dtype=np.float64)
+            cm = np.ascontiguousarray(cuts_mod, dtype=np.float64); om = np.ascontiguousarray(off_mod, dtype=np.int32)
+            p_mod = xm.shape[1]
+        else:
+            xm = cm = om = None
+            p_mod = 0
+        cc = np.ascontiguousarray(cuts_con, dtype=np.float64); oc = np.ascontiguousarray(off_con, dtype=np.int32)
+        if xc.shape[0] != n or z.size != n or (xm is not None and xm.shape[0] != n):
+            raise ValueError("row count mismatch")
+        if oc.size != xc.shape[1] + 1 or (om is not None and om.size != p_mod + 1):
+            raise ValueError("cut offsets must have p+1 entries")
+        check(load().bcfgpu_set_data(self._h, n, xc.shape[1], p_mod, _dp(y), _ip(z), _dp(xc), _dp(xm), _dp(cc),
+                                     _ip(oc), _dp(cm), _ip(om)))
+        self.n = n
+        self.off_con, self.off_mod = oc, om
+        self.p_con, self.p_mod = xc.shape[1], p_mod
+        self.h2d_bytes = y.nbytes + z.nbytes + xc.nbytes + (xm.nbytes if xm is not None else 0) + cc.nbytes + \
+            (cm.nbytes if cm is not None else 0)
+
+    def run(self, nburn, nsim, nthin=1):
+        check(load().bcfgpu_run(self._h, nburn, nsim, nthin))
+
+    @property
+    def last_run_ms(self):
+        v = C.c_double()
+        check(load().bcfgpu_last_run_ms(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def kernel_launches(self):
+        v = C.c_int64()
+        check(load().bcfgpu_kernel_launches(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def num_saved(self):
+        v = C.c_int32()
+        check(load().bcfgpu_num_saved(self._h, C.byref(v)))
+        return v.value
+
+    def _vec(self, name):
+        o = np.zeros(self.n)
+        check(getattr(load(), "bcfgpu_get_" + name)(self._h, _dp(o)))
+        return o
+
+    def tau_mean(self):
+        return self._vec("tau_mean")
+
+    def tau_var(self):
+        return self._vec("tau_var")
+
+    def mu_mean(self):
+        return self._vec("mu_mean")
+
+    def yhat_mean(self):
+        return self._vec("yhat_mean")
+
+    def sigma(self):
+        o = np.zeros(max(self.num_saved, 1))
+        check(load().bcfgpu_get_sigma(self._h, _dp(o)))
+        return o[: self.num_saved]
+
+    def scales(self):
+        a = np.zeros(max(self.num_saved, 1)); b = np.zeros(max(self.num_saved, 1))
+        check(load().bcfgpu_get_scales(self._h, _dp(a), _dp(b)))
+        return a[: self.num_saved], b[: self.num_saved]
+
+    def draws(self, which):
+        idx = {"tau": 0, "mu": 1, "yhat": 2}[which]
+        o = np.zeros((self.num_saved, self.n))
+        check(load().bcfgpu_get_draws(self._h, idx, _dp(o)))
+        return o
+
+    def scalars(self):
+        o = np.zeros(8)
+        check(load().bcfgpu_get_scalars(self._h, _dp(o)))
+        return dict(sigma=o[0], mscale=o[1], bscale1=o[2], bscale0=o[3], delta_con=o[4], tau_con=o[5], tau_mod=o[6],
+                    sweep=int(o[7]))
+
+    def fits(self):
+        a = np.zeros(self.n); b = np.zeros(self.n)
+        check(load().bcfgpu_get_fits(self._h, _dp(a), _dp(b)))
+        return a, b
+
+    def counters(self):
+        o = np.zeros(4, dtype=np.int64)
+        check(load().bcfgpu_get_counters(self._h, _lp(o)))
+        return dict(birth_prop=int(o[0]), birth_acc=int(o[1]), death_prop=int(o[2]), death_acc=int(o[3]))
+
+    def trace(self):
+        t = np.zeros((self.T, 5), dtype=np.int32); lr = np.zeros(self.T)
+        check(load().bcfgpu_get_trace(self._h, _ip(t), _dp(lr)))
+        return t, lr
+
+    def get_tree(self, tid):
+        k = C.c_int32()
+        check(load().bcfgpu_tree_size(self._h, tid, C.byref(k)))
+        k = k.value
+        heap = np.zeros(k, dtype=np.uint32); var = np.zeros(k, dtype=np.int32); cut = np.zeros(k, dtype=np.int32)
+        mu = np.zeros(k)
+        check(load().bcfgpu_get_tree(self._h, tid, _up(heap), _ip(var), _ip(cut), _dp(mu)))
+        return heap, var, cut, mu
+
+    def set_tree(self, tid, heap, var, cut, mu):
+        heap = np.ascontiguousarray(heap, dtype=np.uint32); var = np.ascontiguousarray(var, dtype=np.int32)
+        cut = np.ascontiguousarray(cut, dtype=np.int32); mu = np.ascontiguousarray(mu, dtype=np.float64)
+        check(load().bcfgpu_set_tree(self._h, tid, len(heap), _up(heap), _ip(var), _ip(cut), _dp(mu)))
+
+    def leaf_ids(self, tid):
+        o = np.zeros(self.n, dtype=np.uint32)
+        check(load().bcfgpu_get_leaf_ids(self._h, tid, _up(o)))
+        return o
+
+    def verify_leaf_cache(self):
+        v = C.c_int64()
+        check(load().bcfgpu_verify_leaf_cache(self._h, C.byref(v)))
+        return v.value
+
+    def op_suffstats(self, tid, r, birth_leaf_heap=0, var=0, cut=0):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        nl = C.c_int32()
+        heap = np.zeros(MAX_LEAVES, dtype=np.uint32)
+        ct = np.zeros(MAX_LEAVES, dtype=np.int64); cc = np.zeros(MAX_LEAVES, dtype=np.int64)
+        st = np.zeros(MAX_LEAVES); sc = np.zeros(MAX_LEAVES); ob = np.zeros(8)
+        check(load().bcfgpu_op_suffstats(self._h, tid, _dp(r), int(birth_leaf_heap), int(var), int(cut), C.byref(nl),
+                                         _up(heap), _lp(ct), _lp(cc), _dp(st), _dp(sc), _dp(ob)))
+        k = nl.value
+        return dict(heap=heap[:k], cnt_trt=ct[:k], cnt_ctl=cc[:k], sum_trt=st[:k], sum_ctl=sc[:k], birth=ob)
+
+    def op_hist_all(self, forest, slot, nleaf, r):
+        off = self.off_con if forest == 0 else self.off_mod
+        p = self.p_con if forest == 0 else self.p_mod
+        nb = int(off[p]) + p
+        slot = np.ascontiguousarray(slot, dtype=np.int32); r = np.ascontiguousarray(r, dtype=np.float64)
+        cnt = np.zeros((nleaf, nb), dtype=np.int64); s = np.zeros((nleaf, nb)); ms = C.c_double()
+        check(load().bcfgpu_op_hist_all(self._h, forest, _ip(slot), nleaf, _dp(r), _lp(cnt), _dp(s), C.byref(ms)))
+        return cnt, s, ms.value
+
+
+def op_bin_column(x, cuts):
+    x = np.ascontiguousarray(x, dtype=np.float64); cuts = np.ascontiguousarray(cuts, dtype=np.float64)
+    out = np.zeros(x.size, dtype=np.uint16)
+    check(load().bcfgpu_op_bin_column(_dp(x), x.size, _dp(cuts), cuts.size, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+    return out
+
+
+def op_lil(sum_phi, sum_phi_r, tau):
+    a = np.ascontiguousarray(sum_phi, dtype=np.float64); b = np.ascontiguousarray(sum_phi_r, dtype=np.float64)
+    t = np.ascontiguousarray(tau, dtype=np.float64); o = np.zeros(a.size)
+    check(load().bcfgpu_op_lil(_dp(a), _dp(b), _dp(t), a.size, _dp(o)))
+    return o
+
+
+def op_rng_probe(seed, chain, sweep, tree, purpose, idx):
+    o = np.zeros(3)
+    check(load().bcfgpu_op_rng_probe(seed, chain, sweep, tree, purpose, idx, _dp(o)))
+    return o

@@ -1,0 +1,347 @@
+// bcf_device.cuh -- device-side data structures and building blocks of the BCF Gibbs sweep (sm_100a).
+//
+// What is replaced (third-party `bcf` C++ sampler reached from R/bcf_iv.R:89 and R/bcf_itt.R:71):
+//   tree / tree::bn / fit  -> flat TreeRec + cached uint8 leaf slot per (tree, observation)        (a2)
+//   getsuff / allsuff      -> one fused pass: per-leaf (count, sum r) by treatment group, exact    (a4,a5)
+//   bd / bdhet             -> propose() + decide(): structural prior ratio, integrated likelihood  (a6)
+//   drmu / drmuhet         -> leaf draws inside decide()                                            (a7)
+// Sums are accumulated in 64-bit FIXED POINT (value * 2^44 split in three 21-bit limbs), so every reduction
+// is associative: results do not depend on thread, CTA or GPU partitioning, and every CTA / rank can replay the
+// Metropolis-Hastings decision from the same bits.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace bcf {
+
+constexpr int MAXL = 128;           // BCFGPU_MAX_LEAVES
+constexpr int MAXN = 256;           // node capacity (2*MAXL-1 used)
+constexpr int KEYS = MAXL + 1;      // leaf slots + the would-be right child of a birth
+constexpr int MAX_DEPTH = 30;       // BCFGPU_MAX_DEPTH
+constexpr int TILE = 256;           // observations per warp tile (8 per lane)
+constexpr int PAD_SLOT = 255;       // slot value of padding observations
+constexpr int FX_SHIFT = 44;        // fixed point: value * 2^44
+constexpr int LIMB_BITS = 21;
+constexpr int KREG = 8;             // key-loop (register + REDUX) path up to this many keys, shared atomics above
+constexpr int NMOM = 6;             // moments per group: yy, yGc, yGm, GcGc, GcGm, GmGm
+constexpr int THREADS = 256;
+
+enum { PUR_MOVE = 0, PUR_NODE = 1, PUR_CUT = 2, PUR_LEAF = 3, PUR_BSCALE1 = 10, PUR_BSCALE0 = 11,
+       PUR_MSCALE = 12, PUR_DELTA_CON = 13, PUR_DELTA_MOD = 14, PUR_SIGMA = 15 };
+constexpr uint32_t TREE_SWEEP_LEVEL = 0xFFFFFFFFu;
+
+enum { ERR_NAN = 1, ERR_FX_RANGE = 2, ERR_BARRIER_TIMEOUT = 4 };
+
+// ---------------------------------------------------------------------------------------------
+// Flat tree.  Node 0 is the root; nodes are kept compact (swap-with-last on death).
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) TreeRec {
+    int32_t nnodes, nleaves;
+    int32_t pad_[2];
+    int16_t parent[MAXN], left[MAXN], right[MAXN];   // -1 = none
+    uint16_t var[MAXN], cut[MAXN];                   // split rule of internal nodes
+    uint8_t node_slot[MAXN];                         // leaf slot of leaf nodes
+    uint8_t depth[MAXN];
+    uint32_t heap[MAXN];                             // heap id: root 1, children 2i / 2i+1
+    int16_t slot_node[MAXL];                         // node of each leaf slot
+    double mu[MAXL];                                 // leaf value per slot
+};
+static_assert(sizeof(TreeRec) % 16 == 0, "TreeRec must be copyable as uint4");
+
+struct Proposal {
+    int32_t move;        // 0 none, 1 birth, 2 death
+    int32_t node;        // birth: the leaf node; death: the nog node
+    int32_t slot;        // birth: slot of the leaf (left child keeps it); death: slot of the left child
+    int32_t slot_b;      // birth: slot the right child would get (= nleaves); death: slot of the right child
+    int32_t var, cut;
+    uint32_t heap;
+    int32_t pad_;
+    double log_prior;    // log of the structural part of the MH ratio (alpha1)
+    double u_acc;
+};
+
+struct Scalars {
+    double sigma, mscale, bscale1, bscale0, delta_con, delta_mod, tau_con, tau_mod;
+    uint32_t sweep;      // global sweep index (Philox counter word 0)
+    int32_t parity;      // which TreeRec copy is current
+    int32_t run_it, nburn, nthin, nsim, save_ctr, save_row;   // save_row: row to write this sweep or -1
+    int32_t pad_[2];
+};
+
+struct ForestDev {
+    int32_t p, ntree, tree0, is_con;
+    const uint8_t* bins8;      // [col][n_pad]
+    const uint16_t* bins16;    // [col][n_pad]
+    const int32_t* col_index;  // [p] index within bins8 / bins16
+    const uint8_t* col_is16;   // [p]
+    const int32_t* ncut;       // [p]
+    double pg[32];             // alpha / (1+depth)^beta, tabulated on the host (bit-identical pow)
+};
+
+struct Dev {
+    int64_t n_pad;             // padded local observations (multiple of TILE)
+    int64_t n_global;          // real observations over all shards (chi-square degrees of freedom)
+    int32_t n_tiles, trt_tiles;  // tiles [0, trt_tiles) are treated, the rest control
+    int32_t T, max_leaves, min_leaf;
+    int32_t use_muscale, use_tauscale;
+    uint32_t key0, key1;       // Philox key
+    double nu, lambda, con_sd, mod_sd;
+    ForestDev f[2];
+    const double* y;
+    double *r, *Gc, *Gm;
+    uint8_t* slots;            // [T][n_pad]
+    TreeRec* trees[2];
+    Proposal* prop;            // [T]
+    long long* totals;         // [T][KEYS][2][4]  (count, limb0, limb1, limb2) by (key, group)
+    long long* mom;            // [2 buffers][2 groups][NMOM][3]; the GRAPH engine uses buffer 0 only
+    Scalars* sc;
+    int32_t* err;              // device error flags (ERR_*)
+    int32_t* trace;            // [T][5]
+    double* trace_logr;        // [T]
+    long long* counters;       // [4]
+    double *tau_sum, *tau_sq, *mu_sum, *yhat_sum;
+    double *draws_tau, *draws_mu, *draws_yhat;   // [nsim][n_pad] or null
+    double *sigma_post, *msd_post, *bsd_post;    // [cap]
+    int32_t post_cap;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, same addressing as the oracle: counter = (sweep, tree, purpose, idx)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct Rng { uint32_t k0, k1; };
+
+__host__ __device__ inline void rng_u2(Rng g, uint32_t sweep, uint32_t tree, uint32_t purpose, uint32_t idx,
+                                       double& ua, double& ub)
+{
+    uint32_t o[4];
+    philox4x32_10(sweep, tree, purpose, idx, g.k0, g.k1, o);
+    const double inv53 = 1.0 / 9007199254740992.0;
+    ua = ((double)(((uint64_t)(o[0] >> 5) << 26) | (uint64_t)(o[1] >> 6)) + 0.5) * inv53;
+    ub = ((double)(((uint64_t)(o[2] >> 5) << 26) | (uint64_t)(o[3] >> 6)) + 0.5) * inv53;
+}
+
+__device__ inline double rng_normal(Rng g, uint32_t sweep, uint32_t tree, uint32_t purpose, uint32_t idx)
+{
+    double ua, ub;
+    rng_u2(g, sweep, tree, purpose, idx, ua, ub);
+    return sqrt(-2.0 * log(ua)) * cos(6.283185307179586476925286766559 * ub);
+}
+
+// Gamma(a, 1) by Marsaglia-Tsang; attempt t uses idx 2t (normal) and 2t+1 (uniform), as the oracle does.
+__device__ inline double rng_gamma(Rng g, uint32_t sweep, uint32_t purpose, double a)
+{
+    double boost = 1.0;
+    if (a < 1.0) {
+        double ua, ub;
+        rng_u2(g, sweep, TREE_SWEEP_LEVEL, purpose, 0xFFFFFFFFu, ua, ub);
+        boost = pow(ua, 1.0 / a);
+        a += 1.0;
+    }
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (uint32_t t = 0;; ++t) {
+        const double z = rng_normal(g, sweep, TREE_SWEEP_LEVEL, purpose, 2 * t);
+        double ua, ub;
+        rng_u2(g, sweep, TREE_SWEEP_LEVEL, purpose, 2 * t + 1, ua, ub);
+        const double w = 1.0 + c * z;
+        if (w <= 0.0) continue;
+        const double v = w * w * w;
+        if (log(ua) < 0.5 * z * z + d - d * v + d * log(v)) return boost * d * v;
+        if (t > 1000000u) return boost * d;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed point
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long to_fixed(double x, int& bad)
+{
+    // |x| < 2^18 keeps x * 2^44 inside int64 with headroom; NaN compares false and trips the flag
+    if (!(fabs(x) < 262144.0)) { bad = 1; return 0; }
+    return __double2ll_rn(x * 17592186044416.0);
+}
+// exact value of limb sums (w0 + w1*2^21 + w2*2^42) / 2^44 rounded once to double
+__host__ __device__ inline double limbs_to_double(long long w0, long long w1, long long w2)
+{
+    __int128 v = (__int128)w0 + ((__int128)w1 << LIMB_BITS) + ((__int128)w2 << (2 * LIMB_BITS));
+    const long long hi = (long long)(v >> 40);
+    const long long lo = (long long)(v & (((__int128)1 << 40) - 1));
+    return ((double)hi * 1099511627776.0 + (double)lo) * (1.0 / 17592186044416.0);
+}
+
+// Accumulate one warp tile (8 observations per lane) of (key, value) pairs into the CTA table
+// tab[key][group][4] = (count, limb0, limb1, limb2).  Keys >= K (padding) are ignored.
+// K <= KREG: per-key predicated register sums + warp REDUX, four shared atomics per key per warp.
+// K >  KREG: one shared atomic set per observation (addresses are spread when there are many leaves).
+__device__ __forceinline__ void accum_tile(long long (*tab)[2][4], const int (&key)[8], const double (&val)[8],
+                                           int g, int K, int lane, int& bad)
+{
+    int l0[8], l1[8], l2[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        const long long v = to_fixed(val[o], bad);
+        l0[o] = (int)(v & 0x1FFFFF);
+        l1[o] = (int)((v >> LIMB_BITS) & 0x1FFFFF);
+        l2[o] = (int)(v >> (2 * LIMB_BITS));
+    }
+    if (K <= KREG) {
+        for (int k = 0; k < K; ++k) {
+            int c = 0, a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const bool m = (key[o] == k);
+                c += m ? 1 : 0; a0 += m ? l0[o] : 0; a1 += m ? l1[o] : 0; a2 += m ? l2[o] : 0;
+            }
+            c = __reduce_add_sync(0xffffffffu, c);
+            a0 = __reduce_add_sync(0xffffffffu, a0);
+            a1 = __reduce_add_sync(0xffffffffu, a1);
+            a2 = __reduce_add_sync(0xffffffffu, a2);
+            if (lane < 4 && c != 0) {
+                const long long v = lane == 0 ? c : lane == 1 ? a0 : lane == 2 ? a1 : a2;
+                atomicAdd((unsigned long long*)&tab[k][g][lane], (unsigned long long)v);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const int k = key[o];
+            if (k < K) {
+                atomicAdd((unsigned long long*)&tab[k][g][0], 1ull);
+                atomicAdd((unsigned long long*)&tab[k][g][1], (unsigned long long)(long long)l0[o]);
+                atomicAdd((unsigned long long*)&tab[k][g][2], (unsigned long long)(long long)l1[o]);
+                atomicAdd((unsigned long long*)&tab[k][g][3], (unsigned long long)(long long)l2[o]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Loads: 8 consecutive observations per lane
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8_u8(const uint8_t* p, int (&out)[8])
+{
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    out[0] = v.x & 0xFF; out[1] = (v.x >> 8) & 0xFF; out[2] = (v.x >> 16) & 0xFF; out[3] = v.x >> 24;
+    out[4] = v.y & 0xFF; out[5] = (v.y >> 8) & 0xFF; out[6] = (v.y >> 16) & 0xFF; out[7] = v.y >> 24;
+}
+__device__ __forceinline__ void st8_u8(uint8_t* p, const int (&in)[8])
+{
+    uint2 v;
+    v.x = (uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16) | ((uint32_t)in[3] << 24);
+    v.y = (uint32_t)in[4] | ((uint32_t)in[5] << 8) | ((uint32_t)in[6] << 16) | ((uint32_t)in[7] << 24);
+    *reinterpret_cast<uint2*>(p) = v;
+}
+__device__ __forceinline__ void ld8_u16(const uint16_t* p, int (&out)[8])
+{
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    out[0] = v.x & 0xFFFF; out[1] = v.x >> 16; out[2] = v.y & 0xFFFF; out[3] = v.y >> 16;
+    out[4] = v.z & 0xFFFF; out[5] = v.z >> 16; out[6] = v.w & 0xFFFF; out[7] = v.w >> 16;
+}
+__device__ __forceinline__ void ld8_f64(const double* p, double (&out)[8])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double2 v = reinterpret_cast<const double2*>(p)[j];
+        out[2 * j] = v.x; out[2 * j + 1] = v.y;
+    }
+}
+__device__ __forceinline__ void st8_f64(double* p, const double (&in)[8])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(p)[j] = make_double2(in[2 * j], in[2 * j + 1]);
+}
+// bins of variable v for 8 observations starting at `base`
+__device__ __forceinline__ void ld8_bins(const ForestDev& F, int v, int64_t n_pad, int64_t base, int (&out)[8])
+{
+    const int ci = F.col_index[v];
+    if (F.col_is16[v]) ld8_u16(F.bins16 + (int64_t)ci * n_pad + base, out);
+    else ld8_u8(F.bins8 + (int64_t)ci * n_pad + base, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tree structure helpers (run by single threads on a TreeRec staged in shared memory)
+// ---------------------------------------------------------------------------------------------
+// usable cutpoint range of variable v at `node` (tree::rg)
+__device__ inline void tree_rg(const TreeRec& tr, const ForestDev& F, int node, int v, int& lo, int& hi)
+{
+    lo = 0; hi = F.ncut[v] - 1;
+    int child = node;
+    for (int a = tr.parent[node]; a >= 0; child = a, a = tr.parent[a]) {
+        if (tr.var[a] != v) continue;
+        if (tr.left[a] == child) hi = min(hi, (int)tr.cut[a] - 1);
+        else lo = max(lo, (int)tr.cut[a] + 1);
+    }
+}
+// Variables exhausted on the path to `node`, ascending; returns how many.  Every variable has >= 1 cutpoint
+// (checked by set_data), so the good variables are exactly the others.
+__device__ inline int tree_exhausted(const TreeRec& tr, const ForestDev& F, int node, int (&ex)[MAX_DEPTH + 2])
+{
+    int nex = 0;
+    for (int a = tr.parent[node]; a >= 0; a = tr.parent[a]) {
+        const int v = tr.var[a];
+        bool seen = false;
+        for (int b = tr.parent[node]; b != a; b = tr.parent[b]) if (tr.var[b] == v) { seen = true; break; }
+        if (seen) continue;
+        int lo, hi;
+        tree_rg(tr, F, node, v, lo, hi);
+        if (hi < lo) {
+            int j = nex++;
+            while (j > 0 && ex[j - 1] > v) { ex[j] = ex[j - 1]; --j; }
+            ex[j] = v;
+        }
+    }
+    return nex;
+}
+__device__ inline int tree_ngoodvars(const TreeRec& tr, const ForestDev& F, int node)
+{
+    if (tr.depth[node] >= MAX_DEPTH) return 0;
+    int ex[MAX_DEPTH + 2];
+    return F.p - tree_exhausted(tr, F, node, ex);
+}
+// vi-th good variable in increasing order
+__device__ inline int tree_pick_var(const TreeRec& tr, const ForestDev& F, int node, int vi)
+{
+    int ex[MAX_DEPTH + 2];
+    const int nex = tree_exhausted(tr, F, node, ex);
+    int v = vi;
+    for (int j = 0; j < nex; ++j) if (ex[j] <= v) ++v;
+    return v;
+}
+__device__ inline void tree_remove_node(TreeRec& tr, int i)
+{
+    const int last = tr.nnodes - 1;
+    if (i != last) {
+        tr.parent[i] = tr.parent[last]; tr.left[i] = tr.left[last]; tr.right[i] = tr.right[last];
+        tr.var[i] = tr.var[last]; tr.cut[i] = tr.cut[last]; tr.node_slot[i] = tr.node_slot[last];
+        tr.depth[i] = tr.depth[last]; tr.heap[i] = tr.heap[last];
+        const int p = tr.parent[i];
+        if (p >= 0) { if (tr.left[p] == last) tr.left[p] = (int16_t)i; else tr.right[p] = (int16_t)i; }
+        if (tr.left[i] >= 0) { tr.parent[tr.left[i]] = (int16_t)i; tr.parent[tr.right[i]] = (int16_t)i; }
+        else tr.slot_node[tr.node_slot[i]] = (int16_t)i;
+    }
+    tr.nnodes = last;
+}
+__host__ __device__ inline double lil(double sum_phi, double sum_phi_r, double tau)
+{
+    const double d = 1.0 / (tau * tau) + sum_phi;
+    return -log(tau) - 0.5 * log(d) + 0.5 * sum_phi_r * sum_phi_r / d;
+}
+// left-aligned heap id: orders prefix-free node sets (leaves; nogs) left-to-right, i.e. in DFS order
+__device__ inline uint32_t dfs_key(uint32_t heap, int depth) { return heap << (MAX_DEPTH - depth); }
+
+}  // namespace bcf

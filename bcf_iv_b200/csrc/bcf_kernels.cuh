@@ -1,0 +1,461 @@
+// bcf_kernels.cuh -- __global__ entry points (GRAPH engine and stand-alone operators).
+#pragma once
+#include "bcf_step.cuh"
+
+namespace bcf {
+
+// ---------------------------------------------------------------------------------------------
+// K0: bin one column.  out = #{c : cuts[c] <= x}  (upper bound), so  x < cuts[c]  <=>  out <= c.
+// Written at the observation's internal (treated-first, padded) position.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int upper_bound_cut(const double* __restrict__ cuts, int ncut, double x)
+{
+    int lo = 0, hi = ncut;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cuts[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// grid.y = column within the chunk
+__global__ void __launch_bounds__(256) k_bin(const double* __restrict__ x, int64_t n, int ncols, int col0,
+                                             const double* __restrict__ cuts, const int32_t* __restrict__ off,
+                                             const int32_t* __restrict__ col_index, const uint8_t* __restrict__ col_is16,
+                                             const int32_t* __restrict__ pos, int64_t n_pad, uint8_t* bins8,
+                                             uint16_t* bins16)
+{
+    const int c = blockIdx.y;
+    if (c >= ncols) return;
+    const int v = col0 + c;
+    const double* xc = x + (int64_t)c * n;
+    const double* cv = cuts + off[v];
+    const int nc = off[v + 1] - off[v];
+    const int ci = col_index[v];
+    const bool w16 = col_is16[v] != 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = upper_bound_cut(cv, nc, xc[i]);
+        const int64_t q = pos ? (int64_t)pos[i] : i;
+        if (w16) bins16[(int64_t)ci * n_pad + q] = (uint16_t)b;
+        else bins8[(int64_t)ci * n_pad + q] = (uint8_t)b;
+    }
+}
+__global__ void k_bin_simple(const double* __restrict__ x, int64_t n, const double* __restrict__ cuts, int ncut,
+                             uint16_t* out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (uint16_t)upper_bound_cut(cuts, ncut, x[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: assign every observation to its leaf slot by walking the flat tree over the binned columns.
+// mode 0: write slots; mode 1: compare with the cached slots and count mismatches.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_assign(Dev d, int tree, int forest, const TreeRec* trees, int mode,
+                                                unsigned long long* mismatches, const int32_t* __restrict__ orig)
+{
+    __shared__ TreeRec tr;
+    load_tree(&tr, &trees[tree]);
+    __syncthreads();
+    const ForestDev& F = d.f[forest];
+    uint8_t* sl = d.slots + (int64_t)tree * d.n_pad;
+    unsigned long long bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        int slot = PAD_SLOT;
+        if (orig[i] >= 0) {
+            int node = 0;
+            while (tr.left[node] >= 0) {
+                const int v = tr.var[node];
+                const int ci = F.col_index[v];
+                const int b = F.col_is16[v] ? (int)F.bins16[(int64_t)ci * d.n_pad + i] : (int)F.bins8[(int64_t)ci * d.n_pad + i];
+                node = (b <= (int)tr.cut[node]) ? tr.left[node] : tr.right[node];
+            }
+            slot = tr.node_slot[node];
+        }
+        if (mode == 0) sl[i] = (uint8_t)slot;
+        else if (sl[i] != (uint8_t)slot) ++bad;
+    }
+    if (mode == 1 && bad) atomicAdd(mismatches, bad);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GRAPH engine: one kernel per tree.  Kernel j decides tree j-1 (from the totals its predecessor reduced),
+// proposes for tree j, then makes ONE pass over the observations that applies tree j-1's update to the
+// residual / leaf cache and accumulates tree j's sufficient statistics.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) k_tree_step(Dev d, int prev, int cur)
+{
+    __shared__ StepShared sm;
+    const Scalars sc = *d.sc;
+    const int par = sc.parity;
+    const bool writer = (blockIdx.x == 0);
+    if (threadIdx.x == 0) { sm.ai.active = 0; sm.ci.active = 0; sm.bad = 0; }
+    __syncthreads();
+    if (prev >= 0) {
+        const ForestDev& F = d.f[prev >= d.f[1].tree0 ? 1 : 0];
+        load_tree(&sm.tr, &d.trees[par][prev]);
+        if (threadIdx.x == 0) sm.prop = d.prop[prev];
+        __syncthreads();
+        decide(sm, d, F, prev, sc, writer);
+        if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.tr);
+        __syncthreads();
+    }
+    if (cur >= 0) {
+        const int fc = cur >= d.f[1].tree0 ? 1 : 0;
+        load_tree(&sm.tr, &d.trees[par][cur]);
+        __syncthreads();
+        propose(sm, d, d.f[fc], cur, sc.sweep);
+        begin_stats(sm, fc);
+        if (writer && threadIdx.x == 0) d.prop[cur] = sm.prop;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    int bad = 0;
+    for (int tile = blockIdx.x * wpb + wib; tile < d.n_tiles; tile += gridDim.x * wpb)
+        step_tile(sm, d, prev, cur, tile, lane, bad);
+    if (bad) sm.bad = ERR_FX_RANGE;
+    __syncthreads();
+    if (cur >= 0) flush_stats(sm, d, cur);
+    if (threadIdx.x == 0 && sm.bad) atomicOr(d.err, sm.bad);
+}
+
+// Sweep epilogue, observation pass (see refit_tile)
+__global__ void __launch_bounds__(THREADS) k_sweep_end(Dev d, int prev)
+{
+    __shared__ StepShared sm;
+    const Scalars sc = *d.sc;
+    const int par = sc.parity;
+    const bool writer = (blockIdx.x == 0);
+    if (threadIdx.x == 0) { sm.ai.active = 0; sm.ci.active = 0; sm.bad = 0; }
+    {
+        long long* tb = &sm.tab[0][0][0];
+        for (int i = threadIdx.x; i < NMOM * 8; i += blockDim.x) tb[i] = 0;
+    }
+    __syncthreads();
+    {
+        const ForestDev& F = d.f[prev >= d.f[1].tree0 ? 1 : 0];
+        load_tree(&sm.tr, &d.trees[par][prev]);
+        if (threadIdx.x == 0) sm.prop = d.prop[prev];
+        __syncthreads();
+        decide(sm, d, F, prev, sc, writer);
+        if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.tr);
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    int bad = 0;
+    for (int tile = blockIdx.x * wpb + wib; tile < d.n_tiles; tile += gridDim.x * wpb)
+        refit_tile(sm, d, prev, d.trees[par ^ 1], tile, lane, bad);
+    if (bad) sm.bad = ERR_FX_RANGE;
+    __syncthreads();
+    const long long* tb = &sm.tab[0][0][0];
+    for (int i = threadIdx.x; i < NMOM * 8; i += blockDim.x) {
+        const int m = i >> 3, g = (i >> 2) & 1, q = i & 3;
+        if (q >= 1 && tb[i] != 0) atomicAdd((unsigned long long*)&d.mom[(g * NMOM + m) * 3 + (q - 1)], (unsigned long long)tb[i]);
+    }
+    if (threadIdx.x == 0 && sm.bad) atomicOr(d.err, sm.bad);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sweep epilogue, scalar part (one CTA): scale draws, leaf-variance mixing, sigma [SURVEY A.4]; advances the
+// sweep counter, flips the tree parity and decides whether this sweep is saved.
+// ---------------------------------------------------------------------------------------------
+// `scs` is the CTA's shared copy of the scalars (identical in every CTA); thread 0 updates it in place.
+__device__ inline void sweep_scalars(const Dev& d, const TreeRec* newtrees, const long long* mom, double* red /* >= 2*blockDim */,
+                                     Scalars* scs, bool write_global)
+{
+    const int t = threadIdx.x;
+    // sum of mu^2 and leaf count over the mu trees, deterministic (fixed partition, fixed order)
+    double ssq = 0.0, cnt = 0.0;
+    for (int j = d.f[0].tree0 + t; j < d.f[0].tree0 + d.f[0].ntree; j += blockDim.x) {
+        const TreeRec& tr = newtrees[j];
+        const int L = __ldcg(&tr.nleaves);
+        for (int l = 0; l < L; ++l) { const double m = __ldcg(&tr.mu[l]); ssq += m * m; }
+        cnt += L;
+    }
+    red[t] = ssq; red[blockDim.x + t] = cnt;
+    __syncthreads();
+    if (t == 0) {
+        Scalars sc = *scs;
+        const Rng rng{d.key0, d.key1};
+        double tssq = 0.0, tcnt = 0.0;
+        for (int i = 0; i < (int)blockDim.x; ++i) { tssq += red[i]; tcnt += red[blockDim.x + i]; }
+        double M[2][NMOM];
+        for (int g = 0; g < 2; ++g)
+            for (int m = 0; m < NMOM; ++m) {
+                const long long* q = mom + (g * NMOM + m) * 3;
+                M[g][m] = limbs_to_double(__ldcg(q), __ldcg(q + 1), __ldcg(q + 2));
+            }
+        const double s2 = sc.sigma * sc.sigma;
+        double ms = sc.mscale, b1 = sc.bscale1, b0 = sc.bscale0;
+        if (d.use_tauscale && d.f[1].ntree > 0) {
+            // ww_g = sum Gm^2 / s2 ; rw_g = sum (y - ms Gc) Gm / s2   (moments: 0 yy, 1 yGc, 2 yGm, 3 GcGc, 4 GcGm, 5 GmGm)
+            double v = 1.0 / (M[1][5] / s2 + 2.0);
+            b1 = v * ((M[1][2] - ms * M[1][4]) / s2) + rng_normal(rng, sc.sweep, TREE_SWEEP_LEVEL, PUR_BSCALE1, 0) * sqrt(v);
+            v = 1.0 / (M[0][5] / s2 + 2.0);
+            b0 = v * ((M[0][2] - ms * M[0][4]) / s2) + rng_normal(rng, sc.sweep, TREE_SWEEP_LEVEL, PUR_BSCALE0, 0) * sqrt(v);
+        }
+        if (d.use_muscale) {
+            const double ww = (M[1][3] + M[0][3]) / s2;
+            const double rw = ((M[1][1] - b1 * M[1][4]) + (M[0][1] - b0 * M[0][4])) / s2;
+            const double v = 1.0 / (ww + 1.0);
+            ms = v * rw + rng_normal(rng, sc.sweep, TREE_SWEEP_LEVEL, PUR_MSCALE, 0) * sqrt(v);
+            const double q = tssq / (sc.tau_con * sc.tau_con);
+            sc.delta_con = rng_gamma(rng, sc.sweep, PUR_DELTA_CON, 0.5 * (1.0 + tcnt)) / (0.5 * (1.0 + q));
+            sc.tau_con = d.con_sd / (sqrt(sc.delta_con) * sqrt((double)d.f[0].ntree));
+        }
+        double rss = 0.0;
+        for (int g = 0; g < 2; ++g) {
+            const double b = g ? b1 : b0;
+            rss += M[g][0] + ms * ms * M[g][3] + b * b * M[g][5] - 2.0 * ms * M[g][1] - 2.0 * b * M[g][2] + 2.0 * ms * b * M[g][4];
+        }
+        const double chi2 = 2.0 * rng_gamma(rng, sc.sweep, PUR_SIGMA, 0.5 * (d.nu + (double)d.n_global));
+        sc.sigma = sqrt((d.nu * d.lambda + rss) / chi2);
+        sc.mscale = ms; sc.bscale1 = b1; sc.bscale0 = b0;
+        if (!(sc.sigma == sc.sigma) || !(ms == ms) || !(b1 == b1) || !(b0 == b0)) atomicOr(d.err, ERR_NAN);
+        // bcf saves iteration i when i >= burn and i % thin == 0
+        sc.save_row = -1;
+        if (sc.run_it >= sc.nburn && (sc.run_it % sc.nthin) == 0 && sc.save_ctr < sc.nsim) {
+            sc.save_row = sc.save_ctr;
+            if (write_global && sc.save_ctr < d.post_cap) {
+                d.sigma_post[sc.save_ctr] = sc.sigma;
+                d.msd_post[sc.save_ctr] = fabs(ms) * d.con_sd;
+                d.bsd_post[sc.save_ctr] = fabs(b1 - b0) * d.mod_sd;
+            }
+            sc.save_ctr++;
+        }
+        sc.run_it++;
+        sc.sweep++;
+        sc.parity ^= 1;
+        *scs = sc;
+        if (write_global) *d.sc = sc;
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(THREADS) k_scalars(Dev d)
+{
+    __shared__ double red[2 * THREADS];
+    __shared__ Scalars scs;
+    if (threadIdx.x == 0) scs = *d.sc;
+    __syncthreads();
+    sweep_scalars(d, d.trees[scs.parity ^ 1], d.mom, red, &scs, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sweep epilogue, finishing pass: rebuild the full residual with the new scales, accumulate the posterior
+// (K5: running sums instead of nsim x n matrices; optional draws), clear the per-sweep totals.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finish_range(const Dev& d, const Scalars& sc, int64_t i0, int64_t stride)
+{
+    const double ms = sc.mscale, b1 = sc.bscale1, b0 = sc.bscale0;
+    const int64_t trt_end = (int64_t)d.trt_tiles * TILE;
+    const int row = sc.save_row;
+    for (int64_t i = i0; i < d.n_pad; i += stride) {
+        const double gc = d.Gc[i], gm = d.Gm[i];
+        const double b = i < trt_end ? b1 : b0;
+        const double mu = ms * gc, yh = mu + b * gm;
+        d.r[i] = d.y[i] - yh;
+        if (row >= 0) {
+            const double tau = (b1 - b0) * gm;
+            d.tau_sum[i] += tau; d.tau_sq[i] += tau * tau; d.mu_sum[i] += mu; d.yhat_sum[i] += yh;
+            if (d.draws_tau) d.draws_tau[(int64_t)row * d.n_pad + i] = tau;
+            if (d.draws_mu) d.draws_mu[(int64_t)row * d.n_pad + i] = mu;
+            if (d.draws_yhat) d.draws_yhat[(int64_t)row * d.n_pad + i] = yh;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_finish(Dev d)
+{
+    const Scalars sc = *d.sc;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    finish_range(d, sc, i0, stride);
+    const int64_t ntot = (int64_t)d.T * KEYS * 8;
+    for (int64_t i = i0; i < ntot; i += stride) d.totals[i] = 0;
+    for (int64_t i = i0; i < 2 * NMOM * 3; i += stride) d.mom[i] = 0;
+}
+
+// initial state [SURVEY A.2]: Gc = ybar (200 root leaves of ybar/200), Gm = 1 (50 root leaves of 1/50)
+__global__ void k_init_state(Dev d, const int32_t* __restrict__ orig, double gc0, double gm0)
+{
+    const Scalars sc = *d.sc;
+    const int64_t trt_end = (int64_t)d.trt_tiles * TILE;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool real = orig[i] >= 0;
+        const double gc = real ? gc0 : 0.0, gm = real ? gm0 : 0.0;
+        d.Gc[i] = gc; d.Gm[i] = gm;
+        d.r[i] = real ? d.y[i] - sc.mscale * gc - (i < trt_end ? sc.bscale1 : sc.bscale0) * gm : 0.0;
+        d.tau_sum[i] = d.tau_sq[i] = d.mu_sum[i] = d.yhat_sum[i] = 0.0;
+        for (int t = 0; t < d.T; ++t) d.slots[(int64_t)t * d.n_pad + i] = real ? 0 : PAD_SLOT;
+    }
+}
+// recompute Gc / Gm / r from the current trees (after set_tree)
+__global__ void k_refit_all(Dev d, const TreeRec* trees)
+{
+    const Scalars sc = *d.sc;
+    const int64_t trt_end = (int64_t)d.trt_tiles * TILE;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        double G[2] = {0.0, 0.0};
+        for (int f = 0; f < 2; ++f)
+            for (int j = d.f[f].tree0; j < d.f[f].tree0 + d.f[f].ntree; ++j) {
+                const int s = d.slots[(int64_t)j * d.n_pad + i];
+                if (s != PAD_SLOT) G[f] += trees[j].mu[s];
+            }
+        d.Gc[i] = G[0]; d.Gm[i] = G[1];
+        d.r[i] = d.y[i] - sc.mscale * G[0] - (i < trt_end ? sc.bscale1 : sc.bscale0) * G[1];
+    }
+}
+
+// gather an internal-order vector back to the caller's row order; which: 0 copy, 1 mean (x/ns), 2 variance
+__global__ void k_unpermute(const double* __restrict__ a, const double* __restrict__ b, const int32_t* __restrict__ pos,
+                            int64_t n, double ns, int which, double scale_trt, double scale_ctl, int64_t trt_end,
+                            double* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = pos[i];
+        double v;
+        if (which == 0) v = a[q] * (q < trt_end ? scale_trt : scale_ctl);
+        else if (which == 1) v = a[q] / ns;
+        else { const double m = a[q] / ns; v = ns > 1.0 ? fmax(0.0, (b[q] - ns * m * m) / (ns - 1.0)) : 0.0; }
+        out[i] = v;
+    }
+}
+__global__ void k_permute_in(const double* __restrict__ in, const int32_t* __restrict__ pos, int64_t n, double* out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[pos[i]] = in[i];
+}
+__global__ void k_leaf_heap(Dev d, int tree, const TreeRec* trees, const int32_t* __restrict__ pos, int64_t n,
+                            uint32_t* out)
+{
+    const TreeRec& tr = trees[tree];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int s = d.slots[(int64_t)tree * d.n_pad + pos[i]];
+        out[i] = s == PAD_SLOT ? 0u : tr.heap[tr.slot_node[s]];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 stand-alone: per-leaf (count, sum r) by group for a caller-supplied residual, optional birth split.
+// Same accumulation code as the sampler's fused pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) k_op_stats(Dev d, int tree, int forest, const double* __restrict__ r,
+                                                      int K, int birth, int sx, int var, int cut, long long* out)
+{
+    __shared__ long long tab[KEYS][2][4];
+    for (int i = threadIdx.x; i < K * 8; i += blockDim.x) (&tab[0][0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    int bad = 0;
+    for (int tile = blockIdx.x * wpb + wib; tile < d.n_tiles; tile += gridDim.x * wpb) {
+        const int64_t base = (int64_t)tile * TILE + lane * 8;
+        const int g = tile < d.trt_tiles ? 1 : 0;
+        double rv[8];
+        int key[8];
+        ld8_f64(r + base, rv);
+        ld8_u8(d.slots + (int64_t)tree * d.n_pad + base, key);
+        if (birth) {
+            int bc[8];
+            ld8_bins(d.f[forest], var, d.n_pad, base, bc);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) if (key[o] == sx && bc[o] > cut) key[o] = K - 1;
+        }
+        accum_tile(tab, key, rv, g, K, lane, bad);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * 8; i += blockDim.x) {
+        const long long v = (&tab[0][0][0])[i];
+        if (v != 0) atomicAdd((unsigned long long*)&out[i], (unsigned long long)v);
+    }
+    if (bad) atomicOr(d.err, ERR_FX_RANGE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2': all-candidate histogram.  For every variable v of a forest and every bin b, per leaf label:
+// (count, sum r) of the observations with that (leaf, bin) -- the sufficient statistics of EVERY candidate
+// (variable, cutpoint) split at once (prefix sums over b give the left child of cut c).
+// grid.y = variable.  uint8 columns: shared-memory histogram per CTA (leaf x bin x 4 words), flushed with
+// integer REDs.  uint16 columns (10 000 cutpoints): global integer atomics directly.
+// Loads: 128-bit for the uint8 bins / labels (16 observations per lane), 128-bit pairs for r.
+// ---------------------------------------------------------------------------------------------
+constexpr int HIST_SMEM_ENTRIES = 1024;   // (leaf, bin) cells of 4 x int64 = 32 KB
+__global__ void __launch_bounds__(256) k_hist(Dev d, int forest, const uint8_t* __restrict__ label,
+                                              const double* __restrict__ r, int nleaf, const int32_t* __restrict__ off,
+                                              long long* out /* [leaf][off[p]+p][4] */)
+{
+    __shared__ long long h[HIST_SMEM_ENTRIES][4];
+    const ForestDev& F = d.f[forest];
+    const int v = blockIdx.y;
+    const int nb = F.ncut[v] + 1;
+    const int64_t nbt = (int64_t)off[F.p] + F.p;
+    const int64_t vbase = (int64_t)off[v] + v;
+    const bool w16 = F.col_is16[v] != 0;
+    const bool use_smem = !w16 && nleaf * nb <= HIST_SMEM_ENTRIES;
+    if (use_smem) for (int i = threadIdx.x; i < nleaf * nb * 4; i += blockDim.x) (&h[0][0])[i] = 0;
+    __syncthreads();
+    int bad = 0;
+    const int ci = F.col_index[v];
+    const int64_t nchunk = d.n_pad / 16;
+    for (int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunk; ch += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t base = ch * 16;
+        int lab[16], bin[16];
+        {
+            const uint4 q = *reinterpret_cast<const uint4*>(label + base);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int o = 0; o < 16; ++o) lab[o] = (w[o >> 2] >> (8 * (o & 3))) & 0xFF;
+        }
+        if (w16) {
+            int t8[8];
+            ld8_u16(F.bins16 + (int64_t)ci * d.n_pad + base, t8);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) bin[o] = t8[o];
+            ld8_u16(F.bins16 + (int64_t)ci * d.n_pad + base + 8, t8);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) bin[8 + o] = t8[o];
+        } else {
+            const uint4 q = *reinterpret_cast<const uint4*>(F.bins8 + (int64_t)ci * d.n_pad + base);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int o = 0; o < 16; ++o) bin[o] = (w[o >> 2] >> (8 * (o & 3))) & 0xFF;
+        }
+#pragma unroll
+        for (int o = 0; o < 16; o += 2) {
+            const double2 rr = *reinterpret_cast<const double2*>(r + base + o);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int lb = lab[o + e];
+                if (lb >= nleaf) continue;
+                const long long fx = to_fixed(e ? rr.y : rr.x, bad);
+                const long long l0 = fx & 0x1FFFFF, l1 = (fx >> LIMB_BITS) & 0x1FFFFF, l2 = fx >> (2 * LIMB_BITS);
+                long long* cell = use_smem ? h[lb * nb + bin[o + e]] : out + ((int64_t)lb * nbt + vbase + bin[o + e]) * 4;
+                atomicAdd((unsigned long long*)&cell[0], 1ull);
+                atomicAdd((unsigned long long*)&cell[1], (unsigned long long)l0);
+                atomicAdd((unsigned long long*)&cell[2], (unsigned long long)l1);
+                atomicAdd((unsigned long long*)&cell[3], (unsigned long long)l2);
+            }
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nleaf * nb * 4; i += blockDim.x) {
+            const long long val = (&h[0][0])[i];
+            if (val == 0) continue;
+            const int cellid = i >> 2, q = i & 3, lb = cellid / nb, b = cellid % nb;
+            atomicAdd((unsigned long long*)&out[((int64_t)lb * nbt + vbase + b) * 4 + q], (unsigned long long)val);
+        }
+    }
+    if (bad) atomicOr(d.err, ERR_FX_RANGE);
+}
+
+__global__ void k_lil(const double* a, const double* b, const double* tau, int m, double* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = lil(a[i], b[i], tau[i]);
+}
+__global__ void k_rng_probe(uint32_t k0, uint32_t k1, uint32_t sweep, uint32_t tree, uint32_t purpose, uint32_t idx,
+                            double* out)
+{
+    const Rng g{k0, k1};
+    rng_u2(g, sweep, tree, purpose, idx, out[0], out[1]);
+    out[2] = rng_normal(g, sweep, tree, purpose, idx);
+}
+
+}  // namespace bcf

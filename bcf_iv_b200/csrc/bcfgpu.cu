@@ -1,0 +1,1052 @@
+// bcfgpu.cu -- host side of libbcfgpu.so: the C-ABI declared in include/bcfgpu.h.
+// No CPU fallback: every compute entry point needs a CUDA device and fails with BCFGPU_ERR_CUDA otherwise.
+#include "../../include/bcfgpu.h"
+#include "bcf_kernels.cuh"
+#include "bcf_persistent.cuh"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bcf;
+
+static_assert(MAXL == BCFGPU_MAX_LEAVES, "header / device constant mismatch");
+static_assert(MAX_DEPTH == BCFGPU_MAX_DEPTH, "header / device constant mismatch");
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? BCFGPU_ERR_OOM : BCFGPU_ERR_CUDA,            \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                           \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (torch ships libnccl.so.2; only the sharded mode needs it)
+// ------------------------------------------------------------------------------------------------
+struct NcclId { char b[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+    if (g_nccl.lib) return BCFGPU_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return fail(BCFGPU_ERR_NCCL, "cannot dlopen libnccl.so.2 (put torch's nvidia/nccl/lib on LD_LIBRARY_PATH or import torch first)");
+    g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(BCFGPU_ERR_NCCL, "libnccl is missing expected symbols");
+    g_nccl.lib = lib;
+    return BCFGPU_OK;
+}
+constexpr int NCCL_INT64 = 4, NCCL_SUM = 0;
+#define NK(call)                                                                                       \
+    do {                                                                                               \
+        int r_ = (call);                                                                               \
+        if (r_ != 0) return fail(BCFGPU_ERR_NCCL, std::string(#call) + ": " +                          \
+                                 (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"));   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct ForestHost {
+    int p = 0, p8 = 0, p16 = 0;
+    std::vector<int32_t> off, ncut, col_index;
+    std::vector<uint8_t> is16;
+    std::vector<double> cuts;
+    double* d_cuts = nullptr; int32_t* d_off = nullptr; int32_t* d_ncut = nullptr; int32_t* d_col_index = nullptr;
+    uint8_t* d_is16 = nullptr; uint8_t* d_bins8 = nullptr; uint16_t* d_bins16 = nullptr;
+};
+
+struct bcfgpu_handle {
+    bcfgpu_config cfg;
+    int device = 0, num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int rank = 0, nranks = 1;
+    void* comm = nullptr;
+    int64_t n = 0, n_pad = 0, n_global = 0;
+    int ntrt = 0, T = 0;
+    bool has_data = false;
+    std::vector<void*> allocs;        // data-lifetime allocations
+    std::vector<void*> run_allocs;    // run-lifetime allocations (posterior buffers)
+    ForestHost fh[2];
+    std::vector<int32_t> pos;
+    int32_t *d_pos = nullptr, *d_orig = nullptr;
+    double* d_tmp = nullptr;          // n_pad doubles scratch
+    double* d_tmp2 = nullptr;
+    Dev dev;
+    Dev graph_dev;                    // Dev the graph was captured with
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    int grid_obs = 0, grid_fin = 0;
+    int engine = BCFGPU_ENGINE_GRAPH;
+    int coop_grid = 0;
+    unsigned int* d_bar = nullptr;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    int32_t nsaved = 0, post_cap = 0;
+    int keep = 0;
+};
+
+template <typename Tp>
+static int dmalloc(bcfgpu_handle* h, Tp** p, size_t count, bool run_scope = false)
+{
+    void* q = nullptr;
+    const size_t bytes = std::max<size_t>(count * sizeof(Tp), 16);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return fail(BCFGPU_ERR_OOM, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes: " + cudaGetErrorString(e));
+    }
+    (run_scope ? h->run_allocs : h->allocs).push_back(q);
+    *p = (Tp*)q;
+    return BCFGPU_OK;
+}
+#define DM(...) do { int r_ = dmalloc(__VA_ARGS__); if (r_) return r_; } while (0)
+
+static void free_list(std::vector<void*>& v) { for (void* p : v) cudaFree(p); v.clear(); }
+static void drop_graph(bcfgpu_handle* h)
+{
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+}
+
+static int use_device(bcfgpu_handle* h)
+{
+    CK(cudaSetDevice(h->device));
+    return BCFGPU_OK;
+}
+#define USE(h) do { if (!(h)) return fail(BCFGPU_ERR_BAD_ARG, "null handle"); int r_ = use_device(h); if (r_) return r_; } while (0)
+#define NEED_DATA(h) do { if (!(h)->has_data) return fail(BCFGPU_ERR_STATE, "set_data has not been called"); } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int bcfgpu_abi_version(void) { return BCFGPU_ABI_VERSION; }
+
+int bcfgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* bcfgpu_last_error(void) { return g_err.c_str(); }
+
+void bcfgpu_config_init(bcfgpu_config* c)
+{
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->struct_size = (int32_t)sizeof(bcfgpu_config);
+    c->ntree_con = 200; c->ntree_mod = 50;
+    c->alpha_con = 0.95; c->beta_con = 2.0; c->alpha_mod = 0.25; c->beta_mod = 3.0;
+    c->con_sd = 2.0; c->mod_sd = 1.0 / 0.674;
+    c->nu = 3.0; c->lambda = 1.0; c->sigma_init = 1.0;
+    c->use_muscale = 1; c->use_tauscale = 1;
+    c->min_leaf = 5; c->max_leaves = 0;
+    c->seed = 42; c->chain = 0; c->device = -1; c->engine = BCFGPU_ENGINE_AUTO; c->keep_draws = 0;
+}
+
+int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
+{
+    if (!cfg || !out) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(bcfgpu_config)) return fail(BCFGPU_ERR_BAD_ARG, "bcfgpu_config.struct_size mismatch (ABI)");
+    if (cfg->ntree_con < 1 || cfg->ntree_mod < 0) return fail(BCFGPU_ERR_BAD_ARG, "ntree_con must be >= 1 and ntree_mod >= 0");
+    if (cfg->ntree_con + cfg->ntree_mod > 65535) return fail(BCFGPU_ERR_BAD_ARG, "too many trees");
+    if (!(cfg->alpha_con > 0 && cfg->alpha_con < 1 && cfg->alpha_mod > 0 && cfg->alpha_mod < 1))
+        return fail(BCFGPU_ERR_BAD_ARG, "base_control / base_moderate must be in (0,1)");
+    if (!(cfg->con_sd > 0 && cfg->mod_sd > 0 && cfg->nu > 0 && cfg->lambda > 0 && cfg->sigma_init > 0))
+        return fail(BCFGPU_ERR_BAD_ARG, "con_sd, mod_sd, nu, lambda, sigma_init must be positive");
+    if (cfg->max_leaves < 0 || cfg->max_leaves > MAXL || cfg->max_leaves == 1) return fail(BCFGPU_ERR_BAD_ARG, "max_leaves must be 0 or in [2,128]");
+    if (cfg->min_leaf < 1) return fail(BCFGPU_ERR_BAD_ARG, "min_leaf must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BCFGPU_ERR_CUDA, "no CUDA device available (libbcfgpu has no CPU fallback)");
+    }
+    int dev = cfg->device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(BCFGPU_ERR_BAD_ARG, "device ordinal out of range");
+    bcfgpu_handle* h = new bcfgpu_handle();
+    h->cfg = *cfg;
+    if (h->cfg.max_leaves == 0) h->cfg.max_leaves = MAXL;
+    h->device = dev;
+    h->T = cfg->ntree_con + cfg->ntree_mod;
+    memset(&h->dev, 0, sizeof(Dev));
+    memset(&h->graph_dev, 0, sizeof(Dev));
+    cudaError_t e2 = cudaSetDevice(dev);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev0);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev1);
+    if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e2 != cudaSuccess) { delete h; return fail(BCFGPU_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e2)); }
+    h->engine = cfg->engine == BCFGPU_ENGINE_AUTO ? BCFGPU_ENGINE_PERSISTENT : cfg->engine;
+    *out = h;
+    return BCFGPU_OK;
+}
+
+int bcfgpu_destroy(bcfgpu_handle* h)
+{
+    if (!h) return BCFGPU_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_graph(h);
+    free_list(h->allocs);
+    free_list(h->run_allocs);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return BCFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharding
+// ------------------------------------------------------------------------------------------------
+int bcfgpu_nccl_unique_id(char id_out[128])
+{
+    if (!id_out) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
+    int r = nccl_load();
+    if (r) return r;
+    NcclId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, id.b, 128);
+    return BCFGPU_OK;
+}
+
+int bcfgpu_set_shard(bcfgpu_handle* h, int rank, int nranks, const char nccl_unique_id[128])
+{
+    USE(h);
+    if (h->has_data) return fail(BCFGPU_ERR_STATE, "set_shard must be called before set_data");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(BCFGPU_ERR_BAD_ARG, "bad rank / nranks");
+    h->rank = rank; h->nranks = nranks;
+    if (nranks == 1) return BCFGPU_OK;
+    if (!nccl_unique_id) return fail(BCFGPU_ERR_BAD_ARG, "null nccl_unique_id");
+    int r = nccl_load();
+    if (r) return r;
+    NcclId id;
+    memcpy(id.b, nccl_unique_id, 128);
+    NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    return BCFGPU_OK;
+}
+
+}  // extern "C"
+
+// all-reduce (sum) of int64 words across shards; no-op on one rank
+static int shard_allreduce(bcfgpu_handle* h, long long* buf, size_t count)
+{
+    if (h->nranks <= 1) return BCFGPU_OK;
+    NK(g_nccl.AllReduce(buf, buf, count, NCCL_INT64, NCCL_SUM, h->comm, h->stream));
+    return BCFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// data
+// ------------------------------------------------------------------------------------------------
+static int setup_forest(bcfgpu_handle* h, int f, int p, const double* cuts, const int32_t* off)
+{
+    ForestHost& F = h->fh[f];
+    F = ForestHost();
+    F.p = p;
+    if (p == 0) return BCFGPU_OK;
+    if (off[0] != 0) return fail(BCFGPU_ERR_BAD_ARG, "cut_off[0] must be 0");
+    F.off.assign(off, off + p + 1);
+    F.ncut.resize(p); F.col_index.resize(p); F.is16.resize(p);
+    for (int v = 0; v < p; ++v) {
+        const int nc = off[v + 1] - off[v];
+        if (nc < 1) return fail(BCFGPU_ERR_BAD_ARG, "every covariate needs at least one cutpoint");
+        if (nc > 65535) return fail(BCFGPU_ERR_BAD_ARG, "at most 65535 cutpoints per covariate");
+        for (int c = 1; c < nc; ++c)
+            if (!(cuts[off[v] + c] >= cuts[off[v] + c - 1])) return fail(BCFGPU_ERR_BAD_ARG, "cutpoints must be sorted and finite");
+        F.ncut[v] = nc;
+        F.is16[v] = nc > 255;
+        F.col_index[v] = F.is16[v] ? F.p16++ : F.p8++;
+    }
+    F.cuts.assign(cuts, cuts + off[p]);
+    DM(h, &F.d_cuts, F.cuts.size());
+    DM(h, &F.d_off, F.off.size());
+    DM(h, &F.d_ncut, (size_t)p);
+    DM(h, &F.d_col_index, (size_t)p);
+    DM(h, &F.d_is16, (size_t)p);
+    DM(h, &F.d_bins8, (size_t)std::max(F.p8, 1) * h->n_pad);
+    DM(h, &F.d_bins16, (size_t)std::max(F.p16, 1) * h->n_pad);
+    CK(cudaMemcpyAsync(F.d_cuts, F.cuts.data(), F.cuts.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(F.d_off, F.off.data(), F.off.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(F.d_ncut, F.ncut.data(), (size_t)p * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(F.d_col_index, F.col_index.data(), (size_t)p * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(F.d_is16, F.is16.data(), (size_t)p, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(F.d_bins8, 0, (size_t)std::max(F.p8, 1) * h->n_pad, h->stream));
+    CK(cudaMemsetAsync(F.d_bins16, 0, (size_t)std::max(F.p16, 1) * h->n_pad * 2, h->stream));
+    return BCFGPU_OK;
+}
+
+// K0 over a column-major host matrix, chunked by columns so the fp64 staging buffer stays bounded
+static int bin_forest(bcfgpu_handle* h, int f, const double* x)
+{
+    ForestHost& F = h->fh[f];
+    if (F.p == 0) return BCFGPU_OK;
+    const int64_t n = h->n;
+    const size_t max_stage = (size_t)1 << 28;   // 256 Mi doubles = 2 GiB
+    int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(F.p, (int64_t)(max_stage / (size_t)n)));
+    double* stage = nullptr;
+    CK(cudaMalloc((void**)&stage, (size_t)chunk * n * 8));
+    int rc = BCFGPU_OK;
+    for (int c0 = 0; c0 < F.p && rc == BCFGPU_OK; c0 += chunk) {
+        const int nc = std::min(chunk, F.p - c0);
+        cudaError_t e = cudaMemcpyAsync(stage, x + (size_t)c0 * n, (size_t)nc * n * 8, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { rc = fail(BCFGPU_ERR_CUDA, std::string("H2D of X: ") + cudaGetErrorString(e)); break; }
+        dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 4096), (unsigned)nc);
+        k_bin<<<grid, 256, 0, h->stream>>>(stage, n, nc, c0, F.d_cuts, F.d_off, F.d_col_index, F.d_is16, h->d_pos,
+                                            h->n_pad, F.d_bins8, F.d_bins16);
+        h->launches++;
+        e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(BCFGPU_ERR_CUDA, std::string("k_bin: ") + cudaGetErrorString(e));
+    }
+    cudaFree(stage);
+    return rc;
+}
+
+static void fill_forest_dev(const bcfgpu_handle* h, int f, ForestDev& D)
+{
+    const ForestHost& F = h->fh[f];
+    D.p = F.p;
+    D.ntree = f == 0 ? h->cfg.ntree_con : h->cfg.ntree_mod;
+    D.tree0 = f == 0 ? 0 : h->cfg.ntree_con;
+    D.is_con = f == 0;
+    D.bins8 = F.d_bins8; D.bins16 = F.d_bins16; D.col_index = F.d_col_index; D.col_is16 = F.d_is16; D.ncut = F.d_ncut;
+    const double a = f == 0 ? h->cfg.alpha_con : h->cfg.alpha_mod, b = f == 0 ? h->cfg.beta_con : h->cfg.beta_mod;
+    for (int dpt = 0; dpt < 32; ++dpt) D.pg[dpt] = a / std::pow(1.0 + (double)dpt, b);
+}
+
+static void root_tree(TreeRec& tr, double mu)
+{
+    memset(&tr, 0, sizeof(tr));
+    tr.nnodes = 1; tr.nleaves = 1;
+    for (int i = 0; i < MAXN; ++i) { tr.parent[i] = tr.left[i] = tr.right[i] = -1; tr.var[i] = tr.cut[i] = 0xFFFF; }
+    tr.node_slot[0] = 0; tr.depth[0] = 0; tr.heap[0] = 1; tr.slot_node[0] = 0; tr.mu[0] = mu;
+}
+
+static int build_graph(bcfgpu_handle* h);
+
+extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32_t p_mod, const double* y,
+                               const int32_t* z, const double* xcon, const double* xmod, const double* cuts_con,
+                               const int32_t* cut_off_con, const double* cuts_mod, const int32_t* cut_off_mod)
+{
+    USE(h);
+    const bcfgpu_config& c = h->cfg;
+    if (n < 1 || n > 2000000000ll) return fail(BCFGPU_ERR_BAD_ARG, "n must be in [1, 2e9]");
+    if (!y || !z || !xcon || !cuts_con || !cut_off_con) return fail(BCFGPU_ERR_BAD_ARG, "null data pointer");
+    if (p_con < 1 || p_con > 65535) return fail(BCFGPU_ERR_BAD_ARG, "p_con must be in [1, 65535]");
+    if (c.ntree_mod > 0 && (p_mod < 1 || p_mod > 65535 || !xmod || !cuts_mod || !cut_off_mod))
+        return fail(BCFGPU_ERR_BAD_ARG, "moderate forest needs x_moderate and its cutpoints");
+    if (c.ntree_mod == 0) p_mod = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (z[i] != 0 && z[i] != 1) return fail(BCFGPU_ERR_BAD_ARG, "z must be 0/1");
+        if (!std::isfinite(y[i])) return fail(BCFGPU_ERR_BAD_ARG, "y must be finite");
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    drop_graph(h);
+    free_list(h->allocs);
+    free_list(h->run_allocs);
+    h->has_data = false;
+    h->n = n;
+    int64_t ntrt = 0;
+    for (int64_t i = 0; i < n; ++i) ntrt += z[i];
+    const int64_t trt_pad = (ntrt + TILE - 1) / TILE * TILE;
+    const int64_t ctl_pad = (n - ntrt + TILE - 1) / TILE * TILE;
+    h->ntrt = (int)ntrt;
+    h->n_pad = trt_pad + ctl_pad;
+    const int64_t n_pad = h->n_pad;
+    // bcf: perm = order(z, decreasing = TRUE): treated rows first, ties in original order
+    h->pos.resize(n);
+    std::vector<int32_t> orig(n_pad, -1);
+    {
+        int64_t kt = 0, kc = trt_pad;
+        for (int64_t i = 0; i < n; ++i) { const int64_t q = z[i] ? kt++ : kc++; h->pos[i] = (int32_t)q; orig[q] = (int32_t)i; }
+    }
+    Dev& d = h->dev;
+    memset(&d, 0, sizeof(Dev));
+    d.n_pad = n_pad; d.n_tiles = (int32_t)(n_pad / TILE); d.trt_tiles = (int32_t)(trt_pad / TILE);
+    d.T = h->T; d.max_leaves = c.max_leaves; d.min_leaf = c.min_leaf;
+    d.use_muscale = c.use_muscale; d.use_tauscale = c.use_tauscale;
+    {
+        const uint64_t s = c.seed + (uint64_t)c.chain * 0x9E3779B97F4A7C15ull;
+        d.key0 = (uint32_t)s; d.key1 = (uint32_t)(s >> 32);
+    }
+    d.nu = c.nu; d.lambda = c.lambda; d.con_sd = c.con_sd; d.mod_sd = c.mod_sd;
+
+    DM(h, &h->d_pos, (size_t)n);
+    DM(h, &h->d_orig, (size_t)n_pad);
+    CK(cudaMemcpyAsync(h->d_pos, h->pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_orig, orig.data(), (size_t)n_pad * 4, cudaMemcpyHostToDevice, h->stream));
+    double* dy = nullptr;
+    DM(h, &dy, (size_t)n_pad);
+    DM(h, &d.r, (size_t)n_pad); DM(h, &d.Gc, (size_t)n_pad); DM(h, &d.Gm, (size_t)n_pad);
+    DM(h, &d.tau_sum, (size_t)n_pad); DM(h, &d.tau_sq, (size_t)n_pad); DM(h, &d.mu_sum, (size_t)n_pad); DM(h, &d.yhat_sum, (size_t)n_pad);
+    DM(h, &h->d_tmp, (size_t)n_pad); DM(h, &h->d_tmp2, (size_t)n_pad);
+    DM(h, &d.slots, (size_t)h->T * n_pad);
+    DM(h, &d.trees[0], (size_t)h->T); DM(h, &d.trees[1], (size_t)h->T);
+    DM(h, &d.prop, (size_t)h->T);
+    DM(h, &d.totals, (size_t)h->T * KEYS * 8);
+    DM(h, &d.mom, (size_t)2 * 2 * NMOM * 3);
+    DM(h, &d.sc, 1);
+    DM(h, &d.err, 4);
+    DM(h, &d.trace, (size_t)h->T * 5);
+    DM(h, &d.trace_logr, (size_t)h->T);
+    DM(h, &d.counters, 4);
+    DM(h, &h->d_bar, 64);
+    d.y = dy;
+    CK(cudaMemsetAsync(d.totals, 0, (size_t)h->T * KEYS * 8 * 8, h->stream));
+    CK(cudaMemsetAsync(d.mom, 0, 2 * 2 * NMOM * 3 * 8, h->stream));
+    CK(cudaMemsetAsync(d.err, 0, 16, h->stream));
+    CK(cudaMemsetAsync(d.trace, 0, (size_t)h->T * 5 * 4, h->stream));
+    CK(cudaMemsetAsync(d.trace_logr, 0, (size_t)h->T * 8, h->stream));
+    CK(cudaMemsetAsync(d.counters, 0, 32, h->stream));
+    CK(cudaMemsetAsync(d.prop, 0, (size_t)h->T * sizeof(Proposal), h->stream));
+    CK(cudaMemsetAsync(h->d_bar, 0, 64 * 4, h->stream));
+    {
+        std::vector<double> yi((size_t)n_pad, 0.0);
+        for (int64_t i = 0; i < n; ++i) yi[h->pos[i]] = y[i];
+        CK(cudaMemcpyAsync(dy, yi.data(), (size_t)n_pad * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    int rc;
+    if ((rc = setup_forest(h, 0, p_con, cuts_con, cut_off_con))) return rc;
+    if ((rc = setup_forest(h, 1, p_mod, cuts_mod, cut_off_mod))) return rc;
+    if ((rc = bin_forest(h, 0, xcon))) return rc;
+    if ((rc = bin_forest(h, 1, xmod))) return rc;
+    fill_forest_dev(h, 0, d.f[0]);
+    fill_forest_dev(h, 1, d.f[1]);
+
+    // ybar from an order-independent fixed-point sum, so any sharding starts from identical bits
+    long long ysum[4] = {0, 0, 0, 0};   // count, limb0, limb1, limb2
+    for (int64_t i = 0; i < n; ++i) {
+        if (!(std::fabs(y[i]) < 262144.0)) return fail(BCFGPU_ERR_BAD_ARG, "|y| too large: pass the standardised outcome");
+        const long long v = std::llrint(y[i] * 17592186044416.0);
+        ysum[0] += 1; ysum[1] += v & 0x1FFFFF; ysum[2] += (v >> LIMB_BITS) & 0x1FFFFF; ysum[3] += v >> (2 * LIMB_BITS);
+    }
+    if (h->nranks > 1) {
+        long long* dq = (long long*)h->d_tmp;
+        CK(cudaMemcpyAsync(dq, ysum, 32, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = shard_allreduce(h, dq, 4))) return rc;
+        CK(cudaMemcpyAsync(ysum, dq, 32, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->n_global = ysum[0];
+    d.n_global = h->n_global;
+    const double ybar = limbs_to_double(ysum[1], ysum[2], ysum[3]) / (double)h->n_global;
+
+    // trees, scalars [SURVEY A.2]
+    {
+        std::vector<TreeRec> trees((size_t)h->T);
+        const double trt_init = 1.0;
+        for (int j = 0; j < h->T; ++j)
+            root_tree(trees[j], j < c.ntree_con ? ybar / c.ntree_con : trt_init / c.ntree_mod);
+        CK(cudaMemcpyAsync(d.trees[0], trees.data(), sizeof(TreeRec) * h->T, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.trees[1], trees.data(), sizeof(TreeRec) * h->T, cudaMemcpyHostToDevice, h->stream));
+        Scalars sc;
+        memset(&sc, 0, sizeof(sc));
+        sc.sigma = c.sigma_init; sc.mscale = 1.0; sc.bscale1 = 0.5; sc.bscale0 = -0.5;
+        sc.delta_con = sc.delta_mod = 1.0;
+        sc.tau_con = c.con_sd / std::sqrt((double)c.ntree_con);
+        sc.tau_mod = c.ntree_mod > 0 ? c.mod_sd / std::sqrt((double)c.ntree_mod) : 1.0;
+        sc.sweep = 0; sc.parity = 0; sc.run_it = 0; sc.nburn = 0; sc.nthin = 1; sc.nsim = 0; sc.save_ctr = 0; sc.save_row = -1;
+        CK(cudaMemcpyAsync(d.sc, &sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->grid_obs = (int)std::max<int64_t>(1, std::min<int64_t>((d.n_tiles + (THREADS / 32) - 1) / (THREADS / 32), (int64_t)h->num_sms * 4));
+    h->grid_fin = (int)std::max<int64_t>(1, std::min<int64_t>((n_pad + 255) / 256, (int64_t)h->num_sms * 8));
+    k_init_state<<<h->grid_fin, 256, 0, h->stream>>>(d, h->d_orig, ybar, c.ntree_mod > 0 ? 1.0 : 0.0);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_data = true;
+    h->nsaved = 0;
+    return BCFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep launch: GRAPH engine
+// ------------------------------------------------------------------------------------------------
+static int enqueue_sweep(bcfgpu_handle* h)
+{
+    const Dev& d = h->dev;
+    int rc;
+    for (int j = 0; j < h->T; ++j) {
+        k_tree_step<<<h->grid_obs, THREADS, 0, h->stream>>>(d, j - 1, j);
+        if ((rc = shard_allreduce(h, d.totals + (size_t)j * KEYS * 8, KEYS * 8))) return rc;
+    }
+    k_sweep_end<<<h->grid_obs, THREADS, 0, h->stream>>>(d, h->T - 1);
+    if ((rc = shard_allreduce(h, d.mom, 2 * NMOM * 3))) return rc;
+    k_scalars<<<1, THREADS, 0, h->stream>>>(d);
+    k_finish<<<h->grid_fin, 256, 0, h->stream>>>(d);
+    CK(cudaGetLastError());
+    return BCFGPU_OK;
+}
+
+static int build_graph(bcfgpu_handle* h)
+{
+    if (h->gexec && memcmp(&h->graph_dev, &h->dev, sizeof(Dev)) == 0) return BCFGPU_OK;
+    drop_graph(h);
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_sweep(h);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
+    if (rc) { if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; } return rc; }
+    if (e != cudaSuccess) return fail(BCFGPU_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(&h->gexec, h->graph, 0));
+    h->graph_dev = h->dev;
+    return BCFGPU_OK;
+}
+
+static int run_persistent(bcfgpu_handle* h, int total);
+
+static int check_device_err(bcfgpu_handle* h)
+{
+    struct { int32_t err; } sc;
+    CK(cudaMemcpy(&sc.err, h->dev.err, 4, cudaMemcpyDeviceToHost));
+    if (sc.err) cudaMemset(h->dev.err, 0, 4);
+    if (sc.err & ERR_BARRIER_TIMEOUT) return fail(BCFGPU_ERR_CUDA, "grid barrier timed out inside the persistent sweep kernel");
+    if (sc.err & ERR_NAN) return fail(BCFGPU_ERR_NUMERIC, "NaN in a leaf / scale / sigma draw");
+    if (sc.err & ERR_FX_RANGE) return fail(BCFGPU_ERR_NUMERIC, "residual outside the fixed-point range (|r| >= 2^18) or NaN");
+    return BCFGPU_OK;
+}
+
+extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin)
+{
+    USE(h); NEED_DATA(h);
+    if (nburn < 0 || nsim < 0 || nthin < 1) return fail(BCFGPU_ERR_BAD_ARG, "need nburn >= 0, nsim >= 0, nthin >= 1");
+    const int64_t total64 = (int64_t)nburn + (int64_t)nsim * nthin;
+    if (total64 > 2000000000ll) return fail(BCFGPU_ERR_BAD_ARG, "too many sweeps");
+    const int total = (int)total64;
+    Dev& d = h->dev;
+    CK(cudaStreamSynchronize(h->stream));
+    // posterior buffers of this run
+    free_list(h->run_allocs);
+    d.draws_tau = d.draws_mu = d.draws_yhat = nullptr;
+    const int cap = std::max(nsim, 1);
+    DM(h, &d.sigma_post, (size_t)cap, true); DM(h, &d.msd_post, (size_t)cap, true); DM(h, &d.bsd_post, (size_t)cap, true);
+    d.post_cap = cap;
+    h->keep = h->cfg.keep_draws;
+    if (nsim > 0) {
+        if (h->keep & 1) DM(h, &d.draws_tau, (size_t)nsim * d.n_pad, true);
+        if (h->keep & 2) DM(h, &d.draws_mu, (size_t)nsim * d.n_pad, true);
+        if (h->keep & 4) DM(h, &d.draws_yhat, (size_t)nsim * d.n_pad, true);
+    }
+    CK(cudaMemsetAsync(d.tau_sum, 0, (size_t)d.n_pad * 8, h->stream));
+    CK(cudaMemsetAsync(d.tau_sq, 0, (size_t)d.n_pad * 8, h->stream));
+    CK(cudaMemsetAsync(d.mu_sum, 0, (size_t)d.n_pad * 8, h->stream));
+    CK(cudaMemsetAsync(d.yhat_sum, 0, (size_t)d.n_pad * 8, h->stream));
+    Scalars sc;
+    CK(cudaMemcpyAsync(&sc, d.sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    sc.run_it = 0; sc.nburn = nburn; sc.nthin = nthin; sc.nsim = nsim; sc.save_ctr = 0; sc.save_row = -1;
+    CK(cudaMemcpyAsync(d.sc, &sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
+    h->nsaved = 0;
+    int rc = BCFGPU_OK;
+    const bool persistent = (h->engine == BCFGPU_ENGINE_PERSISTENT) && h->nranks == 1;
+    if (!persistent && h->nranks == 1) { if ((rc = build_graph(h))) return rc; }
+    CK(cudaEventRecord(h->ev0, h->stream));
+    if (persistent) {
+        rc = run_persistent(h, total);
+    } else if (h->nranks == 1) {
+        for (int it = 0; it < total; ++it) CK(cudaGraphLaunch(h->gexec, h->stream));
+        h->launches += (int64_t)total * (h->T + 3);
+    } else {
+        for (int it = 0; it < total && rc == BCFGPU_OK; ++it) rc = enqueue_sweep(h);
+        h->launches += (int64_t)total * (h->T + 3);
+    }
+    if (rc) { cudaStreamSynchronize(h->stream); return rc; }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    if ((rc = check_device_err(h))) return rc;
+    CK(cudaMemcpy(&sc, d.sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    h->nsaved = sc.save_ctr;
+    return BCFGPU_OK;
+}
+
+extern "C" {
+
+int bcfgpu_last_run_ms(bcfgpu_handle* h, double* ms)
+{
+    if (!h || !ms) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
+    *ms = h->last_ms;
+    return BCFGPU_OK;
+}
+int bcfgpu_kernel_launches(bcfgpu_handle* h, int64_t* count)
+{
+    if (!h || !count) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
+    *count = h->launches;
+    return BCFGPU_OK;
+}
+int bcfgpu_num_saved(bcfgpu_handle* h, int32_t* ns)
+{
+    if (!h || !ns) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
+    *ns = h->nsaved;
+    return BCFGPU_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+static int fetch_vec(bcfgpu_handle* h, const double* a, const double* b, int which, double st, double sc_, double* out)
+{
+    const Dev& d = h->dev;
+    const int grid = (int)std::min<int64_t>((h->n + 255) / 256, 4096);
+    k_unpermute<<<grid, 256, 0, h->stream>>>(a, b, h->d_pos, h->n, (double)h->nsaved, which, st, sc_,
+                                              (int64_t)d.trt_tiles * TILE, h->d_tmp);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->d_tmp, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BCFGPU_OK;
+}
+#define NEED_SAVED(h) do { if ((h)->nsaved < 1) return fail(BCFGPU_ERR_STATE, "no saved draws: call run with nsim >= 1"); } while (0)
+
+extern "C" {
+
+int bcfgpu_get_tau_mean(bcfgpu_handle* h, double* out)
+{
+    USE(h); NEED_DATA(h); NEED_SAVED(h);
+    if (!out) return fail(BCFGPU_ERR_BAD_ARG, "null output");
+    return fetch_vec(h, h->dev.tau_sum, nullptr, 1, 1, 1, out);
+}
+int bcfgpu_get_tau_var(bcfgpu_handle* h, double* out)
+{
+    USE(h); NEED_DATA(h); NEED_SAVED(h);
+    if (!out) return fail(BCFGPU_ERR_BAD_ARG, "null output");
+    return fetch_vec(h, h->dev.tau_sum, h->dev.tau_sq, 2, 1, 1, out);
+}
+int bcfgpu_get_mu_mean(bcfgpu_handle* h, double* out)
+{
+    USE(h); NEED_DATA(h); NEED_SAVED(h);
+    if (!out) return fail(BCFGPU_ERR_BAD_ARG, "null output");
+    return fetch_vec(h, h->dev.mu_sum, nullptr, 1, 1, 1, out);
+}
+int bcfgpu_get_yhat_mean(bcfgpu_handle* h, double* out)
+{
+    USE(h); NEED_DATA(h); NEED_SAVED(h);
+    if (!out) return fail(BCFGPU_ERR_BAD_ARG, "null output");
+    return fetch_vec(h, h->dev.yhat_sum, nullptr, 1, 1, 1, out);
+}
+int bcfgpu_get_sigma(bcfgpu_handle* h, double* out)
+{
+    USE(h); NEED_DATA(h);
+    if (!out) return fail(BCFGPU_ERR_BAD_ARG, "null output");
+    if (h->nsaved > 0) CK(cudaMemcpy(out, h->dev.sigma_post, (size_t)h->nsaved * 8, cudaMemcpyDeviceToHost));
+    return BCFGPU_OK;
+}
+int bcfgpu_get_scales(bcfgpu_handle* h, double* mu_scale, double* tau_scale)
+{
+    USE(h); NEED_DATA(h);
+    if (h->nsaved > 0 && mu_scale) CK(cudaMemcpy(mu_scale, h->dev.msd_post, (size_t)h->nsaved * 8, cudaMemcpyDeviceToHost));
+    if (h->nsaved > 0 && tau_scale) CK(cudaMemcpy(tau_scale, h->dev.bsd_post, (size_t)h->nsaved * 8, cudaMemcpyDeviceToHost));
+    return BCFGPU_OK;
+}
+int bcfgpu_get_draws(bcfgpu_handle* h, int32_t which, double* out)
+{
+    USE(h); NEED_DATA(h);
+    if (!out) return fail(BCFGPU_ERR_BAD_ARG, "null output");
+    const double* src = which == 0 ? h->dev.draws_tau : which == 1 ? h->dev.draws_mu : which == 2 ? h->dev.draws_yhat : nullptr;
+    if (!src) return fail(BCFGPU_ERR_STATE, "these draws were not kept (bcfgpu_config.keep_draws)");
+    for (int s = 0; s < h->nsaved; ++s) {
+        int rc = fetch_vec(h, src + (size_t)s * h->dev.n_pad, nullptr, 0, 1.0, 1.0, out + (size_t)s * h->n);
+        if (rc) return rc;
+    }
+    return BCFGPU_OK;
+}
+
+int bcfgpu_get_scalars(bcfgpu_handle* h, double out[8])
+{
+    USE(h); NEED_DATA(h);
+    CK(cudaStreamSynchronize(h->stream));
+    Scalars sc;
+    CK(cudaMemcpy(&sc, h->dev.sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    out[0] = sc.sigma; out[1] = sc.mscale; out[2] = sc.bscale1; out[3] = sc.bscale0; out[4] = sc.delta_con;
+    out[5] = sc.tau_con; out[6] = sc.tau_mod; out[7] = (double)sc.sweep;
+    return BCFGPU_OK;
+}
+int bcfgpu_get_fits(bcfgpu_handle* h, double* ac, double* am)
+{
+    USE(h); NEED_DATA(h);
+    CK(cudaStreamSynchronize(h->stream));
+    Scalars sc;
+    CK(cudaMemcpy(&sc, h->dev.sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    int rc;
+    if (ac && (rc = fetch_vec(h, h->dev.Gc, nullptr, 0, sc.mscale, sc.mscale, ac))) return rc;
+    if (am && (rc = fetch_vec(h, h->dev.Gm, nullptr, 0, sc.bscale1, sc.bscale0, am))) return rc;
+    return BCFGPU_OK;
+}
+int bcfgpu_get_counters(bcfgpu_handle* h, int64_t out[4])
+{
+    USE(h); NEED_DATA(h);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->dev.counters, 32, cudaMemcpyDeviceToHost));
+    return BCFGPU_OK;
+}
+int bcfgpu_get_trace(bcfgpu_handle* h, int32_t* trace5, double* logr)
+{
+    USE(h); NEED_DATA(h);
+    CK(cudaStreamSynchronize(h->stream));
+    if (trace5) CK(cudaMemcpy(trace5, h->dev.trace, (size_t)h->T * 5 * 4, cudaMemcpyDeviceToHost));
+    if (logr) CK(cudaMemcpy(logr, h->dev.trace_logr, (size_t)h->T * 8, cudaMemcpyDeviceToHost));
+    return BCFGPU_OK;
+}
+
+}  // extern "C"
+
+static int current_parity(bcfgpu_handle* h, int* par)
+{
+    Scalars sc;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(&sc, h->dev.sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    *par = sc.parity;
+    return BCFGPU_OK;
+}
+static int fetch_tree(bcfgpu_handle* h, int tree, TreeRec* tr)
+{
+    if (tree < 0 || tree >= h->T) return fail(BCFGPU_ERR_BAD_ARG, "tree index out of range");
+    int par, rc;
+    if ((rc = current_parity(h, &par))) return rc;
+    CK(cudaMemcpy(tr, h->dev.trees[par] + tree, sizeof(TreeRec), cudaMemcpyDeviceToHost));
+    return BCFGPU_OK;
+}
+static void preorder(const TreeRec& tr, int node, uint32_t* heap, int32_t* var, int32_t* cut, double* mu, int& k)
+{
+    const bool leaf = tr.left[node] < 0;
+    heap[k] = tr.heap[node]; var[k] = leaf ? -1 : (int32_t)tr.var[node]; cut[k] = leaf ? -1 : (int32_t)tr.cut[node];
+    mu[k] = leaf ? tr.mu[tr.node_slot[node]] : 0.0;
+    ++k;
+    if (!leaf) { preorder(tr, tr.left[node], heap, var, cut, mu, k); preorder(tr, tr.right[node], heap, var, cut, mu, k); }
+}
+
+extern "C" {
+
+int bcfgpu_tree_size(bcfgpu_handle* h, int32_t tree, int32_t* nnodes)
+{
+    USE(h); NEED_DATA(h);
+    TreeRec tr; int rc;
+    if ((rc = fetch_tree(h, tree, &tr))) return rc;
+    *nnodes = tr.nnodes;
+    return BCFGPU_OK;
+}
+int bcfgpu_get_tree(bcfgpu_handle* h, int32_t tree, uint32_t* heap, int32_t* var, int32_t* cut, double* mu)
+{
+    USE(h); NEED_DATA(h);
+    TreeRec tr; int rc;
+    if ((rc = fetch_tree(h, tree, &tr))) return rc;
+    int k = 0;
+    preorder(tr, 0, heap, var, cut, mu, k);
+    return BCFGPU_OK;
+}
+
+int bcfgpu_set_tree(bcfgpu_handle* h, int32_t tree, int32_t nnodes, const uint32_t* heap, const int32_t* var,
+                    const int32_t* cut, const double* mu)
+{
+    USE(h); NEED_DATA(h);
+    if (tree < 0 || tree >= h->T) return fail(BCFGPU_ERR_BAD_ARG, "tree index out of range");
+    if (nnodes < 1 || nnodes > 2 * h->cfg.max_leaves - 1 || (nnodes % 2) == 0) return fail(BCFGPU_ERR_BAD_ARG, "bad node count");
+    const int f = tree >= h->cfg.ntree_con ? 1 : 0;
+    const ForestHost& F = h->fh[f];
+    TreeRec tr;
+    root_tree(tr, 0.0);
+    tr.nnodes = nnodes; tr.nleaves = 0;
+    // nodes keep the caller's order; link them through their heap ids
+    std::vector<std::pair<uint32_t, int>> byheap;
+    for (int k = 0; k < nnodes; ++k) byheap.push_back({heap[k], k});
+    std::sort(byheap.begin(), byheap.end());
+    auto find = [&](uint32_t id) -> int {
+        auto it = std::lower_bound(byheap.begin(), byheap.end(), std::make_pair(id, -1));
+        return (it != byheap.end() && it->first == id) ? it->second : -1;
+    };
+    const int root = find(1u);
+    if (root < 0) return fail(BCFGPU_ERR_BAD_ARG, "serialised tree has no root (heap id 1)");
+    // node 0 must be the root: swap indices
+    std::vector<int> idx(nnodes);
+    for (int k = 0; k < nnodes; ++k) idx[k] = k;
+    std::swap(idx[root], idx[0]);   // caller node k -> TreeRec node idx[k]
+    for (int k = 0; k < nnodes; ++k) {
+        const int i = idx[k];
+        const uint32_t id = heap[k];
+        if (id == 0) return fail(BCFGPU_ERR_BAD_ARG, "heap id 0");
+        int depth = 0;
+        for (uint32_t t = id; t > 1; t >>= 1) ++depth;
+        if (depth > MAX_DEPTH) return fail(BCFGPU_ERR_BAD_ARG, "tree deeper than BCFGPU_MAX_DEPTH");
+        tr.heap[i] = id; tr.depth[i] = (uint8_t)depth;
+        const int par = id == 1 ? -1 : find(id >> 1);
+        if (id != 1 && par < 0) return fail(BCFGPU_ERR_BAD_ARG, "node without parent");
+        tr.parent[i] = (int16_t)(par < 0 ? -1 : idx[par]);
+        const int l = find(2 * id), r = find(2 * id + 1);
+        if ((l < 0) != (r < 0)) return fail(BCFGPU_ERR_BAD_ARG, "node with one child");
+        if (l >= 0) {
+            if (var[k] < 0 || var[k] >= F.p || cut[k] < 0 || cut[k] >= F.ncut[var[k]]) return fail(BCFGPU_ERR_BAD_ARG, "split rule out of range");
+            tr.left[i] = (int16_t)idx[l]; tr.right[i] = (int16_t)idx[r];
+            tr.var[i] = (uint16_t)var[k]; tr.cut[i] = (uint16_t)cut[k];
+        } else {
+            const int s = tr.nleaves++;
+            if (s >= h->cfg.max_leaves) return fail(BCFGPU_ERR_BAD_ARG, "too many leaves");
+            tr.node_slot[i] = (uint8_t)s; tr.slot_node[s] = (int16_t)i; tr.mu[s] = mu[k];
+        }
+    }
+    if (2 * tr.nleaves - 1 != nnodes) return fail(BCFGPU_ERR_BAD_ARG, "not a full binary tree");
+    int par, rc;
+    if ((rc = current_parity(h, &par))) return rc;
+    CK(cudaMemcpy(h->dev.trees[0] + tree, &tr, sizeof(TreeRec), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dev.trees[1] + tree, &tr, sizeof(TreeRec), cudaMemcpyHostToDevice));
+    k_assign<<<h->grid_fin, 256, 0, h->stream>>>(h->dev, tree, f, h->dev.trees[par], 0, nullptr, h->d_orig);
+    k_refit_all<<<h->grid_fin, 256, 0, h->stream>>>(h->dev, h->dev.trees[par]);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return BCFGPU_OK;
+}
+
+int bcfgpu_get_leaf_ids(bcfgpu_handle* h, int32_t tree, uint32_t* out)
+{
+    USE(h); NEED_DATA(h);
+    if (tree < 0 || tree >= h->T || !out) return fail(BCFGPU_ERR_BAD_ARG, "bad argument");
+    int par, rc;
+    if ((rc = current_parity(h, &par))) return rc;
+    uint32_t* tmp = (uint32_t*)h->d_tmp;
+    k_leaf_heap<<<(int)std::min<int64_t>((h->n + 255) / 256, 4096), 256, 0, h->stream>>>(h->dev, tree, h->dev.trees[par], h->d_pos, h->n, tmp);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, tmp, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BCFGPU_OK;
+}
+
+int bcfgpu_verify_leaf_cache(bcfgpu_handle* h, int64_t* mismatches)
+{
+    USE(h); NEED_DATA(h);
+    if (!mismatches) return fail(BCFGPU_ERR_BAD_ARG, "null output");
+    int par, rc;
+    if ((rc = current_parity(h, &par))) return rc;
+    unsigned long long* cnt = (unsigned long long*)h->d_tmp2;
+    CK(cudaMemsetAsync(cnt, 0, 8, h->stream));
+    for (int t = 0; t < h->T; ++t)
+        k_assign<<<h->grid_fin, 256, 0, h->stream>>>(h->dev, t, t >= h->cfg.ntree_con ? 1 : 0, h->dev.trees[par], 1, cnt, h->d_orig);
+    h->launches += h->T;
+    CK(cudaGetLastError());
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, cnt, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *mismatches = (int64_t)v;
+    return BCFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone operators
+// ------------------------------------------------------------------------------------------------
+int bcfgpu_op_bin_column(const double* x, int64_t n, const double* cuts, int32_t ncut, uint16_t* out)
+{
+    if (!x || !cuts || !out || n < 1 || ncut < 1 || ncut > 65535) return fail(BCFGPU_ERR_BAD_ARG, "bad argument");
+    if (bcfgpu_device_count() == 0) return fail(BCFGPU_ERR_CUDA, "no CUDA device available (libbcfgpu has no CPU fallback)");
+    double *dx = nullptr, *dc = nullptr; uint16_t* dout = nullptr;
+    CK(cudaMalloc((void**)&dx, (size_t)n * 8));
+    CK(cudaMalloc((void**)&dc, (size_t)ncut * 8));
+    CK(cudaMalloc((void**)&dout, (size_t)n * 2));
+    CK(cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc, cuts, (size_t)ncut * 8, cudaMemcpyHostToDevice));
+    k_bin_simple<<<(int)std::min<int64_t>((n + 255) / 256, 4096), 256>>>(dx, n, dc, ncut, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout, (size_t)n * 2, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dc); cudaFree(dout);
+    return BCFGPU_OK;
+}
+
+int bcfgpu_op_suffstats(bcfgpu_handle* h, int32_t tree, const double* r, uint32_t birth_leaf_heap, int32_t var,
+                        int32_t cut, int32_t* nleaves, uint32_t* heap, int64_t* cnt_trt, int64_t* cnt_ctl,
+                        double* sum_trt, double* sum_ctl, double out_birth[8])
+{
+    USE(h); NEED_DATA(h);
+    if (!r || !nleaves || !heap || !cnt_trt || !cnt_ctl || !sum_trt || !sum_ctl) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
+    TreeRec tr; int rc;
+    if ((rc = fetch_tree(h, tree, &tr))) return rc;
+    const int f = tree >= h->cfg.ntree_con ? 1 : 0;
+    const int L = tr.nleaves;
+    int sx = -1;
+    if (birth_leaf_heap) {
+        for (int s = 0; s < L; ++s) if (tr.heap[tr.slot_node[s]] == birth_leaf_heap) sx = s;
+        if (sx < 0) return fail(BCFGPU_ERR_BAD_ARG, "no leaf with that heap id");
+        if (var < 0 || var >= h->fh[f].p || cut < 0 || cut >= h->fh[f].ncut[var]) return fail(BCFGPU_ERR_BAD_ARG, "split rule out of range");
+        if (!out_birth) return fail(BCFGPU_ERR_BAD_ARG, "null out_birth");
+    }
+    const int K = L + (sx >= 0 ? 1 : 0);
+    // r in the caller's order -> internal order (padding rows 0)
+    CK(cudaMemsetAsync(h->d_tmp2, 0, (size_t)h->n_pad * 8, h->stream));
+    CK(cudaMemcpyAsync(h->d_tmp, r, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
+    k_permute_in<<<(int)std::min<int64_t>((h->n + 255) / 256, 4096), 256, 0, h->stream>>>(h->d_tmp, h->d_pos, h->n, h->d_tmp2);
+    long long* dout = nullptr;
+    CK(cudaMalloc((void**)&dout, (size_t)KEYS * 8 * 8));
+    CK(cudaMemsetAsync(dout, 0, (size_t)KEYS * 8 * 8, h->stream));
+    k_op_stats<<<h->grid_obs, THREADS, 0, h->stream>>>(h->dev, tree, f, h->d_tmp2, K, sx >= 0, sx, var, cut, dout);
+    h->launches += 2;
+    std::vector<long long> tot((size_t)KEYS * 8);
+    cudaError_t e = cudaMemcpyAsync(tot.data(), dout, tot.size() * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dout);
+    if (e != cudaSuccess) return fail(BCFGPU_ERR_CUDA, std::string("op_suffstats: ") + cudaGetErrorString(e));
+    if ((rc = check_device_err(h))) return rc;
+    auto cntv = [&](int k, int g) { return tot[(size_t)k * 8 + g * 4]; };
+    auto sumv = [&](int k, int g) { const long long* q = &tot[(size_t)k * 8 + g * 4]; return limbs_to_double(q[1], q[2], q[3]); };
+    auto sum_exact = [&](int k1, int k2, int g) {   // exact merge of two keys before rounding
+        const long long* a = &tot[(size_t)k1 * 8 + g * 4]; const long long* b = &tot[(size_t)k2 * 8 + g * 4];
+        return limbs_to_double(a[1] + b[1], a[2] + b[2], a[3] + b[3]);
+    };
+    // leaves in DFS (left-to-right) order
+    std::vector<std::pair<uint32_t, int>> order;
+    for (int s = 0; s < L; ++s) { const int nd = tr.slot_node[s]; order.push_back({tr.heap[nd] << (MAX_DEPTH - tr.depth[nd]), s}); }
+    std::sort(order.begin(), order.end());
+    *nleaves = L;
+    for (int q = 0; q < L; ++q) {
+        const int s = order[q].second;
+        heap[q] = tr.heap[tr.slot_node[s]];
+        if (s == sx) {
+            cnt_trt[q] = cntv(s, 1) + cntv(L, 1); cnt_ctl[q] = cntv(s, 0) + cntv(L, 0);
+            sum_trt[q] = sum_exact(s, L, 1); sum_ctl[q] = sum_exact(s, L, 0);
+        } else {
+            cnt_trt[q] = cntv(s, 1); cnt_ctl[q] = cntv(s, 0); sum_trt[q] = sumv(s, 1); sum_ctl[q] = sumv(s, 0);
+        }
+    }
+    if (sx >= 0) {
+        out_birth[0] = (double)cntv(sx, 1); out_birth[1] = (double)cntv(sx, 0); out_birth[2] = sumv(sx, 1); out_birth[3] = sumv(sx, 0);
+        out_birth[4] = (double)cntv(L, 1); out_birth[5] = (double)cntv(L, 0); out_birth[6] = sumv(L, 1); out_birth[7] = sumv(L, 0);
+    }
+    return BCFGPU_OK;
+}
+
+int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, int32_t nleaf, const double* r,
+                       int64_t* cnt, double* sum, double* device_ms)
+{
+    USE(h); NEED_DATA(h);
+    if (forest < 0 || forest > 1 || !slot || !r || !cnt || !sum || nleaf < 1 || nleaf > 254) return fail(BCFGPU_ERR_BAD_ARG, "bad argument");
+    const ForestHost& F = h->fh[forest];
+    if (F.p == 0) return fail(BCFGPU_ERR_BAD_ARG, "forest has no covariates");
+    const int64_t nbt = (int64_t)F.off[F.p] + F.p;
+    // labels -> internal order, uint8, padding = 255
+    std::vector<uint8_t> lab((size_t)h->n_pad, 255);
+    for (int64_t i = 0; i < h->n; ++i) lab[h->pos[i]] = (slot[i] >= 0 && slot[i] < nleaf) ? (uint8_t)slot[i] : 255;
+    uint8_t* dlab = nullptr; long long* dout = nullptr;
+    CK(cudaMalloc((void**)&dlab, (size_t)h->n_pad));
+    cudaError_t e = cudaMalloc((void**)&dout, (size_t)nleaf * nbt * 32);
+    if (e != cudaSuccess) { cudaFree(dlab); return fail(BCFGPU_ERR_OOM, "op_hist_all: output too large"); }
+    CK(cudaMemcpyAsync(dlab, lab.data(), (size_t)h->n_pad, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_tmp2, 0, (size_t)h->n_pad * 8, h->stream));
+    CK(cudaMemcpyAsync(h->d_tmp, r, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
+    k_permute_in<<<(int)std::min<int64_t>((h->n + 255) / 256, 4096), 256, 0, h->stream>>>(h->d_tmp, h->d_pos, h->n, h->d_tmp2);
+    CK(cudaMemsetAsync(dout, 0, (size_t)nleaf * nbt * 32, h->stream));
+    const int64_t nchunk = h->n_pad / 16;
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((nchunk + 255) / 256, (int64_t)h->num_sms * 2)), (unsigned)F.p);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    k_hist<<<grid, 256, 0, h->stream>>>(h->dev, forest, dlab, h->d_tmp2, nleaf, F.d_off, dout);
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->launches += 2;
+    std::vector<long long> tot((size_t)nleaf * nbt * 4);
+    e = cudaMemcpyAsync(tot.data(), dout, tot.size() * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    cudaFree(dlab); cudaFree(dout);
+    if (e != cudaSuccess) return fail(BCFGPU_ERR_CUDA, std::string("op_hist_all: ") + cudaGetErrorString(e));
+    if (device_ms) *device_ms = ms;
+    for (size_t k = 0; k < (size_t)nleaf * nbt; ++k) {
+        cnt[k] = tot[k * 4];
+        sum[k] = limbs_to_double(tot[k * 4 + 1], tot[k * 4 + 2], tot[k * 4 + 3]);
+    }
+    return check_device_err(h);
+}
+
+int bcfgpu_op_lil(const double* sum_phi, const double* sum_phi_r, const double* tau, int32_t m, double* out)
+{
+    if (!sum_phi || !sum_phi_r || !tau || !out || m < 1) return fail(BCFGPU_ERR_BAD_ARG, "bad argument");
+    if (bcfgpu_device_count() == 0) return fail(BCFGPU_ERR_CUDA, "no CUDA device available (libbcfgpu has no CPU fallback)");
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, (size_t)m * 8 * 4));
+    CK(cudaMemcpy(d, sum_phi, (size_t)m * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d + m, sum_phi_r, (size_t)m * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d + 2 * m, tau, (size_t)m * 8, cudaMemcpyHostToDevice));
+    k_lil<<<(m + 127) / 128, 128>>>(d, d + m, d + 2 * m, m, d + 3 * m);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, d + 3 * m, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return BCFGPU_OK;
+}
+
+int bcfgpu_op_rng_probe(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t tree, uint32_t purpose, uint32_t idx,
+                        double out3[3])
+{
+    if (!out3) return fail(BCFGPU_ERR_BAD_ARG, "null output");
+    if (bcfgpu_device_count() == 0) return fail(BCFGPU_ERR_CUDA, "no CUDA device available (libbcfgpu has no CPU fallback)");
+    const uint64_t s = seed + (uint64_t)chain * 0x9E3779B97F4A7C15ull;
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, 24));
+    k_rng_probe<<<1, 1>>>((uint32_t)s, (uint32_t)(s >> 32), sweep, tree, purpose, idx, d);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out3, d, 24, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return BCFGPU_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// PERSISTENT engine launch
+// ------------------------------------------------------------------------------------------------
+static int run_persistent(bcfgpu_handle* h, int total)
+{
+    if (total <= 0) return BCFGPU_OK;
+    if (h->coop_grid == 0) {
+        int coop = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+        if (!coop) return fail(BCFGPU_ERR_CUDA, "device does not support cooperative launch");
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PTHREADS, 0));
+        if (per_sm < 1) return fail(BCFGPU_ERR_CUDA, "persistent kernel does not fit on an SM");
+        h->coop_grid = h->num_sms * std::min(per_sm, PERSIST_CTAS_PER_SM);
+    }
+    // keep launches short enough to stay interruptible (R_CheckUserInterrupt between batches)
+    const int batch = 256;
+    for (int done = 0; done < total; done += batch) {
+        int nsw = std::min(batch, total - done);
+        Dev d = h->dev;
+        unsigned int* bar = h->d_bar;
+        CK(cudaMemsetAsync(bar, 0, 4, h->stream));
+        void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar};
+        CK(cudaLaunchCooperativeKernel((const void*)k_persistent, dim3(h->coop_grid), dim3(PTHREADS), args, 0, h->stream));
+        h->launches++;
+    }
+    return BCFGPU_OK;
+}

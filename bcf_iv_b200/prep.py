@@ -30,7 +30,11 @@ def cp_quantile(x: np.ndarray, num: int = CP_NUM, cat_levels: int = CP_CAT_LEVEL
         return ux[:-1] + np.diff(ux) / 2.0
     n = x.size
     xs = np.sort(x)
-    qs = np.quantile(xs, np.arange(n) / n)          # R quantile type 7 == numpy 'linear'
+    # R quantile type 7 at probabilities k/n, k = 0..n-1, computed directly on the sorted column
+    hq = (n - 1) * (np.arange(n) / n)
+    lo = np.floor(hq).astype(np.int64)
+    hi = np.minimum(lo + 1, n - 1)
+    qs = xs[lo] + (hq - lo) * (xs[hi] - xs[lo])
     # approxfun(ties = mean): collapse tied abscissae, averaging their ordinates
     uxs, inv = np.unique(xs, return_inverse=True)
     mq = np.bincount(inv, weights=qs) / np.bincount(inv)

@@ -1,0 +1,167 @@
+/*
+ * bcfgpu.h -- C-ABI of libbcfgpu.so, the B200 (sm_100a) implementation of the Bayesian Causal
+ * Forest Gibbs sampler behind BayesIV's bcf_iv() / bcf_itt().
+ *
+ * What this boundary replaces in the reference (fbargaglistoffi/BCF-IV):
+ *   R/bcf_iv.R:89   itt_bcf <- quiet(bcf(y[-index], z[-index], x[-index,], x[-index,], pihat, nburn=, nsim=))
+ *   R/bcf_itt.R:71  bcf_fit <- quiet(bcf(...same...))
+ * i.e. the native entry that bcf::bcf reaches through Rcpp's
+ *   .Call("_bcf_bcfoverparRcppClean", y, z, t(x_c), t(x_m), cutpoint lists, nburn, nsim, nthin, ...)
+ * (third-party package `bcf`, imported un-pinned at DESCRIPTION:23 / NAMESPACE:9; source not vendored,
+ * see SURVEY.md 8b/8c).  The R shim that binds these entry points with .Call is
+ * bcf_iv_b200/R/src/r_shim.c; INTEGRATION.md shows the wiring.
+ *
+ * Conventions
+ *   - plain C, no R / torch / CUDA types in any signature; every pointer is a HOST pointer unless the
+ *     name says `_dev`.
+ *   - every function returns a bcfgpu_status (0 = ok); bcfgpu_last_error() gives the message of the last
+ *     failure on the calling thread.
+ *   - the caller allocates every output buffer; the library owns all device memory behind the handle.
+ *   - there is NO CPU fallback: with no CUDA device every compute call fails with BCFGPU_ERR_CUDA.
+ *   - matrices are COLUMN-MAJOR doubles (R's native layout, no transpose needed): X[i + n*v].
+ *   - rows may be in any order; the library applies bcf's `perm = order(z, decreasing=TRUE)` (treated rows
+ *     first, stable) internally and un-permutes every per-observation output.
+ */
+#ifndef BCFGPU_H
+#define BCFGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCFGPU_API __attribute__((visibility("default")))
+
+#define BCFGPU_ABI_VERSION 1
+#define BCFGPU_MAX_LEAVES 128   /* structural cap per tree (leaf slots are uint8, 255 = padding) */
+#define BCFGPU_MAX_DEPTH 30     /* heap node ids are 32-bit */
+
+typedef enum bcfgpu_status {
+    BCFGPU_OK = 0,
+    BCFGPU_ERR_BAD_ARG = 1,
+    BCFGPU_ERR_CUDA = 2,        /* includes "no CUDA device": there is no CPU path */
+    BCFGPU_ERR_NCCL = 3,
+    BCFGPU_ERR_NUMERIC = 4,     /* NaN / fixed-point range guard tripped on device (bcf stop()s on NaN too) */
+    BCFGPU_ERR_OOM = 5,
+    BCFGPU_ERR_STATE = 6        /* call order (e.g. run before set_data) */
+} bcfgpu_status;
+
+typedef enum bcfgpu_engine {
+    BCFGPU_ENGINE_AUTO = 0,
+    BCFGPU_ENGINE_GRAPH = 1,       /* one kernel per tree, a sweep captured in a CUDA graph */
+    BCFGPU_ENGINE_PERSISTENT = 2   /* one cooperative kernel per batch of sweeps, grid barrier per tree */
+} bcfgpu_engine;
+
+/* Hyper-parameters of the sampler: bcf()'s arguments after the R wrapper's rescaling. */
+typedef struct bcfgpu_config {
+    int32_t struct_size;          /* = sizeof(bcfgpu_config), ABI guard */
+    int32_t ntree_con;            /* ntree_control  (200) */
+    int32_t ntree_mod;            /* ntree_moderate (50)  */
+    double alpha_con, beta_con;   /* base_control .95, power_control 2   */
+    double alpha_mod, beta_mod;   /* base_moderate .25, power_moderate 3 */
+    double con_sd;                /* 2 when sd_control == 2*sd(y), else sd_control/sd(y) */
+    double mod_sd;                /* (1 or sd_moderate/sd(y)) / 0.674 when use_tauscale */
+    double nu, lambda;            /* sigma^2 prior: nu*lambda / chisq_nu */
+    double sigma_init;            /* sd(yscale) */
+    int32_t use_muscale, use_tauscale;
+    int32_t min_leaf;             /* 5: birth needs >= min_leaf observations in each child */
+    int32_t max_leaves;           /* 0 -> BCFGPU_MAX_LEAVES */
+    uint64_t seed;                /* Philox key; reproducible for fixed (seed, chain) on any GPU count */
+    uint32_t chain;               /* chain index: mixes into the key (one chain per GPU in chains mode) */
+    int32_t device;               /* CUDA ordinal; -1 = current device */
+    int32_t engine;               /* bcfgpu_engine */
+    int32_t keep_draws;           /* bit0 tau, bit1 mu, bit2 yhat: keep nsim x n draws on device */
+    int32_t reserved[7];
+} bcfgpu_config;
+
+typedef struct bcfgpu_handle bcfgpu_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+BCFGPU_API int bcfgpu_abi_version(void);
+BCFGPU_API int bcfgpu_device_count(void);                   /* 0 when no usable CUDA device */
+BCFGPU_API const char *bcfgpu_last_error(void);
+BCFGPU_API void bcfgpu_config_init(bcfgpu_config *cfg);     /* bcf()'s defaults */
+BCFGPU_API int bcfgpu_create(const bcfgpu_config *cfg, bcfgpu_handle **out);
+BCFGPU_API int bcfgpu_destroy(bcfgpu_handle *h);
+
+/* ---- observation-sharded mode: call before set_data on every rank ------------------
+ * nccl_unique_id: the 128 bytes of an ncclUniqueId made on rank 0 (bcfgpu_nccl_unique_id) and broadcast by
+ * the caller (torch.distributed, MPI, ...).  Each rank then passes only ITS rows to set_data. */
+BCFGPU_API int bcfgpu_nccl_unique_id(char id_out[128]);
+BCFGPU_API int bcfgpu_set_shard(bcfgpu_handle *h, int rank, int nranks, const char nccl_unique_id[128]);
+
+/* ---- data ------------------------------------------------------------------------------------
+ * y: standardised outcome (n); z: 0/1 treatment = BayesIV's instrument (n);
+ * xcon/xmod: column-major n x p_con / n x p_mod (xcon already has pihat appended when include_pi="control");
+ * cuts_*: concatenated sorted cutpoints, cut_off_*[v]..cut_off_*[v+1] are variable v's (bcf's xinfo).
+ * Bins X into column-major uint8/uint16 on device (kernel K0) and resets the chain to its initial state. */
+BCFGPU_API int bcfgpu_set_data(bcfgpu_handle *h, int64_t n, int32_t p_con, int32_t p_mod, const double *y,
+                               const int32_t *z, const double *xcon, const double *xmod,
+                               const double *cuts_con, const int32_t *cut_off_con,
+                               const double *cuts_mod, const int32_t *cut_off_mod);
+
+/* ---- sampling --------------------------------------------------------------------------------
+ * Runs nburn + nsim*nthin Gibbs sweeps (continuing the chain if called again); sweep it is saved when
+ * it >= nburn and it % nthin == 0, as bcf does.  Blocking. */
+BCFGPU_API int bcfgpu_run(bcfgpu_handle *h, int32_t nburn, int32_t nsim, int32_t nthin);
+BCFGPU_API int bcfgpu_last_run_ms(bcfgpu_handle *h, double *device_ms);  /* CUDA-event time of the last run */
+BCFGPU_API int bcfgpu_kernel_launches(bcfgpu_handle *h, int64_t *count); /* kernels launched since create */
+
+/* ---- results (standardised scale, original row order; the R wrapper rescales by sd(y)/mean(y)) ---- */
+BCFGPU_API int bcfgpu_num_saved(bcfgpu_handle *h, int32_t *nsaved);
+BCFGPU_API int bcfgpu_get_tau_mean(bcfgpu_handle *h, double *out_n);    /* colMeans(b_post): what BayesIV uses */
+BCFGPU_API int bcfgpu_get_tau_var(bcfgpu_handle *h, double *out_n);     /* per-observation posterior variance */
+BCFGPU_API int bcfgpu_get_mu_mean(bcfgpu_handle *h, double *out_n);
+BCFGPU_API int bcfgpu_get_yhat_mean(bcfgpu_handle *h, double *out_n);
+BCFGPU_API int bcfgpu_get_sigma(bcfgpu_handle *h, double *out_nsaved);
+BCFGPU_API int bcfgpu_get_scales(bcfgpu_handle *h, double *mu_scale_nsaved, double *tau_scale_nsaved);
+/* which: 0 tau, 1 mu, 2 yhat; out is nsaved x n ROW-major per draw (draw-major), needs keep_draws */
+BCFGPU_API int bcfgpu_get_draws(bcfgpu_handle *h, int32_t which, double *out_nsaved_by_n);
+
+/* ---- chain state (parity tests, checkpoints, predict) ------------------------------------------ */
+/* scalars: {sigma, mscale, bscale1, bscale0, delta_con, tau_con, tau_mod, sweeps_done} */
+BCFGPU_API int bcfgpu_get_scalars(bcfgpu_handle *h, double out8[8]);
+/* allfit_con = mscale * sum of mu trees, allfit_mod = bscale_z * sum of tau trees (original row order) */
+BCFGPU_API int bcfgpu_get_fits(bcfgpu_handle *h, double *allfit_con_n, double *allfit_mod_n);
+/* counters: {birth proposed, birth accepted, death proposed, death accepted} */
+BCFGPU_API int bcfgpu_get_counters(bcfgpu_handle *h, int64_t out4[4]);
+/* last sweep's move per tree: trace5[t] = {move (0 none,1 birth,2 death), accepted, node heap id, var, cut};
+ * logr[t] = log MH ratio (NaN when not evaluated) */
+BCFGPU_API int bcfgpu_get_trace(bcfgpu_handle *h, int32_t *trace5_T, double *logr_T);
+BCFGPU_API int bcfgpu_tree_size(bcfgpu_handle *h, int32_t tree, int32_t *nnodes);
+/* preorder serialisation: heap id (root 1, children 2i / 2i+1), split var (-1 = leaf), cut index, mu */
+BCFGPU_API int bcfgpu_get_tree(bcfgpu_handle *h, int32_t tree, uint32_t *heap, int32_t *var, int32_t *cut, double *mu);
+/* replace a tree's structure and leaf values; recomputes its leaf assignment (kernel K1) and the fits */
+BCFGPU_API int bcfgpu_set_tree(bcfgpu_handle *h, int32_t tree, int32_t nnodes, const uint32_t *heap,
+                               const int32_t *var, const int32_t *cut, const double *mu);
+/* cached leaf of every observation for one tree, as the leaf's heap id (original row order) */
+BCFGPU_API int bcfgpu_get_leaf_ids(bcfgpu_handle *h, int32_t tree, uint32_t *heap_n);
+/* re-derive every cached leaf slot from the tree structures (K1) and count mismatches with the cache */
+BCFGPU_API int bcfgpu_verify_leaf_cache(bcfgpu_handle *h, int64_t *mismatches);
+
+/* ---- stand-alone operators on the handle's binned data (kernel-level parity) ----------- */
+/* K0: bin one column: out[i] = #{c : cuts[c] <= x[i]}  (so x < cuts[c]  <=>  out <= c) */
+BCFGPU_API int bcfgpu_op_bin_column(const double *x, int64_t n, const double *cuts, int32_t ncut, uint16_t *out);
+/* K2: per-leaf sufficient statistics of tree `tree` for a caller-supplied residual r (original row order):
+ * for each leaf in DFS order: heap id, count treated, count control, sum r treated, sum r control.
+ * If birth_leaf_heap != 0 additionally splits that leaf by (var, cut): out_birth = {nl_trt, nl_ctl, sl_trt,
+ * sl_ctl, nr_trt, nr_ctl, sr_trt, sr_ctl}. */
+BCFGPU_API int bcfgpu_op_suffstats(bcfgpu_handle *h, int32_t tree, const double *r_n, uint32_t birth_leaf_heap,
+                                   int32_t var, int32_t cut, int32_t *nleaves, uint32_t *heap, int64_t *cnt_trt,
+                                   int64_t *cnt_ctl, double *sum_trt, double *sum_ctl, double out_birth[8]);
+/* K2': all-candidate histogram: for leaf labels slot[i] in [0,nleaf) (or <0 = skip) and forest (0 con, 1 mod):
+ * cnt/sum[leaf][cut_off[v] + v + b] over bins b = 0..ncut_v.  (count, residual sum) for every (var, cutpoint). */
+BCFGPU_API int bcfgpu_op_hist_all(bcfgpu_handle *h, int32_t forest, const int32_t *slot_n, int32_t nleaf,
+                                  const double *r_n, int64_t *cnt, double *sum, double *device_ms);
+/* K3: integrated log-likelihood of a leaf, weighted form (bcf's lilhet without the cancelling term) */
+BCFGPU_API int bcfgpu_op_lil(const double *sum_phi, const double *sum_phi_r, const double *tau, int32_t m, double *out);
+/* Philox stream probe: {ua, ub, normal} for (seed, chain, sweep, tree, purpose, idx), computed on device */
+BCFGPU_API int bcfgpu_op_rng_probe(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t tree, uint32_t purpose,
+                                   uint32_t idx, double out3[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCFGPU_H */
