@@ -56,9 +56,11 @@ struct Proposal {
     int32_t slot_b;      // birth: slot the right child would get (= nleaves); death: slot of the right child
     int32_t var, cut;
     uint32_t heap;
-    int32_t pad_;
+    int32_t is16;        // width of the proposed variable's bin column
+    const void* bins;    // its column in HBM (n_pad entries)
     double log_prior;    // log of the structural part of the MH ratio (alpha1)
-    double u_acc;
+    double log_u;        // log of the accept uniform: accept iff log_u < log ratio
+    double z_extra[2];   // normals of the leaves a move would create: birth {left, right child}, death {merged leaf}
 };
 
 struct Scalars {
@@ -92,9 +94,8 @@ struct Dev {
     double *r, *Gc, *Gm;
     uint8_t* slots;            // [T][n_pad]
     TreeRec* trees[2];
-    Proposal* prop;            // [T]
     long long* totals;         // [T][KEYS][2][4]  (count, limb0, limb1, limb2) by (key, group)
-    long long* mom;            // [2 buffers][2 groups][NMOM][3]; the GRAPH engine uses buffer 0 only
+    long long* mom;            // [2 buffers][2 groups][NMOM][3]; sweep s uses buffer s & 1
     Scalars* sc;
     int32_t* err;              // device error flags (ERR_*)
     int32_t* trace;            // [T][5]
@@ -104,6 +105,7 @@ struct Dev {
     double *draws_tau, *draws_mu, *draws_yhat;   // [nsim][n_pad] or null
     double *sigma_post, *msd_post, *bsd_post;    // [cap]
     int32_t post_cap;
+    long long* prof;           // optional [16] cycle counters of CTA 0 (persistent engine), null = off
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -265,12 +267,17 @@ __device__ __forceinline__ void st8_f64(double* p, const double (&in)[8])
 #pragma unroll
     for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(p)[j] = make_double2(in[2 * j], in[2 * j + 1]);
 }
-// bins of variable v for 8 observations starting at `base`
-__device__ __forceinline__ void ld8_bins(const ForestDev& F, int v, int64_t n_pad, int64_t base, int (&out)[8])
+// bins of one variable (column base pointer resolved at proposal time) for 8 observations starting at `base`
+__device__ __forceinline__ void ld8_bins(const void* col, int is16, int64_t base, int (&out)[8])
+{
+    if (is16) ld8_u16(reinterpret_cast<const uint16_t*>(col) + base, out);
+    else ld8_u8(reinterpret_cast<const uint8_t*>(col) + base, out);
+}
+__device__ __forceinline__ const void* bin_column(const ForestDev& F, int v, int64_t n_pad, int& is16)
 {
     const int ci = F.col_index[v];
-    if (F.col_is16[v]) ld8_u16(F.bins16 + (int64_t)ci * n_pad + base, out);
-    else ld8_u8(F.bins8 + (int64_t)ci * n_pad + base, out);
+    is16 = F.col_is16[v];
+    return is16 ? (const void*)(F.bins16 + (int64_t)ci * n_pad) : (const void*)(F.bins8 + (int64_t)ci * n_pad);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -88,33 +88,33 @@ __global__ void __launch_bounds__(THREADS) k_tree_step(Dev d, int prev, int cur)
     const Scalars sc = *d.sc;
     const int par = sc.parity;
     const bool writer = (blockIdx.x == 0);
-    if (threadIdx.x == 0) { sm.ai.active = 0; sm.ci.active = 0; sm.bad = 0; }
+    if (threadIdx.x == 0) { sm.ai.active = 0; sm.st[1].ci.active = 0; sm.bad = 0; }
     __syncthreads();
     if (prev >= 0) {
+        // the proposal of tree prev is a pure function of its structure and the Philox counters: replay it
         const ForestDev& F = d.f[prev >= d.f[1].tree0 ? 1 : 0];
-        load_tree(&sm.tr, &d.trees[par][prev]);
-        if (threadIdx.x == 0) sm.prop = d.prop[prev];
+        load_tree(&sm.st[0].tr, &d.trees[par][prev]);
         __syncthreads();
-        decide(sm, d, F, prev, sc, writer);
-        if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.tr);
+        propose(sm, 0, d, F, prev, sc.sweep);
+        decide(sm, 0, d, F, prev, sc, writer);
+        if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.st[0].tr);
         __syncthreads();
     }
     if (cur >= 0) {
         const int fc = cur >= d.f[1].tree0 ? 1 : 0;
-        load_tree(&sm.tr, &d.trees[par][cur]);
+        load_tree(&sm.st[1].tr, &d.trees[par][cur]);
         __syncthreads();
-        propose(sm, d, d.f[fc], cur, sc.sweep);
-        begin_stats(sm, fc);
-        if (writer && threadIdx.x == 0) d.prop[cur] = sm.prop;
+        propose(sm, 1, d, d.f[fc], cur, sc.sweep);
+        begin_stats(sm, 1, fc, sc);
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     int bad = 0;
     for (int tile = blockIdx.x * wpb + wib; tile < d.n_tiles; tile += gridDim.x * wpb)
-        step_tile(sm, d, prev, cur, tile, lane, bad);
+        step_tile(sm, sm.st[1].ci, d, prev, cur, tile, lane, bad);
     if (bad) sm.bad = ERR_FX_RANGE;
     __syncthreads();
-    if (cur >= 0) flush_stats(sm, d, cur);
+    if (cur >= 0) flush_stats(sm, sm.st[1].ci.K, d, cur);
     if (threadIdx.x == 0 && sm.bad) atomicOr(d.err, sm.bad);
 }
 
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(THREADS) k_sweep_end(Dev d, int prev)
     const Scalars sc = *d.sc;
     const int par = sc.parity;
     const bool writer = (blockIdx.x == 0);
-    if (threadIdx.x == 0) { sm.ai.active = 0; sm.ci.active = 0; sm.bad = 0; }
+    if (threadIdx.x == 0) { sm.ai.active = 0; sm.bad = 0; }
     {
         long long* tb = &sm.tab[0][0][0];
         for (int i = threadIdx.x; i < NMOM * 8; i += blockDim.x) tb[i] = 0;
@@ -133,11 +133,11 @@ __global__ void __launch_bounds__(THREADS) k_sweep_end(Dev d, int prev)
     __syncthreads();
     {
         const ForestDev& F = d.f[prev >= d.f[1].tree0 ? 1 : 0];
-        load_tree(&sm.tr, &d.trees[par][prev]);
-        if (threadIdx.x == 0) sm.prop = d.prop[prev];
+        load_tree(&sm.st[0].tr, &d.trees[par][prev]);
         __syncthreads();
-        decide(sm, d, F, prev, sc, writer);
-        if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.tr);
+        propose(sm, 0, d, F, prev, sc.sweep);
+        decide(sm, 0, d, F, prev, sc, writer);
+        if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.st[0].tr);
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -147,9 +147,10 @@ __global__ void __launch_bounds__(THREADS) k_sweep_end(Dev d, int prev)
     if (bad) sm.bad = ERR_FX_RANGE;
     __syncthreads();
     const long long* tb = &sm.tab[0][0][0];
+    long long* mom = d.mom + (size_t)(sc.sweep & 1u) * (2 * NMOM * 3);   // moment buffer of this sweep
     for (int i = threadIdx.x; i < NMOM * 8; i += blockDim.x) {
         const int m = i >> 3, g = (i >> 2) & 1, q = i & 3;
-        if (q >= 1 && tb[i] != 0) atomicAdd((unsigned long long*)&d.mom[(g * NMOM + m) * 3 + (q - 1)], (unsigned long long)tb[i]);
+        if (q >= 1 && tb[i] != 0) atomicAdd((unsigned long long*)&mom[(g * NMOM + m) * 3 + (q - 1)], (unsigned long long)tb[i]);
     }
     if (threadIdx.x == 0 && sm.bad) atomicOr(d.err, sm.bad);
 }
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(THREADS) k_scalars(Dev d)
     __shared__ Scalars scs;
     if (threadIdx.x == 0) scs = *d.sc;
     __syncthreads();
-    sweep_scalars(d, d.trees[scs.parity ^ 1], d.mom, red, &scs, true);
+    sweep_scalars(d, d.trees[scs.parity ^ 1], d.mom + (size_t)(scs.sweep & 1u) * (2 * NMOM * 3), red, &scs, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -269,7 +270,8 @@ __global__ void __launch_bounds__(256) k_finish(Dev d)
     finish_range(d, sc, i0, stride);
     const int64_t ntot = (int64_t)d.T * KEYS * 8;
     for (int64_t i = i0; i < ntot; i += stride) d.totals[i] = 0;
-    for (int64_t i = i0; i < 2 * NMOM * 3; i += stride) d.mom[i] = 0;
+    long long* mom_next = d.mom + (size_t)(sc.sweep & 1u) * (2 * NMOM * 3);   // sc.sweep is already the next sweep's index
+    for (int64_t i = i0; i < 2 * NMOM * 3; i += stride) mom_next[i] = 0;
 }
 
 // initial state [SURVEY A.2]: Gc = ybar (200 root leaves of ybar/200), Gm = 1 (50 root leaves of 1/50)
@@ -353,7 +355,9 @@ __global__ void __launch_bounds__(THREADS) k_op_stats(Dev d, int tree, int fores
         ld8_u8(d.slots + (int64_t)tree * d.n_pad + base, key);
         if (birth) {
             int bc[8];
-            ld8_bins(d.f[forest], var, d.n_pad, base, bc);
+            int w16;
+            const void* col = bin_column(d.f[forest], var, d.n_pad, w16);
+            ld8_bins(col, w16, base, bc);
 #pragma unroll
             for (int o = 0; o < 8; ++o) if (key[o] == sx && bc[o] > cut) key[o] = K - 1;
         }

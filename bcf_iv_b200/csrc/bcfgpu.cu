@@ -104,6 +104,8 @@ struct bcfgpu_handle {
     int grid_obs = 0, grid_fin = 0;
     int engine = BCFGPU_ENGINE_GRAPH;
     int coop_grid = 0;
+    int res_ntl = 0;                  // tiles per CTA of the shared-memory-resident kernel (0 = state in HBM)
+    size_t res_smem = 0;
     unsigned int* d_bar = nullptr;
     int64_t launches = 0;
     double last_ms = 0.0;
@@ -377,6 +379,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     free_list(h->allocs);
     free_list(h->run_allocs);
     h->has_data = false;
+    h->coop_grid = 0;
     h->n = n;
     int64_t ntrt = 0;
     for (int64_t i = 0; i < n; ++i) ntrt += z[i];
@@ -414,7 +417,6 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     DM(h, &h->d_tmp, (size_t)n_pad); DM(h, &h->d_tmp2, (size_t)n_pad);
     DM(h, &d.slots, (size_t)h->T * n_pad);
     DM(h, &d.trees[0], (size_t)h->T); DM(h, &d.trees[1], (size_t)h->T);
-    DM(h, &d.prop, (size_t)h->T);
     DM(h, &d.totals, (size_t)h->T * KEYS * 8);
     DM(h, &d.mom, (size_t)2 * 2 * NMOM * 3);
     DM(h, &d.sc, 1);
@@ -423,6 +425,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     DM(h, &d.trace_logr, (size_t)h->T);
     DM(h, &d.counters, 4);
     DM(h, &h->d_bar, 64);
+    if (getenv("BCFGPU_PROFILE")) { DM(h, &d.prof, 16); CK(cudaMemsetAsync(d.prof, 0, 128, h->stream)); }
     d.y = dy;
     CK(cudaMemsetAsync(d.totals, 0, (size_t)h->T * KEYS * 8 * 8, h->stream));
     CK(cudaMemsetAsync(d.mom, 0, 2 * 2 * NMOM * 3 * 8, h->stream));
@@ -430,7 +433,6 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     CK(cudaMemsetAsync(d.trace, 0, (size_t)h->T * 5 * 4, h->stream));
     CK(cudaMemsetAsync(d.trace_logr, 0, (size_t)h->T * 8, h->stream));
     CK(cudaMemsetAsync(d.counters, 0, 32, h->stream));
-    CK(cudaMemsetAsync(d.prop, 0, (size_t)h->T * sizeof(Proposal), h->stream));
     CK(cudaMemsetAsync(h->d_bar, 0, 64 * 4, h->stream));
     {
         std::vector<double> yi((size_t)n_pad, 0.0);
@@ -571,7 +573,7 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
     CK(cudaMemcpyAsync(d.sc, &sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
     h->nsaved = 0;
     int rc = BCFGPU_OK;
-    const bool persistent = (h->engine == BCFGPU_ENGINE_PERSISTENT) && h->nranks == 1;
+    const bool persistent = (h->engine == BCFGPU_ENGINE_PERSISTENT || h->engine == BCFGPU_ENGINE_PERSISTENT_HBM) && h->nranks == 1;
     if (!persistent && h->nranks == 1) { if ((rc = build_graph(h))) return rc; }
     CK(cudaEventRecord(h->ev0, h->stream));
     if (persistent) {
@@ -592,6 +594,16 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
     if ((rc = check_device_err(h))) return rc;
     CK(cudaMemcpy(&sc, d.sc, sizeof(sc), cudaMemcpyDeviceToHost));
     h->nsaved = sc.save_ctr;
+    if (d.prof) {   // BCFGPU_PROFILE=1: phase cycle counters of CTA 0 (persistent engine)
+        long long pc[8];
+        CK(cudaMemcpy(pc, d.prof, 64, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(d.prof, 0, 64));
+        const char* nm[8] = {"tiles", "flush", "barrier", "decide", "store", "load+propose", "epilogue", "-"};
+        long long tot = 0; for (int k = 0; k < 7; ++k) tot += pc[k];
+        fprintf(stderr, "[bcfgpu profile] %d sweeps:", total);
+        for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.1f%%(%.0f cyc/tree)", nm[k], 100.0 * pc[k] / (double)std::max(tot, 1ll), (double)pc[k] / ((double)total * h->T));
+        fprintf(stderr, "\n");
+    }
     return BCFGPU_OK;
 }
 
@@ -1032,10 +1044,28 @@ static int run_persistent(bcfgpu_handle* h, int total)
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
         if (!coop) return fail(BCFGPU_ERR_CUDA, "device does not support cooperative launch");
-        int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PTHREADS, 0));
-        if (per_sm < 1) return fail(BCFGPU_ERR_CUDA, "persistent kernel does not fit on an SM");
-        h->coop_grid = h->num_sms * std::min(per_sm, PERSIST_CTAS_PER_SM);
+        h->coop_grid = h->num_sms * PERSIST_CTAS_PER_SM;
+        // resident variant: does this CTA's share of the tiles fit in shared memory next to the static part?
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, k_resident));
+        int max_optin = 0;
+        CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        const int grid = std::min<int>(h->coop_grid, std::max(1, h->dev.n_tiles));
+        const int ntl_max = (h->dev.n_tiles + grid - 1) / grid;
+        const size_t need = (size_t)ntl_max * RES_BYTES_PER_TILE;
+        h->res_ntl = 0;
+        if (h->engine != BCFGPU_ENGINE_PERSISTENT_HBM && !getenv("BCFGPU_NO_RESIDENT") && need + fa.sharedSizeBytes + 1024 <= (size_t)max_optin) {
+            CK(cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resident, PTHREADS, need));
+            if (per_sm >= 1) { h->res_ntl = ntl_max; h->res_smem = need; }
+        }
+        if (h->res_ntl == 0) {
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PTHREADS, 0));
+            if (per_sm < 1) return fail(BCFGPU_ERR_CUDA, "persistent kernel does not fit on an SM");
+        }
+        h->coop_grid = grid;
     }
     // keep launches short enough to stay interruptible (R_CheckUserInterrupt between batches)
     const int batch = 256;
@@ -1044,8 +1074,14 @@ static int run_persistent(bcfgpu_handle* h, int total)
         Dev d = h->dev;
         unsigned int* bar = h->d_bar;
         CK(cudaMemsetAsync(bar, 0, 4, h->stream));
-        void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar};
-        CK(cudaLaunchCooperativeKernel((const void*)k_persistent, dim3(h->coop_grid), dim3(PTHREADS), args, 0, h->stream));
+        if (h->res_ntl > 0) {
+            int ntl = h->res_ntl;
+            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};
+            CK(cudaLaunchCooperativeKernel((const void*)k_resident, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
+        } else {
+            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar};
+            CK(cudaLaunchCooperativeKernel((const void*)k_persistent, dim3(h->coop_grid), dim3(PTHREADS), args, 0, h->stream));
+        }
         h->launches++;
     }
     return BCFGPU_OK;

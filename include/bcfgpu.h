@@ -51,7 +51,9 @@ typedef enum bcfgpu_status {
 typedef enum bcfgpu_engine {
     BCFGPU_ENGINE_AUTO = 0,
     BCFGPU_ENGINE_GRAPH = 1,       /* one kernel per tree, a sweep captured in a CUDA graph */
-    BCFGPU_ENGINE_PERSISTENT = 2   /* one cooperative kernel per batch of sweeps, grid barrier per tree */
+    BCFGPU_ENGINE_PERSISTENT = 2,  /* one cooperative kernel per batch of sweeps, grid barrier per tree; the
+                                      observation state lives in shared memory when the CTA's share fits */
+    BCFGPU_ENGINE_PERSISTENT_HBM = 3 /* same schedule, observation state kept in HBM/L2 (any n) */
 } bcfgpu_engine;
 
 /* Hyper-parameters of the sampler: bcf()'s arguments after the R wrapper's rescaling. */
