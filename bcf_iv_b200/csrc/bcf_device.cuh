@@ -45,6 +45,7 @@ struct __align__(16) TreeRec {
     uint8_t depth[MAXN];
     uint32_t heap[MAXN];                             // heap id: root 1, children 2i / 2i+1
     int16_t slot_node[MAXL];                         // node of each leaf slot
+    int32_t cnt0[MAXL], cnt1[MAXL];                  // observations in the leaf, control / treated (all shards)
     double mu[MAXL];                                 // leaf value per slot
 };
 static_assert(sizeof(TreeRec) % 16 == 0, "TreeRec must be copyable as uint4");
@@ -61,6 +62,13 @@ struct Proposal {
     double log_prior;    // log of the structural part of the MH ratio (alpha1)
     double log_u;        // log of the accept uniform: accept iff log_u < log ratio
     double z_extra[2];   // normals of the leaves a move would create: birth {left, right child}, death {merged leaf}
+};
+
+// Proposal of one tree for the coming sweep, made ahead of time (it depends only on the tree's structure and the
+// Philox counters) together with the standard normals of its current leaves.
+struct PropRec {
+    Proposal P;
+    double z[MAXL];
 };
 
 struct Scalars {
@@ -91,9 +99,11 @@ struct Dev {
     double nu, lambda, con_sd, mod_sd;
     ForestDev f[2];
     const double* y;
-    double *r, *Gc, *Gm;
+    long long* rfx;            // FULL residual y - allfit as a fixed-point integer (value * 2^44): updated exactly
+    double *Gc, *Gm;           // unscaled forest fits: sum of the mu / tau trees' leaf values
     uint8_t* slots;            // [T][n_pad]
     TreeRec* trees[2];
+    PropRec* proprec;          // [T] proposals of the sweep in progress
     long long* totals;         // [T][KEYS][2][4]  (count, limb0, limb1, limb2) by (key, group)
     long long* mom;            // [2 buffers][2 groups][NMOM][3]; sweep s uses buffer s & 1
     Scalars* sc;
@@ -173,8 +183,8 @@ __device__ inline double rng_gamma(Rng g, uint32_t sweep, uint32_t purpose, doub
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long to_fixed(double x, int& bad)
 {
-    // |x| < 2^18 keeps x * 2^44 inside int64 with headroom; NaN compares false and trips the flag
-    if (!(fabs(x) < 262144.0)) { bad = 1; return 0; }
+    // |x| < 2^15 keeps x * 2^44 below 2^59, so eight of them add up inside int64; NaN compares false and trips the flag
+    if (!(fabs(x) < 32768.0)) { bad = 1; return 0; }
     return __double2ll_rn(x * 17592186044416.0);
 }
 // exact value of limb sums (w0 + w1*2^21 + w2*2^42) / 2^44 rounded once to double
@@ -186,50 +196,105 @@ __host__ __device__ inline double limbs_to_double(long long w0, long long w1, lo
     return ((double)hi * 1099511627776.0 + (double)lo) * (1.0 / 17592186044416.0);
 }
 
-// Accumulate one warp tile (8 observations per lane) of (key, value) pairs into the CTA table
-// tab[key][group][4] = (count, limb0, limb1, limb2).  Keys >= K (padding) are ignored.
-// K <= KREG: per-key predicated register sums + warp REDUX, four shared atomics per key per warp.
-// K >  KREG: one shared atomic set per observation (addresses are spread when there are many leaves).
-__device__ __forceinline__ void accum_tile(long long (*tab)[2][4], const int (&key)[8], const double (&val)[8],
-                                           int g, int K, int lane, int& bad)
+// CTA-level statistics table.  There is no native 64-bit shared-memory add on sm_100 (atomicAdd on a shared
+// long long compiles to a LDS + ATOMS.CAST.SPIN retry loop, which collapses under contention), so:
+//   K <= KREG keys : every warp owns a private (key, group, 4-word) table and adds its REDUX results with plain
+//                    read-modify-writes; the tables are summed when the CTA flushes;
+//   K >  KREG keys : one table of 32-bit words per (key, group): count + four 16-bit limbs, native ATOMS.ADD.32
+//                    (addresses are spread when a tree has many leaves).
+constexpr int NWARP_MAX = 16;
+union StatTab {
+    long long w[NWARP_MAX][KREG][2][4];     // (count, limb0, limb1, limb2), 21-bit limbs
+    unsigned int d[KEYS][2][8];             // (count, m0, m1, m2, m3), 16-bit limbs; 3 words of padding
+};
+constexpr int STATTAB_WORDS64 = (int)(sizeof(StatTab) / 8);
+constexpr int ROWSUM_WORDS = KREG * 8;   // (key, group, word) sums over the warps' tables
+
+// split a partial sum (|s| < 2^63) into the three words of the global representation and add them, reduced over the
+// warp, to row `row` of the warp's private table
+__device__ __forceinline__ void warp_add_limbs(StatTab& tab, int warp, int row, int g, int lane, long long s, int cnt)
 {
-    int l0[8], l1[8], l2[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-        const long long v = to_fixed(val[o], bad);
-        l0[o] = (int)(v & 0x1FFFFF);
-        l1[o] = (int)((v >> LIMB_BITS) & 0x1FFFFF);
-        l2[o] = (int)(v >> (2 * LIMB_BITS));
+    int l0 = (int)(s & 0x1FFFFF), l1 = (int)((s >> LIMB_BITS) & 0x1FFFFF), l2 = (int)(s >> (2 * LIMB_BITS));
+    l0 = __reduce_add_sync(0xffffffffu, l0);
+    l1 = __reduce_add_sync(0xffffffffu, l1);
+    l2 = __reduce_add_sync(0xffffffffu, l2);
+    if (lane < 4) {
+        const long long v = lane == 0 ? cnt : lane == 1 ? l0 : lane == 2 ? l1 : l2;
+        tab.w[warp][row][g][lane] += v;
     }
+}
+
+// Accumulate one warp tile (8 observations per lane) of (key, fixed-point residual) pairs.  Keys >= K (padding,
+// residual 0) are ignored.
+//   K <= KREG: row 0 of the warp's table receives the TOTAL over all keys, rows 1..K-1 their own sums (key 0 is
+//              recovered by subtraction when the CTA flushes: integer sums are exact).  Only the last key of a
+//              birth proposal (the would-be right child) needs its count; every other count is cached in the tree.
+//   K >  KREG: native 32-bit shared atomics per observation.
+__device__ __forceinline__ void accum_tile(StatTab& tab, const int (&key)[8], const long long (&R)[8], int g, int K,
+                                           bool count_last, int lane, int warp)
+{
     if (K <= KREG) {
-        for (int k = 0; k < K; ++k) {
-            int c = 0, a0 = 0, a1 = 0, a2 = 0;
+        long long tot = 0;
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                const bool m = (key[o] == k);
-                c += m ? 1 : 0; a0 += m ? l0[o] : 0; a1 += m ? l1[o] : 0; a2 += m ? l2[o] : 0;
-            }
-            c = __reduce_add_sync(0xffffffffu, c);
-            a0 = __reduce_add_sync(0xffffffffu, a0);
-            a1 = __reduce_add_sync(0xffffffffu, a1);
-            a2 = __reduce_add_sync(0xffffffffu, a2);
-            if (lane < 4 && c != 0) {
-                const long long v = lane == 0 ? c : lane == 1 ? a0 : lane == 2 ? a1 : a2;
-                atomicAdd((unsigned long long*)&tab[k][g][lane], (unsigned long long)v);
-            }
+        for (int o = 0; o < 8; ++o) tot += R[o];
+        warp_add_limbs(tab, warp, 0, g, lane, tot, 0);
+        int clast = 0;
+        if (count_last) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o) clast += (key[o] == K - 1) ? 1 : 0;
+            clast = __reduce_add_sync(0xffffffffu, clast);
         }
+        for (int k = 1; k < K; ++k) {
+            long long s = 0;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) s += (key[o] == k) ? R[o] : 0ll;
+            warp_add_limbs(tab, warp, k, g, lane, s, (k == K - 1) ? clast : 0);
+        }
+        __syncwarp();
     } else {
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
             const int k = key[o];
             if (k < K) {
-                atomicAdd((unsigned long long*)&tab[k][g][0], 1ull);
-                atomicAdd((unsigned long long*)&tab[k][g][1], (unsigned long long)(long long)l0[o]);
-                atomicAdd((unsigned long long*)&tab[k][g][2], (unsigned long long)(long long)l1[o]);
-                atomicAdd((unsigned long long*)&tab[k][g][3], (unsigned long long)(long long)l2[o]);
+                const long long v = R[o];
+                atomicAdd(&tab.d[k][g][0], 1u);
+                atomicAdd(&tab.d[k][g][1], (unsigned int)(v & 0xFFFF));
+                atomicAdd(&tab.d[k][g][2], (unsigned int)((v >> 16) & 0xFFFF));
+                atomicAdd(&tab.d[k][g][3], (unsigned int)((v >> 32) & 0xFFFF));
+                atomicAdd(&tab.d[k][g][4], (unsigned int)(int)(v >> 48));
             }
         }
     }
+}
+// word q (0 count, 1..3 the 21-bit limbs of the global representation) of entry (k, g), summed over the CTA
+__device__ __forceinline__ long long stat_word(const StatTab& tab, int K, int nwarps, int k, int g, int q)
+{
+    if (K <= KREG) {
+        long long v = 0;
+        if (k == 0) {
+            if (q == 0) return 0;
+            for (int w = 0; w < nwarps; ++w) {
+                v += tab.w[w][0][g][q];
+                for (int kk = 1; kk < K; ++kk) v -= tab.w[w][kk][g][q];
+            }
+        } else {
+            for (int w = 0; w < nwarps; ++w) v += tab.w[w][k][g][q];
+        }
+        return v;
+    }
+    const unsigned int* e = tab.d[k][g];
+    if (q == 0) return (long long)e[0];
+    const __int128 V = (__int128)e[1] + ((__int128)e[2] << 16) + ((__int128)e[3] << 32) + ((__int128)(int)e[4] << 48);
+    if (q == 1) return (long long)(V & 0x1FFFFF);
+    if (q == 2) return (long long)((V >> LIMB_BITS) & 0x1FFFFF);
+    return (long long)(V >> (2 * LIMB_BITS));
+}
+// plain sum over the warps' tables (moments pass: rows are independent quantities)
+__device__ __forceinline__ long long table_word(const StatTab& tab, int nwarps, int row, int g, int q)
+{
+    long long v = 0;
+    for (int w = 0; w < nwarps; ++w) v += tab.w[w][row][g][q];
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -266,6 +331,24 @@ __device__ __forceinline__ void st8_f64(double* p, const double (&in)[8])
 {
 #pragma unroll
     for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(p)[j] = make_double2(in[2 * j], in[2 * j + 1]);
+}
+__device__ __forceinline__ void ld8_i64(const long long* p, long long (&out)[8])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const longlong2 v = reinterpret_cast<const longlong2*>(p)[j];
+        out[2 * j] = v.x; out[2 * j + 1] = v.y;
+    }
+}
+__device__ __forceinline__ void st8_i64(long long* p, const long long (&in)[8])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) reinterpret_cast<longlong2*>(p)[j] = make_longlong2(in[2 * j], in[2 * j + 1]);
+}
+// the residual of one observation, re-derived from the fits: the ONE expression every engine uses
+__device__ __forceinline__ long long resync_fx(double y, double ms, double gc, double b, double gm, int& bad)
+{
+    return to_fixed(y - (ms * gc + b * gm), bad);
 }
 // bins of one variable (column base pointer resolved at proposal time) for 8 observations starting at `base`
 __device__ __forceinline__ void ld8_bins(const void* col, int is16, int64_t base, int (&out)[8])

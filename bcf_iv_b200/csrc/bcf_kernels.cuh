@@ -4,6 +4,13 @@
 
 namespace bcf {
 
+// StepShared is larger than the 48 KB static limit: the sampler kernels take it as dynamic shared memory
+// (launch with STEP_SMEM_BYTES, after cudaFuncSetAttribute(MaxDynamicSharedMemorySize)).
+constexpr size_t STEP_SMEM_BYTES = (sizeof(StepShared) + 15) / 16 * 16;
+#define BCF_STEP_SMEM(sm)                                         \
+    extern __shared__ __align__(16) unsigned char bcf_dyn_smem[]; \
+    StepShared& sm = *reinterpret_cast<StepShared*>(bcf_dyn_smem)
+
 // ---------------------------------------------------------------------------------------------
 // K0: bin one column.  out = #{c : cuts[c] <= x}  (upper bound), so  x < cuts[c]  <=>  out <= c.
 // Written at the observation's internal (treated-first, padded) position.
@@ -82,20 +89,28 @@ __global__ void __launch_bounds__(256) k_assign(Dev d, int tree, int forest, con
 // proposes for tree j, then makes ONE pass over the observations that applies tree j-1's update to the
 // residual / leaf cache and accumulates tree j's sufficient statistics.
 // ---------------------------------------------------------------------------------------------
+// proposals of the coming sweep, one CTA per tree (they depend only on the structures and the Philox counters)
+__global__ void __launch_bounds__(THREADS) k_propose_all(Dev d)
+{
+    BCF_STEP_SMEM(sm);
+    const Scalars sc = *d.sc;
+    propose_range(sm, d, d.trees[sc.parity], sc.sweep, blockIdx.x, gridDim.x, -1, 0);
+}
+
 __global__ void __launch_bounds__(THREADS) k_tree_step(Dev d, int prev, int cur)
 {
-    __shared__ StepShared sm;
+    BCF_STEP_SMEM(sm);
     const Scalars sc = *d.sc;
     const int par = sc.parity;
     const bool writer = (blockIdx.x == 0);
     if (threadIdx.x == 0) { sm.ai.active = 0; sm.st[1].ci.active = 0; sm.bad = 0; }
     __syncthreads();
     if (prev >= 0) {
-        // the proposal of tree prev is a pure function of its structure and the Philox counters: replay it
         const ForestDev& F = d.f[prev >= d.f[1].tree0 ? 1 : 0];
         load_tree(&sm.st[0].tr, &d.trees[par][prev]);
         __syncthreads();
-        propose(sm, 0, d, F, prev, sc.sweep);
+        fetch_proposal(sm, 0, d, prev, sm.st[0].tr.nleaves);
+        __syncthreads();
         decide(sm, 0, d, F, prev, sc, writer);
         if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.st[0].tr);
         __syncthreads();
@@ -104,38 +119,35 @@ __global__ void __launch_bounds__(THREADS) k_tree_step(Dev d, int prev, int cur)
         const int fc = cur >= d.f[1].tree0 ? 1 : 0;
         load_tree(&sm.st[1].tr, &d.trees[par][cur]);
         __syncthreads();
-        propose(sm, 1, d, d.f[fc], cur, sc.sweep);
+        fetch_proposal(sm, 1, d, cur, sm.st[1].tr.nleaves);
+        __syncthreads();
         begin_stats(sm, 1, fc, sc);
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    int bad = 0;
     for (int tile = blockIdx.x * wpb + wib; tile < d.n_tiles; tile += gridDim.x * wpb)
-        step_tile(sm, sm.st[1].ci, d, prev, cur, tile, lane, bad);
-    if (bad) sm.bad = ERR_FX_RANGE;
+        step_tile(sm, sm.st[1].ci, d, prev, cur, tile, lane);
     __syncthreads();
     if (cur >= 0) flush_stats(sm, sm.st[1].ci.K, d, cur);
     if (threadIdx.x == 0 && sm.bad) atomicOr(d.err, sm.bad);
 }
 
-// Sweep epilogue, observation pass (see refit_tile)
+// Sweep epilogue, observation pass (see last_tile)
 __global__ void __launch_bounds__(THREADS) k_sweep_end(Dev d, int prev)
 {
-    __shared__ StepShared sm;
+    BCF_STEP_SMEM(sm);
     const Scalars sc = *d.sc;
     const int par = sc.parity;
     const bool writer = (blockIdx.x == 0);
     if (threadIdx.x == 0) { sm.ai.active = 0; sm.bad = 0; }
-    {
-        long long* tb = &sm.tab[0][0][0];
-        for (int i = threadIdx.x; i < NMOM * 8; i += blockDim.x) tb[i] = 0;
-    }
+    moments_begin(sm);
     __syncthreads();
     {
         const ForestDev& F = d.f[prev >= d.f[1].tree0 ? 1 : 0];
         load_tree(&sm.st[0].tr, &d.trees[par][prev]);
         __syncthreads();
-        propose(sm, 0, d, F, prev, sc.sweep);
+        fetch_proposal(sm, 0, d, prev, sm.st[0].tr.nleaves);
+        __syncthreads();
         decide(sm, 0, d, F, prev, sc, writer);
         if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.st[0].tr);
         __syncthreads();
@@ -143,15 +155,10 @@ __global__ void __launch_bounds__(THREADS) k_sweep_end(Dev d, int prev)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     int bad = 0;
     for (int tile = blockIdx.x * wpb + wib; tile < d.n_tiles; tile += gridDim.x * wpb)
-        refit_tile(sm, d, prev, d.trees[par ^ 1], tile, lane, bad);
+        last_tile(sm, d, prev, tile, lane, bad);
     if (bad) sm.bad = ERR_FX_RANGE;
     __syncthreads();
-    const long long* tb = &sm.tab[0][0][0];
-    long long* mom = d.mom + (size_t)(sc.sweep & 1u) * (2 * NMOM * 3);   // moment buffer of this sweep
-    for (int i = threadIdx.x; i < NMOM * 8; i += blockDim.x) {
-        const int m = i >> 3, g = (i >> 2) & 1, q = i & 3;
-        if (q >= 1 && tb[i] != 0) atomicAdd((unsigned long long*)&mom[(g * NMOM + m) * 3 + (q - 1)], (unsigned long long)tb[i]);
-    }
+    moments_flush(sm, d.mom + (size_t)(sc.sweep & 1u) * (2 * NMOM * 3));   // moment buffer of this sweep
     if (threadIdx.x == 0 && sm.bad) atomicOr(d.err, sm.bad);
 }
 
@@ -246,6 +253,7 @@ __global__ void __launch_bounds__(THREADS) k_scalars(Dev d)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void finish_range(const Dev& d, const Scalars& sc, int64_t i0, int64_t stride)
 {
+    int bad = 0;
     const double ms = sc.mscale, b1 = sc.bscale1, b0 = sc.bscale0;
     const int64_t trt_end = (int64_t)d.trt_tiles * TILE;
     const int row = sc.save_row;
@@ -253,7 +261,7 @@ __device__ __forceinline__ void finish_range(const Dev& d, const Scalars& sc, in
         const double gc = d.Gc[i], gm = d.Gm[i];
         const double b = i < trt_end ? b1 : b0;
         const double mu = ms * gc, yh = mu + b * gm;
-        d.r[i] = d.y[i] - yh;
+        d.rfx[i] = resync_fx(d.y[i], ms, gc, b, gm, bad);
         if (row >= 0) {
             const double tau = (b1 - b0) * gm;
             d.tau_sum[i] += tau; d.tau_sq[i] += tau * tau; d.mu_sum[i] += mu; d.yhat_sum[i] += yh;
@@ -262,6 +270,7 @@ __device__ __forceinline__ void finish_range(const Dev& d, const Scalars& sc, in
             if (d.draws_yhat) d.draws_yhat[(int64_t)row * d.n_pad + i] = yh;
         }
     }
+    if (bad) atomicOr(d.err, ERR_FX_RANGE);
 }
 __global__ void __launch_bounds__(256) k_finish(Dev d)
 {
@@ -283,7 +292,9 @@ __global__ void k_init_state(Dev d, const int32_t* __restrict__ orig, double gc0
         const bool real = orig[i] >= 0;
         const double gc = real ? gc0 : 0.0, gm = real ? gm0 : 0.0;
         d.Gc[i] = gc; d.Gm[i] = gm;
-        d.r[i] = real ? d.y[i] - sc.mscale * gc - (i < trt_end ? sc.bscale1 : sc.bscale0) * gm : 0.0;
+        int bad = 0;
+        d.rfx[i] = real ? resync_fx(d.y[i], sc.mscale, gc, i < trt_end ? sc.bscale1 : sc.bscale0, gm, bad) : 0ll;
+        if (bad) atomicOr(d.err, ERR_FX_RANGE);
         d.tau_sum[i] = d.tau_sq[i] = d.mu_sum[i] = d.yhat_sum[i] = 0.0;
         for (int t = 0; t < d.T; ++t) d.slots[(int64_t)t * d.n_pad + i] = real ? 0 : PAD_SLOT;
     }
@@ -301,10 +312,21 @@ __global__ void k_refit_all(Dev d, const TreeRec* trees)
                 if (s != PAD_SLOT) G[f] += trees[j].mu[s];
             }
         d.Gc[i] = G[0]; d.Gm[i] = G[1];
-        d.r[i] = d.y[i] - sc.mscale * G[0] - (i < trt_end ? sc.bscale1 : sc.bscale0) * G[1];
+        int bad = 0;
+        d.rfx[i] = resync_fx(d.y[i], sc.mscale, G[0], i < trt_end ? sc.bscale1 : sc.bscale0, G[1], bad);
+        if (bad) atomicOr(d.err, ERR_FX_RANGE);
     }
 }
 
+// per-leaf observation counts of one tree from its cached slots: out[slot][0 control / 1 treated]
+__global__ void k_count_leaves(Dev d, int tree, long long* out)
+{
+    const int64_t trt_end = (int64_t)d.trt_tiles * TILE;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        const int s = d.slots[(int64_t)tree * d.n_pad + i];
+        if (s != PAD_SLOT) atomicAdd((unsigned long long*)&out[2 * s + (i < trt_end ? 1 : 0)], 1ull);
+    }
+}
 // gather an internal-order vector back to the caller's row order; which: 0 copy, 1 mean (x/ns), 2 variance
 __global__ void k_unpermute(const double* __restrict__ a, const double* __restrict__ b, const int32_t* __restrict__ pos,
                             int64_t n, double ns, int which, double scale_trt, double scale_ctl, int64_t trt_end,
@@ -341,17 +363,20 @@ __global__ void k_leaf_heap(Dev d, int tree, const TreeRec* trees, const int32_t
 __global__ void __launch_bounds__(THREADS) k_op_stats(Dev d, int tree, int forest, const double* __restrict__ r,
                                                       int K, int birth, int sx, int var, int cut, long long* out)
 {
-    __shared__ long long tab[KEYS][2][4];
-    for (int i = threadIdx.x; i < K * 8; i += blockDim.x) (&tab[0][0][0])[i] = 0;
+    __shared__ StatTab tab;
+    for (int i = threadIdx.x; i < STATTAB_WORDS64; i += blockDim.x) reinterpret_cast<long long*>(&tab)[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     int bad = 0;
     for (int tile = blockIdx.x * wpb + wib; tile < d.n_tiles; tile += gridDim.x * wpb) {
         const int64_t base = (int64_t)tile * TILE + lane * 8;
         const int g = tile < d.trt_tiles ? 1 : 0;
-        double rv[8];
+        double rd[8];
+        long long rv[8];
         int key[8];
-        ld8_f64(r + base, rv);
+        ld8_f64(r + base, rd);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) rv[o] = to_fixed(rd[o], bad);
         ld8_u8(d.slots + (int64_t)tree * d.n_pad + base, key);
         if (birth) {
             int bc[8];
@@ -361,11 +386,11 @@ __global__ void __launch_bounds__(THREADS) k_op_stats(Dev d, int tree, int fores
 #pragma unroll
             for (int o = 0; o < 8; ++o) if (key[o] == sx && bc[o] > cut) key[o] = K - 1;
         }
-        accum_tile(tab, key, rv, g, K, lane, bad);
+        accum_tile(tab, key, rv, g, K, true, lane, wib);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < K * 8; i += blockDim.x) {
-        const long long v = (&tab[0][0][0])[i];
+        const long long v = stat_word(tab, K, wpb, i >> 3, (i >> 2) & 1, i & 3);
         if (v != 0) atomicAdd((unsigned long long*)&out[i], (unsigned long long)v);
     }
     if (bad) atomicOr(d.err, ERR_FX_RANGE);

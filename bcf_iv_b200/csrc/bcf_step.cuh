@@ -22,15 +22,16 @@ struct ApplyInfo {
     int32_t is16;
     int32_t forest;      // forest of the previous tree
     const void* bins;    // column of the birth variable
-    double dlt_right;
-    double s1, s0;       // scale of the forest's fit for treated / control rows (mscale or bscale1/bscale0)
+    double dlt_right;    // change of the leaf value for observations moving to the new right child
+    long long dfx_right[2];   // the same, scaled by the forest's scale and in fixed point, control / treated rows
+    int32_t uniform;     // the tree had one leaf and keeps it: every observation gets dlt[0] / dfx[g][0]
+    int32_t pad_;
 };
 
 struct CurInfo {
     int32_t active, K;   // K = number of keys = nleaves (+1 for a birth proposal)
     int32_t birth, sx, cut, is16, forest, new_slot;
     const void* bins;
-    double s1, s0;       // scale of this forest's fit for treated / control rows
 };
 
 // A tree in flight: its structure, its proposal, the leaf normals and the statistics-pass set-up.  Two stages, so
@@ -44,9 +45,13 @@ struct TreeStage {
 
 struct StepShared {
     TreeStage st[2];
-    double cnt[KEYS], sphi[KEYS], sphir[KEYS];
+    double cnt[KEYS + 1], sphi[KEYS + 1], sphir[KEYS + 1];   // entry KEYS: the pair a move merges / splits, pooled
+    double pinv[KEYS + 1], plog[KEYS + 1], pmean[KEYS + 1], psd[KEYS + 1];   // 1/prec, log prec, posterior mean, sd
+    double log_tau;
     double mu_old[MAXL], mu_new[MAXL];
-    double dlt[KEYS];
+    double dlt[KEYS];              // change of the leaf value per OLD slot
+    long long dfx[2][KEYS];        // scale * dlt in fixed point, control / treated rows: what the residual loses
+    double nc1[KEYS + 1], nc0[KEYS + 1];   // counts per key, treated / control
     uint8_t remap[MAXL];
     int32_t ngood[MAXL];
     uint32_t lkey[MAXL];
@@ -55,7 +60,9 @@ struct StepShared {
     ApplyInfo ai;
     int32_t accepted;
     int32_t bad;
-    long long tab[KEYS][2][4];
+    StatTab tab;
+    long long rowsum[ROWSUM_WORDS];
+    long long tot[KEYS * 8];       // reduced statistics of the tree being decided, staged from L2
 };
 
 __device__ inline void load_tree(TreeRec* dst, const TreeRec* src)
@@ -195,20 +202,43 @@ __device__ inline void propose(StepShared& sm, int stage, const Dev& d, const Fo
     __syncthreads();
 }
 
-// lil(l) + lil(r) - lil(l+r) with one logarithm (bcf's three lil calls fused) [SURVEY A.3]
-__device__ __forceinline__ double lil_split_gain(double pl, double rl, double pr, double rr, double tau, double log_tau)
+// publish a staged proposal (and leaf normals) to HBM / fetch it back into a stage
+__device__ inline void publish_proposal(const StepShared& sm, int stage, const Dev& d, int tree)
 {
-    const double a = 1.0 / (tau * tau);
-    const double dl = a + pl, dr = a + pr, dt = a + (pl + pr);
-    const double st = rl + rr;
-    return -log_tau - 0.5 * log(dl * dr / dt) + 0.5 * (rl * rl / dl + rr * rr / dr - st * st / dt);
+    const TreeStage& S = sm.st[stage];
+    PropRec* R = d.proprec + tree;
+    const int t = threadIdx.x;
+    if (t == 0) R->P = S.prop;
+    if (t >= 32 && t - 32 < S.tr.nleaves) R->z[t - 32] = S.z[t - 32];
+}
+__device__ inline void fetch_proposal(StepShared& sm, int stage, const Dev& d, int tree, int nleaves)
+{
+    TreeStage& S = sm.st[stage];
+    const PropRec* R = d.proprec + tree;
+    const int t = threadIdx.x;
+    if (t < (int)(sizeof(Proposal) / 8)) reinterpret_cast<long long*>(&S.prop)[t] = __ldcg(reinterpret_cast<const long long*>(&R->P) + t);
+    if (t >= 32 && t - 32 < nleaves) S.z[t - 32] = __ldcg(&R->z[t - 32]);
 }
 
 // ---------------------------------------------------------------------------------------------
-// decide(): given the reduced statistics of tree `tree` (d.totals) and its proposal (sm.prop), take the MH
-// decision, update the structure in sm.tr, redraw every leaf value and build the apply tables.
+// decide(): given the reduced statistics of tree `tree` (d.totals) and its proposal (stage.prop), take the MH
+// decision, update the structure in stage.tr, redraw every leaf value and build the apply tables.
 // bcf's bd() likelihood half + drmu() [bcf-recall, SURVEY A.3 steps 2-3].  `writer` CTA records the trace.
+//
+// Phase 1 (one thread per key, plus one for the pooled pair): statistics -> precision, its log and reciprocal,
+// posterior mean and sd.  Phase 2 (thread 0): compare, update the structure.  Phase 3 (one thread per leaf):
+// mu = mean + z * sd.  The critical path holds one L2 round trip, one log, one division and one sqrt.
 // ---------------------------------------------------------------------------------------------
+// statistics of one key: counts (cached in the tree, or reduced for the would-be right child of a birth) and the
+// reduced fixed-point residual sums -> (count, sum phi, sum phi * R) of bcf's sinfo
+__device__ __forceinline__ void key_raw(const long long* tot, int key, double& S1, double& S0, double& c1, double& c0)
+{
+    const long long* q = tot + key * 8;   // [control: count, limb0, limb1, limb2][treated: ...]
+    S1 = limbs_to_double(q[5], q[6], q[7]);
+    S0 = limbs_to_double(q[1], q[2], q[3]);
+    c1 = (double)q[4]; c0 = (double)q[0];
+}
+
 __device__ inline void decide(StepShared& sm, int stage, const Dev& d, const ForestDev& F, int tree, const Scalars& sc,
                               bool writer)
 {
@@ -220,79 +250,111 @@ __device__ inline void decide(StepShared& sm, int stage, const Dev& d, const For
     const int K = L + (P.move == 1 ? 1 : 0);
     const bool is_con = F.is_con != 0;
     const double s1 = is_con ? sc.mscale : sc.bscale1, s0 = is_con ? sc.mscale : sc.bscale0;
-    const double s2 = sc.sigma * sc.sigma;
-    const double phi1 = s1 * s1 / s2, phi0 = s0 * s0 / s2;
     const double tau = is_con ? sc.tau_con : sc.tau_mod;
+    // the two keys a move pools: birth (leaf part staying left, would-be right child), death (the two children)
+    const int pa = P.slot, pb = (P.move == 1) ? L : P.slot_b;
 
-    if (t < K) {
-        const long long* q = d.totals + ((size_t)tree * KEYS + t) * 8;
-        // reduced by integer atomics in L2: read there, never from a stale L1 line
-        const longlong2 c0 = __ldcg(reinterpret_cast<const longlong2*>(q));        // control: count, limb0
-        const longlong2 c1 = __ldcg(reinterpret_cast<const longlong2*>(q) + 1);    //          limb1, limb2
-        const longlong2 t0 = __ldcg(reinterpret_cast<const longlong2*>(q) + 2);    // treated
-        const longlong2 t1 = __ldcg(reinterpret_cast<const longlong2*>(q) + 3);
-        const double n1 = (double)t0.x, n0 = (double)c0.x;
-        const double S1 = limbs_to_double(t0.y, t1.x, t1.y);
-        const double S0 = limbs_to_double(c0.y, c1.x, c1.y);
-        const double mo = (t < L) ? tr.mu[t] : tr.mu[P.slot];
-        sm.cnt[t] = n1 + n0;
-        sm.sphi[t] = n1 * phi1 + n0 * phi0;
-        sm.sphir[t] = phi1 * (S1 / s1 + n1 * mo) + phi0 * (S0 / s0 + n0 * mo);
+    // reduced by integer atomics in L2: stage them with ONE round trip, straight from L2 (never a stale L1 line)
+    {
+        const long long* q = d.totals + (size_t)tree * KEYS * 8;
+        for (int i = t; i < K * 8; i += blockDim.x) sm.tot[i] = __ldcg(q + i);
     }
     if (t < MAXL) { sm.remap[t] = (uint8_t)t; if (t < L) sm.mu_old[t] = tr.mu[t]; }
+    __syncthreads();
+
+    // Phase 1.  Keys: leaf slots 0..L-1 (for a birth the proposed leaf's key holds the part that stays LEFT) and
+    // key L = the would-be right child.  Thread KEYS handles the pooled pair of the move (sum of its two keys).
+    if (t < K || (t == KEYS && P.move != 0)) {
+        const double s2 = sc.sigma * sc.sigma;
+        const double phi1 = s1 * s1 / s2, phi0 = s0 * s0 / s2;
+        const double a = 1.0 / (tau * tau);
+        double n1 = 0.0, n0 = 0.0, sphi = 0.0, sphir = 0.0;
+        const int nk = (t < K) ? 1 : 2;
+        for (int q = 0; q < nk; ++q) {
+            const int key = (t < K) ? t : (q == 0 ? pa : pb);
+            double S1, S0, c1, c0, k1, k0, mo;
+            key_raw(sm.tot, key, S1, S0, c1, c0);
+            if (key < L) {
+                k1 = (double)tr.cnt1[key]; k0 = (double)tr.cnt0[key]; mo = tr.mu[key];
+                if (P.move == 1 && key == P.slot) {      // left part = leaf - right part
+                    double R1, R0, r1, r0;
+                    key_raw(sm.tot, L, R1, R0, r1, r0);
+                    k1 -= r1; k0 -= r0;
+                }
+            } else { k1 = c1; k0 = c0; mo = tr.mu[P.slot]; }
+            n1 += k1; n0 += k0;
+            sphi += k1 * phi1 + k0 * phi0;
+            sphir += phi1 * (S1 / s1 + k1 * mo) + phi0 * (S0 / s0 + k0 * mo);
+        }
+        const double prec = a + sphi, inv = 1.0 / prec;
+        sm.nc1[t] = n1; sm.nc0[t] = n0;
+        sm.cnt[t] = n1 + n0; sm.sphi[t] = sphi; sm.sphir[t] = sphir;
+        sm.pinv[t] = inv; sm.plog[t] = log(prec); sm.pmean[t] = sphir * inv; sm.psd[t] = sqrt(inv);
+    }
+    if (t == KEYS + 1) sm.log_tau = log(tau);
     __syncthreads();
 
     if (t == 0) {
         int accepted = 0;
         double logr = nan("");
-        const double log_tau = log(tau);
-        if (P.move == 1) {
-            const int sx = P.slot, kr = L;
-            if (sm.cnt[sx] >= d.min_leaf && sm.cnt[kr] >= d.min_leaf) {
-                logr = P.log_prior + lil_split_gain(sm.sphi[sx], sm.sphir[sx], sm.sphi[kr], sm.sphir[kr], tau, log_tau);
+        if (P.move != 0) {
+            // lil(a) + lil(b) - lil(a+b), weighted form [SURVEY A.3]
+            const double gain = -sm.log_tau - 0.5 * (sm.plog[pa] + sm.plog[pb] - sm.plog[KEYS])
+                              + 0.5 * (sm.sphir[pa] * sm.sphir[pa] * sm.pinv[pa] + sm.sphir[pb] * sm.sphir[pb] * sm.pinv[pb]
+                                       - sm.sphir[KEYS] * sm.sphir[KEYS] * sm.pinv[KEYS]);
+            if (P.move == 1) {
+                if (sm.cnt[pa] >= d.min_leaf && sm.cnt[pb] >= d.min_leaf) {
+                    logr = P.log_prior + gain;
+                    accepted = (P.log_u < logr) ? 1 : 0;
+                }
+            } else {
+                logr = P.log_prior - gain;
                 accepted = (P.log_u < logr) ? 1 : 0;
             }
+        }
+        if (P.move == 1) {
+            const int sx = pa, kr = pb;
             if (accepted) {
-                const int nx = P.node, a = tr.nnodes, b = tr.nnodes + 1;
-                tr.left[nx] = (int16_t)a; tr.right[nx] = (int16_t)b;
+                const int nx = P.node, na = tr.nnodes, nb = tr.nnodes + 1;
+                tr.left[nx] = (int16_t)na; tr.right[nx] = (int16_t)nb;
                 tr.var[nx] = (uint16_t)P.var; tr.cut[nx] = (uint16_t)P.cut;
                 for (int q = 0; q < 2; ++q) {
-                    const int ch = q ? b : a;
+                    const int ch = q ? nb : na;
                     tr.parent[ch] = (int16_t)nx; tr.left[ch] = tr.right[ch] = -1;
                     tr.var[ch] = tr.cut[ch] = 0xFFFF;
                     tr.depth[ch] = tr.depth[nx] + 1;
                     tr.heap[ch] = 2u * tr.heap[nx] + (uint32_t)q;
                 }
-                tr.node_slot[a] = (uint8_t)sx; tr.slot_node[sx] = (int16_t)a;
-                tr.node_slot[b] = (uint8_t)kr; tr.slot_node[kr] = (int16_t)b;
+                tr.node_slot[na] = (uint8_t)sx; tr.slot_node[sx] = (int16_t)na;
+                tr.node_slot[nb] = (uint8_t)kr; tr.slot_node[kr] = (int16_t)nb;
                 tr.nnodes += 2; tr.nleaves = L + 1;
                 S.z[sx] = P.z_extra[0]; S.z[kr] = P.z_extra[1];
-            } else {   // the leaf stays whole: fold the would-be right child back in
-                sm.cnt[sx] += sm.cnt[kr]; sm.sphi[sx] += sm.sphi[kr]; sm.sphir[sx] += sm.sphir[kr];
+                // cached counts: entries sx (left part) and kr (right child) are already what phase 1 computed
+            } else {   // the leaf stays whole: it is the pooled pair
+                sm.nc1[sx] = sm.nc1[KEYS]; sm.nc0[sx] = sm.nc0[KEYS];
+                sm.pmean[sx] = sm.pmean[KEYS]; sm.psd[sx] = sm.psd[KEYS];
             }
-        } else if (P.move == 2) {
-            const int sa = P.slot, sb = P.slot_b;
-            logr = P.log_prior - lil_split_gain(sm.sphi[sa], sm.sphir[sa], sm.sphi[sb], sm.sphir[sb], tau, log_tau);
-            accepted = (P.log_u < logr) ? 1 : 0;
-            if (accepted) {
-                const int nx = P.node, na = tr.left[nx], nb = tr.right[nx];
-                tr.left[nx] = tr.right[nx] = -1; tr.var[nx] = tr.cut[nx] = 0xFFFF;
-                tr.node_slot[nx] = (uint8_t)sa; tr.slot_node[sa] = (int16_t)nx;
-                sm.cnt[sa] += sm.cnt[sb]; sm.sphi[sa] += sm.sphi[sb]; sm.sphir[sa] += sm.sphir[sb];
-                S.z[sa] = P.z_extra[0];
-                sm.remap[sb] = (uint8_t)sa;
-                const int last = L - 1;
-                if (sb != last) {   // keep slots compact: the last slot moves into the hole
-                    const int nd = tr.slot_node[last];
-                    tr.slot_node[sb] = (int16_t)nd; tr.node_slot[nd] = (uint8_t)sb;
-                    sm.cnt[sb] = sm.cnt[last]; sm.sphi[sb] = sm.sphi[last]; sm.sphir[sb] = sm.sphir[last];
-                    S.z[sb] = S.z[last];
-                    for (int s = 0; s < L; ++s) if (sm.remap[s] == last) sm.remap[s] = (uint8_t)sb;
-                }
-                tr.nleaves = L - 1;
-                tree_remove_node(tr, max(na, nb));
-                tree_remove_node(tr, min(na, nb));
+        } else if (P.move == 2 && accepted) {
+            const int sa = pa, sb = pb;
+            const int nx = P.node, na = tr.left[nx], nb = tr.right[nx];
+            tr.left[nx] = tr.right[nx] = -1; tr.var[nx] = tr.cut[nx] = 0xFFFF;
+            tr.node_slot[nx] = (uint8_t)sa; tr.slot_node[sa] = (int16_t)nx;
+            sm.pmean[sa] = sm.pmean[KEYS]; sm.psd[sa] = sm.psd[KEYS];
+            sm.nc1[sa] = sm.nc1[KEYS]; sm.nc0[sa] = sm.nc0[KEYS];
+            S.z[sa] = P.z_extra[0];
+            sm.remap[sb] = (uint8_t)sa;
+            const int last = L - 1;
+            if (sb != last) {   // keep slots compact: the last slot moves into the hole
+                const int nd = tr.slot_node[last];
+                tr.slot_node[sb] = (int16_t)nd; tr.node_slot[nd] = (uint8_t)sb;
+                sm.pmean[sb] = sm.pmean[last]; sm.psd[sb] = sm.psd[last];
+                sm.nc1[sb] = sm.nc1[last]; sm.nc0[sb] = sm.nc0[last];
+                S.z[sb] = S.z[last];
+                for (int s = 0; s < L; ++s) if (sm.remap[s] == last) sm.remap[s] = (uint8_t)sb;
             }
+            tr.nleaves = L - 1;
+            tree_remove_node(tr, max(na, nb));
+            tree_remove_node(tr, min(na, nb));
         }
         sm.accepted = accepted;
         if (writer) {
@@ -307,21 +369,28 @@ __device__ inline void decide(StepShared& sm, int stage, const Dev& d, const For
 
     const int Lnew = tr.nleaves;
     if (t < Lnew) {
-        const double prec = 1.0 / (tau * tau) + sm.sphi[t];
-        const double m = sm.sphir[t] / prec + S.z[t] / sqrt(prec);
+        const double m = sm.pmean[t] + S.z[t] * sm.psd[t];
         if (!(m == m)) sm.bad = ERR_NAN;
         sm.mu_new[t] = m;
         tr.mu[t] = m;
+        tr.cnt1[t] = (int32_t)sm.nc1[t]; tr.cnt0[t] = (int32_t)sm.nc0[t];
     }
     __syncthreads();
-    if (t < L) sm.dlt[t] = sm.mu_new[sm.remap[t]] - sm.mu_old[t];
+    int fxbad = 0;
+    if (t < L) {
+        const double dl = sm.mu_new[sm.remap[t]] - sm.mu_old[t];
+        sm.dlt[t] = dl;
+        sm.dfx[1][t] = to_fixed(s1 * dl, fxbad); sm.dfx[0][t] = to_fixed(s0 * dl, fxbad);
+    }
     if (t == 0) {
         ApplyInfo& ai = sm.ai;
         ai.active = 1; ai.changed = sm.accepted; ai.birth = (sm.accepted && P.move == 1) ? 1 : 0;
         ai.sx = P.slot; ai.cut = P.cut; ai.bins = P.bins; ai.is16 = P.is16; ai.right_slot = L; ai.forest = is_con ? 0 : 1;
         ai.dlt_right = ai.birth ? (sm.mu_new[L] - sm.mu_old[P.slot]) : 0.0;
-        ai.s1 = s1; ai.s0 = s0;
+        ai.dfx_right[1] = to_fixed(s1 * ai.dlt_right, fxbad); ai.dfx_right[0] = to_fixed(s0 * ai.dlt_right, fxbad);
+        ai.uniform = (L == 1 && !ai.birth) ? 1 : 0;
     }
+    if (fxbad) sm.bad = ERR_FX_RANGE;
     __syncthreads();
 }
 
@@ -335,57 +404,97 @@ __device__ inline void begin_stats(StepShared& sm, int stage, int forest, const 
         CurInfo& ci = S.ci;
         ci.active = 1; ci.K = K; ci.birth = S.prop.move == 1; ci.sx = S.prop.slot; ci.cut = S.prop.cut;
         ci.bins = S.prop.bins; ci.is16 = S.prop.is16; ci.forest = forest; ci.new_slot = S.tr.nleaves;
-        ci.s1 = forest == 0 ? sc.mscale : sc.bscale1; ci.s0 = forest == 0 ? sc.mscale : sc.bscale0;
     }
-    long long* tb = &sm.tab[0][0][0];
-    for (int i = t; i < K * 8; i += blockDim.x) tb[i] = 0;
+    long long* tb = reinterpret_cast<long long*>(&sm.tab);
+    for (int i = t; i < STATTAB_WORDS64; i += blockDim.x) tb[i] = 0;
 }
 
-// flush the CTA table into the global totals of `tree` (integer REDs: order-independent)
+// flush the CTA table into the global totals of `tree` (integer REDs: order-independent).  Must be entered by every
+// thread of the CTA after a __syncthreads() that ends the tile pass.
 __device__ inline void flush_stats(StepShared& sm, int K, const Dev& d, int tree)
 {
-    const long long* tb = &sm.tab[0][0][0];
     long long* q = d.totals + (size_t)tree * KEYS * 8;
-    for (int i = threadIdx.x; i < K * 8; i += blockDim.x) {
-        const long long v = tb[i];
-        if (v != 0) atomicAdd((unsigned long long*)&q[i], (unsigned long long)v);
+    const int t = threadIdx.x;
+    if (K <= KREG) {
+        // sum the warps' private tables: 16 lanes per (key, group, word) entry, then a shuffle tree
+        const int nwarps = blockDim.x >> 5;
+        const int nent = K * 8;
+        for (int e0 = 0; e0 < nent; e0 += blockDim.x / 16) {
+            const int e = e0 + (t >> 4), w = t & 15;
+            long long v = 0;
+            if (e < nent) for (int ww = w; ww < nwarps; ww += 16) v += sm.tab.w[ww][e >> 3][(e >> 2) & 1][e & 3];
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (e < nent && w == 0) sm.rowsum[e] = v;
+        }
+        __syncthreads();
+        if (t < nent) {
+            const int k = t >> 3, gq = t & 7;
+            long long v = sm.rowsum[t];
+            if (k == 0) {          // row 0 holds the total over all keys: key 0 = total - the others (exact)
+                if ((gq & 3) == 0) v = 0;
+                else for (int kk = 1; kk < K; ++kk) v -= sm.rowsum[kk * 8 + gq];
+            }
+            if (v != 0) atomicAdd((unsigned long long*)&q[t], (unsigned long long)v);
+        }
+    } else {
+        for (int i = t; i < K * 8; i += blockDim.x) {
+            const long long v = stat_word(sm.tab, K, 0, i >> 3, (i >> 2) & 1, i & 3);
+            if (v != 0) atomicAdd((unsigned long long*)&q[i], (unsigned long long)v);
+        }
     }
 }
 
-// apply the decided update of the previous tree to 8 observations: new slot and the change of the leaf value
-__device__ __forceinline__ void apply8(const StepShared& sm, const ApplyInfo& ai, int (&sp)[8], const int (&bp)[8],
-                                       double (&dl)[8])
+// apply the decided update of the previous tree to 8 observations: new slot, the change of the leaf value (dl, goes
+// into the forest fit G) and what the fixed-point residual loses (df = scale_g * dl, rounded once per leaf)
+__device__ __forceinline__ void apply8(const StepShared& sm, const ApplyInfo& ai, int g, int (&sp)[8], const int (&bp)[8],
+                                       double (&G)[8], long long (&R)[8])
 {
+    if (ai.uniform) {
+        const double d0 = sm.dlt[0];
+        const long long f0 = sm.dfx[g][0];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const bool real = sp[o] != PAD_SLOT;
+            G[o] += real ? d0 : 0.0;
+            R[o] -= real ? f0 : 0ll;
+        }
+        return;
+    }
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
         const int s = sp[o];
-        dl[o] = 0.0;
         if (s != PAD_SLOT) {
             double x = sm.dlt[s];
+            long long f = sm.dfx[g][s];
             int ns = sm.remap[s];
-            if (ai.birth && s == ai.sx && bp[o] > ai.cut) { x = ai.dlt_right; ns = ai.right_slot; }
-            dl[o] = x;
+            if (ai.birth && s == ai.sx && bp[o] > ai.cut) { x = ai.dlt_right; f = ai.dfx_right[g]; ns = ai.right_slot; }
+            G[o] += x;
+            R[o] -= f;
             sp[o] = ns;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// One warp tile of the fused pass (state in HBM/L2): apply the previous tree's update to r (and its leaf slots),
-// then accumulate the current tree's statistics.  r is the FULL residual y - allfit.  All loads are issued
+// One warp tile of the fused pass (state in HBM/L2): apply the previous tree's update to the residual, to its
+// forest's fit and to its leaf slots, then accumulate the current tree's statistics.  All loads are issued
 // before the first dependent use.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void step_tile(StepShared& sm, const CurInfo& ci, const Dev& d, int prev, int cur, int tile,
-                                          int lane, int& bad)
+                                          int lane)
 {
     const int64_t base = (int64_t)tile * TILE + lane * 8;
     const int g = tile < d.trt_tiles ? 1 : 0;
     const ApplyInfo& ai = sm.ai;
-    double r[8];
+    long long R[8];
+    double G[8];
     int sp[8], bp[8], key[8], bc[8];
     uint8_t* sl = d.slots + (int64_t)prev * d.n_pad + base;
-    ld8_f64(d.r + base, r);
+    double* Gp = (ai.forest ? d.Gm : d.Gc) + base;
+    ld8_i64(d.rfx + base, R);
     if (ai.active) {
+        ld8_f64(Gp, G);
         ld8_u8(sl, sp);
         if (ai.birth) ld8_bins(ai.bins, ai.is16, base, bp);
     }
@@ -394,95 +503,100 @@ __device__ __forceinline__ void step_tile(StepShared& sm, const CurInfo& ci, con
         if (ci.birth) ld8_bins(ci.bins, ci.is16, base, bc);
     }
     if (ai.active) {
-        double dl[8];
-        apply8(sm, ai, sp, bp, dl);
-        const double sg = g ? ai.s1 : ai.s0;
-#pragma unroll
-        for (int o = 0; o < 8; ++o) r[o] -= sg * dl[o];
+        apply8(sm, ai, g, sp, bp, G, R);
         if (ai.changed) st8_u8(sl, sp);
-        st8_f64(d.r + base, r);
+        st8_f64(Gp, G);
+        st8_i64(d.rfx + base, R);
     }
     if (ci.active) {
         if (ci.birth) {
 #pragma unroll
             for (int o = 0; o < 8; ++o) if (key[o] == ci.sx && bc[o] > ci.cut) key[o] = ci.new_slot;
         }
-        accum_tile(sm.tab, key, r, g, ci.K, lane, bad);
+        accum_tile(sm.tab, key, R, g, ci.K, ci.birth != 0, lane, (int)(threadIdx.x >> 5));
     }
 }
 
-// moments of 8 observations into tab[m][g][1..3] (limbs); padding rows have y = G = 0
-__device__ __forceinline__ void moments8(long long (*mt)[2][4], const double (&y)[8], const double (&gc)[8],
+// moments of 8 observations into the warp's table rows 0..5 (words 1..3 = limbs); padding rows have y = G = 0
+__device__ __forceinline__ void moments8(StatTab& tab, const double (&y)[8], const double (&gc)[8],
                                          const double (&gm)[8], int g, int lane, int& bad)
 {
+    const int warp = threadIdx.x >> 5;
 #pragma unroll
     for (int m = 0; m < NMOM; ++m) {
-        int l0 = 0, l1 = 0, l2 = 0;
+        long long s = 0;
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
             const double a = (m < 3) ? y[o] : (m < 5 ? gc[o] : gm[o]);
             const double b = (m == 0) ? y[o] : (m == 1 || m == 3) ? gc[o] : gm[o];
-            const long long v = to_fixed(a * b, bad);
-            l0 += (int)(v & 0x1FFFFF); l1 += (int)((v >> LIMB_BITS) & 0x1FFFFF); l2 += (int)(v >> (2 * LIMB_BITS));
+            s += to_fixed(a * b, bad);
         }
-        l0 = __reduce_add_sync(0xffffffffu, l0);
-        l1 = __reduce_add_sync(0xffffffffu, l1);
-        l2 = __reduce_add_sync(0xffffffffu, l2);
-        if (lane < 3) {
-            const long long v = lane == 0 ? l0 : lane == 1 ? l1 : l2;
-            if (v != 0) atomicAdd((unsigned long long*)&mt[m][g][1 + lane], (unsigned long long)v);
-        }
+        warp_add_limbs(tab, warp, m, g, lane, s, 0);
+    }
+    __syncwarp();
+}
+// clear the table before a moments pass / flush the six moments of both groups into `mom`
+__device__ inline void moments_begin(StepShared& sm)
+{
+    long long* tb = reinterpret_cast<long long*>(&sm.tab);
+    for (int i = threadIdx.x; i < STATTAB_WORDS64; i += blockDim.x) tb[i] = 0;
+}
+__device__ inline void moments_flush(const StepShared& sm, long long* mom)
+{
+    const int nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < NMOM * 8; i += blockDim.x) {
+        const int m = i >> 3, g = (i >> 2) & 1, q = i & 3;
+        if (q == 0) continue;
+        const long long v = table_word(sm.tab, nwarps, m, g, q);
+        if (v != 0) atomicAdd((unsigned long long*)&mom[(g * NMOM + m) * 3 + (q - 1)], (unsigned long long)v);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sweep epilogue, observation pass (state in HBM): finish the last tree (slots only), re-derive both forest fits
-// from the trees (Gc = sum of mu-tree leaves, Gm = sum of tau-tree leaves) and accumulate the six second moments
-// per treatment group that the scale and sigma draws need [SURVEY A.4].
+// Sweep epilogue, observation pass (state in HBM): apply the last tree, then accumulate the six second moments of
+// (y, Gc, Gm) per treatment group that the scale and sigma draws need [SURVEY A.4].
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void refit_tile(StepShared& sm, const Dev& d, int prev, const TreeRec* newtrees,
-                                           int tile, int lane, int& bad)
+__device__ __forceinline__ void last_tile(StepShared& sm, const Dev& d, int prev, int tile, int lane, int& bad)
 {
     const int64_t base = (int64_t)tile * TILE + lane * 8;
     const int g = tile < d.trt_tiles ? 1 : 0;
     const ApplyInfo& ai = sm.ai;
-    int sp[8];
+    double gc[8], gm[8], y[8];
+    ld8_f64(d.Gc + base, gc); ld8_f64(d.Gm + base, gm); ld8_f64(d.y + base, y);
     if (ai.active) {
+        int sp[8], bp[8];
+        long long R[8];
         uint8_t* sl = d.slots + (int64_t)prev * d.n_pad + base;
         ld8_u8(sl, sp);
-        if (ai.changed) {
-            int bp[8];
-            double dl[8];
-            if (ai.birth) ld8_bins(ai.bins, ai.is16, base, bp);
-            apply8(sm, ai, sp, bp, dl);
-            st8_u8(sl, sp);
-        }
+        if (ai.birth) ld8_bins(ai.bins, ai.is16, base, bp);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) R[o] = 0;            // the residual is re-derived after the scale draws
+        if (ai.forest) { apply8(sm, ai, g, sp, bp, gm, R); st8_f64(d.Gm + base, gm); }
+        else { apply8(sm, ai, g, sp, bp, gc, R); st8_f64(d.Gc + base, gc); }
+        if (ai.changed) st8_u8(sl, sp);
     }
-    double G[2][8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) { G[0][o] = 0.0; G[1][o] = 0.0; }
-    for (int f = 0; f < 2; ++f) {
-        const int t0 = d.f[f].tree0, nt = d.f[f].ntree;
-        for (int j = t0; j < t0 + nt; ++j) {
-            int s[8];
-            const double* mu;
-            if (j == prev) {
-#pragma unroll
-                for (int o = 0; o < 8; ++o) s[o] = sp[o];
-                mu = sm.mu_new;
-            } else {
-                ld8_u8(d.slots + (int64_t)j * d.n_pad + base, s);
-                mu = newtrees[j].mu;
-            }
-#pragma unroll
-            for (int o = 0; o < 8; ++o) if (s[o] != PAD_SLOT) G[f][o] += mu[s[o]];
+    moments8(sm.tab, y, gc, gm, g, lane, bad);
+}
+
+// Make (and publish to HBM) the proposals of sweep `sweep` for the trees j = first, first + stride, ... < T.
+// `trees` holds their current structure; tree `smem_tree` (if >= 0) is taken from stage `smem_stage` instead
+// (the tree a CTA has just decided and whose HBM copy may not be visible yet).  Uses the other stage as scratch.
+__device__ inline void propose_range(StepShared& sm, const Dev& d, const TreeRec* trees, uint32_t sweep, int first,
+                                     int stride, int smem_tree, int smem_stage)
+{
+    const int scratch = smem_stage ^ 1;
+    for (int j = first; j < d.T; j += stride) {
+        const ForestDev& F = d.f[j >= d.f[1].tree0 ? 1 : 0];
+        int st = smem_stage;
+        if (j != smem_tree) {
+            st = scratch;
+            load_tree(&sm.st[st].tr, &trees[j]);
+            __syncthreads();
         }
+        propose(sm, st, d, F, j, sweep);
+        publish_proposal(sm, st, d, j);
+        __syncthreads();
     }
-    st8_f64(d.Gc + base, G[0]);
-    st8_f64(d.Gm + base, G[1]);
-    double y[8];
-    ld8_f64(d.y + base, y);
-    moments8(sm.tab, y, G[0], G[1], g, lane, bad);
 }
 
 }  // namespace bcf

@@ -209,6 +209,11 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev1);
     if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e2 != cudaSuccess) { delete h; return fail(BCFGPU_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e2)); }
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_propose_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_tree_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_sweep_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
+    if (e2 != cudaSuccess) { delete h; return fail(BCFGPU_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e2)); }
     h->engine = cfg->engine == BCFGPU_ENGINE_AUTO ? BCFGPU_ENGINE_PERSISTENT : cfg->engine;
     *out = h;
     return BCFGPU_OK;
@@ -348,12 +353,13 @@ static void fill_forest_dev(const bcfgpu_handle* h, int f, ForestDev& D)
     for (int dpt = 0; dpt < 32; ++dpt) D.pg[dpt] = a / std::pow(1.0 + (double)dpt, b);
 }
 
-static void root_tree(TreeRec& tr, double mu)
+static void root_tree(TreeRec& tr, double mu, int32_t ntrt = 0, int32_t nctl = 0)
 {
     memset(&tr, 0, sizeof(tr));
     tr.nnodes = 1; tr.nleaves = 1;
     for (int i = 0; i < MAXN; ++i) { tr.parent[i] = tr.left[i] = tr.right[i] = -1; tr.var[i] = tr.cut[i] = 0xFFFF; }
     tr.node_slot[0] = 0; tr.depth[0] = 0; tr.heap[0] = 1; tr.slot_node[0] = 0; tr.mu[0] = mu;
+    tr.cnt1[0] = ntrt; tr.cnt0[0] = nctl;
 }
 
 static int build_graph(bcfgpu_handle* h);
@@ -412,11 +418,12 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     CK(cudaMemcpyAsync(h->d_orig, orig.data(), (size_t)n_pad * 4, cudaMemcpyHostToDevice, h->stream));
     double* dy = nullptr;
     DM(h, &dy, (size_t)n_pad);
-    DM(h, &d.r, (size_t)n_pad); DM(h, &d.Gc, (size_t)n_pad); DM(h, &d.Gm, (size_t)n_pad);
+    DM(h, &d.rfx, (size_t)n_pad); DM(h, &d.Gc, (size_t)n_pad); DM(h, &d.Gm, (size_t)n_pad);
     DM(h, &d.tau_sum, (size_t)n_pad); DM(h, &d.tau_sq, (size_t)n_pad); DM(h, &d.mu_sum, (size_t)n_pad); DM(h, &d.yhat_sum, (size_t)n_pad);
     DM(h, &h->d_tmp, (size_t)n_pad); DM(h, &h->d_tmp2, (size_t)n_pad);
     DM(h, &d.slots, (size_t)h->T * n_pad);
     DM(h, &d.trees[0], (size_t)h->T); DM(h, &d.trees[1], (size_t)h->T);
+    DM(h, &d.proprec, (size_t)h->T);
     DM(h, &d.totals, (size_t)h->T * KEYS * 8);
     DM(h, &d.mom, (size_t)2 * 2 * NMOM * 3);
     DM(h, &d.sc, 1);
@@ -449,21 +456,23 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     fill_forest_dev(h, 1, d.f[1]);
 
     // ybar from an order-independent fixed-point sum, so any sharding starts from identical bits
-    long long ysum[4] = {0, 0, 0, 0};   // count, limb0, limb1, limb2
+    long long ysum[5] = {0, 0, 0, 0, (long long)ntrt};   // count, limb0, limb1, limb2, treated count
     for (int64_t i = 0; i < n; ++i) {
-        if (!(std::fabs(y[i]) < 262144.0)) return fail(BCFGPU_ERR_BAD_ARG, "|y| too large: pass the standardised outcome");
+        if (!(std::fabs(y[i]) < 32768.0)) return fail(BCFGPU_ERR_BAD_ARG, "|y| too large: pass the standardised outcome");
         const long long v = std::llrint(y[i] * 17592186044416.0);
         ysum[0] += 1; ysum[1] += v & 0x1FFFFF; ysum[2] += (v >> LIMB_BITS) & 0x1FFFFF; ysum[3] += v >> (2 * LIMB_BITS);
     }
     if (h->nranks > 1) {
         long long* dq = (long long*)h->d_tmp;
-        CK(cudaMemcpyAsync(dq, ysum, 32, cudaMemcpyHostToDevice, h->stream));
-        if ((rc = shard_allreduce(h, dq, 4))) return rc;
-        CK(cudaMemcpyAsync(ysum, dq, 32, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(dq, ysum, 40, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = shard_allreduce(h, dq, 5))) return rc;
+        CK(cudaMemcpyAsync(ysum, dq, 40, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
     h->n_global = ysum[0];
     d.n_global = h->n_global;
+    if (h->n_global > 2000000000ll) return fail(BCFGPU_ERR_BAD_ARG, "more than 2e9 observations over all shards");
+    const int32_t ntrt_g = (int32_t)ysum[4], nctl_g = (int32_t)(ysum[0] - ysum[4]);
     const double ybar = limbs_to_double(ysum[1], ysum[2], ysum[3]) / (double)h->n_global;
 
     // trees, scalars [SURVEY A.2]
@@ -471,7 +480,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
         std::vector<TreeRec> trees((size_t)h->T);
         const double trt_init = 1.0;
         for (int j = 0; j < h->T; ++j)
-            root_tree(trees[j], j < c.ntree_con ? ybar / c.ntree_con : trt_init / c.ntree_mod);
+            root_tree(trees[j], j < c.ntree_con ? ybar / c.ntree_con : trt_init / c.ntree_mod, ntrt_g, nctl_g);
         CK(cudaMemcpyAsync(d.trees[0], trees.data(), sizeof(TreeRec) * h->T, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(d.trees[1], trees.data(), sizeof(TreeRec) * h->T, cudaMemcpyHostToDevice, h->stream));
         Scalars sc;
@@ -502,11 +511,12 @@ static int enqueue_sweep(bcfgpu_handle* h)
 {
     const Dev& d = h->dev;
     int rc;
+    k_propose_all<<<h->T, THREADS, STEP_SMEM_BYTES, h->stream>>>(d);
     for (int j = 0; j < h->T; ++j) {
-        k_tree_step<<<h->grid_obs, THREADS, 0, h->stream>>>(d, j - 1, j);
+        k_tree_step<<<h->grid_obs, THREADS, STEP_SMEM_BYTES, h->stream>>>(d, j - 1, j);
         if ((rc = shard_allreduce(h, d.totals + (size_t)j * KEYS * 8, KEYS * 8))) return rc;
     }
-    k_sweep_end<<<h->grid_obs, THREADS, 0, h->stream>>>(d, h->T - 1);
+    k_sweep_end<<<h->grid_obs, THREADS, STEP_SMEM_BYTES, h->stream>>>(d, h->T - 1);
     if ((rc = shard_allreduce(h, d.mom, 2 * NMOM * 3))) return rc;
     k_scalars<<<1, THREADS, 0, h->stream>>>(d);
     k_finish<<<h->grid_fin, 256, 0, h->stream>>>(d);
@@ -537,7 +547,7 @@ static int check_device_err(bcfgpu_handle* h)
     if (sc.err) cudaMemset(h->dev.err, 0, 4);
     if (sc.err & ERR_BARRIER_TIMEOUT) return fail(BCFGPU_ERR_CUDA, "grid barrier timed out inside the persistent sweep kernel");
     if (sc.err & ERR_NAN) return fail(BCFGPU_ERR_NUMERIC, "NaN in a leaf / scale / sigma draw");
-    if (sc.err & ERR_FX_RANGE) return fail(BCFGPU_ERR_NUMERIC, "residual outside the fixed-point range (|r| >= 2^18) or NaN");
+    if (sc.err & ERR_FX_RANGE) return fail(BCFGPU_ERR_NUMERIC, "residual outside the fixed-point range (|r| >= 2^15) or NaN");
     return BCFGPU_OK;
 }
 
@@ -580,10 +590,10 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
         rc = run_persistent(h, total);
     } else if (h->nranks == 1) {
         for (int it = 0; it < total; ++it) CK(cudaGraphLaunch(h->gexec, h->stream));
-        h->launches += (int64_t)total * (h->T + 3);
+        h->launches += (int64_t)total * (h->T + 4);
     } else {
         for (int it = 0; it < total && rc == BCFGPU_OK; ++it) rc = enqueue_sweep(h);
-        h->launches += (int64_t)total * (h->T + 3);
+        h->launches += (int64_t)total * (h->T + 4);
     }
     if (rc) { cudaStreamSynchronize(h->stream); return rc; }
     CK(cudaEventRecord(h->ev1, h->stream));
@@ -835,14 +845,24 @@ int bcfgpu_set_tree(bcfgpu_handle* h, int32_t tree, int32_t nnodes, const uint32
     if (2 * tr.nleaves - 1 != nnodes) return fail(BCFGPU_ERR_BAD_ARG, "not a full binary tree");
     int par, rc;
     if ((rc = current_parity(h, &par))) return rc;
+    CK(cudaMemcpy(h->dev.trees[par] + tree, &tr, sizeof(TreeRec), cudaMemcpyHostToDevice));
+    k_assign<<<h->grid_fin, 256, 0, h->stream>>>(h->dev, tree, f, h->dev.trees[par], 0, nullptr, h->d_orig);
+    // leaf counts (cached in the tree): count the fresh assignment, over all shards
+    long long* dcnt = (long long*)h->d_tmp2;
+    CK(cudaMemsetAsync(dcnt, 0, (size_t)MAXL * 2 * 8, h->stream));
+    k_count_leaves<<<h->grid_fin, 256, 0, h->stream>>>(h->dev, tree, dcnt);
+    if ((rc = shard_allreduce(h, dcnt, (size_t)MAXL * 2))) return rc;
+    std::vector<long long> cnt((size_t)MAXL * 2);
+    CK(cudaMemcpyAsync(cnt.data(), dcnt, cnt.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < tr.nleaves; ++s) { tr.cnt0[s] = (int32_t)cnt[2 * s]; tr.cnt1[s] = (int32_t)cnt[2 * s + 1]; }
     CK(cudaMemcpy(h->dev.trees[0] + tree, &tr, sizeof(TreeRec), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dev.trees[1] + tree, &tr, sizeof(TreeRec), cudaMemcpyHostToDevice));
-    k_assign<<<h->grid_fin, 256, 0, h->stream>>>(h->dev, tree, f, h->dev.trees[par], 0, nullptr, h->d_orig);
     k_refit_all<<<h->grid_fin, 256, 0, h->stream>>>(h->dev, h->dev.trees[par]);
-    h->launches += 2;
+    h->launches += 3;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
-    return BCFGPU_OK;
+    return check_device_err(h);
 }
 
 int bcfgpu_get_leaf_ids(bcfgpu_handle* h, int32_t tree, uint32_t* out)
@@ -932,7 +952,13 @@ int bcfgpu_op_suffstats(bcfgpu_handle* h, int32_t tree, const double* r, uint32_
     cudaFree(dout);
     if (e != cudaSuccess) return fail(BCFGPU_ERR_CUDA, std::string("op_suffstats: ") + cudaGetErrorString(e));
     if ((rc = check_device_err(h))) return rc;
-    auto cntv = [&](int k, int g) { return tot[(size_t)k * 8 + g * 4]; };
+    // counts: cached in the tree (kept exact by the sampler: birth children are counted, everything else follows);
+    // only the would-be right child of the birth split (key L) is counted by this pass
+    auto cntv = [&](int k, int g) -> long long {
+        if (k == L) return tot[(size_t)k * 8 + g * 4];
+        const long long whole = g ? tr.cnt1[k] : tr.cnt0[k];
+        return (k == sx) ? whole - tot[(size_t)L * 8 + g * 4] : whole;
+    };
     auto sumv = [&](int k, int g) { const long long* q = &tot[(size_t)k * 8 + g * 4]; return limbs_to_double(q[1], q[2], q[3]); };
     auto sum_exact = [&](int k1, int k2, int g) {   // exact merge of two keys before rounding
         const long long* a = &tot[(size_t)k1 * 8 + g * 4]; const long long* b = &tot[(size_t)k2 * 8 + g * 4];
@@ -1052,7 +1078,7 @@ static int run_persistent(bcfgpu_handle* h, int total)
         CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
         const int grid = std::min<int>(h->coop_grid, std::max(1, h->dev.n_tiles));
         const int ntl_max = (h->dev.n_tiles + grid - 1) / grid;
-        const size_t need = (size_t)ntl_max * RES_BYTES_PER_TILE;
+        const size_t need = STEP_SMEM_BYTES + (size_t)ntl_max * RES_BYTES_PER_TILE;
         h->res_ntl = 0;
         if (h->engine != BCFGPU_ENGINE_PERSISTENT_HBM && !getenv("BCFGPU_NO_RESIDENT") && need + fa.sharedSizeBytes + 1024 <= (size_t)max_optin) {
             CK(cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
@@ -1062,7 +1088,7 @@ static int run_persistent(bcfgpu_handle* h, int total)
         }
         if (h->res_ntl == 0) {
             int per_sm = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PTHREADS, 0));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PTHREADS, STEP_SMEM_BYTES));
             if (per_sm < 1) return fail(BCFGPU_ERR_CUDA, "persistent kernel does not fit on an SM");
         }
         h->coop_grid = grid;
@@ -1080,7 +1106,7 @@ static int run_persistent(bcfgpu_handle* h, int total)
             CK(cudaLaunchCooperativeKernel((const void*)k_resident, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
         } else {
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar};
-            CK(cudaLaunchCooperativeKernel((const void*)k_persistent, dim3(h->coop_grid), dim3(PTHREADS), args, 0, h->stream));
+            CK(cudaLaunchCooperativeKernel((const void*)k_persistent, dim3(h->coop_grid), dim3(PTHREADS), args, STEP_SMEM_BYTES, h->stream));
         }
         h->launches++;
     }

@@ -91,10 +91,10 @@ def test_posterior_outputs_match_oracle():
     assert np.allclose(tv, out["tau"][:, inv].var(axis=0, ddof=1), rtol=1e-6, atol=1e-9)
 
 
-def test_engines_agree():
-    """Fixed-point reductions are order-independent: the graph engine and the persistent engine with the same
-    arithmetic (state in HBM) give the same bits; the shared-memory-resident kernel keeps (base, G) instead of a
-    running residual and agrees to rounding."""
+def test_engines_are_bit_identical():
+    """The residual is an integer (fixed-point) state updated exactly and every reduction is an integer sum, so the
+    three engines -- graph, persistent with the state in HBM, persistent with the state in shared memory -- walk the
+    same chain bit for bit whatever their thread / CTA partitioning."""
     pr = make_problem(n=3000, p=12, seed=21)
     kw = dict(seed=4, ntree_con=50, ntree_mod=20)
     a = gpu_sampler(pr, engine=1, **kw)
@@ -102,12 +102,12 @@ def test_engines_agree():
     c = gpu_sampler(pr, engine=2, **kw)
     for s in (a, b, c):
         s.run(5, 10)
-    assert np.array_equal(a.tau_mean(), b.tau_mean())
-    assert np.array_equal(a.sigma(), b.sigma())
-    assert a.scalars() == b.scalars()
-    assert np.allclose(a.tau_mean(), c.tau_mean(), rtol=1e-10, atol=1e-11)
-    assert np.allclose(a.sigma(), c.sigma(), rtol=1e-11)
-    assert a.counters() == c.counters()
+    for other in (b, c):
+        assert np.array_equal(a.tau_mean(), other.tau_mean())
+        assert np.array_equal(a.mu_mean(), other.mu_mean())
+        assert np.array_equal(a.sigma(), other.sigma())
+        assert a.scalars() == other.scalars()
+        assert a.counters() == other.counters()
 
 
 def test_engine_handover():

@@ -1,0 +1,135 @@
+"""Kernel-level parity: each CUDA operator against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): bins, node assignments and leaf counts bit-exact; fp64 leaf sums within
+1e-10 * sum|r| (fixed-point 2^-44 accumulation vs sequential fp64); log-likelihood terms within 1e-10 relative.
+"""
+import numpy as np
+import pytest
+
+from bcf_iv_b200 import _lib, prep
+from helpers import gpu_sampler, make_problem, oracle_sampler
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_tree(rng, ncut, nleaves, max_depth=12):
+    """random full binary tree as (heap, var, cut, mu) with valid (var, cut) given ancestors (bcf's rg rule)"""
+    p = len(ncut)
+    leaves = {1: {}}          # heap id -> {var: (lo, hi)}
+    internal = {}
+    while len(leaves) < nleaves:
+        cand = [h for h in leaves if h.bit_length() - 1 < max_depth]
+        if not cand:
+            break
+        h = cand[rng.integers(len(cand))]
+        rngs = leaves[h]
+        ok = [v for v in range(p) if rngs.get(v, (0, ncut[v] - 1))[1] >= rngs.get(v, (0, ncut[v] - 1))[0]]
+        if not ok:
+            break
+        v = ok[rng.integers(len(ok))]
+        lo, hi = rngs.get(v, (0, ncut[v] - 1))
+        c = int(rng.integers(lo, hi + 1))
+        del leaves[h]
+        internal[h] = (v, c)
+        l = dict(rngs); l[v] = (lo, c - 1)
+        r = dict(rngs); r[v] = (c + 1, hi)
+        leaves[2 * h] = l
+        leaves[2 * h + 1] = r
+    heap, var, cut, mu = [], [], [], []
+    for h, (v, c) in internal.items():
+        heap.append(h); var.append(v); cut.append(c); mu.append(0.0)
+    for h in leaves:
+        heap.append(h); var.append(-1); cut.append(-1); mu.append(float(rng.standard_normal()))
+    return np.array(heap, np.uint32), np.array(var, np.int32), np.array(cut, np.int32), np.array(mu)
+
+
+def test_k0_bins_match_definition():
+    """bin = #{cut <= x}: x < cut[c]  <=>  bin <= c, for binary, few-valued and 10 000-cutpoint columns."""
+    rng = np.random.default_rng(0)
+    for x in (rng.integers(0, 2, 5000).astype(float), rng.integers(0, 5, 5000).astype(float),
+              rng.standard_normal(20000), np.repeat(rng.standard_normal(50), 100)):
+        cuts = prep.cp_quantile(x)
+        b = _lib.op_bin_column(x, cuts)
+        assert np.array_equal(b, np.searchsorted(cuts, x, side="right"))
+        for c in (0, len(cuts) // 2, len(cuts) - 1):
+            assert np.array_equal(x < cuts[c], b <= c)
+
+
+@pytest.mark.parametrize("continuous,nleaves", [(False, 6), (True, 9), (True, 40), (True, 128)])
+def test_k1_k2_assignment_and_sufficient_statistics(continuous, nleaves):
+    """set_tree -> K1 leaf assignment bit-exact with the oracle's tree walk over the raw doubles; K2 per-leaf counts
+    exact and sums within 1e-10 * sum|r|, with and without a birth split; small trees take the REDUX path, trees
+    with more than 8 keys the shared-atomics path."""
+    pr = make_problem(n=4111, p=9, seed=13, continuous=continuous)
+    g = gpu_sampler(pr, ntree_con=3, ntree_mod=2)
+    o = oracle_sampler(pr, ntree_con=3, ntree_mod=2)
+    rng = np.random.default_rng(5)
+    perm, inv = pr.P.perm, pr.P.inv_perm
+    for tid, cuts in ((1, pr.P.cuts_c), (3, pr.P.cuts_m)):
+        ncut = [len(c) for c in cuts]
+        heap, var, cut, mu = _random_tree(rng, ncut, nleaves)
+        g.set_tree(tid, heap, var, cut, mu)
+        o.set_tree(tid, heap, var, cut, mu)
+        assert np.array_equal(g.leaf_ids(tid), o.assign_leaves(tid)[inv])
+        assert g.verify_leaf_cache() == 0
+        r = rng.standard_normal(pr.n) * 3.0
+        z = pr.P.z
+        st = g.op_suffstats(tid, r)
+        # oracle: counts / sums per leaf for each group via unit weights restricted to the group
+        rp = r[perm]
+        zt = (z[perm] == 1).astype(float)
+        h1, n1, _, s1 = o.allsuff(tid, zt, rp)            # phi = 1{treated}: sum phi, sum phi*r
+        h0, n0, _, s0 = o.allsuff(tid, 1.0 - zt, rp)
+        assert np.array_equal(st["heap"], h1)
+        _, _, c1, _ = o.allsuff(tid, zt, rp)
+        assert np.array_equal(st["cnt_trt"], np.round(o.allsuff(tid, zt, np.ones(pr.n))[3]).astype(np.int64))
+        assert np.array_equal(st["cnt_ctl"], np.round(o.allsuff(tid, 1.0 - zt, np.ones(pr.n))[3]).astype(np.int64))
+        tol = 1e-10 * np.abs(r).sum()
+        assert np.all(np.abs(st["sum_trt"] - s1) <= tol) and np.all(np.abs(st["sum_ctl"] - s0) <= tol)
+        # birth split of one leaf
+        hl, vl, cl, _ = g.get_tree(tid)
+        leaf_heaps = hl[vl < 0]
+        lh = int(leaf_heaps[rng.integers(len(leaf_heaps))])
+        v = int(rng.integers(len(ncut))); c = int(rng.integers(ncut[v]))
+        sb = g.op_suffstats(tid, r, birth_leaf_heap=lh, var=v, cut=c)
+        ot = o.getsuff_birth(tid, lh, v, c, zt, rp)        # {l.n0, l.n, l.sy, r.n0, r.n, r.sy} with phi = 1{treated}
+        oc = o.getsuff_birth(tid, lh, v, c, 1.0 - zt, rp)
+        b = sb["birth"]
+        assert (b[0], b[1], b[4], b[5]) == (ot[1], oc[1], ot[4], oc[4])       # counts by group, exact
+        assert abs(b[2] - ot[2]) <= tol and abs(b[3] - oc[2]) <= tol and abs(b[6] - ot[5]) <= tol and abs(b[7] - oc[5]) <= tol
+        # the whole-leaf statistics are unchanged by a proposal
+        assert np.array_equal(sb["cnt_trt"], st["cnt_trt"]) and np.allclose(sb["sum_trt"], st["sum_trt"], atol=tol, rtol=0)
+
+
+def test_k2prime_all_candidate_histogram():
+    """(count, residual sum) for every (leaf, variable, cutpoint bin) at once vs a plain loop; uint8 and uint16 columns."""
+    pr = make_problem(n=3001, p=7, seed=17, continuous=True)
+    g = gpu_sampler(pr, ntree_con=2, ntree_mod=2)
+    o = oracle_sampler(pr, ntree_con=2, ntree_mod=2)
+    rng = np.random.default_rng(3)
+    r = rng.standard_normal(pr.n)
+    for forest in (0, 1):
+        for nleaf in (1, 3, 20):
+            slot = rng.integers(-1, nleaf, pr.n).astype(np.int32)
+            cg, sg, ms = g.op_hist_all(forest, slot, nleaf, r)
+            co, so = o.hist_all(forest, slot[pr.P.perm], nleaf, r[pr.P.perm])
+            assert np.array_equal(cg, co)
+            assert np.allclose(sg, so, rtol=0, atol=1e-10 * np.abs(r).sum())
+            assert ms > 0
+
+
+def test_k3_integrated_likelihood():
+    from oracle import orc
+    rng = np.random.default_rng(1)
+    a = rng.uniform(1, 1e6, 200); b = rng.standard_normal(200) * 1e3; t = rng.uniform(0.01, 2, 200)
+    ref = np.array([orc.lil(x, y, z) for x, y, z in zip(a, b, t)])
+    assert np.allclose(_lib.op_lil(a, b, t), ref, rtol=1e-10, atol=0)
+
+
+def test_philox_stream_matches_oracle():
+    from oracle import orc
+    for args in ((42, 0, 0, 0, 0, 0), (42, 3, 17, 249, 3, 1234567), (2**63 + 5, 7, 4000, 0xFFFFFFFF, 15, 9)):
+        g = _lib.op_rng_probe(*args)
+        o = orc.rng_probe(*args)
+        assert g[0] == o[0] and g[1] == o[1]                 # uniforms: integer arithmetic, bit-exact
+        assert g[2] == pytest.approx(o[2], rel=1e-13, abs=1e-15)   # Box-Muller: device vs glibc log/cos
