@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- BCF Gibbs sweeps/sec at the headline shape (BASELINE.json: n=1M, p=100, 200 mu + 50 tau trees).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm: libbcfgpu.so through its C-ABI
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU arm: the oracle restatement of bcf
+
+A STEP is one Gibbs sweep: one birth/death + leaf-redraw update of every one of the 250 trees, the
+parameter-expansion scale draws and the sigma draw.  N > 1 (torchrun, one process per GPU)
+runs ONE INDEPENDENT CHAIN PER GPU on the replicated data with no data-path collective (SURVEY 8e "chains"):
+weak scaling, value = sweeps of all chains / max-over-ranks time.  `--mode sharded` instead shards the
+observations over the ranks with one NCCL all-reduce of the leaf statistics per tree.
+
+Timed region of `value`: inputs binned and resident in HBM, chain burnt in (tree sizes stationary), W warm-up
+sweeps, then exactly K sweeps bracketed by barrier + synchronize, timed with CUDA events on the library's stream,
+max over ranks.  `e2e`: the whole bcf()-shaped call through the C-ABI with HOST buffers -- create, set_data (H2D
+of y, z, X and binning), run(K sweeps), colMeans(tau) back to the host -- by wall clock.
+
+The oracle (oracle/) is used here ONLY as the timed CPU baseline (`cpu_baseline`, `--impl reference`); the measured
+product path never touches it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bcf_gibbs_sweeps_per_sec"
+UNIT = "sweeps/s"
+T_CON, T_MOD = 200, 50
+
+
+def algorithmic_bytes_per_sweep(n, T, bx=1):
+    """per (obs, tree) read r 8 + write r 8 + leaf slot 1 + proposed variable's bin bx; 48 B/obs epilogue."""
+    return n * (T * (17 + bx) + 48)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic_per_sweep(n, engine_name):
+    """dram bytes per sweep from the committed ncu --set full capture of the same workload, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            tr = json.load(f)
+        e = tr.get(f"{engine_name}:n={n}")
+        return float(e["dram_bytes_per_sweep"]) if e else None
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.th = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), line.strip()))
+        self.th = threading.Thread(target=pump, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        if self.proc is None:
+            return None
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in inside:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def pinned_like(a):
+    """copy of a numpy array in pinned host memory (what the e2e leg hands to the C-ABI), keeping Fortran order"""
+    import torch
+    if a.ndim == 2 and a.flags.f_contiguous:
+        t = torch.empty((a.shape[1], a.shape[0]), dtype=torch.from_numpy(np.zeros(1, a.dtype)).dtype, pin_memory=True)
+        v = t.numpy().T
+    else:
+        t = torch.empty(a.shape, dtype=torch.from_numpy(np.zeros(1, a.dtype)).dtype, pin_memory=True)
+        v = t.numpy()
+    v[...] = a
+    return v, t
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of bcf's sweep, all host threads, on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------------------------
+def oracle_sampler_from(w, rows, nthreads):
+    from oracle import orc
+    z = w["z"][rows]
+    order = np.argsort(-z, kind="stable")                      # bcf: perm = order(z, decreasing = TRUE)
+    rows = rows[order]
+    p_con, p_mod = w["x_con"].shape[1], w["x_mod"].shape[1]
+    cc = [w["cuts_con"][w["off_con"][v]:w["off_con"][v + 1]] for v in range(p_con)]
+    cm = [w["cuts_mod"][w["off_mod"][v]:w["off_mod"][v + 1]] for v in range(p_mod)]
+    return orc.OracleSampler(w["y"][rows], int(z.sum()), w["x_con"][rows], w["x_mod"][rows], cc, cm,
+                             lambda_=w["lambda_"], sigma_init=w["sigma_init"], nthreads=nthreads)
+
+
+def time_oracle(w, n_full, n_sample, sweeps, warm, nthreads):
+    """sweeps/s of the CPU oracle scaled to the full n: cost is O(n) per tree pass (4 passes/tree)."""
+    rows = np.arange(n_sample, dtype=np.int64)                 # rows are iid: the first n_sample are a random sample
+    o = oracle_sampler_from(w, rows, nthreads)
+    if warm:
+        o.sweeps(warm)
+    t0 = time.perf_counter()
+    o.sweeps(sweeps)
+    dt = time.perf_counter() - t0
+    o.close()
+    return (sweeps / dt) * (n_sample / n_full), dt
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    from oracle import orc
+    from bcf_iv_b200 import workload
+    orc.build()
+    nth = orc.max_threads()
+    n, p = args.n, args.p
+    # calibrate on 20k rows, then size the sample so that warmup + steps sweeps take about args.cpu_budget seconds
+    n_cal = min(n, 20000)
+    w = workload.synthetic_sampler_inputs(min(n, 200000), p, seed=args.data_seed)
+    _, dt_cal = time_oracle(w, n, n_cal, 1, 1, nth)
+    per_row_sweep = dt_cal / n_cal
+    n_sample = int(min(n, len(w["y"]), max(5000, args.cpu_budget / (per_row_sweep * (args.steps + args.warmup)))))
+    val, dt = time_oracle(w, n, n_sample, args.steps, args.warmup, nth)
+    sample = (f"{args.steps} timed sweeps (+{args.warmup} warm-up) of the oracle on the first {n_sample} rows of the "
+              f"same synthetic workload, {nth} OpenMP threads over observations; sweeps/s scaled by n_sample/n "
+              f"(cost is O(n) per tree pass)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world, "cpu"),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of the un-vendored bcf package's sweep (oracle/bcf_oracle.c), not bcf itself: "
+                "the reference cannot be installed or run here (no R, bcf sources absent; SURVEY 8c)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, world, where):
+    return {"workload": f"bcf sampler called directly: n_s={args.n}, p={args.p} binary covariates + pihat "
+                        f"(p_con={args.p + 1}), {T_CON} mu + {T_MOD} tau trees (BASELINE.json metric shape)",
+            "n": args.n, "p": args.p, "ntree_control": T_CON, "ntree_moderate": T_MOD,
+            "parallelism": (f"chains x{world} (one independent chain per GPU, data replicated)" if args.mode == "chains"
+                            else f"observation shards x{world} (NCCL all-reduce of leaf statistics per tree)"),
+            "where": where}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bcf_iv_b200 import _lib, workload
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if _lib.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (libbcfgpu has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n, p, K, W = args.n, args.p, args.steps, args.warmup
+    T = T_CON + T_MOD
+    sharded = args.mode == "sharded" and world > 1
+    w = workload.synthetic_sampler_inputs(n, p, seed=args.data_seed)
+    if sharded:
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        rows = slice(lo, hi)
+    else:
+        rows = slice(0, n)
+    host = {k: w[k][rows] if k in ("y", "z", "x_con", "x_mod") else w[k] for k in w}
+    # pinned host copies: what the e2e call is handed (R would hand pageable memory; pinned is the contract's case)
+    keep = []
+    for k in ("y", "z", "x_con", "x_mod"):
+        a = host[k]
+        if k.startswith("x_"):
+            a = np.asfortranarray(a)
+        host[k], t = pinned_like(a)
+        keep.append(t)
+
+    engine = {"auto": 0, "graph": 1, "persistent": 2, "persistent_hbm": 3}[args.engine]
+
+    def make_sampler():
+        s = _lib.Sampler(engine=engine, lambda_=w["lambda_"], sigma_init=w["sigma_init"], seed=args.seed,
+                         chain=0 if sharded else rank, device=local_rank)
+        if sharded:
+            uid = [_lib.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            s.set_shard(rank, world, uid[0])
+        return s
+
+    def set_data(s):
+        s.set_data(host["y"], host["z"], host["x_con"], host["x_mod"], w["cuts_con"], w["off_con"], w["cuts_mod"],
+                   w["off_mod"])
+
+    # ---- device-resident leg: `value` ----
+    s = make_sampler()
+    set_data(s)
+    s.run(args.burnin, 0)                       # untimed burn-in: tree sizes (and so the sweep cost) become stationary
+    for _ in range(1):
+        s.run(W, 0)                             # W warm-up sweeps
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.3)
+    l0 = s.kernel_launches
+    barrier()
+    t0 = time.time()
+    s.run(0, K)                                 # exactly K sweeps, every one saved into the posterior accumulators
+    torch.cuda.synchronize()
+    t1 = time.time()
+    dev_ms = s.last_run_ms                      # CUDA events on the library's stream around the K sweeps
+    barrier()
+    launches = s.kernel_launches - l0
+    time.sleep(0.25)
+    clocks.stop()
+    ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks((t1 - t0) * 1e3)
+    total_launches = int(sum_over_ranks(launches))
+    units = K * (1 if sharded else world)       # sweeps of all chains (sharded: one chain over all ranks)
+    value = units / (ms * 1e-3)
+    sizes = [len(s.get_tree(t)[0]) for t in range(0, T, 5)]
+    acc = s.counters()
+    sig = s.scalars()["sigma"]
+    s.close()
+
+    # ---- end-to-end leg through the C-ABI with host buffers ----
+    barrier()
+    e0 = time.perf_counter()
+    s2 = make_sampler()
+    set_data(s2)
+    s2.run(0, K)
+    tau = s2.tau_mean()
+    torch.cuda.synchronize()
+    e1 = time.perf_counter()
+    h2d = s2.h2d_bytes
+    d2h = tau.nbytes
+    s2.close()
+    e2e_s = max_over_ranks(e1 - e0)
+    e2e_val = units / e2e_s
+    if not np.all(np.isfinite(tau)):
+        raise SystemExit("bench.py: non-finite posterior mean")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    n_local = host["y"].shape[0]
+    b_sweep = algorithmic_bytes_per_sweep(n_local, T)
+    peak, peak_src = measured_peak_gbs()
+    sweeps_per_launch = K / max(launches, 1)
+    launch_ms = dev_ms / max(launches, 1)
+    achieved = b_sweep * sweeps_per_launch / (launch_ms * 1e-3) / 1e9
+    eng_name = {0: "persistent", 1: "graph", 2: "persistent", 3: "persistent_hbm"}[engine]
+    traffic_sweep = ncu_traffic_per_sweep(n_local, eng_name)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
+        "vs_baseline": None, "dtype": "f64 (fixed-point int64 residual sums, exact)", "data": "synthetic",
+        "config": dict(workload_config(args, world, "B200"), engine=eng_name, burnin_sweeps=args.burnin,
+                       l2="no flush: per-sweep working set (250 MB leaf-slot cache + 101 MB bins + 40 MB state) "
+                          "exceeds the 126 MB L2",
+                       mean_nodes_per_tree=float(np.mean(sizes)), sigma=sig, moves=acc,
+                       wall_ms_per_step=wall_ms / K),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (traffic_sweep * sweeps_per_launch if traffic_sweep is not None else None),
+                     "peak_source": peak_src, "kernel": "k_resident" if eng_name == "persistent" else eng_name,
+                     "algorithmic_bytes_per_sweep": b_sweep, "sweeps_per_launch": sweeps_per_launch,
+                     "launch_ms": launch_ms},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                "call": "bcfgpu_create + set_data(pinned host y, z, X_control, X_moderate: H2D + binning) + "
+                        f"run({K} sweeps) + get_tau_mean (D2H), wall clock; bytes amortised over the {K} sweeps",
+                "seconds": e2e_s},
+        "gpu_launches": total_launches,
+        "clocks": clocks.summary(t0, t1),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import orc
+        orc.build()
+        nth = orc.max_threads()
+        n_s = min(n, args.cpu_sample)
+        val, dt = time_oracle(w, n, n_s, 2, 1, nth)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": nth, "kind": "port",
+                                "sample": f"2 timed sweeps (+1 warm-up) of the oracle on the first {n_s} rows of the "
+                                          f"same workload, {nth} OpenMP threads; scaled by n_sample/n ({dt:.1f} s of CPU)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="chains", choices=["chains", "sharded"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "graph", "persistent", "persistent_hbm"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--p", type=int, default=100)
+    ap.add_argument("--burnin", type=int, default=100)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--data-seed", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=100_000)
+    ap.add_argument("--cpu-budget", type=float, default=120.0, help="seconds of CPU work for --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps < 1 or args.warmup < 0:
+        raise SystemExit("need --steps >= 1 and --warmup >= 0")
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
