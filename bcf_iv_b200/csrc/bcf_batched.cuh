@@ -1,0 +1,744 @@
+// bcf_batched.cuh -- BATCHED engine: up to NB trees of the Gibbs sweep per observation pass and per grid barrier.
+//
+// Backfitting is sequential in the trees: the sufficient statistics of tree j are sums of the residual AFTER trees
+// 0..j-1 have been redrawn.  But the residual is a fixed-point INTEGER and every update is an integer subtraction of
+// a per-leaf constant, so the dependency is linear and can be resolved after the fact, exactly:
+//
+//     S_j[k]  =  S0_j[k]  -  sum_{m<j} sum_{k'} D_m[k'] * N_{m,j}[k'][k]
+//
+// S0_j[k]      : sum of the residual as it was BEFORE the batch over the observations with key k in tree j,
+// D_m[k']      : what an observation with key k' in tree m loses when tree m is redrawn (known once m is decided),
+// N_{m,j}[k'][k]: how many observations have key k' in tree m AND key k in tree j (a count: data-independent of the
+//                decisions).  "Key" = leaf slot, with the would-be right child of a birth proposal as its own key.
+// One pass over the CTA's observations therefore accumulates, for a whole batch, the per-tree key sums and the
+// pairwise cross counts; after ONE grid barrier every CTA replays the batch's Metropolis-Hastings decisions in tree
+// order from the same reduced integers (so nothing is broadcast), which yields per tree the tables the next pass
+// applies to the residual, to the forest fit and to the leaf-slot cache.  The chain is bit-identical to the
+// tree-at-a-time engines: same integers, same Philox counters, same fp64 expressions in the same order.
+//
+// State of the CTA's observations (fixed-point residual R, fit G of the forest being swept, the batch's keys) lives in
+// shared memory for the whole launch; per tree the HBM traffic is 1 B/obs of leaf slots + the proposed variable's bin.
+// Trees whose key space exceeds KB (or whose cross tables would not fit) are processed alone ("big" batches) with the
+// shared-atomics statistics table of the tree-at-a-time engines.
+#pragma once
+#include "bcf_persistent.cuh"
+
+namespace bcf {
+
+constexpr int NB = 8;              // trees per batch
+constexpr int KB = 8;              // key-space bound of a batched tree
+constexpr int XCAP = 256;          // cross-count cells of a batch: sum over pairs m<q of (K_m-1)(K_q-1)
+constexpr int APCAP = 136;         // apply-table entries: NB*KB, or the KEYS = 129 of one big tree
+static_assert(APCAP >= KEYS && APCAP >= NB * KB, "apply table too small");
+using TreeSmall = TreeT<2 * KB, KB>;
+using SmallStage = TreeStageT<TreeSmall, KB>;
+constexpr int BAT_BYTES_PER_TILE = TILE * (8 + 8) + NB * TILE;   // R, G, keys of the batch (one byte per tree)
+
+struct BatchStage {
+    int32_t first, nb, big, forest;       // trees [first, first + nb); big: ONE tree, staged in BatchSmem::big
+    int32_t ncell;                        // cross-count cells in use
+    int32_t K[NB];                        // key-space size of each tree (leaves + 1 for a birth proposal)
+    int16_t xoff[NB][NB];                 // xoff[q][m], m < q: first cell of the pair's (K_m-1) x (K_q-1) table
+    SmallStage st[NB];
+};
+
+// what the next pass applies to the observations of a decided batch, per tree and per (pre-decision) key
+struct ApplyTab {
+    int32_t n, first, forest, pad_;
+    int32_t changed[NB], off[NB];
+    long long DR[2][APCAP];               // fixed-point residual loss, control / treated rows
+    double DG[APCAP];                     // change of the leaf value (goes into the forest's fit)
+    uint8_t NS[APCAP];                    // leaf slot after the move
+};
+
+struct AccTab {                           // CTA-level statistics of the pass (native 32-bit shared atomics)
+    unsigned int btab[NB][KB][2][5];      // (count, four 16-bit limbs) per (tree, key >= 1, group)
+    unsigned int totr[2][5];              // sum of R over all observations (key 0 of every tree = total - others)
+    unsigned int xtab[XCAP][2];           // cross counts per (cell, group)
+};
+struct ResolveTab {                       // the batch's reduced statistics, staged from L2 with one round trip
+    long long tot[NB][KB][2][4];
+    long long x[XCAP][2];
+};
+
+struct BatchSmem {
+    // ---- scratch of propose_stage() / decide_core(): same names as StepShared ----
+    double cnt[KEYS + 1], sphi[KEYS + 1], sphir[KEYS + 1];
+    double pinv[KEYS + 1], plog[KEYS + 1], pmean[KEYS + 1], psd[KEYS + 1];
+    double log_tau;
+    double mu_old[MAXL], mu_new[MAXL];
+    double dlt[KEYS];
+    long long dfx[2][KEYS];
+    double nc1[KEYS + 1], nc0[KEYS + 1];
+    uint8_t remap[MAXL];
+    int32_t ngood[MAXL];
+    uint32_t lkey[MAXL];
+    uint32_t nkey[MAXN];
+    uint8_t nogflag[MAXN];
+    ApplyInfo ai;
+    int32_t accepted;
+    int32_t bad;
+    long long tot[KEYS * 8];
+    // ---- batched engine ----
+    TreeStage big;                        // a big tree in flight / scratch stage of the proposals
+    BatchStage bst[2];
+    ApplyTab ap;
+    union {                               // pass / epilogue tables and the resolve staging never live together
+        AccTab acc;
+        StatTab tab;
+        ResolveTab rs;
+        double red[2 * PTHREADS];
+    } p;
+    long long totr_run[2][2];             // running total of R by group, 128-bit (lo, hi)
+    long long corr[KB][2][2];             // corrected key sums of the tree being decided, 128-bit (lo, hi)
+    int32_t cq[KB][2];                    // pre-decision counts per (key, group) of the tree being decided
+};
+constexpr size_t BATCH_SMEM_BYTES = (sizeof(BatchSmem) + 15) / 16 * 16;
+
+struct BatPtrs { uint32_t R, G, keys; };
+
+__device__ __forceinline__ __int128 i128_from(const long long (&p)[2])
+{
+    return (__int128)(((unsigned __int128)(unsigned long long)p[1] << 64) | (unsigned long long)p[0]);
+}
+__device__ __forceinline__ void i128_to(long long (&p)[2], __int128 v)
+{
+    p[0] = (long long)(unsigned long long)v;
+    p[1] = (long long)(v >> 64);
+}
+__device__ __forceinline__ __int128 limbs_to_i128(long long w0, long long w1, long long w2)
+{
+    return (__int128)w0 + ((__int128)w1 << LIMB_BITS) + ((__int128)w2 << (2 * LIMB_BITS));
+}
+
+// per-lane partial sum -> four 16-bit limbs, reduced over the warp, added to (count, l0..l3) with native atomics
+__device__ __forceinline__ void warp_add16(unsigned int* e, long long s, int lane)
+{
+    int l0 = (int)(s & 0xFFFF), l1 = (int)((s >> 16) & 0xFFFF), l2 = (int)((s >> 32) & 0xFFFF), l3 = (int)(s >> 48);
+    l0 = __reduce_add_sync(0xffffffffu, l0);
+    l1 = __reduce_add_sync(0xffffffffu, l1);
+    l2 = __reduce_add_sync(0xffffffffu, l2);
+    l3 = __reduce_add_sync(0xffffffffu, l3);
+    if (lane < 4) {
+        const int v = lane == 0 ? l0 : lane == 1 ? l1 : lane == 2 ? l2 : l3;
+        if (v != 0) atomicAdd(&e[1 + lane], (unsigned int)v);
+    }
+}
+// word q (0 count, 1..3 the 21-bit limbs of the global representation) of a (count, four 16-bit limbs) entry
+__device__ __forceinline__ long long acc_word(const unsigned int* e, int q)
+{
+    if (q == 0) return (long long)e[0];
+    const __int128 V = (__int128)e[1] + ((__int128)e[2] << 16) + ((__int128)e[3] << 32) + ((__int128)(int)e[4] << 48);
+    if (q == 1) return (long long)(V & 0x1FFFFF);
+    if (q == 2) return (long long)((V >> LIMB_BITS) & 0x1FFFFF);
+    return (long long)(V >> (2 * LIMB_BITS));
+}
+__device__ __forceinline__ void sts_v2(uint32_t a, uint2 v)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void unpack8(uint2 v, int (&out)[8])
+{
+    out[0] = v.x & 0xFF; out[1] = (v.x >> 8) & 0xFF; out[2] = (v.x >> 16) & 0xFF; out[3] = v.x >> 24;
+    out[4] = v.y & 0xFF; out[5] = (v.y >> 8) & 0xFF; out[6] = (v.y >> 16) & 0xFF; out[7] = v.y >> 24;
+}
+// one bit per byte of a pair of 0x00 / 0xFF byte masks -> 8 bits (observation o of the lane = bit o)
+__device__ __forceinline__ uint32_t bytes_to_bits(uint32_t e0, uint32_t e1)
+{
+    return (((e0 & 0x08040201u) * 0x01010101u) >> 24) | (((e1 & 0x80402010u) * 0x01010101u) >> 24);
+}
+
+// keys of one tree for the lane's 8 observations: the cached leaf slot, with the observations a birth proposal would
+// send to the right child re-keyed to `new_slot` (padding observations keep 255)
+__device__ __forceinline__ uint2 tree_keys(const Dev& d, const CurInfo& ci, int tree, int64_t gb)
+{
+    uint2 key = *reinterpret_cast<const uint2*>(d.slots + (int64_t)tree * d.n_pad + gb);
+    if (ci.birth) {
+        uint32_t g0, g1;   // 0xFF where bin > cut
+        if (ci.is16) {
+            const uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ci.bins) + gb);
+            const uint32_t c = (uint32_t)ci.cut;
+            g0 = ((b.x & 0xFFFF) > c ? 0xFFu : 0u) | ((b.x >> 16) > c ? 0xFF00u : 0u) | ((b.y & 0xFFFF) > c ? 0xFF0000u : 0u) |
+                 ((b.y >> 16) > c ? 0xFF000000u : 0u);
+            g1 = ((b.z & 0xFFFF) > c ? 0xFFu : 0u) | ((b.z >> 16) > c ? 0xFF00u : 0u) | ((b.w & 0xFFFF) > c ? 0xFF0000u : 0u) |
+                 ((b.w >> 16) > c ? 0xFF000000u : 0u);
+        } else {
+            const uint2 b = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(ci.bins) + gb);
+            const uint32_t cv = (uint32_t)ci.cut * 0x01010101u;
+            g0 = __vcmpgtu4(b.x, cv);
+            g1 = __vcmpgtu4(b.y, cv);
+        }
+        const uint32_t sxv = (uint32_t)ci.sx * 0x01010101u, nv = (uint32_t)ci.new_slot * 0x01010101u;
+        const uint32_t m0 = __vcmpeq4(key.x, sxv) & g0, m1 = __vcmpeq4(key.y, sxv) & g1;
+        key.x = (key.x & ~m0) | (nv & m0);
+        key.y = (key.y & ~m1) | (nv & m1);
+    }
+    return key;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One warp tile: apply the decided batch `sm.ap` (if do_apply), then accumulate the statistics of batch `cur`.
+// PAD: the tile may hold padding observations (key 255, R = G = 0): only the last tile of each treatment group.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool PAD>
+__device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const BatPtrs& rs, int tile0, int lt, int lane,
+                                           const BatchStage* cur, bool do_apply, bool fswitch)
+{
+    const int tile = tile0 + lt;
+    const int g = tile < d.trt_tiles ? 1 : 0;
+    const int64_t gb = (int64_t)tile * TILE + lane * 8;
+    const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+    const uint32_t ktile = rs.keys + (uint32_t)lt * (uint32_t)(NB * TILE) + (uint32_t)lane * 8u;
+    long long R[8];
+    res_ld8i(rs.R + toff, lane, R);
+    if (do_apply) {
+        const ApplyTab& ap = sm.ap;
+        double G[8];
+        res_ld8(rs.G + toff, lane, G);
+        const int na = ap.n;
+        for (int q = 0; q < na; ++q) {
+            int key[8];
+            unpack8(lds_v2(ktile + (uint32_t)q * TILE), key);
+            const int off = ap.off[q];
+            const long long* DRq = &ap.DR[g][off];
+            const double* DGq = &ap.DG[off];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                if (PAD && key[o] == PAD_SLOT) continue;
+                R[o] -= DRq[key[o]];
+                G[o] += DGq[key[o]];
+            }
+            if (ap.changed[q]) {
+                int ns[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) ns[o] = (PAD && key[o] == PAD_SLOT) ? PAD_SLOT : (int)ap.NS[off + key[o]];
+                st8_u8(d.slots + (int64_t)(ap.first + q) * d.n_pad + gb, ns);
+            }
+        }
+        if (fswitch) {   // forest switch: park the mu forest's fit in HBM, bring the tau forest's in
+            st8_f64(d.Gc + gb, G);
+            ld8_f64(d.Gm + gb, G);
+        }
+        res_st8(rs.G + toff, lane, G);
+        res_st8i(rs.R + toff, lane, R);
+    }
+    if (cur == nullptr) return;
+    if (cur->big) {
+        const CurInfo& ci = sm.big.ci;
+        const uint2 kk = tree_keys(d, ci, cur->first, gb);
+        sts_v2(ktile, kk);
+        int key[8];
+        unpack8(kk, key);
+        accum_tile(sm.p.tab, key, R, g, ci.K, ci.birth != 0, lane, (int)(threadIdx.x >> 5));
+        return;
+    }
+    {   // the total of R: key 0 of every tree of the batch is (total - its other keys), exact in integers
+        long long tot = 0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) tot += R[o];
+        warp_add16(sm.p.acc.totr[g], tot, lane);
+    }
+    unsigned long long Ms[NB];   // per tree: byte k-1 = which of the lane's 8 observations have key k
+    const int nb = cur->nb;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        Ms[q] = 0ull;
+        if (q < nb) {
+            const CurInfo& ci = cur->st[q].ci;
+            const int K = cur->K[q];
+            const uint2 key = tree_keys(d, ci, cur->first + q, gb);
+            sts_v2(ktile + (uint32_t)q * TILE, key);
+            unsigned long long M = 0ull;
+            for (int k = 1; k < K; ++k) {
+                const uint32_t kv = (uint32_t)k * 0x01010101u;
+                const uint32_t bits = bytes_to_bits(__vcmpeq4(key.x, kv), __vcmpeq4(key.y, kv));
+                long long s = 0;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) s += ((bits >> o) & 1u) ? R[o] : 0ll;
+                unsigned int* e = sm.p.acc.btab[q][k][g];
+                warp_add16(e, s, lane);
+                if (ci.birth && k == K - 1) {   // only the would-be right child needs counting: the rest is cached
+                    const int c = __reduce_add_sync(0xffffffffu, __popc(bits));
+                    if (lane == 0 && c) atomicAdd(&e[0], (unsigned int)c);
+                }
+                M |= (unsigned long long)bits << (8 * (k - 1));
+            }
+            if (K > 1) {
+#pragma unroll
+                for (int m = 0; m < q; ++m) {
+                    const int Km = cur->K[m];
+                    if (Km > 1) {
+                        unsigned int* xt = &sm.p.acc.xtab[cur->xoff[q][m]][g];
+                        for (int kp = 1; kp < Km; ++kp) {
+                            const uint32_t bm = (uint32_t)(Ms[m] >> (8 * (kp - 1))) & 0xFFu;
+                            for (int k = 1; k < K; ++k) {
+                                const uint32_t bk = (uint32_t)(M >> (8 * (k - 1))) & 0xFFu;
+                                const int c = __reduce_add_sync(0xffffffffu, __popc(bm & bk));
+                                if (lane == 0 && c) atomicAdd(&xt[2 * ((kp - 1) * (K - 1) + (k - 1))], (unsigned int)c);
+                            }
+                        }
+                    }
+                }
+            }
+            Ms[q] = M;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage the batch that starts at tree `first`: compact copies of up to NB candidate trees with their proposals, then
+// (thread 0) how many of them form the batch.  Reads only what was final before the sweep started.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ inline void stage_big(BatchSmem& sm, BatchStage& B, const Dev& d, const TreeRec* trees)
+{
+    const int t = threadIdx.x;
+    load_tree(&sm.big.tr, &trees[B.first]);
+    __syncthreads();
+    fetch_stage(sm.big, d, B.first, sm.big.tr.nleaves);
+    __syncthreads();
+    if (t == 0) {
+        const int L = sm.big.tr.nleaves;
+        CurInfo& ci = sm.big.ci;
+        ci.active = 1; ci.K = L + (sm.big.prop.move == 1 ? 1 : 0); ci.birth = sm.big.prop.move == 1;
+        ci.sx = sm.big.prop.slot; ci.cut = sm.big.prop.cut; ci.bins = sm.big.prop.bins; ci.is16 = sm.big.prop.is16;
+        ci.forest = B.forest; ci.new_slot = L;
+        B.K[0] = ci.K;
+    }
+    __syncthreads();
+}
+// A big batch keeps its full tree in BatchSmem::big, which the batch in flight may still need: stage_big() is
+// called separately, once that stage is free.
+__device__ inline void stage_batch(BatchSmem& sm, BatchStage& B, const Dev& d, const TreeRec* trees, int first)
+{
+    const int t = threadIdx.x;
+    const int f = (d.f[1].ntree > 0 && first >= d.f[1].tree0) ? 1 : 0;
+    const int fend = f ? d.T : (d.f[1].ntree > 0 ? d.f[1].tree0 : d.T);
+    const int ncand = min(NB, fend - first);
+    {
+        const int q = t >> 6, i = t & 63;
+        if (q < ncand) {
+            const TreeRec* src = &trees[first + q];
+            SmallStage& S = B.st[q];
+            if (i < 2 * KB) {
+                S.tr.parent[i] = __ldcg(&src->parent[i]); S.tr.left[i] = __ldcg(&src->left[i]);
+                S.tr.right[i] = __ldcg(&src->right[i]); S.tr.var[i] = __ldcg(&src->var[i]); S.tr.cut[i] = __ldcg(&src->cut[i]);
+                S.tr.node_slot[i] = __ldcg(&src->node_slot[i]); S.tr.depth[i] = __ldcg(&src->depth[i]);
+                S.tr.heap[i] = __ldcg(&src->heap[i]);
+            } else if (i < 3 * KB) {
+                const int s = i - 2 * KB;
+                S.tr.slot_node[s] = __ldcg(&src->slot_node[s]); S.tr.cnt0[s] = __ldcg(&src->cnt0[s]);
+                S.tr.cnt1[s] = __ldcg(&src->cnt1[s]); S.tr.mu[s] = __ldcg(&src->mu[s]);
+            } else if (i == 3 * KB) {
+                S.tr.nnodes = __ldcg(&src->nnodes); S.tr.nleaves = __ldcg(&src->nleaves);
+            } else if (i >= 32 && i < 32 + (int)(sizeof(Proposal) / 8)) {
+                reinterpret_cast<long long*>(&S.prop)[i - 32] = __ldcg(reinterpret_cast<const long long*>(&d.proprec[first + q].P) + (i - 32));
+            } else if (i >= 48 && i < 48 + KB) {
+                S.z[i - 48] = __ldcg(&d.proprec[first + q].z[i - 48]);
+            }
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        B.first = first; B.forest = f; B.big = 0; B.ncell = 0;
+        int nb = 0, cells = 0;
+        for (int q = 0; q < ncand; ++q) {
+            const SmallStage& S = B.st[q];
+            const int L = S.tr.nleaves, K = L + (S.prop.move == 1 ? 1 : 0);
+            if (K > KB) { if (q == 0) { B.big = 1; nb = 1; } break; }
+            int add = 0;
+            for (int m = 0; m < q; ++m) add += (B.K[m] - 1) * (K - 1);
+            if (cells + add > XCAP) break;
+            for (int m = 0; m < q; ++m) { B.xoff[q][m] = (int16_t)cells; cells += (B.K[m] - 1) * (K - 1); }
+            B.K[q] = K;
+            CurInfo& ci = B.st[q].ci;
+            ci.active = 1; ci.K = K; ci.birth = S.prop.move == 1; ci.sx = S.prop.slot; ci.cut = S.prop.cut;
+            ci.bins = S.prop.bins; ci.is16 = S.prop.is16; ci.forest = f; ci.new_slot = L;
+            nb = q + 1;
+        }
+        B.nb = nb; B.ncell = cells;
+    }
+    __syncthreads();
+}
+
+// clear the pass tables of the batch about to be accumulated
+__device__ inline void begin_batch(BatchSmem& sm, const BatchStage& B)
+{
+    const int t = threadIdx.x;
+    if (B.big) {
+        long long* tb = reinterpret_cast<long long*>(&sm.p.tab);
+        for (int i = t; i < STATTAB_WORDS64; i += blockDim.x) tb[i] = 0;
+    } else {
+        unsigned int* tb = reinterpret_cast<unsigned int*>(&sm.p.acc);
+        const int nw = (int)(offsetof(AccTab, xtab) / 4) + 2 * B.ncell;
+        for (int i = t; i < nw; i += blockDim.x) tb[i] = 0u;
+    }
+}
+
+// CTA tables -> global totals / cross counts (integer REDs: order-independent).  After a __syncthreads().
+__device__ inline void flush_batch(BatchSmem& sm, const BatchStage& B, long long* totals, long long* cross)
+{
+    const int t = threadIdx.x;
+    if (B.big) {
+        const int K = B.K[0];
+        long long* q = totals + (size_t)B.first * KEYS * 8;
+        for (int i = t; i < K * 8; i += blockDim.x) {
+            const long long v = stat_word(sm.p.tab, K, 0, i >> 3, (i >> 2) & 1, i & 3);
+            if (v != 0) atomicAdd((unsigned long long*)&q[i], (unsigned long long)v);
+        }
+        return;
+    }
+    const int nb = B.nb;
+    for (int i = t; i < nb * KB * 8; i += blockDim.x) {
+        const int q = i / (KB * 8), k = (i >> 3) & (KB - 1), g = (i >> 2) & 1, w = i & 3;
+        long long v = 0;
+        if (k == 0) { if (q == 0) v = acc_word(sm.p.acc.totr[g], w); }        // key 0 of the first tree carries the total
+        else if (k < B.K[q]) v = acc_word(sm.p.acc.btab[q][k][g], w);
+        if (v != 0) atomicAdd((unsigned long long*)&totals[(size_t)(B.first + q) * KEYS * 8 + k * 8 + g * 4 + w], (unsigned long long)v);
+    }
+    long long* xg = cross + (size_t)B.first * (XCAP * 2);
+    for (int i = t; i < 2 * B.ncell; i += blockDim.x) {
+        const unsigned int v = sm.p.acc.xtab[i >> 1][i & 1];
+        if (v != 0) atomicAdd((unsigned long long*)&xg[i], (unsigned long long)v);
+    }
+}
+
+__device__ inline void store_small(TreeRec* dst, const TreeSmall& tr)
+{
+    const int t = threadIdx.x;
+    if (t < 2 * KB) {
+        dst->parent[t] = tr.parent[t]; dst->left[t] = tr.left[t]; dst->right[t] = tr.right[t]; dst->var[t] = tr.var[t];
+        dst->cut[t] = tr.cut[t]; dst->node_slot[t] = tr.node_slot[t]; dst->depth[t] = tr.depth[t]; dst->heap[t] = tr.heap[t];
+    } else if (t >= 32 && t < 32 + KB) {
+        const int s = t - 32;
+        dst->slot_node[s] = tr.slot_node[s]; dst->cnt0[s] = tr.cnt0[s]; dst->cnt1[s] = tr.cnt1[s]; dst->mu[s] = tr.mu[s];
+    } else if (t == 64) {
+        dst->nnodes = tr.nnodes; dst->nleaves = tr.nleaves;
+    }
+}
+
+// apply-table rows of a decided tree (keys of the PRE-decision key space)
+template <class Stage>
+__device__ __forceinline__ void fill_apply(BatchSmem& sm, const Stage& S, int q, int off, int L, int K)
+{
+    const int t = threadIdx.x;
+    ApplyTab& ap = sm.ap;
+    if (t < K) {
+        if (t < L) {
+            ap.DR[0][off + t] = sm.dfx[0][t]; ap.DR[1][off + t] = sm.dfx[1][t];
+            ap.DG[off + t] = sm.dlt[t]; ap.NS[off + t] = sm.remap[t];
+        } else {   // the part of leaf sx a birth proposal would have sent right
+            const int sx = S.prop.slot;
+            const bool acc = sm.ai.birth != 0;
+            ap.DR[0][off + t] = acc ? sm.ai.dfx_right[0] : sm.dfx[0][sx];
+            ap.DR[1][off + t] = acc ? sm.ai.dfx_right[1] : sm.dfx[1][sx];
+            ap.DG[off + t] = acc ? sm.ai.dlt_right : sm.dlt[sx];
+            ap.NS[off + t] = acc ? (uint8_t)L : sm.remap[sx];
+        }
+    }
+    if (t == 0) { ap.changed[q] = sm.accepted; ap.off[q] = off; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// After the grid barrier: replay the batch's decisions in tree order from the reduced integers.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d, const Scalars& sc, TreeRec* newtrees,
+                                     const long long* totals, const long long* cross)
+{
+    const int t = threadIdx.x;
+    const ForestDev& F = d.f[B.forest];
+    if (B.big) {
+        const int tree = B.first;
+        const bool writer = ((int)blockIdx.x == tree % (int)gridDim.x);
+        const int L = sm.big.tr.nleaves, K = B.K[0];
+        const long long* q = totals + (size_t)tree * KEYS * 8;
+        for (int i = t; i < K * 8; i += blockDim.x) sm.tot[i] = __ldcg(q + i);
+        decide_core(sm, sm.big, d, F, tree, sc, writer);
+        fill_apply(sm, sm.big, 0, 0, L, K);
+        if (t == 0) { sm.ap.n = 1; sm.ap.first = tree; sm.ap.forest = B.forest; }
+        if (writer) store_tree(&newtrees[tree], &sm.big.tr);
+        __syncthreads();
+        return;
+    }
+    const int nb = B.nb;
+    ResolveTab& rs = sm.p.rs;
+    for (int i = t; i < nb * KB * 8; i += blockDim.x) {
+        const int q = i / (KB * 8), k = (i >> 3) & (KB - 1);
+        if (k < B.K[q]) (&rs.tot[0][0][0][0])[i] = __ldcg(&totals[(size_t)(B.first + q) * KEYS * 8 + (i & (KB * 8 - 1))]);
+    }
+    {
+        const long long* xg = cross + (size_t)B.first * (XCAP * 2);
+        for (int i = t; i < 2 * B.ncell; i += blockDim.x) (&rs.x[0][0])[i] = __ldcg(xg + i);
+    }
+    __syncthreads();
+    if (t < 2) i128_to(sm.totr_run[t], limbs_to_i128(rs.tot[0][0][t][1], rs.tot[0][0][t][2], rs.tot[0][0][t][3]));
+    __syncthreads();
+    for (int q = 0; q < nb; ++q) {
+        SmallStage& S = B.st[q];
+        const int tree = B.first + q;
+        const bool writer = ((int)blockIdx.x == tree % (int)gridDim.x);
+        const int L = S.tr.nleaves, K = B.K[q];
+        const bool birth = S.prop.move == 1;
+        const int sx = S.prop.slot;
+        // pre-decision counts and the corrected sums of keys >= 1
+        if (t < 2 * K) {
+            const int k = t >> 1, g = t & 1;
+            const int cL = birth ? (int)rs.tot[q][L][g][0] : 0;
+            int c;
+            if (k < L) c = (g ? S.tr.cnt1[k] : S.tr.cnt0[k]) - ((birth && k == sx) ? cL : 0);
+            else c = cL;
+            sm.cq[k][g] = c;
+            if (k >= 1) {
+                __int128 v = limbs_to_i128(rs.tot[q][k][g][1], rs.tot[q][k][g][2], rs.tot[q][k][g][3]);
+                for (int m = 0; m < q; ++m) {
+                    const int om = sm.ap.off[m];
+                    const long long D0 = sm.ap.DR[g][om];
+                    v -= (__int128)D0 * c;
+                    const int Km = B.K[m];
+                    if (Km > 1) {
+                        const int base = B.xoff[q][m] + (k - 1);
+                        for (int kp = 1; kp < Km; ++kp)
+                            v -= (__int128)(sm.ap.DR[g][om + kp] - D0) * rs.x[base + (kp - 1) * (K - 1)][g];
+                    }
+                }
+                i128_to(sm.corr[k][g], v);
+            }
+        }
+        __syncthreads();
+        if (t < 2) {   // key 0 = running total - the other keys
+            __int128 v = i128_from(sm.totr_run[t]);
+            for (int k = 1; k < K; ++k) v -= i128_from(sm.corr[k][t]);
+            i128_to(sm.corr[0][t], v);
+        }
+        __syncthreads();
+        if (t < 2 * K) {
+            const int k = t >> 1, g = t & 1;
+            const __int128 v = i128_from(sm.corr[k][g]);
+            long long* o = &sm.tot[k * 8 + g * 4];
+            o[0] = (birth && k == L) ? rs.tot[q][L][g][0] : 0;
+            o[1] = (long long)(v & 0x1FFFFF);
+            o[2] = (long long)((v >> LIMB_BITS) & 0x1FFFFF);
+            o[3] = (long long)(v >> (2 * LIMB_BITS));
+        }
+        decide_core(sm, S, d, F, tree, sc, writer);     // starts with a __syncthreads()
+        fill_apply(sm, S, q, q * KB, L, K);
+        if (writer) store_small(&newtrees[tree], S.tr);
+        __syncthreads();
+        if (t < 2) {   // the residual total after this tree's update
+            __int128 v = i128_from(sm.totr_run[t]);
+            for (int k = 0; k < K; ++k) v -= (__int128)sm.ap.DR[t][q * KB + k] * sm.cq[k][t];
+            i128_to(sm.totr_run[t], v);
+        }
+        __syncthreads();
+    }
+    if (t == 0) { sm.ap.n = nb; sm.ap.first = B.first; sm.ap.forest = B.forest; }
+    __syncthreads();
+}
+
+// proposals of sweep `sweep` for the trees j = blockIdx.x, + gridDim.x, ... from their (visible) HBM records
+__device__ inline void propose_all_b(BatchSmem& sm, const Dev& d, const TreeRec* trees, uint32_t sweep)
+{
+    for (int j = blockIdx.x; j < d.T; j += gridDim.x) {
+        const ForestDev& F = d.f[(d.f[1].ntree > 0 && j >= d.f[1].tree0) ? 1 : 0];
+        load_tree(&sm.big.tr, &trees[j]);
+        __syncthreads();
+        propose_stage(sm, sm.big, d, F, j, sweep);
+        publish_stage(sm.big, d, j);
+        __syncthreads();
+    }
+}
+
+#define BCF_PROF_DECL                                                                                   \
+    const bool prof = (d.prof != nullptr) && blockIdx.x == 0 && t == 0;                                 \
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                                                         \
+    long long tp = clock64();
+#define PROF(k) do { if (prof) { const long long now_ = clock64(); pc[k] += now_ - tp; tp = now_; } } while (0)
+
+__global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, unsigned int* bar, int ntl_max)
+{
+    extern __shared__ __align__(16) unsigned char bcf_dyn_smem[];
+    BatchSmem& sm = *reinterpret_cast<BatchSmem*>(bcf_dyn_smem);
+    unsigned char* dyn = bcf_dyn_smem + BATCH_SMEM_BYTES;
+    __shared__ Scalars scs;
+    __shared__ int bar_ok;
+    const int t = threadIdx.x;
+    const bool writer0 = (blockIdx.x == 0);
+    const int lane = t & 31, wib = t >> 5, wpb = blockDim.x >> 5;
+    unsigned int target = 0;
+    int bad = 0;
+    BCF_PROF_DECL
+    BatPtrs rs;
+    rs.R = (uint32_t)__cvta_generic_to_shared(dyn);
+    rs.G = rs.R + (uint32_t)ntl_max * (TILE * 8u);
+    rs.keys = rs.G + (uint32_t)ntl_max * (TILE * 8u);
+    if (t == 0) { scs = *d.sc; sm.bad = 0; }
+    __syncthreads();
+    const int T = d.T;
+    const int tmod = d.f[1].tree0;
+    const bool has_mod = d.f[1].ntree > 0;
+    const int tile0 = (int)((int64_t)blockIdx.x * d.n_tiles / gridDim.x);
+    const int tile1 = (int)((int64_t)(blockIdx.x + 1) * d.n_tiles / gridDim.x);
+    const int ntl = tile1 - tile0;
+    const int pad_a = d.trt_tiles - 1 - tile0, pad_b = d.n_tiles - 1 - tile0;   // local tiles that may hold padding
+
+    // entry: the residual and the mu forest's fit move into shared memory
+    for (int lt = wib; lt < ntl; lt += wpb) {
+        const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
+        const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+        long long R[8];
+        double gc[8];
+        ld8_i64(d.rfx + gb, R); ld8_f64(d.Gc + gb, gc);
+        res_st8i(rs.R + toff, lane, R);
+        res_st8(rs.G + toff, lane, gc);
+    }
+    __syncthreads();
+    // proposals of the first sweep of this launch (later sweeps: made in the previous sweep's epilogue)
+    propose_all_b(sm, d, d.trees[scs.parity], scs.sweep);
+    grid_arrive(bar, target);
+    if (!grid_wait(bar, target, d.err, &bar_ok)) return;
+
+    for (int sw = 0; sw < nsweeps; ++sw) {
+        const Scalars sc = scs;
+        const int par = sc.parity;
+        long long* mom = d.mom + (size_t)(sc.sweep & 1u) * (2 * NMOM * 3);
+        long long* totals = sweep_totals(d, sc.sweep);
+        long long* cross = d.cross + (size_t)(sc.sweep & 1u) * (size_t)T * (XCAP * 2);
+        if (t == 0) sm.ap.n = 0;
+        stage_batch(sm, sm.bst[0], d, d.trees[par], 0);
+        if (sm.bst[0].big) stage_big(sm, sm.bst[0], d, d.trees[par]);
+        begin_batch(sm, sm.bst[0]);
+        __syncthreads();
+        PROF(6);
+        int first = 0, bi = 0;
+        while (first < T) {
+            BatchStage& B = sm.bst[bi & 1];
+            BatchStage& Bn = sm.bst[(bi + 1) & 1];
+            const int nb = B.nb;
+            const bool do_apply = sm.ap.n > 0;
+            const bool fswitch = has_mod && first == tmod && first > 0;
+            for (int lt = wib; lt < ntl; lt += wpb) {
+                if (lt == pad_a || lt == pad_b) batch_tile<true>(sm, d, rs, tile0, lt, lane, &B, do_apply, fswitch);
+                else batch_tile<false>(sm, d, rs, tile0, lt, lane, &B, do_apply, fswitch);
+            }
+            __syncthreads();
+            PROF(0);
+            flush_batch(sm, B, totals, cross);
+            grid_arrive(bar, target);
+            PROF(1);
+            if (first + nb < T) stage_batch(sm, Bn, d, d.trees[par], first + nb);   // while the barrier is in flight
+            PROF(5);
+            if (!grid_wait(bar, target, d.err, &bar_ok)) return;
+            PROF(2);
+            resolve_batch(sm, B, d, sc, d.trees[par ^ 1], totals, cross);
+            PROF(3);
+            first += nb; ++bi;
+            if (first < T) {
+                if (Bn.big) stage_big(sm, Bn, d, d.trees[par]);   // BatchSmem::big is free only now
+                begin_batch(sm, Bn);
+            }
+            __syncthreads();
+            PROF(4);
+        }
+        // ---- epilogue: apply the last batch, moments of (y, Gc, Gm) ----
+        {
+            long long* tb = reinterpret_cast<long long*>(&sm.p.tab);
+            for (int i = t; i < STATTAB_WORDS64; i += blockDim.x) tb[i] = 0;
+        }
+        __syncthreads();
+        {
+            const bool fswitch = false;
+            for (int lt = wib; lt < ntl; lt += wpb) {
+                if (lt == pad_a || lt == pad_b) batch_tile<true>(sm, d, rs, tile0, lt, lane, nullptr, true, fswitch);
+                else batch_tile<false>(sm, d, rs, tile0, lt, lane, nullptr, true, fswitch);
+                const int tile = tile0 + lt;
+                const int64_t gb = (int64_t)tile * TILE + lane * 8;
+                double G[8], y[8], other[8];
+                res_ld8(rs.G + (uint32_t)lt * (TILE * 8u), lane, G);
+                ld8_f64(d.y + gb, y);
+                if (has_mod) { ld8_f64(d.Gc + gb, other); moments8(sm.p.tab, y, other, G, tile < d.trt_tiles ? 1 : 0, lane, bad); }
+                else {
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) other[o] = 0.0;
+                    moments8(sm.p.tab, y, G, other, tile < d.trt_tiles ? 1 : 0, lane, bad);
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const int nwarps = blockDim.x >> 5;
+            for (int i = t; i < NMOM * 8; i += blockDim.x) {
+                const int m = i >> 3, g = (i >> 2) & 1, q = i & 3;
+                if (q == 0) continue;
+                const long long v = table_word(sm.p.tab, nwarps, m, g, q);
+                if (v != 0) atomicAdd((unsigned long long*)&mom[(g * NMOM + m) * 3 + (q - 1)], (unsigned long long)v);
+            }
+        }
+        grid_arrive(bar, target);
+        if (!grid_wait(bar, target, d.err, &bar_ok)) return;
+        sweep_scalars(d, d.trees[par ^ 1], mom, sm.p.red, &scs, writer0);
+        if (sw + 1 < nsweeps) propose_all_b(sm, d, d.trees[par ^ 1], sc.sweep + 1u);   // every tree record is visible now
+        grid_arrive(bar, target);   // the proposals must be visible before the next sweep stages them (wait: below)
+        // ---- finishing pass: posterior accumulation, residual re-derived with the new scales, back to the mu forest ----
+        {
+            const Scalars sn = scs;
+            const double ms = sn.mscale, b1 = sn.bscale1, b0 = sn.bscale0;
+            const int row = sn.save_row;
+            for (int lt = wib; lt < ntl; lt += wpb) {
+                const int tile = tile0 + lt;
+                const int64_t gb = (int64_t)tile * TILE + lane * 8;
+                const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+                const double b = tile < d.trt_tiles ? b1 : b0;
+                double gc[8], gm[8], y[8];
+                long long R[8];
+                ld8_f64(d.y + gb, y);
+                if (has_mod) { res_ld8(rs.G + toff, lane, gm); ld8_f64(d.Gc + gb, gc); st8_f64(d.Gm + gb, gm); res_st8(rs.G + toff, lane, gc); }
+                else {
+                    res_ld8(rs.G + toff, lane, gc);
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) gm[o] = 0.0;
+                }
+#pragma unroll
+                for (int o = 0; o < 8; ++o) R[o] = resync_fx(y[o], ms, gc[o], b, gm[o], bad);
+                res_st8i(rs.R + toff, lane, R);
+                if (row >= 0) {
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const int64_t i = gb + o;
+                        const double mu = ms * gc[o], yh = mu + b * gm[o], tau = (b1 - b0) * gm[o];
+                        d.tau_sum[i] += tau; d.tau_sq[i] += tau * tau; d.mu_sum[i] += mu; d.yhat_sum[i] += yh;
+                        if (d.draws_tau) d.draws_tau[(int64_t)row * d.n_pad + i] = tau;
+                        if (d.draws_mu) d.draws_mu[(int64_t)row * d.n_pad + i] = mu;
+                        if (d.draws_yhat) d.draws_yhat[(int64_t)row * d.n_pad + i] = yh;
+                    }
+                }
+            }
+            const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + t, gstride = (int64_t)gridDim.x * blockDim.x;
+            const int64_t ntot = (int64_t)T * KEYS * 8;
+            for (int64_t i = gtid; i < ntot; i += gstride) totals[i] = 0;
+            const int64_t nx = (int64_t)T * XCAP * 2;
+            for (int64_t i = gtid; i < nx; i += gstride) cross[i] = 0;
+            long long* mom_next = d.mom + (size_t)((sc.sweep + 1u) & 1u) * (2 * NMOM * 3);
+            for (int64_t i = gtid; i < 2 * NMOM * 3; i += gstride) mom_next[i] = 0;
+        }
+        if (!grid_wait(bar, target, d.err, &bar_ok)) return;
+        PROF(6);
+    }
+    // exit: park the state in HBM in the form every engine understands (Gm was stored by the finishing pass)
+    for (int lt = wib; lt < ntl; lt += wpb) {
+        const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
+        const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+        double G[8];
+        long long R[8];
+        res_ld8(rs.G + toff, lane, G);
+        res_ld8i(rs.R + toff, lane, R);
+        st8_f64(d.Gc + gb, G);
+        st8_i64(d.rfx + gb, R);
+    }
+    if (prof) for (int k = 0; k < 8; ++k) d.prof[k] += pc[k];
+    if (bad) atomicOr(d.err, ERR_FX_RANGE);
+    if (t == 0 && sm.bad) atomicOr(d.err, sm.bad);
+}
+
+#undef PROF
+#undef BCF_PROF_DECL
+
+}  // namespace bcf

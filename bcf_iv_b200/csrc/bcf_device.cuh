@@ -36,18 +36,21 @@ enum { ERR_NAN = 1, ERR_FX_RANGE = 2, ERR_BARRIER_TIMEOUT = 4 };
 // ---------------------------------------------------------------------------------------------
 // Flat tree.  Node 0 is the root; nodes are kept compact (swap-with-last on death).
 // ---------------------------------------------------------------------------------------------
-struct __align__(16) TreeRec {
+template <int NN, int NL>
+struct __align__(16) TreeT {
+    static constexpr int kNodes = NN, kLeaves = NL;
     int32_t nnodes, nleaves;
     int32_t pad_[2];
-    int16_t parent[MAXN], left[MAXN], right[MAXN];   // -1 = none
-    uint16_t var[MAXN], cut[MAXN];                   // split rule of internal nodes
-    uint8_t node_slot[MAXN];                         // leaf slot of leaf nodes
-    uint8_t depth[MAXN];
-    uint32_t heap[MAXN];                             // heap id: root 1, children 2i / 2i+1
-    int16_t slot_node[MAXL];                         // node of each leaf slot
-    int32_t cnt0[MAXL], cnt1[MAXL];                  // observations in the leaf, control / treated (all shards)
-    double mu[MAXL];                                 // leaf value per slot
+    int16_t parent[NN], left[NN], right[NN];       // -1 = none
+    uint16_t var[NN], cut[NN];                     // split rule of internal nodes
+    uint8_t node_slot[NN];                         // leaf slot of leaf nodes
+    uint8_t depth[NN];
+    uint32_t heap[NN];                             // heap id: root 1, children 2i / 2i+1
+    int16_t slot_node[NL];                         // node of each leaf slot
+    int32_t cnt0[NL], cnt1[NL];                    // observations in the leaf, control / treated (all shards)
+    double mu[NL];                                 // leaf value per slot
 };
+using TreeRec = TreeT<MAXN, MAXL>;                 // the HBM record of every tree
 static_assert(sizeof(TreeRec) % 16 == 0, "TreeRec must be copyable as uint4");
 
 struct Proposal {
@@ -104,7 +107,8 @@ struct Dev {
     uint8_t* slots;            // [T][n_pad]
     TreeRec* trees[2];
     PropRec* proprec;          // [T] proposals of the sweep in progress
-    long long* totals;         // [T][KEYS][2][4]  (count, limb0, limb1, limb2) by (key, group)
+    long long* totals;         // [2][T][KEYS][2][4]  (count, limb0, limb1, limb2) by (key, group); see sweep_totals
+    long long* cross;          // [2][T][XCAP][2] cross counts of the batched engine, indexed by the batch's first tree
     long long* mom;            // [2 buffers][2 groups][NMOM][3]; sweep s uses buffer s & 1
     Scalars* sc;
     int32_t* err;              // device error flags (ERR_*)
@@ -117,6 +121,15 @@ struct Dev {
     int32_t post_cap;
     long long* prof;           // optional [16] cycle counters of CTA 0 (persistent engine), null = off
 };
+
+// The persistent engines alternate between two statistics buffers by sweep parity: every sweep zeroes the buffer it
+// used in its finishing pass, and a whole sweep (many grid barriers) passes before that buffer is added to again, so a
+// CTA that is still zeroing can never erase the first REDs of a CTA that already started the next sweep.  The graph
+// engine (kernel boundaries order everything) always uses buffer 0.  Between sweeps both buffers are all zero.
+__device__ __forceinline__ long long* sweep_totals(const Dev& d, uint32_t sweep)
+{
+    return d.totals + (size_t)(sweep & 1u) * (size_t)d.T * KEYS * 8;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10, same addressing as the oracle: counter = (sweep, tree, purpose, idx)
@@ -367,7 +380,8 @@ __device__ __forceinline__ const void* bin_column(const ForestDev& F, int v, int
 // Tree structure helpers (run by single threads on a TreeRec staged in shared memory)
 // ---------------------------------------------------------------------------------------------
 // usable cutpoint range of variable v at `node` (tree::rg)
-__device__ inline void tree_rg(const TreeRec& tr, const ForestDev& F, int node, int v, int& lo, int& hi)
+template <class Tree>
+__device__ inline void tree_rg(const Tree& tr, const ForestDev& F, int node, int v, int& lo, int& hi)
 {
     lo = 0; hi = F.ncut[v] - 1;
     int child = node;
@@ -379,7 +393,8 @@ __device__ inline void tree_rg(const TreeRec& tr, const ForestDev& F, int node, 
 }
 // Variables exhausted on the path to `node`, ascending; returns how many.  Every variable has >= 1 cutpoint
 // (checked by set_data), so the good variables are exactly the others.
-__device__ inline int tree_exhausted(const TreeRec& tr, const ForestDev& F, int node, int (&ex)[MAX_DEPTH + 2])
+template <class Tree>
+__device__ inline int tree_exhausted(const Tree& tr, const ForestDev& F, int node, int (&ex)[MAX_DEPTH + 2])
 {
     int nex = 0;
     for (int a = tr.parent[node]; a >= 0; a = tr.parent[a]) {
@@ -397,14 +412,16 @@ __device__ inline int tree_exhausted(const TreeRec& tr, const ForestDev& F, int 
     }
     return nex;
 }
-__device__ inline int tree_ngoodvars(const TreeRec& tr, const ForestDev& F, int node)
+template <class Tree>
+__device__ inline int tree_ngoodvars(const Tree& tr, const ForestDev& F, int node)
 {
     if (tr.depth[node] >= MAX_DEPTH) return 0;
     int ex[MAX_DEPTH + 2];
     return F.p - tree_exhausted(tr, F, node, ex);
 }
 // vi-th good variable in increasing order
-__device__ inline int tree_pick_var(const TreeRec& tr, const ForestDev& F, int node, int vi)
+template <class Tree>
+__device__ inline int tree_pick_var(const Tree& tr, const ForestDev& F, int node, int vi)
 {
     int ex[MAX_DEPTH + 2];
     const int nex = tree_exhausted(tr, F, node, ex);
@@ -412,7 +429,8 @@ __device__ inline int tree_pick_var(const TreeRec& tr, const ForestDev& F, int n
     for (int j = 0; j < nex; ++j) if (ex[j] <= v) ++v;
     return v;
 }
-__device__ inline void tree_remove_node(TreeRec& tr, int i)
+template <class Tree>
+__device__ inline void tree_remove_node(Tree& tr, int i)
 {
     const int last = tr.nnodes - 1;
     if (i != last) {

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(THREADS) k_tree_step(Dev d, int prev, int cur)
         __syncthreads();
         fetch_proposal(sm, 0, d, prev, sm.st[0].tr.nleaves);
         __syncthreads();
-        decide(sm, 0, d, F, prev, sc, writer);
+        decide(sm, 0, d, F, prev, sc, writer, d.totals);
         if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.st[0].tr);
         __syncthreads();
     }
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(THREADS) k_tree_step(Dev d, int prev, int cur)
     for (int tile = blockIdx.x * wpb + wib; tile < d.n_tiles; tile += gridDim.x * wpb)
         step_tile(sm, sm.st[1].ci, d, prev, cur, tile, lane);
     __syncthreads();
-    if (cur >= 0) flush_stats(sm, sm.st[1].ci.K, d, cur);
+    if (cur >= 0) flush_stats(sm, sm.st[1].ci.K, d.totals, cur);
     if (threadIdx.x == 0 && sm.bad) atomicOr(d.err, sm.bad);
 }
 
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(THREADS) k_sweep_end(Dev d, int prev)
         __syncthreads();
         fetch_proposal(sm, 0, d, prev, sm.st[0].tr.nleaves);
         __syncthreads();
-        decide(sm, 0, d, F, prev, sc, writer);
+        decide(sm, 0, d, F, prev, sc, writer, d.totals);
         if (writer) store_tree(&d.trees[par ^ 1][prev], &sm.st[0].tr);
         __syncthreads();
     }

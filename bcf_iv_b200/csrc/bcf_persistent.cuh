@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_persistent(Dev d, int nsweeps, 
         const Scalars sc = scs;
         const int par = sc.parity;
         long long* mom = d.mom + (size_t)(sc.sweep & 1u) * (2 * NMOM * 3);
+        long long* totals = sweep_totals(d, sc.sweep);
         if (t == 0) sm.ai.active = 0;
         load_tree(&sm.st[0].tr, &d.trees[par][0]);
         __syncthreads();
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_persistent(Dev d, int nsweeps, 
                 step_tile(sm, sm.st[s].ci, d, j - 1, j, tile, lane);
             __syncthreads();
             PROF(0);
-            flush_stats(sm, sm.st[s].ci.K, d, j);
+            flush_stats(sm, sm.st[s].ci.K, totals, j);
             grid_arrive(bar, target);
             PROF(1);
             if (j + 1 < T) {   // stage tree j+1 while the barrier is in flight
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_persistent(Dev d, int nsweeps, 
             PROF(5);
             if (!grid_wait(bar, target, d.err, &bar_ok)) return;
             PROF(2);
-            decide(sm, s, d, d.f[fj], j, sc, writer);
+            decide(sm, s, d, d.f[fj], j, sc, writer, totals);
             PROF(3);
             if (writer) store_tree(&d.trees[par ^ 1][j], &sm.st[s].tr);
             PROF(4);
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_persistent(Dev d, int nsweeps, 
             }
             const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + t, gstride = (int64_t)gridDim.x * blockDim.x;
             const int64_t ntot = (int64_t)T * KEYS * 8;
-            for (int64_t i = gtid; i < ntot; i += gstride) d.totals[i] = 0;
+            for (int64_t i = gtid; i < ntot; i += gstride) totals[i] = 0;
             long long* mom_next = d.mom + (size_t)((sc.sweep + 1u) & 1u) * (2 * NMOM * 3);
             for (int64_t i = gtid; i < 2 * NMOM * 3; i += gstride) mom_next[i] = 0;
         }
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_resident(Dev d, int nsweeps, un
         const Scalars sc = scs;
         const int par = sc.parity;
         long long* mom = d.mom + (size_t)(sc.sweep & 1u) * (2 * NMOM * 3);
+        long long* totals = sweep_totals(d, sc.sweep);
         if (t == 0) sm.ai.active = 0;
         load_tree(&sm.st[0].tr, &d.trees[par][0]);
         __syncthreads();
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_resident(Dev d, int nsweeps, un
                 res_tile(sm, sm.st[s].ci, d, rs, j - 1, s ^ 1, s, tile0, lt, lane, do_apply, true);
             __syncthreads();
             PROF(0);
-            flush_stats(sm, sm.st[s].ci.K, d, j);
+            flush_stats(sm, sm.st[s].ci.K, totals, j);
             grid_arrive(bar, target);
             PROF(1);
             if (j + 1 < T) {   // stage tree j+1 while the barrier is in flight
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_resident(Dev d, int nsweeps, un
             PROF(5);
             if (!grid_wait(bar, target, d.err, &bar_ok)) return;
             PROF(2);
-            decide(sm, s, d, d.f[fj], j, sc, writer);
+            decide(sm, s, d, d.f[fj], j, sc, writer, totals);
             PROF(3);
             if (writer) store_tree(&d.trees[par ^ 1][j], &sm.st[s].tr);
             cp_async_wait_all();
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_resident(Dev d, int nsweeps, un
             }
             const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + t, gstride = (int64_t)gridDim.x * blockDim.x;
             const int64_t ntot = (int64_t)T * KEYS * 8;
-            for (int64_t i = gtid; i < ntot; i += gstride) d.totals[i] = 0;
+            for (int64_t i = gtid; i < ntot; i += gstride) totals[i] = 0;
             long long* mom_next = d.mom + (size_t)((sc.sweep + 1u) & 1u) * (2 * NMOM * 3);
             for (int64_t i = gtid; i < 2 * NMOM * 3; i += gstride) mom_next[i] = 0;
         }

@@ -36,12 +36,14 @@ struct CurInfo {
 
 // A tree in flight: its structure, its proposal, the leaf normals and the statistics-pass set-up.  Two stages, so
 // that tree j+1 can be proposed while tree j still waits for its reduced statistics.
-struct TreeStage {
-    TreeRec tr;
+template <class Tree, int NZ>
+struct TreeStageT {
+    Tree tr;
     Proposal prop;
-    double z[KEYS];                // standard normal of each (current, then new) leaf slot
+    double z[NZ];                  // standard normal of each (current, then new) leaf slot
     CurInfo ci;
 };
+using TreeStage = TreeStageT<TreeRec, KEYS>;
 
 struct StepShared {
     TreeStage st[2];
@@ -82,10 +84,10 @@ __device__ inline void store_tree(TreeRec* dst, const TreeRec* src)
 // propose(): one birth/death proposal for the tree staged in sm.tr (bcf's bd(), structural half)
 // [bcf-recall, SURVEY A.3 step 2].  All threads of the CTA take part; result in sm.prop, sm.z.
 // ---------------------------------------------------------------------------------------------
-__device__ inline void propose(StepShared& sm, int stage, const Dev& d, const ForestDev& F, int tree, uint32_t sweep)
+template <class SM, class Stage>
+__device__ inline void propose_stage(SM& sm, Stage& S, const Dev& d, const ForestDev& F, int tree, uint32_t sweep)
 {
-    TreeStage& S = sm.st[stage];
-    TreeRec& tr = S.tr;
+    auto& tr = S.tr;
     const int t = threadIdx.x;
     const int L = tr.nleaves, NN = tr.nnodes;
     const Rng rng{d.key0, d.key1};
@@ -202,22 +204,35 @@ __device__ inline void propose(StepShared& sm, int stage, const Dev& d, const Fo
     __syncthreads();
 }
 
-// publish a staged proposal (and leaf normals) to HBM / fetch it back into a stage
-__device__ inline void publish_proposal(const StepShared& sm, int stage, const Dev& d, int tree)
+__device__ inline void propose(StepShared& sm, int stage, const Dev& d, const ForestDev& F, int tree, uint32_t sweep)
 {
-    const TreeStage& S = sm.st[stage];
+    propose_stage(sm, sm.st[stage], d, F, tree, sweep);
+}
+
+// publish a staged proposal (and leaf normals) to HBM / fetch it back into a stage
+template <class Stage>
+__device__ inline void publish_stage(const Stage& S, const Dev& d, int tree)
+{
     PropRec* R = d.proprec + tree;
     const int t = threadIdx.x;
     if (t == 0) R->P = S.prop;
     if (t >= 32 && t - 32 < S.tr.nleaves) R->z[t - 32] = S.z[t - 32];
 }
-__device__ inline void fetch_proposal(StepShared& sm, int stage, const Dev& d, int tree, int nleaves)
+__device__ inline void publish_proposal(const StepShared& sm, int stage, const Dev& d, int tree)
 {
-    TreeStage& S = sm.st[stage];
+    publish_stage(sm.st[stage], d, tree);
+}
+template <class Stage>
+__device__ inline void fetch_stage(Stage& S, const Dev& d, int tree, int nleaves)
+{
     const PropRec* R = d.proprec + tree;
     const int t = threadIdx.x;
     if (t < (int)(sizeof(Proposal) / 8)) reinterpret_cast<long long*>(&S.prop)[t] = __ldcg(reinterpret_cast<const long long*>(&R->P) + t);
     if (t >= 32 && t - 32 < nleaves) S.z[t - 32] = __ldcg(&R->z[t - 32]);
+}
+__device__ inline void fetch_proposal(StepShared& sm, int stage, const Dev& d, int tree, int nleaves)
+{
+    fetch_stage(sm.st[stage], d, tree, nleaves);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -239,11 +254,12 @@ __device__ __forceinline__ void key_raw(const long long* tot, int key, double& S
     c1 = (double)q[4]; c0 = (double)q[0];
 }
 
-__device__ inline void decide(StepShared& sm, int stage, const Dev& d, const ForestDev& F, int tree, const Scalars& sc,
-                              bool writer)
+// decide_core(): the statistics of the tree are already in sm.tot (K x [control: count, limb0..2][treated: ...])
+template <class SM, class Stage>
+__device__ inline void decide_core(SM& sm, Stage& S, const Dev& d, const ForestDev& F, int tree, const Scalars& sc,
+                                   bool writer)
 {
-    TreeStage& S = sm.st[stage];
-    TreeRec& tr = S.tr;
+    auto& tr = S.tr;
     const Proposal P = S.prop;
     const int t = threadIdx.x;
     const int L = tr.nleaves;
@@ -254,11 +270,6 @@ __device__ inline void decide(StepShared& sm, int stage, const Dev& d, const For
     // the two keys a move pools: birth (leaf part staying left, would-be right child), death (the two children)
     const int pa = P.slot, pb = (P.move == 1) ? L : P.slot_b;
 
-    // reduced by integer atomics in L2: stage them with ONE round trip, straight from L2 (never a stale L1 line)
-    {
-        const long long* q = d.totals + (size_t)tree * KEYS * 8;
-        for (int i = t; i < K * 8; i += blockDim.x) sm.tot[i] = __ldcg(q + i);
-    }
     if (t < MAXL) { sm.remap[t] = (uint8_t)t; if (t < L) sm.mu_old[t] = tr.mu[t]; }
     __syncthreads();
 
@@ -394,6 +405,18 @@ __device__ inline void decide(StepShared& sm, int stage, const Dev& d, const For
     __syncthreads();
 }
 
+// `totals`: the statistics buffer of the sweep in progress (see sweep_totals)
+__device__ inline void decide(StepShared& sm, int stage, const Dev& d, const ForestDev& F, int tree, const Scalars& sc,
+                              bool writer, const long long* totals)
+{
+    TreeStage& S = sm.st[stage];
+    const int K = S.tr.nleaves + (S.prop.move == 1 ? 1 : 0);
+    // reduced by integer atomics in L2: stage them with ONE round trip, straight from L2 (never a stale L1 line)
+    const long long* q = totals + (size_t)tree * KEYS * 8;
+    for (int i = threadIdx.x; i < K * 8; i += blockDim.x) sm.tot[i] = __ldcg(q + i);
+    decide_core(sm, S, d, F, tree, sc, writer);
+}
+
 // Set up the statistics pass for the proposal in sm.prop (tree staged in sm.tr) and clear the CTA table.
 __device__ inline void begin_stats(StepShared& sm, int stage, int forest, const Scalars& sc)
 {
@@ -411,9 +434,9 @@ __device__ inline void begin_stats(StepShared& sm, int stage, int forest, const 
 
 // flush the CTA table into the global totals of `tree` (integer REDs: order-independent).  Must be entered by every
 // thread of the CTA after a __syncthreads() that ends the tile pass.
-__device__ inline void flush_stats(StepShared& sm, int K, const Dev& d, int tree)
+__device__ inline void flush_stats(StepShared& sm, int K, long long* totals, int tree)
 {
-    long long* q = d.totals + (size_t)tree * KEYS * 8;
+    long long* q = totals + (size_t)tree * KEYS * 8;
     const int t = threadIdx.x;
     if (K <= KREG) {
         // sum the warps' private tables: 16 lanes per (key, group, word) entry, then a shuffle tree

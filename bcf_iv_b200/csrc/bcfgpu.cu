@@ -3,6 +3,7 @@
 #include "../../include/bcfgpu.h"
 #include "bcf_kernels.cuh"
 #include "bcf_persistent.cuh"
+#include "bcf_batched.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -104,7 +105,8 @@ struct bcfgpu_handle {
     int grid_obs = 0, grid_fin = 0;
     int engine = BCFGPU_ENGINE_GRAPH;
     int coop_grid = 0;
-    int res_ntl = 0;                  // tiles per CTA of the shared-memory-resident kernel (0 = state in HBM)
+    int res_ntl = 0;                  // tiles per CTA of the shared-memory-resident kernels (0 = state in HBM)
+    int kernel = 0;                   // persistent kernel in use: 1 k_persistent, 2 k_resident, 3 k_batched
     size_t res_smem = 0;
     unsigned int* d_bar = nullptr;
     int64_t launches = 0;
@@ -214,7 +216,8 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_sweep_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (e2 != cudaSuccess) { delete h; return fail(BCFGPU_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e2)); }
-    h->engine = cfg->engine == BCFGPU_ENGINE_AUTO ? BCFGPU_ENGINE_PERSISTENT : cfg->engine;
+    if (cfg->engine < BCFGPU_ENGINE_AUTO || cfg->engine > BCFGPU_ENGINE_BATCHED) { delete h; return fail(BCFGPU_ERR_BAD_ARG, "unknown engine"); }
+    h->engine = cfg->engine == BCFGPU_ENGINE_AUTO ? BCFGPU_ENGINE_BATCHED : cfg->engine;
     *out = h;
     return BCFGPU_OK;
 }
@@ -424,7 +427,8 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     DM(h, &d.slots, (size_t)h->T * n_pad);
     DM(h, &d.trees[0], (size_t)h->T); DM(h, &d.trees[1], (size_t)h->T);
     DM(h, &d.proprec, (size_t)h->T);
-    DM(h, &d.totals, (size_t)h->T * KEYS * 8);
+    DM(h, &d.totals, (size_t)2 * h->T * KEYS * 8);
+    DM(h, &d.cross, (size_t)2 * h->T * XCAP * 2);
     DM(h, &d.mom, (size_t)2 * 2 * NMOM * 3);
     DM(h, &d.sc, 1);
     DM(h, &d.err, 4);
@@ -434,7 +438,8 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     DM(h, &h->d_bar, 64);
     if (getenv("BCFGPU_PROFILE")) { DM(h, &d.prof, 16); CK(cudaMemsetAsync(d.prof, 0, 128, h->stream)); }
     d.y = dy;
-    CK(cudaMemsetAsync(d.totals, 0, (size_t)h->T * KEYS * 8 * 8, h->stream));
+    CK(cudaMemsetAsync(d.totals, 0, (size_t)2 * h->T * KEYS * 8 * 8, h->stream));
+    CK(cudaMemsetAsync(d.cross, 0, (size_t)2 * h->T * XCAP * 2 * 8, h->stream));
     CK(cudaMemsetAsync(d.mom, 0, 2 * 2 * NMOM * 3 * 8, h->stream));
     CK(cudaMemsetAsync(d.err, 0, 16, h->stream));
     CK(cudaMemsetAsync(d.trace, 0, (size_t)h->T * 5 * 4, h->stream));
@@ -583,7 +588,7 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
     CK(cudaMemcpyAsync(d.sc, &sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
     h->nsaved = 0;
     int rc = BCFGPU_OK;
-    const bool persistent = (h->engine == BCFGPU_ENGINE_PERSISTENT || h->engine == BCFGPU_ENGINE_PERSISTENT_HBM) && h->nranks == 1;
+    const bool persistent = h->engine != BCFGPU_ENGINE_GRAPH && h->nranks == 1;
     if (!persistent && h->nranks == 1) { if ((rc = build_graph(h))) return rc; }
     CK(cudaEventRecord(h->ev0, h->stream));
     if (persistent) {
@@ -1070,27 +1075,41 @@ static int run_persistent(bcfgpu_handle* h, int total)
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
         if (!coop) return fail(BCFGPU_ERR_CUDA, "device does not support cooperative launch");
-        h->coop_grid = h->num_sms * PERSIST_CTAS_PER_SM;
-        // resident variant: does this CTA's share of the tiles fit in shared memory next to the static part?
-        cudaFuncAttributes fa;
-        CK(cudaFuncGetAttributes(&fa, k_resident));
         int max_optin = 0;
         CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-        const int grid = std::min<int>(h->coop_grid, std::max(1, h->dev.n_tiles));
+        const int grid = std::min<int>(h->num_sms * PERSIST_CTAS_PER_SM, std::max(1, h->dev.n_tiles));
         const int ntl_max = (h->dev.n_tiles + grid - 1) / grid;
-        const size_t need = STEP_SMEM_BYTES + (size_t)ntl_max * RES_BYTES_PER_TILE;
         h->res_ntl = 0;
-        if (h->engine != BCFGPU_ENGINE_PERSISTENT_HBM && !getenv("BCFGPU_NO_RESIDENT") && need + fa.sharedSizeBytes + 1024 <= (size_t)max_optin) {
-            CK(cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        h->kernel = 0;
+        const bool want_batched = h->engine == BCFGPU_ENGINE_BATCHED || h->cfg.engine == BCFGPU_ENGINE_AUTO;
+        const bool may_reside = h->engine != BCFGPU_ENGINE_PERSISTENT_HBM && !getenv("BCFGPU_NO_RESIDENT");
+        // does this CTA's share of the observation state fit in shared memory next to the kernel's scratch?
+        auto fits = [&](const void* fn, size_t need) -> int {
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) return 0;
+            if (need + fa.sharedSizeBytes + 1024 > (size_t)max_optin) return 0;
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) return 0;
             int per_sm = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resident, PTHREADS, need));
-            if (per_sm >= 1) { h->res_ntl = ntl_max; h->res_smem = need; }
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PTHREADS, need) != cudaSuccess) return 0;
+            return per_sm >= 1;
+        };
+        if (want_batched && may_reside) {
+            const size_t need = BATCH_SMEM_BYTES + (size_t)ntl_max * BAT_BYTES_PER_TILE;
+            if (fits((const void*)k_batched, need)) { h->kernel = 3; h->res_ntl = ntl_max; h->res_smem = need; }
+            else if (h->cfg.engine == BCFGPU_ENGINE_BATCHED)
+                return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_BATCHED: the observations of one SM do not fit in shared memory at this n");
         }
-        if (h->res_ntl == 0) {
+        if (h->kernel == 0 && may_reside) {
+            const size_t need = STEP_SMEM_BYTES + (size_t)ntl_max * RES_BYTES_PER_TILE;
+            if (fits((const void*)k_resident, need)) { h->kernel = 2; h->res_ntl = ntl_max; h->res_smem = need; }
+        }
+        if (h->kernel == 0) {
             int per_sm = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PTHREADS, STEP_SMEM_BYTES));
             if (per_sm < 1) return fail(BCFGPU_ERR_CUDA, "persistent kernel does not fit on an SM");
+            h->kernel = 1;
         }
+        cudaGetLastError();
         h->coop_grid = grid;
     }
     // keep launches short enough to stay interruptible (R_CheckUserInterrupt between batches)
@@ -1100,8 +1119,11 @@ static int run_persistent(bcfgpu_handle* h, int total)
         Dev d = h->dev;
         unsigned int* bar = h->d_bar;
         CK(cudaMemsetAsync(bar, 0, 4, h->stream));
-        if (h->res_ntl > 0) {
-            int ntl = h->res_ntl;
+        int ntl = h->res_ntl;
+        if (h->kernel == 3) {
+            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};
+            CK(cudaLaunchCooperativeKernel((const void*)k_batched, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
+        } else if (h->kernel == 2) {
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};
             CK(cudaLaunchCooperativeKernel((const void*)k_resident, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
         } else {

@@ -53,7 +53,10 @@ typedef enum bcfgpu_engine {
     BCFGPU_ENGINE_GRAPH = 1,       /* one kernel per tree, a sweep captured in a CUDA graph */
     BCFGPU_ENGINE_PERSISTENT = 2,  /* one cooperative kernel per batch of sweeps, grid barrier per tree; the
                                       observation state lives in shared memory when the CTA's share fits */
-    BCFGPU_ENGINE_PERSISTENT_HBM = 3 /* same schedule, observation state kept in HBM/L2 (any n) */
+    BCFGPU_ENGINE_PERSISTENT_HBM = 3, /* same schedule, observation state kept in HBM/L2 (any n) */
+    BCFGPU_ENGINE_BATCHED = 4      /* cooperative kernel, up to 8 trees per observation pass and per grid barrier (exact
+                                      integer cross-count correction), state in shared memory; AUTO picks it when the
+                                      observations of an SM fit, else PERSISTENT */
 } bcfgpu_engine;
 
 /* Hyper-parameters of the sampler: bcf()'s arguments after the R wrapper's rescaling. */

@@ -715,6 +715,22 @@ ORC_API int orc_set_tree(orc_sampler *s, int tree_id, int nnodes, const uint32_t
     return 0;
 }
 
+/* rebuild allfit_con / allfit_mod / allfit from the current trees (after orc_set_tree) */
+ORC_API void orc_refit(orc_sampler *s)
+{
+    const int n = s->n;
+    for (int k = 0; k < n; ++k) { s->allfit_con[k] = 0; s->allfit_mod[k] = 0; }
+    for (int j = 0; j < s->cfg.ntree_con; ++j) {
+        fit_tree(s, s->t_con[j], s->xc, s->p_con, &s->xi_c, s->ftemp);
+        for (int k = 0; k < n; ++k) s->allfit_con[k] += s->mscale * s->ftemp[k];
+    }
+    for (int j = 0; j < s->cfg.ntree_mod; ++j) {
+        fit_tree(s, s->t_mod[j], s->xm, s->p_mod, &s->xi_m, s->ftemp);
+        for (int k = 0; k < n; ++k) s->allfit_mod[k] += (k < s->ntrt ? s->bscale1 : s->bscale0) * s->ftemp[k];
+    }
+    for (int k = 0; k < n; ++k) s->allfit[k] = s->allfit_con[k] + s->allfit_mod[k];
+}
+
 /* ---- standalone unit functions on a sampler's data (kernel-level parity) ---- */
 /* leaf heap id each observation falls in, for the given tree of forest `forest` (0 con, 1 mod) */
 ORC_API void orc_assign_leaves(orc_sampler *s, int tree_id, uint32_t *leaf_heap_id)

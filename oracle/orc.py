@@ -68,6 +68,7 @@ def lib():
         L.orc_get_tree.argtypes = [C.c_void_p, C.c_int, up, ip, ip, dp]
         L.orc_set_tree.restype = C.c_int
         L.orc_set_tree.argtypes = [C.c_void_p, C.c_int, C.c_int, up, ip, ip, dp]
+        L.orc_refit.argtypes = [C.c_void_p]
         L.orc_assign_leaves.argtypes = [C.c_void_p, C.c_int, up]
         L.orc_allsuff.restype = C.c_int
         L.orc_allsuff.argtypes = [C.c_void_p, C.c_int, dp, dp, up, dp, dp, dp]
@@ -213,6 +214,9 @@ class OracleSampler:
         rc = lib().orc_set_tree(self.h, tid, len(heap), _up(heap), _ip(var), _ip(cut), _dp(mu))
         if rc != 0:
             raise ValueError("bad serialised tree")
+
+    def refit(self):
+        lib().orc_refit(self.h)
 
     def assign_leaves(self, tid):
         o = np.zeros(self.n, dtype=np.uint32)

@@ -14,7 +14,7 @@ ap.add_argument("--n", type=int, default=1000000)
 ap.add_argument("--p", type=int, default=100)
 ap.add_argument("--sweeps", type=int, default=50)
 ap.add_argument("--warm", type=int, default=20)
-ap.add_argument("--engines", default="1,2")
+ap.add_argument("--engines", default="4,2")
 a = ap.parse_args()
 
 t0 = time.time()

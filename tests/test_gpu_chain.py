@@ -41,7 +41,7 @@ def _compare_state(g, o, pr, check_trees=True):
             assert np.allclose(mg[og][leaf], mo[oo][leaf], rtol=TOL, atol=TOL)
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3])
+@pytest.mark.parametrize("engine", [1, 2, 3, 4])
 def test_chain_matches_oracle_readme_shape(engine):
     """Config C1 shape (n_s = 500, p = 10 binary + pihat): 30 sweeps, compared after 1, 5 and 30."""
     pr = make_problem(n=500, p=10, seed=3)
@@ -56,7 +56,7 @@ def test_chain_matches_oracle_readme_shape(engine):
     assert g.verify_leaf_cache() == 0
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3])
+@pytest.mark.parametrize("engine", [1, 2, 3, 4])
 def test_chain_matches_oracle_continuous_covariates(engine):
     """Continuous X -> 10 000-cutpoint uint16 grids on most columns; ragged n (not a multiple of the tile)."""
     pr = make_problem(n=1237, p=6, seed=5, continuous=True)
@@ -93,16 +93,18 @@ def test_posterior_outputs_match_oracle():
 
 def test_engines_are_bit_identical():
     """The residual is an integer (fixed-point) state updated exactly and every reduction is an integer sum, so the
-    three engines -- graph, persistent with the state in HBM, persistent with the state in shared memory -- walk the
-    same chain bit for bit whatever their thread / CTA partitioning."""
+    four engines -- graph, persistent with the state in HBM, persistent with the state in shared memory, and the
+    batched engine (8 trees per pass, exact cross-count correction) -- walk the same chain bit for bit whatever
+    their thread / CTA partitioning."""
     pr = make_problem(n=3000, p=12, seed=21)
     kw = dict(seed=4, ntree_con=50, ntree_mod=20)
     a = gpu_sampler(pr, engine=1, **kw)
     b = gpu_sampler(pr, engine=3, **kw)
     c = gpu_sampler(pr, engine=2, **kw)
-    for s in (a, b, c):
+    e = gpu_sampler(pr, engine=4, **kw)
+    for s in (a, b, c, e):
         s.run(5, 10)
-    for other in (b, c):
+    for other in (b, c, e):
         assert np.array_equal(a.tau_mean(), other.tau_mean())
         assert np.array_equal(a.mu_mean(), other.mu_mean())
         assert np.array_equal(a.sigma(), other.sigma())
@@ -124,3 +126,28 @@ def test_engine_handover():
     mix.run(8, 0)
     _compare_state(mix, o, pr)
     _compare_state(ref, o, pr)
+
+
+@pytest.mark.parametrize("engine", [2, 4])
+def test_chain_with_big_and_small_trees_mixed(engine):
+    """Trees with more than 8 keys take the batched engine's solo path (shared-atomics table), the others are batched
+    around them; install deep trees in both forests, then walk the chain against the oracle."""
+    from test_gpu_kernels import _random_tree
+    pr = make_problem(n=2500, p=8, seed=31, continuous=True)
+    kw = dict(seed=6, ntree_con=21, ntree_mod=11)
+    g = gpu_sampler(pr, engine=engine, **kw)
+    o = oracle_sampler(pr, max_leaves=128, **kw)
+    rng = np.random.default_rng(12)
+    for tid, nl in ((0, 12), (3, 30), (4, 9), (9, 5), (20, 17), (21, 10), (25, 3), (31, 25)):
+        cuts = pr.P.cuts_c if tid < 21 else pr.P.cuts_m
+        heap, var, cut, mu = _random_tree(rng, [len(c) for c in cuts], nl)
+        mu = mu * 0.05
+        g.set_tree(tid, heap, var, cut, mu)
+        o.set_tree(tid, heap, var, cut, mu)
+    # the oracle keeps its fits incrementally: rebuild them from the installed trees
+    o.refit()
+    for k in (1, 3, 8):
+        g.run(k, 0)
+        o.sweeps(k)
+        _compare_state(g, o, pr)
+    assert g.verify_leaf_cache() == 0
