@@ -27,7 +27,8 @@ namespace bcf {
 
 constexpr int NB = 8;              // trees per batch
 constexpr int KB = 8;              // key-space bound of a batched tree
-constexpr int XCAP = 256;          // cross-count cells of a batch: sum over pairs m<q of (K_m-1)(K_q-1)
+constexpr int MAXC = 16;           // "columns" of a batch: its (tree, key >= 1) pairs, sum of (K_q - 1)
+constexpr int XCAP = 128;          // cross-count cells of a batch: sum over pairs m<q of (K_m-1)(K_q-1) <= MAXC^2/2
 constexpr int APCAP = 136;         // apply-table entries: NB*KB, or the KEYS = 129 of one big tree
 static_assert(APCAP >= KEYS && APCAP >= NB * KB, "apply table too small");
 using TreeSmall = TreeT<2 * KB, KB>;
@@ -36,24 +37,29 @@ constexpr int BAT_BYTES_PER_TILE = TILE * (8 + 8) + NB * TILE;   // R, G, keys o
 
 struct BatchStage {
     int32_t first, nb, big, forest;       // trees [first, first + nb); big: ONE tree, staged in BatchSmem::big
-    int32_t ncell;                        // cross-count cells in use
+    int32_t ncell, ncol;                  // cross-count cells / columns in use
     int32_t K[NB];                        // key-space size of each tree (leaves + 1 for a birth proposal)
     int16_t xoff[NB][NB];                 // xoff[q][m], m < q: first cell of the pair's (K_m-1) x (K_q-1) table
+    uint8_t colbase[NB];                  // first column of each tree (column = colbase[q] + key - 1)
+    uint8_t cell_c1[XCAP], cell_c2[XCAP]; // the two columns of every cross-count cell
     SmallStage st[NB];
 };
 
 // what the next pass applies to the observations of a decided batch, per tree and per (pre-decision) key
-struct ApplyTab {
+struct __align__(16) ApRow {
+    long long dr;                         // fixed-point residual loss
+    double dg;                            // change of the leaf value (goes into the forest's fit)
+};
+struct __align__(16) ApplyTab {
     int32_t n, first, forest, pad_;
     int32_t changed[NB], off[NB];
-    long long DR[2][APCAP];               // fixed-point residual loss, control / treated rows
-    double DG[APCAP];                     // change of the leaf value (goes into the forest's fit)
+    ApRow T[2][APCAP];                    // control / treated rows: one 16-byte load per observation and tree
     uint8_t NS[APCAP];                    // leaf slot after the move
 };
 
 struct AccTab {                           // CTA-level statistics of the pass (native 32-bit shared atomics)
-    unsigned int btab[NB][KB][2][5];      // (count, four 16-bit limbs) per (tree, key >= 1, group)
-    unsigned int totr[2][5];              // sum of R over all observations (key 0 of every tree = total - others)
+    unsigned int btab[NB][KB][2][4];      // (count, three 21-bit limbs) per (tree, key >= 1, group)
+    unsigned int totr[2][4];              // sum of R over all observations (key 0 of every tree = total - others)
     unsigned int xtab[XCAP][2];           // cross counts per (cell, group)
 };
 struct ResolveTab {                       // the batch's reduced statistics, staged from L2 with one round trip
@@ -89,10 +95,11 @@ struct BatchSmem {
         ResolveTab rs;
         double red[2 * PTHREADS];
     } p;
-    long long totr_run[2][2];             // running total of R by group, 128-bit (lo, hi)
-    long long corr[KB][2][2];             // corrected key sums of the tree being decided, 128-bit (lo, hi)
-    int32_t cq[KB][2];                    // pre-decision counts per (key, group) of the tree being decided
+    int32_t cq[NB][KB][2];                // pre-decision counts per (tree of the batch, key, group)
 };
+// what depends only on COUNTS (known before the batch's decisions): precision terms of every key and pooled pair
+struct PreKey { double k1, k0, inv, plog, psd, pad_; };
+static_assert(sizeof(PreKey) * NB * (KB + 1) <= sizeof(long long) * KEYS * 8, "PreKey table aliases BatchSmem::tot");
 constexpr size_t BATCH_SMEM_BYTES = (sizeof(BatchSmem) + 15) / 16 * 16;
 
 struct BatPtrs { uint32_t R, G, keys; };
@@ -111,27 +118,24 @@ __device__ __forceinline__ __int128 limbs_to_i128(long long w0, long long w1, lo
     return (__int128)w0 + ((__int128)w1 << LIMB_BITS) + ((__int128)w2 << (2 * LIMB_BITS));
 }
 
-// per-lane partial sum -> four 16-bit limbs, reduced over the warp, added to (count, l0..l3) with native atomics
-__device__ __forceinline__ void warp_add16(unsigned int* e, long long s, int lane)
+// per-lane partial sum (|s| < 2^62) -> the three 21-bit limbs of the global representation, reduced over the warp
+// and added to (count, l0, l1, l2) with native 32-bit shared atomics.  A CTA table word holds at most
+// tiles * 32 lanes * 2^21, so a flush is due every 63 tiles at the latest (the resident kernel holds < 32).
+__device__ __forceinline__ void warp_add21(unsigned int* e, long long s, int lane)
 {
-    int l0 = (int)(s & 0xFFFF), l1 = (int)((s >> 16) & 0xFFFF), l2 = (int)((s >> 32) & 0xFFFF), l3 = (int)(s >> 48);
+    int l0 = (int)(s & 0x1FFFFF), l1 = (int)((s >> LIMB_BITS) & 0x1FFFFF), l2 = (int)(s >> (2 * LIMB_BITS));
     l0 = __reduce_add_sync(0xffffffffu, l0);
     l1 = __reduce_add_sync(0xffffffffu, l1);
     l2 = __reduce_add_sync(0xffffffffu, l2);
-    l3 = __reduce_add_sync(0xffffffffu, l3);
-    if (lane < 4) {
-        const int v = lane == 0 ? l0 : lane == 1 ? l1 : lane == 2 ? l2 : l3;
-        if (v != 0) atomicAdd(&e[1 + lane], (unsigned int)v);
+    if (lane < 3) {
+        const int v = lane == 0 ? l0 : lane == 1 ? l1 : l2;
+        atomicAdd(&e[1 + lane], (unsigned int)v);
     }
 }
-// word q (0 count, 1..3 the 21-bit limbs of the global representation) of a (count, four 16-bit limbs) entry
+// word q (0 count, 1..3 the limbs; the top limb is signed) of a CTA table entry
 __device__ __forceinline__ long long acc_word(const unsigned int* e, int q)
 {
-    if (q == 0) return (long long)e[0];
-    const __int128 V = (__int128)e[1] + ((__int128)e[2] << 16) + ((__int128)e[3] << 32) + ((__int128)(int)e[4] << 48);
-    if (q == 1) return (long long)(V & 0x1FFFFF);
-    if (q == 2) return (long long)((V >> LIMB_BITS) & 0x1FFFFF);
-    return (long long)(V >> (2 * LIMB_BITS));
+    return q == 3 ? (long long)(int)e[3] : (long long)e[q];
 }
 __device__ __forceinline__ void sts_v2(uint32_t a, uint2 v)
 {
@@ -149,21 +153,30 @@ __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t e0, uint32_t e1)
 }
 
 // keys of one tree for the lane's 8 observations: the cached leaf slot, with the observations a birth proposal would
-// send to the right child re-keyed to `new_slot` (padding observations keep 255)
-__device__ __forceinline__ uint2 tree_keys(const Dev& d, const CurInfo& ci, int tree, int64_t gb)
+// send to the right child re-keyed to `new_slot` (padding observations keep 255).  Split in load / compute so that
+// the loads of the next tree are in flight while this one is processed.
+__device__ __forceinline__ void keys_load(const Dev& d, const CurInfo& ci, int tree, int64_t gb, uint2& sl, uint4& bn)
 {
-    uint2 key = *reinterpret_cast<const uint2*>(d.slots + (int64_t)tree * d.n_pad + gb);
+    sl = *reinterpret_cast<const uint2*>(d.slots + (int64_t)tree * d.n_pad + gb);
+    if (ci.birth) {
+        if (ci.is16) bn = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ci.bins) + gb);
+        else {
+            const uint2 b = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(ci.bins) + gb);
+            bn.x = b.x; bn.y = b.y;
+        }
+    }
+}
+__device__ __forceinline__ uint2 keys_make(const CurInfo& ci, uint2 key, uint4 b)
+{
     if (ci.birth) {
         uint32_t g0, g1;   // 0xFF where bin > cut
         if (ci.is16) {
-            const uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ci.bins) + gb);
             const uint32_t c = (uint32_t)ci.cut;
             g0 = ((b.x & 0xFFFF) > c ? 0xFFu : 0u) | ((b.x >> 16) > c ? 0xFF00u : 0u) | ((b.y & 0xFFFF) > c ? 0xFF0000u : 0u) |
                  ((b.y >> 16) > c ? 0xFF000000u : 0u);
             g1 = ((b.z & 0xFFFF) > c ? 0xFFu : 0u) | ((b.z >> 16) > c ? 0xFF00u : 0u) | ((b.w & 0xFFFF) > c ? 0xFF0000u : 0u) |
                  ((b.w >> 16) > c ? 0xFF000000u : 0u);
         } else {
-            const uint2 b = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(ci.bins) + gb);
             const uint32_t cv = (uint32_t)ci.cut * 0x01010101u;
             g0 = __vcmpgtu4(b.x, cv);
             g1 = __vcmpgtu4(b.y, cv);
@@ -191,6 +204,9 @@ __device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const Ba
     const uint32_t ktile = rs.keys + (uint32_t)lt * (uint32_t)(NB * TILE) + (uint32_t)lane * 8u;
     long long R[8];
     res_ld8i(rs.R + toff, lane, R);
+    uint2 sl_n = make_uint2(0u, 0u);
+    uint4 bn_n = make_uint4(0u, 0u, 0u, 0u);
+    if (cur != nullptr) keys_load(d, cur->big ? sm.big.ci : cur->st[0].ci, cur->first, gb, sl_n, bn_n);   // in flight during the apply
     if (do_apply) {
         const ApplyTab& ap = sm.ap;
         double G[8];
@@ -200,13 +216,13 @@ __device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const Ba
             int key[8];
             unpack8(lds_v2(ktile + (uint32_t)q * TILE), key);
             const int off = ap.off[q];
-            const long long* DRq = &ap.DR[g][off];
-            const double* DGq = &ap.DG[off];
+            const ApRow* Tq = &ap.T[g][off];
 #pragma unroll
             for (int o = 0; o < 8; ++o) {
                 if (PAD && key[o] == PAD_SLOT) continue;
-                R[o] -= DRq[key[o]];
-                G[o] += DGq[key[o]];
+                const ApRow r = Tq[key[o]];
+                R[o] -= r.dr;
+                G[o] += r.dg;
             }
             if (ap.changed[q]) {
                 int ns[8];
@@ -225,7 +241,7 @@ __device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const Ba
     if (cur == nullptr) return;
     if (cur->big) {
         const CurInfo& ci = sm.big.ci;
-        const uint2 kk = tree_keys(d, ci, cur->first, gb);
+        const uint2 kk = keys_make(ci, sl_n, bn_n);
         sts_v2(ktile, kk);
         int key[8];
         unpack8(kk, key);
@@ -236,53 +252,48 @@ __device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const Ba
         long long tot = 0;
 #pragma unroll
         for (int o = 0; o < 8; ++o) tot += R[o];
-        warp_add16(sm.p.acc.totr[g], tot, lane);
+        warp_add21(sm.p.acc.totr[g], tot, lane);
     }
-    unsigned long long Ms[NB];   // per tree: byte k-1 = which of the lane's 8 observations have key k
+    // per (tree, key >= 1) "column": the sum of R over its observations, and which of the lane's 8 observations
+    // belong to it (one byte per lane and column in the warp's scratch: the cross counts are read off that)
+    const int warp = (int)(threadIdx.x >> 5);
+    uint8_t* colb = reinterpret_cast<uint8_t*>(sm.tot) + warp * (MAXC * 32);
     const int nb = cur->nb;
+    for (int q = 0; q < nb; ++q) {
+        const CurInfo& ci = cur->st[q].ci;
+        const int K = cur->K[q];
+        const uint2 sl = sl_n;
+        const uint4 bn = bn_n;
+        if (q + 1 < nb) keys_load(d, cur->st[q + 1].ci, cur->first + q + 1, gb, sl_n, bn_n);   // next tree's loads in flight
+        const uint2 key = keys_make(ci, sl, bn);
+        sts_v2(ktile + (uint32_t)q * TILE, key);
+        uint8_t* cb = colb + (int)cur->colbase[q] * 32 + lane;
+        for (int k = 1; k < K; ++k) {
+            const uint32_t kv = (uint32_t)k * 0x01010101u;
+            const uint32_t bits = bytes_to_bits(__vcmpeq4(key.x, kv), __vcmpeq4(key.y, kv));
+            long long s = 0;
 #pragma unroll
-    for (int q = 0; q < NB; ++q) {
-        Ms[q] = 0ull;
-        if (q < nb) {
-            const CurInfo& ci = cur->st[q].ci;
-            const int K = cur->K[q];
-            const uint2 key = tree_keys(d, ci, cur->first + q, gb);
-            sts_v2(ktile + (uint32_t)q * TILE, key);
-            unsigned long long M = 0ull;
-            for (int k = 1; k < K; ++k) {
-                const uint32_t kv = (uint32_t)k * 0x01010101u;
-                const uint32_t bits = bytes_to_bits(__vcmpeq4(key.x, kv), __vcmpeq4(key.y, kv));
-                long long s = 0;
-#pragma unroll
-                for (int o = 0; o < 8; ++o) s += ((bits >> o) & 1u) ? R[o] : 0ll;
-                unsigned int* e = sm.p.acc.btab[q][k][g];
-                warp_add16(e, s, lane);
-                if (ci.birth && k == K - 1) {   // only the would-be right child needs counting: the rest is cached
-                    const int c = __reduce_add_sync(0xffffffffu, __popc(bits));
-                    if (lane == 0 && c) atomicAdd(&e[0], (unsigned int)c);
-                }
-                M |= (unsigned long long)bits << (8 * (k - 1));
+            for (int o = 0; o < 8; ++o) s += ((bits >> o) & 1u) ? R[o] : 0ll;
+            unsigned int* e = sm.p.acc.btab[q][k][g];
+            warp_add21(e, s, lane);
+            if (ci.birth && k == K - 1) {   // only the would-be right child needs counting: the rest is cached
+                const int c = __reduce_add_sync(0xffffffffu, __popc(bits));
+                if (lane == 0) atomicAdd(&e[0], (unsigned int)c);
             }
-            if (K > 1) {
-#pragma unroll
-                for (int m = 0; m < q; ++m) {
-                    const int Km = cur->K[m];
-                    if (Km > 1) {
-                        unsigned int* xt = &sm.p.acc.xtab[cur->xoff[q][m]][g];
-                        for (int kp = 1; kp < Km; ++kp) {
-                            const uint32_t bm = (uint32_t)(Ms[m] >> (8 * (kp - 1))) & 0xFFu;
-                            for (int k = 1; k < K; ++k) {
-                                const uint32_t bk = (uint32_t)(M >> (8 * (k - 1))) & 0xFFu;
-                                const int c = __reduce_add_sync(0xffffffffu, __popc(bm & bk));
-                                if (lane == 0 && c) atomicAdd(&xt[2 * ((kp - 1) * (K - 1) + (k - 1))], (unsigned int)c);
-                            }
-                        }
-                    }
-                }
-            }
-            Ms[q] = M;
+            cb[(k - 1) * 32] = (uint8_t)bits;
         }
     }
+    __syncwarp();
+    // cross counts: N[c1][c2] = sum over lanes of popc(byte(c1) & byte(c2)); lane l takes cells l, l + 32, ...
+    for (int cell = lane; cell < cur->ncell; cell += 32) {
+        const uint4* a = reinterpret_cast<const uint4*>(colb + (int)cur->cell_c1[cell] * 32);
+        const uint4* b = reinterpret_cast<const uint4*>(colb + (int)cur->cell_c2[cell] * 32);
+        const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+        const int c = __popc(a0.x & b0.x) + __popc(a0.y & b0.y) + __popc(a0.z & b0.z) + __popc(a0.w & b0.w) +
+                      __popc(a1.x & b1.x) + __popc(a1.y & b1.y) + __popc(a1.z & b1.z) + __popc(a1.w & b1.w);
+        if (c) atomicAdd(&sm.p.acc.xtab[cell][g], (unsigned int)c);
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -339,23 +350,38 @@ __device__ inline void stage_batch(BatchSmem& sm, BatchStage& B, const Dev& d, c
     }
     __syncthreads();
     if (t == 0) {
-        B.first = first; B.forest = f; B.big = 0; B.ncell = 0;
-        int nb = 0, cells = 0;
+        B.first = first; B.forest = f; B.big = 0; B.ncell = 0; B.ncol = 0;
+        int nb = 0, cells = 0, cols = 0;
         for (int q = 0; q < ncand; ++q) {
             const SmallStage& S = B.st[q];
             const int L = S.tr.nleaves, K = L + (S.prop.move == 1 ? 1 : 0);
             if (K > KB) { if (q == 0) { B.big = 1; nb = 1; } break; }
             int add = 0;
             for (int m = 0; m < q; ++m) add += (B.K[m] - 1) * (K - 1);
-            if (cells + add > XCAP) break;
+            if (cells + add > XCAP || cols + K - 1 > MAXC) break;
+            B.colbase[q] = (uint8_t)cols;
             for (int m = 0; m < q; ++m) { B.xoff[q][m] = (int16_t)cells; cells += (B.K[m] - 1) * (K - 1); }
+            cols += K - 1;
             B.K[q] = K;
             CurInfo& ci = B.st[q].ci;
             ci.active = 1; ci.K = K; ci.birth = S.prop.move == 1; ci.sx = S.prop.slot; ci.cut = S.prop.cut;
             ci.bins = S.prop.bins; ci.is16 = S.prop.is16; ci.forest = f; ci.new_slot = L;
             nb = q + 1;
         }
-        B.nb = nb; B.ncell = cells;
+        B.nb = nb; B.ncell = cells; B.ncol = cols;
+    }
+    __syncthreads();
+    // the two columns of every cross-count cell, in parallel over (q, m, kp, k)
+    if (!B.big) {
+        for (int i = t; i < NB * NB * (KB - 1) * (KB - 1); i += blockDim.x) {
+            const int k = 1 + i % (KB - 1), kp = 1 + (i / (KB - 1)) % (KB - 1);
+            const int m = (i / ((KB - 1) * (KB - 1))) % NB, q = i / ((KB - 1) * (KB - 1) * NB);
+            if (q < B.nb && m < q && kp < B.K[m] && k < B.K[q]) {
+                const int cell = B.xoff[q][m] + (kp - 1) * (B.K[q] - 1) + (k - 1);
+                B.cell_c1[cell] = (uint8_t)(B.colbase[m] + kp - 1);
+                B.cell_c2[cell] = (uint8_t)(B.colbase[q] + k - 1);
+            }
+        }
     }
     __syncthreads();
 }
@@ -402,16 +428,15 @@ __device__ inline void flush_batch(BatchSmem& sm, const BatchStage& B, long long
     }
 }
 
-__device__ inline void store_small(TreeRec* dst, const TreeSmall& tr)
+__device__ inline void store_small(TreeRec* dst, const TreeSmall& tr, int t)   // one warp, t = lane
 {
-    const int t = threadIdx.x;
     if (t < 2 * KB) {
         dst->parent[t] = tr.parent[t]; dst->left[t] = tr.left[t]; dst->right[t] = tr.right[t]; dst->var[t] = tr.var[t];
         dst->cut[t] = tr.cut[t]; dst->node_slot[t] = tr.node_slot[t]; dst->depth[t] = tr.depth[t]; dst->heap[t] = tr.heap[t];
-    } else if (t >= 32 && t < 32 + KB) {
-        const int s = t - 32;
+    } else if (t < 3 * KB) {
+        const int s = t - 2 * KB;
         dst->slot_node[s] = tr.slot_node[s]; dst->cnt0[s] = tr.cnt0[s]; dst->cnt1[s] = tr.cnt1[s]; dst->mu[s] = tr.mu[s];
-    } else if (t == 64) {
+    } else if (t == 3 * KB) {
         dst->nnodes = tr.nnodes; dst->nleaves = tr.nleaves;
     }
 }
@@ -424,14 +449,14 @@ __device__ __forceinline__ void fill_apply(BatchSmem& sm, const Stage& S, int q,
     ApplyTab& ap = sm.ap;
     if (t < K) {
         if (t < L) {
-            ap.DR[0][off + t] = sm.dfx[0][t]; ap.DR[1][off + t] = sm.dfx[1][t];
-            ap.DG[off + t] = sm.dlt[t]; ap.NS[off + t] = sm.remap[t];
+            ap.T[0][off + t].dr = sm.dfx[0][t]; ap.T[1][off + t].dr = sm.dfx[1][t];
+            ap.T[0][off + t].dg = ap.T[1][off + t].dg = sm.dlt[t]; ap.NS[off + t] = sm.remap[t];
         } else {   // the part of leaf sx a birth proposal would have sent right
             const int sx = S.prop.slot;
             const bool acc = sm.ai.birth != 0;
-            ap.DR[0][off + t] = acc ? sm.ai.dfx_right[0] : sm.dfx[0][sx];
-            ap.DR[1][off + t] = acc ? sm.ai.dfx_right[1] : sm.dfx[1][sx];
-            ap.DG[off + t] = acc ? sm.ai.dlt_right : sm.dlt[sx];
+            ap.T[0][off + t].dr = acc ? sm.ai.dfx_right[0] : sm.dfx[0][sx];
+            ap.T[1][off + t].dr = acc ? sm.ai.dfx_right[1] : sm.dfx[1][sx];
+            ap.T[0][off + t].dg = ap.T[1][off + t].dg = acc ? sm.ai.dlt_right : sm.dlt[sx];
             ap.NS[off + t] = acc ? (uint8_t)L : sm.remap[sx];
         }
     }
@@ -459,6 +484,10 @@ __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d,
         __syncthreads();
         return;
     }
+    const bool rprof = d.prof != nullptr && blockIdx.x == 0 && t == 0;
+    long long rp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long rtp = clock64();
+#define RPROF(k) do { if (rprof) { const long long now_ = clock64(); rp[k] += now_ - rtp; rtp = now_; } } while (0)
     const int nb = B.nb;
     ResolveTab& rs = sm.p.rs;
     for (int i = t; i < nb * KB * 8; i += blockDim.x) {
@@ -470,68 +499,221 @@ __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d,
         for (int i = t; i < 2 * B.ncell; i += blockDim.x) (&rs.x[0][0])[i] = __ldcg(xg + i);
     }
     __syncthreads();
-    if (t < 2) i128_to(sm.totr_run[t], limbs_to_i128(rs.tot[0][0][t][1], rs.tot[0][0][t][2], rs.tot[0][0][t][3]));
+    RPROF(0);
+    const bool is_con = F.is_con != 0;
+    const double s1 = is_con ? sc.mscale : sc.bscale1, s0 = is_con ? sc.mscale : sc.bscale0;
+    const double tau = is_con ? sc.tau_con : sc.tau_mod;
+    const double s2 = sc.sigma * sc.sigma;
+    const double phi1 = s1 * s1 / s2, phi0 = s0 * s0 / s2;
+    const double a = 1.0 / (tau * tau);
+    const double rs1 = 1.0 / s1, rs0 = 1.0 / s0;
+    const double log_tau = log(tau);
+    // Everything that depends on counts only -- precision, its log and reciprocal, the posterior sd -- for every key
+    // and pooled pair of every tree of the batch, in parallel (the divisions, logs and square roots of the batch).
+    PreKey* pre = reinterpret_cast<PreKey*>(sm.tot);
+    if (t < nb * (KB + 1)) {
+        const int q = t / (KB + 1), e = t % (KB + 1);
+        const SmallStage& S = B.st[q];
+        const int L = S.tr.nleaves, K = B.K[q], mv = S.prop.move, sx = S.prop.slot;
+        if (e < K || (e == KB && mv != 0)) {
+            const double cL1 = mv == 1 ? (double)rs.tot[q][L][1][0] : 0.0, cL0 = mv == 1 ? (double)rs.tot[q][L][0][0] : 0.0;
+            const int pa = sx, pb = (mv == 1) ? L : S.prop.slot_b;
+            double k1 = 0.0, k0 = 0.0, A = 0.0;
+            const int nk = e < K ? 1 : 2;
+            for (int j = 0; j < nk; ++j) {
+                const int key = e < K ? e : (j == 0 ? pa : pb);
+                double c1, c0;
+                if (key < L) {
+                    c1 = (double)S.tr.cnt1[key]; c0 = (double)S.tr.cnt0[key];
+                    if (mv == 1 && key == sx) { c1 -= cL1; c0 -= cL0; }
+                } else { c1 = cL1; c0 = cL0; }
+                k1 += c1; k0 += c0;
+                A += c1 * phi1 + c0 * phi0;
+            }
+            const double prec = a + A, inv = 1.0 / prec;
+            PreKey& pk = pre[q * (KB + 1) + e];
+            pk.k1 = k1; pk.k0 = k0; pk.inv = inv; pk.plog = log(prec); pk.psd = sqrt(inv);
+        }
+    }
     __syncthreads();
-    for (int q = 0; q < nb; ++q) {
-        SmallStage& S = B.st[q];
-        const int tree = B.first + q;
-        const bool writer = ((int)blockIdx.x == tree % (int)gridDim.x);
-        const int L = S.tr.nleaves, K = B.K[q];
-        const bool birth = S.prop.move == 1;
-        const int sx = S.prop.slot;
-        // pre-decision counts and the corrected sums of keys >= 1
-        if (t < 2 * K) {
-            const int k = t >> 1, g = t & 1;
-            const int cL = birth ? (int)rs.tot[q][L][g][0] : 0;
-            int c;
-            if (k < L) c = (g ? S.tr.cnt1[k] : S.tr.cnt0[k]) - ((birth && k == sx) ? cL : 0);
-            else c = cL;
-            sm.cq[k][g] = c;
-            if (k >= 1) {
-                __int128 v = limbs_to_i128(rs.tot[q][k][g][1], rs.tot[q][k][g][2], rs.tot[q][k][g][3]);
-                for (int m = 0; m < q; ++m) {
-                    const int om = sm.ap.off[m];
-                    const long long D0 = sm.ap.DR[g][om];
-                    v -= (__int128)D0 * c;
-                    const int Km = B.K[m];
-                    if (Km > 1) {
-                        const int base = B.xoff[q][m] + (k - 1);
-                        for (int kp = 1; kp < Km; ++kp)
-                            v -= (__int128)(sm.ap.DR[g][om + kp] - D0) * rs.x[base + (kp - 1) * (K - 1)][g];
-                    }
-                }
-                i128_to(sm.corr[k][g], v);
+    RPROF(1);
+    // The decisions form a serial chain (tree q needs the residual losses D of the trees before it), but a short
+    // one: WARP q owns tree q of the batch.  It keeps the tree's key sums in registers (lane 2k+g = key k, group g),
+    // folds in the correction of every earlier tree as soon as that tree's D rows are published (one named barrier
+    // per tree: the owner arrives, the later warps wait), takes its decision, publishes its own D rows, and only
+    // then does the bookkeeping nobody waits for (tree record, slot map, trace, HBM write-back).
+    const int wq = t >> 5, l = t & 31;
+    if (wq < NB) {
+        const unsigned FULL = 0xffffffffu;
+        const int q = wq;
+        const bool active = q < nb;
+        const int qq = active ? q : 0;
+        SmallStage& S = B.st[qq];
+        auto& tr = S.tr;
+        const Proposal& P = S.prop;
+        const int tree = B.first + qq;
+        const bool writer = active && ((int)blockIdx.x == tree % (int)gridDim.x);
+        const int L = tr.nleaves, K = B.K[qq];
+        const bool birth = P.move == 1;
+        const int sx = P.slot;
+        const int pa = P.slot, pb = birth ? L : P.slot_b;
+        const int off = qq * KB;
+        const int k = l >> 1, g = l & 1;
+        __int128 v = 0, run = 0;
+        int c = 0;
+        if (active) {
+            if (l < 2) run = limbs_to_i128(rs.tot[0][0][l][1], rs.tot[0][0][l][2], rs.tot[0][0][l][3]);
+            if (l < 2 * K) {
+                const int cL = birth ? (int)rs.tot[q][L][g][0] : 0;
+                if (k < L) c = (g ? tr.cnt1[k] : tr.cnt0[k]) - ((birth && k == sx) ? cL : 0);
+                else c = cL;
+                sm.cq[q][k][g] = c;
+                if (k >= 1) v = limbs_to_i128(rs.tot[q][k][g][1], rs.tot[q][k][g][2], rs.tot[q][k][g][3]);
             }
         }
-        __syncthreads();
-        if (t < 2) {   // key 0 = running total - the other keys
-            __int128 v = i128_from(sm.totr_run[t]);
-            for (int k = 1; k < K; ++k) v -= i128_from(sm.corr[k][t]);
-            i128_to(sm.corr[0][t], v);
+        for (int m = 0; m < nb; ++m) {
+            if (active && q == m) {
+                // ---- key 0 = running total - the other keys (lanes of the same group) ----
+                __int128 others = (l < 2 * K && k >= 1) ? v : (__int128)0;
+                for (int sft = 2; sft < 2 * K; sft <<= 1) {
+                    const long long olo = __shfl_xor_sync(FULL, (long long)(unsigned long long)others, sft);
+                    const long long ohi = __shfl_xor_sync(FULL, (long long)(others >> 64), sft);
+                    others += (__int128)(((unsigned __int128)(unsigned long long)ohi << 64) | (unsigned long long)olo);
+                }
+                if (l < 2) v = run - others;
+                double Sd;   // exact integer -> double, as limbs_to_double does
+                {
+                    const long long hi = (long long)(v >> 40);
+                    const long long lo = (long long)(v & (((__int128)1 << 40) - 1));
+                    Sd = ((double)hi * 1099511627776.0 + (double)lo) * (1.0 / 17592186044416.0);
+                }
+                // ---- posteriors: lane k = key k, lane KB = pooled pair ----
+                const int kk = l < K ? l : 0;
+                const double S1 = __shfl_sync(FULL, Sd, 2 * kk + 1), S0 = __shfl_sync(FULL, Sd, 2 * kk);
+                const PreKey pk = pre[q * (KB + 1) + (l < K ? l : KB)];
+                const double mo = tr.mu[(l < L) ? l : sx];          // old value of the leaf the key belongs to
+                double Bk = 0.0;
+                if (l < K) Bk = phi1 * (S1 * rs1 + pk.k1 * mo) + phi0 * (S0 * rs0 + pk.k0 * mo);
+                const double Ba = __shfl_sync(FULL, Bk, pa), Bb = __shfl_sync(FULL, Bk, pb);
+                const double Bp = Ba + Bb;
+                // ---- the MH decision (every lane computes it from the same values) ----
+                int accepted = 0;
+                double logr = nan("");
+                const PreKey pkp = pre[q * (KB + 1) + KB];
+                if (P.move != 0) {
+                    const PreKey pka = pre[q * (KB + 1) + pa], pkb = pre[q * (KB + 1) + pb];
+                    const double gain = -log_tau - 0.5 * (pka.plog + pkb.plog - pkp.plog)
+                                      + 0.5 * (Ba * Ba * pka.inv + Bb * Bb * pkb.inv - Bp * Bp * pkp.inv);
+                    if (birth) {
+                        if (pka.k1 + pka.k0 >= d.min_leaf && pkb.k1 + pkb.k0 >= d.min_leaf) {
+                            logr = P.log_prior + gain;
+                            accepted = (P.log_u < logr) ? 1 : 0;
+                        }
+                    } else {
+                        logr = P.log_prior - gain;
+                        accepted = (P.log_u < logr) ? 1 : 0;
+                    }
+                }
+                // ---- the new leaf of every pre-decision key: posterior, normal, slot ----
+                // pooled pair: a rejected birth keeps leaf sx whole, an accepted death merges its two leaves
+                const bool pooled = (birth && !accepted && (l == sx || l == L)) || (P.move == 2 && accepted && (l == pa || l == pb));
+                const double pm = pooled ? Bp * pkp.inv : Bk * pk.inv;
+                const double ps = pooled ? pkp.psd : pk.psd;
+                const double n1 = pooled ? pkp.k1 : pk.k1, n0 = pooled ? pkp.k0 : pk.k0;
+                double z;
+                int ns = l;
+                if (birth) {
+                    if (accepted) z = (l == sx) ? P.z_extra[0] : (l == L ? P.z_extra[1] : S.z[l < L ? l : 0]);
+                    else { z = S.z[l < L ? l : sx]; if (l == L) ns = sx; }
+                } else if (P.move == 2 && accepted) {
+                    z = (l == pa || l == pb) ? P.z_extra[0] : S.z[l < L ? l : 0];
+                    const int last = L - 1;
+                    if (l == pb) ns = pa;
+                    if (pb != last && ns == last) ns = pb;      // the last slot moves into the hole
+                } else z = S.z[l < L ? l : 0];
+                int fxbad = 0;
+                double mnew = 0.0, dl = 0.0;
+                if (l < K) {
+                    mnew = pm + z * ps;
+                    if (!(mnew == mnew)) sm.bad = ERR_NAN;
+                    dl = mnew - mo;
+                    ApRow r1, r0;
+                    r1.dr = to_fixed(s1 * dl, fxbad); r1.dg = dl; r0.dr = to_fixed(s0 * dl, fxbad); r0.dg = dl;
+                    sm.ap.T[1][off + l] = r1; sm.ap.T[0][off + l] = r0;
+                }
+                if (fxbad) sm.bad = ERR_FX_RANGE;
+                __threadfence_block();
+                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
+                // ---- bookkeeping nobody waits for ----
+                if (l < K) sm.ap.NS[off + l] = (uint8_t)ns;
+                if (l == 0) { sm.ap.changed[q] = accepted; sm.ap.off[q] = off; }
+                __syncwarp();
+                if (l == 0) {   // topology, exactly decide_core's
+                    if (birth) {
+                        if (accepted) {
+                            const int kr = pb, nx = P.node, na = tr.nnodes, nbn = tr.nnodes + 1;
+                            tr.left[nx] = (int16_t)na; tr.right[nx] = (int16_t)nbn;
+                            tr.var[nx] = (uint16_t)P.var; tr.cut[nx] = (uint16_t)P.cut;
+                            for (int ch2 = 0; ch2 < 2; ++ch2) {
+                                const int ch = ch2 ? nbn : na;
+                                tr.parent[ch] = (int16_t)nx; tr.left[ch] = tr.right[ch] = -1;
+                                tr.var[ch] = tr.cut[ch] = 0xFFFF;
+                                tr.depth[ch] = tr.depth[nx] + 1;
+                                tr.heap[ch] = 2u * tr.heap[nx] + (uint32_t)ch2;
+                            }
+                            tr.node_slot[na] = (uint8_t)sx; tr.slot_node[sx] = (int16_t)na;
+                            tr.node_slot[nbn] = (uint8_t)kr; tr.slot_node[kr] = (int16_t)nbn;
+                            tr.nnodes += 2; tr.nleaves = L + 1;
+                        }
+                    } else if (P.move == 2 && accepted) {
+                        const int sa = pa, sb = pb;
+                        const int nx = P.node, na = tr.left[nx], nbn = tr.right[nx];
+                        tr.left[nx] = tr.right[nx] = -1; tr.var[nx] = tr.cut[nx] = 0xFFFF;
+                        tr.node_slot[nx] = (uint8_t)sa; tr.slot_node[sa] = (int16_t)nx;
+                        const int last = L - 1;
+                        if (sb != last) {   // keep slots compact: the last slot moves into the hole
+                            const int nd = tr.slot_node[last];
+                            tr.slot_node[sb] = (int16_t)nd; tr.node_slot[nd] = (uint8_t)sb;
+                        }
+                        tr.nleaves = L - 1;
+                        tree_remove_node(tr, max(na, nbn));
+                        tree_remove_node(tr, min(na, nbn));
+                    }
+                    if (writer) {
+                        int32_t* trc = d.trace + 5 * tree;
+                        trc[0] = P.move; trc[1] = accepted; trc[2] = (int32_t)P.heap; trc[3] = P.var; trc[4] = P.cut;
+                        d.trace_logr[tree] = logr;
+                        if (P.move == 1) { atomicAdd((unsigned long long*)&d.counters[0], 1ull); if (accepted) atomicAdd((unsigned long long*)&d.counters[1], 1ull); }
+                        if (P.move == 2) { atomicAdd((unsigned long long*)&d.counters[2], 1ull); if (accepted) atomicAdd((unsigned long long*)&d.counters[3], 1ull); }
+                    }
+                }
+                __syncwarp();
+                if (l < K) { tr.mu[ns] = mnew; tr.cnt1[ns] = (int32_t)n1; tr.cnt0[ns] = (int32_t)n0; }   // keys of one new leaf agree
+                __syncwarp();
+                if (writer) store_small(&newtrees[tree], tr, l);
+            } else if (active && q > m) {
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
+                // fold tree m's update into this tree's sums and into the running total
+                const int om = m * KB, Km = B.K[m];
+                if (l < 2 * K && k >= 1) {
+                    const long long D0 = sm.ap.T[g][om].dr;
+                    v -= (__int128)D0 * c;
+                    const int base = B.xoff[q][m] + (k - 1);
+                    for (int kp = 1; kp < Km; ++kp)
+                        v -= (__int128)(sm.ap.T[g][om + kp].dr - D0) * rs.x[base + (kp - 1) * (K - 1)][g];
+                }
+                if (l < 2) for (int kp = 0; kp < Km; ++kp) run -= (__int128)sm.ap.T[l][om + kp].dr * sm.cq[m][kp][l];
+            } else {
+                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
+            }
         }
-        __syncthreads();
-        if (t < 2 * K) {
-            const int k = t >> 1, g = t & 1;
-            const __int128 v = i128_from(sm.corr[k][g]);
-            long long* o = &sm.tot[k * 8 + g * 4];
-            o[0] = (birth && k == L) ? rs.tot[q][L][g][0] : 0;
-            o[1] = (long long)(v & 0x1FFFFF);
-            o[2] = (long long)((v >> LIMB_BITS) & 0x1FFFFF);
-            o[3] = (long long)(v >> (2 * LIMB_BITS));
-        }
-        decide_core(sm, S, d, F, tree, sc, writer);     // starts with a __syncthreads()
-        fill_apply(sm, S, q, q * KB, L, K);
-        if (writer) store_small(&newtrees[tree], S.tr);
-        __syncthreads();
-        if (t < 2) {   // the residual total after this tree's update
-            __int128 v = i128_from(sm.totr_run[t]);
-            for (int k = 0; k < K; ++k) v -= (__int128)sm.ap.DR[t][q * KB + k] * sm.cq[k][t];
-            i128_to(sm.totr_run[t], v);
-        }
-        __syncthreads();
     }
+    __syncthreads();
     if (t == 0) { sm.ap.n = nb; sm.ap.first = B.first; sm.ap.forest = B.forest; }
     __syncthreads();
+    RPROF(6);
+    if (rprof) for (int kx = 0; kx < 8; ++kx) d.prof[8 + kx] += rp[kx];
+#undef RPROF
 }
 
 // proposals of sweep `sweep` for the trees j = blockIdx.x, + gridDim.x, ... from their (visible) HBM records

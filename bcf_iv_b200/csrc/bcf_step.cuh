@@ -255,7 +255,8 @@ __device__ __forceinline__ void key_raw(const long long* tot, int key, double& S
 }
 
 // decide_core(): the statistics of the tree are already in sm.tot (K x [control: count, limb0..2][treated: ...])
-template <class SM, class Stage>
+// WARP: run by ONE warp (lanes = threads 0..31 of the CTA) with warp-level synchronisation only; needs K <= 16.
+template <class SM, class Stage, bool WARP = false>
 __device__ inline void decide_core(SM& sm, Stage& S, const Dev& d, const ForestDev& F, int tree, const Scalars& sc,
                                    bool writer)
 {
@@ -270,15 +271,19 @@ __device__ inline void decide_core(SM& sm, Stage& S, const Dev& d, const ForestD
     // the two keys a move pools: birth (leaf part staying left, would-be right child), death (the two children)
     const int pa = P.slot, pb = (P.move == 1) ? L : P.slot_b;
 
-    if (t < MAXL) { sm.remap[t] = (uint8_t)t; if (t < L) sm.mu_old[t] = tr.mu[t]; }
-    __syncthreads();
+    constexpr int TPOOL = WARP ? 16 : KEYS;          // thread of the pooled pair
+    constexpr int TLOG = WARP ? 17 : KEYS + 1;
+    for (int i = t; i < (WARP ? 2 * 16 : MAXL); i += (WARP ? 32 : MAXL)) { if (i < MAXL) sm.remap[i] = (uint8_t)i; }
+    if (t < L) sm.mu_old[t] = tr.mu[t];
+    if (WARP) __syncwarp(); else __syncthreads();
 
     // Phase 1.  Keys: leaf slots 0..L-1 (for a birth the proposed leaf's key holds the part that stays LEFT) and
     // key L = the would-be right child.  Thread KEYS handles the pooled pair of the move (sum of its two keys).
-    if (t < K || (t == KEYS && P.move != 0)) {
+    if (t < K || (t == TPOOL && P.move != 0)) {
         const double s2 = sc.sigma * sc.sigma;
         const double phi1 = s1 * s1 / s2, phi0 = s0 * s0 / s2;
         const double a = 1.0 / (tau * tau);
+        const double rs1 = 1.0 / s1, rs0 = 1.0 / s0;   // one reciprocal per forest and sweep, shared by every leaf
         double n1 = 0.0, n0 = 0.0, sphi = 0.0, sphir = 0.0;
         const int nk = (t < K) ? 1 : 2;
         for (int q = 0; q < nk; ++q) {
@@ -295,15 +300,16 @@ __device__ inline void decide_core(SM& sm, Stage& S, const Dev& d, const ForestD
             } else { k1 = c1; k0 = c0; mo = tr.mu[P.slot]; }
             n1 += k1; n0 += k0;
             sphi += k1 * phi1 + k0 * phi0;
-            sphir += phi1 * (S1 / s1 + k1 * mo) + phi0 * (S0 / s0 + k0 * mo);
+            sphir += phi1 * (S1 * rs1 + k1 * mo) + phi0 * (S0 * rs0 + k0 * mo);
         }
         const double prec = a + sphi, inv = 1.0 / prec;
-        sm.nc1[t] = n1; sm.nc0[t] = n0;
-        sm.cnt[t] = n1 + n0; sm.sphi[t] = sphi; sm.sphir[t] = sphir;
-        sm.pinv[t] = inv; sm.plog[t] = log(prec); sm.pmean[t] = sphir * inv; sm.psd[t] = sqrt(inv);
+        const int w = (t < K) ? t : KEYS;
+        sm.nc1[w] = n1; sm.nc0[w] = n0;
+        sm.cnt[w] = n1 + n0; sm.sphi[w] = sphi; sm.sphir[w] = sphir;
+        sm.pinv[w] = inv; sm.plog[w] = log(prec); sm.pmean[w] = sphir * inv; sm.psd[w] = sqrt(inv);
     }
-    if (t == KEYS + 1) sm.log_tau = log(tau);
-    __syncthreads();
+    if (t == TLOG) sm.log_tau = log(tau);
+    if (WARP) __syncwarp(); else __syncthreads();
 
     if (t == 0) {
         int accepted = 0;
@@ -376,7 +382,7 @@ __device__ inline void decide_core(SM& sm, Stage& S, const Dev& d, const ForestD
             if (P.move == 2) { atomicAdd((unsigned long long*)&d.counters[2], 1ull); if (accepted) atomicAdd((unsigned long long*)&d.counters[3], 1ull); }
         }
     }
-    __syncthreads();
+    if (WARP) __syncwarp(); else __syncthreads();
 
     const int Lnew = tr.nleaves;
     if (t < Lnew) {
@@ -386,7 +392,7 @@ __device__ inline void decide_core(SM& sm, Stage& S, const Dev& d, const ForestD
         tr.mu[t] = m;
         tr.cnt1[t] = (int32_t)sm.nc1[t]; tr.cnt0[t] = (int32_t)sm.nc0[t];
     }
-    __syncthreads();
+    if (WARP) __syncwarp(); else __syncthreads();
     int fxbad = 0;
     if (t < L) {
         const double dl = sm.mu_new[sm.remap[t]] - sm.mu_old[t];
@@ -402,7 +408,7 @@ __device__ inline void decide_core(SM& sm, Stage& S, const Dev& d, const ForestD
         ai.uniform = (L == 1 && !ai.birth) ? 1 : 0;
     }
     if (fxbad) sm.bad = ERR_FX_RANGE;
-    __syncthreads();
+    if (WARP) __syncwarp(); else __syncthreads();
 }
 
 // `totals`: the statistics buffer of the sweep in progress (see sweep_totals)

@@ -609,15 +609,21 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
     if ((rc = check_device_err(h))) return rc;
     CK(cudaMemcpy(&sc, d.sc, sizeof(sc), cudaMemcpyDeviceToHost));
     h->nsaved = sc.save_ctr;
-    if (d.prof) {   // BCFGPU_PROFILE=1: phase cycle counters of CTA 0 (persistent engine)
-        long long pc[8];
-        CK(cudaMemcpy(pc, d.prof, 64, cudaMemcpyDeviceToHost));
-        CK(cudaMemset(d.prof, 0, 64));
+    if (d.prof) {   // BCFGPU_PROFILE=1: phase cycle counters of CTA 0 (persistent engines)
+        long long pc[16];
+        CK(cudaMemcpy(pc, d.prof, 128, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(d.prof, 0, 128));
         const char* nm[8] = {"tiles", "flush", "barrier", "decide", "store", "load+propose", "epilogue", "-"};
         long long tot = 0; for (int k = 0; k < 7; ++k) tot += pc[k];
         fprintf(stderr, "[bcfgpu profile] %d sweeps:", total);
         for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.1f%%(%.0f cyc/tree)", nm[k], 100.0 * pc[k] / (double)std::max(tot, 1ll), (double)pc[k] / ((double)total * h->T));
         fprintf(stderr, "\n");
+        bool any = false; for (int k = 8; k < 16; ++k) any |= pc[k] != 0;
+        if (any) {
+            fprintf(stderr, "[bcfgpu profile] resolve detail (cyc/tree):");
+            for (int k = 8; k < 16; ++k) fprintf(stderr, " r%d=%.0f", k - 8, (double)pc[k] / ((double)total * h->T));
+            fprintf(stderr, "\n");
+        }
     }
     return BCFGPU_OK;
 }
