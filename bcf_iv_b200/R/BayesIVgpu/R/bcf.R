@@ -1,0 +1,75 @@
+#' Bayesian Causal Forest on the GPU: a bcf()-compatible front end
+#'
+#' Same formal arguments and return fields as bcf::bcf, which BayesIV calls at R/bcf_iv.R:89 and R/bcf_itt.R:71 of
+#' fbargaglistoffi/BCF-IV; the Gibbs sampler runs in libbcfgpu.so (CUDA, sm_100a) through .Call (src/r_shim.c).
+#' Arguments of bcf 2.x that have no meaning here (n_cores, n_threads, save_tree_directory, log_file, no_output,
+#' verbose, update_interval) are accepted and ignored.  There is no CPU fallback.
+#' @export
+bcf <- function(y, z, x_control, x_moderate = x_control, pihat, nburn, nsim, nthin = 1, update_interval = 100,
+                ntree_control = 200, sd_control = 2 * sd(y), base_control = 0.95, power_control = 2,
+                ntree_moderate = 50, sd_moderate = sd(y), base_moderate = 0.25, power_moderate = 3,
+                nu = 3, lambda = NULL, sigq = 0.9, sighat = NULL, include_pi = "control",
+                use_muscale = TRUE, use_tauscale = TRUE,
+                w = NULL, random_seed = sample.int(.Machine$integer.max, 1), n_chains = 1, n_cores = NULL,
+                n_threads = NULL, no_output = TRUE, save_tree_directory = NULL, log_file = NULL, verbose = FALSE,
+                device = -1L, keep_draws = TRUE) {
+  if (!is.null(w)) stop("observation weights are not implemented")
+  x_control <- as.matrix(x_control); x_moderate <- as.matrix(x_moderate); pihat <- as.matrix(pihat)
+  n <- length(y)
+  if (any(!is.finite(y)) || any(!is.finite(x_control)) || any(!is.finite(x_moderate)) || any(!is.finite(pihat)))
+    stop("Missing or non-finite values in y, x_control, x_moderate or pihat")
+  if (!all(sort(unique(z)) %in% c(0, 1))) stop("z must be a vector of 0's and 1's")
+  if (length(z) != n || nrow(x_control) != n || nrow(x_moderate) != n || nrow(pihat) != n)
+    stop("y, z, x_control, x_moderate and pihat must have the same number of rows")
+  if (!(include_pi %in% c("control", "moderate", "both", "none"))) stop("bad include_pi")
+  if (nburn < 100) warning("A low (<100) value for nburn was supplied")
+  if (length(unique(y)) < 5) warning("y appears to be discrete")
+  if (.Call("bcfgpu_R_device_count") < 1L) stop("no CUDA device available (libbcfgpu has no CPU fallback)")
+
+  x_c <- if (include_pi %in% c("control", "both")) cbind(x_control, pihat) else x_control
+  x_m <- if (include_pi %in% c("moderate", "both")) cbind(x_moderate, pihat) else x_moderate
+  storage.mode(x_c) <- "double"; storage.mode(x_m) <- "double"
+  cut_c <- lapply(seq_len(ncol(x_c)), function(j) .cutpoints(x_c[, j]))
+  cut_m <- lapply(seq_len(ncol(x_m)), function(j) .cutpoints(x_m[, j]))
+  muy <- mean(y); sdy <- sd(y); yscale <- (y - muy) / sdy
+  if (is.null(sighat)) sighat <- summary(lm(yscale ~ z + x_c))$sigma
+  if (is.null(lambda)) lambda <- sighat^2 * qchisq(1 - sigq, nu) / nu
+  con_sd <- if (isTRUE(all.equal(sd_control, 2 * sdy))) 2 else sd_control / sdy
+  mod_sd <- (if (isTRUE(all.equal(sd_moderate, sdy))) 1 else sd_moderate / sdy) / (if (use_tauscale) 0.674 else 1)
+  perm <- order(z, decreasing = TRUE)           # reported only: the library permutes and un-permutes internally
+
+  chains <- lapply(seq_len(n_chains) - 1L, function(ch) {
+    cfg <- list(ntree_control = ntree_control, ntree_moderate = ntree_moderate, base_control = base_control,
+                power_control = power_control, base_moderate = base_moderate, power_moderate = power_moderate,
+                con_sd = con_sd, mod_sd = mod_sd, nu = nu, lambda = lambda, sigma_init = sd(yscale),
+                use_muscale = as.integer(use_muscale), use_tauscale = as.integer(use_tauscale),
+                seed = random_seed, chain = ch, device = device)
+    .Call("bcfgpu_R_fit", as.double(yscale), as.integer(z), x_c, x_m,
+          as.double(unlist(cut_c)), as.integer(c(0L, cumsum(lengths(cut_c)))),
+          as.double(unlist(cut_m)), as.integer(c(0L, cumsum(lengths(cut_m)))),
+          cfg, as.integer(nburn), as.integer(nsim), as.integer(nthin), isTRUE(keep_draws))
+  })
+  bind <- function(f) do.call(rbind, lapply(chains, function(r) t(r[[f]])))      # n x nsim -> nsim x n, chains stacked
+  avg <- function(f) Reduce(`+`, lapply(chains, `[[`, f)) / length(chains)
+  fit <- list(sigma = sdy * unlist(lapply(chains, `[[`, "sigma")),
+              mu_scale = sdy * unlist(lapply(chains, `[[`, "mu_scale")),
+              tau_scale = sdy * unlist(lapply(chains, `[[`, "tau_scale")),
+              perm = perm,
+              tau_mean = sdy * avg("tau_mean"), mu_mean = muy + sdy * avg("mu_mean"),
+              yhat_mean = muy + sdy * avg("yhat_mean"), tau_var = sdy^2 * avg("tau_var"))
+  if (isTRUE(keep_draws)) {
+    fit$tau <- sdy * bind("tau"); fit$mu <- muy + sdy * bind("mu"); fit$yhat <- muy + sdy * bind("yhat")
+  }
+  fit
+}
+
+# bcf's .cp_quantile: one value -> itself; fewer than 8 distinct -> midpoints; else 10000 points of the empirical
+# quantile function over an equispaced grid
+.cutpoints <- function(x, num = 10000, cat_levels = 8) {
+  ux <- sort(unique(x))
+  if (length(ux) == 1) { warning("A supplied covariate contains a single distinct value."); return(x[1]) }
+  if (length(ux) < cat_levels) return(ux[-length(ux)] + diff(ux) / 2)
+  n <- length(x)
+  q <- approxfun(sort(x), quantile(x, 0:(n - 1) / n), ties = mean)
+  q(seq(min(x), max(x), length.out = num))
+}

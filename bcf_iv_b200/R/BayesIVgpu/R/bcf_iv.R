@@ -1,0 +1,43 @@
+#' Bayesian Causal Forest with Instrumental Variables (GPU sampler)
+#'
+#' Drop-in for BayesIV::bcf_iv (reference R/bcf_iv.R:47): same arguments, same returned data.frame
+#' (node, CCACE, pvalue, Weak_IV_test, Pi_obs, ITT, Pi_compliers, Adj_pvalue; one row per rpart node number).
+#' The ITT forest is fitted by bcf() of this package, i.e. on the GPU; the complier-proportion forest too
+#' (the reference uses bartCause::bartc for it), everything else is unchanged CPU code.
+#' @export
+bcf_iv <- function(y, w, z, x, binary = FALSE, n_burn = 500, n_sim = 500, inference_ratio = 0.5, max_depth = 2,
+                   cp = 0.01, minsplit = 10, adj_method = "holm", seed = 42) {
+  if (binary) stop("binary = TRUE needs the probit BART of bartCause::bartc, which this build does not replace")
+  x <- as.matrix(x)
+  index <- .honest_split(nrow(x), inference_ratio, seed)
+  all_rows <- data.frame(y = y, w = w, z = z, x)
+  inference <- all_rows[index, ]
+  xd <- x[-index, , drop = FALSE]
+  pihat <- .logit_pihat(z[-index], xd)
+
+  fit <- function(outcome) bcf(outcome, z[-index], xd, xd, pihat, nburn = n_burn, nsim = n_sim,
+                               random_seed = seed, keep_draws = FALSE)$tau_mean
+  pic <- fit(w[-index])                       # posterior mean share of compliers given x
+  itt <- fit(y[-index])                       # posterior mean intention-to-treat effect given x  (the hot path)
+  tauhat <- itt / pic
+
+  tree <- rpart::rpart(tauhat ~ ., data = data.frame(tauhat = tauhat, xd), maxdepth = max_depth, cp = cp,
+                       minsplit = minsplit)
+  nodes <- as.numeric(row.names(tree$frame))
+  is_leaf <- tree$frame$var == "<leaf>"
+  out <- data.frame(node = rep(NA_character_, length(nodes)), CCACE = NA, pvalue = NA, Weak_IV_test = NA,
+                    Pi_obs = NA, ITT = NA, Pi_compliers = NA)
+  for (k in seq_along(nodes)) {
+    rule <- if (nodes[k] == 1) NA_character_ else .node_rule(tree, nodes[k])
+    sub <- if (nodes[k] == 1) inference else inference[which(eval(parse(text = rule), inference)), ]
+    if (nodes[k] != 1 && length(unique(sub$w)) == 1 && length(unique(sub$z)) == 1) next
+    r <- .node_iv(sub)
+    out[k, ] <- list(rule, round(r[["effect"]], 4), round(r[["p"]], 4), round(r[["weak"]], 4),
+                     round(nrow(sub) / nrow(inference), 4), round(r[["effect"]] * r[["compliers"]], 4),
+                     round(r[["compliers"]], 4))
+  }
+  row.names(out) <- nodes
+  out$Adj_pvalue <- NA
+  out$Adj_pvalue[is_leaf] <- round(p.adjust(as.numeric(out$pvalue[is_leaf]), adj_method), 5)
+  out
+}

@@ -1,0 +1,141 @@
+/*
+ * r_shim.c -- the .Call boundary between R and libbcfgpu.so (include/bcfgpu.h).
+ *
+ * Replaces, for BayesIV, the native entry that bcf::bcf reaches through Rcpp:
+ *     .Call("_bcf_bcfoverparRcppClean", y, z, t(x_c), t(x_m), cutpoint lists, nburn, nsim, nthin, ...)
+ * (third-party package `bcf`; BayesIV call sites R/bcf_iv.R:89 and R/bcf_itt.R:71 of fbargaglistoffi/BCF-IV).
+ * Differences by design: matrices stay in R's native column-major layout (no transpose, no copy), the caller's rows
+ * stay in their order (the library applies and undoes bcf's treated-first permutation), outputs are allocated here
+ * with allocVector/allocMatrix and filled by the library, errors become R errors carrying bcfgpu_last_error().
+ *
+ * Not compiled in this repository's CI (no R in the image): tests/test_r_package.py syntax-checks it against a stub
+ * of Rinternals.h; INTEGRATION.md shows the build line.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <R_ext/Utils.h>
+#include <string.h>
+
+#include "bcfgpu.h"
+
+static void check(int rc, bcfgpu_handle *h)
+{
+    if (rc != BCFGPU_OK) {
+        char msg[512];
+        strncpy(msg, bcfgpu_last_error(), sizeof(msg) - 1);
+        msg[sizeof(msg) - 1] = 0;
+        if (h) bcfgpu_destroy(h);
+        Rf_error("libbcfgpu: %s", msg);
+    }
+}
+
+static double num(SEXP list, const char *name, double dflt)
+{
+    SEXP names = Rf_getAttrib(list, R_NamesSymbol);
+    for (R_xlen_t i = 0; i < Rf_xlength(list); ++i)
+        if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return Rf_asReal(VECTOR_ELT(list, i));
+    return dflt;
+}
+
+/* .Call("bcfgpu_R_device_count") */
+SEXP bcfgpu_R_device_count(void) { return Rf_ScalarInteger(bcfgpu_device_count()); }
+
+/*
+ * .Call("bcfgpu_R_fit", yscale, z, x_c, x_m, cuts_c, off_c, cuts_m, off_m, cfg, nburn, nsim, nthin, keep_draws)
+ *   yscale  numeric n      standardised outcome            z       integer n (0/1)
+ *   x_c/x_m numeric matrices n x p_con / n x p_mod (column-major, as R stores them)
+ *   cuts_*  numeric        concatenated cutpoints          off_*   integer p+1 offsets
+ *   cfg     named list     the bcfgpu_config fields that differ from bcf's defaults
+ * Runs nburn + nsim*nthin sweeps in batches of 256 with R_CheckUserInterrupt() between batches.
+ * Returns list(tau_mean, tau_var, mu_mean, yhat_mean, sigma, mu_scale, tau_scale, tau, mu, yhat, device_ms)
+ * on the standardised scale; tau/mu/yhat are nsim x n matrices when keep_draws, else NULL.
+ */
+SEXP bcfgpu_R_fit(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off_c, SEXP cuts_m, SEXP off_m, SEXP cfg_list,
+                  SEXP nburn_, SEXP nsim_, SEXP nthin_, SEXP keep_)
+{
+    const R_xlen_t n = Rf_xlength(y);
+    if (!Rf_isReal(y) || !Rf_isInteger(z) || !Rf_isMatrix(xc) || !Rf_isReal(xc) || !Rf_isMatrix(xm) || !Rf_isReal(xm))
+        Rf_error("bcfgpu_R_fit: y, x_control, x_moderate must be double, z integer");
+    if (Rf_xlength(z) != n || Rf_nrows(xc) != n || Rf_nrows(xm) != n) Rf_error("bcfgpu_R_fit: row counts differ");
+    const int p_con = Rf_ncols(xc), p_mod = Rf_ncols(xm);
+    if (Rf_xlength(off_c) != p_con + 1 || Rf_xlength(off_m) != p_mod + 1) Rf_error("bcfgpu_R_fit: bad cutpoint offsets");
+    const int nburn = Rf_asInteger(nburn_), nsim = Rf_asInteger(nsim_), nthin = Rf_asInteger(nthin_);
+    const int keep = Rf_asLogical(keep_);
+
+    bcfgpu_config cfg;
+    bcfgpu_config_init(&cfg);
+    cfg.ntree_con = (int32_t)num(cfg_list, "ntree_control", cfg.ntree_con);
+    cfg.ntree_mod = (int32_t)num(cfg_list, "ntree_moderate", cfg.ntree_mod);
+    cfg.alpha_con = num(cfg_list, "base_control", cfg.alpha_con);
+    cfg.beta_con = num(cfg_list, "power_control", cfg.beta_con);
+    cfg.alpha_mod = num(cfg_list, "base_moderate", cfg.alpha_mod);
+    cfg.beta_mod = num(cfg_list, "power_moderate", cfg.beta_mod);
+    cfg.con_sd = num(cfg_list, "con_sd", cfg.con_sd);
+    cfg.mod_sd = num(cfg_list, "mod_sd", cfg.mod_sd);
+    cfg.nu = num(cfg_list, "nu", cfg.nu);
+    cfg.lambda = num(cfg_list, "lambda", cfg.lambda);
+    cfg.sigma_init = num(cfg_list, "sigma_init", cfg.sigma_init);
+    cfg.use_muscale = (int32_t)num(cfg_list, "use_muscale", 1);
+    cfg.use_tauscale = (int32_t)num(cfg_list, "use_tauscale", 1);
+    cfg.seed = (uint64_t)num(cfg_list, "seed", 42);
+    cfg.chain = (uint32_t)num(cfg_list, "chain", 0);
+    cfg.device = (int32_t)num(cfg_list, "device", -1);
+    cfg.keep_draws = keep ? 7 : 0;
+
+    bcfgpu_handle *h = NULL;
+    check(bcfgpu_create(&cfg, &h), NULL);
+    check(bcfgpu_set_data(h, (int64_t)n, p_con, p_mod, REAL(y), INTEGER(z), REAL(xc), REAL(xm), REAL(cuts_c),
+                          INTEGER(off_c), REAL(cuts_m), INTEGER(off_m)), h);
+    /* burn-in in interruptible batches, then the saved part in one call (it owns the posterior accumulators) */
+    for (int done = 0; done < nburn; done += 256) {
+        check(bcfgpu_run(h, nburn - done < 256 ? nburn - done : 256, 0, 1), h);
+        R_CheckUserInterrupt();
+    }
+    check(bcfgpu_run(h, 0, nsim, nthin), h);
+    double ms = 0;
+    bcfgpu_last_run_ms(h, &ms);
+    int32_t ns = 0;
+    check(bcfgpu_num_saved(h, &ns), h);
+
+    const char *nm[] = {"tau_mean", "tau_var", "mu_mean", "yhat_mean", "sigma", "mu_scale", "tau_scale", "tau", "mu",
+                        "yhat", "device_ms", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+    SEXP v;
+    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_tau_mean(h, REAL(v)), h); SET_VECTOR_ELT(out, 0, v); UNPROTECT(1);
+    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_tau_var(h, REAL(v)), h); SET_VECTOR_ELT(out, 1, v); UNPROTECT(1);
+    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_mu_mean(h, REAL(v)), h); SET_VECTOR_ELT(out, 2, v); UNPROTECT(1);
+    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_yhat_mean(h, REAL(v)), h); SET_VECTOR_ELT(out, 3, v); UNPROTECT(1);
+    v = PROTECT(Rf_allocVector(REALSXP, ns)); check(bcfgpu_get_sigma(h, REAL(v)), h); SET_VECTOR_ELT(out, 4, v); UNPROTECT(1);
+    {
+        SEXP a = PROTECT(Rf_allocVector(REALSXP, ns)), b = PROTECT(Rf_allocVector(REALSXP, ns));
+        check(bcfgpu_get_scales(h, REAL(a), REAL(b)), h);
+        SET_VECTOR_ELT(out, 5, a); SET_VECTOR_ELT(out, 6, b);
+        UNPROTECT(2);
+    }
+    if (keep) {
+        /* the library returns draw-major rows (nsaved x n, row-major) = an n x nsaved column-major R matrix: the R
+         * wrapper transposes to bcf's nsim x n */
+        for (int which = 0; which < 3; ++which) {
+            v = PROTECT(Rf_allocMatrix(REALSXP, (int)n, ns));
+            check(bcfgpu_get_draws(h, which, REAL(v)), h);
+            SET_VECTOR_ELT(out, 7 + which, v);
+            UNPROTECT(1);
+        }
+    }
+    SET_VECTOR_ELT(out, 10, Rf_ScalarReal(ms));
+    bcfgpu_destroy(h);
+    UNPROTECT(1);
+    return out;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"bcfgpu_R_device_count", (DL_FUNC)&bcfgpu_R_device_count, 0},
+    {"bcfgpu_R_fit", (DL_FUNC)&bcfgpu_R_fit, 13},
+    {NULL, NULL, 0}};
+
+void R_init_BayesIVgpu(DllInfo *dll)
+{
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}

@@ -1,0 +1,291 @@
+"""`bcf_iv()` / `bcf_itt()` -- Python twins of the reference's two public functions, driving the GPU sampler.
+
+Reference: R/bcf_iv.R:47-304 and R/bcf_itt.R:33-254 (fbargaglistoffi/BCF-IV).  Same arguments, defaults and returned
+table; the steps are the reference's: honest split -> logistic propensity (on the LOGIT scale, R/bcf_iv.R:75) ->
+complier proportion -> ITT by Bayesian Causal Forest (THE HOT PATH, R/bcf_iv.R:89, here bcf_iv_b200.bcf.bcf on the GPU)
+-> tauhat = itt / pic -> depth-limited CART on tauhat -> per-node 2SLS and weak-instrument test on the inference
+sample -> p-value adjustment on the leaves.  The R version of the same glue is bcf_iv_b200/R/BayesIVgpu/R/.
+
+Everything except the sampler stays on the CPU (north_star): the pieces R takes from rpart / AER / stats are restated
+here in closed form (`cart`, `tsls`, `p_adjust`, `logit_link`).  Deviations, all forced by what is not in scope:
+  * the complier proportion `pic` comes from the same GPU sampler run on the treatment received (tau of  w ~ z  is
+    P(complier | x)) instead of bartCause::bartc (a different third-party sampler);
+  * binary = TRUE (the reference switches to bartc there and never reaches bcf) raises NotImplementedError;
+  * the honest split uses NumPy's generator: the same seed gives a different split than R's sample().
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import bcf as _bcf
+
+COLUMNS = ["node", "CCACE", "pvalue", "Weak_IV_test", "Pi_obs", "ITT", "Pi_compliers", "Adj_pvalue"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stats::glm(z ~ x, binomial) + predict(type = "link")   (R/bcf_iv.R:72-75)
+# ---------------------------------------------------------------------------------------------------------------
+def logit_link(z, X, iters=25, tol=1e-8):
+    """IRLS logistic regression of z on (1, X); returns the linear predictor (log-odds), as predict.glm does by default."""
+    z = np.asarray(z, dtype=np.float64)
+    A = np.column_stack([np.ones(len(z)), np.asarray(X, dtype=np.float64)])
+    # drop aliased columns the way glm does (their coefficient is NA and they do not enter the prediction)
+    q, r = np.linalg.qr(A)
+    keep = np.abs(np.diag(r)) > 1e-10 * max(1.0, np.abs(np.diag(r)).max())
+    A = A[:, keep]
+    beta = np.zeros(A.shape[1])
+    eta = np.zeros(len(z))
+    dev_old = np.inf
+    for _ in range(iters):
+        mu = 1.0 / (1.0 + np.exp(-eta))
+        wgt = np.clip(mu * (1.0 - mu), 1e-10, None)
+        zz = eta + (z - mu) / wgt
+        AtW = A.T * wgt
+        beta = np.linalg.solve(AtW @ A, AtW @ zz)
+        eta = A @ beta
+        mu = np.clip(1.0 / (1.0 + np.exp(-eta)), 1e-12, 1 - 1e-12)
+        dev = -2.0 * np.sum(z * np.log(mu) + (1 - z) * np.log(1 - mu))
+        if abs(dev - dev_old) / (abs(dev) + 0.1) < tol:
+            break
+        dev_old = dev
+    return eta
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rpart::rpart(tauhat ~ ., method = "anova", maxdepth, cp, minsplit)   (R/bcf_iv.R:101-105, R/bcf_itt.R:82-84)
+# ---------------------------------------------------------------------------------------------------------------
+class CartNode:
+    __slots__ = ("id", "n", "mean", "dev", "var", "cut", "left", "right", "rule")
+
+    def __init__(self, id_, idx, y, rule):
+        self.id, self.n, self.mean = id_, len(idx), float(y[idx].mean())
+        self.dev = float(((y[idx] - self.mean) ** 2).sum())
+        self.var = self.cut = self.left = self.right = None
+        self.rule = rule                                    # list of (var, "<" or ">=", cut): path.rpart's conditions
+
+
+def _best_split(X, y, idx, minbucket):
+    best = (0.0, None, None)
+    yy = y[idx]
+    tot, n = yy.sum(), len(idx)
+    base = tot * tot / n
+    for v in range(X.shape[1]):
+        xv = X[idx, v]
+        order = np.argsort(xv, kind="stable")
+        xs, ys = xv[order], yy[order]
+        cs = np.cumsum(ys)[:-1]
+        nl = np.arange(1, n)
+        ok = (xs[1:] != xs[:-1]) & (nl >= minbucket) & (n - nl >= minbucket)
+        if not ok.any():
+            continue
+        gain = cs ** 2 / nl + (tot - cs) ** 2 / (n - nl) - base      # decrease of the sum of squares
+        gain = np.where(ok, gain, -np.inf)
+        j = int(np.argmax(gain))
+        if gain[j] > best[0] * (1 + 1e-12):
+            best = (float(gain[j]), v, 0.5 * (xs[j] + xs[j + 1]))
+    return best
+
+
+def cart(X, y, maxdepth=2, cp=0.01, minsplit=20, minbucket=None):
+    """Regression tree with rpart's stopping rules: a node is split only if it has >= minsplit rows, each child gets
+    >= minbucket = round(minsplit / 3), and the split improves the fit by at least cp * (root deviance).
+    Nodes are numbered like rpart's frame: root 1, children 2i and 2i + 1; rows with x < cut go LEFT."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if minbucket is None:
+        minbucket = int(round(minsplit / 3.0))
+    root = CartNode(1, np.arange(len(y)), y, [])
+    nodes, where = {1: root}, np.ones(len(y), dtype=np.int64)
+    todo = [(root, np.arange(len(y)), 0)]
+    while todo:
+        nd, idx, depth = todo.pop()
+        if depth >= maxdepth or nd.n < minsplit or nd.dev <= 0:
+            continue
+        gain, v, cut = _best_split(X, y, idx, minbucket)
+        if v is None or gain < cp * root.dev:
+            continue
+        li, ri = idx[X[idx, v] < cut], idx[X[idx, v] >= cut]
+        nd.var, nd.cut = v, cut
+        nd.left = CartNode(2 * nd.id, li, y, nd.rule + [(v, "<", cut)])
+        nd.right = CartNode(2 * nd.id + 1, ri, y, nd.rule + [(v, ">=", cut)])
+        nodes[nd.left.id], nodes[nd.right.id] = nd.left, nd.right
+        where[li], where[ri] = nd.left.id, nd.right.id
+        todo += [(nd.left, li, depth + 1), (nd.right, ri, depth + 1)]
+    return nodes, where
+
+
+def rule_text(rule, names):
+    """the node's path as the reference prints it: 'x1< 0.5 & x2>=0.5' (path.rpart's format)"""
+    return " & ".join(f"{names[v]}{'< ' if op == '<' else '>='}{cut:.4g}" for v, op, cut in rule)
+
+
+def rule_mask(rule, X):
+    m = np.ones(X.shape[0], dtype=bool)
+    for v, op, cut in rule:
+        m &= (X[:, v] < cut) if op == "<" else (X[:, v] >= cut)
+    return m
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# AER::ivreg(y ~ w | z) + summary(diagnostics = TRUE)   (R/bcf_iv.R:127-132, 158-163)
+# ---------------------------------------------------------------------------------------------------------------
+def _t_sf2(t, df):
+    from scipy.stats import t as tdist
+    return float(2.0 * tdist.sf(abs(t), df))
+
+
+def tsls(y, w, z):
+    """Just-identified 2SLS of y on (1, w) with instrument z: coefficient of w, its t-test p-value (n - 2 df, as
+    summary.ivreg), and the weak-instrument test (first-stage F of z, on (1, n - 2) df)."""
+    y, w, z = (np.asarray(a, dtype=np.float64) for a in (y, w, z))
+    n = len(y)
+    zc, wc, yc = z - z.mean(), w - w.mean(), y - y.mean()
+    szw, szz = float(zc @ wc), float(zc @ zc)
+    if szz == 0 or szw == 0:
+        return float("nan"), float("nan"), float("nan")
+    beta = float(zc @ yc) / szw
+    alpha = y.mean() - beta * w.mean()
+    res = y - alpha - beta * w
+    s2 = float(res @ res) / (n - 2)
+    se = math.sqrt(s2 * szz) / abs(szw)                       # sqrt(s2 / (sum (what - mean)^2)), what = fitted first stage
+    p = _t_sf2(beta / se, n - 2) if se > 0 else float("nan")
+    # first stage w ~ z
+    g = szw / szz
+    r1 = wc - g * zc
+    s2f = float(r1 @ r1) / (n - 2)
+    if s2f <= 0:
+        pweak = 0.0
+    else:
+        from scipy.stats import f as fdist
+        pweak = float(fdist.sf(g * g * szz / s2f, 1, n - 2))
+    return beta, p, pweak
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stats::p.adjust   (R/bcf_iv.R:183)
+# ---------------------------------------------------------------------------------------------------------------
+def p_adjust(p, method="holm"):
+    p = np.asarray(p, dtype=np.float64)
+    n = len(p)
+    if n == 0 or method == "none":
+        return p.copy()
+    o = np.argsort(p)
+    ro = np.argsort(o)
+    ps = p[o]
+    i = np.arange(1, n + 1)
+    if method == "bonferroni":
+        return np.minimum(1.0, p * n)
+    if method == "holm":
+        return np.minimum(1.0, np.maximum.accumulate((n - i + 1) * ps))[ro]
+    if method in ("hochberg", "hockberg"):                   # the reference's docstring spells it "hockberg"
+        return np.minimum(1.0, np.minimum.accumulate(((n - i + 1) * ps)[::-1])[::-1])[ro]
+    if method in ("BH", "fdr"):
+        return np.minimum(1.0, np.minimum.accumulate((n / i * ps)[::-1])[::-1])[ro]
+    if method == "BY":
+        q = np.sum(1.0 / i)
+        return np.minimum(1.0, np.minimum.accumulate((q * n / i * ps)[::-1])[::-1])[ro]
+    if method == "hommel":
+        q = pa = np.full(n, np.min(n * ps / i))
+        for m in range(n - 1, 1, -1):
+            i1 = np.arange(n - m + 1)
+            i2 = np.arange(n - m + 1, n)
+            q1 = np.min(m * ps[i2] / np.arange(2, m + 1))
+            q = q.copy()
+            q[i1] = np.minimum(m * ps[i1], q1)
+            q[i2] = q[n - m]
+            pa = np.maximum(pa, q)
+        return np.maximum(pa, ps)[ro]
+    raise ValueError(f"unknown p-value adjustment method {method!r}")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the two public functions
+# ---------------------------------------------------------------------------------------------------------------
+def _split(n, inference_ratio, seed):
+    rng = np.random.default_rng(seed)
+    index = rng.choice(n, int(n * inference_ratio), replace=False)     # the INFERENCE rows (R/bcf_iv.R:57)
+    disc = np.setdiff1d(np.arange(n), index)
+    return disc, index
+
+
+def _node_rows(nodes, where, names, inf_y, inf_w, inf_z, inf_X):
+    """per-node 2SLS on the inference sample; rows indexed like the reference's bcfivMat (by rpart node number)"""
+    ids = sorted(nodes)
+    rows = {}
+    for nid in ids:
+        nd = nodes[nid]
+        m = rule_mask(nd.rule, inf_X)
+        ys, ws, zs = inf_y[m], inf_w[m], inf_z[m]
+        if nid != 1 and len(np.unique(ws)) == 1 and len(np.unique(zs)) == 1:
+            rows[nid] = None                                  # R/bcf_iv.R:157: node skipped, row stays NA
+            continue
+        eff, p, pweak = tsls(ys, ws, zs)
+        comp = float(np.mean(zs == ws))
+        rows[nid] = dict(node=(None if nid == 1 else rule_text(nd.rule, names)), CCACE=round(eff, 4), pvalue=round(p, 4),
+                         Weak_IV_test=round(pweak, 4), Pi_obs=round(m.mean(), 4), ITT=round(eff * comp, 4),
+                         Pi_compliers=round(comp, 4))
+    return ids, rows
+
+
+def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5, max_depth=2, cp=0.01, minsplit=10,
+           adj_method="holm", seed=42, **bcf_args):
+    """Discovery and estimation of heterogeneity in the complier average causal effect (R/bcf_iv.R:47).
+    Returns a pandas DataFrame with the reference's columns (COLUMNS), one row per CART node."""
+    import pandas as pd
+    if binary:
+        raise NotImplementedError("binary = TRUE uses bartCause::bartc in the reference (R/bcf_iv.R:198) and never "
+                                  "reaches the BCF sampler; that probit BART path is not part of this build")
+    y, w, z = (np.asarray(a, dtype=np.float64).ravel() for a in (y, w, z))
+    X = np.asarray(x, dtype=np.float64)
+    names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
+    disc, index = _split(len(y), inference_ratio, seed)
+    pihat = logit_link(z[disc], X[disc])
+    fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
+    fit_args.update(bcf_args)
+    pic = _bcf.bcf(w[disc], z[disc], X[disc], X[disc], pihat, **fit_args)["tau_mean"]      # P(complier | x)
+    itt = _bcf.bcf(y[disc], z[disc], X[disc], X[disc], pihat, **fit_args)["tau_mean"]      # R/bcf_iv.R:89-91
+    tauhat = itt / pic                                                                      # R/bcf_iv.R:94
+    nodes, where = cart(X[disc], tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
+    ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
+    leaves = {nid for nid in ids if nodes[nid].left is None}
+    tab = pd.DataFrame([rows[n] if rows[n] is not None else {c: None for c in COLUMNS[:-1]} for n in ids],
+                       index=ids, columns=COLUMNS[:-1])
+    adj = pd.Series([None] * len(ids), index=ids, dtype=object)
+    lv = [n for n in ids if n in leaves and rows[n] is not None]
+    if lv:
+        a = np.round(p_adjust([rows[n]["pvalue"] for n in lv], adj_method), 5)
+        for n_, v in zip(lv, a):
+            adj[n_] = float(v)
+    tab["Adj_pvalue"] = adj
+    return tab
+
+
+def bcf_itt(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5, max_depth=2, seed=42, **bcf_args):
+    """Heterogeneity in the intention-to-treat effect (R/bcf_itt.R:33): prints the node effects and returns None,
+    as the reference does."""
+    if binary:
+        raise NotImplementedError("binary = TRUE uses bartCause::bartc in the reference (R/bcf_itt.R:166)")
+    y, w, z = (np.asarray(a, dtype=np.float64).ravel() for a in (y, w, z))
+    X = np.asarray(x, dtype=np.float64)
+    names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
+    disc, index = _split(len(y), inference_ratio, seed)
+    pihat = logit_link(z[disc], X[disc])
+    fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
+    fit_args.update(bcf_args)
+    tauhat = _bcf.bcf(y[disc], z[disc], X[disc], X[disc], pihat, **fit_args)["tau_mean"]   # R/bcf_itt.R:71-75
+    nodes, where = cart(X[disc], tauhat, maxdepth=max_depth)                                # rpart defaults (R/bcf_itt.R:82)
+    ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
+    for nid in ids:
+        r = rows[nid]
+        if r is None:
+            continue
+        if nid == 1:
+            print(f"The effect on the overall sample is {r['CCACE']}")
+        else:
+            print(f"The effect on the subpopulation {r['node']} is {r['CCACE']}")
+        print(f"P-value {r['pvalue']}")
+        print(f"P-value Weak-Instrument Test {r['Weak_IV_test']}")
+        print(f"Proportion of observations in the node:  {r['Pi_obs']:.2f}")
+    return None

@@ -1,0 +1,118 @@
+"""`bcf()` -- the drop-in for the one call BayesIV makes into the hot path.
+
+Reference call sites (fbargaglistoffi/BCF-IV):
+    R/bcf_iv.R:89    itt_bcf <- quiet(bcf(y[-index], z[-index], x[-index,], x[-index,], pihat, nburn=n_burn, nsim=n_sim))
+    R/bcf_itt.R:71   bcf_fit <- quiet(bcf(... same ...))
+and the only use of the result: `$tau` -> colMeans (R/bcf_iv.R:90-91, R/bcf_itt.R:74-75).
+
+Same formal argument names, meanings, defaults and error behaviour as `bcf::bcf` [bcf-recall, SURVEY.md A.1 / 8b]; the
+sampler itself is libbcfgpu.so (CUDA, sm_100a) behind the C-ABI of include/bcfgpu.h.  There is no CPU path: without a
+CUDA device the call raises.  The R twin of this file is bcf_iv_b200/R/BayesIVgpu/R/bcf.R.
+"""
+from __future__ import annotations
+
+import threading
+import warnings
+
+import numpy as np
+
+from . import _lib, prep
+
+DRAW_BYTES_CAP = 8 << 30   # keep nsim x n draws on the device only below this (3 matrices of doubles)
+
+
+def _run_chain(out, idx, P, cuts, cfg, nburn, nsim, nthin, keep, device):
+    try:
+        s = _lib.Sampler(device=device, **cfg)
+        s.set_data(P.yscale, P.z, P.x_c, P.x_m, *cuts)
+        s.run(nburn, nsim, nthin)
+        r = {"sigma": s.sigma(), "scales": s.scales(), "tau_mean": s.tau_mean(), "mu_mean": s.mu_mean(),
+             "yhat_mean": s.yhat_mean(), "tau_var": s.tau_var(), "ms": s.last_run_ms, "moves": s.counters()}
+        if keep:
+            r["tau"], r["mu"], r["yhat"] = s.draws("tau"), s.draws("mu"), s.draws("yhat")
+        s.close()
+        out[idx] = r
+    except BaseException as e:     # re-raised on the calling thread
+        out[idx] = e
+
+
+def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nthin=1, update_interval=100,
+        ntree_control=200, sd_control=None, base_control=0.95, power_control=2.0,
+        ntree_moderate=50, sd_moderate=None, base_moderate=0.25, power_moderate=3.0,
+        nu=3.0, lambda_=None, sigq=0.9, sighat=None, include_pi="control", use_muscale=True, use_tauscale=True,
+        w=None, random_seed=None, n_chains=1, n_cores=None, n_threads=None, no_output=True,
+        save_tree_directory=None, log_file=None, verbose=False,
+        devices=None, keep_draws=None, engine=_lib.ENGINE_AUTO):
+    """Fit the Bayesian Causal Forest  y = mu(x, pihat) + tau(x) z + eps  on the GPU.
+
+    Returns a dict with bcf's fields: `sigma` (nsim*n_chains), `yhat`, `mu`, `tau` (nsim*n_chains x n, original row
+    order, original y units), `mu_scale`, `tau_scale`, `perm`; plus `tau_mean` / `mu_mean` / `yhat_mean` / `tau_var`
+    (what BayesIV actually consumes: colMeans) which are accumulated on the device and always present.
+
+    Extras beyond bcf's signature: `devices` (CUDA ordinals, chains are dealt round-robin: one independent chain per
+    GPU), `keep_draws` (None = keep the three nsim x n matrices only while they fit DRAW_BYTES_CAP),
+    `engine`.  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
+    no_output, verbose, update_interval) are accepted and ignored; observation weights `w` are not implemented.
+    """
+    if nburn is None or nsim is None:
+        raise TypeError("bcf() needs nburn and nsim")
+    if w is not None:
+        raise NotImplementedError("observation weights (bcf 2.x `w`) are not implemented; BayesIV never passes them")
+    if x_moderate is None:
+        x_moderate = x_control
+    if pihat is None:
+        raise TypeError("bcf() needs pihat")
+    if int(nburn) < 0 or int(nsim) < 1 or int(nthin) < 1:
+        raise ValueError("need nburn >= 0, nsim >= 1, nthin >= 1")
+    if nburn < 100:
+        warnings.warn("A low (<100) value for nburn was supplied")
+    if _lib.device_count() < 1:
+        raise _lib.BcfGpuError(2, "no CUDA device available (libbcfgpu has no CPU fallback)")
+    P = prep.prepare(y, z, x_control, x_moderate, pihat, include_pi=include_pi, sd_control=sd_control,
+                     sd_moderate=sd_moderate, nu=nu, lambda_=lambda_, sigq=sigq, sighat=sighat,
+                     use_tauscale=use_tauscale)
+    cc, oc = prep.pack_cuts(P.cuts_c)
+    cm, om = prep.pack_cuts(P.cuts_m)
+    n = P.n
+    if keep_draws is None:
+        keep_draws = 3 * 8 * n * int(nsim) <= DRAW_BYTES_CAP
+    seed = int(random_seed) if random_seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+    devs = list(devices) if devices is not None else list(range(min(_lib.device_count(), max(1, int(n_chains)))))
+    cfg = dict(ntree_con=int(ntree_control), ntree_mod=int(ntree_moderate), alpha_con=float(base_control),
+               beta_con=float(power_control), alpha_mod=float(base_moderate), beta_mod=float(power_moderate),
+               con_sd=P.con_sd, mod_sd=P.mod_sd, nu=float(nu), lambda_=P.lambda_, sigma_init=P.sigma_init,
+               use_muscale=int(bool(use_muscale)), use_tauscale=int(bool(use_tauscale)), seed=seed,
+               keep_draws=7 if keep_draws else 0, engine=int(engine))
+    res = [None] * int(n_chains)
+    threads = []
+    for c in range(int(n_chains)):
+        ccfg = dict(cfg, chain=c)
+        th = threading.Thread(target=_run_chain, args=(res, c, P, (cc, oc, cm, om), ccfg, int(nburn), int(nsim),
+                                                       int(nthin), keep_draws, devs[c % len(devs)]))
+        th.start()
+        threads.append(th)
+        if len(devs) == 1:
+            th.join()           # chains that share a GPU run one after the other (each launch fills the device)
+    for th in threads:
+        th.join()
+    for r in res:
+        if isinstance(r, BaseException):
+            raise r
+    sdy, muy = P.sdy, P.muy
+    out = {
+        "sigma": sdy * np.concatenate([r["sigma"] for r in res]),
+        "mu_scale": sdy * np.concatenate([r["scales"][0] for r in res]),
+        "tau_scale": sdy * np.concatenate([r["scales"][1] for r in res]),
+        "perm": P.perm + 1,                                   # R's 1-based order(z, decreasing = TRUE)
+        "tau_mean": sdy * np.mean([r["tau_mean"] for r in res], axis=0),
+        "mu_mean": muy + sdy * np.mean([r["mu_mean"] for r in res], axis=0),
+        "yhat_mean": muy + sdy * np.mean([r["yhat_mean"] for r in res], axis=0),
+        "tau_var": sdy ** 2 * np.mean([r["tau_var"] for r in res], axis=0),
+        "device_ms": [r["ms"] for r in res],
+        "moves": [r["moves"] for r in res],
+    }
+    if keep_draws:                                            # chains rbind-ed, as bcf 2.x does
+        out["tau"] = sdy * np.concatenate([r["tau"] for r in res], axis=0)
+        out["mu"] = muy + sdy * np.concatenate([r["mu"] for r in res], axis=0)
+        out["yhat"] = muy + sdy * np.concatenate([r["yhat"] for r in res], axis=0)
+    return out

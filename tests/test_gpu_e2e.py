@@ -1,0 +1,112 @@
+"""End-to-end on the GPU through the public front ends: bcf() (the call of R/bcf_iv.R:89), bcf_iv(), bcf_itt(), and
+the two multi-GPU modes.  Level-2 parity of BASELINE.json: posterior estimands against the model's known truth and
+against the CPU oracle, within Monte-Carlo error."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from bcf_iv_b200 import _lib, bayesiv, bcf, datasets
+from helpers import make_problem, oracle_sampler
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bcf_front_end_matches_oracle_posterior_means():
+    """bcf(...)$tau -> colMeans, in the caller's row order and y units, against the oracle's run of the same chain"""
+    d = datasets.generate_dataset_wide(n=600, p=8, seed=2)
+    pihat = 0.05 * np.random.default_rng(5).standard_normal(600)
+    fit = bcf.bcf(d["y"], d["z"], d["X"], d["X"], pihat, nburn=100, nsim=60, random_seed=17)
+    assert fit["tau"].shape == (60, 600) and fit["sigma"].shape == (60,)
+    assert np.allclose(fit["tau"].mean(axis=0), fit["tau_mean"], rtol=1e-9, atol=1e-9)
+    from bcf_iv_b200 import prep
+    P = prep.prepare(d["y"], d["z"], d["X"], d["X"], pihat)
+    class Pr: pass
+    pr = Pr(); pr.P = P
+    o = oracle_sampler(pr, seed=17, max_leaves=128)
+    out = o.run(100, 60, 1)
+    assert np.allclose(fit["tau_mean"], P.sdy * out["tau_mean"][P.inv_perm], rtol=1e-7, atol=1e-7)
+    assert np.allclose(fit["sigma"], P.sdy * out["sigma"], rtol=1e-7)
+    assert np.array_equal(fit["perm"], P.perm + 1)
+
+
+def test_chains_are_independent_and_stack_like_bcf2():
+    d = datasets.generate_dataset_wide(n=400, p=6, seed=4)
+    pihat = np.zeros(400) + 0.01 * np.arange(400) / 400
+    two = bcf.bcf(d["y"], d["z"], d["X"], d["X"], pihat, nburn=100, nsim=20, random_seed=3, n_chains=2)
+    one = bcf.bcf(d["y"], d["z"], d["X"], d["X"], pihat, nburn=100, nsim=20, random_seed=3, n_chains=1)
+    assert two["tau"].shape == (40, 400)
+    assert np.array_equal(two["tau"][:20], one["tau"])            # chain 0 alone == chain 0 among two
+    assert not np.allclose(two["tau"][20:], one["tau"])            # chain 1 has its own Philox key
+
+
+def test_bcf_iv_recovers_the_readme_subgroups():
+    """README.md:79-97 workload (n=1000, p=10, compliance .75, effect 2): the discovered tree splits on x1 and x2 and
+    the leaf CCACEs are +2 / -2 in the two effect cells (R/generate_dataset.R:52-55)."""
+    d = datasets.generate_dataset(n=1000, p=10, compliance=0.75, seed=7)
+    tab = bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], n_burn=400, n_sim=400, max_depth=2, seed=42)
+    assert list(tab.columns) == bayesiv.COLUMNS and tab.index[0] == 1
+    assert tab.loc[1, "node"] is None and 0.5 < tab.loc[1, "Pi_compliers"] < 1.0
+    rules = " ".join(str(r) for r in tab["node"].dropna())
+    assert "x1" in rules and "x2" in rules
+    leaves = tab.dropna(subset=["Adj_pvalue"])
+    eff = leaves["CCACE"].astype(float)
+    assert eff.max() > 1.2 and eff.min() < -1.2
+    # the two effect leaves are significant after Holm, the complier share is about .75 + the never-assigned half
+    assert (leaves["Adj_pvalue"].astype(float) < 0.05).sum() >= 2
+
+
+def test_bcf_itt_prints_and_returns_none(capsys):
+    d = datasets.generate_dataset(n=600, p=10, seed=9)
+    assert bayesiv.bcf_itt(d["y"], d["w"], d["z"], d["X"], n_burn=150, n_sim=150) is None
+    out = capsys.readouterr().out
+    assert "The effect on the overall sample is" in out and "P-value Weak-Instrument Test" in out
+
+
+# ---- observation shards over 2 GPUs (needs 2 devices: run with `gpurun --gpus 2`) ---------------------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _shard_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from bcf_iv_b200 import multi
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pr = make_problem(n=3000, p=8, seed=12)
+    P = pr.P
+    # shards must be contiguous in the sampler's input order; any order is fine since the library permutes per shard
+    kw = dict(lambda_=P.lambda_, sigma_init=P.sigma_init, con_sd=P.con_sd, mod_sd=P.mod_sd, seed=5, ntree_con=30,
+              ntree_mod=10, device=rank)
+    tau, ms, scal = multi.run_sharded(kw, P.yscale, P.z, P.x_c, P.x_m,
+                                      (pr.cuts_c_flat, pr.off_c, pr.cuts_m_flat, pr.off_m), 6, 6)
+    ret[rank] = (tau, scal)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_lib.device_count() < 2, reason="needs 2 GPUs")
+def test_observation_shards_walk_the_single_gpu_chain():
+    """2 shards + NCCL all-reduce of the leaf statistics == the same chain on one GPU: identical decisions (integer
+    statistics are partition-independent), posterior means equal to fp64 round-off of the per-shard moments."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    mp.spawn(_shard_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    pr = make_problem(n=3000, p=8, seed=12)
+    P = pr.P
+    from helpers import gpu_sampler
+    s = gpu_sampler(pr, seed=5, ntree_con=30, ntree_mod=10, engine=1)
+    s.run(6, 6)
+    ref, sc = s.tau_mean(), s.scalars()
+    for r in (0, 1):
+        tau, scal = ret[r]
+        assert np.allclose(tau, ref, rtol=1e-9, atol=1e-9)
+        assert scal["sigma"] == pytest.approx(sc["sigma"], rel=1e-9) and scal["sweep"] == sc["sweep"]
+    assert np.array_equal(ret[0][0], ret[1][0])
