@@ -522,7 +522,8 @@ static int enqueue_sweep(bcfgpu_handle* h)
         if ((rc = shard_allreduce(h, d.totals + (size_t)j * KEYS * 8, KEYS * 8))) return rc;
     }
     k_sweep_end<<<h->grid_obs, THREADS, STEP_SMEM_BYTES, h->stream>>>(d, h->T - 1);
-    if ((rc = shard_allreduce(h, d.mom, 2 * NMOM * 3))) return rc;
+    // both parity buffers (the sweep's own and the all-zero one of the next sweep): the host does not track the parity
+    if ((rc = shard_allreduce(h, d.mom, 2 * 2 * NMOM * 3))) return rc;
     k_scalars<<<1, THREADS, 0, h->stream>>>(d);
     k_finish<<<h->grid_fin, 256, 0, h->stream>>>(d);
     CK(cudaGetLastError());

@@ -48,7 +48,8 @@ def test_bcf_iv_recovers_the_readme_subgroups():
     d = datasets.generate_dataset(n=1000, p=10, compliance=0.75, seed=7)
     tab = bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], n_burn=400, n_sim=400, max_depth=2, seed=42)
     assert list(tab.columns) == bayesiv.COLUMNS and tab.index[0] == 1
-    assert tab.loc[1, "node"] is None and 0.5 < tab.loc[1, "Pi_compliers"] < 1.0
+    import pandas as pd
+    assert pd.isna(tab.loc[1, "node"]) and 0.5 < float(tab.loc[1, "Pi_compliers"]) < 1.0
     rules = " ".join(str(r) for r in tab["node"].dropna())
     assert "x1" in rules and "x2" in rules
     leaves = tab.dropna(subset=["Adj_pvalue"])
