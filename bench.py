@@ -360,10 +360,11 @@ def run_ours(args):
         orc.build()
         nth = orc.max_threads()
         n_s = min(n, args.cpu_sample)
-        val, dt = time_oracle(w, n, n_s, 2, 1, nth)
+        val, dt = time_oracle(w, n, n_s, args.cpu_sweeps, 1, nth)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": nth, "kind": "port",
-                                "sample": f"2 timed sweeps (+1 warm-up) of the oracle on the first {n_s} rows of the "
-                                          f"same workload, {nth} OpenMP threads; scaled by n_sample/n ({dt:.1f} s of CPU)"}
+                                "sample": f"{args.cpu_sweeps} timed sweeps (+1 warm-up) of the oracle (CPU restatement of "
+                                          f"bcf's sweep) on the first {n_s} rows of the same workload, {nth} OpenMP "
+                                          f"threads over observations; scaled by n_sample/n ({dt:.1f} s wall)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -383,7 +384,8 @@ def main():
     ap.add_argument("--burnin", type=int, default=100)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--data-seed", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=100_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sweeps", type=int, default=8)
     ap.add_argument("--cpu-budget", type=float, default=120.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
