@@ -115,6 +115,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """every host core this process may use (torchrun exports OMP_NUM_THREADS=1: the oracle takes the count explicitly)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -167,7 +175,7 @@ def run_reference(args):
     from oracle import orc
     from bcf_iv_b200 import workload
     orc.build()
-    nth = orc.max_threads()
+    nth = host_threads()
     n, p = args.n, args.p
     # calibrate on 20k rows, then size the sample so that warmup + steps sweeps take about args.cpu_budget seconds
     n_cal = min(n, 20000)
@@ -358,7 +366,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         from oracle import orc
         orc.build()
-        nth = orc.max_threads()
+        nth = host_threads()
         n_s = min(n, args.cpu_sample)
         val, dt = time_oracle(w, n, n_s, args.cpu_sweeps, 1, nth)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": nth, "kind": "port",
@@ -379,8 +387,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="chains", choices=["chains", "sharded"])
     ap.add_argument("--engine", default="auto", choices=["auto", "graph", "persistent", "persistent_hbm", "batched"])
-    ap.add_argument("--n", type=int, default=1_000_000)
-    ap.add_argument("--p", type=int, default=100)
+    ap.add_argument("--nobs", "--n", dest="n", type=int, default=1_000_000)     # (--n / --p clash with torchrun abbreviations)
+    ap.add_argument("--ncov", "--p", dest="p", type=int, default=100)
     ap.add_argument("--burnin", type=int, default=100)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--data-seed", type=int, default=0)
