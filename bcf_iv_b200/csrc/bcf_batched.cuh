@@ -465,6 +465,253 @@ __device__ __forceinline__ void fill_apply(BatchSmem& sm, const Stage& S, int q,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The decision chain of a batch of small trees, run by NB warps (warp w owns tree w; l = lane).  Shared by the batched
+// and the pipelined engines.  rs: the batch's reduced statistics (rs.tot[q][k][g][4], rs.x[cell][g]); ap: the apply
+// tables being built (T rows, DL limb rows, NS, changed, off); cq: pre-decision counts per (tree, key, group).
+// ---------------------------------------------------------------------------------------------------------------
+struct ChainConsts { double s1, s0, rs1, rs0, phi1, phi0, log_tau; };
+struct ChainPrev {                       // the previous batch, when its update is not in the statistics (n = 0: none)
+    int n;
+    const int32_t* K;
+    const int16_t (*xoff)[NB];           // xoff[q][m]: first cross cell of (previous tree m, this batch's tree q)
+    const int4 (*DL)[2];
+    const int32_t (*cq)[KB][2];
+};
+template <class RS, class AP>
+__device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, SmallStage* st, const int32_t* Kq,
+                                               const int16_t (*xoff)[NB], RS& rs, AP& ap, int32_t (*cq)[KB][2],
+                                               const PreKey* pre, const ChainConsts& cc, const ChainPrev& pv, const Dev& d,
+                                               TreeRec* newtrees, int32_t* bad)
+{
+    {
+        const unsigned FULL = 0xffffffffu;
+        const int q = w;
+        const bool active = q < nb;
+        const int qq = active ? q : 0;
+        SmallStage& S = st[qq];
+        auto& tr = S.tr;
+        const Proposal& P = S.prop;
+        const int tree = first + qq;
+        const bool writer = active && ((int)blockIdx.x == tree % (int)gridDim.x);
+        const int L = tr.nleaves, K = Kq[qq];
+        const int move = P.move;
+        const bool birth = move == 1;
+        const int sx = P.slot;
+        const int pa = P.slot, pb = birth ? L : P.slot_b;
+        const int off = qq * KB;
+        // lane l = key l, both treatment groups.  The key sums stay in the global limb representation
+        // (value = w0 + w1 2^21 + w2 2^42, limbs not normalised): a correction is then three 32 x 32 -> 64 bit
+        // multiply-adds per term instead of 128-bit arithmetic.  Key 0 is (total - other keys), formed once here.
+        long long wa0 = 0, wa1 = 0, wa2 = 0, wb0 = 0, wb1 = 0, wb2 = 0;   // group 0 (control), group 1 (treated)
+        int c0 = 0, c1 = 0;
+        // everything the decision needs that is known before the chain starts
+        const PreKey pk = pre[qq * (KB + 1) + (l < K ? l : KB)];
+        const PreKey pkp = pre[qq * (KB + 1) + KB];
+        const double mo = tr.mu[(l < L) ? l : sx];            // old value of the leaf the key belongs to
+        const double zl = S.z[l < L ? l : sx];
+        const double ze0 = P.z_extra[0], ze1 = P.z_extra[1];
+        const double log_prior = P.log_prior, log_u = P.log_u;
+        double gain_c = 0.0, inv_a = 0.0, inv_b = 0.0;          // count-only part of the likelihood gain
+        bool big_enough = true;
+        if (active && move != 0) {
+            const PreKey pka = pre[qq * (KB + 1) + pa], pkb = pre[qq * (KB + 1) + pb];
+            gain_c = -cc.log_tau - 0.5 * (pka.plog + pkb.plog - pkp.plog);
+            inv_a = pka.inv; inv_b = pkb.inv;
+            big_enough = pka.k1 + pka.k0 >= d.min_leaf && pkb.k1 + pkb.k0 >= d.min_leaf;
+        }
+        if (active && l < K) {
+            const int cL0 = birth ? (int)rs.tot[q][L][0][0] : 0, cL1 = birth ? (int)rs.tot[q][L][1][0] : 0;
+            if (l < L) { c0 = tr.cnt0[l] - ((birth && l == sx) ? cL0 : 0); c1 = tr.cnt1[l] - ((birth && l == sx) ? cL1 : 0); }
+            else { c0 = cL0; c1 = cL1; }
+            cq[q][l][0] = c0; cq[q][l][1] = c1;
+            if (l >= 1) {
+                wa0 = rs.tot[q][l][0][1]; wa1 = rs.tot[q][l][0][2]; wa2 = rs.tot[q][l][0][3];
+                wb0 = rs.tot[q][l][1][1]; wb1 = rs.tot[q][l][1][2]; wb2 = rs.tot[q][l][1][3];
+            } else {
+                wa0 = rs.tot[0][0][0][1]; wa1 = rs.tot[0][0][0][2]; wa2 = rs.tot[0][0][0][3];
+                wb0 = rs.tot[0][0][1][1]; wb1 = rs.tot[0][0][1][2]; wb2 = rs.tot[0][0][1][3];
+                for (int kx = 1; kx < K; ++kx) {
+                    wa0 -= rs.tot[q][kx][0][1]; wa1 -= rs.tot[q][kx][0][2]; wa2 -= rs.tot[q][kx][0][3];
+                    wb0 -= rs.tot[q][kx][1][1]; wb1 -= rs.tot[q][kx][1][2]; wb2 -= rs.tot[q][kx][1][3];
+                }
+            }
+        }
+        // fold the update of one decided tree (its D rows as limbs, `DLm[kp][g]`) into this tree's sums:
+        //     w -= sum over that tree's keys kp of D[kp] * N[kp][l],   N[kp][l] = #{key kp there and key l here}.
+        // The counts do not depend on the decision: they are formed BEFORE waiting for it (N[0][l], and the whole of
+        // lane 0's row, by subtraction from the marginal counts).  barid > 0: wait for the owner's rows first.
+        auto fold = [&](const int4 (*DLm)[2], int Km, int xb, const int32_t (*cqm)[2], int barid) {
+            const int stride = K - 1;
+            int na0 = 0, na1 = 0, nb0 = 0, nb1 = 0, nc0 = 0, nc1 = 0;   // N[kp][l] for kp = 1, 2, 3, by group
+            int nz0 = c0, nz1 = c1;                                       // N[0][l]
+            if (l < K) {
+                for (int kp = 1; kp < Km; ++kp) {
+                    int x0, x1;
+                    if (l >= 1) { x0 = (int)rs.x[xb + (kp - 1) * stride + (l - 1)][0]; x1 = (int)rs.x[xb + (kp - 1) * stride + (l - 1)][1]; }
+                    else {
+                        x0 = cqm[kp][0]; x1 = cqm[kp][1];
+                        for (int kx = 1; kx < K; ++kx) { x0 -= (int)rs.x[xb + (kp - 1) * stride + (kx - 1)][0]; x1 -= (int)rs.x[xb + (kp - 1) * stride + (kx - 1)][1]; }
+                    }
+                    nz0 -= x0; nz1 -= x1;
+                    if (kp == 1) { na0 = x0; na1 = x1; } else if (kp == 2) { nb0 = x0; nb1 = x1; } else if (kp == 3) { nc0 = x0; nc1 = x1; }
+                }
+            }
+            if (barid > 0) asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(NB * 32) : "memory");
+            if (l < K) {
+                const int4 z0 = DLm[0][0], z1 = DLm[0][1];
+                wa0 -= (long long)z0.x * nz0; wa1 -= (long long)z0.y * nz0; wa2 -= (long long)z0.z * nz0;
+                wb0 -= (long long)z1.x * nz1; wb1 -= (long long)z1.y * nz1; wb2 -= (long long)z1.z * nz1;
+                if (Km > 1) {
+                    const int4 a0 = DLm[1][0], a1 = DLm[1][1];
+                    wa0 -= (long long)a0.x * na0; wa1 -= (long long)a0.y * na0; wa2 -= (long long)a0.z * na0;
+                    wb0 -= (long long)a1.x * na1; wb1 -= (long long)a1.y * na1; wb2 -= (long long)a1.z * na1;
+                }
+                if (Km > 2) {
+                    const int4 a0 = DLm[2][0], a1 = DLm[2][1];
+                    wa0 -= (long long)a0.x * nb0; wa1 -= (long long)a0.y * nb0; wa2 -= (long long)a0.z * nb0;
+                    wb0 -= (long long)a1.x * nb1; wb1 -= (long long)a1.y * nb1; wb2 -= (long long)a1.z * nb1;
+                }
+                if (Km > 3) {
+                    const int4 a0 = DLm[3][0], a1 = DLm[3][1];
+                    wa0 -= (long long)a0.x * nc0; wa1 -= (long long)a0.y * nc0; wa2 -= (long long)a0.z * nc0;
+                    wb0 -= (long long)a1.x * nc1; wb1 -= (long long)a1.y * nc1; wb2 -= (long long)a1.z * nc1;
+                }
+                for (int kp = 4; kp < Km; ++kp) {   // rare: wide trees, counts re-read
+                    int x0, x1;
+                    if (l >= 1) { x0 = (int)rs.x[xb + (kp - 1) * stride + (l - 1)][0]; x1 = (int)rs.x[xb + (kp - 1) * stride + (l - 1)][1]; }
+                    else {
+                        x0 = cqm[kp][0]; x1 = cqm[kp][1];
+                        for (int kx = 1; kx < K; ++kx) { x0 -= (int)rs.x[xb + (kp - 1) * stride + (kx - 1)][0]; x1 -= (int)rs.x[xb + (kp - 1) * stride + (kx - 1)][1]; }
+                    }
+                    const int4 a0 = DLm[kp][0], a1 = DLm[kp][1];
+                    wa0 -= (long long)a0.x * x0; wa1 -= (long long)a0.y * x0; wa2 -= (long long)a0.z * x0;
+                    wb0 -= (long long)a1.x * x1; wb1 -= (long long)a1.y * x1; wb2 -= (long long)a1.z * x1;
+                }
+            }
+        };
+        // the previous batch (pipelined engine): decided long ago, its update is simply not in the statistics yet
+        if (active) for (int m = 0; m < pv.n; ++m) fold(&pv.DL[m * KB], pv.K[m], pv.xoff[q][m], pv.cq[m], 0);
+        const bool cprof = d.prof != nullptr && blockIdx.x == 0 && l == 0;
+        long long ct = 0;
+#define CPROF(k) do { if (cprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[8 + (k)], (unsigned long long)(now_ - ct)); ct = now_; } } while (0)
+        for (int m = 0; m < nb; ++m) {
+            if (active && q == m) {
+                if (cprof) ct = clock64();
+                // exact integer -> double, as limbs_to_double does
+                const __int128 v0 = limbs_to_i128(wa0, wa1, wa2), v1 = limbs_to_i128(wb0, wb1, wb2);
+                const double S0 = ((double)(long long)(v0 >> 40) * 1099511627776.0 + (double)(long long)(v0 & (((__int128)1 << 40) - 1))) * (1.0 / 17592186044416.0);
+                const double S1 = ((double)(long long)(v1 >> 40) * 1099511627776.0 + (double)(long long)(v1 & (((__int128)1 << 40) - 1))) * (1.0 / 17592186044416.0);
+                CPROF(2);
+                double Bk = 0.0;
+                if (l < K) Bk = cc.phi1 * (S1 * cc.rs1 + pk.k1 * mo) + cc.phi0 * (S0 * cc.rs0 + pk.k0 * mo);
+                const double Ba = __shfl_sync(FULL, Bk, pa), Bb = __shfl_sync(FULL, Bk, pb);
+                const double Bp = Ba + Bb;
+                CPROF(3);
+                // ---- the MH decision (every lane computes it from the same values) ----
+                int accepted = 0;
+                double logr = nan("");
+                if (move != 0) {
+                    const double gain = gain_c + 0.5 * (Ba * Ba * inv_a + Bb * Bb * inv_b - Bp * Bp * pkp.inv);
+                    if (birth) {
+                        if (big_enough) { logr = log_prior + gain; accepted = (log_u < logr) ? 1 : 0; }
+                    } else {
+                        logr = log_prior - gain;
+                        accepted = (log_u < logr) ? 1 : 0;
+                    }
+                }
+                // ---- the new leaf of every pre-decision key: posterior, normal, slot ----
+                // pooled pair: a rejected birth keeps leaf sx whole, an accepted death merges its two leaves
+                const bool pooled = (birth && !accepted && (l == sx || l == L)) || (move == 2 && accepted && (l == pa || l == pb));
+                const double pm = pooled ? Bp * pkp.inv : Bk * pk.inv;
+                const double ps = pooled ? pkp.psd : pk.psd;
+                double z = zl;
+                int ns = l;
+                if (birth) {
+                    if (accepted) z = (l == sx) ? ze0 : (l == L ? ze1 : zl);
+                    else if (l == L) ns = sx;
+                } else if (move == 2 && accepted) {
+                    if (l == pa || l == pb) z = ze0;
+                    const int last = L - 1;
+                    if (l == pb) ns = pa;
+                    if (pb != last && ns == last) ns = pb;      // the last slot moves into the hole
+                }
+                int fxbad = 0;
+                double mnew = 0.0, dl = 0.0;
+                if (l < K) {
+                    mnew = pm + z * ps;
+                    if (!(mnew == mnew)) *bad = ERR_NAN;
+                    dl = mnew - mo;
+                    ApRow r1, r0;
+                    r1.dr = to_fixed(cc.s1 * dl, fxbad); r1.dg = dl; r0.dr = to_fixed(cc.s0 * dl, fxbad); r0.dg = dl;
+                    ap.T[1][off + l] = r1; ap.T[0][off + l] = r0;
+                    ap.DL[off + l][1] = make_int4((int)(r1.dr & 0x1FFFFF), (int)((r1.dr >> LIMB_BITS) & 0x1FFFFF), (int)(r1.dr >> (2 * LIMB_BITS)), 0);
+                    ap.DL[off + l][0] = make_int4((int)(r0.dr & 0x1FFFFF), (int)((r0.dr >> LIMB_BITS) & 0x1FFFFF), (int)(r0.dr >> (2 * LIMB_BITS)), 0);
+                }
+                if (fxbad) *bad = ERR_FX_RANGE;
+                CPROF(4);
+                __threadfence_block();
+                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
+                CPROF(5);
+                // ---- bookkeeping nobody waits for ----
+                const double n1 = pooled ? pkp.k1 : pk.k1, n0 = pooled ? pkp.k0 : pk.k0;
+                if (l < K) ap.NS[off + l] = (uint8_t)ns;
+                if (l == 0) { ap.changed[q] = accepted; ap.off[q] = off; }
+                __syncwarp();
+                if (l == 0) {   // topology, exactly decide_core's
+                    if (birth) {
+                        if (accepted) {
+                            const int kr = pb, nx = P.node, na = tr.nnodes, nbn = tr.nnodes + 1;
+                            tr.left[nx] = (int16_t)na; tr.right[nx] = (int16_t)nbn;
+                            tr.var[nx] = (uint16_t)P.var; tr.cut[nx] = (uint16_t)P.cut;
+                            for (int ch2 = 0; ch2 < 2; ++ch2) {
+                                const int ch = ch2 ? nbn : na;
+                                tr.parent[ch] = (int16_t)nx; tr.left[ch] = tr.right[ch] = -1;
+                                tr.var[ch] = tr.cut[ch] = 0xFFFF;
+                                tr.depth[ch] = tr.depth[nx] + 1;
+                                tr.heap[ch] = 2u * tr.heap[nx] + (uint32_t)ch2;
+                            }
+                            tr.node_slot[na] = (uint8_t)sx; tr.slot_node[sx] = (int16_t)na;
+                            tr.node_slot[nbn] = (uint8_t)kr; tr.slot_node[kr] = (int16_t)nbn;
+                            tr.nnodes += 2; tr.nleaves = L + 1;
+                        }
+                    } else if (move == 2 && accepted) {
+                        const int sa = pa, sb = pb;
+                        const int nx = P.node, na = tr.left[nx], nbn = tr.right[nx];
+                        tr.left[nx] = tr.right[nx] = -1; tr.var[nx] = tr.cut[nx] = 0xFFFF;
+                        tr.node_slot[nx] = (uint8_t)sa; tr.slot_node[sa] = (int16_t)nx;
+                        const int last = L - 1;
+                        if (sb != last) {   // keep slots compact: the last slot moves into the hole
+                            const int nd = tr.slot_node[last];
+                            tr.slot_node[sb] = (int16_t)nd; tr.node_slot[nd] = (uint8_t)sb;
+                        }
+                        tr.nleaves = L - 1;
+                        tree_remove_node(tr, max(na, nbn));
+                        tree_remove_node(tr, min(na, nbn));
+                    }
+                    if (writer) {
+                        int32_t* trc = d.trace + 5 * tree;
+                        trc[0] = move; trc[1] = accepted; trc[2] = (int32_t)P.heap; trc[3] = P.var; trc[4] = P.cut;
+                        d.trace_logr[tree] = logr;
+                        if (move == 1) { atomicAdd((unsigned long long*)&d.counters[0], 1ull); if (accepted) atomicAdd((unsigned long long*)&d.counters[1], 1ull); }
+                        if (move == 2) { atomicAdd((unsigned long long*)&d.counters[2], 1ull); if (accepted) atomicAdd((unsigned long long*)&d.counters[3], 1ull); }
+                    }
+                }
+                __syncwarp();
+                if (l < K) { tr.mu[ns] = mnew; tr.cnt1[ns] = (int32_t)n1; tr.cnt0[ns] = (int32_t)n0; }   // keys of one new leaf agree
+                __syncwarp();
+                if (writer) store_small(&newtrees[tree], tr, l);
+            } else if (active && q > m) {
+                fold(&ap.DL[m * KB], Kq[m], xoff[q][m], cq[m], 1 + m);
+                if (q == m + 1) CPROF(7);
+            } else {
+                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
+            }
+        }
+    }
+#undef CPROF
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // After the grid barrier: replay the batch's decisions in tree order from the reduced integers.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d, const Scalars& sc, TreeRec* newtrees,
@@ -543,231 +790,11 @@ __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d,
     // folds in the correction of every earlier tree as soon as that tree's D rows are published (one named barrier
     // per tree: the owner arrives, the later warps wait), takes its decision, publishes its own D rows, and only
     // then does the bookkeeping nobody waits for (tree record, slot map, trace, HBM write-back).
-    const int wq = t >> 5, l = t & 31;
-    if (wq < NB) {
-        const unsigned FULL = 0xffffffffu;
-        const int q = wq;
-        const bool active = q < nb;
-        const int qq = active ? q : 0;
-        SmallStage& S = B.st[qq];
-        auto& tr = S.tr;
-        const Proposal& P = S.prop;
-        const int tree = B.first + qq;
-        const bool writer = active && ((int)blockIdx.x == tree % (int)gridDim.x);
-        const int L = tr.nleaves, K = B.K[qq];
-        const int move = P.move;
-        const bool birth = move == 1;
-        const int sx = P.slot;
-        const int pa = P.slot, pb = birth ? L : P.slot_b;
-        const int off = qq * KB;
-        // lane l = key l, both treatment groups.  The key sums stay in the global limb representation
-        // (value = w0 + w1 2^21 + w2 2^42, limbs not normalised): a correction is then three 32 x 32 -> 64 bit
-        // multiply-adds per term instead of 128-bit arithmetic.  Key 0 is (total - other keys), formed once here.
-        long long wa0 = 0, wa1 = 0, wa2 = 0, wb0 = 0, wb1 = 0, wb2 = 0;   // group 0 (control), group 1 (treated)
-        int c0 = 0, c1 = 0;
-        // everything the decision needs that is known before the chain starts
-        const PreKey pk = pre[qq * (KB + 1) + (l < K ? l : KB)];
-        const PreKey pkp = pre[qq * (KB + 1) + KB];
-        const double mo = tr.mu[(l < L) ? l : sx];            // old value of the leaf the key belongs to
-        const double zl = S.z[l < L ? l : sx];
-        const double ze0 = P.z_extra[0], ze1 = P.z_extra[1];
-        const double log_prior = P.log_prior, log_u = P.log_u;
-        double gain_c = 0.0, inv_a = 0.0, inv_b = 0.0;          // count-only part of the likelihood gain
-        bool big_enough = true;
-        if (active && move != 0) {
-            const PreKey pka = pre[qq * (KB + 1) + pa], pkb = pre[qq * (KB + 1) + pb];
-            gain_c = -log_tau - 0.5 * (pka.plog + pkb.plog - pkp.plog);
-            inv_a = pka.inv; inv_b = pkb.inv;
-            big_enough = pka.k1 + pka.k0 >= d.min_leaf && pkb.k1 + pkb.k0 >= d.min_leaf;
-        }
-        if (active && l < K) {
-            const int cL0 = birth ? (int)rs.tot[q][L][0][0] : 0, cL1 = birth ? (int)rs.tot[q][L][1][0] : 0;
-            if (l < L) { c0 = tr.cnt0[l] - ((birth && l == sx) ? cL0 : 0); c1 = tr.cnt1[l] - ((birth && l == sx) ? cL1 : 0); }
-            else { c0 = cL0; c1 = cL1; }
-            sm.cq[q][l][0] = c0; sm.cq[q][l][1] = c1;
-            if (l >= 1) {
-                wa0 = rs.tot[q][l][0][1]; wa1 = rs.tot[q][l][0][2]; wa2 = rs.tot[q][l][0][3];
-                wb0 = rs.tot[q][l][1][1]; wb1 = rs.tot[q][l][1][2]; wb2 = rs.tot[q][l][1][3];
-            } else {
-                wa0 = rs.tot[0][0][0][1]; wa1 = rs.tot[0][0][0][2]; wa2 = rs.tot[0][0][0][3];
-                wb0 = rs.tot[0][0][1][1]; wb1 = rs.tot[0][0][1][2]; wb2 = rs.tot[0][0][1][3];
-                for (int kx = 1; kx < K; ++kx) {
-                    wa0 -= rs.tot[q][kx][0][1]; wa1 -= rs.tot[q][kx][0][2]; wa2 -= rs.tot[q][kx][0][3];
-                    wb0 -= rs.tot[q][kx][1][1]; wb1 -= rs.tot[q][kx][1][2]; wb2 -= rs.tot[q][kx][1][3];
-                }
-            }
-        }
-        const bool cprof = d.prof != nullptr && blockIdx.x == 0 && l == 0;
-        long long ct = 0;
-#define CPROF(k) do { if (cprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[8 + (k)], (unsigned long long)(now_ - ct)); ct = now_; } } while (0)
-        for (int m = 0; m < nb; ++m) {
-            if (active && q == m) {
-                if (cprof) ct = clock64();
-                // exact integer -> double, as limbs_to_double does
-                const __int128 v0 = limbs_to_i128(wa0, wa1, wa2), v1 = limbs_to_i128(wb0, wb1, wb2);
-                const double S0 = ((double)(long long)(v0 >> 40) * 1099511627776.0 + (double)(long long)(v0 & (((__int128)1 << 40) - 1))) * (1.0 / 17592186044416.0);
-                const double S1 = ((double)(long long)(v1 >> 40) * 1099511627776.0 + (double)(long long)(v1 & (((__int128)1 << 40) - 1))) * (1.0 / 17592186044416.0);
-                CPROF(2);
-                double Bk = 0.0;
-                if (l < K) Bk = phi1 * (S1 * rs1 + pk.k1 * mo) + phi0 * (S0 * rs0 + pk.k0 * mo);
-                const double Ba = __shfl_sync(FULL, Bk, pa), Bb = __shfl_sync(FULL, Bk, pb);
-                const double Bp = Ba + Bb;
-                CPROF(3);
-                // ---- the MH decision (every lane computes it from the same values) ----
-                int accepted = 0;
-                double logr = nan("");
-                if (move != 0) {
-                    const double gain = gain_c + 0.5 * (Ba * Ba * inv_a + Bb * Bb * inv_b - Bp * Bp * pkp.inv);
-                    if (birth) {
-                        if (big_enough) { logr = log_prior + gain; accepted = (log_u < logr) ? 1 : 0; }
-                    } else {
-                        logr = log_prior - gain;
-                        accepted = (log_u < logr) ? 1 : 0;
-                    }
-                }
-                // ---- the new leaf of every pre-decision key: posterior, normal, slot ----
-                // pooled pair: a rejected birth keeps leaf sx whole, an accepted death merges its two leaves
-                const bool pooled = (birth && !accepted && (l == sx || l == L)) || (move == 2 && accepted && (l == pa || l == pb));
-                const double pm = pooled ? Bp * pkp.inv : Bk * pk.inv;
-                const double ps = pooled ? pkp.psd : pk.psd;
-                double z = zl;
-                int ns = l;
-                if (birth) {
-                    if (accepted) z = (l == sx) ? ze0 : (l == L ? ze1 : zl);
-                    else if (l == L) ns = sx;
-                } else if (move == 2 && accepted) {
-                    if (l == pa || l == pb) z = ze0;
-                    const int last = L - 1;
-                    if (l == pb) ns = pa;
-                    if (pb != last && ns == last) ns = pb;      // the last slot moves into the hole
-                }
-                int fxbad = 0;
-                double mnew = 0.0, dl = 0.0;
-                if (l < K) {
-                    mnew = pm + z * ps;
-                    if (!(mnew == mnew)) sm.bad = ERR_NAN;
-                    dl = mnew - mo;
-                    ApRow r1, r0;
-                    r1.dr = to_fixed(s1 * dl, fxbad); r1.dg = dl; r0.dr = to_fixed(s0 * dl, fxbad); r0.dg = dl;
-                    sm.ap.T[1][off + l] = r1; sm.ap.T[0][off + l] = r0;
-                    sm.ap.DL[off + l][1] = make_int4((int)(r1.dr & 0x1FFFFF), (int)((r1.dr >> LIMB_BITS) & 0x1FFFFF), (int)(r1.dr >> (2 * LIMB_BITS)), 0);
-                    sm.ap.DL[off + l][0] = make_int4((int)(r0.dr & 0x1FFFFF), (int)((r0.dr >> LIMB_BITS) & 0x1FFFFF), (int)(r0.dr >> (2 * LIMB_BITS)), 0);
-                }
-                if (fxbad) sm.bad = ERR_FX_RANGE;
-                CPROF(4);
-                __threadfence_block();
-                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
-                CPROF(5);
-                // ---- bookkeeping nobody waits for ----
-                const double n1 = pooled ? pkp.k1 : pk.k1, n0 = pooled ? pkp.k0 : pk.k0;
-                if (l < K) sm.ap.NS[off + l] = (uint8_t)ns;
-                if (l == 0) { sm.ap.changed[q] = accepted; sm.ap.off[q] = off; }
-                __syncwarp();
-                if (l == 0) {   // topology, exactly decide_core's
-                    if (birth) {
-                        if (accepted) {
-                            const int kr = pb, nx = P.node, na = tr.nnodes, nbn = tr.nnodes + 1;
-                            tr.left[nx] = (int16_t)na; tr.right[nx] = (int16_t)nbn;
-                            tr.var[nx] = (uint16_t)P.var; tr.cut[nx] = (uint16_t)P.cut;
-                            for (int ch2 = 0; ch2 < 2; ++ch2) {
-                                const int ch = ch2 ? nbn : na;
-                                tr.parent[ch] = (int16_t)nx; tr.left[ch] = tr.right[ch] = -1;
-                                tr.var[ch] = tr.cut[ch] = 0xFFFF;
-                                tr.depth[ch] = tr.depth[nx] + 1;
-                                tr.heap[ch] = 2u * tr.heap[nx] + (uint32_t)ch2;
-                            }
-                            tr.node_slot[na] = (uint8_t)sx; tr.slot_node[sx] = (int16_t)na;
-                            tr.node_slot[nbn] = (uint8_t)kr; tr.slot_node[kr] = (int16_t)nbn;
-                            tr.nnodes += 2; tr.nleaves = L + 1;
-                        }
-                    } else if (move == 2 && accepted) {
-                        const int sa = pa, sb = pb;
-                        const int nx = P.node, na = tr.left[nx], nbn = tr.right[nx];
-                        tr.left[nx] = tr.right[nx] = -1; tr.var[nx] = tr.cut[nx] = 0xFFFF;
-                        tr.node_slot[nx] = (uint8_t)sa; tr.slot_node[sa] = (int16_t)nx;
-                        const int last = L - 1;
-                        if (sb != last) {   // keep slots compact: the last slot moves into the hole
-                            const int nd = tr.slot_node[last];
-                            tr.slot_node[sb] = (int16_t)nd; tr.node_slot[nd] = (uint8_t)sb;
-                        }
-                        tr.nleaves = L - 1;
-                        tree_remove_node(tr, max(na, nbn));
-                        tree_remove_node(tr, min(na, nbn));
-                    }
-                    if (writer) {
-                        int32_t* trc = d.trace + 5 * tree;
-                        trc[0] = move; trc[1] = accepted; trc[2] = (int32_t)P.heap; trc[3] = P.var; trc[4] = P.cut;
-                        d.trace_logr[tree] = logr;
-                        if (move == 1) { atomicAdd((unsigned long long*)&d.counters[0], 1ull); if (accepted) atomicAdd((unsigned long long*)&d.counters[1], 1ull); }
-                        if (move == 2) { atomicAdd((unsigned long long*)&d.counters[2], 1ull); if (accepted) atomicAdd((unsigned long long*)&d.counters[3], 1ull); }
-                    }
-                }
-                __syncwarp();
-                if (l < K) { tr.mu[ns] = mnew; tr.cnt1[ns] = (int32_t)n1; tr.cnt0[ns] = (int32_t)n0; }   // keys of one new leaf agree
-                __syncwarp();
-                if (writer) store_small(&newtrees[tree], tr, l);
-            } else if (active && q > m) {
-                // fold tree m's update into this tree's sums: w -= sum over tree m's keys kp of D[kp] * N[kp][l], with
-                // N[kp][l] = observations with key kp in tree m and key l in this tree.  The counts do not depend on
-                // tree m's decision: they are formed BEFORE waiting for it (N[0][l] and the whole of lane 0's row by
-                // subtraction from the marginal counts).
-                const int om = m * KB, Km = B.K[m];
-                const int stride = K - 1;
-                const int xb = B.xoff[q][m];
-                int na0 = 0, na1 = 0, nb0 = 0, nb1 = 0, nc0 = 0, nc1 = 0;   // N[kp][l] for kp = 1, 2, 3, by group
-                int nz0 = c0, nz1 = c1;                                       // N[0][l]
-                if (l < K) {
-                    for (int kp = 1; kp < Km; ++kp) {
-                        int x0, x1;
-                        if (l >= 1) { x0 = (int)rs.x[xb + (kp - 1) * stride + (l - 1)][0]; x1 = (int)rs.x[xb + (kp - 1) * stride + (l - 1)][1]; }
-                        else {
-                            x0 = sm.cq[m][kp][0]; x1 = sm.cq[m][kp][1];
-                            for (int kx = 1; kx < K; ++kx) { x0 -= (int)rs.x[xb + (kp - 1) * stride + (kx - 1)][0]; x1 -= (int)rs.x[xb + (kp - 1) * stride + (kx - 1)][1]; }
-                        }
-                        nz0 -= x0; nz1 -= x1;
-                        if (kp == 1) { na0 = x0; na1 = x1; } else if (kp == 2) { nb0 = x0; nb1 = x1; } else if (kp == 3) { nc0 = x0; nc1 = x1; }
-                    }
-                }
-                asm volatile("bar.sync %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
-                if (cprof) ct = clock64();
-                if (l < K) {
-                    const int4 z0 = sm.ap.DL[om][0], z1 = sm.ap.DL[om][1];
-                    wa0 -= (long long)z0.x * nz0; wa1 -= (long long)z0.y * nz0; wa2 -= (long long)z0.z * nz0;
-                    wb0 -= (long long)z1.x * nz1; wb1 -= (long long)z1.y * nz1; wb2 -= (long long)z1.z * nz1;
-                    if (Km > 1) {
-                        const int4 a0 = sm.ap.DL[om + 1][0], a1 = sm.ap.DL[om + 1][1];
-                        wa0 -= (long long)a0.x * na0; wa1 -= (long long)a0.y * na0; wa2 -= (long long)a0.z * na0;
-                        wb0 -= (long long)a1.x * na1; wb1 -= (long long)a1.y * na1; wb2 -= (long long)a1.z * na1;
-                    }
-                    if (Km > 2) {
-                        const int4 a0 = sm.ap.DL[om + 2][0], a1 = sm.ap.DL[om + 2][1];
-                        wa0 -= (long long)a0.x * nb0; wa1 -= (long long)a0.y * nb0; wa2 -= (long long)a0.z * nb0;
-                        wb0 -= (long long)a1.x * nb1; wb1 -= (long long)a1.y * nb1; wb2 -= (long long)a1.z * nb1;
-                    }
-                    if (Km > 3) {
-                        const int4 a0 = sm.ap.DL[om + 3][0], a1 = sm.ap.DL[om + 3][1];
-                        wa0 -= (long long)a0.x * nc0; wa1 -= (long long)a0.y * nc0; wa2 -= (long long)a0.z * nc0;
-                        wb0 -= (long long)a1.x * nc1; wb1 -= (long long)a1.y * nc1; wb2 -= (long long)a1.z * nc1;
-                    }
-                    for (int kp = 4; kp < Km; ++kp) {   // rare: wide trees, counts re-read
-                        int x0, x1;
-                        if (l >= 1) { x0 = (int)rs.x[xb + (kp - 1) * stride + (l - 1)][0]; x1 = (int)rs.x[xb + (kp - 1) * stride + (l - 1)][1]; }
-                        else {
-                            x0 = sm.cq[m][kp][0]; x1 = sm.cq[m][kp][1];
-                            for (int kx = 1; kx < K; ++kx) { x0 -= (int)rs.x[xb + (kp - 1) * stride + (kx - 1)][0]; x1 -= (int)rs.x[xb + (kp - 1) * stride + (kx - 1)][1]; }
-                        }
-                        const int4 a0 = sm.ap.DL[om + kp][0], a1 = sm.ap.DL[om + kp][1];
-                        wa0 -= (long long)a0.x * x0; wa1 -= (long long)a0.y * x0; wa2 -= (long long)a0.z * x0;
-                        wb0 -= (long long)a1.x * x1; wb1 -= (long long)a1.y * x1; wb2 -= (long long)a1.z * x1;
-                    }
-                }
-                if (q == m + 1) CPROF(7);
-            } else {
-                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
-            }
-        }
+    if ((t >> 5) < NB) {
+        ChainConsts cc{s1, s0, rs1, rs0, phi1, phi0, log_tau};
+        ChainPrev pv{0, nullptr, nullptr, nullptr, nullptr};
+        decision_chain(t >> 5, t & 31, nb, B.first, B.st, B.K, B.xoff, rs, sm.ap, sm.cq, pre, cc, pv, d, newtrees, &sm.bad);
     }
-#undef CPROF
     __syncthreads();
     if (t == 0) { sm.ap.n = nb; sm.ap.first = B.first; sm.ap.forest = B.forest; }
     __syncthreads();
