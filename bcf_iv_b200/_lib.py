@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libbcfgpu.so")
 
 MAX_LEAVES = 128
 STATUS = {0: "OK", 1: "BAD_ARG", 2: "CUDA", 3: "NCCL", 4: "NUMERIC", 5: "OOM", 6: "STATE"}
-ENGINE_AUTO, ENGINE_GRAPH, ENGINE_PERSISTENT, ENGINE_PERSISTENT_HBM, ENGINE_BATCHED = 0, 1, 2, 3, 4
+ENGINE_AUTO, ENGINE_GRAPH, ENGINE_PERSISTENT, ENGINE_PERSISTENT_HBM, ENGINE_BATCHED, ENGINE_PIPELINED = 0, 1, 2, 3, 4, 5
 
 # every symbol include/bcfgpu.h declares (tests check the library exports each of them)
 SYMBOLS = [

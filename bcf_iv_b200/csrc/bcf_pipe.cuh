@@ -1,0 +1,644 @@
+// bcf_pipe.cuh -- PIPELINED engine: the batched engine with the decisions taken off the observation pass's critical path.
+//
+// In the batched engine a batch costs  pass + flush + grid barrier + decision chain, one after the other, and during
+// the last three almost every warp of the SM idles.  Here the CTA is split in two roles:
+//   * 16 PASS warps stream the SM's observations:  STATS(b)  ->  flush + arrive at grid barrier b  ->  APPLY(b-1);
+//   * 8 RESOLVE warps (one per tree of a batch) wait for grid barrier b, stage the reduced statistics, walk the
+//     decision chain of batch b and publish its apply tables.
+// STATS(b) therefore runs while batch b-1 is still being decided: it sees the residual WITHOUT batch b-1's update.
+// That is repaired exactly like the dependencies inside a batch (bcf_batched.cuh): the pass also counts, per pair
+// (tree m of batch b-1, tree q of batch b), how many observations fall in each pair of keys, and the chain folds
+// D_m * N into tree q's integer sums before deciding it.  Still bit-identical to the tree-at-a-time chain.
+// CTA-local hand-shakes are named barriers (H1(b): pass -> resolve "batch b is flushed", H2(b): resolve -> pass
+// "batch b's tables are ready"); the grid barrier is arrived at by the pass role and waited for by the resolve role.
+//
+// Only sweeps whose trees all have <= KB keys run here: when a wider tree shows up at the start of a sweep the kernel
+// parks the chain state and returns; the host runs that sweep with the batched engine and comes back.
+#pragma once
+#include "bcf_batched.cuh"
+
+namespace bcf {
+
+constexpr int PP_WARPS = 16;                         // pass warps
+constexpr int PR_WARPS = NB;                         // resolve warps: one per tree of a batch
+constexpr int PP_THREADS = PP_WARPS * 32, PR_THREADS = PR_WARPS * 32;
+constexpr int PIPE_THREADS = PP_THREADS + PR_THREADS;   // 768
+constexpr int PMAXC = 12;                            // columns ((tree, key >= 1) pairs) of a batch
+constexpr int PXW = 72;                              // cells between trees of one batch: (C^2 - sum c_q^2) / 2 <= 66
+constexpr int PXX = PMAXC * PMAXC;                   // cells between two consecutive batches
+constexpr int PXCAP = PXW + PXX;
+constexpr int PIPE_XSTRIDE = 512;                    // words per batch slot of Dev::cross (>= 2 * PXCAP)
+constexpr int PIPE_BYTES_PER_TILE = TILE * (8 + 8) + 2 * (NB / 2) * TILE;   // R, G, nibble-packed keys of two batches
+static_assert(2 * PXCAP <= PIPE_XSTRIDE, "cross-count slot too small");
+
+enum { BAR_H1 = 9, BAR_H2 = 11, BAR_PASS = 13, BAR_RES = 14 };   // named barriers 1..8 belong to the decision chain
+
+struct __align__(16) TMeta {                         // what the pass needs to know about a tree, per sweep
+    const void* bins;                                // column of the proposed variable
+    uint8_t K, L, birth, sx;
+    uint16_t cut;
+    uint8_t is16, pad_;
+};
+
+struct PipePlan {
+    int32_t first, nb, forest, nprev;                // nprev: trees of the previous batch not yet applied (0 or its nb)
+    int32_t ncell_w, ncell, ncol, ncolp;
+    int32_t K[NB], Kp[NB];
+    uint8_t colbase[NB], colbasep[NB];
+    int16_t xoff[NB][NB];                            // [q][m < q]       cells inside the batch
+    int16_t xoffp[NB][NB];                           // [q][m in prev]   cells against the previous batch
+    uint8_t cell_c1[PXCAP], cell_c2[PXCAP];          // columns of a cell: 0.. this batch, PMAXC.. previous batch
+    CurInfo ci[NB];
+};
+
+struct __align__(16) PipeApply {
+    int32_t n, first, forest, pad_;
+    int32_t changed[NB], off[NB];
+    ApRow T[2][NB * KB];
+    int4 DL[NB * KB][2];
+    uint8_t NS[NB * KB];
+};
+struct PipeRS { long long tot[NB][KB][2][4]; int x[PXCAP][2]; };
+struct PipeAcc { unsigned int btab[NB][KB][2][4]; unsigned int totr[2][4]; unsigned int xtab[PXCAP][2]; };
+
+struct PipeSmem {
+    // scratch of propose_stage() (same names as StepShared; the trees here have <= KB leaves)
+    int32_t ngood[KB];
+    uint32_t lkey[KB];
+    uint32_t nkey[2 * KB];
+    uint8_t nogflag[2 * KB];
+    int32_t bad;
+    int32_t anybig;
+    SmallStage pst;                                  // stage of the proposals
+    SmallStage st[NB];                               // resolve role: the batch's trees
+    PipePlan plan[2];
+    PipeApply ap[2];
+    int32_t cq[2][NB][KB][2];
+    PipeRS rs;
+    PreKey pre[NB * (KB + 1)];
+    union { PipeAcc acc; StatTab tab; double red[2 * PIPE_THREADS]; } p;
+    uint8_t colb[PP_WARPS][2 * PMAXC][32];
+};
+constexpr size_t PIPE_SMEM_BYTES = (sizeof(PipeSmem) + 15) / 16 * 16;
+
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n)
+{
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+struct PipePtrs { uint32_t R, G, keys; };            // keys: [tile][parity][pair][TILE bytes]
+
+// ---------------------------------------------------------------------------------------------------------------
+// pass role
+// ---------------------------------------------------------------------------------------------------------------
+// plan of the batch starting at `first` (thread 0 of the pass role), then the cell -> column lists in parallel
+__device__ inline void pipe_plan(PipeSmem& sm, PipePlan& P, const PipePlan* prev, const Dev& d, const TMeta* meta, int first, int pt)
+{
+    if (pt == 0) {
+        const int f = (d.f[1].ntree > 0 && first >= d.f[1].tree0) ? 1 : 0;
+        const int fend = f ? d.T : (d.f[1].ntree > 0 ? d.f[1].tree0 : d.T);
+        const int ncand = min(NB, fend - first);
+        int nb = 0, cells = 0, cols = 0;
+        for (int q = 0; q < ncand; ++q) {
+            const TMeta m = meta[first + q];
+            const int K = m.K;
+            if (cols + K - 1 > PMAXC) break;
+            P.colbase[q] = (uint8_t)cols;
+            for (int mm = 0; mm < q; ++mm) { P.xoff[q][mm] = (int16_t)cells; cells += (P.K[mm] - 1) * (K - 1); }
+            cols += K - 1;
+            P.K[q] = K;
+            CurInfo& ci = P.ci[q];
+            ci.active = 1; ci.K = K; ci.birth = m.birth; ci.sx = m.sx; ci.cut = m.cut; ci.bins = m.bins; ci.is16 = m.is16;
+            ci.forest = f; ci.new_slot = m.L;
+            nb = q + 1;
+        }
+        P.first = first; P.nb = nb; P.forest = f; P.ncol = cols; P.ncell_w = cells;
+        const int np = prev ? prev->nb : 0;
+        P.nprev = np; P.ncolp = prev ? prev->ncol : 0;
+        for (int mm = 0; mm < np; ++mm) { P.Kp[mm] = prev->K[mm]; P.colbasep[mm] = prev->colbase[mm]; }
+        for (int q = 0; q < nb; ++q)
+            for (int mm = 0; mm < np; ++mm) { P.xoffp[q][mm] = (int16_t)cells; cells += (P.Kp[mm] - 1) * (P.K[q] - 1); }
+        P.ncell = cells;
+    }
+    named_sync(BAR_PASS, PP_THREADS);
+    for (int i = pt; i < 2 * NB * NB * (KB - 1) * (KB - 1); i += PP_THREADS) {
+        const int k = 1 + i % (KB - 1), kp = 1 + (i / (KB - 1)) % (KB - 1);
+        const int m = (i / ((KB - 1) * (KB - 1))) % NB, q = (i / ((KB - 1) * (KB - 1) * NB)) % NB;
+        const int cross = i / ((KB - 1) * (KB - 1) * NB * NB);
+        if (q >= P.nb || k >= P.K[q]) continue;
+        if (!cross) {
+            if (m < q && kp < P.K[m]) {
+                const int cell = P.xoff[q][m] + (kp - 1) * (P.K[q] - 1) + (k - 1);
+                P.cell_c1[cell] = (uint8_t)(P.colbase[m] + kp - 1);
+                P.cell_c2[cell] = (uint8_t)(P.colbase[q] + k - 1);
+            }
+        } else if (m < P.nprev && kp < P.Kp[m]) {
+            const int cell = P.xoffp[q][m] + (kp - 1) * (P.K[q] - 1) + (k - 1);
+            P.cell_c1[cell] = (uint8_t)(PMAXC + P.colbasep[m] + kp - 1);
+            P.cell_c2[cell] = (uint8_t)(P.colbase[q] + k - 1);
+        }
+    }
+    // clear the pass tables of this batch
+    {
+        unsigned int* tb = reinterpret_cast<unsigned int*>(&sm.p.acc);
+        const int nw = (int)(offsetof(PipeAcc, xtab) / 4) + 2 * PXCAP;
+        for (int i = pt; i < nw; i += PP_THREADS) tb[i] = 0u;
+    }
+    named_sync(BAR_PASS, PP_THREADS);
+}
+
+// statistics of batch P over one warp tile; `kw` / `kr`: key areas of this batch (written) and of the previous one
+__device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, const PipePlan& P, const Dev& d, const PipePtrs& rs, int tile0, int lt,
+                                                int lane, int warp, int parity)
+{
+    const int tile = tile0 + lt;
+    const int g = tile < d.trt_tiles ? 1 : 0;
+    const int64_t gb = (int64_t)tile * TILE + lane * 8;
+    const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+    const uint32_t kbase = rs.keys + (uint32_t)lt * (uint32_t)(2 * (NB / 2) * TILE) + (uint32_t)lane * 8u;
+    const uint32_t kw = kbase + (uint32_t)parity * (uint32_t)((NB / 2) * TILE);
+    const uint32_t kr = kbase + (uint32_t)(parity ^ 1) * (uint32_t)((NB / 2) * TILE);
+    long long R[8];
+    uint2 sl_n = make_uint2(0u, 0u);
+    uint4 bn_n = make_uint4(0u, 0u, 0u, 0u);
+    keys_load(d, P.ci[0], P.first, gb, sl_n, bn_n);
+    res_ld8i(rs.R + toff, lane, R);
+    {
+        long long tot = 0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) tot += R[o];
+        warp_add21(sm.p.acc.totr[g], tot, lane);
+    }
+    uint8_t* colb = &sm.colb[warp][0][0];
+    const int nb = P.nb;
+    uint2 held = make_uint2(0u, 0u);
+    for (int q = 0; q < nb; ++q) {
+        const CurInfo& ci = P.ci[q];
+        const int K = P.K[q];
+        const uint2 sl = sl_n;
+        const uint4 bn = bn_n;
+        if (q + 1 < nb) keys_load(d, P.ci[q + 1], P.first + q + 1, gb, sl_n, bn_n);
+        const uint2 key = keys_make(ci, sl, bn);
+        // two trees share a byte (4 bits each; padding observations read 0xF)
+        const uint2 nib = make_uint2(key.x & 0x0F0F0F0Fu, key.y & 0x0F0F0F0Fu);
+        if (q & 1) sts_v2(kw + (uint32_t)(q >> 1) * TILE, make_uint2(held.x | (nib.x << 4), held.y | (nib.y << 4)));
+        else { held = nib; if (q == nb - 1) sts_v2(kw + (uint32_t)(q >> 1) * TILE, held); }
+        uint8_t* cb = colb + (int)P.colbase[q] * 32 + lane;
+        for (int k = 1; k < K; ++k) {
+            const uint32_t kv = (uint32_t)k * 0x01010101u;
+            const uint32_t bits = bytes_to_bits(__vcmpeq4(key.x, kv), __vcmpeq4(key.y, kv));
+            long long s = 0;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) s += ((bits >> o) & 1u) ? R[o] : 0ll;
+            unsigned int* e = sm.p.acc.btab[q][k][g];
+            warp_add21(e, s, lane);
+            if (ci.birth && k == K - 1) {
+                const int c = __reduce_add_sync(0xffffffffu, __popc(bits));
+                if (lane == 0) atomicAdd(&e[0], (unsigned int)c);
+            }
+            cb[(k - 1) * 32] = (uint8_t)bits;
+        }
+    }
+    // the previous batch's columns, from its stored keys
+    const int np = P.nprev;
+    for (int j = 0; 2 * j < np; ++j) {
+        const uint2 w = lds_v2(kr + (uint32_t)j * TILE);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = 2 * j + h;
+            if (m < np) {
+                const uint32_t n0 = (w.x >> (4 * h)) & 0x0F0F0F0Fu, n1 = (w.y >> (4 * h)) & 0x0F0F0F0Fu;
+                uint8_t* cb = colb + (PMAXC + (int)P.colbasep[m]) * 32 + lane;
+                const int Km = P.Kp[m];
+                for (int kp = 1; kp < Km; ++kp) {
+                    const uint32_t kv = (uint32_t)kp * 0x01010101u;
+                    cb[(kp - 1) * 32] = (uint8_t)bytes_to_bits(__vcmpeq4(n0, kv), __vcmpeq4(n1, kv));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int cell = lane; cell < P.ncell; cell += 32) {
+        const uint4* a = reinterpret_cast<const uint4*>(colb + (int)P.cell_c1[cell] * 32);
+        const uint4* b = reinterpret_cast<const uint4*>(colb + (int)P.cell_c2[cell] * 32);
+        const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+        const int c = __popc(a0.x & b0.x) + __popc(a0.y & b0.y) + __popc(a0.z & b0.z) + __popc(a0.w & b0.w) +
+                      __popc(a1.x & b1.x) + __popc(a1.y & b1.y) + __popc(a1.z & b1.z) + __popc(a1.w & b1.w);
+        if (c) atomicAdd(&sm.p.acc.xtab[cell][g], (unsigned int)c);
+    }
+    __syncwarp();
+}
+
+// apply a decided batch to one warp tile; fswitch: the batch is the first of the tau forest (G changes forest first)
+template <bool PAD>
+__device__ __forceinline__ void pipe_apply_tile(const PipeApply& ap, const Dev& d, const PipePtrs& rs, int tile0, int lt, int lane,
+                                                int parity, bool fswitch)
+{
+    const int tile = tile0 + lt;
+    const int g = tile < d.trt_tiles ? 1 : 0;
+    const int64_t gb = (int64_t)tile * TILE + lane * 8;
+    const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+    const uint32_t kr = rs.keys + (uint32_t)lt * (uint32_t)(2 * (NB / 2) * TILE) + (uint32_t)lane * 8u +
+                        (uint32_t)parity * (uint32_t)((NB / 2) * TILE);
+    long long R[8];
+    double G[8];
+    res_ld8i(rs.R + toff, lane, R);
+    res_ld8(rs.G + toff, lane, G);
+    if (fswitch) {   // park the mu forest's fit in HBM, bring the tau forest's in
+        st8_f64(d.Gc + gb, G);
+        ld8_f64(d.Gm + gb, G);
+    }
+    const int na = ap.n;
+    for (int j = 0; 2 * j < na; ++j) {
+        const uint2 w = lds_v2(kr + (uint32_t)j * TILE);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = 2 * j + h;
+            if (q < na) {
+                int key[8];
+                unpack8(make_uint2((w.x >> (4 * h)) & 0x0F0F0F0Fu, (w.y >> (4 * h)) & 0x0F0F0F0Fu), key);
+                const int off = ap.off[q];
+                const ApRow* Tq = &ap.T[g][off];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    if (PAD && key[o] == 15) continue;
+                    const ApRow r = Tq[key[o]];
+                    R[o] -= r.dr;
+                    G[o] += r.dg;
+                }
+                if (ap.changed[q]) {
+                    int ns[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) ns[o] = (PAD && key[o] == 15) ? PAD_SLOT : (int)ap.NS[off + key[o]];
+                    st8_u8(d.slots + (int64_t)(ap.first + q) * d.n_pad + gb, ns);
+                }
+            }
+        }
+    }
+    res_st8(rs.G + toff, lane, G);
+    res_st8i(rs.R + toff, lane, R);
+}
+
+__device__ inline void pipe_flush(PipeSmem& sm, const PipePlan& P, long long* totals, long long* cross, int pt)
+{
+    const int nb = P.nb;
+    for (int i = pt; i < nb * KB * 8; i += PP_THREADS) {
+        const int q = i / (KB * 8), k = (i >> 3) & (KB - 1), g = (i >> 2) & 1, w = i & 3;
+        long long v = 0;
+        if (k == 0) { if (q == 0) v = acc_word(sm.p.acc.totr[g], w); }        // key 0 of the first tree carries the total
+        else if (k < P.K[q]) v = acc_word(sm.p.acc.btab[q][k][g], w);
+        if (v != 0) atomicAdd((unsigned long long*)&totals[(size_t)(P.first + q) * KEYS * 8 + k * 8 + g * 4 + w], (unsigned long long)v);
+    }
+    long long* xg = cross + (size_t)P.first * PIPE_XSTRIDE;
+    for (int i = pt; i < 2 * P.ncell; i += PP_THREADS) {
+        const unsigned int v = sm.p.acc.xtab[i >> 1][i & 1];
+        if (v != 0) atomicAdd((unsigned long long*)&xg[i], (unsigned long long)v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// resolve role
+// ---------------------------------------------------------------------------------------------------------------
+// compact copies of the (up to NB) trees starting at `first`, with proposals and leaf normals: warp q takes tree q
+__device__ inline void pipe_stage_trees(PipeSmem& sm, const Dev& d, const TreeRec* trees, int first, int rw, int l)
+{
+    const int f = (d.f[1].ntree > 0 && first >= d.f[1].tree0) ? 1 : 0;
+    const int fend = f ? d.T : (d.f[1].ntree > 0 ? d.f[1].tree0 : d.T);
+    if (rw >= min(NB, fend - first)) return;
+    const TreeRec* src = &trees[first + rw];
+    SmallStage& S = sm.st[rw];
+    if (l < 2 * KB) {
+        S.tr.parent[l] = __ldcg(&src->parent[l]); S.tr.left[l] = __ldcg(&src->left[l]); S.tr.right[l] = __ldcg(&src->right[l]);
+        S.tr.var[l] = __ldcg(&src->var[l]); S.tr.cut[l] = __ldcg(&src->cut[l]); S.tr.node_slot[l] = __ldcg(&src->node_slot[l]);
+        S.tr.depth[l] = __ldcg(&src->depth[l]); S.tr.heap[l] = __ldcg(&src->heap[l]);
+    } else if (l < 3 * KB) {
+        const int s = l - 2 * KB;
+        S.tr.slot_node[s] = __ldcg(&src->slot_node[s]); S.tr.cnt0[s] = __ldcg(&src->cnt0[s]);
+        S.tr.cnt1[s] = __ldcg(&src->cnt1[s]); S.tr.mu[s] = __ldcg(&src->mu[s]);
+    } else if (l == 3 * KB) {
+        S.tr.nnodes = __ldcg(&src->nnodes); S.tr.nleaves = __ldcg(&src->nleaves);
+    }
+    if (l < (int)(sizeof(Proposal) / 8))
+        reinterpret_cast<long long*>(&S.prop)[l] = __ldcg(reinterpret_cast<const long long*>(&d.proprec[first + rw].P) + l);
+    else if (l >= 16 && l < 16 + KB)
+        S.z[l - 16] = __ldcg(&d.proprec[first + rw].z[l - 16]);
+}
+
+// everything of a batch's decisions (resolve role, PR_THREADS threads; rt = thread within the role)
+__device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, const Dev& d, const Scalars& sc, TreeRec* newtrees,
+                                    const long long* totals, const long long* cross, int rt)
+{
+    const int nb = P.nb;
+    const ForestDev& F = d.f[P.forest];
+    PipeRS& rs = sm.rs;
+    for (int i = rt; i < nb * KB * 8; i += PR_THREADS) {
+        const int q = i / (KB * 8), k = (i >> 3) & (KB - 1);
+        if (k < P.K[q]) (&rs.tot[0][0][0][0])[i] = __ldcg(&totals[(size_t)(P.first + q) * KEYS * 8 + (i & (KB * 8 - 1))]);
+    }
+    {
+        const long long* xg = cross + (size_t)P.first * PIPE_XSTRIDE;
+        for (int i = rt; i < 2 * P.ncell; i += PR_THREADS) (&rs.x[0][0])[i] = (int)__ldcg(xg + i);
+    }
+    named_sync(BAR_RES, PR_THREADS);
+    const bool is_con = F.is_con != 0;
+    const double s1 = is_con ? sc.mscale : sc.bscale1, s0 = is_con ? sc.mscale : sc.bscale0;
+    const double tau = is_con ? sc.tau_con : sc.tau_mod;
+    const double s2 = sc.sigma * sc.sigma;
+    const double phi1 = s1 * s1 / s2, phi0 = s0 * s0 / s2;
+    const double a = 1.0 / (tau * tau);
+    if (rt < nb * (KB + 1)) {   // count-only terms of every key and pooled pair (as in resolve_batch)
+        const int q = rt / (KB + 1), e = rt % (KB + 1);
+        const SmallStage& S = sm.st[q];
+        const int L = S.tr.nleaves, K = P.K[q], mv = S.prop.move, sx = S.prop.slot;
+        if (e < K || (e == KB && mv != 0)) {
+            const double cL1 = mv == 1 ? (double)rs.tot[q][L][1][0] : 0.0, cL0 = mv == 1 ? (double)rs.tot[q][L][0][0] : 0.0;
+            const int pa = sx, pb = (mv == 1) ? L : S.prop.slot_b;
+            double k1 = 0.0, k0 = 0.0, A = 0.0;
+            const int nk = e < K ? 1 : 2;
+            for (int j = 0; j < nk; ++j) {
+                const int key = e < K ? e : (j == 0 ? pa : pb);
+                double c1, c0;
+                if (key < L) {
+                    c1 = (double)S.tr.cnt1[key]; c0 = (double)S.tr.cnt0[key];
+                    if (mv == 1 && key == sx) { c1 -= cL1; c0 -= cL0; }
+                } else { c1 = cL1; c0 = cL0; }
+                k1 += c1; k0 += c0;
+                A += c1 * phi1 + c0 * phi0;
+            }
+            const double prec = a + A, inv = 1.0 / prec;
+            PreKey& pk = sm.pre[q * (KB + 1) + e];
+            pk.k1 = k1; pk.k0 = k0; pk.inv = inv; pk.plog = log(prec); pk.psd = sqrt(inv);
+        }
+    }
+    named_sync(BAR_RES, PR_THREADS);
+    {
+        ChainConsts cc{s1, s0, 1.0 / s1, 1.0 / s0, phi1, phi0, log(tau)};
+        const PipeApply& app = sm.ap[(b & 1) ^ 1];
+        ChainPrev pv{P.nprev, P.Kp, P.xoffp, app.DL, sm.cq[(b & 1) ^ 1]};
+        decision_chain(rt >> 5, rt & 31, nb, P.first, sm.st, P.K, P.xoff, rs, sm.ap[b & 1], sm.cq[b & 1], sm.pre, cc, pv, d,
+                       newtrees, &sm.bad);
+    }
+    named_sync(BAR_RES, PR_THREADS);
+    if (rt == 0) { PipeApply& ap = sm.ap[b & 1]; ap.n = nb; ap.first = P.first; ap.forest = P.forest; }
+}
+
+// proposals of sweep `sweep` (all threads of the CTA)
+__device__ inline void pipe_propose_all(PipeSmem& sm, const Dev& d, const TreeRec* trees, uint32_t sweep)
+{
+    const int t = threadIdx.x;
+    for (int j = blockIdx.x; j < d.T; j += gridDim.x) {
+        const ForestDev& F = d.f[(d.f[1].ntree > 0 && j >= d.f[1].tree0) ? 1 : 0];
+        if (t < 32) {
+            // only this tree: reuse the staging code with a one-warp mapping
+            const TreeRec* src = &trees[j];
+            SmallStage& S = sm.pst;
+            if (t < 2 * KB) {
+                S.tr.parent[t] = __ldcg(&src->parent[t]); S.tr.left[t] = __ldcg(&src->left[t]); S.tr.right[t] = __ldcg(&src->right[t]);
+                S.tr.var[t] = __ldcg(&src->var[t]); S.tr.cut[t] = __ldcg(&src->cut[t]); S.tr.node_slot[t] = __ldcg(&src->node_slot[t]);
+                S.tr.depth[t] = __ldcg(&src->depth[t]); S.tr.heap[t] = __ldcg(&src->heap[t]);
+            } else if (t < 3 * KB) {
+                const int s = t - 2 * KB;
+                S.tr.slot_node[s] = __ldcg(&src->slot_node[s]); S.tr.cnt0[s] = __ldcg(&src->cnt0[s]);
+                S.tr.cnt1[s] = __ldcg(&src->cnt1[s]); S.tr.mu[s] = __ldcg(&src->mu[s]);
+            } else if (t == 3 * KB) {
+                S.tr.nnodes = __ldcg(&src->nnodes); S.tr.nleaves = __ldcg(&src->nleaves);
+            }
+        }
+        __syncthreads();
+        if (sm.pst.tr.nleaves <= KB) {
+            propose_stage(sm, sm.pst, d, F, j, sweep);
+            publish_stage(sm.pst, d, j);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, unsigned int* bar, int ntl_max, int* done_out)
+{
+    extern __shared__ __align__(16) unsigned char bcf_dyn_smem[];
+    PipeSmem& sm = *reinterpret_cast<PipeSmem*>(bcf_dyn_smem);
+    unsigned char* dyn = bcf_dyn_smem + PIPE_SMEM_BYTES;
+    __shared__ Scalars scs;
+    __shared__ int bar_ok;
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+    const bool is_pass = warp < PP_WARPS;
+    const int pt = t, rt = t - PP_THREADS, rw = warp - PP_WARPS;
+    const bool writer0 = (blockIdx.x == 0);
+    // Grid barrier counters (every thread counts the events itself).  bar[2]: the full barriers.  bar[0] / bar[1]: the
+    // batch barriers, by batch parity -- the pass role may arrive at batch b+1 before batch b's barrier has completed
+    // (it only waits for b-1's decisions), so consecutive batches must not share a counter; it cannot reach b+2
+    // before b has completed, so two counters are enough.
+    unsigned int target = 0, tbatch[2] = {0u, 0u};
+    int bad = 0;
+    PipePtrs rs;
+    rs.R = (uint32_t)__cvta_generic_to_shared(dyn);
+    rs.G = rs.R + (uint32_t)ntl_max * (TILE * 8u);
+    rs.keys = rs.G + (uint32_t)ntl_max * (TILE * 8u);
+    TMeta* meta = reinterpret_cast<TMeta*>(dyn + (size_t)ntl_max * PIPE_BYTES_PER_TILE);
+    if (t == 0) { scs = *d.sc; sm.bad = 0; }
+    __syncthreads();
+    const int T = d.T;
+    const int tmod = d.f[1].tree0;
+    const bool has_mod = d.f[1].ntree > 0;
+    const int tile0 = (int)((int64_t)blockIdx.x * d.n_tiles / gridDim.x);
+    const int tile1 = (int)((int64_t)(blockIdx.x + 1) * d.n_tiles / gridDim.x);
+    const int ntl = tile1 - tile0;
+    const int pad_a = d.trt_tiles - 1 - tile0, pad_b = d.n_tiles - 1 - tile0;
+    auto grid_all = [&]() {   // full grid barrier, every thread of the CTA
+        target += gridDim.x;
+        __syncthreads();
+        if (t == 0) red_release_add_u32(bar + 2, 1u);
+    };
+    auto grid_all_wait = [&]() -> bool { return grid_wait(bar + 2, target, d.err, &bar_ok); };
+
+    if (is_pass)
+        for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+            const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
+            const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+            long long R[8];
+            double gc[8];
+            ld8_i64(d.rfx + gb, R); ld8_f64(d.Gc + gb, gc);
+            res_st8i(rs.R + toff, lane, R);
+            res_st8(rs.G + toff, lane, gc);
+        }
+    __syncthreads();
+    pipe_propose_all(sm, d, d.trees[scs.parity], scs.sweep);
+    grid_all();
+    if (!grid_all_wait()) return;
+
+    int done = 0;
+    for (int sw = 0; sw < nsweeps; ++sw) {
+        const Scalars sc = scs;
+        const int par = sc.parity;
+        long long* mom = d.mom + (size_t)(sc.sweep & 1u) * (2 * NMOM * 3);
+        long long* totals = sweep_totals(d, sc.sweep);
+        long long* cross = d.cross + (size_t)(sc.sweep & 1u) * (size_t)T * PIPE_XSTRIDE;
+        // ---- what the pass needs to know about every tree; a tree too wide for this engine ends the launch ----
+        if (t == 0) sm.anybig = 0;
+        __syncthreads();
+        for (int j = t; j < T; j += PIPE_THREADS) {
+            const TreeRec* tr = &d.trees[par][j];
+            const Proposal* P = &d.proprec[j].P;
+            const int L = __ldcg(&tr->nleaves), mv = __ldcg(&P->move);
+            TMeta m;
+            m.L = (uint8_t)L; m.birth = mv == 1; m.K = (uint8_t)min(255, L + (mv == 1 ? 1 : 0));
+            m.sx = (uint8_t)__ldcg(&P->slot); m.cut = (uint16_t)__ldcg(&P->cut); m.is16 = (uint8_t)__ldcg(&P->is16); m.pad_ = 0;
+            m.bins = (const void*)__ldcg(reinterpret_cast<const unsigned long long*>(&P->bins));
+            meta[j] = m;
+            if (m.K > KB || L > KB) sm.anybig = 1;
+        }
+        __syncthreads();
+        if (sm.anybig) break;
+
+        if (is_pass) {
+            // =================== pass role ===================
+            int first = 0, b = 0;
+            while (first < T) {
+                PipePlan& P = sm.plan[b & 1];
+                pipe_plan(sm, P, b > 0 ? &sm.plan[(b & 1) ^ 1] : nullptr, d, meta, first, pt);
+                for (int lt = warp; lt < ntl; lt += PP_WARPS) pipe_stats_tile(sm, P, d, rs, tile0, lt, lane, warp, b & 1);
+                named_sync(BAR_PASS, PP_THREADS);
+                pipe_flush(sm, P, totals, cross, pt);
+                named_sync(BAR_PASS, PP_THREADS);
+                if (pt == 0) red_release_add_u32(bar + (b & 1), 1u);
+                named_arrive(BAR_H1 + (b & 1), PIPE_THREADS);           // H1(b): flushed, plan visible
+                if (b > 0) {
+                    named_sync(BAR_H2 + ((b - 1) & 1), PIPE_THREADS);   // H2(b-1): its tables are ready
+                    const PipeApply& ap = sm.ap[(b - 1) & 1];
+                    const bool fswitch = has_mod && ap.first == tmod && tmod > 0;
+                    for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+                        if (lt == pad_a || lt == pad_b) pipe_apply_tile<true>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
+                        else pipe_apply_tile<false>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
+                    }
+                    named_sync(BAR_PASS, PP_THREADS);
+                }
+                first += P.nb; ++b;
+            }
+            {   // drain: the last batch
+                named_sync(BAR_H2 + ((b - 1) & 1), PIPE_THREADS);
+                const PipeApply& ap = sm.ap[(b - 1) & 1];
+                const bool fswitch = has_mod && ap.first == tmod && tmod > 0;
+                for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+                    if (lt == pad_a || lt == pad_b) pipe_apply_tile<true>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
+                    else pipe_apply_tile<false>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
+                }
+            }
+        } else {
+            // =================== resolve role ===================
+            int first = 0, b = 0;
+            while (first < T) {
+                pipe_stage_trees(sm, d, d.trees[par], first, rw, lane);     // while the pass still streams batch b
+                named_sync(BAR_H1 + (b & 1), PIPE_THREADS);                  // H1(b)
+                const PipePlan& P = sm.plan[b & 1];
+                tbatch[b & 1] += gridDim.x;
+                if (rt == 0) {
+                    const long long t0 = clock64();
+                    while (ld_acquire_u32(bar + (b & 1)) < tbatch[b & 1])
+                        if (clock64() - t0 > 8000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); __trap(); }
+                }
+                named_sync(BAR_RES, PR_THREADS);
+                pipe_resolve(sm, P, b, d, sc, d.trees[par ^ 1], totals, cross, rt);
+                named_arrive(BAR_H2 + (b & 1), PIPE_THREADS);                // H2(b)
+                first += P.nb; ++b;
+            }
+        }
+        __syncthreads();
+        // ---- epilogue: moments of (y, Gc, Gm) ----
+        if (is_pass) {
+            long long* tb = reinterpret_cast<long long*>(&sm.p.tab);
+            for (int i = pt; i < STATTAB_WORDS64; i += PP_THREADS) tb[i] = 0;
+        }
+        __syncthreads();
+        if (is_pass)
+            for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+                const int tile = tile0 + lt;
+                const int64_t gb = (int64_t)tile * TILE + lane * 8;
+                double G[8], y[8], other[8];
+                res_ld8(rs.G + (uint32_t)lt * (TILE * 8u), lane, G);
+                ld8_f64(d.y + gb, y);
+                if (has_mod) { ld8_f64(d.Gc + gb, other); moments8(sm.p.tab, y, other, G, tile < d.trt_tiles ? 1 : 0, lane, bad); }
+                else {
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) other[o] = 0.0;
+                    moments8(sm.p.tab, y, G, other, tile < d.trt_tiles ? 1 : 0, lane, bad);
+                }
+            }
+        __syncthreads();
+        for (int i = t; i < NMOM * 8; i += PIPE_THREADS) {
+            const int m = i >> 3, g = (i >> 2) & 1, q = i & 3;
+            if (q == 0) continue;
+            const long long v = table_word(sm.p.tab, PP_WARPS, m, g, q);
+            if (v != 0) atomicAdd((unsigned long long*)&mom[(g * NMOM + m) * 3 + (q - 1)], (unsigned long long)v);
+        }
+        grid_all();
+        if (!grid_all_wait()) return;
+        sweep_scalars(d, d.trees[par ^ 1], mom, sm.p.red, &scs, writer0);
+        if (sw + 1 < nsweeps) pipe_propose_all(sm, d, d.trees[par ^ 1], sc.sweep + 1u);
+        grid_all();   // proposals visible before the next sweep reads them (wait: below)
+        // ---- finishing pass ----
+        {
+            const Scalars sn = scs;
+            const double ms = sn.mscale, b1 = sn.bscale1, b0 = sn.bscale0;
+            const int row = sn.save_row;
+            if (is_pass)
+                for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+                    const int tile = tile0 + lt;
+                    const int64_t gb = (int64_t)tile * TILE + lane * 8;
+                    const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+                    const double bb = tile < d.trt_tiles ? b1 : b0;
+                    double gc[8], gm[8], y[8];
+                    long long R[8];
+                    ld8_f64(d.y + gb, y);
+                    if (has_mod) { res_ld8(rs.G + toff, lane, gm); ld8_f64(d.Gc + gb, gc); st8_f64(d.Gm + gb, gm); res_st8(rs.G + toff, lane, gc); }
+                    else {
+                        res_ld8(rs.G + toff, lane, gc);
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) gm[o] = 0.0;
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) R[o] = resync_fx(y[o], ms, gc[o], bb, gm[o], bad);
+                    res_st8i(rs.R + toff, lane, R);
+                    if (row >= 0) {
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int64_t i = gb + o;
+                            const double mu = ms * gc[o], yh = mu + bb * gm[o], tau = (b1 - b0) * gm[o];
+                            d.tau_sum[i] += tau; d.tau_sq[i] += tau * tau; d.mu_sum[i] += mu; d.yhat_sum[i] += yh;
+                            if (d.draws_tau) d.draws_tau[(int64_t)row * d.n_pad + i] = tau;
+                            if (d.draws_mu) d.draws_mu[(int64_t)row * d.n_pad + i] = mu;
+                            if (d.draws_yhat) d.draws_yhat[(int64_t)row * d.n_pad + i] = yh;
+                        }
+                    }
+                }
+            const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + t, gstride = (int64_t)gridDim.x * blockDim.x;
+            const int64_t ntot = (int64_t)T * KEYS * 8;
+            for (int64_t i = gtid; i < ntot; i += gstride) totals[i] = 0;
+            const int64_t nx = (int64_t)T * PIPE_XSTRIDE;
+            for (int64_t i = gtid; i < nx; i += gstride) cross[i] = 0;
+            long long* mom_next = d.mom + (size_t)((sc.sweep + 1u) & 1u) * (2 * NMOM * 3);
+            for (int64_t i = gtid; i < 2 * NMOM * 3; i += gstride) mom_next[i] = 0;
+        }
+        if (!grid_all_wait()) return;
+        ++done;
+    }
+    // exit: park the state in HBM in the form every engine understands (Gm was stored by the finishing pass)
+    if (is_pass)
+        for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+            const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
+            const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+            double G[8];
+            long long R[8];
+            res_ld8(rs.G + toff, lane, G);
+            res_ld8i(rs.R + toff, lane, R);
+            st8_f64(d.Gc + gb, G);
+            st8_i64(d.rfx + gb, R);
+        }
+    if (writer0 && t == 0) *done_out = done;
+    if (bad) atomicOr(d.err, ERR_FX_RANGE);
+    if (t == 0 && sm.bad) atomicOr(d.err, sm.bad);
+}
+
+}  // namespace bcf

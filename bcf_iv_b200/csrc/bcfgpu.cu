@@ -4,6 +4,7 @@
 #include "bcf_kernels.cuh"
 #include "bcf_persistent.cuh"
 #include "bcf_batched.cuh"
+#include "bcf_pipe.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -106,7 +107,9 @@ struct bcfgpu_handle {
     int engine = BCFGPU_ENGINE_GRAPH;
     int coop_grid = 0;
     int res_ntl = 0;                  // tiles per CTA of the shared-memory-resident kernels (0 = state in HBM)
-    int kernel = 0;                   // persistent kernel in use: 1 k_persistent, 2 k_resident, 3 k_batched
+    int kernel = 0;                   // persistent kernel in use: 1 k_persistent, 2 k_resident, 3 k_batched, 4 k_pipe (+ k_batched)
+    size_t pipe_smem = 0;             // dynamic shared memory of k_pipe (kernel 4; res_smem is then k_batched's)
+    int* d_done = nullptr;            // sweeps completed by the last k_pipe launch
     size_t res_smem = 0;
     unsigned int* d_bar = nullptr;
     int64_t launches = 0;
@@ -216,7 +219,7 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_sweep_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (e2 != cudaSuccess) { delete h; return fail(BCFGPU_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e2)); }
-    if (cfg->engine < BCFGPU_ENGINE_AUTO || cfg->engine > BCFGPU_ENGINE_BATCHED) { delete h; return fail(BCFGPU_ERR_BAD_ARG, "unknown engine"); }
+    if (cfg->engine < BCFGPU_ENGINE_AUTO || cfg->engine > BCFGPU_ENGINE_PIPELINED) { delete h; return fail(BCFGPU_ERR_BAD_ARG, "unknown engine"); }
     h->engine = cfg->engine == BCFGPU_ENGINE_AUTO ? BCFGPU_ENGINE_BATCHED : cfg->engine;
     *out = h;
     return BCFGPU_OK;
@@ -428,7 +431,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     DM(h, &d.trees[0], (size_t)h->T); DM(h, &d.trees[1], (size_t)h->T);
     DM(h, &d.proprec, (size_t)h->T);
     DM(h, &d.totals, (size_t)2 * h->T * KEYS * 8);
-    DM(h, &d.cross, (size_t)2 * h->T * XCAP * 2);
+    DM(h, &d.cross, (size_t)2 * h->T * PIPE_XSTRIDE);
     DM(h, &d.mom, (size_t)2 * 2 * NMOM * 3);
     DM(h, &d.sc, 1);
     DM(h, &d.err, 4);
@@ -436,10 +439,11 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     DM(h, &d.trace_logr, (size_t)h->T);
     DM(h, &d.counters, 4);
     DM(h, &h->d_bar, 64);
+    DM(h, &h->d_done, 4);
     if (getenv("BCFGPU_PROFILE")) { DM(h, &d.prof, 16); CK(cudaMemsetAsync(d.prof, 0, 128, h->stream)); }
     d.y = dy;
     CK(cudaMemsetAsync(d.totals, 0, (size_t)2 * h->T * KEYS * 8 * 8, h->stream));
-    CK(cudaMemsetAsync(d.cross, 0, (size_t)2 * h->T * XCAP * 2 * 8, h->stream));
+    CK(cudaMemsetAsync(d.cross, 0, (size_t)2 * h->T * PIPE_XSTRIDE * 8, h->stream));
     CK(cudaMemsetAsync(d.mom, 0, 2 * 2 * NMOM * 3 * 8, h->stream));
     CK(cudaMemsetAsync(d.err, 0, 16, h->stream));
     CK(cudaMemsetAsync(d.trace, 0, (size_t)h->T * 5 * 4, h->stream));
@@ -1088,23 +1092,29 @@ static int run_persistent(bcfgpu_handle* h, int total)
         const int ntl_max = (h->dev.n_tiles + grid - 1) / grid;
         h->res_ntl = 0;
         h->kernel = 0;
-        const bool want_batched = h->engine == BCFGPU_ENGINE_BATCHED || h->cfg.engine == BCFGPU_ENGINE_AUTO;
+        const bool want_batched = h->engine == BCFGPU_ENGINE_BATCHED || h->engine == BCFGPU_ENGINE_PIPELINED || h->cfg.engine == BCFGPU_ENGINE_AUTO;
         const bool may_reside = h->engine != BCFGPU_ENGINE_PERSISTENT_HBM && !getenv("BCFGPU_NO_RESIDENT");
         // does this CTA's share of the observation state fit in shared memory next to the kernel's scratch?
-        auto fits = [&](const void* fn, size_t need) -> int {
+        auto fits = [&](const void* fn, size_t need, int threads = PTHREADS) -> int {
             cudaFuncAttributes fa;
             if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) return 0;
             if (need + fa.sharedSizeBytes + 1024 > (size_t)max_optin) return 0;
             if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) return 0;
             int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PTHREADS, need) != cudaSuccess) return 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, need) != cudaSuccess) return 0;
             return per_sm >= 1;
         };
         if (want_batched && may_reside) {
             const size_t need = BATCH_SMEM_BYTES + (size_t)ntl_max * BAT_BYTES_PER_TILE;
             if (fits((const void*)k_batched, need)) { h->kernel = 3; h->res_ntl = ntl_max; h->res_smem = need; }
-            else if (h->cfg.engine == BCFGPU_ENGINE_BATCHED)
-                return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_BATCHED: the observations of one SM do not fit in shared memory at this n");
+            else if (h->cfg.engine == BCFGPU_ENGINE_BATCHED || h->cfg.engine == BCFGPU_ENGINE_PIPELINED)
+                return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_BATCHED / PIPELINED: the observations of one SM do not fit in shared memory at this n");
+            // the pipelined kernel on top of it (the batched one then serves the sweeps that hold a wide tree)
+            if (h->kernel == 3 && h->cfg.engine == BCFGPU_ENGINE_PIPELINED) {
+                const size_t needp = PIPE_SMEM_BYTES + (size_t)ntl_max * PIPE_BYTES_PER_TILE + (size_t)h->T * sizeof(TMeta) + 16;
+                if (fits((const void*)k_pipe, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; }
+                else return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_PIPELINED: the observations of one SM do not fit in shared memory at this n");
+            }
         }
         if (h->kernel == 0 && may_reside) {
             const size_t need = STEP_SMEM_BYTES + (size_t)ntl_max * RES_BYTES_PER_TILE;
@@ -1121,12 +1131,34 @@ static int run_persistent(bcfgpu_handle* h, int total)
     }
     // keep launches short enough to stay interruptible (R_CheckUserInterrupt between batches)
     const int batch = 256;
-    for (int done = 0; done < total; done += batch) {
+    for (int done = 0; done < total;) {
         int nsw = std::min(batch, total - done);
         Dev d = h->dev;
         unsigned int* bar = h->d_bar;
-        CK(cudaMemsetAsync(bar, 0, 4, h->stream));
+        CK(cudaMemsetAsync(bar, 0, 16, h->stream));
         int ntl = h->res_ntl;
+        if (h->kernel == 4) {
+            // pipelined kernel; it returns early at a sweep that holds a tree wider than KB keys: that one sweep is
+            // run by the batched kernel, then the pipelined one resumes
+            int* dn = h->d_done;
+            CK(cudaMemsetAsync(dn, 0, 4, h->stream));
+            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl, (void*)&dn};
+            CK(cudaLaunchCooperativeKernel((const void*)k_pipe, dim3(h->coop_grid), dim3(PIPE_THREADS), args, h->pipe_smem, h->stream));
+            h->launches++;
+            int ndone = 0;
+            CK(cudaMemcpyAsync(&ndone, dn, 4, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            done += ndone;
+            if (ndone < nsw) {
+                int one = 1;
+                CK(cudaMemsetAsync(bar, 0, 16, h->stream));
+                void* a2[] = {(void*)&d, (void*)&one, (void*)&bar, (void*)&ntl};
+                CK(cudaLaunchCooperativeKernel((const void*)k_batched, dim3(h->coop_grid), dim3(PTHREADS), a2, h->res_smem, h->stream));
+                h->launches++;
+                done += 1;
+            }
+            continue;
+        }
         if (h->kernel == 3) {
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};
             CK(cudaLaunchCooperativeKernel((const void*)k_batched, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
@@ -1138,6 +1170,7 @@ static int run_persistent(bcfgpu_handle* h, int total)
             CK(cudaLaunchCooperativeKernel((const void*)k_persistent, dim3(h->coop_grid), dim3(PTHREADS), args, STEP_SMEM_BYTES, h->stream));
         }
         h->launches++;
+        done += nsw;
     }
     return BCFGPU_OK;
 }

@@ -57,6 +57,9 @@ typedef enum bcfgpu_engine {
     BCFGPU_ENGINE_BATCHED = 4      /* cooperative kernel, up to 8 trees per observation pass and per grid barrier (exact
                                       integer cross-count correction), state in shared memory; AUTO picks it when the
                                       observations of an SM fit, else PERSISTENT */
+    , BCFGPU_ENGINE_PIPELINED = 5  /* BATCHED with the decisions off the pass's critical path: 16 warps stream the
+                                      observations while 8 warps decide the previous batch (cross-batch counts keep it
+                                      exact); sweeps that hold a tree with more than 8 keys fall back to BATCHED */
 } bcfgpu_engine;
 
 /* Hyper-parameters of the sampler: bcf()'s arguments after the R wrapper's rescaling. */

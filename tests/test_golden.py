@@ -34,7 +34,7 @@ def test_oracle_reproduces_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("engine", [1, 2, 4])
+@pytest.mark.parametrize("engine", [1, 2, 4, 5])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_gpu_matches_golden(name, engine):
     g = _load(name)

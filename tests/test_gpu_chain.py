@@ -41,7 +41,7 @@ def _compare_state(g, o, pr, check_trees=True):
             assert np.allclose(mg[og][leaf], mo[oo][leaf], rtol=TOL, atol=TOL)
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3, 4])
+@pytest.mark.parametrize("engine", [1, 2, 3, 4, 5])
 def test_chain_matches_oracle_readme_shape(engine):
     """Config C1 shape (n_s = 500, p = 10 binary + pihat): 30 sweeps, compared after 1, 5 and 30."""
     pr = make_problem(n=500, p=10, seed=3)
@@ -56,7 +56,7 @@ def test_chain_matches_oracle_readme_shape(engine):
     assert g.verify_leaf_cache() == 0
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3, 4])
+@pytest.mark.parametrize("engine", [1, 2, 3, 4, 5])
 def test_chain_matches_oracle_continuous_covariates(engine):
     """Continuous X -> 10 000-cutpoint uint16 grids on most columns; ragged n (not a multiple of the tile)."""
     pr = make_problem(n=1237, p=6, seed=5, continuous=True)
@@ -93,8 +93,8 @@ def test_posterior_outputs_match_oracle():
 
 def test_engines_are_bit_identical():
     """The residual is an integer (fixed-point) state updated exactly and every reduction is an integer sum, so the
-    four engines -- graph, persistent with the state in HBM, persistent with the state in shared memory, and the
-    batched engine (8 trees per pass, exact cross-count correction) -- walk the same chain bit for bit whatever
+    engines -- graph, persistent with the state in HBM, persistent with the state in shared memory, the batched
+    engine (8 trees per pass, exact cross-count correction) and its pipelined version -- walk the same chain bit for bit whatever
     their thread / CTA partitioning."""
     pr = make_problem(n=3000, p=12, seed=21)
     kw = dict(seed=4, ntree_con=50, ntree_mod=20)
@@ -102,9 +102,10 @@ def test_engines_are_bit_identical():
     b = gpu_sampler(pr, engine=3, **kw)
     c = gpu_sampler(pr, engine=2, **kw)
     e = gpu_sampler(pr, engine=4, **kw)
-    for s in (a, b, c, e):
+    f = gpu_sampler(pr, engine=5, **kw)
+    for s in (a, b, c, e, f):
         s.run(5, 10)
-    for other in (b, c, e):
+    for other in (b, c, e, f):
         assert np.array_equal(a.tau_mean(), other.tau_mean())
         assert np.array_equal(a.mu_mean(), other.mu_mean())
         assert np.array_equal(a.sigma(), other.sigma())
@@ -128,7 +129,7 @@ def test_engine_handover():
     _compare_state(ref, o, pr)
 
 
-@pytest.mark.parametrize("engine", [2, 4])
+@pytest.mark.parametrize("engine", [2, 4, 5])
 def test_chain_with_big_and_small_trees_mixed(engine):
     """Trees with more than 8 keys take the batched engine's solo path (shared-atomics table), the others are batched
     around them; install deep trees in both forests, then walk the chain against the oracle."""
