@@ -31,6 +31,9 @@ constexpr int PIPE_XSTRIDE = 512;                    // words per batch slot of 
 constexpr int PIPE_BYTES_PER_TILE = TILE * (8 + 8) + 2 * (NB / 2) * TILE;   // R, G, nibble-packed keys of two batches
 static_assert(2 * PXCAP <= PIPE_XSTRIDE, "cross-count slot too small");
 
+// registers per thread: 768 x 80 at launch; the role section re-splits the CTA's OWN
+// allocation (the pool of setmaxnreg is per CTA): 512 x 72 + 256 x 96 = 61440
+constexpr int PIPE_REGS_BASE = 80, PIPE_REGS_PASS = 72, PIPE_REGS_RESOLVE = 96;
 enum { BAR_H1 = 9, BAR_H2 = 11, BAR_PASS = 13, BAR_RES = 14 };   // named barriers 1..8 belong to the decision chain
 
 struct __align__(16) TMeta {                         // what the pass needs to know about a tree, per sweep
@@ -493,20 +496,30 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
         __syncthreads();
         if (sm.anybig) break;
 
+        // The two roles need different register budgets (the decision chain keeps a tree's sums, posterior terms and
+        // constants live; the pass is a streaming loop): re-split the SM's register file for the role section.
         if (is_pass) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_PASS));
             // =================== pass role ===================
+            const bool prof = d.prof != nullptr && blockIdx.x == 0 && pt == 0;
+            long long tp = clock64();
+#define PPROF(k) do { if (prof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
             int first = 0, b = 0;
             while (first < T) {
                 PipePlan& P = sm.plan[b & 1];
                 pipe_plan(sm, P, b > 0 ? &sm.plan[(b & 1) ^ 1] : nullptr, d, meta, first, pt);
+                PPROF(5);
                 for (int lt = warp; lt < ntl; lt += PP_WARPS) pipe_stats_tile(sm, P, d, rs, tile0, lt, lane, warp, b & 1);
                 named_sync(BAR_PASS, PP_THREADS);
+                PPROF(0);
                 pipe_flush(sm, P, totals, cross, pt);
                 named_sync(BAR_PASS, PP_THREADS);
                 if (pt == 0) red_release_add_u32(bar + (b & 1), 1u);
                 named_arrive(BAR_H1 + (b & 1), PIPE_THREADS);           // H1(b): flushed, plan visible
+                PPROF(1);
                 if (b > 0) {
                     named_sync(BAR_H2 + ((b - 1) & 1), PIPE_THREADS);   // H2(b-1): its tables are ready
+                    PPROF(2);
                     const PipeApply& ap = sm.ap[(b - 1) & 1];
                     const bool fswitch = has_mod && ap.first == tmod && tmod > 0;
                     for (int lt = warp; lt < ntl; lt += PP_WARPS) {
@@ -514,9 +527,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                         else pipe_apply_tile<false>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
                     }
                     named_sync(BAR_PASS, PP_THREADS);
+                    PPROF(3);
                 }
                 first += P.nb; ++b;
             }
+#undef PPROF
             {   // drain: the last batch
                 named_sync(BAR_H2 + ((b - 1) & 1), PIPE_THREADS);
                 const PipeApply& ap = sm.ap[(b - 1) & 1];
@@ -526,12 +541,18 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                     else pipe_apply_tile<false>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
                 }
             }
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_BASE));
         } else {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_RESOLVE));
             // =================== resolve role ===================
+            const bool prof = d.prof != nullptr && blockIdx.x == 0 && rt == 0;
+            long long tp = clock64();
+#define QPROF(k) do { if (prof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
             int first = 0, b = 0;
             while (first < T) {
                 pipe_stage_trees(sm, d, d.trees[par], first, rw, lane);     // while the pass still streams batch b
                 named_sync(BAR_H1 + (b & 1), PIPE_THREADS);                  // H1(b)
+                QPROF(10);
                 const PipePlan& P = sm.plan[b & 1];
                 tbatch[b & 1] += gridDim.x;
                 if (rt == 0) {
@@ -540,10 +561,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                         if (clock64() - t0 > 8000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); __trap(); }
                 }
                 named_sync(BAR_RES, PR_THREADS);
+                QPROF(11);
                 pipe_resolve(sm, P, b, d, sc, d.trees[par ^ 1], totals, cross, rt);
                 named_arrive(BAR_H2 + (b & 1), PIPE_THREADS);                // H2(b)
+                QPROF(12);
                 first += P.nb; ++b;
             }
+#undef QPROF
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_BASE));
         }
         __syncthreads();
         // ---- epilogue: moments of (y, Gc, Gm) ----

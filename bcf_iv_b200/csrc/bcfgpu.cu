@@ -618,7 +618,7 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
         long long pc[16];
         CK(cudaMemcpy(pc, d.prof, 128, cudaMemcpyDeviceToHost));
         CK(cudaMemset(d.prof, 0, 128));
-        const char* nm[8] = {"tiles", "flush", "barrier", "decide", "store", "load+propose", "epilogue", "-"};
+        const char* nm[8] = {"tiles", "flush", "barrier", "decide", "store", "load+propose", "epilogue", "-"};   // k_pipe: stats, flush, wait H2, apply, -, plan
         long long tot = 0; for (int k = 0; k < 7; ++k) tot += pc[k];
         fprintf(stderr, "[bcfgpu profile] %d sweeps:", total);
         for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.1f%%(%.0f cyc/tree)", nm[k], 100.0 * pc[k] / (double)std::max(tot, 1ll), (double)pc[k] / ((double)total * h->T));
