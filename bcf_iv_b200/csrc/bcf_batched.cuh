@@ -55,6 +55,7 @@ struct __align__(16) ApplyTab {
     int32_t changed[NB], off[NB];
     ApRow T[2][APCAP];                    // control / treated rows: one 16-byte load per observation and tree
     int4 DL[NB * KB][2];                  // the three 21-bit limbs of T[g][row].dr (batched trees): what resolve multiplies
+    long long TL[NB][2][4];               // per tree and group: sum over its keys of D * count = what the total of R loses (limbs)
     uint8_t NS[APCAP];                    // leaf slot after the move
 };
 
@@ -158,11 +159,12 @@ __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t e0, uint32_t e1)
 // the loads of the next tree are in flight while this one is processed.
 __device__ __forceinline__ void keys_load(const Dev& d, const CurInfo& ci, int tree, int64_t gb, uint2& sl, uint4& bn)
 {
-    sl = *reinterpret_cast<const uint2*>(d.slots + (int64_t)tree * d.n_pad + gb);
+    // streamed once per sweep: keep them out of L1 (L2 only), which then holds the few register spills of the kernel
+    sl = __ldcg(reinterpret_cast<const uint2*>(d.slots + (int64_t)tree * d.n_pad + gb));
     if (ci.birth) {
-        if (ci.is16) bn = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ci.bins) + gb);
+        if (ci.is16) bn = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ci.bins) + gb));
         else {
-            const uint2 b = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(ci.bins) + gb);
+            const uint2 b = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(ci.bins) + gb));
             bn.x = b.x; bn.y = b.y;
         }
     }
@@ -476,6 +478,7 @@ struct ChainPrev {                       // the previous batch, when its update 
     const int16_t (*xoff)[NB];           // xoff[q][m]: first cross cell of (previous tree m, this batch's tree q)
     const int4 (*DL)[2];
     const int32_t (*cq)[KB][2];
+    const long long (*TL)[2][4];         // TL[m][g][limb]: total loss of previous tree m
 };
 template <class RS, class AP>
 __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, SmallStage* st, const int32_t* Kq,
@@ -590,7 +593,53 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
             }
         };
         // the previous batch (pipelined engine): decided long ago, its update is simply not in the statistics yet
-        if (active) for (int m = 0; m < pv.n; ++m) fold(&pv.DL[m * KB], pv.K[m], pv.xoff[q][m], pv.cq[m], 0);
+        // All of that batch's D rows are known, so the whole warp works on it: lane = key (l & 7) x quarter of the
+        // previous trees (l >> 3); key 0 takes each tree's TOTAL loss and hands back what the other keys took.
+        if (pv.n > 0) {
+            const int jg = l >> 3, ll = l & 7;
+            const int cc0 = __shfl_sync(FULL, c0, ll), cc1 = __shfl_sync(FULL, c1, ll);
+            long long a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+            if (active && ll < K) {
+                const int stride = K - 1;
+                for (int m = jg; m < pv.n; m += 4) {
+                    const int Km = pv.K[m];
+                    const int4 (*DLm)[2] = &pv.DL[m * KB];
+                    if (ll >= 1) {
+                        const int xb = pv.xoff[q][m] + (ll - 1);
+                        int nz0 = cc0, nz1 = cc1;
+                        for (int kp = 1; kp < Km; ++kp) {
+                            const int x0 = (int)rs.x[xb + (kp - 1) * stride][0], x1 = (int)rs.x[xb + (kp - 1) * stride][1];
+                            const int4 r0 = DLm[kp][0], r1 = DLm[kp][1];
+                            nz0 -= x0; nz1 -= x1;
+                            a0 += (long long)r0.x * x0; a1 += (long long)r0.y * x0; a2 += (long long)r0.z * x0;
+                            b0 += (long long)r1.x * x1; b1 += (long long)r1.y * x1; b2 += (long long)r1.z * x1;
+                        }
+                        const int4 z0 = DLm[0][0], z1 = DLm[0][1];
+                        a0 += (long long)z0.x * nz0; a1 += (long long)z0.y * nz0; a2 += (long long)z0.z * nz0;
+                        b0 += (long long)z1.x * nz1; b1 += (long long)z1.y * nz1; b2 += (long long)z1.z * nz1;
+                    } else {
+                        a0 += pv.TL[m][0][0]; a1 += pv.TL[m][0][1]; a2 += pv.TL[m][0][2];
+                        b0 += pv.TL[m][1][0]; b1 += pv.TL[m][1][1]; b2 += pv.TL[m][1][2];
+                    }
+                }
+            }
+#pragma unroll
+            for (int sft = 8; sft <= 16; sft <<= 1) {   // the four quarters
+                a0 += __shfl_xor_sync(FULL, a0, sft); a1 += __shfl_xor_sync(FULL, a1, sft); a2 += __shfl_xor_sync(FULL, a2, sft);
+                b0 += __shfl_xor_sync(FULL, b0, sft); b1 += __shfl_xor_sync(FULL, b1, sft); b2 += __shfl_xor_sync(FULL, b2, sft);
+            }
+            long long s0 = ll >= 1 ? a0 : 0, s1_ = ll >= 1 ? a1 : 0, s2_ = ll >= 1 ? a2 : 0;
+            long long u0 = ll >= 1 ? b0 : 0, u1 = ll >= 1 ? b1 : 0, u2 = ll >= 1 ? b2 : 0;
+#pragma unroll
+            for (int sft = 1; sft <= 4; sft <<= 1) {    // what the keys >= 1 took, over the 8 key lanes
+                s0 += __shfl_xor_sync(FULL, s0, sft); s1_ += __shfl_xor_sync(FULL, s1_, sft); s2_ += __shfl_xor_sync(FULL, s2_, sft);
+                u0 += __shfl_xor_sync(FULL, u0, sft); u1 += __shfl_xor_sync(FULL, u1, sft); u2 += __shfl_xor_sync(FULL, u2, sft);
+            }
+            if (active && l < K) {
+                if (l >= 1) { wa0 -= a0; wa1 -= a1; wa2 -= a2; wb0 -= b0; wb1 -= b1; wb2 -= b2; }
+                else { wa0 -= a0 - s0; wa1 -= a1 - s1_; wa2 -= a2 - s2_; wb0 -= b0 - u0; wb1 -= b1 - u1; wb2 -= b2 - u2; }
+            }
+        }
         const bool cprof = d.prof != nullptr && blockIdx.x == 0 && l == 0;
         long long ct = 0;
 #define CPROF(k) do { if (cprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[8 + (k)], (unsigned long long)(now_ - ct)); ct = now_; } } while (0)
@@ -700,6 +749,23 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
                 if (l < K) { tr.mu[ns] = mnew; tr.cnt1[ns] = (int32_t)n1; tr.cnt0[ns] = (int32_t)n0; }   // keys of one new leaf agree
                 __syncwarp();
                 if (writer) store_small(&newtrees[tree], tr, l);
+                {   // what the total of R loses to this tree, for the next batch's key 0 (pipelined engine)
+                    long long t0 = 0, t1 = 0, t2 = 0, v0 = 0, v1 = 0, v2 = 0;
+                    if (l < K) {
+                        const int4 r0 = ap.DL[off + l][0], r1 = ap.DL[off + l][1];
+                        t0 = (long long)r0.x * c0; t1 = (long long)r0.y * c0; t2 = (long long)r0.z * c0;
+                        v0 = (long long)r1.x * c1; v1 = (long long)r1.y * c1; v2 = (long long)r1.z * c1;
+                    }
+#pragma unroll
+                    for (int sft = 1; sft <= 4; sft <<= 1) {
+                        t0 += __shfl_xor_sync(FULL, t0, sft); t1 += __shfl_xor_sync(FULL, t1, sft); t2 += __shfl_xor_sync(FULL, t2, sft);
+                        v0 += __shfl_xor_sync(FULL, v0, sft); v1 += __shfl_xor_sync(FULL, v1, sft); v2 += __shfl_xor_sync(FULL, v2, sft);
+                    }
+                    if (l == 0) {
+                        ap.TL[q][0][0] = t0; ap.TL[q][0][1] = t1; ap.TL[q][0][2] = t2;
+                        ap.TL[q][1][0] = v0; ap.TL[q][1][1] = v1; ap.TL[q][1][2] = v2;
+                    }
+                }
             } else if (active && q > m) {
                 fold(&ap.DL[m * KB], Kq[m], xoff[q][m], cq[m], 1 + m);
                 if (q == m + 1) CPROF(7);
@@ -792,7 +858,7 @@ __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d,
     // then does the bookkeeping nobody waits for (tree record, slot map, trace, HBM write-back).
     if ((t >> 5) < NB) {
         ChainConsts cc{s1, s0, rs1, rs0, phi1, phi0, log_tau};
-        ChainPrev pv{0, nullptr, nullptr, nullptr, nullptr};
+        ChainPrev pv{0, nullptr, nullptr, nullptr, nullptr, nullptr};
         decision_chain(t >> 5, t & 31, nb, B.first, B.st, B.K, B.xoff, rs, sm.ap, sm.cq, pre, cc, pv, d, newtrees, &sm.bad);
     }
     __syncthreads();

@@ -48,6 +48,7 @@ struct PipePlan {
     int32_t ncell_w, ncell, ncol, ncolp;
     int32_t K[NB], Kp[NB];
     uint8_t colbase[NB], colbasep[NB];
+    int16_t cbase[NB], cbasep[NB];                   // first cell of tree q: inside the batch / against the previous batch
     int16_t xoff[NB][NB];                            // [q][m < q]       cells inside the batch
     int16_t xoffp[NB][NB];                           // [q][m in prev]   cells against the previous batch
     uint8_t cell_c1[PXCAP], cell_c2[PXCAP];          // columns of a cell: 0.. this batch, PMAXC.. previous batch
@@ -59,6 +60,7 @@ struct __align__(16) PipeApply {
     int32_t changed[NB], off[NB];
     ApRow T[2][NB * KB];
     int4 DL[NB * KB][2];
+    long long TL[NB][2][4];
     uint8_t NS[NB * KB];
 };
 struct PipeRS { long long tot[NB][KB][2][4]; int x[PXCAP][2]; };
@@ -96,55 +98,75 @@ struct PipePtrs { uint32_t R, G, keys; };            // keys: [tile][parity][pai
 // ---------------------------------------------------------------------------------------------------------------
 // pass role
 // ---------------------------------------------------------------------------------------------------------------
-// plan of the batch starting at `first` (thread 0 of the pass role), then the cell -> column lists in parallel
+// Plan of the batch starting at `first`, by the pass role.  Cell layout (closed form, so nothing is enumerated
+// serially): tree q owns the cells  base_q + (K_q - 1) * c1 + (k - 1)  for every EARLIER column c1 of the batch
+// (c1 < colbase[q]) and, behind all of those, the cells against the previous batch's columns; hence
+//     xoff[q][m]  = base_q  + (K_q - 1) * colbase[m],        xoffp[q][m] = basep_q + (K_q - 1) * colbasep[m].
 __device__ inline void pipe_plan(PipeSmem& sm, PipePlan& P, const PipePlan* prev, const Dev& d, const TMeta* meta, int first, int pt)
 {
-    if (pt == 0) {
+    if (pt < 32) {
+        const unsigned FULL = 0xffffffffu;
+        const int l = pt;
         const int f = (d.f[1].ntree > 0 && first >= d.f[1].tree0) ? 1 : 0;
         const int fend = f ? d.T : (d.f[1].ntree > 0 ? d.f[1].tree0 : d.T);
         const int ncand = min(NB, fend - first);
-        int nb = 0, cells = 0, cols = 0;
-        for (int q = 0; q < ncand; ++q) {
-            const TMeta m = meta[first + q];
-            const int K = m.K;
-            if (cols + K - 1 > PMAXC) break;
-            P.colbase[q] = (uint8_t)cols;
-            for (int mm = 0; mm < q; ++mm) { P.xoff[q][mm] = (int16_t)cells; cells += (P.K[mm] - 1) * (K - 1); }
-            cols += K - 1;
-            P.K[q] = K;
-            CurInfo& ci = P.ci[q];
-            ci.active = 1; ci.K = K; ci.birth = m.birth; ci.sx = m.sx; ci.cut = m.cut; ci.bins = m.bins; ci.is16 = m.is16;
+        TMeta m;
+        m.K = 1; m.L = 1; m.birth = 0; m.sx = 0; m.cut = 0; m.is16 = 0; m.pad_ = 0; m.bins = nullptr;
+        if (l < ncand) m = meta[first + l];
+        const int c = (l < ncand) ? (int)m.K - 1 : 0;            // own columns
+        int cb = c;                                                 // inclusive prefix of the columns
+#pragma unroll
+        for (int sft = 1; sft < NB; sft <<= 1) { const int v = __shfl_up_sync(FULL, cb, sft); if (l >= sft) cb += v; }
+        const int colbase = cb - c;
+        const unsigned okm = __ballot_sync(FULL, l < ncand && cb <= PMAXC);
+        const int nb = __ffs(~okm) - 1;                             // leading trees whose columns still fit
+        const bool in = l < nb;
+        const int wcells = in ? c * colbase : 0;                    // cells against earlier columns of this batch
+        int wb = wcells;
+#pragma unroll
+        for (int sft = 1; sft < NB; sft <<= 1) { const int v = __shfl_up_sync(FULL, wb, sft); if (l >= sft) wb += v; }
+        const int base = wb - wcells;
+        const int ncell_w = __shfl_sync(FULL, wb, NB - 1);
+        const int ncol = __shfl_sync(FULL, in ? cb : 0, max(nb - 1, 0));
+        const int np = prev ? prev->nb : 0, ncolp = prev ? prev->ncol : 0;
+        const int xcells = in ? c * ncolp : 0;                      // cells against the previous batch's columns
+        int xb = xcells;
+#pragma unroll
+        for (int sft = 1; sft < NB; sft <<= 1) { const int v = __shfl_up_sync(FULL, xb, sft); if (l >= sft) xb += v; }
+        const int basep = ncell_w + xb - xcells;
+        const int ncell = ncell_w + __shfl_sync(FULL, xb, NB - 1);
+        if (l < NB) {
+            P.K[l] = in ? (int)m.K : 1;
+            P.colbase[l] = (uint8_t)colbase;
+            P.cbase[l] = (int16_t)base; P.cbasep[l] = (int16_t)basep;
+            P.Kp[l] = (l < np) ? prev->K[l] : 1;
+            P.colbasep[l] = (l < np) ? prev->colbase[l] : 0;
+            CurInfo& ci = P.ci[l];
+            ci.active = 1; ci.K = m.K; ci.birth = m.birth; ci.sx = m.sx; ci.cut = m.cut; ci.bins = m.bins; ci.is16 = m.is16;
             ci.forest = f; ci.new_slot = m.L;
-            nb = q + 1;
         }
-        P.first = first; P.nb = nb; P.forest = f; P.ncol = cols; P.ncell_w = cells;
-        const int np = prev ? prev->nb : 0;
-        P.nprev = np; P.ncolp = prev ? prev->ncol : 0;
-        for (int mm = 0; mm < np; ++mm) { P.Kp[mm] = prev->K[mm]; P.colbasep[mm] = prev->colbase[mm]; }
-        for (int q = 0; q < nb; ++q)
-            for (int mm = 0; mm < np; ++mm) { P.xoffp[q][mm] = (int16_t)cells; cells += (P.Kp[mm] - 1) * (P.K[q] - 1); }
-        P.ncell = cells;
+        if (l == 0) {
+            P.first = first; P.nb = nb; P.forest = f; P.ncol = ncol; P.ncell_w = ncell_w; P.nprev = np; P.ncolp = ncolp;
+            P.ncell = ncell;
+        }
     }
     named_sync(BAR_PASS, PP_THREADS);
-    for (int i = pt; i < 2 * NB * NB * (KB - 1) * (KB - 1); i += PP_THREADS) {
-        const int k = 1 + i % (KB - 1), kp = 1 + (i / (KB - 1)) % (KB - 1);
-        const int m = (i / ((KB - 1) * (KB - 1))) % NB, q = (i / ((KB - 1) * (KB - 1) * NB)) % NB;
-        const int cross = i / ((KB - 1) * (KB - 1) * NB * NB);
-        if (q >= P.nb || k >= P.K[q]) continue;
-        if (!cross) {
-            if (m < q && kp < P.K[m]) {
-                const int cell = P.xoff[q][m] + (kp - 1) * (P.K[q] - 1) + (k - 1);
-                P.cell_c1[cell] = (uint8_t)(P.colbase[m] + kp - 1);
-                P.cell_c2[cell] = (uint8_t)(P.colbase[q] + k - 1);
-            }
-        } else if (m < P.nprev && kp < P.Kp[m]) {
-            const int cell = P.xoffp[q][m] + (kp - 1) * (P.K[q] - 1) + (k - 1);
-            P.cell_c1[cell] = (uint8_t)(PMAXC + P.colbasep[m] + kp - 1);
-            P.cell_c2[cell] = (uint8_t)(P.colbase[q] + k - 1);
+    {   // offsets of every pair and the two columns of every cell, from the closed form
+        if (pt < NB * NB) {
+            const int q = pt / NB, m = pt % NB;
+            P.xoff[q][m] = (int16_t)(P.cbase[q] + (P.K[q] - 1) * (int)P.colbase[m]);
+            P.xoffp[q][m] = (int16_t)(P.cbasep[q] + (P.K[q] - 1) * (int)P.colbasep[m]);
         }
-    }
-    // clear the pass tables of this batch
-    {
+        const int nb = P.nb, ncw = P.ncell_w, nc = P.ncell;
+        for (int cell = pt; cell < nc; cell += PP_THREADS) {
+            const bool cross = cell >= ncw;
+            int q = 0;
+            for (int qq = 1; qq < nb; ++qq) if (cell >= (cross ? P.cbasep[qq] : P.cbase[qq])) q = qq;
+            const int j = cell - (cross ? P.cbasep[q] : P.cbase[q]), w = P.K[q] - 1;
+            P.cell_c1[cell] = (uint8_t)((cross ? PMAXC : 0) + j / w);
+            P.cell_c2[cell] = (uint8_t)(P.colbase[q] + j % w);
+        }
+        // clear the pass tables of this batch
         unsigned int* tb = reinterpret_cast<unsigned int*>(&sm.p.acc);
         const int nw = (int)(offsetof(PipeAcc, xtab) / 4) + 2 * PXCAP;
         for (int i = pt; i < nw; i += PP_THREADS) tb[i] = 0u;
@@ -336,6 +358,9 @@ __device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, cons
     const int nb = P.nb;
     const ForestDev& F = d.f[P.forest];
     PipeRS& rs = sm.rs;
+    const bool rprof = d.prof != nullptr && blockIdx.x == 0 && rt == 0;
+    long long rtp = clock64();
+#define RPROF(k) do { if (rprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - rtp)); rtp = now_; } } while (0)
     for (int i = rt; i < nb * KB * 8; i += PR_THREADS) {
         const int q = i / (KB * 8), k = (i >> 3) & (KB - 1);
         if (k < P.K[q]) (&rs.tot[0][0][0][0])[i] = __ldcg(&totals[(size_t)(P.first + q) * KEYS * 8 + (i & (KB * 8 - 1))]);
@@ -345,6 +370,7 @@ __device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, cons
         for (int i = rt; i < 2 * P.ncell; i += PR_THREADS) (&rs.x[0][0])[i] = (int)__ldcg(xg + i);
     }
     named_sync(BAR_RES, PR_THREADS);
+    RPROF(8);
     const bool is_con = F.is_con != 0;
     const double s1 = is_con ? sc.mscale : sc.bscale1, s0 = is_con ? sc.mscale : sc.bscale0;
     const double tau = is_con ? sc.tau_con : sc.tau_mod;
@@ -376,14 +402,17 @@ __device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, cons
         }
     }
     named_sync(BAR_RES, PR_THREADS);
+    RPROF(9);
     {
         ChainConsts cc{s1, s0, 1.0 / s1, 1.0 / s0, phi1, phi0, log(tau)};
         const PipeApply& app = sm.ap[(b & 1) ^ 1];
-        ChainPrev pv{P.nprev, P.Kp, P.xoffp, app.DL, sm.cq[(b & 1) ^ 1]};
+        ChainPrev pv{P.nprev, P.Kp, P.xoffp, app.DL, sm.cq[(b & 1) ^ 1], app.TL};
         decision_chain(rt >> 5, rt & 31, nb, P.first, sm.st, P.K, P.xoff, rs, sm.ap[b & 1], sm.cq[b & 1], sm.pre, cc, pv, d,
                        newtrees, &sm.bad);
     }
     named_sync(BAR_RES, PR_THREADS);
+    RPROF(14);
+#undef RPROF
     if (rt == 0) { PipeApply& ap = sm.ap[b & 1]; ap.n = nb; ap.first = P.first; ap.forest = P.forest; }
 }
 
@@ -552,7 +581,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
             while (first < T) {
                 pipe_stage_trees(sm, d, d.trees[par], first, rw, lane);     // while the pass still streams batch b
                 named_sync(BAR_H1 + (b & 1), PIPE_THREADS);                  // H1(b)
-                QPROF(10);
+                QPROF(4);
                 const PipePlan& P = sm.plan[b & 1];
                 tbatch[b & 1] += gridDim.x;
                 if (rt == 0) {
@@ -561,10 +590,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                         if (clock64() - t0 > 8000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); __trap(); }
                 }
                 named_sync(BAR_RES, PR_THREADS);
-                QPROF(11);
+                QPROF(6);
                 pipe_resolve(sm, P, b, d, sc, d.trees[par ^ 1], totals, cross, rt);
                 named_arrive(BAR_H2 + (b & 1), PIPE_THREADS);                // H2(b)
-                QPROF(12);
+                QPROF(7);
                 first += P.nb; ++b;
             }
 #undef QPROF

@@ -220,7 +220,7 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (e2 != cudaSuccess) { delete h; return fail(BCFGPU_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e2)); }
     if (cfg->engine < BCFGPU_ENGINE_AUTO || cfg->engine > BCFGPU_ENGINE_PIPELINED) { delete h; return fail(BCFGPU_ERR_BAD_ARG, "unknown engine"); }
-    h->engine = cfg->engine == BCFGPU_ENGINE_AUTO ? BCFGPU_ENGINE_BATCHED : cfg->engine;
+    h->engine = cfg->engine == BCFGPU_ENGINE_AUTO ? BCFGPU_ENGINE_PIPELINED : cfg->engine;
     *out = h;
     return BCFGPU_OK;
 }
@@ -621,7 +621,7 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
         const char* nm[8] = {"tiles", "flush", "barrier", "decide", "store", "load+propose", "epilogue", "-"};   // k_pipe: stats, flush, wait H2, apply, -, plan
         long long tot = 0; for (int k = 0; k < 7; ++k) tot += pc[k];
         fprintf(stderr, "[bcfgpu profile] %d sweeps:", total);
-        for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.1f%%(%.0f cyc/tree)", nm[k], 100.0 * pc[k] / (double)std::max(tot, 1ll), (double)pc[k] / ((double)total * h->T));
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%.1f%%(%.0f cyc/tree)", nm[k], 100.0 * pc[k] / (double)std::max(tot, 1ll), (double)pc[k] / ((double)total * h->T));
         fprintf(stderr, "\n");
         bool any = false; for (int k = 8; k < 16; ++k) any |= pc[k] != 0;
         if (any) {
@@ -1110,10 +1110,11 @@ static int run_persistent(bcfgpu_handle* h, int total)
             else if (h->cfg.engine == BCFGPU_ENGINE_BATCHED || h->cfg.engine == BCFGPU_ENGINE_PIPELINED)
                 return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_BATCHED / PIPELINED: the observations of one SM do not fit in shared memory at this n");
             // the pipelined kernel on top of it (the batched one then serves the sweeps that hold a wide tree)
-            if (h->kernel == 3 && h->cfg.engine == BCFGPU_ENGINE_PIPELINED) {
+            if (h->kernel == 3 && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096) {
                 const size_t needp = PIPE_SMEM_BYTES + (size_t)ntl_max * PIPE_BYTES_PER_TILE + (size_t)h->T * sizeof(TMeta) + 16;
                 if (fits((const void*)k_pipe, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; }
-                else return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_PIPELINED: the observations of one SM do not fit in shared memory at this n");
+                else if (h->cfg.engine == BCFGPU_ENGINE_PIPELINED)
+                    return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_PIPELINED: the observations of one SM do not fit in shared memory at this n");
             }
         }
         if (h->kernel == 0 && may_reside) {

@@ -267,7 +267,7 @@ def run_ours(args):
         host[k], t = pinned_like(a)
         keep.append(t)
 
-    engine = {"auto": 0, "graph": 1, "persistent": 2, "persistent_hbm": 3, "batched": 4}[args.engine]
+    engine = {"auto": 0, "graph": 1, "persistent": 2, "persistent_hbm": 3, "batched": 4, "pipelined": 5}[args.engine]
 
     def make_sampler():
         s = _lib.Sampler(engine=engine, lambda_=w["lambda_"], sigma_init=w["sigma_init"], seed=args.seed,
@@ -340,7 +340,7 @@ def run_ours(args):
     sweeps_per_launch = K / max(launches, 1)
     launch_ms = dev_ms / max(launches, 1)
     achieved = b_sweep * sweeps_per_launch / (launch_ms * 1e-3) / 1e9
-    eng_name = {0: "batched", 1: "graph", 2: "persistent", 3: "persistent_hbm", 4: "batched"}[engine]
+    eng_name = {0: "pipelined", 1: "graph", 2: "persistent", 3: "persistent_hbm", 4: "batched", 5: "pipelined"}[engine]
     traffic_sweep = ncu_traffic_per_sweep(n_local, eng_name)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -353,7 +353,7 @@ def run_ours(args):
                        wall_ms_per_step=wall_ms / K),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic_sweep * sweeps_per_launch if traffic_sweep is not None else None),
-                     "peak_source": peak_src, "kernel": {"batched": "k_batched", "persistent": "k_resident", "persistent_hbm": "k_persistent"}.get(eng_name, eng_name),
+                     "peak_source": peak_src, "kernel": {"pipelined": "k_pipe", "batched": "k_batched", "persistent": "k_resident", "persistent_hbm": "k_persistent"}.get(eng_name, eng_name),
                      "algorithmic_bytes_per_sweep": b_sweep, "sweeps_per_launch": sweeps_per_launch,
                      "launch_ms": launch_ms},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
@@ -386,7 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="chains", choices=["chains", "sharded"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "graph", "persistent", "persistent_hbm", "batched"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "graph", "persistent", "persistent_hbm", "batched", "pipelined"])
     ap.add_argument("--nobs", "--n", dest="n", type=int, default=1_000_000)     # (--n / --p clash with torchrun abbreviations)
     ap.add_argument("--ncov", "--p", dest="p", type=int, default=100)
     ap.add_argument("--burnin", type=int, default=100)

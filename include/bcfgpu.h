@@ -55,11 +55,12 @@ typedef enum bcfgpu_engine {
                                       observation state lives in shared memory when the CTA's share fits */
     BCFGPU_ENGINE_PERSISTENT_HBM = 3, /* same schedule, observation state kept in HBM/L2 (any n) */
     BCFGPU_ENGINE_BATCHED = 4      /* cooperative kernel, up to 8 trees per observation pass and per grid barrier (exact
-                                      integer cross-count correction), state in shared memory; AUTO picks it when the
-                                      observations of an SM fit, else PERSISTENT */
+                                      integer cross-count correction), state in shared memory */
     , BCFGPU_ENGINE_PIPELINED = 5  /* BATCHED with the decisions off the pass's critical path: 16 warps stream the
                                       observations while 8 warps decide the previous batch (cross-batch counts keep it
-                                      exact); sweeps that hold a tree with more than 8 keys fall back to BATCHED */
+                                      exact); sweeps that hold a tree with more than 8 keys fall back to BATCHED.
+                                      AUTO = PIPELINED when the observations of an SM fit in shared memory, else BATCHED,
+                                      else PERSISTENT */
 } bcfgpu_engine;
 
 /* Hyper-parameters of the sampler: bcf()'s arguments after the R wrapper's rescaling. */
