@@ -22,7 +22,7 @@ ENGINE_AUTO, ENGINE_GRAPH, ENGINE_PERSISTENT, ENGINE_PERSISTENT_HBM, ENGINE_BATC
 SYMBOLS = [
     "bcfgpu_abi_version", "bcfgpu_device_count", "bcfgpu_last_error", "bcfgpu_config_init", "bcfgpu_create",
     "bcfgpu_destroy", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_data", "bcfgpu_run",
-    "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
+    "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_engine_in_use", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
     "bcfgpu_get_mu_mean", "bcfgpu_get_yhat_mean", "bcfgpu_get_sigma", "bcfgpu_get_scales", "bcfgpu_get_draws",
     "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
     "bcfgpu_get_tree", "bcfgpu_set_tree", "bcfgpu_get_leaf_ids", "bcfgpu_verify_leaf_cache", "bcfgpu_op_bin_column",
@@ -76,6 +76,7 @@ def load():
     L.bcfgpu_run.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.bcfgpu_last_run_ms.argtypes = [vp, dp]
     L.bcfgpu_kernel_launches.argtypes = [vp, lp]
+    L.bcfgpu_engine_in_use.argtypes = [vp, ip]
     L.bcfgpu_num_saved.argtypes = [vp, ip]
     for nm in ("tau_mean", "tau_var", "mu_mean", "yhat_mean", "sigma"):
         getattr(L, "bcfgpu_get_" + nm).argtypes = [vp, dp]
@@ -214,6 +215,14 @@ class Sampler:
         v = C.c_int64()
         check(load().bcfgpu_kernel_launches(self._h, C.byref(v)))
         return v.value
+
+    @property
+    def engine_in_use(self):
+        """(sweep kernel, shard exchange) of the last run: kernel 0 graph, 1 k_persistent, 2 k_resident, 3 k_batched,
+        4 k_pipe; exchange 0 none, 1 ncclAllReduce per tree, 2 in-kernel peer-memory mailboxes"""
+        o = np.zeros(2, dtype=np.int32)
+        check(load().bcfgpu_engine_in_use(self._h, _ip(o)))
+        return int(o[0]), int(o[1])
 
     @property
     def num_saved(self):

@@ -98,6 +98,7 @@ struct BatchSmem {
         double red[2 * PTHREADS];
     } p;
     int32_t cq[NB][KB][2];                // pre-decision counts per (tree of the batch, key, group)
+    long long momsum[MAIL_MOM_WORDS];     // sharded mode: the sweep's moments summed over the shards
 };
 // what depends only on COUNTS (known before the batch's decisions): precision terms of every key and pooled pair
 struct PreKey { double k1, k0, inv, plog, psd, pad_; };
@@ -777,12 +778,45 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
 #undef CPROF
 }
 
+// Observation shards: CTA 0 stores this rank's reduced words of the batch into its mailbox on every peer and releases
+// sequence number `seq` there (see PeerDev).  Layout: totals words packed (tree q, word w) -> q * KB * 8 + w (a big
+// tree: its K * 8 words), then the cross counts from MAIL_TOT_WORDS on.
+__device__ inline void peer_push_batch(const BatchStage& B, const Dev& d, const long long* totals, const long long* cross,
+                                       int slot, unsigned long long seq)
+{
+    const int t = threadIdx.x;
+    const int nt = B.big ? B.K[0] * 8 : B.nb * KB * 8, nx = B.big ? 0 : 2 * B.ncell;
+    for (int i = t; i < nt + nx; i += blockDim.x) {
+        long long v;
+        int dst;
+        if (i < nt) {
+            v = __ldcg(&totals[B.big ? (size_t)B.first * KEYS * 8 + i : (size_t)(B.first + i / (KB * 8)) * KEYS * 8 + (i & (KB * 8 - 1))]);
+            dst = i;
+        } else {
+            v = __ldcg(&cross[(size_t)B.first * (XCAP * 2) + (i - nt)]);
+            dst = MAIL_TOT_WORDS + (i - nt);
+        }
+        for (int p = 0; p < d.pr.nranks; ++p)
+            if (p != d.pr.rank) d.pr.peer[p][d.pr.rank].batch[slot][dst] = v;
+    }
+    peer_release(d, slot, seq);
+}
+// sum of the peers' words (fixed order; integers, so any order gives the same bits)
+__device__ __forceinline__ long long peer_sum(const Dev& d, int slot, int idx)
+{
+    long long v = 0;
+    for (int p = 0; p < d.pr.nranks; ++p)
+        if (p != d.pr.rank) v += __ldcg(&d.pr.mine[p].batch[slot][idx]);
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // After the grid barrier: replay the batch's decisions in tree order from the reduced integers.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d, const Scalars& sc, TreeRec* newtrees,
-                                     const long long* totals, const long long* cross)
+                                     const long long* totals, const long long* cross, int slot)
 {
+    const bool sharded = d.pr.nranks > 1;
     const int t = threadIdx.x;
     const ForestDev& F = d.f[B.forest];
     if (B.big) {
@@ -790,7 +824,7 @@ __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d,
         const bool writer = ((int)blockIdx.x == tree % (int)gridDim.x);
         const int L = sm.big.tr.nleaves, K = B.K[0];
         const long long* q = totals + (size_t)tree * KEYS * 8;
-        for (int i = t; i < K * 8; i += blockDim.x) sm.tot[i] = __ldcg(q + i);
+        for (int i = t; i < K * 8; i += blockDim.x) sm.tot[i] = __ldcg(q + i) + (sharded ? peer_sum(d, slot, i) : 0ll);
         decide_core(sm, sm.big, d, F, tree, sc, writer);
         fill_apply(sm, sm.big, 0, 0, L, K);
         if (t == 0) { sm.ap.n = 1; sm.ap.first = tree; sm.ap.forest = B.forest; }
@@ -806,11 +840,11 @@ __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d,
     ResolveTab& rs = sm.p.rs;
     for (int i = t; i < nb * KB * 8; i += blockDim.x) {
         const int q = i / (KB * 8), k = (i >> 3) & (KB - 1);
-        if (k < B.K[q]) (&rs.tot[0][0][0][0])[i] = __ldcg(&totals[(size_t)(B.first + q) * KEYS * 8 + (i & (KB * 8 - 1))]);
+        if (k < B.K[q]) (&rs.tot[0][0][0][0])[i] = __ldcg(&totals[(size_t)(B.first + q) * KEYS * 8 + (i & (KB * 8 - 1))]) + (sharded ? peer_sum(d, slot, i) : 0ll);
     }
     {
         const long long* xg = cross + (size_t)B.first * (XCAP * 2);
-        for (int i = t; i < 2 * B.ncell; i += blockDim.x) (&rs.x[0][0])[i] = __ldcg(xg + i);
+        for (int i = t; i < 2 * B.ncell; i += blockDim.x) (&rs.x[0][0])[i] = __ldcg(xg + i) + (sharded ? peer_sum(d, slot, MAIL_TOT_WORDS + i) : 0ll);
     }
     __syncthreads();
     RPROF(0);
@@ -899,6 +933,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
     const bool writer0 = (blockIdx.x == 0);
     const int lane = t & 31, wib = t >> 5, wpb = blockDim.x >> 5;
     unsigned int target = 0;
+    unsigned long long bev = 0, mev = 0;   // batch / moments exchanges of this launch (sharded mode)
     int bad = 0;
     BCF_PROF_DECL
     BatPtrs rs;
@@ -962,8 +997,13 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
             if (first + nb < T) stage_batch(sm, Bn, d, d.trees[par], first + nb);   // while the barrier is in flight
             PROF(5);
             if (!grid_wait(bar, target, d.err, &bar_ok)) return;
+            if (d.pr.nranks > 1) {   // observation shards: swap the batch's words with the peers
+                ++bev;
+                if (blockIdx.x == 0) peer_push_batch(B, d, totals, cross, (int)(bev & 1u), d.pr.seq0 + bev);
+                if (!peer_wait(d, (int)(bev & 1u), d.pr.seq0 + bev, &bar_ok)) return;
+            }
             PROF(2);
-            resolve_batch(sm, B, d, sc, d.trees[par ^ 1], totals, cross);
+            resolve_batch(sm, B, d, sc, d.trees[par ^ 1], totals, cross, (int)(bev & 1u));
             PROF(3);
             first += nb; ++bi;
             if (first < T) {
@@ -1009,7 +1049,27 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
         }
         grid_arrive(bar, target);
         if (!grid_wait(bar, target, d.err, &bar_ok)) return;
-        sweep_scalars(d, d.trees[par ^ 1], mom, sm.p.red, &scs, writer0);
+        if (d.pr.nranks > 1) {   // the sweep's moments, summed over the shards
+            ++mev;
+            if (blockIdx.x == 0) {
+                for (int i = t; i < MAIL_MOM_WORDS; i += blockDim.x) {
+                    const long long v = __ldcg(&mom[i]);
+                    for (int p = 0; p < d.pr.nranks; ++p)
+                        if (p != d.pr.rank) d.pr.peer[p][d.pr.rank].mom[i] = v;
+                }
+                peer_release(d, 2, d.pr.seq0 + mev);
+            }
+            if (!peer_wait(d, 2, d.pr.seq0 + mev, &bar_ok)) return;
+            for (int i = t; i < MAIL_MOM_WORDS; i += blockDim.x) {
+                long long v = __ldcg(&mom[i]);
+                for (int p = 0; p < d.pr.nranks; ++p)
+                    if (p != d.pr.rank) v += __ldcg(&d.pr.mine[p].mom[i]);
+                sm.momsum[i] = v;
+            }
+            __syncthreads();
+            sweep_scalars(d, d.trees[par ^ 1], sm.momsum, sm.p.red, &scs, writer0, true);
+        } else
+            sweep_scalars(d, d.trees[par ^ 1], mom, sm.p.red, &scs, writer0);
         if (sw + 1 < nsweeps) propose_all_b(sm, d, d.trees[par ^ 1], sc.sweep + 1u);   // every tree record is visible now
         grid_arrive(bar, target);   // the proposals must be visible before the next sweep stages them (wait: below)
         // ---- finishing pass: posterior accumulation, residual re-derived with the new scales, back to the mu forest ----

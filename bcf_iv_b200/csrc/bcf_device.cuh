@@ -92,7 +92,31 @@ struct ForestDev {
     double pg[32];             // alpha / (1+depth)^beta, tabulated on the host (bit-identical pow)
 };
 
+// ---------------------------------------------------------------------------------------------
+// Observation shards over several GPUs: the per-batch leaf statistics are exchanged INSIDE the sweep
+// kernel through peer memory (NVLink / NVSwitch): every rank owns one Mailbox per source rank in its own HBM; after
+// its local grid barrier a rank stores its batch words into its mailbox on every peer and then releases a sequence
+// number; a rank proceeds once all its mailboxes carry the sequence number it expects, and sums the (integer) words in
+// a fixed order.  Two batch slots are enough: a rank cannot be two batches ahead of a peer whose words it needs.
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_RANKS = 8;
+constexpr int MAIL_TOT_WORDS = KEYS * 8;            // totals words of a batch (a big tree: KEYS * 8; 8 small trees: 512)
+constexpr int MAIL_X_WORDS = 256;                   // cross-count words of a batch
+constexpr int MAIL_MOM_WORDS = 2 * NMOM * 3;
+struct __align__(16) Mailbox {
+    unsigned long long flag[4];                     // [0], [1]: batch slots, [2]: moments -- sequence number of the last complete push
+    long long batch[2][MAIL_TOT_WORDS + MAIL_X_WORDS];
+    long long mom[MAIL_MOM_WORDS + 4];
+};
+struct PeerDev {
+    int32_t rank, nranks;
+    unsigned long long seq0;                        // launch id << 32: sequence numbers never repeat across launches
+    Mailbox* mine;                                  // [nranks] my mailboxes, indexed by SOURCE rank (local HBM)
+    Mailbox* peer[MAX_RANKS];                       // peer[p]: rank p's mailbox array, mapped here (cudaIpc)
+};
+
 struct Dev {
+    PeerDev pr;
     int64_t n_pad;             // padded local observations (multiple of TILE)
     int64_t n_global;          // real observations over all shards (chi-square degrees of freedom)
     int32_t n_tiles, trt_tiles;  // tiles [0, trt_tiles) are treated, the rest control

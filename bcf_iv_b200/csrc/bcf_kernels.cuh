@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(THREADS) k_sweep_end(Dev d, int prev)
 // sweep counter, flips the tree parity and decides whether this sweep is saved.
 // ---------------------------------------------------------------------------------------------
 // `scs` is the CTA's shared copy of the scalars (identical in every CTA); thread 0 updates it in place.
+// mom_plain: `mom` is a CTA-local (shared memory) copy already summed over the shards -> plain loads
 __device__ inline void sweep_scalars(const Dev& d, const TreeRec* newtrees, const long long* mom, double* red /* >= 2*blockDim */,
-                                     Scalars* scs, bool write_global)
+                                     Scalars* scs, bool write_global, bool mom_plain = false)
 {
     const int t = threadIdx.x;
     // sum of mu^2 and leaf count over the mu trees, deterministic (fixed partition, fixed order)
@@ -190,7 +191,7 @@ __device__ inline void sweep_scalars(const Dev& d, const TreeRec* newtrees, cons
         for (int g = 0; g < 2; ++g)
             for (int m = 0; m < NMOM; ++m) {
                 const long long* q = mom + (g * NMOM + m) * 3;
-                M[g][m] = limbs_to_double(__ldcg(q), __ldcg(q + 1), __ldcg(q + 2));
+                M[g][m] = mom_plain ? limbs_to_double(q[0], q[1], q[2]) : limbs_to_double(__ldcg(q), __ldcg(q + 1), __ldcg(q + 2));
             }
         const double s2 = sc.sigma * sc.sigma;
         double ms = sc.mscale, b1 = sc.bscale1, b0 = sc.bscale0;

@@ -66,6 +66,42 @@ __device__ __forceinline__ bool grid_wait(unsigned int* bar, unsigned int target
     return *ok_smem != 0;
 }
 
+// ---- peer mailboxes (observation shards): see PeerDev ----
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// after this rank's words are in every peer's mailbox (all threads of the pushing CTA, then a __syncthreads)
+__device__ __forceinline__ void peer_release(const Dev& d, int kind, unsigned long long seq)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < d.pr.nranks && (int)threadIdx.x != d.pr.rank)
+        st_release_sys_u64(&d.pr.peer[threadIdx.x][d.pr.rank].flag[kind], seq);
+}
+// every CTA: wait until every peer's words of sequence number `seq` have arrived in this rank's mailboxes
+__device__ __forceinline__ bool peer_wait(const Dev& d, int kind, unsigned long long seq, int* ok_smem)
+{
+    if (threadIdx.x == 0) {
+        int good = 1;
+        const long long t0 = clock64();
+        for (int p = 0; p < d.pr.nranks && good; ++p) {
+            if (p == d.pr.rank) continue;
+            while (ld_acquire_sys_u64(&d.pr.mine[p].flag[kind]) < seq)
+                if (clock64() - t0 > 120000000000ll) { good = 0; atomicOr(d.err, ERR_BARRIER_TIMEOUT); break; }
+        }
+        *ok_smem = good;
+    }
+    __syncthreads();
+    return *ok_smem != 0;
+}
+
 #define BCF_PROF_DECL                                                                                   \
     const bool prof = (d.prof != nullptr) && blockIdx.x == 0 && t == 0;                                 \
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                                                         \

@@ -41,6 +41,7 @@ struct NcclApi {
     int (*GetUniqueId)(NcclId*) = nullptr;
     int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -55,6 +56,7 @@ static int nccl_load()
     g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
@@ -62,7 +64,7 @@ static int nccl_load()
     g_nccl.lib = lib;
     return BCFGPU_OK;
 }
-constexpr int NCCL_INT64 = 4, NCCL_SUM = 0;
+constexpr int NCCL_INT8 = 0, NCCL_INT64 = 4, NCCL_SUM = 0, NCCL_MIN = 3;
 #define NK(call)                                                                                       \
     do {                                                                                               \
         int r_ = (call);                                                                               \
@@ -89,6 +91,12 @@ struct bcfgpu_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int rank = 0, nranks = 1;
     void* comm = nullptr;
+    Mailbox* d_mail = nullptr;        // [nranks] this rank's mailboxes (peer-memory exchange of the sharded mode)
+    Mailbox* peer_mail[MAX_RANKS] = {nullptr};   // the peers' mailbox arrays, mapped with cudaIpc
+    bool peer_ok = false;             // every rank mapped every peer: the sweep kernel exchanges through NVLink itself
+    unsigned long long launch_id = 0;
+    bool shard_decided = false, shard_persistent = false;
+    int last_kernel = 0;
     int64_t n = 0, n_pad = 0, n_global = 0;
     int ntrt = 0, T = 0;
     bool has_data = false;
@@ -233,6 +241,8 @@ int bcfgpu_destroy(bcfgpu_handle* h)
     drop_graph(h);
     free_list(h->allocs);
     free_list(h->run_allocs);
+    for (int p = 0; p < MAX_RANKS; ++p) if (h->peer_mail[p]) cudaIpcCloseMemHandle(h->peer_mail[p]);
+    if (h->d_mail) cudaFree(h->d_mail);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -244,6 +254,42 @@ int bcfgpu_destroy(bcfgpu_handle* h)
 // ------------------------------------------------------------------------------------------------
 // sharding
 // ------------------------------------------------------------------------------------------------
+// Map every peer's mailbox array into this process (cudaIpc over NVLink / NVSwitch).  Collective over the ranks; if any
+// rank cannot map any peer, all ranks agree to keep the NCCL all-reduce path.
+static int setup_peers(bcfgpu_handle* h)
+{
+    h->peer_ok = false;
+    if (h->nranks > MAX_RANKS || !g_nccl.AllGather || getenv("BCFGPU_NO_PEER")) return BCFGPU_OK;
+    CK(cudaMalloc((void**)&h->d_mail, sizeof(Mailbox) * h->nranks));
+    CK(cudaMemset(h->d_mail, 0, sizeof(Mailbox) * h->nranks));
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, h->d_mail));
+    char *d_send = nullptr, *d_recv = nullptr;
+    long long* d_flag = nullptr;
+    CK(cudaMalloc((void**)&d_send, sizeof(mine)));
+    CK(cudaMalloc((void**)&d_recv, sizeof(mine) * h->nranks));
+    CK(cudaMalloc((void**)&d_flag, 8));
+    CK(cudaMemcpy(d_send, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NK(g_nccl.AllGather(d_send, d_recv, sizeof(mine), NCCL_INT8, h->comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)h->nranks);
+    CK(cudaMemcpyAsync(all.data(), d_recv, sizeof(mine) * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    long long ok = 1;
+    for (int p = 0; p < h->nranks && ok; ++p) {
+        if (p == h->rank) continue;
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        else h->peer_mail[p] = (Mailbox*)q;
+    }
+    CK(cudaMemcpy(d_flag, &ok, 8, cudaMemcpyHostToDevice));
+    NK(g_nccl.AllReduce(d_flag, d_flag, 1, NCCL_INT64, NCCL_MIN, h->comm, h->stream));
+    CK(cudaMemcpyAsync(&ok, d_flag, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_send); cudaFree(d_recv); cudaFree(d_flag);
+    h->peer_ok = ok != 0;
+    return BCFGPU_OK;
+}
+
 int bcfgpu_nccl_unique_id(char id_out[128])
 {
     if (!id_out) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
@@ -268,7 +314,7 @@ int bcfgpu_set_shard(bcfgpu_handle* h, int rank, int nranks, const char nccl_uni
     NcclId id;
     memcpy(id.b, nccl_unique_id, 128);
     NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
-    return BCFGPU_OK;
+    return setup_peers(h);
 }
 
 }  // extern "C"
@@ -392,6 +438,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     free_list(h->run_allocs);
     h->has_data = false;
     h->coop_grid = 0;
+    h->shard_decided = false;
     h->n = n;
     int64_t ntrt = 0;
     for (int64_t i = 0; i < n; ++i) ntrt += z[i];
@@ -409,6 +456,8 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     }
     Dev& d = h->dev;
     memset(&d, 0, sizeof(Dev));
+    d.pr.rank = h->rank; d.pr.nranks = h->peer_ok ? h->nranks : 1; d.pr.seq0 = 0; d.pr.mine = h->d_mail;
+    for (int p = 0; p < MAX_RANKS; ++p) d.pr.peer[p] = h->peer_mail[p];
     d.n_pad = n_pad; d.n_tiles = (int32_t)(n_pad / TILE); d.trt_tiles = (int32_t)(trt_pad / TILE);
     d.T = h->T; d.max_leaves = c.max_leaves; d.min_leaf = c.min_leaf;
     d.use_muscale = c.use_muscale; d.use_tauscale = c.use_tauscale;
@@ -549,6 +598,7 @@ static int build_graph(bcfgpu_handle* h)
 }
 
 static int run_persistent(bcfgpu_handle* h, int total);
+static int select_kernel(bcfgpu_handle* h);
 
 static int check_device_err(bcfgpu_handle* h)
 {
@@ -593,11 +643,30 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
     CK(cudaMemcpyAsync(d.sc, &sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
     h->nsaved = 0;
     int rc = BCFGPU_OK;
-    const bool persistent = h->engine != BCFGPU_ENGINE_GRAPH && h->nranks == 1;
+    bool persistent = h->engine != BCFGPU_ENGINE_GRAPH && h->nranks == 1;
+    if (h->nranks > 1 && h->peer_ok && h->engine != BCFGPU_ENGINE_GRAPH) {
+        // observation shards with the in-kernel peer exchange: only the batched kernel has it, and every rank must
+        // take the same path (the shards differ by a row, so "does it fit in shared memory" is agreed on, not assumed)
+        if (!h->shard_decided) {
+            if ((rc = select_kernel(h))) return rc;
+            long long ok = h->kernel == 3 ? 1 : 0;
+            long long* dq = (long long*)h->d_tmp;
+            CK(cudaMemcpyAsync(dq, &ok, 8, cudaMemcpyHostToDevice, h->stream));
+            NK(g_nccl.AllReduce(dq, dq, 1, NCCL_INT64, NCCL_MIN, h->comm, h->stream));
+            CK(cudaMemcpyAsync(&ok, dq, 8, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            h->shard_persistent = ok != 0;
+            h->shard_decided = true;
+            if (!h->shard_persistent) d.pr.nranks = 1;
+        }
+        persistent = h->shard_persistent;
+    }
     if (!persistent && h->nranks == 1) { if ((rc = build_graph(h))) return rc; }
     CK(cudaEventRecord(h->ev0, h->stream));
+    h->last_kernel = 0;
     if (persistent) {
         rc = run_persistent(h, total);
+        h->last_kernel = h->kernel;
     } else if (h->nranks == 1) {
         for (int it = 0; it < total; ++it) CK(cudaGraphLaunch(h->gexec, h->stream));
         h->launches += (int64_t)total * (h->T + 4);
@@ -645,6 +714,13 @@ int bcfgpu_kernel_launches(bcfgpu_handle* h, int64_t* count)
 {
     if (!h || !count) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
     *count = h->launches;
+    return BCFGPU_OK;
+}
+int bcfgpu_engine_in_use(bcfgpu_handle* h, int32_t out2[2])
+{
+    if (!h || !out2) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
+    out2[0] = h->last_kernel;
+    out2[1] = h->nranks <= 1 ? 0 : (h->last_kernel == 0 ? 1 : 2);
     return BCFGPU_OK;
 }
 int bcfgpu_num_saved(bcfgpu_handle* h, int32_t* ns)
@@ -1079,9 +1155,8 @@ int bcfgpu_op_rng_probe(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t 
 // ------------------------------------------------------------------------------------------------
 // PERSISTENT engine launch
 // ------------------------------------------------------------------------------------------------
-static int run_persistent(bcfgpu_handle* h, int total)
+static int select_kernel(bcfgpu_handle* h)
 {
-    if (total <= 0) return BCFGPU_OK;
     if (h->coop_grid == 0) {
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
@@ -1110,7 +1185,7 @@ static int run_persistent(bcfgpu_handle* h, int total)
             else if (h->cfg.engine == BCFGPU_ENGINE_BATCHED || h->cfg.engine == BCFGPU_ENGINE_PIPELINED)
                 return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_BATCHED / PIPELINED: the observations of one SM do not fit in shared memory at this n");
             // the pipelined kernel on top of it (the batched one then serves the sweeps that hold a wide tree)
-            if (h->kernel == 3 && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096) {
+            if (h->kernel == 3 && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && h->nranks == 1) {
                 const size_t needp = PIPE_SMEM_BYTES + (size_t)ntl_max * PIPE_BYTES_PER_TILE + (size_t)h->T * sizeof(TMeta) + 16;
                 if (fits((const void*)k_pipe, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; }
                 else if (h->cfg.engine == BCFGPU_ENGINE_PIPELINED)
@@ -1130,11 +1205,19 @@ static int run_persistent(bcfgpu_handle* h, int total)
         cudaGetLastError();
         h->coop_grid = grid;
     }
+    return BCFGPU_OK;
+}
+
+static int run_persistent(bcfgpu_handle* h, int total)
+{
+    if (total <= 0) return BCFGPU_OK;
+    { int rc = select_kernel(h); if (rc) return rc; }
     // keep launches short enough to stay interruptible (R_CheckUserInterrupt between batches)
     const int batch = 256;
     for (int done = 0; done < total;) {
         int nsw = std::min(batch, total - done);
         Dev d = h->dev;
+        d.pr.seq0 = (++h->launch_id) << 32;
         unsigned int* bar = h->d_bar;
         CK(cudaMemsetAsync(bar, 0, 16, h->stream));
         int ntl = h->res_ntl;

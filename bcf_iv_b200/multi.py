@@ -100,5 +100,6 @@ def run_sharded(sampler_kwargs, y, z, x_con, x_mod, cuts, nburn, nsim, nthin=1, 
     tau = gather_rows(s.tau_mean(), group)
     ms = s.last_run_ms
     scal = s.scalars()
+    scal["engine_in_use"] = s.engine_in_use
     s.close()
     return tau, ms, scal

@@ -307,6 +307,7 @@ def run_ours(args):
     total_launches = int(sum_over_ranks(launches))
     units = K * (1 if sharded else world)       # sweeps of all chains (sharded: one chain over all ranks)
     value = units / (ms * 1e-3)
+    in_use = s.engine_in_use
     sizes = [len(s.get_tree(t)[0]) for t in range(0, T, 5)]
     acc = s.counters()
     sig = s.scalars()["sigma"]
@@ -340,20 +341,21 @@ def run_ours(args):
     sweeps_per_launch = K / max(launches, 1)
     launch_ms = dev_ms / max(launches, 1)
     achieved = b_sweep * sweeps_per_launch / (launch_ms * 1e-3) / 1e9
-    eng_name = {0: "pipelined", 1: "graph", 2: "persistent", 3: "persistent_hbm", 4: "batched", 5: "pipelined"}[engine]
+    eng_name = {0: "graph", 1: "persistent_hbm", 2: "persistent", 3: "batched", 4: "pipelined"}[in_use[0]]
+    exchange = {0: "none", 1: "ncclAllReduce per tree", 2: "in-kernel peer-memory mailboxes (NVLink)"}[in_use[1]]
     traffic_sweep = ncu_traffic_per_sweep(n_local, eng_name)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
         "vs_baseline": None, "dtype": "f64 (fixed-point int64 residual sums, exact)", "data": "synthetic",
-        "config": dict(workload_config(args, world, "B200"), engine=eng_name, burnin_sweeps=args.burnin,
+        "config": dict(workload_config(args, world, "B200"), engine=eng_name, shard_exchange=exchange, burnin_sweeps=args.burnin,
                        l2="no flush: per-sweep working set (250 MB leaf-slot cache + 101 MB bins + 40 MB state) "
                           "exceeds the 126 MB L2",
                        mean_nodes_per_tree=float(np.mean(sizes)), sigma=sig, moves=acc,
                        wall_ms_per_step=wall_ms / K),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic_sweep * sweeps_per_launch if traffic_sweep is not None else None),
-                     "peak_source": peak_src, "kernel": {"pipelined": "k_pipe", "batched": "k_batched", "persistent": "k_resident", "persistent_hbm": "k_persistent"}.get(eng_name, eng_name),
+                     "peak_source": peak_src, "kernel": {"pipelined": "k_pipe", "batched": "k_batched", "persistent": "k_resident", "persistent_hbm": "k_persistent", "graph": "k_tree_step x T (CUDA graph)"}.get(eng_name, eng_name),
                      "algorithmic_bytes_per_sweep": b_sweep, "sweeps_per_launch": sweeps_per_launch,
                      "launch_ms": launch_ms},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,

@@ -73,7 +73,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _shard_worker(rank, world, port, ret):
+def _shard_worker(rank, world, port, ret, engine):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -85,7 +85,7 @@ def _shard_worker(rank, world, port, ret):
     P = pr.P
     # shards must be contiguous in the sampler's input order; any order is fine since the library permutes per shard
     kw = dict(lambda_=P.lambda_, sigma_init=P.sigma_init, con_sd=P.con_sd, mod_sd=P.mod_sd, seed=5, ntree_con=30,
-              ntree_mod=10, device=rank)
+              ntree_mod=10, device=rank, engine=engine)
     tau, ms, scal = multi.run_sharded(kw, P.yscale, P.z, P.x_c, P.x_m,
                                       (pr.cuts_c_flat, pr.off_c, pr.cuts_m_flat, pr.off_m), 6, 6)
     ret[rank] = (tau, scal)
@@ -93,13 +93,15 @@ def _shard_worker(rank, world, port, ret):
 
 
 @pytest.mark.skipif(_lib.device_count() < 2, reason="needs 2 GPUs")
-def test_observation_shards_walk_the_single_gpu_chain():
-    """2 shards + NCCL all-reduce of the leaf statistics == the same chain on one GPU: identical decisions (integer
-    statistics are partition-independent), posterior means equal to fp64 round-off of the per-shard moments."""
+@pytest.mark.parametrize("engine", [_lib.ENGINE_GRAPH, _lib.ENGINE_AUTO])
+def test_observation_shards_walk_the_single_gpu_chain(engine):
+    """2 shards == the same chain on one GPU: identical decisions (integer statistics are partition-independent).
+    ENGINE_GRAPH: one kernel per tree + ncclAllReduce of its leaf statistics (the checked baseline);
+    ENGINE_AUTO: the batched sweep kernel exchanging each batch's words itself through peer memory (NVLink)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    mp.spawn(_shard_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    mp.spawn(_shard_worker, args=(2, _free_port(), ret, engine), nprocs=2, join=True)
     pr = make_problem(n=3000, p=8, seed=12)
     P = pr.P
     from helpers import gpu_sampler
@@ -110,4 +112,5 @@ def test_observation_shards_walk_the_single_gpu_chain():
         tau, scal = ret[r]
         assert np.allclose(tau, ref, rtol=1e-9, atol=1e-9)
         assert scal["sigma"] == pytest.approx(sc["sigma"], rel=1e-9) and scal["sweep"] == sc["sweep"]
+        assert scal["engine_in_use"] == ((0, 1) if engine == _lib.ENGINE_GRAPH else (3, 2))
     assert np.array_equal(ret[0][0], ret[1][0])
