@@ -207,7 +207,7 @@ def workload_config(args, world, where):
                         f"(p_con={args.p + 1}), {T_CON} mu + {T_MOD} tau trees (BASELINE.json metric shape)",
             "n": args.n, "p": args.p, "ntree_control": T_CON, "ntree_moderate": T_MOD,
             "parallelism": (f"chains x{world} (one independent chain per GPU, data replicated)" if args.mode == "chains"
-                            else f"observation shards x{world} (NCCL all-reduce of leaf statistics per tree)"),
+                            else f"observation shards x{world} (one exchange of the leaf statistics per batch of trees)"),
             "where": where}
 
 
