@@ -34,6 +34,7 @@ static_assert(APCAP >= KEYS && APCAP >= NB * KB, "apply table too small");
 using TreeSmall = TreeT<2 * KB, KB>;
 using SmallStage = TreeStageT<TreeSmall, KB>;
 constexpr int BAT_BYTES_PER_TILE = TILE * (8 + 8) + NB * TILE;   // R, G, keys of the batch (one byte per tree)
+constexpr int FLUSH_TILES = 48;    // tiles of a CTA between two flushes of its 32-bit statistics tables (<= 63)
 
 struct BatchStage {
     int32_t first, nb, big, forest;       // trees [first, first + nb); big: ONE tree, staged in BatchSmem::big
@@ -197,7 +198,8 @@ __device__ __forceinline__ uint2 keys_make(const CurInfo& ci, uint2 key, uint4 b
 // One warp tile: apply the decided batch `sm.ap` (if do_apply), then accumulate the statistics of batch `cur`.
 // PAD: the tile may hold padding observations (key 255, R = G = 0): only the last tile of each treatment group.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool PAD>
+// RES: the state (R, G, keys) of the CTA's tiles is in shared memory; else in HBM / L2 (any n).
+template <bool PAD, bool RES>
 __device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const BatPtrs& rs, int tile0, int lt, int lane,
                                            const BatchStage* cur, bool do_apply, bool fswitch)
 {
@@ -206,19 +208,21 @@ __device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const Ba
     const int64_t gb = (int64_t)tile * TILE + lane * 8;
     const uint32_t toff = (uint32_t)lt * (TILE * 8u);
     const uint32_t ktile = rs.keys + (uint32_t)lt * (uint32_t)(NB * TILE) + (uint32_t)lane * 8u;
+    uint8_t* kglob = RES ? nullptr : d.keys + (int64_t)tile * (NB * TILE) + lane * 8;
     long long R[8];
-    res_ld8i(rs.R + toff, lane, R);
+    if (RES) res_ld8i(rs.R + toff, lane, R); else ld8_i64(d.rfx + gb, R);
     uint2 sl_n = make_uint2(0u, 0u);
     uint4 bn_n = make_uint4(0u, 0u, 0u, 0u);
     if (cur != nullptr) keys_load(d, cur->big ? sm.big.ci : cur->st[0].ci, cur->first, gb, sl_n, bn_n);   // in flight during the apply
     if (do_apply) {
         const ApplyTab& ap = sm.ap;
         double G[8];
-        res_ld8(rs.G + toff, lane, G);
+        double* Gf = (ap.forest ? d.Gm : d.Gc) + gb;     // HBM mode: the decided batch's forest
+        if (RES) res_ld8(rs.G + toff, lane, G); else ld8_f64(Gf, G);
         const int na = ap.n;
         for (int q = 0; q < na; ++q) {
             int key[8];
-            unpack8(lds_v2(ktile + (uint32_t)q * TILE), key);
+            unpack8(RES ? lds_v2(ktile + (uint32_t)q * TILE) : *reinterpret_cast<const uint2*>(kglob + q * TILE), key);
             const int off = ap.off[q];
             const ApRow* Tq = &ap.T[g][off];
 #pragma unroll
@@ -235,18 +239,23 @@ __device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const Ba
                 st8_u8(d.slots + (int64_t)(ap.first + q) * d.n_pad + gb, ns);
             }
         }
-        if (fswitch) {   // forest switch: park the mu forest's fit in HBM, bring the tau forest's in
-            st8_f64(d.Gc + gb, G);
-            ld8_f64(d.Gm + gb, G);
+        if (RES) {
+            if (fswitch) {   // forest switch: park the mu forest's fit in HBM, bring the tau forest's in
+                st8_f64(d.Gc + gb, G);
+                ld8_f64(d.Gm + gb, G);
+            }
+            res_st8(rs.G + toff, lane, G);
+            res_st8i(rs.R + toff, lane, R);
+        } else {
+            st8_f64(Gf, G);
+            st8_i64(d.rfx + gb, R);
         }
-        res_st8(rs.G + toff, lane, G);
-        res_st8i(rs.R + toff, lane, R);
     }
     if (cur == nullptr) return;
     if (cur->big) {
         const CurInfo& ci = sm.big.ci;
         const uint2 kk = keys_make(ci, sl_n, bn_n);
-        sts_v2(ktile, kk);
+        if (RES) sts_v2(ktile, kk); else *reinterpret_cast<uint2*>(kglob) = kk;
         int key[8];
         unpack8(kk, key);
         accum_tile(sm.p.tab, key, R, g, ci.K, ci.birth != 0, lane, (int)(threadIdx.x >> 5));
@@ -270,7 +279,7 @@ __device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const Ba
         const uint4 bn = bn_n;
         if (q + 1 < nb) keys_load(d, cur->st[q + 1].ci, cur->first + q + 1, gb, sl_n, bn_n);   // next tree's loads in flight
         const uint2 key = keys_make(ci, sl, bn);
-        sts_v2(ktile + (uint32_t)q * TILE, key);
+        if (RES) sts_v2(ktile + (uint32_t)q * TILE, key); else *reinterpret_cast<uint2*>(kglob + q * TILE) = key;
         uint8_t* cb = colb + (int)cur->colbase[q] * 32 + lane;
         for (int k = 1; k < K; ++k) {
             const uint32_t kv = (uint32_t)k * 0x01010101u;
@@ -922,6 +931,7 @@ __device__ inline void propose_all_b(BatchSmem& sm, const Dev& d, const TreeRec*
     long long tp = clock64();
 #define PROF(k) do { if (prof) { const long long now_ = clock64(); pc[k] += now_ - tp; tp = now_; } } while (0)
 
+template <bool RES>
 __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, unsigned int* bar, int ntl_max)
 {
     extern __shared__ __align__(16) unsigned char bcf_dyn_smem[];
@@ -951,15 +961,16 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
     const int pad_a = d.trt_tiles - 1 - tile0, pad_b = d.n_tiles - 1 - tile0;   // local tiles that may hold padding
 
     // entry: the residual and the mu forest's fit move into shared memory
-    for (int lt = wib; lt < ntl; lt += wpb) {
-        const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
-        const uint32_t toff = (uint32_t)lt * (TILE * 8u);
-        long long R[8];
-        double gc[8];
-        ld8_i64(d.rfx + gb, R); ld8_f64(d.Gc + gb, gc);
-        res_st8i(rs.R + toff, lane, R);
-        res_st8(rs.G + toff, lane, gc);
-    }
+    if (RES)
+        for (int lt = wib; lt < ntl; lt += wpb) {
+            const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
+            const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+            long long R[8];
+            double gc[8];
+            ld8_i64(d.rfx + gb, R); ld8_f64(d.Gc + gb, gc);
+            res_st8i(rs.R + toff, lane, R);
+            res_st8(rs.G + toff, lane, gc);
+        }
     __syncthreads();
     // proposals of the first sweep of this launch (later sweeps: made in the previous sweep's epilogue)
     propose_all_b(sm, d, d.trees[scs.parity], scs.sweep);
@@ -985,9 +996,20 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
             const int nb = B.nb;
             const bool do_apply = sm.ap.n > 0;
             const bool fswitch = has_mod && first == tmod && first > 0;
-            for (int lt = wib; lt < ntl; lt += wpb) {
-                if (lt == pad_a || lt == pad_b) batch_tile<true>(sm, d, rs, tile0, lt, lane, &B, do_apply, fswitch);
-                else batch_tile<false>(sm, d, rs, tile0, lt, lane, &B, do_apply, fswitch);
+            // the CTA tables hold 32-bit words: at most FLUSH_TILES tiles between two flushes (HBM mode: many tiles)
+            for (int lt0 = 0; lt0 < ntl; lt0 += FLUSH_TILES) {
+                const int lt1 = min(ntl, lt0 + FLUSH_TILES);
+                for (int lt = lt0 + wib; lt < lt1; lt += wpb) {
+                    if (lt == pad_a || lt == pad_b) batch_tile<true, RES>(sm, d, rs, tile0, lt, lane, &B, do_apply, fswitch);
+                    else batch_tile<false, RES>(sm, d, rs, tile0, lt, lane, &B, do_apply, fswitch);
+                }
+                if (lt1 < ntl) {
+                    __syncthreads();
+                    flush_batch(sm, B, totals, cross);
+                    __syncthreads();
+                    begin_batch(sm, B);
+                    __syncthreads();
+                }
             }
             __syncthreads();
             PROF(0);
@@ -1022,12 +1044,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
         {
             const bool fswitch = false;
             for (int lt = wib; lt < ntl; lt += wpb) {
-                if (lt == pad_a || lt == pad_b) batch_tile<true>(sm, d, rs, tile0, lt, lane, nullptr, true, fswitch);
-                else batch_tile<false>(sm, d, rs, tile0, lt, lane, nullptr, true, fswitch);
+                if (lt == pad_a || lt == pad_b) batch_tile<true, RES>(sm, d, rs, tile0, lt, lane, nullptr, true, fswitch);
+                else batch_tile<false, RES>(sm, d, rs, tile0, lt, lane, nullptr, true, fswitch);
                 const int tile = tile0 + lt;
                 const int64_t gb = (int64_t)tile * TILE + lane * 8;
                 double G[8], y[8], other[8];
-                res_ld8(rs.G + (uint32_t)lt * (TILE * 8u), lane, G);
+                if (RES) res_ld8(rs.G + (uint32_t)lt * (TILE * 8u), lane, G); else ld8_f64((has_mod ? d.Gm : d.Gc) + gb, G);
                 ld8_f64(d.y + gb, y);
                 if (has_mod) { ld8_f64(d.Gc + gb, other); moments8(sm.p.tab, y, other, G, tile < d.trt_tiles ? 1 : 0, lane, bad); }
                 else {
@@ -1085,7 +1107,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
                 double gc[8], gm[8], y[8];
                 long long R[8];
                 ld8_f64(d.y + gb, y);
-                if (has_mod) { res_ld8(rs.G + toff, lane, gm); ld8_f64(d.Gc + gb, gc); st8_f64(d.Gm + gb, gm); res_st8(rs.G + toff, lane, gc); }
+                if (!RES) {
+                    ld8_f64(d.Gc + gb, gc);
+                    if (has_mod) ld8_f64(d.Gm + gb, gm);
+                    else {
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) gm[o] = 0.0;
+                    }
+                } else if (has_mod) { res_ld8(rs.G + toff, lane, gm); ld8_f64(d.Gc + gb, gc); st8_f64(d.Gm + gb, gm); res_st8(rs.G + toff, lane, gc); }
                 else {
                     res_ld8(rs.G + toff, lane, gc);
 #pragma unroll
@@ -1093,7 +1122,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
                 }
 #pragma unroll
                 for (int o = 0; o < 8; ++o) R[o] = resync_fx(y[o], ms, gc[o], b, gm[o], bad);
-                res_st8i(rs.R + toff, lane, R);
+                if (RES) res_st8i(rs.R + toff, lane, R); else st8_i64(d.rfx + gb, R);
                 if (row >= 0) {
 #pragma unroll
                     for (int o = 0; o < 8; ++o) {
@@ -1118,16 +1147,17 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
         PROF(6);
     }
     // exit: park the state in HBM in the form every engine understands (Gm was stored by the finishing pass)
-    for (int lt = wib; lt < ntl; lt += wpb) {
-        const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
-        const uint32_t toff = (uint32_t)lt * (TILE * 8u);
-        double G[8];
-        long long R[8];
-        res_ld8(rs.G + toff, lane, G);
-        res_ld8i(rs.R + toff, lane, R);
-        st8_f64(d.Gc + gb, G);
-        st8_i64(d.rfx + gb, R);
-    }
+    if (RES)
+        for (int lt = wib; lt < ntl; lt += wpb) {
+            const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
+            const uint32_t toff = (uint32_t)lt * (TILE * 8u);
+            double G[8];
+            long long R[8];
+            res_ld8(rs.G + toff, lane, G);
+            res_ld8i(rs.R + toff, lane, R);
+            st8_f64(d.Gc + gb, G);
+            st8_i64(d.rfx + gb, R);
+        }
     if (prof) for (int k = 0; k < 8; ++k) d.prof[k] += pc[k];
     if (bad) atomicOr(d.err, ERR_FX_RANGE);
     if (t == 0 && sm.bad) atomicOr(d.err, sm.bad);

@@ -129,6 +129,7 @@ struct Dev {
     long long* rfx;            // FULL residual y - allfit as a fixed-point integer (value * 2^44): updated exactly
     double *Gc, *Gm;           // unscaled forest fits: sum of the mu / tau trees' leaf values
     uint8_t* slots;            // [T][n_pad]
+    uint8_t* keys;             // [n_tiles][NB][TILE] keys of the batch in flight (batched engine with the state in HBM)
     TreeRec* trees[2];
     PropRec* proprec;          // [T] proposals of the sweep in progress
     long long* totals;         // [2][T][KEYS][2][4]  (count, limb0, limb1, limb2) by (key, group); see sweep_totals

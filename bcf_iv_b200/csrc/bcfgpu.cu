@@ -226,6 +226,7 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_tree_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_sweep_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_batched<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM_BYTES);
     if (e2 != cudaSuccess) { delete h; return fail(BCFGPU_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e2)); }
     if (cfg->engine < BCFGPU_ENGINE_AUTO || cfg->engine > BCFGPU_ENGINE_PIPELINED) { delete h; return fail(BCFGPU_ERR_BAD_ARG, "unknown engine"); }
     h->engine = cfg->engine == BCFGPU_ENGINE_AUTO ? BCFGPU_ENGINE_PIPELINED : cfg->engine;
@@ -649,7 +650,7 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
         // take the same path (the shards differ by a row, so "does it fit in shared memory" is agreed on, not assumed)
         if (!h->shard_decided) {
             if ((rc = select_kernel(h))) return rc;
-            long long ok = h->kernel == 3 ? 1 : 0;
+            long long ok = (h->kernel == 3 || h->kernel == 5) ? 1 : 0;
             long long* dq = (long long*)h->d_tmp;
             CK(cudaMemcpyAsync(dq, &ok, 8, cudaMemcpyHostToDevice, h->stream));
             NK(g_nccl.AllReduce(dq, dq, 1, NCCL_INT64, NCCL_MIN, h->comm, h->stream));
@@ -1179,11 +1180,16 @@ static int select_kernel(bcfgpu_handle* h)
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, need) != cudaSuccess) return 0;
             return per_sm >= 1;
         };
-        if (want_batched && may_reside) {
+        if (want_batched) {
             const size_t need = BATCH_SMEM_BYTES + (size_t)ntl_max * BAT_BYTES_PER_TILE;
-            if (fits((const void*)k_batched, need)) { h->kernel = 3; h->res_ntl = ntl_max; h->res_smem = need; }
-            else if (h->cfg.engine == BCFGPU_ENGINE_BATCHED || h->cfg.engine == BCFGPU_ENGINE_PIPELINED)
-                return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_BATCHED / PIPELINED: the observations of one SM do not fit in shared memory at this n");
+            if (may_reside && fits((const void*)k_batched<true>, need)) { h->kernel = 3; h->res_ntl = ntl_max; h->res_smem = need; }
+            else if (fits((const void*)k_batched<false>, BATCH_SMEM_BYTES)) {
+                // the SM's observations do not fit in shared memory: same kernel with the state in HBM / L2
+                h->kernel = 5; h->res_ntl = 0; h->res_smem = BATCH_SMEM_BYTES;
+                if (!h->dev.keys) {
+                    DM(h, &h->dev.keys, (size_t)h->dev.n_pad * NB);
+                }
+            }
             // the pipelined kernel on top of it (the batched one then serves the sweeps that hold a wide tree)
             if (h->kernel == 3 && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && h->nranks == 1) {
                 const size_t needp = PIPE_SMEM_BYTES + (size_t)ntl_max * PIPE_BYTES_PER_TILE + (size_t)h->T * sizeof(TMeta) + 16;
@@ -1237,7 +1243,7 @@ static int run_persistent(bcfgpu_handle* h, int total)
                 int one = 1;
                 CK(cudaMemsetAsync(bar, 0, 16, h->stream));
                 void* a2[] = {(void*)&d, (void*)&one, (void*)&bar, (void*)&ntl};
-                CK(cudaLaunchCooperativeKernel((const void*)k_batched, dim3(h->coop_grid), dim3(PTHREADS), a2, h->res_smem, h->stream));
+                CK(cudaLaunchCooperativeKernel((const void*)k_batched<true>, dim3(h->coop_grid), dim3(PTHREADS), a2, h->res_smem, h->stream));
                 h->launches++;
                 done += 1;
             }
@@ -1245,7 +1251,10 @@ static int run_persistent(bcfgpu_handle* h, int total)
         }
         if (h->kernel == 3) {
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};
-            CK(cudaLaunchCooperativeKernel((const void*)k_batched, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
+            CK(cudaLaunchCooperativeKernel((const void*)k_batched<true>, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
+        } else if (h->kernel == 5) {
+            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};
+            CK(cudaLaunchCooperativeKernel((const void*)k_batched<false>, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
         } else if (h->kernel == 2) {
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};
             CK(cudaLaunchCooperativeKernel((const void*)k_resident, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));

@@ -341,7 +341,7 @@ def run_ours(args):
     sweeps_per_launch = K / max(launches, 1)
     launch_ms = dev_ms / max(launches, 1)
     achieved = b_sweep * sweeps_per_launch / (launch_ms * 1e-3) / 1e9
-    eng_name = {0: "graph", 1: "persistent_hbm", 2: "persistent", 3: "batched", 4: "pipelined"}[in_use[0]]
+    eng_name = {0: "graph", 1: "persistent_hbm", 2: "persistent", 3: "batched", 4: "pipelined", 5: "batched_hbm"}[in_use[0]]
     exchange = {0: "none", 1: "ncclAllReduce per tree", 2: "in-kernel peer-memory mailboxes (NVLink)"}[in_use[1]]
     traffic_sweep = ncu_traffic_per_sweep(n_local, eng_name)
     line = {
@@ -355,7 +355,7 @@ def run_ours(args):
                        wall_ms_per_step=wall_ms / K),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic_sweep * sweeps_per_launch if traffic_sweep is not None else None),
-                     "peak_source": peak_src, "kernel": {"pipelined": "k_pipe", "batched": "k_batched", "persistent": "k_resident", "persistent_hbm": "k_persistent", "graph": "k_tree_step x T (CUDA graph)"}.get(eng_name, eng_name),
+                     "peak_source": peak_src, "kernel": {"pipelined": "k_pipe", "batched": "k_batched<resident>", "batched_hbm": "k_batched<hbm>", "persistent": "k_resident", "persistent_hbm": "k_persistent", "graph": "k_tree_step x T (CUDA graph)"}.get(eng_name, eng_name),
                      "algorithmic_bytes_per_sweep": b_sweep, "sweeps_per_launch": sweeps_per_launch,
                      "launch_ms": launch_ms},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,

@@ -118,7 +118,7 @@ BCFGPU_API int bcfgpu_run(bcfgpu_handle *h, int32_t nburn, int32_t nsim, int32_t
 BCFGPU_API int bcfgpu_last_run_ms(bcfgpu_handle *h, double *device_ms);  /* CUDA-event time of the last run */
 BCFGPU_API int bcfgpu_kernel_launches(bcfgpu_handle *h, int64_t *count); /* kernels launched since create */
 /* what the last run used: out[0] sweep kernel (0 graph of per-tree kernels, 1 k_persistent, 2 k_resident, 3 k_batched,
- * 4 k_pipe), out[1] shards exchange (0 none, 1 ncclAllReduce per tree, 2 in-kernel peer-memory mailboxes) */
+ * 4 k_pipe, 5 k_batched with the state in HBM), out[1] shards exchange (0 none, 1 ncclAllReduce per tree, 2 in-kernel peer-memory mailboxes) */
 BCFGPU_API int bcfgpu_engine_in_use(bcfgpu_handle *h, int32_t out2[2]);
 
 /* ---- results (standardised scale, original row order; the R wrapper rescales by sd(y)/mean(y)) ---- */

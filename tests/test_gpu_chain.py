@@ -152,3 +152,22 @@ def test_chain_with_big_and_small_trees_mixed(engine):
         o.sweeps(k)
         _compare_state(g, o, pr)
     assert g.verify_leaf_cache() == 0
+
+
+def test_batched_engine_with_the_state_in_hbm(monkeypatch):
+    """BCFGPU_NO_RESIDENT forces the batched kernel's HBM variant (what large n runs): same chain, bit for bit."""
+    pr = make_problem(n=5000, p=9, seed=14, continuous=True)
+    kw = dict(seed=8, ntree_con=40, ntree_mod=16)
+    a = gpu_sampler(pr, engine=4, **kw)
+    a.run(6, 6)
+    assert a.engine_in_use[0] == 3
+    monkeypatch.setenv("BCFGPU_NO_RESIDENT", "1")
+    b = gpu_sampler(pr, engine=4, **kw)
+    b.run(6, 6)
+    assert b.engine_in_use[0] == 5
+    assert a.scalars() == b.scalars() and a.counters() == b.counters()
+    assert np.array_equal(a.tau_mean(), b.tau_mean()) and np.array_equal(a.trace()[0], b.trace()[0])
+    assert b.verify_leaf_cache() == 0
+    o = oracle_sampler(pr, max_leaves=128, **kw)
+    o.sweeps(12)
+    _compare_state(b, o, pr)
