@@ -122,25 +122,6 @@ __device__ __forceinline__ __int128 limbs_to_i128(long long w0, long long w1, lo
     return (__int128)w0 + ((__int128)w1 << LIMB_BITS) + ((__int128)w2 << (2 * LIMB_BITS));
 }
 
-// per-lane partial sum (|s| < 2^62) -> the three 21-bit limbs of the global representation, reduced over the warp
-// and added to (count, l0, l1, l2) with native 32-bit shared atomics.  A CTA table word holds at most
-// tiles * 32 lanes * 2^21, so a flush is due every 63 tiles at the latest (the resident kernel holds < 32).
-__device__ __forceinline__ void warp_add21(unsigned int* e, long long s, int lane)
-{
-    int l0 = (int)(s & 0x1FFFFF), l1 = (int)((s >> LIMB_BITS) & 0x1FFFFF), l2 = (int)(s >> (2 * LIMB_BITS));
-    l0 = __reduce_add_sync(0xffffffffu, l0);
-    l1 = __reduce_add_sync(0xffffffffu, l1);
-    l2 = __reduce_add_sync(0xffffffffu, l2);
-    if (lane < 3) {
-        const int v = lane == 0 ? l0 : lane == 1 ? l1 : l2;
-        atomicAdd(&e[1 + lane], (unsigned int)v);
-    }
-}
-// word q (0 count, 1..3 the limbs; the top limb is signed) of a CTA table entry
-__device__ __forceinline__ long long acc_word(const unsigned int* e, int q)
-{
-    return q == 3 ? (long long)(int)e[3] : (long long)e[q];
-}
 __device__ __forceinline__ void sts_v2(uint32_t a, uint2 v)
 {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
@@ -150,12 +131,6 @@ __device__ __forceinline__ void unpack8(uint2 v, int (&out)[8])
     out[0] = v.x & 0xFF; out[1] = (v.x >> 8) & 0xFF; out[2] = (v.x >> 16) & 0xFF; out[3] = v.x >> 24;
     out[4] = v.y & 0xFF; out[5] = (v.y >> 8) & 0xFF; out[6] = (v.y >> 16) & 0xFF; out[7] = v.y >> 24;
 }
-// one bit per byte of a pair of 0x00 / 0xFF byte masks -> 8 bits (observation o of the lane = bit o)
-__device__ __forceinline__ uint32_t bytes_to_bits(uint32_t e0, uint32_t e1)
-{
-    return (((e0 & 0x08040201u) * 0x01010101u) >> 24) | (((e1 & 0x80402010u) * 0x01010101u) >> 24);
-}
-
 // keys of one tree for the lane's 8 observations: the cached leaf slot, with the observations a birth proposal would
 // send to the right child re-keyed to `new_slot` (padding observations keep 255).  Split in load / compute so that
 // the loads of the next tree are in flight while this one is processed.
@@ -533,10 +508,9 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
             big_enough = pka.k1 + pka.k0 >= d.min_leaf && pkb.k1 + pkb.k0 >= d.min_leaf;
         }
         if (active && l < K) {
-            const int cL0 = birth ? (int)rs.tot[q][L][0][0] : 0, cL1 = birth ? (int)rs.tot[q][L][1][0] : 0;
-            if (l < L) { c0 = tr.cnt0[l] - ((birth && l == sx) ? cL0 : 0); c1 = tr.cnt1[l] - ((birth && l == sx) ? cL1 : 0); }
-            else { c0 = cL0; c1 = cL1; }
-            cq[q][l][0] = c0; cq[q][l][1] = c1;
+            // pre-decision counts of the key: written by the parallel count phase, BEFORE the barrier that precedes
+            // the chain (the other warps read this tree's counts while they wait for its decision)
+            c0 = cq[q][l][0]; c1 = cq[q][l][1];
             if (l >= 1) {
                 wa0 = rs.tot[q][l][0][1]; wa1 = rs.tot[q][l][0][2]; wa2 = rs.tot[q][l][0][3];
                 wb0 = rs.tot[q][l][1][1]; wb1 = rs.tot[q][l][1][2]; wb2 = rs.tot[q][l][1][3];
@@ -890,6 +864,7 @@ __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d,
             const double prec = a + A, inv = 1.0 / prec;
             PreKey& pk = pre[q * (KB + 1) + e];
             pk.k1 = k1; pk.k0 = k0; pk.inv = inv; pk.plog = log(prec); pk.psd = sqrt(inv);
+            if (e < K) { sm.cq[q][e][1] = (int32_t)k1; sm.cq[q][e][0] = (int32_t)k0; }
         }
     }
     __syncthreads();

@@ -335,6 +335,31 @@ __device__ __forceinline__ long long table_word(const StatTab& tab, int nwarps, 
     return v;
 }
 
+// per-lane partial sum (|s| < 2^62) -> the three 21-bit limbs of the global representation, reduced over the warp
+// and added to (count, l0, l1, l2) with native 32-bit shared atomics.  A CTA table word holds at most
+// tiles * 32 lanes * 2^21, so a flush is due every 63 tiles at the latest (the resident kernel holds < 32).
+__device__ __forceinline__ void warp_add21(unsigned int* e, long long s, int lane)
+{
+    int l0 = (int)(s & 0x1FFFFF), l1 = (int)((s >> LIMB_BITS) & 0x1FFFFF), l2 = (int)(s >> (2 * LIMB_BITS));
+    l0 = __reduce_add_sync(0xffffffffu, l0);
+    l1 = __reduce_add_sync(0xffffffffu, l1);
+    l2 = __reduce_add_sync(0xffffffffu, l2);
+    if (lane < 3) {
+        const int v = lane == 0 ? l0 : lane == 1 ? l1 : l2;
+        atomicAdd(&e[1 + lane], (unsigned int)v);
+    }
+}
+// word q (0 count, 1..3 the limbs; the top limb is signed) of a CTA table entry
+__device__ __forceinline__ long long acc_word(const unsigned int* e, int q)
+{
+    return q == 3 ? (long long)(int)e[3] : (long long)e[q];
+}
+// one bit per byte of a pair of 0x00 / 0xFF byte masks -> 8 bits (observation o of the lane = bit o)
+__device__ __forceinline__ uint32_t bytes_to_bits(uint32_t e0, uint32_t e1)
+{
+    return (((e0 & 0x08040201u) * 0x01010101u) >> 24) | (((e1 & 0x80402010u) * 0x01010101u) >> 24);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Loads: 8 consecutive observations per lane
 // ---------------------------------------------------------------------------------------------

@@ -408,11 +408,11 @@ __global__ void __launch_bounds__(THREADS) k_op_stats(Dev d, int tree, int fores
 constexpr int HIST_SMEM_ENTRIES = 1024;   // (leaf, bin) cells of 4 x int64 = 32 KB
 __global__ void __launch_bounds__(256) k_hist(Dev d, int forest, const uint8_t* __restrict__ label,
                                               const double* __restrict__ r, int nleaf, const int32_t* __restrict__ off,
-                                              long long* out /* [leaf][off[p]+p][4] */)
+                                              long long* out /* [leaf][off[p]+p][4] */, const int32_t* __restrict__ cols)
 {
     __shared__ long long h[HIST_SMEM_ENTRIES][4];
     const ForestDev& F = d.f[forest];
-    const int v = blockIdx.y;
+    const int v = cols ? cols[blockIdx.y] : blockIdx.y;     // cols: the columns k_hist_small does not take
     const int nb = F.ncut[v] + 1;
     const int64_t nbt = (int64_t)off[F.p] + F.p;
     const int64_t vbase = (int64_t)off[v] + v;
@@ -471,6 +471,153 @@ __global__ void __launch_bounds__(256) k_hist(Dev d, int forest, const uint8_t* 
             const int cellid = i >> 2, q = i & 3, lb = cellid / nb, b = cellid % nb;
             atomicAdd((unsigned long long*)&out[((int64_t)lb * nbt + vbase + b) * 4 + q], (unsigned long long)val);
         }
+    }
+    if (bad) atomicOr(d.err, ERR_FX_RANGE);
+}
+
+// K2' for columns with few bins (binary / categorical covariates: what BayesIV's designs are).  One pass over the
+// observations serves ALL such columns: a warp loads a tile's labels and residuals once (128-bit / 64-bit coalesced
+// loads), then per column its 8 bin bytes per lane, and accumulates every (leaf, bin >= 1) cell with a masked sum of
+// the fixed-point residual + warp REDUX into a shared-memory table of 32-bit words (count, three 21-bit limbs).  Bin 0
+// of a (leaf, column) is the leaf total minus the other bins (exact in integers), formed when the CTA flushes.
+// Algorithmic traffic: n * (9 + columns) bytes -- every byte is read once.
+constexpr int HIST2_MAX_BINS = 4;        // bins 0..3 (up to 3 cutpoints)
+constexpr int HIST2_MAX_LEAF = 16;
+constexpr int HIST2_CELL_WORDS = 49152 / 16;   // shared table: cells of 4 x u32
+__global__ void __launch_bounds__(256) k_hist_small(Dev d, int forest, const uint8_t* __restrict__ label,
+                                                    const double* __restrict__ r, int nleaf, const int32_t* __restrict__ off,
+                                                    const int32_t* __restrict__ cols, int ncols, const int32_t* __restrict__ cellbase,
+                                                    int ncells, int tiles_per_cta, long long* out, int per_obs)
+{
+    extern __shared__ __align__(16) unsigned int h2[];          // [ncells + nleaf][4]: cells, then the leaf totals
+    if (per_obs) {
+        // Many (leaf, bin) cells per column: one native 32-bit shared atomic per word and observation instead of one
+        // masked warp sum per cell.  Cells hold (count, four 16-bit limbs) in 8 words; every bin (0 included) has its own.
+        const ForestDev& F = d.f[forest];
+        const int t = threadIdx.x, lane = t & 31, wib = t >> 5, wpb = blockDim.x >> 5;
+        for (int i = t; i < ncells * 8; i += blockDim.x) h2[i] = 0u;
+        __syncthreads();
+        int bad = 0;
+        const int tile_lo = blockIdx.x * tiles_per_cta, tile_hi = min(d.n_tiles, tile_lo + tiles_per_cta);
+        for (int tile = tile_lo + wib; tile < tile_hi; tile += wpb) {
+            const int64_t base = (int64_t)tile * TILE + lane * 8;
+            int lab[8];
+            ld8_u8(label + base, lab);
+            double rd[8];
+            long long R[8];
+            ld8_f64(r + base, rd);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) R[o] = to_fixed(rd[o], bad);
+            uint2 bn_n = *reinterpret_cast<const uint2*>(F.bins8 + (int64_t)F.col_index[cols[0]] * d.n_pad + base);
+            for (int ci = 0; ci < ncols; ++ci) {
+                const int v = cols[ci];
+                const uint2 bn = bn_n;
+                if (ci + 1 < ncols) bn_n = *reinterpret_cast<const uint2*>(F.bins8 + (int64_t)F.col_index[cols[ci + 1]] * d.n_pad + base);
+                const int nb = F.ncut[v] + 1;
+                unsigned int* cell0 = h2 + (size_t)cellbase[ci] * 8;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    if (lab[o] >= nleaf) continue;
+                    const int bin = (int)(((o < 4 ? bn.x : bn.y) >> (8 * (o & 3))) & 0xFFu);
+                    unsigned int* e = cell0 + 8 * (lab[o] * nb + bin);
+                    const long long vv = R[o];
+                    atomicAdd(e, 1u);
+                    atomicAdd(e + 1, (unsigned int)(vv & 0xFFFF));
+                    atomicAdd(e + 2, (unsigned int)((vv >> 16) & 0xFFFF));
+                    atomicAdd(e + 3, (unsigned int)((vv >> 32) & 0xFFFF));
+                    atomicAdd(e + 4, (unsigned int)(int)(vv >> 48));
+                }
+            }
+        }
+        __syncthreads();
+        const int64_t nbt = (int64_t)off[F.p] + F.p;
+        for (int i = t; i < ncells; i += blockDim.x) {
+            // which (column, leaf, bin) is cell i: columns are few, a linear search is fine
+            int ci = 0;
+            while (ci + 1 < ncols && cellbase[ci + 1] <= i) ++ci;
+            const int v = cols[ci], nb = F.ncut[v] + 1, j = i - cellbase[ci], l = j / nb, b = j % nb;
+            const unsigned int* e = h2 + (size_t)i * 8;
+            const __int128 V = (__int128)e[1] + ((__int128)e[2] << 16) + ((__int128)e[3] << 32) + ((__int128)(int)e[4] << 48);
+            long long* o = out + ((int64_t)l * nbt + (int64_t)off[v] + v + b) * 4;
+            const long long w0 = (long long)e[0], w1 = (long long)(V & 0x1FFFFF), w2 = (long long)((V >> LIMB_BITS) & 0x1FFFFF), w3 = (long long)(V >> (2 * LIMB_BITS));
+            if (w0) atomicAdd((unsigned long long*)&o[0], (unsigned long long)w0);
+            if (w1) atomicAdd((unsigned long long*)&o[1], (unsigned long long)w1);
+            if (w2) atomicAdd((unsigned long long*)&o[2], (unsigned long long)w2);
+            if (w3) atomicAdd((unsigned long long*)&o[3], (unsigned long long)w3);
+        }
+        if (bad) atomicOr(d.err, ERR_FX_RANGE);
+        return;
+    }
+    const ForestDev& F = d.f[forest];
+    const int t = threadIdx.x, lane = t & 31, wib = t >> 5, wpb = blockDim.x >> 5;
+    for (int i = t; i < (ncells + nleaf) * 4; i += blockDim.x) h2[i] = 0u;
+    __syncthreads();
+    unsigned int* leaf_tot = h2 + (size_t)ncells * 4;
+    int bad = 0;
+    const int tile_lo = blockIdx.x * tiles_per_cta, tile_hi = min(d.n_tiles, tile_lo + tiles_per_cta);
+    for (int tile = tile_lo + wib; tile < tile_hi; tile += wpb) {
+        const int64_t base = (int64_t)tile * TILE + lane * 8;
+        const uint2 lab = *reinterpret_cast<const uint2*>(label + base);
+        double rd[8];
+        long long R[8];
+        ld8_f64(r + base, rd);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) R[o] = to_fixed(rd[o], bad);
+        // which of the lane's 8 observations carry each leaf label (labels >= nleaf: skipped)
+        unsigned long long lbA = 0ull, lbB = 0ull;      // 8 bits per leaf: leaves 0..7 / 8..15
+        for (int l = 0; l < nleaf; ++l) {
+            const uint32_t lv = (uint32_t)l * 0x01010101u;
+            const uint32_t bits = bytes_to_bits(__vcmpeq4(lab.x, lv), __vcmpeq4(lab.y, lv));
+            if (l < 8) lbA |= (unsigned long long)bits << (8 * l); else lbB |= (unsigned long long)bits << (8 * (l - 8));
+            long long s = 0;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) s += ((bits >> o) & 1u) ? R[o] : 0ll;
+            warp_add21(leaf_tot + 4 * l, s, lane);
+            const int c = __reduce_add_sync(0xffffffffu, __popc(bits));
+            if (lane == 0 && c) atomicAdd(leaf_tot + 4 * l, (unsigned int)c);
+        }
+        uint2 bn_n = *reinterpret_cast<const uint2*>(F.bins8 + (int64_t)F.col_index[cols[0]] * d.n_pad + base);
+        for (int ci = 0; ci < ncols; ++ci) {
+            const int v = cols[ci];
+            const uint2 bn = bn_n;
+            if (ci + 1 < ncols) bn_n = *reinterpret_cast<const uint2*>(F.bins8 + (int64_t)F.col_index[cols[ci + 1]] * d.n_pad + base);
+            const int nb = F.ncut[v] + 1;
+            unsigned int* cell0 = h2 + (size_t)cellbase[ci] * 4;      // cells of this column: [leaf][bin - 1]
+            for (int b = 1; b < nb; ++b) {
+                const uint32_t bv = (uint32_t)b * 0x01010101u;
+                const uint32_t binbits = bytes_to_bits(__vcmpeq4(bn.x, bv), __vcmpeq4(bn.y, bv));
+                for (int l = 0; l < nleaf; ++l) {
+                    const uint32_t bits = binbits & (uint32_t)((l < 8 ? lbA >> (8 * l) : lbB >> (8 * (l - 8))) & 0xFFull);
+                    long long s = 0;
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) s += ((bits >> o) & 1u) ? R[o] : 0ll;
+                    unsigned int* e = cell0 + 4 * (l * (nb - 1) + (b - 1));
+                    warp_add21(e, s, lane);
+                    const int c = __reduce_add_sync(0xffffffffu, __popc(bits));
+                    if (lane == 0 && c) atomicAdd(e, (unsigned int)c);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // flush: bins >= 1 directly, bin 0 = leaf total - the others
+    const int64_t nbt = (int64_t)off[F.p] + F.p;
+    for (int i = t; i < ncols * nleaf; i += blockDim.x) {
+        const int ci = i / nleaf, l = i % nleaf, v = cols[ci];
+        const int nb = F.ncut[v] + 1;
+        const int64_t vbase = (int64_t)off[v] + v;
+        long long rest[4] = {(long long)leaf_tot[4 * l], acc_word(leaf_tot + 4 * l, 1), acc_word(leaf_tot + 4 * l, 2), acc_word(leaf_tot + 4 * l, 3)};
+        for (int b = 1; b < nb; ++b) {
+            const unsigned int* e = h2 + (size_t)(cellbase[ci] + l * (nb - 1) + (b - 1)) * 4;
+            long long* o = out + ((int64_t)l * nbt + vbase + b) * 4;
+            for (int q = 0; q < 4; ++q) {
+                const long long w = acc_word(e, q);
+                rest[q] -= w;
+                if (w != 0) atomicAdd((unsigned long long*)&o[q], (unsigned long long)w);
+            }
+        }
+        long long* o0 = out + ((int64_t)l * nbt + vbase) * 4;
+        for (int q = 0; q < 4; ++q) if (rest[q] != 0) atomicAdd((unsigned long long*)&o0[q], (unsigned long long)rest[q]);
     }
     if (bad) atomicOr(d.err, ERR_FX_RANGE);
 }

@@ -399,6 +399,7 @@ __device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, cons
             const double prec = a + A, inv = 1.0 / prec;
             PreKey& pk = sm.pre[q * (KB + 1) + e];
             pk.k1 = k1; pk.k0 = k0; pk.inv = inv; pk.plog = log(prec); pk.psd = sqrt(inv);
+            if (e < K) { sm.cq[b & 1][q][e][1] = (int32_t)k1; sm.cq[b & 1][q][e][0] = (int32_t)k0; }
         }
     }
     named_sync(BAR_RES, PR_THREADS);

@@ -1099,10 +1099,44 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
     CK(cudaMemcpyAsync(h->d_tmp, r, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
     k_permute_in<<<(int)std::min<int64_t>((h->n + 255) / 256, 4096), 256, 0, h->stream>>>(h->d_tmp, h->d_pos, h->n, h->d_tmp2);
     CK(cudaMemsetAsync(dout, 0, (size_t)nleaf * nbt * 32, h->stream));
-    const int64_t nchunk = h->n_pad / 16;
-    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((nchunk + 255) / 256, (int64_t)h->num_sms * 2)), (unsigned)F.p);
+    // columns with at most HIST2_MAX_BINS bins go through the one-pass kernel, the others through the per-column one.
+    // Few (leaf, bin) cells per column: one masked warp sum per cell (bin 0 by subtraction); many: one shared atomic
+    // per word and observation (every bin has its cell).
+    const bool per_obs = false;   // measured on B200 (n = 1e6, 100 binary columns): the masked sums win up to 16 leaves
+    const size_t smem_cap = 160 * 1024;
+    std::vector<int32_t> small, large, cellbase;
+    int ncells = 0;
+    for (int v = 0; v < F.p; ++v) {
+        const int add = per_obs ? nleaf * (F.ncut[v] + 1) : nleaf * F.ncut[v];
+        const size_t need = per_obs ? (size_t)(ncells + add) * 32 : (size_t)(ncells + add + nleaf) * 16;
+        if (!F.is16[v] && F.ncut[v] + 1 <= HIST2_MAX_BINS && nleaf <= HIST2_MAX_LEAF && need <= smem_cap) {
+            small.push_back(v); cellbase.push_back(ncells); ncells += add;
+        } else large.push_back(v);
+    }
+    int32_t* dcols = nullptr;
+    CK(cudaMalloc((void**)&dcols, (size_t)(small.size() * 2 + large.size() + 1) * 4));
+    int32_t* dsmall = dcols; int32_t* dbase = dcols + small.size(); int32_t* dlarge = dcols + 2 * small.size();
+    if (!small.empty()) {
+        CK(cudaMemcpyAsync(dsmall, small.data(), small.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dbase, cellbase.data(), cellbase.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (!large.empty()) CK(cudaMemcpyAsync(dlarge, large.data(), large.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
-    k_hist<<<grid, 256, 0, h->stream>>>(h->dev, forest, dlab, h->d_tmp2, nleaf, F.d_off, dout);
+    if (!small.empty()) {
+        // at most 48 tiles per CTA between flushes (32-bit table words), at least ~2 CTAs per SM
+        const int tiles = h->dev.n_tiles;
+        int tpc = std::max(1, std::min(48, (tiles + h->num_sms * 2 - 1) / (h->num_sms * 2)));
+        const int gridx = (tiles + tpc - 1) / tpc;
+        const size_t smem = per_obs ? (size_t)ncells * 32 : (size_t)(ncells + nleaf) * 16;
+        CK(cudaFuncSetAttribute(k_hist_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        k_hist_small<<<gridx, 256, smem, h->stream>>>(h->dev, forest, dlab, h->d_tmp2, nleaf, F.d_off, dsmall, (int)small.size(), dbase,
+                                                       ncells, tpc, dout, per_obs ? 1 : 0);
+    }
+    if (!large.empty()) {
+        const int64_t nchunk = h->n_pad / 16;
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((nchunk + 255) / 256, (int64_t)h->num_sms * 2)), (unsigned)large.size());
+        k_hist<<<grid, 256, 0, h->stream>>>(h->dev, forest, dlab, h->d_tmp2, nleaf, F.d_off, dout, dlarge);
+    }
     CK(cudaEventRecord(h->ev1, h->stream));
     h->launches += 2;
     std::vector<long long> tot((size_t)nleaf * nbt * 4);
@@ -1110,7 +1144,7 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     float ms = 0.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    cudaFree(dlab); cudaFree(dout);
+    cudaFree(dlab); cudaFree(dout); cudaFree(dcols);
     if (e != cudaSuccess) return fail(BCFGPU_ERR_CUDA, std::string("op_hist_all: ") + cudaGetErrorString(e));
     if (device_ms) *device_ms = ms;
     for (size_t k = 0; k < (size_t)nleaf * nbt; ++k) {
