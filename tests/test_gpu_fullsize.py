@@ -66,3 +66,18 @@ def test_leaf_statistics_are_conserved_at_headline_size(inputs):
         assert np.array_equal(cnt[:, blk].sum(axis=1), np.bincount(slot, minlength=3))
         assert np.allclose(sm[:, blk].sum(axis=1), np.bincount(slot, weights=r, minlength=3), rtol=0, atol=1e-10 * np.abs(r).sum())
     s.close()
+
+
+def test_chains_are_repeatable_run_to_run(inputs):
+    """Same seed, same engine, several runs: identical bits every time (integer statistics, no ordering left to chance).
+    Catches races that a single comparison would only see once in a while (scripts/stress_repro.py runs it longer)."""
+    for engine in (_lib.ENGINE_PIPELINED, _lib.ENGINE_BATCHED):
+        ref = None
+        for _ in range(4):
+            s = _sampler(inputs, engine)
+            s.run(2, 2)
+            got = (s.scalars(), s.counters(), s.trace()[0].tobytes(), s.tau_mean().tobytes())
+            s.close()
+            if ref is None:
+                ref = got
+            assert got == ref
