@@ -33,7 +33,7 @@ static_assert(2 * PXCAP <= PIPE_XSTRIDE, "cross-count slot too small");
 
 // registers per thread: 768 x 80 at launch; the role section re-splits the CTA's OWN
 // allocation (the pool of setmaxnreg is per CTA): 512 x 72 + 256 x 96 = 61440
-constexpr int PIPE_REGS_BASE = 80, PIPE_REGS_PASS = 72, PIPE_REGS_RESOLVE = 96;
+constexpr int PIPE_REGS_BASE = 80, PIPE_REGS_PASS = 64, PIPE_REGS_RESOLVE = 112;
 enum { BAR_H1 = 9, BAR_H2 = 11, BAR_PASS = 13, BAR_RES = 14 };   // named barriers 1..8 belong to the decision chain
 
 struct __align__(16) TMeta {                         // what the pass needs to know about a tree, per sweep
@@ -214,9 +214,10 @@ __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, const PipePlan& P,
         for (int k = 1; k < K; ++k) {
             const uint32_t kv = (uint32_t)k * 0x01010101u;
             const uint32_t bits = bytes_to_bits(__vcmpeq4(key.x, kv), __vcmpeq4(key.y, kv));
-            long long s = 0;
+            long long m[8];
 #pragma unroll
-            for (int o = 0; o < 8; ++o) s += ((bits >> o) & 1u) ? R[o] : 0ll;
+            for (int o = 0; o < 8; ++o) m[o] = ((bits >> o) & 1u) ? R[o] : 0ll;
+            const long long s = ((m[0] + m[1]) + (m[2] + m[3])) + ((m[4] + m[5]) + (m[6] + m[7]));   // short dependency chain
             unsigned int* e = sm.p.acc.btab[q][k][g];
             warp_add21(e, s, lane);
             if (ci.birth && k == K - 1) {
@@ -587,8 +588,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                 tbatch[b & 1] += gridDim.x;
                 if (rt == 0) {
                     const long long t0 = clock64();
-                    while (ld_acquire_u32(bar + (b & 1)) < tbatch[b & 1])
+                    while (ld_acquire_u32(bar + (b & 1)) < tbatch[b & 1]) {
+                        __nanosleep(40);   // the pass warps of this SM need the issue slots
                         if (clock64() - t0 > 8000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); __trap(); }
+                    }
                 }
                 named_sync(BAR_RES, PR_THREADS);
                 QPROF(6);
