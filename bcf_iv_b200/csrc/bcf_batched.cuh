@@ -136,12 +136,11 @@ __device__ __forceinline__ void unpack8(uint2 v, int (&out)[8])
 // the loads of the next tree are in flight while this one is processed.
 __device__ __forceinline__ void keys_load(const Dev& d, const CurInfo& ci, int tree, int64_t gb, uint2& sl, uint4& bn)
 {
-    // streamed once per sweep: keep them out of L1 (L2 only), which then holds the few register spills of the kernel
-    sl = __ldcg(reinterpret_cast<const uint2*>(d.slots + (int64_t)tree * d.n_pad + gb));
+    sl = *reinterpret_cast<const uint2*>(d.slots + (int64_t)tree * d.n_pad + gb);
     if (ci.birth) {
-        if (ci.is16) bn = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ci.bins) + gb));
+        if (ci.is16) bn = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ci.bins) + gb);
         else {
-            const uint2 b = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(ci.bins) + gb));
+            const uint2 b = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(ci.bins) + gb);
             bn.x = b.x; bn.y = b.y;
         }
     }
@@ -288,7 +287,7 @@ __device__ __forceinline__ void batch_tile(BatchSmem& sm, const Dev& d, const Ba
 // Stage the batch that starts at tree `first`: compact copies of up to NB candidate trees with their proposals, then
 // (thread 0) how many of them form the batch.  Reads only what was final before the sweep started.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ inline void stage_big(BatchSmem& sm, BatchStage& B, const Dev& d, const TreeRec* trees)
+__device__ __forceinline__ void stage_big(BatchSmem& sm, BatchStage& B, const Dev& d, const TreeRec* trees)
 {
     const int t = threadIdx.x;
     load_tree(&sm.big.tr, &trees[B.first]);
@@ -307,7 +306,7 @@ __device__ inline void stage_big(BatchSmem& sm, BatchStage& B, const Dev& d, con
 }
 // A big batch keeps its full tree in BatchSmem::big, which the batch in flight may still need: stage_big() is
 // called separately, once that stage is free.
-__device__ inline void stage_batch(BatchSmem& sm, BatchStage& B, const Dev& d, const TreeRec* trees, int first)
+__device__ __forceinline__ void stage_batch(BatchSmem& sm, BatchStage& B, const Dev& d, const TreeRec* trees, int first)
 {
     const int t = threadIdx.x;
     const int f = (d.f[1].ntree > 0 && first >= d.f[1].tree0) ? 1 : 0;
@@ -375,7 +374,7 @@ __device__ inline void stage_batch(BatchSmem& sm, BatchStage& B, const Dev& d, c
 }
 
 // clear the pass tables of the batch about to be accumulated
-__device__ inline void begin_batch(BatchSmem& sm, const BatchStage& B)
+__device__ __forceinline__ void begin_batch(BatchSmem& sm, const BatchStage& B)
 {
     const int t = threadIdx.x;
     if (B.big) {
@@ -389,7 +388,7 @@ __device__ inline void begin_batch(BatchSmem& sm, const BatchStage& B)
 }
 
 // CTA tables -> global totals / cross counts (integer REDs: order-independent).  After a __syncthreads().
-__device__ inline void flush_batch(BatchSmem& sm, const BatchStage& B, long long* totals, long long* cross)
+__device__ __forceinline__ void flush_batch(BatchSmem& sm, const BatchStage& B, long long* totals, long long* cross)
 {
     const int t = threadIdx.x;
     if (B.big) {
@@ -416,7 +415,7 @@ __device__ inline void flush_batch(BatchSmem& sm, const BatchStage& B, long long
     }
 }
 
-__device__ inline void store_small(TreeRec* dst, const TreeSmall& tr, int t)   // one warp, t = lane
+__device__ __forceinline__ void store_small(TreeRec* dst, const TreeSmall& tr, int t)   // one warp, t = lane
 {
     if (t < 2 * KB) {
         dst->parent[t] = tr.parent[t]; dst->left[t] = tr.left[t]; dst->right[t] = tr.right[t]; dst->var[t] = tr.var[t];
@@ -460,14 +459,15 @@ struct ChainConsts { double s1, s0, rs1, rs0, phi1, phi0, log_tau; };
 struct ChainPrev {                       // the previous batch, when its update is not in the statistics (n = 0: none)
     int n;
     const int32_t* K;
-    const int16_t (*xoff)[NB];           // xoff[q][m]: first cross cell of (previous tree m, this batch's tree q)
+    const int16_t* xoff;                 // xoff[q * NT + m]: first cross cell of (previous tree m, this batch's tree q)
     const int4 (*DL)[2];
     const int32_t (*cq)[KB][2];
     const long long (*TL)[2][4];         // TL[m][g][limb]: total loss of previous tree m
 };
-template <class RS, class AP>
+// NT: trees per batch = warps walking the chain (named barriers 1..NT, NT * 32 threads each)
+template <int NT, class RS, class AP>
 __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, SmallStage* st, const int32_t* Kq,
-                                               const int16_t (*xoff)[NB], RS& rs, AP& ap, int32_t (*cq)[KB][2],
+                                               const int16_t* xoff, RS& rs, AP& ap, int32_t (*cq)[KB][2],
                                                const PreKey* pre, const ChainConsts& cc, const ChainPrev& pv, const Dev& d,
                                                TreeRec* newtrees, int32_t* bad)
 {
@@ -543,7 +543,7 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
                     if (kp == 1) { na0 = x0; na1 = x1; } else if (kp == 2) { nb0 = x0; nb1 = x1; } else if (kp == 3) { nc0 = x0; nc1 = x1; }
                 }
             }
-            if (barid > 0) asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(NB * 32) : "memory");
+            if (barid > 0) asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(NT * 32) : "memory");
             if (l < K) {
                 const int4 z0 = DLm[0][0], z1 = DLm[0][1];
                 wa0 -= (long long)z0.x * nz0; wa1 -= (long long)z0.y * nz0; wa2 -= (long long)z0.z * nz0;
@@ -589,7 +589,7 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
                     const int Km = pv.K[m];
                     const int4 (*DLm)[2] = &pv.DL[m * KB];
                     if (ll >= 1) {
-                        const int xb = pv.xoff[q][m] + (ll - 1);
+                        const int xb = pv.xoff[q * NT + m] + (ll - 1);
                         int nz0 = cc0, nz1 = cc1;
                         for (int kp = 1; kp < Km; ++kp) {
                             const int x0 = (int)rs.x[xb + (kp - 1) * stride][0], x1 = (int)rs.x[xb + (kp - 1) * stride][1];
@@ -683,7 +683,7 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
                 if (fxbad) *bad = ERR_FX_RANGE;
                 CPROF(4);
                 __threadfence_block();
-                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
+                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NT * 32) : "memory");
                 CPROF(5);
                 // ---- bookkeeping nobody waits for ----
                 const double n1 = pooled ? pkp.k1 : pk.k1, n0 = pooled ? pkp.k0 : pk.k0;
@@ -751,10 +751,10 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
                     }
                 }
             } else if (active && q > m) {
-                fold(&ap.DL[m * KB], Kq[m], xoff[q][m], cq[m], 1 + m);
+                fold(&ap.DL[m * KB], Kq[m], xoff[q * NT + m], cq[m], 1 + m);
                 if (q == m + 1) CPROF(7);
             } else {
-                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NB * 32) : "memory");
+                asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NT * 32) : "memory");
             }
         }
     }
@@ -764,7 +764,7 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
 // Observation shards: CTA 0 stores this rank's reduced words of the batch into its mailbox on every peer and releases
 // sequence number `seq` there (see PeerDev).  Layout: totals words packed (tree q, word w) -> q * KB * 8 + w (a big
 // tree: its K * 8 words), then the cross counts from MAIL_TOT_WORDS on.
-__device__ inline void peer_push_batch(const BatchStage& B, const Dev& d, const long long* totals, const long long* cross,
+__device__ __forceinline__ void peer_push_batch(const BatchStage& B, const Dev& d, const long long* totals, const long long* cross,
                                        int slot, unsigned long long seq)
 {
     const int t = threadIdx.x;
@@ -796,7 +796,7 @@ __device__ __forceinline__ long long peer_sum(const Dev& d, int slot, int idx)
 // ---------------------------------------------------------------------------------------------------------------
 // After the grid barrier: replay the batch's decisions in tree order from the reduced integers.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d, const Scalars& sc, TreeRec* newtrees,
+__device__ __forceinline__ void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d, const Scalars& sc, TreeRec* newtrees,
                                      const long long* totals, const long long* cross, int slot)
 {
     const bool sharded = d.pr.nranks > 1;
@@ -877,7 +877,7 @@ __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d,
     if ((t >> 5) < NB) {
         ChainConsts cc{s1, s0, rs1, rs0, phi1, phi0, log_tau};
         ChainPrev pv{0, nullptr, nullptr, nullptr, nullptr, nullptr};
-        decision_chain(t >> 5, t & 31, nb, B.first, B.st, B.K, B.xoff, rs, sm.ap, sm.cq, pre, cc, pv, d, newtrees, &sm.bad);
+        decision_chain<NB>(t >> 5, t & 31, nb, B.first, B.st, B.K, &B.xoff[0][0], rs, sm.ap, sm.cq, pre, cc, pv, d, newtrees, &sm.bad);
     }
     __syncthreads();
     if (t == 0) { sm.ap.n = nb; sm.ap.first = B.first; sm.ap.forest = B.forest; }
@@ -888,7 +888,7 @@ __device__ inline void resolve_batch(BatchSmem& sm, BatchStage& B, const Dev& d,
 }
 
 // proposals of sweep `sweep` for the trees j = blockIdx.x, + gridDim.x, ... from their (visible) HBM records
-__device__ inline void propose_all_b(BatchSmem& sm, const Dev& d, const TreeRec* trees, uint32_t sweep)
+__device__ __forceinline__ void propose_all_b(BatchSmem& sm, const Dev& d, const TreeRec* trees, uint32_t sweep)
 {
     for (int j = blockIdx.x; j < d.T; j += gridDim.x) {
         const ForestDev& F = d.f[(d.f[1].ntree > 0 && j >= d.f[1].tree0) ? 1 : 0];
@@ -972,13 +972,13 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
             const bool do_apply = sm.ap.n > 0;
             const bool fswitch = has_mod && first == tmod && first > 0;
             // the CTA tables hold 32-bit words: at most FLUSH_TILES tiles between two flushes (HBM mode: many tiles)
-            for (int lt0 = 0; lt0 < ntl; lt0 += FLUSH_TILES) {
-                const int lt1 = min(ntl, lt0 + FLUSH_TILES);
+            for (int lt0 = 0; lt0 < ntl; lt0 += (RES ? (1 << 30) : FLUSH_TILES)) {   // resident: an SM holds < 48 tiles, one chunk
+                const int lt1 = RES ? ntl : min(ntl, lt0 + FLUSH_TILES);
                 for (int lt = lt0 + wib; lt < lt1; lt += wpb) {
                     if (lt == pad_a || lt == pad_b) batch_tile<true, RES>(sm, d, rs, tile0, lt, lane, &B, do_apply, fswitch);
                     else batch_tile<false, RES>(sm, d, rs, tile0, lt, lane, &B, do_apply, fswitch);
                 }
-                if (lt1 < ntl) {
+                if (!RES && lt1 < ntl) {   // (compile-time dead in the resident kernel: one call site of the flush there)
                     __syncthreads();
                     flush_batch(sm, B, totals, cross);
                     __syncthreads();

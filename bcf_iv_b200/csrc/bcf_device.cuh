@@ -241,16 +241,19 @@ __host__ __device__ inline double limbs_to_double(long long w0, long long w1, lo
 //   K >  KREG keys : one table of 32-bit words per (key, group): count + four 16-bit limbs, native ATOMS.ADD.32
 //                    (addresses are spread when a tree has many leaves).
 constexpr int NWARP_MAX = 16;
-union StatTab {
-    long long w[NWARP_MAX][KREG][2][4];     // (count, limb0, limb1, limb2), 21-bit limbs
+template <int NW>
+union StatTabT {
+    long long w[NW][KREG][2][4];            // (count, limb0, limb1, limb2), 21-bit limbs
     unsigned int d[KEYS][2][8];             // (count, m0, m1, m2, m3), 16-bit limbs; 3 words of padding
 };
+using StatTab = StatTabT<NWARP_MAX>;        // kernels with 16 warps; the pipelined kernel (28 pass warps) uses StatTabT<32>
 constexpr int STATTAB_WORDS64 = (int)(sizeof(StatTab) / 8);
 constexpr int ROWSUM_WORDS = KREG * 8;   // (key, group, word) sums over the warps' tables
 
 // split a partial sum (|s| < 2^63) into the three words of the global representation and add them, reduced over the
 // warp, to row `row` of the warp's private table
-__device__ __forceinline__ void warp_add_limbs(StatTab& tab, int warp, int row, int g, int lane, long long s, int cnt)
+template <class Tab>
+__device__ __forceinline__ void warp_add_limbs(Tab& tab, int warp, int row, int g, int lane, long long s, int cnt)
 {
     int l0 = (int)(s & 0x1FFFFF), l1 = (int)((s >> LIMB_BITS) & 0x1FFFFF), l2 = (int)(s >> (2 * LIMB_BITS));
     l0 = __reduce_add_sync(0xffffffffu, l0);
@@ -268,7 +271,8 @@ __device__ __forceinline__ void warp_add_limbs(StatTab& tab, int warp, int row, 
 //              recovered by subtraction when the CTA flushes: integer sums are exact).  Only the last key of a
 //              birth proposal (the would-be right child) needs its count; every other count is cached in the tree.
 //   K >  KREG: native 32-bit shared atomics per observation.
-__device__ __forceinline__ void accum_tile(StatTab& tab, const int (&key)[8], const long long (&R)[8], int g, int K,
+template <class Tab>
+__device__ __forceinline__ void accum_tile(Tab& tab, const int (&key)[8], const long long (&R)[8], int g, int K,
                                            bool count_last, int lane, int warp)
 {
     if (K <= KREG) {
@@ -305,7 +309,8 @@ __device__ __forceinline__ void accum_tile(StatTab& tab, const int (&key)[8], co
     }
 }
 // word q (0 count, 1..3 the 21-bit limbs of the global representation) of entry (k, g), summed over the CTA
-__device__ __forceinline__ long long stat_word(const StatTab& tab, int K, int nwarps, int k, int g, int q)
+template <class Tab>
+__device__ __forceinline__ long long stat_word(const Tab& tab, int K, int nwarps, int k, int g, int q)
 {
     if (K <= KREG) {
         long long v = 0;
@@ -328,7 +333,8 @@ __device__ __forceinline__ long long stat_word(const StatTab& tab, int K, int nw
     return (long long)(V >> (2 * LIMB_BITS));
 }
 // plain sum over the warps' tables (moments pass: rows are independent quantities)
-__device__ __forceinline__ long long table_word(const StatTab& tab, int nwarps, int row, int g, int q)
+template <class Tab>
+__device__ __forceinline__ long long table_word(const Tab& tab, int nwarps, int row, int g, int q)
 {
     long long v = 0;
     for (int w = 0; w < nwarps; ++w) v += tab.w[w][row][g][q];

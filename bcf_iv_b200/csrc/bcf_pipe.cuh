@@ -19,8 +19,10 @@
 
 namespace bcf {
 
-constexpr int PP_WARPS = 16;                         // pass warps
-constexpr int PR_WARPS = NB;                         // resolve warps: one per tree of a batch
+constexpr int PNB = 4;                               // trees per batch of this engine (its syncs are hidden: small batches
+                                                     // mean less cross-counting; and 28 warps hold an SM's 27 tiles in ONE round)
+constexpr int PP_WARPS = 28;                         // pass warps
+constexpr int PR_WARPS = PNB;                        // resolve warps: one per tree of a batch
 constexpr int PP_THREADS = PP_WARPS * 32, PR_THREADS = PR_WARPS * 32;
 constexpr int PIPE_THREADS = PP_THREADS + PR_THREADS;   // 768
 constexpr int PMAXC = 12;                            // columns ((tree, key >= 1) pairs) of a batch
@@ -28,12 +30,12 @@ constexpr int PXW = 72;                              // cells between trees of o
 constexpr int PXX = PMAXC * PMAXC;                   // cells between two consecutive batches
 constexpr int PXCAP = PXW + PXX;
 constexpr int PIPE_XSTRIDE = 512;                    // words per batch slot of Dev::cross (>= 2 * PXCAP)
-constexpr int PIPE_BYTES_PER_TILE = TILE * (8 + 8) + 2 * (NB / 2) * TILE;   // R, G, nibble-packed keys of two batches
+constexpr int PIPE_BYTES_PER_TILE = TILE * (8 + 8) + 2 * (PNB / 2) * TILE;   // R, G, nibble-packed keys of two batches
 static_assert(2 * PXCAP <= PIPE_XSTRIDE, "cross-count slot too small");
 
 // registers per thread: 768 x 80 at launch; the role section re-splits the CTA's OWN
 // allocation (the pool of setmaxnreg is per CTA): 512 x 72 + 256 x 96 = 61440
-constexpr int PIPE_REGS_BASE = 80, PIPE_REGS_PASS = 64, PIPE_REGS_RESOLVE = 112;
+constexpr int PIPE_REGS_BASE = 64, PIPE_REGS_PASS = 56, PIPE_REGS_RESOLVE = 112;
 enum { BAR_H1 = 9, BAR_H2 = 11, BAR_PASS = 13, BAR_RES = 14 };   // named barriers 1..8 belong to the decision chain
 
 struct __align__(16) TMeta {                         // what the pass needs to know about a tree, per sweep
@@ -46,25 +48,25 @@ struct __align__(16) TMeta {                         // what the pass needs to k
 struct PipePlan {
     int32_t first, nb, forest, nprev;                // nprev: trees of the previous batch not yet applied (0 or its nb)
     int32_t ncell_w, ncell, ncol, ncolp;
-    int32_t K[NB], Kp[NB];
-    uint8_t colbase[NB], colbasep[NB];
-    int16_t cbase[NB], cbasep[NB];                   // first cell of tree q: inside the batch / against the previous batch
-    int16_t xoff[NB][NB];                            // [q][m < q]       cells inside the batch
-    int16_t xoffp[NB][NB];                           // [q][m in prev]   cells against the previous batch
+    int32_t K[PNB], Kp[PNB];
+    uint8_t colbase[PNB], colbasep[PNB];
+    int16_t cbase[PNB], cbasep[PNB];                   // first cell of tree q: inside the batch / against the previous batch
+    int16_t xoff[PNB][PNB];                            // [q][m < q]       cells inside the batch
+    int16_t xoffp[PNB][PNB];                           // [q][m in prev]   cells against the previous batch
     uint8_t cell_c1[PXCAP], cell_c2[PXCAP];          // columns of a cell: 0.. this batch, PMAXC.. previous batch
-    CurInfo ci[NB];
+    CurInfo ci[PNB];
 };
 
 struct __align__(16) PipeApply {
     int32_t n, first, forest, pad_;
-    int32_t changed[NB], off[NB];
-    ApRow T[2][NB * KB];
-    int4 DL[NB * KB][2];
-    long long TL[NB][2][4];
-    uint8_t NS[NB * KB];
+    int32_t changed[PNB], off[PNB];
+    ApRow T[2][PNB * KB];
+    int4 DL[PNB * KB][2];
+    long long TL[PNB][2][4];
+    uint8_t NS[PNB * KB];
 };
-struct PipeRS { long long tot[NB][KB][2][4]; int x[PXCAP][2]; };
-struct PipeAcc { unsigned int btab[NB][KB][2][4]; unsigned int totr[2][4]; unsigned int xtab[PXCAP][2]; };
+struct PipeRS { long long tot[PNB][KB][2][4]; int x[PXCAP][2]; };
+struct PipeAcc { unsigned int btab[PNB][KB][2][4]; unsigned int totr[2][4]; unsigned int xtab[PXCAP][2]; };
 
 struct PipeSmem {
     // scratch of propose_stage() (same names as StepShared; the trees here have <= KB leaves)
@@ -75,13 +77,13 @@ struct PipeSmem {
     int32_t bad;
     int32_t anybig;
     SmallStage pst;                                  // stage of the proposals
-    SmallStage st[NB];                               // resolve role: the batch's trees
+    SmallStage st[PNB];                               // resolve role: the batch's trees
     PipePlan plan[2];
     PipeApply ap[2];
-    int32_t cq[2][NB][KB][2];
+    int32_t cq[2][PNB][KB][2];
     PipeRS rs;
-    PreKey pre[NB * (KB + 1)];
-    union { PipeAcc acc; StatTab tab; double red[2 * PIPE_THREADS]; } p;
+    PreKey pre[PNB * (KB + 1)];
+    union { PipeAcc acc; StatTabT<32> tab; double red[2 * PIPE_THREADS]; } p;
     uint8_t colb[PP_WARPS][2 * PMAXC][32];
 };
 constexpr size_t PIPE_SMEM_BYTES = (sizeof(PipeSmem) + 15) / 16 * 16;
@@ -109,14 +111,14 @@ __device__ inline void pipe_plan(PipeSmem& sm, PipePlan& P, const PipePlan* prev
         const int l = pt;
         const int f = (d.f[1].ntree > 0 && first >= d.f[1].tree0) ? 1 : 0;
         const int fend = f ? d.T : (d.f[1].ntree > 0 ? d.f[1].tree0 : d.T);
-        const int ncand = min(NB, fend - first);
+        const int ncand = min(PNB, fend - first);
         TMeta m;
         m.K = 1; m.L = 1; m.birth = 0; m.sx = 0; m.cut = 0; m.is16 = 0; m.pad_ = 0; m.bins = nullptr;
         if (l < ncand) m = meta[first + l];
         const int c = (l < ncand) ? (int)m.K - 1 : 0;            // own columns
         int cb = c;                                                 // inclusive prefix of the columns
 #pragma unroll
-        for (int sft = 1; sft < NB; sft <<= 1) { const int v = __shfl_up_sync(FULL, cb, sft); if (l >= sft) cb += v; }
+        for (int sft = 1; sft < PNB; sft <<= 1) { const int v = __shfl_up_sync(FULL, cb, sft); if (l >= sft) cb += v; }
         const int colbase = cb - c;
         const unsigned okm = __ballot_sync(FULL, l < ncand && cb <= PMAXC);
         const int nb = __ffs(~okm) - 1;                             // leading trees whose columns still fit
@@ -124,18 +126,18 @@ __device__ inline void pipe_plan(PipeSmem& sm, PipePlan& P, const PipePlan* prev
         const int wcells = in ? c * colbase : 0;                    // cells against earlier columns of this batch
         int wb = wcells;
 #pragma unroll
-        for (int sft = 1; sft < NB; sft <<= 1) { const int v = __shfl_up_sync(FULL, wb, sft); if (l >= sft) wb += v; }
+        for (int sft = 1; sft < PNB; sft <<= 1) { const int v = __shfl_up_sync(FULL, wb, sft); if (l >= sft) wb += v; }
         const int base = wb - wcells;
-        const int ncell_w = __shfl_sync(FULL, wb, NB - 1);
+        const int ncell_w = __shfl_sync(FULL, wb, PNB - 1);
         const int ncol = __shfl_sync(FULL, in ? cb : 0, max(nb - 1, 0));
         const int np = prev ? prev->nb : 0, ncolp = prev ? prev->ncol : 0;
         const int xcells = in ? c * ncolp : 0;                      // cells against the previous batch's columns
         int xb = xcells;
 #pragma unroll
-        for (int sft = 1; sft < NB; sft <<= 1) { const int v = __shfl_up_sync(FULL, xb, sft); if (l >= sft) xb += v; }
+        for (int sft = 1; sft < PNB; sft <<= 1) { const int v = __shfl_up_sync(FULL, xb, sft); if (l >= sft) xb += v; }
         const int basep = ncell_w + xb - xcells;
-        const int ncell = ncell_w + __shfl_sync(FULL, xb, NB - 1);
-        if (l < NB) {
+        const int ncell = ncell_w + __shfl_sync(FULL, xb, PNB - 1);
+        if (l < PNB) {
             P.K[l] = in ? (int)m.K : 1;
             P.colbase[l] = (uint8_t)colbase;
             P.cbase[l] = (int16_t)base; P.cbasep[l] = (int16_t)basep;
@@ -152,8 +154,8 @@ __device__ inline void pipe_plan(PipeSmem& sm, PipePlan& P, const PipePlan* prev
     }
     named_sync(BAR_PASS, PP_THREADS);
     {   // offsets of every pair and the two columns of every cell, from the closed form
-        if (pt < NB * NB) {
-            const int q = pt / NB, m = pt % NB;
+        if (pt < PNB * PNB) {
+            const int q = pt / PNB, m = pt % PNB;
             P.xoff[q][m] = (int16_t)(P.cbase[q] + (P.K[q] - 1) * (int)P.colbase[m]);
             P.xoffp[q][m] = (int16_t)(P.cbasep[q] + (P.K[q] - 1) * (int)P.colbasep[m]);
         }
@@ -182,9 +184,9 @@ __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, const PipePlan& P,
     const int g = tile < d.trt_tiles ? 1 : 0;
     const int64_t gb = (int64_t)tile * TILE + lane * 8;
     const uint32_t toff = (uint32_t)lt * (TILE * 8u);
-    const uint32_t kbase = rs.keys + (uint32_t)lt * (uint32_t)(2 * (NB / 2) * TILE) + (uint32_t)lane * 8u;
-    const uint32_t kw = kbase + (uint32_t)parity * (uint32_t)((NB / 2) * TILE);
-    const uint32_t kr = kbase + (uint32_t)(parity ^ 1) * (uint32_t)((NB / 2) * TILE);
+    const uint32_t kbase = rs.keys + (uint32_t)lt * (uint32_t)(2 * (PNB / 2) * TILE) + (uint32_t)lane * 8u;
+    const uint32_t kw = kbase + (uint32_t)parity * (uint32_t)((PNB / 2) * TILE);
+    const uint32_t kr = kbase + (uint32_t)(parity ^ 1) * (uint32_t)((PNB / 2) * TILE);
     long long R[8];
     uint2 sl_n = make_uint2(0u, 0u);
     uint4 bn_n = make_uint4(0u, 0u, 0u, 0u);
@@ -266,8 +268,8 @@ __device__ __forceinline__ void pipe_apply_tile(const PipeApply& ap, const Dev& 
     const int g = tile < d.trt_tiles ? 1 : 0;
     const int64_t gb = (int64_t)tile * TILE + lane * 8;
     const uint32_t toff = (uint32_t)lt * (TILE * 8u);
-    const uint32_t kr = rs.keys + (uint32_t)lt * (uint32_t)(2 * (NB / 2) * TILE) + (uint32_t)lane * 8u +
-                        (uint32_t)parity * (uint32_t)((NB / 2) * TILE);
+    const uint32_t kr = rs.keys + (uint32_t)lt * (uint32_t)(2 * (PNB / 2) * TILE) + (uint32_t)lane * 8u +
+                        (uint32_t)parity * (uint32_t)((PNB / 2) * TILE);
     long long R[8];
     double G[8];
     res_ld8i(rs.R + toff, lane, R);
@@ -327,12 +329,12 @@ __device__ inline void pipe_flush(PipeSmem& sm, const PipePlan& P, long long* to
 // ---------------------------------------------------------------------------------------------------------------
 // resolve role
 // ---------------------------------------------------------------------------------------------------------------
-// compact copies of the (up to NB) trees starting at `first`, with proposals and leaf normals: warp q takes tree q
+// compact copies of the (up to PNB) trees starting at `first`, with proposals and leaf normals: warp q takes tree q
 __device__ inline void pipe_stage_trees(PipeSmem& sm, const Dev& d, const TreeRec* trees, int first, int rw, int l)
 {
     const int f = (d.f[1].ntree > 0 && first >= d.f[1].tree0) ? 1 : 0;
     const int fend = f ? d.T : (d.f[1].ntree > 0 ? d.f[1].tree0 : d.T);
-    if (rw >= min(NB, fend - first)) return;
+    if (rw >= min(PNB, fend - first)) return;
     const TreeRec* src = &trees[first + rw];
     SmallStage& S = sm.st[rw];
     if (l < 2 * KB) {
@@ -408,8 +410,8 @@ __device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, cons
     {
         ChainConsts cc{s1, s0, 1.0 / s1, 1.0 / s0, phi1, phi0, log(tau)};
         const PipeApply& app = sm.ap[(b & 1) ^ 1];
-        ChainPrev pv{P.nprev, P.Kp, P.xoffp, app.DL, sm.cq[(b & 1) ^ 1], app.TL};
-        decision_chain(rt >> 5, rt & 31, nb, P.first, sm.st, P.K, P.xoff, rs, sm.ap[b & 1], sm.cq[b & 1], sm.pre, cc, pv, d,
+        ChainPrev pv{P.nprev, P.Kp, &P.xoffp[0][0], app.DL, sm.cq[(b & 1) ^ 1], app.TL};
+        decision_chain<PNB>(rt >> 5, rt & 31, nb, P.first, sm.st, P.K, &P.xoff[0][0], rs, sm.ap[b & 1], sm.cq[b & 1], sm.pre, cc, pv, d,
                        newtrees, &sm.bad);
     }
     named_sync(BAR_RES, PR_THREADS);
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
         // ---- epilogue: moments of (y, Gc, Gm) ----
         if (is_pass) {
             long long* tb = reinterpret_cast<long long*>(&sm.p.tab);
-            for (int i = pt; i < STATTAB_WORDS64; i += PP_THREADS) tb[i] = 0;
+            for (int i = pt; i < (int)(sizeof(sm.p.tab) / 8); i += PP_THREADS) tb[i] = 0;
         }
         __syncthreads();
         if (is_pass)

@@ -547,7 +547,8 @@ __device__ __forceinline__ void step_tile(StepShared& sm, const CurInfo& ci, con
 }
 
 // moments of 8 observations into the warp's table rows 0..5 (words 1..3 = limbs); padding rows have y = G = 0
-__device__ __forceinline__ void moments8(StatTab& tab, const double (&y)[8], const double (&gc)[8],
+template <class Tab>
+__device__ __forceinline__ void moments8(Tab& tab, const double (&y)[8], const double (&gc)[8],
                                          const double (&gm)[8], int g, int lane, int& bad)
 {
     const int warp = threadIdx.x >> 5;

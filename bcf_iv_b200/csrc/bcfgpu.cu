@@ -116,6 +116,7 @@ struct bcfgpu_handle {
     int coop_grid = 0;
     int res_ntl = 0;                  // tiles per CTA of the shared-memory-resident kernels (0 = state in HBM)
     int kernel = 0;                   // persistent kernel in use: 1 k_persistent, 2 k_resident, 3 k_batched, 4 k_pipe (+ k_batched)
+    int fallback_kernel = 3;          // what k_pipe hands a sweep with a wide tree to: 3 (k_batched resident) or 5 (HBM)
     size_t pipe_smem = 0;             // dynamic shared memory of k_pipe (kernel 4; res_smem is then k_batched's)
     int* d_done = nullptr;            // sweeps completed by the last k_pipe launch
     size_t res_smem = 0;
@@ -1225,7 +1226,8 @@ static int select_kernel(bcfgpu_handle* h)
                 }
             }
             // the pipelined kernel on top of it (the batched one then serves the sweeps that hold a wide tree)
-            if (h->kernel == 3 && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && h->nranks == 1) {
+            if ((h->kernel == 3 || h->kernel == 5) && may_reside && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && h->nranks == 1) {
+                h->fallback_kernel = h->kernel;
                 const size_t needp = PIPE_SMEM_BYTES + (size_t)ntl_max * PIPE_BYTES_PER_TILE + (size_t)h->T * sizeof(TMeta) + 16;
                 if (fits((const void*)k_pipe, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; }
                 else if (h->cfg.engine == BCFGPU_ENGINE_PIPELINED)
@@ -1277,7 +1279,8 @@ static int run_persistent(bcfgpu_handle* h, int total)
                 int one = 1;
                 CK(cudaMemsetAsync(bar, 0, 16, h->stream));
                 void* a2[] = {(void*)&d, (void*)&one, (void*)&bar, (void*)&ntl};
-                CK(cudaLaunchCooperativeKernel((const void*)k_batched<true>, dim3(h->coop_grid), dim3(PTHREADS), a2, h->res_smem, h->stream));
+                CK(cudaLaunchCooperativeKernel(h->fallback_kernel == 3 ? (const void*)k_batched<true> : (const void*)k_batched<false>, dim3(h->coop_grid),
+                                               dim3(PTHREADS), a2, h->res_smem, h->stream));
                 h->launches++;
                 done += 1;
             }
