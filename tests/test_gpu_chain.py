@@ -171,3 +171,18 @@ def test_batched_engine_with_the_state_in_hbm(monkeypatch):
     o = oracle_sampler(pr, max_leaves=128, **kw)
     o.sweeps(12)
     _compare_state(b, o, pr)
+
+
+@pytest.mark.parametrize("engine", [4, 5])
+@pytest.mark.parametrize("ntree", [(7, 0), (5, 3), (1, 1), (13, 6)])
+def test_odd_forest_sizes(engine, ntree):
+    """Forests that do not fill the engines' batches (and no tau forest at all): batch boundaries, forest switch."""
+    pr = make_problem(n=900, p=8, seed=23)
+    kw = dict(seed=3, ntree_con=ntree[0], ntree_mod=ntree[1])
+    g = gpu_sampler(pr, engine=engine, **kw)
+    o = oracle_sampler(pr, max_leaves=128, **kw)
+    for k in (1, 7):
+        g.run(k, 0)
+        o.sweeps(k)
+        _compare_state(g, o, pr)
+    assert g.verify_leaf_cache() == 0
