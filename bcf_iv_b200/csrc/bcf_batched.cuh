@@ -469,11 +469,13 @@ template <int NT, class RS, class AP>
 __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, SmallStage* st, const int32_t* Kq,
                                                const int16_t* xoff, RS& rs, AP& ap, int32_t (*cq)[KB][2],
                                                const PreKey* pre, const ChainConsts& cc, const ChainPrev& pv, const Dev& d,
-                                               TreeRec* newtrees, int32_t* bad)
+                                               TreeRec* newtrees, int32_t* bad, long long* trc = nullptr)
 {
     {
         const unsigned FULL = 0xffffffffu;
         const int q = w;
+#define CTRACE(e) do { if (trc != nullptr && l == 0) trc[w * 8 + (e)] = clock64(); } while (0)
+        CTRACE(0);
         const bool active = q < nb;
         const int qq = active ? q : 0;
         SmallStage& S = st[qq];
@@ -624,11 +626,13 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
                 else { wa0 -= a0 - s0; wa1 -= a1 - s1_; wa2 -= a2 - s2_; wb0 -= b0 - u0; wb1 -= b1 - u1; wb2 -= b2 - u2; }
             }
         }
+        CTRACE(1);
         const bool cprof = d.prof != nullptr && blockIdx.x == 0 && l == 0;
         long long ct = 0;
 #define CPROF(k) do { if (cprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[8 + (k)], (unsigned long long)(now_ - ct)); ct = now_; } } while (0)
         for (int m = 0; m < nb; ++m) {
             if (active && q == m) {
+                CTRACE(2);
                 if (cprof) ct = clock64();
                 // exact integer -> double, as limbs_to_double does
                 const __int128 v0 = limbs_to_i128(wa0, wa1, wa2), v1 = limbs_to_i128(wb0, wb1, wb2);
@@ -684,7 +688,7 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
                 CPROF(4);
                 __threadfence_block();
                 asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NT * 32) : "memory");
-                CPROF(5);
+                CPROF(5); CTRACE(3);
                 // ---- bookkeeping nobody waits for ----
                 const double n1 = pooled ? pkp.k1 : pk.k1, n0 = pooled ? pkp.k0 : pk.k0;
                 if (l < K) ap.NS[off + l] = (uint8_t)ns;
@@ -750,15 +754,17 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
                         ap.TL[q][1][0] = v0; ap.TL[q][1][1] = v1; ap.TL[q][1][2] = v2;
                     }
                 }
+                CTRACE(4);
             } else if (active && q > m) {
                 fold(&ap.DL[m * KB], Kq[m], xoff[q * NT + m], cq[m], 1 + m);
-                if (q == m + 1) CPROF(7);
             } else {
                 asm volatile("bar.arrive %0, %1;" ::"r"(1 + m), "r"(NT * 32) : "memory");
             }
         }
+        CTRACE(5);
     }
 #undef CPROF
+#undef CTRACE
 }
 
 // Observation shards: CTA 0 stores this rank's reduced words of the batch into its mailbox on every peer and releases

@@ -2,15 +2,19 @@
 //
 // In the batched engine a batch costs  pass + flush + grid barrier + decision chain, one after the other, and during
 // the last three almost every warp of the SM idles.  Here the CTA is split in two roles:
-//   * 16 PASS warps stream the SM's observations:  STATS(b)  ->  flush + arrive at grid barrier b  ->  APPLY(b-1);
-//   * 8 RESOLVE warps (one per tree of a batch) wait for grid barrier b, stage the reduced statistics, walk the
-//     decision chain of batch b and publish its apply tables.
+//   * 27 TILE warps stream the SM's observations (27 tiles of 256 at the headline size: one round):
+//         STATS(b)  ->  APPLY(b-1)  ->  STATS(b+1) ...
+//   * 1 UTILITY warp does everything of the pass that is not per observation: it flushes batch b's CTA tables to the
+//     grid-wide ones and arrives at grid barrier b, plans batch b+1 and stages its trees;
+//   * 4 CHAIN warps (one per tree of a batch) wait for grid barrier b, fetch the reduced statistics, walk the decision
+//     chain of batch b and publish its apply tables.
 // STATS(b) therefore runs while batch b-1 is still being decided: it sees the residual WITHOUT batch b-1's update.
 // That is repaired exactly like the dependencies inside a batch (bcf_batched.cuh): the pass also counts, per pair
 // (tree m of batch b-1, tree q of batch b), how many observations fall in each pair of keys, and the chain folds
 // D_m * N into tree q's integer sums before deciding it.  Still bit-identical to the tree-at-a-time chain.
-// CTA-local hand-shakes are named barriers (H1(b): pass -> resolve "batch b is flushed", H2(b): resolve -> pass
-// "batch b's tables are ready"); the grid barrier is arrived at by the pass role and waited for by the resolve role.
+// CTA-local hand-shakes are named barriers (S(b): tile warps -> utility "statistics of b complete"; PL(b): utility ->
+// tile warps "plan of b ready"; H1(b): utility -> chain "batch b flushed, planned, staged"; H2(b): chain -> everybody
+// "batch b's tables are ready"); the grid barrier is arrived at by the utility warp and waited for by the chain warps.
 //
 // Only sweeps whose trees all have <= KB keys run here: when a wider tree shows up at the start of a sweep the kernel
 // parks the chain state and returns; the host runs that sweep with the batched engine and comes back.
@@ -21,8 +25,12 @@ namespace bcf {
 
 constexpr int PNB = 4;                               // trees per batch of this engine (its syncs are hidden: small batches
                                                      // mean less cross-counting; and 28 warps hold an SM's 27 tiles in ONE round)
-constexpr int PP_WARPS = 28;                         // pass warps
-constexpr int PR_WARPS = PNB;                        // resolve warps: one per tree of a batch
+constexpr int PP_WARPS = 28;                         // pass warps: PT_WARPS tile warps + the utility warp
+constexpr int PT_WARPS = PP_WARPS - 1;
+#ifndef PIPE_CHAIN_FIRST
+#define PIPE_CHAIN_FIRST 0
+#endif
+constexpr int PR_WARPS = PNB;                        // chain warps: one per tree of a batch
 constexpr int PP_THREADS = PP_WARPS * 32, PR_THREADS = PR_WARPS * 32;
 constexpr int PIPE_THREADS = PP_THREADS + PR_THREADS;   // 768
 constexpr int PMAXC = 12;                            // columns ((tree, key >= 1) pairs) of a batch
@@ -36,7 +44,10 @@ static_assert(2 * PXCAP <= PIPE_XSTRIDE, "cross-count slot too small");
 // registers per thread: 768 x 80 at launch; the role section re-splits the CTA's OWN
 // allocation (the pool of setmaxnreg is per CTA): 512 x 72 + 256 x 96 = 61440
 constexpr int PIPE_REGS_BASE = 64, PIPE_REGS_PASS = 56, PIPE_REGS_RESOLVE = 112;
-enum { BAR_H1 = 9, BAR_H2 = 11, BAR_PASS = 13, BAR_RES = 14 };   // named barriers 1..8 belong to the decision chain
+enum { BAR_S = 5, BAR_F = 8, BAR_H1 = 9, BAR_H2 = 11, BAR_PASS = 13, BAR_RES = 14 };   // 1..PNB: the decision chain
+constexpr int H1_THREADS = 32 + PR_THREADS;          // tile warp 0 arrives, chain warps wait
+constexpr int PT_THREADS = PT_WARPS * 32;
+constexpr int H2_THREADS = PT_THREADS + PR_THREADS;  // chain warps arrive, tile warps wait
 
 struct __align__(16) TMeta {                         // what the pass needs to know about a tree, per sweep
     const void* bins;                                // column of the proposed variable
@@ -76,14 +87,15 @@ struct PipeSmem {
     uint8_t nogflag[2 * KB];
     int32_t bad;
     int32_t anybig;
+    int32_t plan_ready, flushed;                      // batches planned + staged (utility warp) / flushed (tile warps), this sweep
     SmallStage pst;                                  // stage of the proposals
-    SmallStage st[PNB];                               // resolve role: the batch's trees
-    PipePlan plan[2];
+    SmallStage st[4][PNB];                            // the batch's trees (staged two batches ahead)
+    PipePlan plan[4];                                 // (planned two batches ahead)
     PipeApply ap[2];
     int32_t cq[2][PNB][KB][2];
     PipeRS rs;
     PreKey pre[PNB * (KB + 1)];
-    union { PipeAcc acc; StatTabT<32> tab; double red[2 * PIPE_THREADS]; } p;
+    union { PipeAcc acc[2]; StatTabT<32> tab; double red[2 * PIPE_THREADS]; } p;
     uint8_t colb[PP_WARPS][2 * PMAXC][32];
 };
 constexpr size_t PIPE_SMEM_BYTES = (sizeof(PipeSmem) + 15) / 16 * 16;
@@ -95,20 +107,41 @@ __device__ __forceinline__ void named_arrive(int id, int n)
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
+__device__ __forceinline__ int ld_acquire_cta_s32(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_s32(int* p, int v)
+{
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// one lane waits for a CTA-local progress counter to reach `target` (bounded: a logic error traps instead of hanging)
+__device__ __forceinline__ void pipe_wait_flag(const int* p, int target, int32_t* err, unsigned ns)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_cta_s32(p) < target) {
+        __nanosleep(ns);
+        if (clock64() - t0 > 8000000000ll) { atomicOr(err, ERR_BARRIER_TIMEOUT); __trap(); }
+    }
+}
+
 struct PipePtrs { uint32_t R, G, keys; };            // keys: [tile][parity][pair][TILE bytes]
 
 // ---------------------------------------------------------------------------------------------------------------
 // pass role
 // ---------------------------------------------------------------------------------------------------------------
-// Plan of the batch starting at `first`, by the pass role.  Cell layout (closed form, so nothing is enumerated
+// Plan of the batch starting at `first`, by ONE warp (the utility warp).  Cell layout (closed form, so nothing is enumerated
 // serially): tree q owns the cells  base_q + (K_q - 1) * c1 + (k - 1)  for every EARLIER column c1 of the batch
 // (c1 < colbase[q]) and, behind all of those, the cells against the previous batch's columns; hence
 //     xoff[q][m]  = base_q  + (K_q - 1) * colbase[m],        xoffp[q][m] = basep_q + (K_q - 1) * colbasep[m].
-__device__ inline void pipe_plan(PipeSmem& sm, PipePlan& P, const PipePlan* prev, const Dev& d, const TMeta* meta, int first, int pt)
+__device__ inline void pipe_plan(PipePlan& P, const PipePlan* prev, const Dev& d, const TMeta* meta, int first, int lane)
 {
-    if (pt < 32) {
+    {
         const unsigned FULL = 0xffffffffu;
-        const int l = pt;
+        const int l = lane;
         const int f = (d.f[1].ntree > 0 && first >= d.f[1].tree0) ? 1 : 0;
         const int fend = f ? d.T : (d.f[1].ntree > 0 ? d.f[1].tree0 : d.T);
         const int ncand = min(PNB, fend - first);
@@ -152,15 +185,15 @@ __device__ inline void pipe_plan(PipeSmem& sm, PipePlan& P, const PipePlan* prev
             P.ncell = ncell;
         }
     }
-    named_sync(BAR_PASS, PP_THREADS);
+    __syncwarp();
     {   // offsets of every pair and the two columns of every cell, from the closed form
-        if (pt < PNB * PNB) {
-            const int q = pt / PNB, m = pt % PNB;
+        if (lane < PNB * PNB) {
+            const int q = lane / PNB, m = lane % PNB;
             P.xoff[q][m] = (int16_t)(P.cbase[q] + (P.K[q] - 1) * (int)P.colbase[m]);
             P.xoffp[q][m] = (int16_t)(P.cbasep[q] + (P.K[q] - 1) * (int)P.colbasep[m]);
         }
         const int nb = P.nb, ncw = P.ncell_w, nc = P.ncell;
-        for (int cell = pt; cell < nc; cell += PP_THREADS) {
+        for (int cell = lane; cell < nc; cell += 32) {
             const bool cross = cell >= ncw;
             int q = 0;
             for (int qq = 1; qq < nb; ++qq) if (cell >= (cross ? P.cbasep[qq] : P.cbase[qq])) q = qq;
@@ -168,17 +201,13 @@ __device__ inline void pipe_plan(PipeSmem& sm, PipePlan& P, const PipePlan* prev
             P.cell_c1[cell] = (uint8_t)((cross ? PMAXC : 0) + j / w);
             P.cell_c2[cell] = (uint8_t)(P.colbase[q] + j % w);
         }
-        // clear the pass tables of this batch
-        unsigned int* tb = reinterpret_cast<unsigned int*>(&sm.p.acc);
-        const int nw = (int)(offsetof(PipeAcc, xtab) / 4) + 2 * PXCAP;
-        for (int i = pt; i < nw; i += PP_THREADS) tb[i] = 0u;
     }
-    named_sync(BAR_PASS, PP_THREADS);
+    __syncwarp();
 }
 
 // statistics of batch P over one warp tile; `kw` / `kr`: key areas of this batch (written) and of the previous one
-__device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, const PipePlan& P, const Dev& d, const PipePtrs& rs, int tile0, int lt,
-                                                int lane, int warp, int parity)
+__device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, PipeAcc& acc, const PipePlan& P, const Dev& d, const PipePtrs& rs,
+                                                int tile0, int lt, int lane, int warp, int parity)
 {
     const int tile = tile0 + lt;
     const int g = tile < d.trt_tiles ? 1 : 0;
@@ -196,7 +225,7 @@ __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, const PipePlan& P,
         long long tot = 0;
 #pragma unroll
         for (int o = 0; o < 8; ++o) tot += R[o];
-        warp_add21(sm.p.acc.totr[g], tot, lane);
+        warp_add21(acc.totr[g], tot, lane);
     }
     uint8_t* colb = &sm.colb[warp][0][0];
     const int nb = P.nb;
@@ -220,7 +249,7 @@ __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, const PipePlan& P,
 #pragma unroll
             for (int o = 0; o < 8; ++o) m[o] = ((bits >> o) & 1u) ? R[o] : 0ll;
             const long long s = ((m[0] + m[1]) + (m[2] + m[3])) + ((m[4] + m[5]) + (m[6] + m[7]));   // short dependency chain
-            unsigned int* e = sm.p.acc.btab[q][k][g];
+            unsigned int* e = acc.btab[q][k][g];
             warp_add21(e, s, lane);
             if (ci.birth && k == K - 1) {
                 const int c = __reduce_add_sync(0xffffffffu, __popc(bits));
@@ -254,7 +283,7 @@ __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, const PipePlan& P,
         const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
         const int c = __popc(a0.x & b0.x) + __popc(a0.y & b0.y) + __popc(a0.z & b0.z) + __popc(a0.w & b0.w) +
                       __popc(a1.x & b1.x) + __popc(a1.y & b1.y) + __popc(a1.z & b1.z) + __popc(a1.w & b1.w);
-        if (c) atomicAdd(&sm.p.acc.xtab[cell][g], (unsigned int)c);
+        if (c) atomicAdd(&acc.xtab[cell][g], (unsigned int)c);
     }
     __syncwarp();
 }
@@ -309,54 +338,73 @@ __device__ __forceinline__ void pipe_apply_tile(const PipeApply& ap, const Dev& 
     res_st8i(rs.R + toff, lane, R);
 }
 
-__device__ inline void pipe_flush(PipeSmem& sm, const PipePlan& P, long long* totals, long long* cross, int pt)
+// the CTA's tables of one batch -> the grid-wide ones, by the tile warps (one word per thread); leaves the tables zeroed
+__device__ inline void pipe_flush(PipeAcc& acc, const PipePlan& P, long long* totals, long long* cross, int tt)
 {
     const int nb = P.nb;
-    for (int i = pt; i < nb * KB * 8; i += PP_THREADS) {
-        const int q = i / (KB * 8), k = (i >> 3) & (KB - 1), g = (i >> 2) & 1, w = i & 3;
-        long long v = 0;
-        if (k == 0) { if (q == 0) v = acc_word(sm.p.acc.totr[g], w); }        // key 0 of the first tree carries the total
-        else if (k < P.K[q]) v = acc_word(sm.p.acc.btab[q][k][g], w);
-        if (v != 0) atomicAdd((unsigned long long*)&totals[(size_t)(P.first + q) * KEYS * 8 + k * 8 + g * 4 + w], (unsigned long long)v);
-    }
-    long long* xg = cross + (size_t)P.first * PIPE_XSTRIDE;
-    for (int i = pt; i < 2 * P.ncell; i += PP_THREADS) {
-        const unsigned int v = sm.p.acc.xtab[i >> 1][i & 1];
-        if (v != 0) atomicAdd((unsigned long long*)&xg[i], (unsigned long long)v);
+    constexpr int NTOT = PNB * KB * 8;
+    for (int i = tt; i < NTOT + 2 * PXCAP; i += PT_WARPS * 32) {
+        if (i < NTOT) {
+            const int q = i / (KB * 8), k = (i >> 3) & (KB - 1), g = (i >> 2) & 1, w = i & 3;
+            long long v = 0;
+            if (k == 0) { if (q == 0) { v = acc_word(acc.totr[g], w); acc.totr[g][w] = 0u; } }   // key 0 of the first tree carries the total
+            else if (q < nb && k < P.K[q]) { v = acc_word(acc.btab[q][k][g], w); acc.btab[q][k][g][w] = 0u; }
+            if (v != 0) atomicAdd((unsigned long long*)&totals[(size_t)(P.first + q) * KEYS * 8 + k * 8 + g * 4 + w], (unsigned long long)v);
+        } else {
+            const int j = i - NTOT;
+            if (j < 2 * P.ncell) {
+                const unsigned int v = acc.xtab[j >> 1][j & 1];
+                acc.xtab[j >> 1][j & 1] = 0u;
+                if (v != 0) atomicAdd((unsigned long long*)&cross[(size_t)P.first * PIPE_XSTRIDE + j], (unsigned long long)v);
+            }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // resolve role
 // ---------------------------------------------------------------------------------------------------------------
-// compact copies of the (up to PNB) trees starting at `first`, with proposals and leaf normals: warp q takes tree q
-__device__ inline void pipe_stage_trees(PipeSmem& sm, const Dev& d, const TreeRec* trees, int first, int rw, int l)
+// compact copies of the (up to PNB) trees starting at `first`, with proposals and leaf normals, by ONE warp.  One tree
+// at a time: all of a tree's loads are in flight together (one L2 round trip per tree) and nothing spills.
+__device__ inline void pipe_stage_trees(SmallStage* st, const Dev& d, const TreeRec* trees, int first, int l)
 {
     const int f = (d.f[1].ntree > 0 && first >= d.f[1].tree0) ? 1 : 0;
     const int fend = f ? d.T : (d.f[1].ntree > 0 ? d.f[1].tree0 : d.T);
-    if (rw >= min(PNB, fend - first)) return;
-    const TreeRec* src = &trees[first + rw];
-    SmallStage& S = sm.st[rw];
-    if (l < 2 * KB) {
-        S.tr.parent[l] = __ldcg(&src->parent[l]); S.tr.left[l] = __ldcg(&src->left[l]); S.tr.right[l] = __ldcg(&src->right[l]);
-        S.tr.var[l] = __ldcg(&src->var[l]); S.tr.cut[l] = __ldcg(&src->cut[l]); S.tr.node_slot[l] = __ldcg(&src->node_slot[l]);
-        S.tr.depth[l] = __ldcg(&src->depth[l]); S.tr.heap[l] = __ldcg(&src->heap[l]);
-    } else if (l < 3 * KB) {
-        const int s = l - 2 * KB;
-        S.tr.slot_node[s] = __ldcg(&src->slot_node[s]); S.tr.cnt0[s] = __ldcg(&src->cnt0[s]);
-        S.tr.cnt1[s] = __ldcg(&src->cnt1[s]); S.tr.mu[s] = __ldcg(&src->mu[s]);
-    } else if (l == 3 * KB) {
-        S.tr.nnodes = __ldcg(&src->nnodes); S.tr.nleaves = __ldcg(&src->nleaves);
+    const int nq = min(PNB, fend - first);
+#pragma unroll 1
+    for (int q = 0; q < nq; ++q) {
+        const TreeRec* src = &trees[first + q];
+        SmallStage& S = st[q];
+        long long pr = 0;
+        double z = 0.0;
+        if (l < (int)(sizeof(Proposal) / 8)) pr = __ldcg(reinterpret_cast<const long long*>(&d.proprec[first + q].P) + l);
+        else if (l >= 16 && l < 16 + KB) z = __ldcg(&d.proprec[first + q].z[l - 16]);
+        if (l < 2 * KB) {
+            const int16_t pa = __ldcg(&src->parent[l]), le = __ldcg(&src->left[l]), ri = __ldcg(&src->right[l]);
+            const uint16_t va = __ldcg(&src->var[l]), cu = __ldcg(&src->cut[l]);
+            const uint8_t ns = __ldcg(&src->node_slot[l]), de = __ldcg(&src->depth[l]);
+            const uint32_t he = __ldcg(&src->heap[l]);
+            S.tr.parent[l] = pa; S.tr.left[l] = le; S.tr.right[l] = ri; S.tr.var[l] = va; S.tr.cut[l] = cu;
+            S.tr.node_slot[l] = ns; S.tr.depth[l] = de; S.tr.heap[l] = he;
+        } else if (l < 3 * KB) {
+            const int s = l - 2 * KB;
+            const int16_t sn = __ldcg(&src->slot_node[s]);
+            const int32_t c0 = __ldcg(&src->cnt0[s]), c1 = __ldcg(&src->cnt1[s]);
+            const double mu = __ldcg(&src->mu[s]);
+            S.tr.slot_node[s] = sn; S.tr.cnt0[s] = c0; S.tr.cnt1[s] = c1; S.tr.mu[s] = mu;
+        } else if (l == 3 * KB) {
+            const int32_t nn = __ldcg(&src->nnodes), nl = __ldcg(&src->nleaves);
+            S.tr.nnodes = nn; S.tr.nleaves = nl;
+        }
+        if (l < (int)(sizeof(Proposal) / 8)) reinterpret_cast<long long*>(&S.prop)[l] = pr;
+        else if (l >= 16 && l < 16 + KB) S.z[l - 16] = z;
     }
-    if (l < (int)(sizeof(Proposal) / 8))
-        reinterpret_cast<long long*>(&S.prop)[l] = __ldcg(reinterpret_cast<const long long*>(&d.proprec[first + rw].P) + l);
-    else if (l >= 16 && l < 16 + KB)
-        S.z[l - 16] = __ldcg(&d.proprec[first + rw].z[l - 16]);
+    __syncwarp();
 }
 
 // everything of a batch's decisions (resolve role, PR_THREADS threads; rt = thread within the role)
-__device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, const Dev& d, const Scalars& sc, TreeRec* newtrees,
-                                    const long long* totals, const long long* cross, int rt)
+__device__ inline void pipe_resolve(PipeSmem& sm, SmallStage* st, const PipePlan& P, int b, const Dev& d, const Scalars& sc,
+                                    TreeRec* newtrees, const long long* totals, const long long* cross, int rt, long long* trc = nullptr)
 {
     const int nb = P.nb;
     const ForestDev& F = d.f[P.forest];
@@ -364,13 +412,32 @@ __device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, cons
     const bool rprof = d.prof != nullptr && blockIdx.x == 0 && rt == 0;
     long long rtp = clock64();
 #define RPROF(k) do { if (rprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - rtp)); rtp = now_; } } while (0)
-    for (int i = rt; i < nb * KB * 8; i += PR_THREADS) {
-        const int q = i / (KB * 8), k = (i >> 3) & (KB - 1);
-        if (k < P.K[q]) (&rs.tot[0][0][0][0])[i] = __ldcg(&totals[(size_t)(P.first + q) * KEYS * 8 + (i & (KB * 8 - 1))]);
-    }
-    {
+    {   // the batch's reduced words: every load is issued before the first store (one L2 round trip)
+        constexpr int NT_IT = (PNB * KB * 8 + PR_THREADS - 1) / PR_THREADS, NX_IT = (2 * PXCAP + PR_THREADS - 1) / PR_THREADS;
         const long long* xg = cross + (size_t)P.first * PIPE_XSTRIDE;
-        for (int i = rt; i < 2 * P.ncell; i += PR_THREADS) (&rs.x[0][0])[i] = (int)__ldcg(xg + i);
+        const int nx = 2 * P.ncell;
+        long long tv[NT_IT], xv[NX_IT];
+#pragma unroll
+        for (int it = 0; it < NT_IT; ++it) {
+            const int i = rt + it * PR_THREADS;
+            const int q = i / (KB * 8), k = (i >> 3) & (KB - 1);
+            tv[it] = (i < nb * KB * 8 && k < P.K[q]) ? __ldcg(&totals[(size_t)(P.first + q) * KEYS * 8 + (i & (KB * 8 - 1))]) : 0ll;
+        }
+#pragma unroll
+        for (int it = 0; it < NX_IT; ++it) {
+            const int i = rt + it * PR_THREADS;
+            xv[it] = i < nx ? __ldcg(xg + i) : 0ll;
+        }
+#pragma unroll
+        for (int it = 0; it < NT_IT; ++it) {
+            const int i = rt + it * PR_THREADS;
+            if (i < nb * KB * 8) (&rs.tot[0][0][0][0])[i] = tv[it];
+        }
+#pragma unroll
+        for (int it = 0; it < NX_IT; ++it) {
+            const int i = rt + it * PR_THREADS;
+            if (i < nx) (&rs.x[0][0])[i] = (int)xv[it];
+        }
     }
     named_sync(BAR_RES, PR_THREADS);
     RPROF(8);
@@ -382,7 +449,7 @@ __device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, cons
     const double a = 1.0 / (tau * tau);
     if (rt < nb * (KB + 1)) {   // count-only terms of every key and pooled pair (as in resolve_batch)
         const int q = rt / (KB + 1), e = rt % (KB + 1);
-        const SmallStage& S = sm.st[q];
+        const SmallStage& S = st[q];
         const int L = S.tr.nleaves, K = P.K[q], mv = S.prop.move, sx = S.prop.slot;
         if (e < K || (e == KB && mv != 0)) {
             const double cL1 = mv == 1 ? (double)rs.tot[q][L][1][0] : 0.0, cL0 = mv == 1 ? (double)rs.tot[q][L][0][0] : 0.0;
@@ -411,8 +478,8 @@ __device__ inline void pipe_resolve(PipeSmem& sm, const PipePlan& P, int b, cons
         ChainConsts cc{s1, s0, 1.0 / s1, 1.0 / s0, phi1, phi0, log(tau)};
         const PipeApply& app = sm.ap[(b & 1) ^ 1];
         ChainPrev pv{P.nprev, P.Kp, &P.xoffp[0][0], app.DL, sm.cq[(b & 1) ^ 1], app.TL};
-        decision_chain<PNB>(rt >> 5, rt & 31, nb, P.first, sm.st, P.K, &P.xoff[0][0], rs, sm.ap[b & 1], sm.cq[b & 1], sm.pre, cc, pv, d,
-                       newtrees, &sm.bad);
+        decision_chain<PNB>(rt >> 5, rt & 31, nb, P.first, st, P.K, &P.xoff[0][0], rs, sm.ap[b & 1], sm.cq[b & 1], sm.pre, cc, pv, d,
+                       newtrees, &sm.bad, trc);
     }
     named_sync(BAR_RES, PR_THREADS);
     RPROF(14);
@@ -460,8 +527,20 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
     __shared__ int bar_ok;
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
+    // role of a warp.  setmaxnreg is a WARPGROUP instruction (4 consecutive warps must ask for the same count), so the
+    // chain warps are one aligned group of four.
+#if PIPE_CHAIN_FIRST
+    const bool is_pass = warp >= PR_WARPS;
+    const int pw = warp - PR_WARPS, rt = t;                 // pass warp index (0: the utility warp), chain thread index
+    const bool is_util = pw == 0;
+    const int tw = pw - 1;                                   // tile warp index
+#else
     const bool is_pass = warp < PP_WARPS;
-    const int pt = t, rt = t - PP_THREADS, rw = warp - PP_WARPS;
+    const int pw = warp, rt = t - PP_THREADS;
+    const bool is_util = pw == PT_WARPS;
+    const int tw = pw;
+#endif
+    const int pt = pw * 32 + lane;
     const bool writer0 = (blockIdx.x == 0);
     // Grid barrier counters (every thread counts the events itself).  bar[2]: the full barriers.  bar[0] / bar[1]: the
     // batch barriers, by batch parity -- the pass role may arrive at batch b+1 before batch b's barrier has completed
@@ -491,7 +570,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
     auto grid_all_wait = [&]() -> bool { return grid_wait(bar + 2, target, d.err, &bar_ok); };
 
     if (is_pass)
-        for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+        for (int lt = pw; lt < ntl; lt += PP_WARPS) {
             const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
             const uint32_t toff = (uint32_t)lt * (TILE * 8u);
             long long R[8];
@@ -513,7 +592,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
         long long* totals = sweep_totals(d, sc.sweep);
         long long* cross = d.cross + (size_t)(sc.sweep & 1u) * (size_t)T * PIPE_XSTRIDE;
         // ---- what the pass needs to know about every tree; a tree too wide for this engine ends the launch ----
-        if (t == 0) sm.anybig = 0;
+        if (t == 0) { sm.anybig = 0; sm.plan_ready = 0; sm.flushed = 0; }
         __syncthreads();
         for (int j = t; j < T; j += PIPE_THREADS) {
             const TreeRec* tr = &d.trees[par][j];
@@ -529,64 +608,103 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
         __syncthreads();
         if (sm.anybig) break;
 
-        // The two roles need different register budgets (the decision chain keeps a tree's sums, posterior terms and
+        // The roles need different register budgets (the decision chain keeps a tree's sums, posterior terms and
         // constants live; the pass is a streaming loop): re-split the SM's register file for the role section.
+#define PTRACE(k) do { if (prof && sw == 0 && b < 64) d.prof[16 + b * 8 + (k)] = clock64(); } while (0)
         if (is_pass) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_PASS));
-            // =================== pass role ===================
-            const bool prof = d.prof != nullptr && blockIdx.x == 0 && pt == 0;
-            long long tp = clock64();
-#define PPROF(k) do { if (prof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
-            int first = 0, b = 0;
-            while (first < T) {
-                PipePlan& P = sm.plan[b & 1];
-                pipe_plan(sm, P, b > 0 ? &sm.plan[(b & 1) ^ 1] : nullptr, d, meta, first, pt);
-                PPROF(5);
-                for (int lt = warp; lt < ntl; lt += PP_WARPS) pipe_stats_tile(sm, P, d, rs, tile0, lt, lane, warp, b & 1);
-                named_sync(BAR_PASS, PP_THREADS);
-                PPROF(0);
-                pipe_flush(sm, P, totals, cross, pt);
-                named_sync(BAR_PASS, PP_THREADS);
-                if (pt == 0) red_release_add_u32(bar + (b & 1), 1u);
-                named_arrive(BAR_H1 + (b & 1), PIPE_THREADS);           // H1(b): flushed, plan visible
-                PPROF(1);
-                if (b > 0) {
-                    named_sync(BAR_H2 + ((b - 1) & 1), PIPE_THREADS);   // H2(b-1): its tables are ready
-                    PPROF(2);
+            if (!is_util) {
+                // =================== tile warps ===================
+                const bool prof = d.prof != nullptr && blockIdx.x == 0 && tw == 0 && lane == 0;
+                const bool cprof = d.prof != nullptr && tw == 0 && lane == 0;
+                long long tp = clock64();
+#define PPROF(k) do { if (cprof) { const long long now_ = clock64(); if (prof) atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); atomicAdd((unsigned long long*)&d.prof[1024 + blockIdx.x * 8 + (k)], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
+                int first = 0, b = 0;
+                if (lane == 0) pipe_wait_flag(&sm.plan_ready, 1, d.err, 20);     // the first plan
+                __syncwarp();
+                while (first < T) {
+                    const PipePlan& P = sm.plan[b & 3];
+                    PPROF(5); PTRACE(0);
+                    for (int lt = tw; lt < ntl; lt += PT_WARPS) pipe_stats_tile(sm, sm.p.acc[b & 1], P, d, rs, tile0, lt, lane, pw, b & 1);
+                    // the next plan is made two batches ahead: warp 0 checks it (an acquire load: kept off the other
+                    // warps, and away from the apply's stores) and the barrier hands the knowledge to everybody
+                    if (tw == 0 && lane == 0 && first + P.nb < T) pipe_wait_flag(&sm.plan_ready, b + 2, d.err, 20);
+                    named_sync(BAR_S, PT_THREADS);                               // every tile warp is through STATS(b)
+                    PPROF(0); PTRACE(1);
+                    pipe_flush(sm.p.acc[b & 1], P, totals, cross, tw * 32 + lane);
+                    named_sync(BAR_F, PT_THREADS);                               // ... and has flushed its share
+                    if (tw == 0) {
+                        if (lane == 0) { red_release_add_u32(bar + (b & 1), 1u); st_release_cta_s32(&sm.flushed, b + 1); }   // grid barrier b
+                        named_arrive(BAR_H1 + (b & 1), H1_THREADS);              // H1(b): flushed (planned, staged: see plan_ready)
+                    }
+                    PPROF(1); PTRACE(2);
+                    if (b > 0) {
+                        named_sync(BAR_H2 + ((b - 1) & 1), H2_THREADS);         // H2(b-1): its tables are ready
+                        PPROF(2); PTRACE(3);
+                        const PipeApply& ap = sm.ap[(b - 1) & 1];
+                        const bool fswitch = has_mod && ap.first == tmod && tmod > 0;
+                        for (int lt = tw; lt < ntl; lt += PT_WARPS) {
+                            if (lt == pad_a || lt == pad_b) pipe_apply_tile<true>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
+                            else pipe_apply_tile<false>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
+                        }
+                        PPROF(3); PTRACE(4);
+                    }
+                    first += P.nb; ++b;
+                }
+#undef PPROF
+                {   // drain: the last batch
+                    named_sync(BAR_H2 + ((b - 1) & 1), H2_THREADS);
                     const PipeApply& ap = sm.ap[(b - 1) & 1];
                     const bool fswitch = has_mod && ap.first == tmod && tmod > 0;
-                    for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+                    for (int lt = tw; lt < ntl; lt += PT_WARPS) {
                         if (lt == pad_a || lt == pad_b) pipe_apply_tile<true>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
                         else pipe_apply_tile<false>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
                     }
-                    named_sync(BAR_PASS, PP_THREADS);
-                    PPROF(3);
                 }
-                first += P.nb; ++b;
-            }
-#undef PPROF
-            {   // drain: the last batch
-                named_sync(BAR_H2 + ((b - 1) & 1), PIPE_THREADS);
-                const PipeApply& ap = sm.ap[(b - 1) & 1];
-                const bool fswitch = has_mod && ap.first == tmod && tmod > 0;
-                for (int lt = warp; lt < ntl; lt += PP_WARPS) {
-                    if (lt == pad_a || lt == pad_b) pipe_apply_tile<true>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
-                    else pipe_apply_tile<false>(ap, d, rs, tile0, lt, lane, (b - 1) & 1, fswitch);
+            } else {
+                // =================== utility warp ===================
+                // Plans the batches and stages their trees, two batches ahead of the statistics and paced only by the
+                // `flushed` counter: nothing ever waits for this warp in the steady state (its shared-memory round
+                // trips are slow while the tile warps stream).  Buffers of batch pb are those of batch pb - 4, whose
+                // decisions every tile warp has seen applied once batch pb - 2 is flushed.
+                {
+                    unsigned int* tb = reinterpret_cast<unsigned int*>(&sm.p.acc[0]);
+                    for (int i = lane; i < (int)(2 * sizeof(PipeAcc) / 4); i += 32) tb[i] = 0u;
                 }
+                int pfirst = 0, pb = 0;
+                long long up = clock64();
+                const bool uprof = d.prof != nullptr && lane == 0;
+#define UPROF(k) do { if (uprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[1024 + 2048 + blockIdx.x * 8 + (k)], (unsigned long long)(now_ - up)); up = now_; } } while (0)
+                while (pfirst < T) {
+                    if (pb >= 2) {
+                        if (lane == 0) pipe_wait_flag(&sm.flushed, pb - 1, d.err, 200);
+                        __syncwarp();
+                    }
+                    UPROF(0);
+                    PipePlan& NP = sm.plan[pb & 3];
+                    pipe_plan(NP, pb > 0 ? &sm.plan[(pb - 1) & 3] : nullptr, d, meta, pfirst, lane);
+                    UPROF(1);
+                    pipe_stage_trees(sm.st[pb & 3], d, d.trees[par], pfirst, lane);
+                    __syncwarp();
+                    UPROF(2);
+                    if (lane == 0) st_release_cta_s32(&sm.plan_ready, pb + 1);
+                    pfirst += NP.nb; ++pb;
+                }
+#undef UPROF
             }
             asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_BASE));
         } else {
             asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_RESOLVE));
-            // =================== resolve role ===================
+            // =================== chain warps ===================
             const bool prof = d.prof != nullptr && blockIdx.x == 0 && rt == 0;
+            const bool cprof = d.prof != nullptr && rt == 0;
             long long tp = clock64();
-#define QPROF(k) do { if (prof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
+#define QPROF(k) do { if (cprof) { const long long now_ = clock64(); if (prof) atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); atomicAdd((unsigned long long*)&d.prof[1024 + blockIdx.x * 8 + (k)], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
             int first = 0, b = 0;
             while (first < T) {
-                pipe_stage_trees(sm, d, d.trees[par], first, rw, lane);     // while the pass still streams batch b
-                named_sync(BAR_H1 + (b & 1), PIPE_THREADS);                  // H1(b)
-                QPROF(4);
-                const PipePlan& P = sm.plan[b & 1];
+                named_sync(BAR_H1 + (b & 1), H1_THREADS);                        // H1(b)
+                QPROF(4); PTRACE(5);
+                const PipePlan& P = sm.plan[b & 3];
                 tbatch[b & 1] += gridDim.x;
                 if (rt == 0) {
                     const long long t0 = clock64();
@@ -596,15 +714,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                     }
                 }
                 named_sync(BAR_RES, PR_THREADS);
-                QPROF(6);
-                pipe_resolve(sm, P, b, d, sc, d.trees[par ^ 1], totals, cross, rt);
-                named_arrive(BAR_H2 + (b & 1), PIPE_THREADS);                // H2(b)
-                QPROF(7);
+                QPROF(6); PTRACE(6);
+                pipe_resolve(sm, sm.st[b & 3], P, b, d, sc, d.trees[par ^ 1], totals, cross, rt,
+                             (d.prof != nullptr && blockIdx.x == 0 && sw == 0 && b >= 8 && b < 16) ? d.prof + 16 + 512 + (b - 8) * 32 : nullptr);
+                named_arrive(BAR_H2 + (b & 1), H2_THREADS);                      // H2(b)
+                QPROF(7); PTRACE(7);
                 first += P.nb; ++b;
             }
 #undef QPROF
             asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_BASE));
         }
+#undef PTRACE
         __syncthreads();
         // ---- epilogue: moments of (y, Gc, Gm) ----
         if (is_pass) {
@@ -613,7 +733,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
         }
         __syncthreads();
         if (is_pass)
-            for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+            for (int lt = pw; lt < ntl; lt += PP_WARPS) {
                 const int tile = tile0 + lt;
                 const int64_t gb = (int64_t)tile * TILE + lane * 8;
                 double G[8], y[8], other[8];
@@ -630,7 +750,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
         for (int i = t; i < NMOM * 8; i += PIPE_THREADS) {
             const int m = i >> 3, g = (i >> 2) & 1, q = i & 3;
             if (q == 0) continue;
-            const long long v = table_word(sm.p.tab, PP_WARPS, m, g, q);
+            const long long v = table_word(sm.p.tab, PIPE_THREADS / 32, m, g, q);
             if (v != 0) atomicAdd((unsigned long long*)&mom[(g * NMOM + m) * 3 + (q - 1)], (unsigned long long)v);
         }
         grid_all();
@@ -644,7 +764,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
             const double ms = sn.mscale, b1 = sn.bscale1, b0 = sn.bscale0;
             const int row = sn.save_row;
             if (is_pass)
-                for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+                for (int lt = pw; lt < ntl; lt += PP_WARPS) {
                     const int tile = tile0 + lt;
                     const int64_t gb = (int64_t)tile * TILE + lane * 8;
                     const uint32_t toff = (uint32_t)lt * (TILE * 8u);
@@ -686,7 +806,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
     }
     // exit: park the state in HBM in the form every engine understands (Gm was stored by the finishing pass)
     if (is_pass)
-        for (int lt = warp; lt < ntl; lt += PP_WARPS) {
+        for (int lt = pw; lt < ntl; lt += PP_WARPS) {
             const int64_t gb = (int64_t)(tile0 + lt) * TILE + lane * 8;
             const uint32_t toff = (uint32_t)lt * (TILE * 8u);
             double G[8];

@@ -491,7 +491,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     DM(h, &d.counters, 4);
     DM(h, &h->d_bar, 64);
     DM(h, &h->d_done, 4);
-    if (getenv("BCFGPU_PROFILE")) { DM(h, &d.prof, 16); CK(cudaMemsetAsync(d.prof, 0, 128, h->stream)); }
+    if (getenv("BCFGPU_PROFILE")) { DM(h, &d.prof, 1024 + 512 * 8); CK(cudaMemsetAsync(d.prof, 0, (1024 + 512 * 8) * 8, h->stream)); }
     d.y = dy;
     CK(cudaMemsetAsync(d.totals, 0, (size_t)2 * h->T * KEYS * 8 * 8, h->stream));
     CK(cudaMemsetAsync(d.cross, 0, (size_t)2 * h->T * PIPE_XSTRIDE * 8, h->stream));
@@ -699,6 +699,43 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
             fprintf(stderr, "[bcfgpu profile] resolve detail (cyc/tree):");
             for (int k = 8; k < 16; ++k) fprintf(stderr, " r%d=%.0f", k - 8, (double)pc[k] / ((double)total * h->T));
             fprintf(stderr, "\n");
+        }
+        if (getenv("BCFGPU_TRACE")) {   // k_pipe: per-CTA phase totals (cycles per batch): 0 stats, 2 wait H2, 3 apply, 5 wait plan | 4 wait H1, 6 wait grid barrier, 7 resolve
+            std::vector<long long> pcx(512 * 8);
+            CK(cudaMemcpy(pcx.data(), d.prof + 1024, pcx.size() * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemset(d.prof + 1024, 0, pcx.size() * 8));
+            const double nbat = (double)total * ((h->cfg.ntree_con + 3) / 4 + (h->cfg.ntree_mod + 3) / 4);
+            for (int k = 0; k < 11; ++k) {   // 8..10: utility warp (wait for the flush, plan, stage)
+                std::vector<double> v;
+                for (int c = 0; c < h->coop_grid && c < 256; ++c) v.push_back((double)pcx[(k < 8 ? c * 8 + k : 2048 + c * 8 + k - 8)] / nbat);
+                if (v.empty()) break;
+                std::vector<double> sv = v; std::sort(sv.begin(), sv.end());
+                if (k == 7 || k == 6 || k == 3 || k == 0) { fprintf(stderr, "[bcfgpu trace] phase %d all:", k); for (double x : v) fprintf(stderr, " %.0f", x / 100.0); fprintf(stderr, "\n"); }
+                fprintf(stderr, "[bcfgpu trace] per-CTA phase %d: cta0=%.0f min=%.0f med=%.0f max=%.0f (cta of max %d)\n", k, v[0], sv.front(), sv[sv.size() / 2], sv.back(),
+                        (int)(std::max_element(v.begin(), v.end()) - v.begin()));
+            }
+        }
+        if (getenv("BCFGPU_TRACE")) {   // k_pipe: CTA 0's batch timeline in the launch's first sweep (cycles since batch 8's plan)
+            long long tr[64 * 8];
+            CK(cudaMemcpy(tr, d.prof + 16, sizeof(tr), cudaMemcpyDeviceToHost));
+            const long long t0 = tr[8 * 8];
+            const char* ev[8] = {"plan", "stats", "flushed", "H2got", "applied", "H1got", "gridbar", "resolved"};
+            for (int b = 8; b < 16 && t0 != 0; ++b) {
+                fprintf(stderr, "[bcfgpu trace] batch %2d:", b);
+                for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%lld", ev[k], tr[b * 8 + k] - t0);
+                fprintf(stderr, "\n");
+            }
+            long long ch[256];
+            CK(cudaMemcpy(ch, d.prof + 16 + 512, sizeof(ch), cudaMemcpyDeviceToHost));
+            for (int b = 8; b < 12 && t0 != 0; ++b) {   // decision chain: per warp enter, prev folded, turn, arrived, booked, left
+                fprintf(stderr, "[bcfgpu trace] chain %2d:", b);
+                for (int w = 0; w < 4; ++w) {
+                    fprintf(stderr, " |w%d", w);
+                    for (int e = 0; e < 6; ++e) fprintf(stderr, " %lld", ch[(b - 8) * 32 + w * 8 + e] - t0);
+                }
+                const long long* u = ch + (b - 8) * 32;
+                fprintf(stderr, " |util S=%lld flush=%lld rel=%lld plan=%lld H2=%lld staged=%lld\n", u[6] - t0, u[7] - t0, u[14] - t0, u[15] - t0, u[22] - t0, u[23] - t0);
+            }
         }
     }
     return BCFGPU_OK;
