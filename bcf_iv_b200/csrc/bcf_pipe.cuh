@@ -76,6 +76,7 @@ struct __align__(16) PipeApply {
     long long TL[PNB][2][4];
     uint8_t NS[PNB * KB];
 };
+struct PipeConsts { ChainConsts cc; double a; };    // what a batch's decisions need from the sweep's scalars
 struct PipeRS { long long tot[PNB][KB][2][4]; int x[PXCAP][2]; };
 struct PipeAcc { unsigned int btab[PNB][KB][2][4]; unsigned int totr[2][4]; unsigned int xtab[PXCAP][2]; };
 
@@ -95,6 +96,7 @@ struct PipeSmem {
     int32_t cq[2][PNB][KB][2];
     PipeRS rs;
     PreKey pre[PNB * (KB + 1)];
+    PipeConsts cons[2];                               // per forest, per sweep
     union { PipeAcc acc[2]; StatTabT<32> tab; double red[2 * PIPE_THREADS]; } p;
     uint8_t colb[PP_WARPS][2 * PMAXC][32];
 };
@@ -407,7 +409,6 @@ __device__ inline void pipe_resolve(PipeSmem& sm, SmallStage* st, const PipePlan
                                     TreeRec* newtrees, const long long* totals, const long long* cross, int rt, long long* trc = nullptr)
 {
     const int nb = P.nb;
-    const ForestDev& F = d.f[P.forest];
     PipeRS& rs = sm.rs;
     const bool rprof = d.prof != nullptr && blockIdx.x == 0 && rt == 0;
     long long rtp = clock64();
@@ -441,17 +442,14 @@ __device__ inline void pipe_resolve(PipeSmem& sm, SmallStage* st, const PipePlan
     }
     named_sync(BAR_RES, PR_THREADS);
     RPROF(8);
-    const bool is_con = F.is_con != 0;
-    const double s1 = is_con ? sc.mscale : sc.bscale1, s0 = is_con ? sc.mscale : sc.bscale0;
-    const double tau = is_con ? sc.tau_con : sc.tau_mod;
-    const double s2 = sc.sigma * sc.sigma;
-    const double phi1 = s1 * s1 / s2, phi0 = s0 * s0 / s2;
-    const double a = 1.0 / (tau * tau);
-    if (rt < nb * (KB + 1)) {   // count-only terms of every key and pooled pair (as in resolve_batch)
-        const int q = rt / (KB + 1), e = rt % (KB + 1);
+    const PipeConsts& pc = sm.cons[P.forest];
+    if (rt < 2 * nb * (KB + 1)) {   // count-only terms of every key and pooled pair (as in resolve_batch); two lanes per
+        const int part = rt & 1;    // entry: one takes 1/prec and its square root, the other log(prec)
+        const int q = (rt >> 1) / (KB + 1), e = (rt >> 1) % (KB + 1);
         const SmallStage& S = st[q];
         const int L = S.tr.nleaves, K = P.K[q], mv = S.prop.move, sx = S.prop.slot;
         if (e < K || (e == KB && mv != 0)) {
+            const double phi1 = pc.cc.phi1, phi0 = pc.cc.phi0;
             const double cL1 = mv == 1 ? (double)rs.tot[q][L][1][0] : 0.0, cL0 = mv == 1 ? (double)rs.tot[q][L][0][0] : 0.0;
             const int pa = sx, pb = (mv == 1) ? L : S.prop.slot_b;
             double k1 = 0.0, k0 = 0.0, A = 0.0;
@@ -466,16 +464,21 @@ __device__ inline void pipe_resolve(PipeSmem& sm, SmallStage* st, const PipePlan
                 k1 += c1; k0 += c0;
                 A += c1 * phi1 + c0 * phi0;
             }
-            const double prec = a + A, inv = 1.0 / prec;
+            const double prec = pc.a + A;
             PreKey& pk = sm.pre[q * (KB + 1) + e];
-            pk.k1 = k1; pk.k0 = k0; pk.inv = inv; pk.plog = log(prec); pk.psd = sqrt(inv);
-            if (e < K) { sm.cq[b & 1][q][e][1] = (int32_t)k1; sm.cq[b & 1][q][e][0] = (int32_t)k0; }
+            if (part == 0) {
+                const double inv = 1.0 / prec;
+                pk.k1 = k1; pk.k0 = k0; pk.inv = inv; pk.psd = sqrt(inv);
+                if (e < K) { sm.cq[b & 1][q][e][1] = (int32_t)k1; sm.cq[b & 1][q][e][0] = (int32_t)k0; }
+            } else {
+                pk.plog = log(prec);
+            }
         }
     }
     named_sync(BAR_RES, PR_THREADS);
     RPROF(9);
     {
-        ChainConsts cc{s1, s0, 1.0 / s1, 1.0 / s0, phi1, phi0, log(tau)};
+        const ChainConsts cc = pc.cc;
         const PipeApply& app = sm.ap[(b & 1) ^ 1];
         ChainPrev pv{P.nprev, P.Kp, &P.xoffp[0][0], app.DL, sm.cq[(b & 1) ^ 1], app.TL};
         decision_chain<PNB>(rt >> 5, rt & 31, nb, P.first, st, P.K, &P.xoff[0][0], rs, sm.ap[b & 1], sm.cq[b & 1], sm.pre, cc, pv, d,
@@ -700,6 +703,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
             const bool cprof = d.prof != nullptr && rt == 0;
             long long tp = clock64();
 #define QPROF(k) do { if (cprof) { const long long now_ = clock64(); if (prof) atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); atomicAdd((unsigned long long*)&d.prof[1024 + blockIdx.x * 8 + (k)], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
+            if (rt < 2) {   // the sweep's scalars as the decisions use them, per forest (the expressions of resolve_batch)
+                const bool is_con = d.f[rt].is_con != 0;
+                const double s1 = is_con ? sc.mscale : sc.bscale1, s0 = is_con ? sc.mscale : sc.bscale0;
+                const double tau = is_con ? sc.tau_con : sc.tau_mod;
+                const double s2 = sc.sigma * sc.sigma;
+                PipeConsts c;
+                c.cc = ChainConsts{s1, s0, 1.0 / s1, 1.0 / s0, s1 * s1 / s2, s0 * s0 / s2, log(tau)};
+                c.a = 1.0 / (tau * tau);
+                sm.cons[rt] = c;
+            }
+            named_sync(BAR_RES, PR_THREADS);
             int first = 0, b = 0;
             while (first < T) {
                 named_sync(BAR_H1 + (b & 1), H1_THREADS);                        // H1(b)
