@@ -22,7 +22,7 @@ ENGINE_AUTO, ENGINE_GRAPH, ENGINE_PERSISTENT, ENGINE_PERSISTENT_HBM, ENGINE_BATC
 SYMBOLS = [
     "bcfgpu_abi_version", "bcfgpu_device_count", "bcfgpu_last_error", "bcfgpu_config_init", "bcfgpu_create",
     "bcfgpu_destroy", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_data", "bcfgpu_run",
-    "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_engine_in_use", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
+    "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_h2d_bytes", "bcfgpu_engine_in_use", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
     "bcfgpu_get_mu_mean", "bcfgpu_get_yhat_mean", "bcfgpu_get_sigma", "bcfgpu_get_scales", "bcfgpu_get_draws",
     "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
     "bcfgpu_get_tree", "bcfgpu_set_tree", "bcfgpu_get_leaf_ids", "bcfgpu_verify_leaf_cache", "bcfgpu_op_bin_column",
@@ -76,6 +76,7 @@ def load():
     L.bcfgpu_run.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.bcfgpu_last_run_ms.argtypes = [vp, dp]
     L.bcfgpu_kernel_launches.argtypes = [vp, lp]
+    L.bcfgpu_h2d_bytes.argtypes = [vp, lp]
     L.bcfgpu_engine_in_use.argtypes = [vp, ip]
     L.bcfgpu_num_saved.argtypes = [vp, ip]
     for nm in ("tau_mean", "tau_var", "mu_mean", "yhat_mean", "sigma"):
@@ -198,8 +199,9 @@ class Sampler:
         self.n = n
         self.off_con, self.off_mod = oc, om
         self.p_con, self.p_mod = xc.shape[1], p_mod
-        self.h2d_bytes = y.nbytes + z.nbytes + xc.nbytes + (xm.nbytes if xm is not None else 0) + cc.nbytes + \
-            (cm.nbytes if cm is not None else 0)
+        v = C.c_int64()
+        check(load().bcfgpu_h2d_bytes(self._h, C.byref(v)))
+        self.h2d_bytes = v.value          # what the library copied (x_mod that IS x_con's leading columns is not copied twice)
 
     def run(self, nburn, nsim, nthin=1):
         check(load().bcfgpu_run(self._h, nburn, nsim, nthin))

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -114,6 +115,7 @@ struct bcfgpu_handle {
     int grid_obs = 0, grid_fin = 0;
     int engine = BCFGPU_ENGINE_GRAPH;
     int coop_grid = 0;
+    int64_t h2d_bytes = 0;                    // copied by the last set_data
     int res_ntl = 0;                  // tiles per CTA of the shared-memory-resident kernels (0 = state in HBM)
     int kernel = 0;                   // persistent kernel in use: 1 k_persistent, 2 k_resident, 3 k_batched, 4 k_pipe (+ k_batched)
     int fallback_kernel = 3;          // what k_pipe hands a sweep with a wide tree to: 3 (k_batched resident) or 5 (HBM)
@@ -332,7 +334,8 @@ static int shard_allreduce(bcfgpu_handle* h, long long* buf, size_t count)
 // ------------------------------------------------------------------------------------------------
 // data
 // ------------------------------------------------------------------------------------------------
-static int setup_forest(bcfgpu_handle* h, int f, int p, const double* cuts, const int32_t* off)
+// share != nullptr: this forest's covariates are the leading columns of that forest's -- same binned columns
+static int setup_forest(bcfgpu_handle* h, int f, int p, const double* cuts, const int32_t* off, const ForestHost* share = nullptr)
 {
     ForestHost& F = h->fh[f];
     F = ForestHost();
@@ -357,17 +360,25 @@ static int setup_forest(bcfgpu_handle* h, int f, int p, const double* cuts, cons
     DM(h, &F.d_ncut, (size_t)p);
     DM(h, &F.d_col_index, (size_t)p);
     DM(h, &F.d_is16, (size_t)p);
-    DM(h, &F.d_bins8, (size_t)std::max(F.p8, 1) * h->n_pad);
-    DM(h, &F.d_bins16, (size_t)std::max(F.p16, 1) * h->n_pad);
+    if (share) { F.d_bins8 = share->d_bins8; F.d_bins16 = share->d_bins16; }
+    else {
+        DM(h, &F.d_bins8, (size_t)std::max(F.p8, 1) * h->n_pad);
+        DM(h, &F.d_bins16, (size_t)std::max(F.p16, 1) * h->n_pad);
+    }
     CK(cudaMemcpyAsync(F.d_cuts, F.cuts.data(), F.cuts.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(F.d_off, F.off.data(), F.off.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(F.d_ncut, F.ncut.data(), (size_t)p * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(F.d_col_index, F.col_index.data(), (size_t)p * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(F.d_is16, F.is16.data(), (size_t)p, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemsetAsync(F.d_bins8, 0, (size_t)std::max(F.p8, 1) * h->n_pad, h->stream));
-    CK(cudaMemsetAsync(F.d_bins16, 0, (size_t)std::max(F.p16, 1) * h->n_pad * 2, h->stream));
+    h->h2d_bytes += (int64_t)(F.cuts.size() * 8 + F.off.size() * 4 + (size_t)p * 9);
+    if (!share) {
+        CK(cudaMemsetAsync(F.d_bins8, 0, (size_t)std::max(F.p8, 1) * h->n_pad, h->stream));
+        CK(cudaMemsetAsync(F.d_bins16, 0, (size_t)std::max(F.p16, 1) * h->n_pad * 2, h->stream));
+    }
     return BCFGPU_OK;
 }
+
+constexpr size_t MAX_STAGE = (size_t)1 << 28;   // fp64 staging buffer of K0: 256 Mi doubles = 2 GiB
 
 // K0 over a column-major host matrix, chunked by columns so the fp64 staging buffer stays bounded
 static int bin_forest(bcfgpu_handle* h, int f, const double* x)
@@ -375,8 +386,7 @@ static int bin_forest(bcfgpu_handle* h, int f, const double* x)
     ForestHost& F = h->fh[f];
     if (F.p == 0) return BCFGPU_OK;
     const int64_t n = h->n;
-    const size_t max_stage = (size_t)1 << 28;   // 256 Mi doubles = 2 GiB
-    int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(F.p, (int64_t)(max_stage / (size_t)n)));
+    int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(F.p, (int64_t)(MAX_STAGE / (size_t)n)));
     double* stage = nullptr;
     CK(cudaMalloc((void**)&stage, (size_t)chunk * n * 8));
     int rc = BCFGPU_OK;
@@ -384,6 +394,7 @@ static int bin_forest(bcfgpu_handle* h, int f, const double* x)
         const int nc = std::min(chunk, F.p - c0);
         cudaError_t e = cudaMemcpyAsync(stage, x + (size_t)c0 * n, (size_t)nc * n * 8, cudaMemcpyHostToDevice, h->stream);
         if (e != cudaSuccess) { rc = fail(BCFGPU_ERR_CUDA, std::string("H2D of X: ") + cudaGetErrorString(e)); break; }
+        h->h2d_bytes += (int64_t)nc * n * 8;
         dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 4096), (unsigned)nc);
         k_bin<<<grid, 256, 0, h->stream>>>(stage, n, nc, c0, F.d_cuts, F.d_off, F.d_col_index, F.d_is16, h->d_pos,
                                             h->n_pad, F.d_bins8, F.d_bins16);
@@ -424,6 +435,15 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
 {
     USE(h);
     const bcfgpu_config& c = h->cfg;
+    const bool sdprof = getenv("BCFGPU_SETDATA_PROFILE") != nullptr;
+    auto sd_t0 = std::chrono::steady_clock::now();
+    auto sd_mark = [&](const char* what) {
+        if (!sdprof) return;
+        cudaStreamSynchronize(h->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bcfgpu set_data] %-28s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - sd_t0).count());
+        sd_t0 = now;
+    };
     if (n < 1 || n > 2000000000ll) return fail(BCFGPU_ERR_BAD_ARG, "n must be in [1, 2e9]");
     if (!y || !z || !xcon || !cuts_con || !cut_off_con) return fail(BCFGPU_ERR_BAD_ARG, "null data pointer");
     if (p_con < 1 || p_con > 65535) return fail(BCFGPU_ERR_BAD_ARG, "p_con must be in [1, 65535]");
@@ -434,11 +454,13 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
         if (z[i] != 0 && z[i] != 1) return fail(BCFGPU_ERR_BAD_ARG, "z must be 0/1");
         if (!std::isfinite(y[i])) return fail(BCFGPU_ERR_BAD_ARG, "y must be finite");
     }
+    sd_mark("argument checks");
     CK(cudaStreamSynchronize(h->stream));
     drop_graph(h);
     free_list(h->allocs);
     free_list(h->run_allocs);
     h->has_data = false;
+    h->h2d_bytes = 0;
     h->coop_grid = 0;
     h->shard_decided = false;
     h->n = n;
@@ -469,6 +491,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     }
     d.nu = c.nu; d.lambda = c.lambda; d.con_sd = c.con_sd; d.mod_sd = c.mod_sd;
 
+    sd_mark("permutation (host)");
     DM(h, &h->d_pos, (size_t)n);
     DM(h, &h->d_orig, (size_t)n_pad);
     CK(cudaMemcpyAsync(h->d_pos, h->pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
@@ -493,6 +516,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     DM(h, &h->d_done, 4);
     if (getenv("BCFGPU_PROFILE")) { DM(h, &d.prof, 1024 + 512 * 8); CK(cudaMemsetAsync(d.prof, 0, (1024 + 512 * 8) * 8, h->stream)); }
     d.y = dy;
+    sd_mark("device allocations");
     CK(cudaMemsetAsync(d.totals, 0, (size_t)2 * h->T * KEYS * 8 * 8, h->stream));
     CK(cudaMemsetAsync(d.cross, 0, (size_t)2 * h->T * PIPE_XSTRIDE * 8, h->stream));
     CK(cudaMemsetAsync(d.mom, 0, 2 * 2 * NMOM * 3 * 8, h->stream));
@@ -505,13 +529,23 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
         std::vector<double> yi((size_t)n_pad, 0.0);
         for (int64_t i = 0; i < n; ++i) yi[h->pos[i]] = y[i];
         CK(cudaMemcpyAsync(dy, yi.data(), (size_t)n_pad * 8, cudaMemcpyHostToDevice, h->stream));
+        h->h2d_bytes += (int64_t)n_pad * 8 + (int64_t)n * 4 + (int64_t)n_pad * 4;   // y, pos, orig
         CK(cudaStreamSynchronize(h->stream));
     }
+    sd_mark("clears + y (host scatter, H2D)");
     int rc;
+    // x_moderate = the leading columns of x_control (same buffer, column-major, same cutpoints)?  Then bin once.
+    bool shared_x = p_mod > 0 && xmod == xcon && p_mod <= p_con && cut_off_mod[0] == 0 && cut_off_con[0] == 0;
+    for (int v = 0; shared_x && v < p_mod; ++v) {
+        const int nc = cut_off_con[v + 1] - cut_off_con[v];
+        shared_x = cut_off_mod[v] == cut_off_con[v] && cut_off_mod[v + 1] - cut_off_mod[v] == nc &&
+                   memcmp(cuts_mod + cut_off_mod[v], cuts_con + cut_off_con[v], (size_t)std::max(nc, 0) * 8) == 0;
+    }
     if ((rc = setup_forest(h, 0, p_con, cuts_con, cut_off_con))) return rc;
-    if ((rc = setup_forest(h, 1, p_mod, cuts_mod, cut_off_mod))) return rc;
+    if ((rc = setup_forest(h, 1, p_mod, cuts_mod, cut_off_mod, shared_x ? &h->fh[0] : nullptr))) return rc;
     if ((rc = bin_forest(h, 0, xcon))) return rc;
-    if ((rc = bin_forest(h, 1, xmod))) return rc;
+    if (!shared_x && (rc = bin_forest(h, 1, xmod))) return rc;
+    sd_mark("X: H2D + binning");
     fill_forest_dev(h, 0, d.f[0]);
     fill_forest_dev(h, 1, d.f[1]);
 
@@ -529,6 +563,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
         CK(cudaMemcpyAsync(ysum, dq, 40, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    sd_mark("ybar (host)");
     h->n_global = ysum[0];
     d.n_global = h->n_global;
     if (h->n_global > 2000000000ll) return fail(BCFGPU_ERR_BAD_ARG, "more than 2e9 observations over all shards");
@@ -559,6 +594,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
+    sd_mark("trees + initial state");
     h->has_data = true;
     h->nsaved = 0;
     return BCFGPU_OK;
@@ -747,6 +783,12 @@ int bcfgpu_last_run_ms(bcfgpu_handle* h, double* ms)
 {
     if (!h || !ms) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
     *ms = h->last_ms;
+    return BCFGPU_OK;
+}
+int bcfgpu_h2d_bytes(bcfgpu_handle* h, int64_t* bytes)
+{
+    if (!h || !bytes) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
+    *bytes = h->h2d_bytes;
     return BCFGPU_OK;
 }
 int bcfgpu_kernel_launches(bcfgpu_handle* h, int64_t* count)

@@ -85,6 +85,7 @@ def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_cont
             nu=3.0, lambda_=None, sigq=0.9, sighat=None, use_tauscale=True) -> Prepared:
     """bcf's R-side preamble [bcf-recall, SURVEY A.1].  Returns arrays in the ORIGINAL row order plus `perm`
     (treated rows first, stable: R's order(z, decreasing=TRUE)); the native library applies the permutation."""
+    same_x = x_moderate is x_control            # bcf(y, z, x, x, pihat): what BayesIV calls (R/bcf_iv.R:89)
     y = np.asarray(y, dtype=np.float64).ravel()
     z = np.asarray(z).ravel()
     x_control = np.asarray(x_control, dtype=np.float64)
@@ -109,8 +110,15 @@ def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_cont
     if np.unique(y).size < 5:
         warnings.warn("y appears to be discrete")
 
-    x_c = np.column_stack([x_control, pihat]) if include_pi in ("control", "both") else x_control
-    x_m = np.column_stack([x_moderate, pihat]) if include_pi in ("moderate", "both") else x_moderate
+    if same_x and include_pi == "control":
+        # one column-major matrix [x | pihat]; x_moderate is its leading columns (the library then bins and copies it once)
+        x_c = np.empty((n, x_control.shape[1] + pihat.shape[1]), dtype=np.float64, order="F")
+        x_c[:, :x_control.shape[1]] = x_control
+        x_c[:, x_control.shape[1]:] = pihat
+        x_m = x_c[:, :x_control.shape[1]]
+    else:
+        x_c = np.column_stack([x_control, pihat]) if include_pi in ("control", "both") else x_control
+        x_m = np.column_stack([x_moderate, pihat]) if include_pi in ("moderate", "both") else x_moderate
 
     P = Prepared()
     P.n = n
@@ -120,7 +128,7 @@ def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_cont
     P.z = z.astype(np.int32)
     P.x_c, P.x_m = x_c, x_m
     P.cuts_c = make_cutpoints(x_c)
-    P.cuts_m = make_cutpoints(x_m)
+    P.cuts_m = P.cuts_c[:x_m.shape[1]] if x_m.base is x_c else make_cutpoints(x_m)
     P.sighat = float(sighat) if sighat is not None else lm_sigma(P.yscale, z, x_c)
     P.lambda_ = float(lambda_) if lambda_ is not None else P.sighat ** 2 * qchisq(1.0 - sigq, nu) / nu
     P.perm = np.argsort(-P.z, kind="stable")          # treated first, ties in original order

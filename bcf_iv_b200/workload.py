@@ -47,5 +47,6 @@ def synthetic_sampler_inputs(n, p, seed=0, rho=0.0, compliance=0.75, effect_size
     cell = (2 * x1 + x2).astype(np.int64) * 2 + z
     sig = np.sqrt(np.mean([(yscale[cell == k]).var() for k in range(8) if np.any(cell == k)]))
     lam = sig ** 2 * prep.qchisq(0.1, 3.0) / 3.0
-    return dict(y=yscale, z=z, x_con=x_con, x_mod=X, cuts_con=cc, off_con=oc, cuts_mod=cm, off_mod=om,
+    return dict(y=yscale, z=z, x_con=x_con, x_mod=x_con[:, :p],   # x_mod: the leading columns of x_con, as in bcf(y, z, x, x, pihat)
+                cuts_con=cc, off_con=oc, cuts_mod=cm, off_mod=om,
                 lambda_=float(lam), sigma_init=float(yscale.std(ddof=1)), muy=muy, sdy=sdy, truth=eff * compliance)

@@ -266,6 +266,10 @@ def run_ours(args):
             a = np.asfortranarray(a)
         host[k], t = pinned_like(a)
         keep.append(t)
+    if not sharded and np.shares_memory(w["x_mod"], w["x_con"]):
+        # BayesIV's call is bcf(y, z, x, x, pihat): x_moderate is the leading columns of x_control = [x | pihat]; handed
+        # over as such (same buffer) the library bins and copies the matrix once
+        host["x_mod"] = host["x_con"][:, :w["x_mod"].shape[1]]
 
     engine = {"auto": 0, "graph": 1, "persistent": 2, "persistent_hbm": 3, "batched": 4, "pipelined": 5}[args.engine]
 

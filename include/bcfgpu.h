@@ -117,6 +117,10 @@ BCFGPU_API int bcfgpu_set_data(bcfgpu_handle *h, int64_t n, int32_t p_con, int32
 BCFGPU_API int bcfgpu_run(bcfgpu_handle *h, int32_t nburn, int32_t nsim, int32_t nthin);
 BCFGPU_API int bcfgpu_last_run_ms(bcfgpu_handle *h, double *device_ms);  /* CUDA-event time of the last run */
 BCFGPU_API int bcfgpu_kernel_launches(bcfgpu_handle *h, int64_t *count); /* kernels launched since create */
+/* bytes set_data copied host -> device.  When x_moderate IS the leading columns of x_control (same pointer, same
+ * cutpoints -- what bcf(y, z, x, x, pihat) of R/bcf_iv.R:89 amounts to) the tau forest shares the mu forest's binned
+ * columns and the matrix crosses the bus once. */
+BCFGPU_API int bcfgpu_h2d_bytes(bcfgpu_handle *h, int64_t *bytes);
 /* what the last run used: out[0] sweep kernel (0 graph of per-tree kernels, 1 k_persistent, 2 k_resident, 3 k_batched,
  * 4 k_pipe, 5 k_batched with the state in HBM), out[1] shards exchange (0 none, 1 ncclAllReduce per tree, 2 in-kernel peer-memory mailboxes) */
 BCFGPU_API int bcfgpu_engine_in_use(bcfgpu_handle *h, int32_t out2[2]);

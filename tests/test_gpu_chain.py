@@ -186,3 +186,24 @@ def test_odd_forest_sizes(engine, ntree):
         o.sweeps(k)
         _compare_state(g, o, pr)
     assert g.verify_leaf_cache() == 0
+
+
+def test_shared_covariate_matrix_is_copied_once_and_changes_nothing():
+    """bcf(y, z, x, x, pihat): x_moderate handed over as the leading columns of x_control's buffer is binned and copied
+    once (bcfgpu_h2d_bytes); the chain is bit-identical to the one fed two separate matrices."""
+    pr = make_problem(n=1200, p=9, seed=5)
+    P = pr.P
+    assert np.shares_memory(P.x_m, P.x_c)
+    a = gpu_sampler(pr, seed=4)
+    shared_bytes = a.h2d_bytes
+    a.run(3, 4)
+    from bcf_iv_b200 import _lib
+    b = _lib.Sampler(lambda_=P.lambda_, sigma_init=P.sigma_init, con_sd=P.con_sd, mod_sd=P.mod_sd, seed=4)
+    b.set_data(P.yscale, P.z, P.x_c, np.array(P.x_m, order="F"), pr.cuts_c_flat, pr.off_c, pr.cuts_m_flat, pr.off_m)
+    assert b.h2d_bytes - shared_bytes == P.x_m.size * 8
+    b.run(3, 4)
+    assert a.trace()[0].tobytes() == b.trace()[0].tobytes()
+    assert a.tau_mean().tobytes() == b.tau_mean().tobytes()
+    assert a.sigma().tobytes() == b.sigma().tobytes()
+    for t in range(a.T):
+        assert tree_signature(*a.get_tree(t)[:3]) == tree_signature(*b.get_tree(t)[:3])

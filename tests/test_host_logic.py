@@ -144,3 +144,24 @@ def test_bcf_front_end_validates_before_touching_the_device():
         bcf.bcf(d["y"], d["z"], d["X"], d["X"], np.zeros(50), nburn=10, nsim=10, w=np.ones(50))
     with pytest.raises(NotImplementedError):
         bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], binary=True)
+
+
+def test_prepare_shares_the_matrix_when_bcf_is_called_with_the_same_x_twice():
+    """R/bcf_iv.R:89 calls bcf(y, z, x, x, pihat): x_moderate becomes the leading columns of x_control = [x | pihat]
+    (one buffer), with the same values and cutpoints as two separate matrices would give."""
+    from bcf_iv_b200 import prep
+    rng = np.random.default_rng(2)
+    n, p = 300, 6
+    X = (rng.random((n, p)) < 0.4).astype(float)
+    X[:, 3] = rng.standard_normal(n)
+    y, z, pihat = rng.standard_normal(n), (rng.random(n) < 0.5).astype(int), 0.1 * rng.standard_normal(n)
+    a = prep.prepare(y, z, X, X, pihat)
+    b = prep.prepare(y, z, X, X.copy(), pihat)
+    assert np.shares_memory(a.x_m, a.x_c) and a.x_c.flags.f_contiguous and a.x_m.flags.f_contiguous
+    assert not np.shares_memory(b.x_m, b.x_c)
+    assert np.array_equal(a.x_c, b.x_c) and np.array_equal(a.x_m, b.x_m)
+    assert len(a.cuts_m) == len(b.cuts_m) == p
+    for u, v in zip(a.cuts_m, b.cuts_m):
+        assert np.array_equal(u, v)
+    c = prep.prepare(y, z, X, X, pihat, include_pi="both")      # pihat in both: two matrices again
+    assert not np.shares_memory(c.x_m, c.x_c) and c.x_m.shape[1] == p + 1
