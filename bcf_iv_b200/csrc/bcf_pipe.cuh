@@ -1,20 +1,21 @@
 // bcf_pipe.cuh -- PIPELINED engine: the batched engine with the decisions taken off the observation pass's critical path.
 //
 // In the batched engine a batch costs  pass + flush + grid barrier + decision chain, one after the other, and during
-// the last three almost every warp of the SM idles.  Here the CTA is split in two roles:
+// the last three almost every warp of the SM idles.  Here the CTA is split in three roles:
 //   * 27 TILE warps stream the SM's observations (27 tiles of 256 at the headline size: one round):
-//         STATS(b)  ->  APPLY(b-1)  ->  STATS(b+1) ...
-//   * 1 UTILITY warp does everything of the pass that is not per observation: it flushes batch b's CTA tables to the
-//     grid-wide ones and arrives at grid barrier b, plans batch b+1 and stages its trees;
+//         STATS(b)  ->  flush, warp 0 arrives at grid barrier b  ->  APPLY(b-1)  ->  STATS(b+1) ...
 //   * 4 CHAIN warps (one per tree of a batch) wait for grid barrier b, fetch the reduced statistics, walk the decision
-//     chain of batch b and publish its apply tables.
+//     chain of batch b and publish its apply tables;
+//   * 1 UTILITY warp plans the batches and stages their trees from HBM, two batches ahead of the statistics, paced by
+//     a shared-memory progress counter: nothing waits for it in the steady state.
 // STATS(b) therefore runs while batch b-1 is still being decided: it sees the residual WITHOUT batch b-1's update.
 // That is repaired exactly like the dependencies inside a batch (bcf_batched.cuh): the pass also counts, per pair
 // (tree m of batch b-1, tree q of batch b), how many observations fall in each pair of keys, and the chain folds
 // D_m * N into tree q's integer sums before deciding it.  Still bit-identical to the tree-at-a-time chain.
-// CTA-local hand-shakes are named barriers (S(b): tile warps -> utility "statistics of b complete"; PL(b): utility ->
-// tile warps "plan of b ready"; H1(b): utility -> chain "batch b flushed, planned, staged"; H2(b): chain -> everybody
-// "batch b's tables are ready"); the grid barrier is arrived at by the utility warp and waited for by the chain warps.
+// CTA-local hand-shakes: named barriers S(b) / F(b) among the tile warps ("statistics of b complete" / "b flushed"),
+// H1(b): tile warp 0 -> chain "batch b flushed (and, transitively, planned and staged)", H2(b): chain -> tile warps
+// "batch b's tables are ready"; counters plan_ready / flushed in shared memory (release / acquire) between the utility
+// warp and tile warp 0.  The grid barrier is arrived at by tile warp 0 and waited for by the chain warps.
 //
 // Only sweeps whose trees all have <= KB keys run here: when a wider tree shows up at the start of a sweep the kernel
 // parks the chain state and returns; the host runs that sweep with the batched engine and comes back.
@@ -24,7 +25,7 @@
 namespace bcf {
 
 constexpr int PNB = 4;                               // trees per batch of this engine (its syncs are hidden: small batches
-                                                     // mean less cross-counting; and 28 warps hold an SM's 27 tiles in ONE round)
+                                                     // mean less cross-counting; and 27 warps hold an SM's 27 tiles in ONE round)
 constexpr int PP_WARPS = 28;                         // pass warps: PT_WARPS tile warps + the utility warp
 constexpr int PT_WARPS = PP_WARPS - 1;
 #ifndef PIPE_CHAIN_FIRST
@@ -32,7 +33,7 @@ constexpr int PT_WARPS = PP_WARPS - 1;
 #endif
 constexpr int PR_WARPS = PNB;                        // chain warps: one per tree of a batch
 constexpr int PP_THREADS = PP_WARPS * 32, PR_THREADS = PR_WARPS * 32;
-constexpr int PIPE_THREADS = PP_THREADS + PR_THREADS;   // 768
+constexpr int PIPE_THREADS = PP_THREADS + PR_THREADS;   // 1024
 constexpr int PMAXC = 12;                            // columns ((tree, key >= 1) pairs) of a batch
 constexpr int PXW = 72;                              // cells between trees of one batch: (C^2 - sum c_q^2) / 2 <= 66
 constexpr int PXX = PMAXC * PMAXC;                   // cells between two consecutive batches
@@ -41,10 +42,10 @@ constexpr int PIPE_XSTRIDE = 512;                    // words per batch slot of 
 constexpr int PIPE_BYTES_PER_TILE = TILE * (8 + 8) + 2 * (PNB / 2) * TILE;   // R, G, nibble-packed keys of two batches
 static_assert(2 * PXCAP <= PIPE_XSTRIDE, "cross-count slot too small");
 
-// registers per thread: 768 x 80 at launch; the role section re-splits the CTA's OWN
-// allocation (the pool of setmaxnreg is per CTA): 512 x 72 + 256 x 96 = 61440
+// registers per thread: 1024 x 64 at launch; the role section re-splits the CTA's OWN allocation (the pool of setmaxnreg
+// is per CTA, the instruction per warpgroup of 4 warps): 896 x 56 + 128 x 112 = 64512
 constexpr int PIPE_REGS_BASE = 64, PIPE_REGS_PASS = 56, PIPE_REGS_RESOLVE = 112;
-enum { BAR_S = 5, BAR_F = 8, BAR_H1 = 9, BAR_H2 = 11, BAR_PASS = 13, BAR_RES = 14 };   // 1..PNB: the decision chain
+enum { BAR_S = 5, BAR_F = 8, BAR_H1 = 9, BAR_H2 = 11, BAR_RES = 14 };   // 1..PNB: the decision chain
 constexpr int H1_THREADS = 32 + PR_THREADS;          // tile warp 0 arrives, chain warps wait
 constexpr int PT_THREADS = PT_WARPS * 32;
 constexpr int H2_THREADS = PT_THREADS + PR_THREADS;  // chain warps arrive, tile warps wait
