@@ -241,13 +241,14 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     X = np.asarray(x, dtype=np.float64)
     names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
     disc, index = _split(len(y), inference_ratio, seed)
-    pihat = logit_link(z[disc], X[disc])
+    Xd = X[disc]                                    # the same matrix twice, as the reference passes it: copied to the GPU once
+    pihat = logit_link(z[disc], Xd)
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)
-    pic = _bcf.bcf(w[disc], z[disc], X[disc], X[disc], pihat, **fit_args)["tau_mean"]      # P(complier | x)
-    itt = _bcf.bcf(y[disc], z[disc], X[disc], X[disc], pihat, **fit_args)["tau_mean"]      # R/bcf_iv.R:89-91
+    pic = _bcf.bcf(w[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"]                # P(complier | x)
+    itt = _bcf.bcf(y[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"]                # R/bcf_iv.R:89-91
     tauhat = itt / pic                                                                      # R/bcf_iv.R:94
-    nodes, where = cart(X[disc], tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
+    nodes, where = cart(Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
     ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
     leaves = {nid for nid in ids if nodes[nid].left is None}
     tab = pd.DataFrame([rows[n] if rows[n] is not None else {c: None for c in COLUMNS[:-1]} for n in ids],
@@ -274,8 +275,9 @@ def bcf_itt(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5
     pihat = logit_link(z[disc], X[disc])
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)
-    tauhat = _bcf.bcf(y[disc], z[disc], X[disc], X[disc], pihat, **fit_args)["tau_mean"]   # R/bcf_itt.R:71-75
-    nodes, where = cart(X[disc], tauhat, maxdepth=max_depth)                                # rpart defaults (R/bcf_itt.R:82)
+    Xd = X[disc]
+    tauhat = _bcf.bcf(y[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"]             # R/bcf_itt.R:71-75
+    nodes, where = cart(Xd, tauhat, maxdepth=max_depth)                                     # rpart defaults (R/bcf_itt.R:82)
     ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
     for nid in ids:
         r = rows[nid]
