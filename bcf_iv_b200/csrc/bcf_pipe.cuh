@@ -99,7 +99,7 @@ struct PipeSmem {
     PreKey pre[PNB * (KB + 1)];
     PipeConsts cons[2];                               // per forest, per sweep
     union { PipeAcc acc[2]; StatTabT<32> tab; double red[2 * PIPE_THREADS]; } p;
-    uint8_t colb[PP_WARPS][2 * PMAXC][32];
+    alignas(16) uint8_t colb[PP_WARPS][2 * PMAXC][32];   // read 16 bytes at a time
 };
 constexpr size_t PIPE_SMEM_BYTES = (sizeof(PipeSmem) + 15) / 16 * 16;
 
