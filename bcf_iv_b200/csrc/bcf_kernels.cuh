@@ -481,6 +481,120 @@ __global__ void __launch_bounds__(256) k_hist(Dev d, int forest, const uint8_t* 
 // the fixed-point residual + warp REDUX into a shared-memory table of 32-bit words (count, three 21-bit limbs).  Bin 0
 // of a (leaf, column) is the leaf total minus the other bins (exact in integers), formed when the CTA flushes.
 // Algorithmic traffic: n * (9 + columns) bytes -- every byte is read once.
+// K2' for two-valued columns (the reference's covariates are binary: one cutpoint, bins {0, 1}).  Per observation and
+// column the work is ONE predicated fp64 add: every lane keeps, in registers, the sum of r and the count over its
+// observations for each (column, leaf) cell of the CTA's column chunk; bin 0 is (leaf total - bin 1), formed by the
+// host from the leaf totals the chunk-0 CTAs add.  grid = (tile ranges, column chunks).  The lane sums are fp64 in a
+// fixed order (tile order), reduced over the warp by shuffles and over the CTA's warps in warp order, then rounded ONCE
+// to the 2^-44 fixed-point grid and added with integer atomics: reproducible for a given launch shape, and within
+// 1e-13 relative of the exact sums.
+#ifndef HISTB_CELLS_N
+#define HISTB_CELLS_N 12
+#endif
+constexpr int HISTB_CELLS = HISTB_CELLS_N;   // (column, leaf) cells per CTA: that many sums + counts in registers (two CTAs per SM)
+template <int NLEAF>
+__global__ void __launch_bounds__(256, 2) k_hist_bits(Dev d, int forest, const uint8_t* __restrict__ label,
+                                                   const double* __restrict__ r, const int32_t* __restrict__ off,
+                                                   const int32_t* __restrict__ cols, int ncols, int tiles_per_cta,
+                                                   long long* out, long long* leaf_tot_out)
+{
+    constexpr int CPC = HISTB_CELLS / NLEAF;                     // columns per chunk
+    __shared__ double ssum[8][HISTB_CELLS + NLEAF];
+    __shared__ int scnt[8][HISTB_CELLS + NLEAF];
+    const ForestDev& F = d.f[forest];
+    const int t = threadIdx.x, lane = t & 31, wib = t >> 5;
+    const int c0 = blockIdx.y * CPC, nc = min(CPC, ncols - c0);
+    const bool totals = blockIdx.y == 0;
+    double acc[CPC][NLEAF], tot[NLEAF];
+    int cnt[CPC][NLEAF], tcnt[NLEAF];
+#pragma unroll
+    for (int l = 0; l < NLEAF; ++l) {
+        tot[l] = 0.0; tcnt[l] = 0;
+#pragma unroll
+        for (int c = 0; c < CPC; ++c) { acc[c][l] = 0.0; cnt[c][l] = 0; }
+    }
+    const uint8_t* colp[CPC];
+#pragma unroll
+    for (int c = 0; c < CPC; ++c) colp[c] = F.bins8 + (int64_t)F.col_index[cols[c0 + min(c, nc - 1)]] * d.n_pad;
+    const int tile_lo = blockIdx.x * tiles_per_cta, tile_hi = min(d.n_tiles, tile_lo + tiles_per_cta);
+    for (int tile = tile_lo + wib; tile < tile_hi; tile += 8) {
+        const int64_t base = (int64_t)tile * TILE + lane * 8;
+        const uint2 lab = *reinterpret_cast<const uint2*>(label + base);
+        uint2 bn[CPC];
+#pragma unroll
+        for (int c = 0; c < CPC; ++c) bn[c] = *reinterpret_cast<const uint2*>(colp[c] + base);
+        double rd[8];
+        ld8_f64(r + base, rd);
+        uint32_t lb[NLEAF];                                       // which of the lane's 8 observations sit in leaf l (labels >= NLEAF: none)
+#pragma unroll
+        for (int l = 0; l < NLEAF; ++l) {
+            const uint32_t lv = (uint32_t)l * 0x01010101u;
+            lb[l] = bytes_to_bits(__vcmpeq4(lab.x, lv), __vcmpeq4(lab.y, lv));
+            if (totals) {
+#pragma unroll
+                for (int o = 0; o < 8; ++o) tot[l] += ((lb[l] >> o) & 1u) ? rd[o] : 0.0;
+                tcnt[l] += __popc(lb[l]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CPC; ++c) {
+            if (c < nc) {
+                const uint32_t one = bytes_to_bits(__vcmpeq4(bn[c].x, 0x01010101u), __vcmpeq4(bn[c].y, 0x01010101u));
+#pragma unroll
+                for (int l = 0; l < NLEAF; ++l) {
+                    const uint32_t bits = one & lb[l];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) acc[c][l] += ((bits >> o) & 1u) ? rd[o] : 0.0;
+                    cnt[c][l] += __popc(bits);
+                }
+            }
+        }
+    }
+    // lanes -> warp (xor tree), warps -> CTA (warp order), then one rounding to fixed point
+#pragma unroll
+    for (int c = 0; c < CPC; ++c)
+#pragma unroll
+        for (int l = 0; l < NLEAF; ++l) {
+            double v = acc[c][l];
+            int k = cnt[c][l];
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, sft); k += __shfl_xor_sync(0xffffffffu, k, sft); }
+            if (lane == 0) { ssum[wib][c * NLEAF + l] = v; scnt[wib][c * NLEAF + l] = k; }
+        }
+#pragma unroll
+    for (int l = 0; l < NLEAF; ++l) {
+        double v = tot[l];
+        int k = tcnt[l];
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, sft); k += __shfl_xor_sync(0xffffffffu, k, sft); }
+        if (lane == 0) { ssum[wib][HISTB_CELLS + l] = v; scnt[wib][HISTB_CELLS + l] = k; }
+    }
+    __syncthreads();
+    if (t < HISTB_CELLS + NLEAF) {
+        double v = 0.0;
+        long long k = 0;
+        for (int w = 0; w < 8; ++w) { v += ssum[w][t]; k += scnt[w][t]; }
+        int bad = 0;
+        const long long fx = to_fixed(v, bad);
+        long long* o = nullptr;
+        if (t < HISTB_CELLS) {
+            const int c = t / NLEAF, l = t % NLEAF;
+            if (c < nc) {
+                const int col = cols[c0 + c];
+                const int64_t nbt = (int64_t)off[F.p] + F.p;
+                o = out + ((int64_t)l * nbt + (int64_t)off[col] + col + 1) * 4;      // bin 1
+            }
+        } else if (totals) o = leaf_tot_out + (t - HISTB_CELLS) * 4;
+        if (o != nullptr && (k != 0 || fx != 0)) {
+            atomicAdd((unsigned long long*)&o[0], (unsigned long long)k);
+            atomicAdd((unsigned long long*)&o[1], (unsigned long long)(fx & 0x1FFFFF));
+            atomicAdd((unsigned long long*)&o[2], (unsigned long long)((fx >> LIMB_BITS) & 0x1FFFFF));
+            atomicAdd((unsigned long long*)&o[3], (unsigned long long)(fx >> (2 * LIMB_BITS)));
+        }
+        if (bad) atomicOr(d.err, ERR_FX_RANGE);
+    }
+}
+
 constexpr int HIST2_MAX_BINS = 4;        // bins 0..3 (up to 3 cutpoints)
 constexpr int HIST2_MAX_LEAF = 16;
 constexpr int HIST2_CELL_WORDS = 49152 / 16;   // shared table: cells of 4 x u32

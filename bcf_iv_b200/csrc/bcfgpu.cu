@@ -1179,14 +1179,19 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
     CK(cudaMemcpyAsync(h->d_tmp, r, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
     k_permute_in<<<(int)std::min<int64_t>((h->n + 255) / 256, 4096), 256, 0, h->stream>>>(h->d_tmp, h->d_pos, h->n, h->d_tmp2);
     CK(cudaMemsetAsync(dout, 0, (size_t)nleaf * nbt * 32, h->stream));
-    // columns with at most HIST2_MAX_BINS bins go through the one-pass kernel, the others through the per-column one.
+    // two-valued columns (one cutpoint) with at most 8 leaves: k_hist_bits (register accumulators, one predicated fp64 add
+    // per observation and column); other columns with at most HIST2_MAX_BINS bins go through the one-pass kernel, the rest
+    // through the per-column one.
     // Few (leaf, bin) cells per column: one masked warp sum per cell (bin 0 by subtraction); many: one shared atomic
     // per word and observation (every bin has its cell).
     const bool per_obs = false;   // measured on B200 (n = 1e6, 100 binary columns): the masked sums win up to 16 leaves
     const size_t smem_cap = 160 * 1024;
-    std::vector<int32_t> small, large, cellbase;
+    std::vector<int32_t> small, large, cellbase, twoval;
     int ncells = 0;
+    const int nl2 = nleaf <= 1 ? 1 : nleaf <= 2 ? 2 : nleaf <= 4 ? 4 : 8;     // k_hist_bits is instantiated for 1, 2, 4, 8 leaves
+    const bool use_bits = nleaf <= 8 && !getenv("BCFGPU_NO_HIST_BITS");
     for (int v = 0; v < F.p; ++v) {
+        if (use_bits && !F.is16[v] && F.ncut[v] == 1) { twoval.push_back(v); continue; }   // two-valued: register accumulators
         const int add = per_obs ? nleaf * (F.ncut[v] + 1) : nleaf * F.ncut[v];
         const size_t need = per_obs ? (size_t)(ncells + add) * 32 : (size_t)(ncells + add + nleaf) * 16;
         if (!F.is16[v] && F.ncut[v] + 1 <= HIST2_MAX_BINS && nleaf <= HIST2_MAX_LEAF && need <= smem_cap) {
@@ -1194,14 +1199,35 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
         } else large.push_back(v);
     }
     int32_t* dcols = nullptr;
-    CK(cudaMalloc((void**)&dcols, (size_t)(small.size() * 2 + large.size() + 1) * 4));
+    CK(cudaMalloc((void**)&dcols, (size_t)(small.size() * 2 + large.size() + twoval.size() + 4) * 4 + 8 * 32));
     int32_t* dsmall = dcols; int32_t* dbase = dcols + small.size(); int32_t* dlarge = dcols + 2 * small.size();
+    int32_t* dtwo = dlarge + large.size();
+    long long* dleaf = reinterpret_cast<long long*>(dcols + ((small.size() * 2 + large.size() + twoval.size() + 2) & ~(size_t)1));   // 8 leaves x 4 words
+    if (!twoval.empty()) {
+        CK(cudaMemcpyAsync(dtwo, twoval.data(), twoval.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemsetAsync(dleaf, 0, 8 * 32, h->stream));
+    }
     if (!small.empty()) {
         CK(cudaMemcpyAsync(dsmall, small.data(), small.size() * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(dbase, cellbase.data(), cellbase.size() * 4, cudaMemcpyHostToDevice, h->stream));
     }
     if (!large.empty()) CK(cudaMemcpyAsync(dlarge, large.data(), large.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
+    if (!twoval.empty()) {
+        const int cpc = HISTB_CELLS / nl2, gy = ((int)twoval.size() + cpc - 1) / cpc;
+        const int tiles = h->dev.n_tiles;
+        const int waves = getenv("BCFGPU_HIST_WAVES") ? std::max(1, atoi(getenv("BCFGPU_HIST_WAVES"))) : 4;
+        const int gx = std::max(1, std::min(tiles, (h->num_sms * 2 * waves + gy - 1) / gy));   // four waves of two CTAs per SM (measured best of 1, 2, 4)
+        const int tpc = (tiles + gx - 1) / gx;
+        dim3 grid((unsigned)((tiles + tpc - 1) / tpc), (unsigned)gy);
+        switch (nl2) {
+        case 1: k_hist_bits<1><<<grid, 256, 0, h->stream>>>(h->dev, forest, dlab, h->d_tmp2, F.d_off, dtwo, (int)twoval.size(), tpc, dout, dleaf); break;
+        case 2: k_hist_bits<2><<<grid, 256, 0, h->stream>>>(h->dev, forest, dlab, h->d_tmp2, F.d_off, dtwo, (int)twoval.size(), tpc, dout, dleaf); break;
+        case 4: k_hist_bits<4><<<grid, 256, 0, h->stream>>>(h->dev, forest, dlab, h->d_tmp2, F.d_off, dtwo, (int)twoval.size(), tpc, dout, dleaf); break;
+        default: k_hist_bits<8><<<grid, 256, 0, h->stream>>>(h->dev, forest, dlab, h->d_tmp2, F.d_off, dtwo, (int)twoval.size(), tpc, dout, dleaf); break;
+        }
+        h->launches++;
+    }
     if (!small.empty()) {
         // at most 48 tiles per CTA between flushes (32-bit table words), at least ~2 CTAs per SM
         const int tiles = h->dev.n_tiles;
@@ -1220,8 +1246,15 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
     CK(cudaEventRecord(h->ev1, h->stream));
     h->launches += 2;
     std::vector<long long> tot((size_t)nleaf * nbt * 4);
+    long long leaf_tot[8 * 4] = {0};
     e = cudaMemcpyAsync(tot.data(), dout, tot.size() * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && !twoval.empty()) e = cudaMemcpyAsync(leaf_tot, dleaf, sizeof(leaf_tot), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    for (int v : twoval)               // bin 0 of a two-valued column: the leaf's total minus bin 1 (word by word: the representation is linear)
+        for (int l = 0; l < nleaf; ++l) {
+            long long* o0 = &tot[((size_t)l * nbt + (size_t)F.off[v] + v) * 4];
+            for (int q = 0; q < 4; ++q) o0[q] = leaf_tot[l * 4 + q] - o0[4 + q];
+        }
     float ms = 0.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     cudaFree(dlab); cudaFree(dout); cudaFree(dcols);
