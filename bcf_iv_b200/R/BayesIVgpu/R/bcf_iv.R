@@ -7,7 +7,9 @@
 #' @export
 bcf_iv <- function(y, w, z, x, binary = FALSE, n_burn = 500, n_sim = 500, inference_ratio = 0.5, max_depth = 2,
                    cp = 0.01, minsplit = 10, adj_method = "holm", seed = 42) {
-  if (binary) stop("binary = TRUE needs the probit BART of bartCause::bartc, which this build does not replace")
+  # binary = TRUE: the reference fits the ITT with bartCause::bartc (probit BART) here; this build fits it with the same
+  # GPU sampler on the 0/1 outcome (its tau is the ITT on the probability scale, as for the complier proportion)
+  if (binary && !all(y %in% c(0, 1))) stop("binary = TRUE needs a 0/1 outcome")
   x <- as.matrix(x)
   index <- .honest_split(nrow(x), inference_ratio, seed)
   all_rows <- data.frame(y = y, w = w, z = z, x)

@@ -10,7 +10,11 @@ Everything except the sampler stays on the CPU (north_star): the pieces R takes 
 here in closed form (`cart`, `tsls`, `p_adjust`, `logit_link`).  Deviations, all forced by what is not in scope:
   * the complier proportion `pic` comes from the same GPU sampler run on the treatment received (tau of  w ~ z  is
     P(complier | x)) instead of bartCause::bartc (a different third-party sampler, SURVEY 8f-1);
-  * binary = TRUE (the reference switches to bartc there and never reaches bcf) raises NotImplementedError;
+  * binary = TRUE: the reference switches to bartc (probit BART, S-learner) for the ITT and never reaches bcf
+    (R/bcf_iv.R:198-202).  Here the ITT on the probability scale, P(y=1 | z=1, x) - P(y=1 | z=0, x) -- the estimand
+    bartc's "ite" reports for a binary response -- is the tau of the same GPU sampler run on the 0/1 outcome (a linear
+    probability BCF, exactly what is done for `pic`); y must be 0/1.  A substitution, not a restatement: say so when
+    comparing numbers with the reference on config C4;
   * the honest split uses NumPy's generator: the same seed gives a different split than R's sample().
 """
 from __future__ import annotations
@@ -250,10 +254,9 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     """Discovery and estimation of heterogeneity in the complier average causal effect (R/bcf_iv.R:47).
     Returns a pandas DataFrame with the reference's columns (COLUMNS), one row per CART node."""
     import pandas as pd
-    if binary:
-        raise NotImplementedError("binary = TRUE uses bartCause::bartc in the reference (R/bcf_iv.R:198) and never "
-                                  "reaches the BCF sampler; that probit BART path is not part of this build")
     y, w, z = (np.asarray(a, dtype=np.float64).ravel() for a in (y, w, z))
+    if binary and not np.all((y == 0) | (y == 1)):
+        raise ValueError("binary = TRUE needs a 0/1 outcome")
     X = np.asarray(x, dtype=np.float64)
     names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
     disc, index = _split(len(y), inference_ratio, seed)
@@ -287,9 +290,9 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
 def bcf_itt(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5, max_depth=2, seed=42, **bcf_args):
     """Heterogeneity in the intention-to-treat effect (R/bcf_itt.R:33): prints the node effects and returns None,
     as the reference does."""
-    if binary:
-        raise NotImplementedError("binary = TRUE uses bartCause::bartc in the reference (R/bcf_itt.R:166)")
     y, w, z = (np.asarray(a, dtype=np.float64).ravel() for a in (y, w, z))
+    if binary and not np.all((y == 0) | (y == 1)):
+        raise ValueError("binary = TRUE needs a 0/1 outcome")
     X = np.asarray(x, dtype=np.float64)
     names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
     disc, index = _split(len(y), inference_ratio, seed)

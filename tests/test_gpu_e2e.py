@@ -59,6 +59,21 @@ def test_bcf_iv_recovers_the_readme_subgroups():
     assert (leaves["Adj_pvalue"].astype(float) < 0.05).sum() >= 2
 
 
+def test_bcf_iv_binary_outcome_runs_through_the_gpu_sampler():
+    """BASELINE config 4 in small: binary outcome, low compliance, correlated covariates.  The reference uses bartc there
+    (R/bcf_iv.R:198); here the ITT on the probability scale is the tau of the GPU sampler on the 0/1 outcome.  The
+    effect cells (x1 = x2 = 0: y more often 1 under assignment; x1 = x2 = 1: less often) keep their signs."""
+    d = datasets.generate_dataset_wide(n=4000, p=10, rho=0.5, compliance=0.6, seed=3, binary_outcome=True)
+    assert set(np.unique(d["y"])) <= {0.0, 1.0}
+    with pytest.warns(UserWarning, match="discrete"):
+        tab = bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], binary=True, n_burn=300, n_sim=300, max_depth=2, seed=42)
+    assert list(tab.columns) == bayesiv.COLUMNS
+    rules = " ".join(str(r) for r in tab["node"].dropna())
+    assert "x1" in rules or "x2" in rules
+    eff = tab.dropna(subset=["Adj_pvalue"])["CCACE"].astype(float)
+    assert eff.max() > 0.15 and eff.min() < -0.15
+
+
 def test_bcf_itt_prints_and_returns_none(capsys):
     d = datasets.generate_dataset(n=600, p=10, seed=9)
     assert bayesiv.bcf_itt(d["y"], d["w"], d["z"], d["X"], n_burn=150, n_sim=150) is None

@@ -142,7 +142,7 @@ def test_bcf_front_end_validates_before_touching_the_device():
         bcf.bcf(d["y"], d["z"], d["X"], d["X"], np.zeros(50))
     with pytest.raises(NotImplementedError):
         bcf.bcf(d["y"], d["z"], d["X"], d["X"], np.zeros(50), nburn=10, nsim=10, w=np.ones(50))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                       # binary = TRUE needs a 0/1 outcome (checked before any device work)
         bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], binary=True)
 
 
