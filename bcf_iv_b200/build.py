@@ -34,7 +34,8 @@ def needs_build() -> bool:
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("BCFGPU_NVCC_EXTRA", "").split()      # e.g. -DBCF_PROF: compile the phase timers / batch timeline of k_pipe in (BCFGPU_PROFILE, BCFGPU_TRACE); they cost ~6 % of the sweep
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)

@@ -474,7 +474,11 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
     {
         const unsigned FULL = 0xffffffffu;
         const int q = w;
+#ifndef BCF_PROF
+#define CTRACE(e) do { } while (0)
+#else
 #define CTRACE(e) do { if (trc != nullptr && l == 0) trc[w * 8 + (e)] = clock64(); } while (0)
+#endif
         CTRACE(0);
         const bool active = q < nb;
         const int qq = active ? q : 0;
@@ -627,13 +631,17 @@ __device__ __forceinline__ void decision_chain(int w, int l, int nb, int first, 
             }
         }
         CTRACE(1);
-        const bool cprof = d.prof != nullptr && blockIdx.x == 0 && l == 0;
+        [[maybe_unused]] const bool cprof = d.prof != nullptr && blockIdx.x == 0 && l == 0;
         long long ct = 0;
+#ifndef BCF_PROF
+#define CPROF(k) do { } while (0)
+#else
 #define CPROF(k) do { if (cprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[8 + (k)], (unsigned long long)(now_ - ct)); ct = now_; } } while (0)
+#endif
         for (int m = 0; m < nb; ++m) {
             if (active && q == m) {
                 CTRACE(2);
-                if (cprof) ct = clock64();
+                if (cprof) ct = BCF_PROF_CLOCK();
                 // exact integer -> double, as limbs_to_double does
                 const __int128 v0 = limbs_to_i128(wa0, wa1, wa2), v1 = limbs_to_i128(wb0, wb1, wb2);
                 const double S0 = ((double)(long long)(v0 >> 40) * 1099511627776.0 + (double)(long long)(v0 & (((__int128)1 << 40) - 1))) * (1.0 / 17592186044416.0);
@@ -821,10 +829,14 @@ __device__ __forceinline__ void resolve_batch(BatchSmem& sm, BatchStage& B, cons
         __syncthreads();
         return;
     }
-    const bool rprof = d.prof != nullptr && blockIdx.x == 0 && t == 0;
+    [[maybe_unused]] const bool rprof = d.prof != nullptr && blockIdx.x == 0 && t == 0;
     long long rp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long rtp = clock64();
+    [[maybe_unused]] long long rtp = BCF_PROF_CLOCK();
+#ifndef BCF_PROF
+#define RPROF(k) do { } while (0)
+#else
 #define RPROF(k) do { if (rprof) { const long long now_ = clock64(); rp[k] += now_ - rtp; rtp = now_; } } while (0)
+#endif
     const int nb = B.nb;
     ResolveTab& rs = sm.p.rs;
     for (int i = t; i < nb * KB * 8; i += blockDim.x) {
@@ -907,10 +919,14 @@ __device__ __forceinline__ void propose_all_b(BatchSmem& sm, const Dev& d, const
 }
 
 #define BCF_PROF_DECL                                                                                   \
-    const bool prof = (d.prof != nullptr) && blockIdx.x == 0 && t == 0;                                 \
+    [[maybe_unused]] const bool prof = (d.prof != nullptr) && blockIdx.x == 0 && t == 0;                                 \
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                                                         \
-    long long tp = clock64();
+    [[maybe_unused]] long long tp = BCF_PROF_CLOCK();
+#ifndef BCF_PROF
+#define PROF(k) do { } while (0)
+#else
 #define PROF(k) do { if (prof) { const long long now_ = clock64(); pc[k] += now_ - tp; tp = now_; } } while (0)
+#endif
 
 template <bool RES>
 __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, unsigned int* bar, int ntl_max)

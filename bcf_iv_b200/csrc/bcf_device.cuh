@@ -13,6 +13,14 @@
 #include <stdint.h>
 #include <math.h>
 
+// Phase timers / batch timelines of the sweep kernels (BCFGPU_PROFILE, BCFGPU_TRACE) are compiled in only with -DBCF_PROF:
+// the clock reads and their bookkeeping cost ~6 % of a sweep.
+#ifdef BCF_PROF
+#define BCF_PROF_CLOCK() clock64()
+#else
+#define BCF_PROF_CLOCK() 0ll
+#endif
+
 namespace bcf {
 
 constexpr int MAXL = 128;           // BCFGPU_MAX_LEAVES

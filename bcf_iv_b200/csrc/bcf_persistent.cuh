@@ -103,10 +103,14 @@ __device__ __forceinline__ bool peer_wait(const Dev& d, int kind, unsigned long 
 }
 
 #define BCF_PROF_DECL                                                                                   \
-    const bool prof = (d.prof != nullptr) && blockIdx.x == 0 && t == 0;                                 \
+    [[maybe_unused]] const bool prof = (d.prof != nullptr) && blockIdx.x == 0 && t == 0;                                 \
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                                                         \
-    long long tp = clock64();
+    [[maybe_unused]] long long tp = BCF_PROF_CLOCK();
+#ifndef BCF_PROF
+#define PROF(k) do { } while (0)
+#else
 #define PROF(k) do { if (prof) { const long long now_ = clock64(); pc[k] += now_ - tp; tp = now_; } } while (0)
+#endif
 
 // =================================================================================================
 // k_persistent: state in HBM/L2

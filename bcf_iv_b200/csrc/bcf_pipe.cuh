@@ -411,9 +411,13 @@ __device__ inline void pipe_resolve(PipeSmem& sm, SmallStage* st, const PipePlan
 {
     const int nb = P.nb;
     PipeRS& rs = sm.rs;
-    const bool rprof = d.prof != nullptr && blockIdx.x == 0 && rt == 0;
-    long long rtp = clock64();
+    [[maybe_unused]] const bool rprof = d.prof != nullptr && blockIdx.x == 0 && rt == 0;
+    [[maybe_unused]] long long rtp = BCF_PROF_CLOCK();
+#ifndef BCF_PROF
+#define RPROF(k) do { } while (0)
+#else
 #define RPROF(k) do { if (rprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - rtp)); rtp = now_; } } while (0)
+#endif
     {   // the batch's reduced words: every load is issued before the first store (one L2 round trip)
         constexpr int NT_IT = (PNB * KB * 8 + PR_THREADS - 1) / PR_THREADS, NX_IT = (2 * PXCAP + PR_THREADS - 1) / PR_THREADS;
         const long long* xg = cross + (size_t)P.first * PIPE_XSTRIDE;
@@ -614,15 +618,23 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
 
         // The roles need different register budgets (the decision chain keeps a tree's sums, posterior terms and
         // constants live; the pass is a streaming loop): re-split the SM's register file for the role section.
+#ifndef BCF_PROF
+#define PTRACE(k) do { } while (0)
+#else
 #define PTRACE(k) do { if (prof && sw == 0 && b < 64) d.prof[16 + b * 8 + (k)] = clock64(); } while (0)
+#endif
         if (is_pass) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_PASS));
             if (!is_util) {
                 // =================== tile warps ===================
-                const bool prof = d.prof != nullptr && blockIdx.x == 0 && tw == 0 && lane == 0;
-                const bool cprof = d.prof != nullptr && tw == 0 && lane == 0;
-                long long tp = clock64();
+                [[maybe_unused]] const bool prof = d.prof != nullptr && blockIdx.x == 0 && tw == 0 && lane == 0;
+                [[maybe_unused]] const bool cprof = d.prof != nullptr && tw == 0 && lane == 0;
+                [[maybe_unused]] long long tp = BCF_PROF_CLOCK();
+#ifndef BCF_PROF
+#define PPROF(k) do { } while (0)
+#else
 #define PPROF(k) do { if (cprof) { const long long now_ = clock64(); if (prof) atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); atomicAdd((unsigned long long*)&d.prof[1024 + blockIdx.x * 8 + (k)], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
+#endif
                 int first = 0, b = 0;
                 if (lane == 0) pipe_wait_flag(&sm.plan_ready, 1, d.err, 20);     // the first plan
                 __syncwarp();
@@ -676,9 +688,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                     for (int i = lane; i < (int)(2 * sizeof(PipeAcc) / 4); i += 32) tb[i] = 0u;
                 }
                 int pfirst = 0, pb = 0;
-                long long up = clock64();
-                const bool uprof = d.prof != nullptr && lane == 0;
+                [[maybe_unused]] long long up = BCF_PROF_CLOCK();
+                [[maybe_unused]] const bool uprof = d.prof != nullptr && lane == 0;
+#ifndef BCF_PROF
+#define UPROF(k) do { } while (0)
+#else
 #define UPROF(k) do { if (uprof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[1024 + 2048 + blockIdx.x * 8 + (k)], (unsigned long long)(now_ - up)); up = now_; } } while (0)
+#endif
                 while (pfirst < T) {
                     if (pb >= 2) {
                         if (lane == 0) pipe_wait_flag(&sm.flushed, pb - 1, d.err, 200);
@@ -700,10 +716,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
         } else {
             asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_RESOLVE));
             // =================== chain warps ===================
-            const bool prof = d.prof != nullptr && blockIdx.x == 0 && rt == 0;
-            const bool cprof = d.prof != nullptr && rt == 0;
-            long long tp = clock64();
+            [[maybe_unused]] const bool prof = d.prof != nullptr && blockIdx.x == 0 && rt == 0;
+            [[maybe_unused]] const bool cprof = d.prof != nullptr && rt == 0;
+            [[maybe_unused]] long long tp = BCF_PROF_CLOCK();
+#ifndef BCF_PROF
+#define QPROF(k) do { } while (0)
+#else
 #define QPROF(k) do { if (cprof) { const long long now_ = clock64(); if (prof) atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); atomicAdd((unsigned long long*)&d.prof[1024 + blockIdx.x * 8 + (k)], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
+#endif
             if (rt < 2) {   // the sweep's scalars as the decisions use them, per forest (the expressions of resolve_batch)
                 const bool is_con = d.f[rt].is_con != 0;
                 const double s1 = is_con ? sc.mscale : sc.bscale1, s0 = is_con ? sc.mscale : sc.bscale0;

@@ -721,6 +721,14 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
     if ((rc = check_device_err(h))) return rc;
     CK(cudaMemcpy(&sc, d.sc, sizeof(sc), cudaMemcpyDeviceToHost));
     h->nsaved = sc.save_ctr;
+#ifndef BCF_PROF
+    if (d.prof) {
+        static bool told = false;
+        if (!told) fprintf(stderr, "[bcfgpu profile] the phase timers of the sweep kernels are compiled out (they cost ~6 %% of a sweep): "
+                                   "rebuild with BCFGPU_NVCC_EXTRA=-DBCF_PROF python -m bcf_iv_b200.build\n");
+        told = true;
+    } else
+#endif
     if (d.prof) {   // BCFGPU_PROFILE=1: phase cycle counters of CTA 0 (persistent engines)
         long long pc[16];
         CK(cudaMemcpy(pc, d.prof, 128, cudaMemcpyDeviceToHost));
