@@ -302,43 +302,65 @@ __device__ __forceinline__ void pipe_apply_tile(const PipeApply& ap, const Dev& 
     const uint32_t toff = (uint32_t)lt * (TILE * 8u);
     const uint32_t kr = rs.keys + (uint32_t)lt * (uint32_t)(2 * (PNB / 2) * TILE) + (uint32_t)lane * 8u +
                         (uint32_t)parity * (uint32_t)((PNB / 2) * TILE);
-    long long R[8];
-    double G[8];
-    res_ld8i(rs.R + toff, lane, R);
-    res_ld8(rs.G + toff, lane, G);
-    if (fswitch) {   // park the mu forest's fit in HBM, bring the tau forest's in
-        st8_f64(d.Gc + gb, G);
-        ld8_f64(d.Gm + gb, G);
-    }
+    // two halves of 4 observations: half the live state (the role has 56 registers; with all 8 the loop spilled)
     const int na = ap.n;
-    for (int j = 0; 2 * j < na; ++j) {
-        const uint2 w = lds_v2(kr + (uint32_t)j * TILE);
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+        long long R[4];
+        double G[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int q = 2 * j + h;
-            if (q < na) {
-                int key[8];
-                unpack8(make_uint2((w.x >> (4 * h)) & 0x0F0F0F0Fu, (w.y >> (4 * h)) & 0x0F0F0F0Fu), key);
-                const int off = ap.off[q];
-                const ApRow* Tq = &ap.T[g][off];
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t a = (uint32_t)((hf * 4 + k) * 32 + lane) * 8u;
+            const uint2 v = lds_v2(rs.R + toff + a);
+            R[k] = (long long)(((unsigned long long)v.y << 32) | v.x);
+            G[k] = lds_f64(rs.G + toff + a);
+        }
+        if (fswitch) {   // park the mu forest's fit in HBM, bring the tau forest's in
+            double2* gc = reinterpret_cast<double2*>(d.Gc + gb + hf * 4);
+            const double2* gm = reinterpret_cast<const double2*>(d.Gm + gb + hf * 4);
+            gc[0] = make_double2(G[0], G[1]); gc[1] = make_double2(G[2], G[3]);
+            const double2 m0 = gm[0], m1 = gm[1];
+            G[0] = m0.x; G[1] = m0.y; G[2] = m1.x; G[3] = m1.y;
+        }
+        for (int j = 0; 2 * j < na; ++j) {
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(kr + (uint32_t)j * TILE + (uint32_t)hf * 4u) : "memory");
 #pragma unroll
-                for (int o = 0; o < 8; ++o) {
-                    if (PAD && key[o] == 15) continue;
-                    const ApRow r = Tq[key[o]];
-                    R[o] -= r.dr;
-                    G[o] += r.dg;
-                }
-                if (ap.changed[q]) {
-                    int ns[8];
+            for (int h = 0; h < 2; ++h) {
+                const int q = 2 * j + h;
+                if (q < na) {
+                    const uint32_t kk = (w >> (4 * h)) & 0x0F0F0F0Fu;
+                    const int off = ap.off[q];
+                    const ApRow* Tq = &ap.T[g][off];
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) ns[o] = (PAD && key[o] == 15) ? PAD_SLOT : (int)ap.NS[off + key[o]];
-                    st8_u8(d.slots + (int64_t)(ap.first + q) * d.n_pad + gb, ns);
+                    for (int o = 0; o < 4; ++o) {
+                        const int key = (int)((kk >> (8 * o)) & 0xFFu);
+                        if (PAD && key == 15) continue;
+                        const ApRow r = Tq[key];
+                        R[o] -= r.dr;
+                        G[o] += r.dg;
+                    }
+                    if (ap.changed[q]) {
+                        uint32_t nsw = 0u;
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            const int key = (int)((kk >> (8 * o)) & 0xFFu);
+                            const uint32_t ns = (PAD && key == 15) ? (uint32_t)PAD_SLOT : (uint32_t)ap.NS[off + key];
+                            nsw |= ns << (8 * o);
+                        }
+                        *reinterpret_cast<uint32_t*>(d.slots + (int64_t)(ap.first + q) * d.n_pad + gb + hf * 4) = nsw;
+                    }
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t a = (uint32_t)((hf * 4 + k) * 32 + lane) * 8u;
+            sts_f64(rs.G + toff + a, G[k]);
+            const unsigned long long u = (unsigned long long)R[k];
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs.R + toff + a), "r"((uint32_t)u), "r"((uint32_t)(u >> 32)) : "memory");
+        }
     }
-    res_st8(rs.G + toff, lane, G);
-    res_st8i(rs.R + toff, lane, R);
 }
 
 // the CTA's tables of one batch -> the grid-wide ones, by the tile warps (one word per thread); leaves the tables zeroed
