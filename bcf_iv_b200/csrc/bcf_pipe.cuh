@@ -209,8 +209,10 @@ __device__ inline void pipe_plan(PipePlan& P, const PipePlan* prev, const Dev& d
 }
 
 // statistics of batch P over one warp tile; `kw` / `kr`: key areas of this batch (written) and of the previous one
+// keep_prev: this warp has ONE tile (a single round of tiles), so the byte columns it formed for the previous batch are still
+// in its column buffer (they live in the halves of `colb` by batch parity) and need not be rebuilt from the stored keys.
 __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, PipeAcc& acc, const PipePlan& P, const Dev& d, const PipePtrs& rs,
-                                                int tile0, int lt, int lane, int warp, int parity)
+                                                int tile0, int lt, int lane, int warp, int parity, bool keep_prev)
 {
     const int tile = tile0 + lt;
     const int g = tile < d.trt_tiles ? 1 : 0;
@@ -230,7 +232,8 @@ __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, PipeAcc& acc, cons
         for (int o = 0; o < 8; ++o) tot += R[o];
         warp_add21(acc.totr[g], tot, lane);
     }
-    uint8_t* colb = &sm.colb[warp][0][0];
+    uint8_t* colb = &sm.colb[warp][parity * PMAXC][0];            // this batch's columns
+    uint8_t* colp = &sm.colb[warp][(parity ^ 1) * PMAXC][0];      // the previous batch's
     const int nb = P.nb;
     uint2 held = make_uint2(0u, 0u);
     for (int q = 0; q < nb; ++q) {
@@ -262,7 +265,7 @@ __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, PipeAcc& acc, cons
         }
     }
     // the previous batch's columns, from its stored keys
-    const int np = P.nprev;
+    const int np = keep_prev ? 0 : P.nprev;
     for (int j = 0; 2 * j < np; ++j) {
         const uint2 w = lds_v2(kr + (uint32_t)j * TILE);
 #pragma unroll
@@ -270,7 +273,7 @@ __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, PipeAcc& acc, cons
             const int m = 2 * j + h;
             if (m < np) {
                 const uint32_t n0 = (w.x >> (4 * h)) & 0x0F0F0F0Fu, n1 = (w.y >> (4 * h)) & 0x0F0F0F0Fu;
-                uint8_t* cb = colb + (PMAXC + (int)P.colbasep[m]) * 32 + lane;
+                uint8_t* cb = colp + (int)P.colbasep[m] * 32 + lane;
                 const int Km = P.Kp[m];
                 for (int kp = 1; kp < Km; ++kp) {
                     const uint32_t kv = (uint32_t)kp * 0x01010101u;
@@ -281,7 +284,8 @@ __device__ __forceinline__ void pipe_stats_tile(PipeSmem& sm, PipeAcc& acc, cons
     }
     __syncwarp();
     for (int cell = lane; cell < P.ncell; cell += 32) {
-        const uint4* a = reinterpret_cast<const uint4*>(colb + (int)P.cell_c1[cell] * 32);
+        const int c1 = (int)P.cell_c1[cell];                      // >= PMAXC: a column of the previous batch
+        const uint4* a = reinterpret_cast<const uint4*>((c1 < PMAXC ? colb : colp - PMAXC * 32) + c1 * 32);
         const uint4* b = reinterpret_cast<const uint4*>(colb + (int)P.cell_c2[cell] * 32);
         const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
         const int c = __popc(a0.x & b0.x) + __popc(a0.y & b0.y) + __popc(a0.z & b0.z) + __popc(a0.w & b0.w) +
@@ -663,7 +667,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                 while (first < T) {
                     const PipePlan& P = sm.plan[b & 3];
                     PPROF(5); PTRACE(0);
-                    for (int lt = tw; lt < ntl; lt += PT_WARPS) pipe_stats_tile(sm, sm.p.acc[b & 1], P, d, rs, tile0, lt, lane, pw, b & 1);
+                    for (int lt = tw; lt < ntl; lt += PT_WARPS) pipe_stats_tile(sm, sm.p.acc[b & 1], P, d, rs, tile0, lt, lane, pw, b & 1, ntl <= PT_WARPS);
                     // the next plan is made two batches ahead: warp 0 checks it (an acquire load: kept off the other
                     // warps, and away from the apply's stores) and the barrier hands the knowledge to everybody
                     if (tw == 0 && lane == 0 && first + P.nb < T) pipe_wait_flag(&sm.plan_ready, b + 2, d.err, 20);

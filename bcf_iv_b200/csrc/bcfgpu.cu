@@ -120,6 +120,7 @@ struct bcfgpu_handle {
     int kernel = 0;                   // persistent kernel in use: 1 k_persistent, 2 k_resident, 3 k_batched, 4 k_pipe (+ k_batched)
     int fallback_kernel = 3;          // what k_pipe hands a sweep with a wide tree to: 3 (k_batched resident) or 5 (HBM)
     size_t pipe_smem = 0;             // dynamic shared memory of k_pipe (kernel 4; res_smem is then k_batched's)
+    int pipe_ntl = 0;                 // tiles per CTA of k_pipe (res_ntl is then k_batched's: 0 when that one keeps its state in HBM)
     int* d_done = nullptr;            // sweeps completed by the last k_pipe launch
     size_t res_smem = 0;
     unsigned int* d_bar = nullptr;
@@ -1319,7 +1320,8 @@ static int select_kernel(bcfgpu_handle* h)
         if (!coop) return fail(BCFGPU_ERR_CUDA, "device does not support cooperative launch");
         int max_optin = 0;
         CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-        const int grid = std::min<int>(h->num_sms * PERSIST_CTAS_PER_SM, std::max(1, h->dev.n_tiles));
+        int grid = std::min<int>(h->num_sms * PERSIST_CTAS_PER_SM, std::max(1, h->dev.n_tiles));
+        if (const char* mc = getenv("BCFGPU_MAX_CTAS")) grid = std::max(1, std::min(grid, atoi(mc)));   // tests: many tiles per CTA at small n
         const int ntl_max = (h->dev.n_tiles + grid - 1) / grid;
         h->res_ntl = 0;
         h->kernel = 0;
@@ -1349,7 +1351,7 @@ static int select_kernel(bcfgpu_handle* h)
             if ((h->kernel == 3 || h->kernel == 5) && may_reside && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && h->nranks == 1) {
                 h->fallback_kernel = h->kernel;
                 const size_t needp = PIPE_SMEM_BYTES + (size_t)ntl_max * PIPE_BYTES_PER_TILE + (size_t)h->T * sizeof(TMeta) + 16;
-                if (fits((const void*)k_pipe, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; }
+                if (fits((const void*)k_pipe, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; h->pipe_ntl = ntl_max; }
                 else if (h->cfg.engine == BCFGPU_ENGINE_PIPELINED)
                     return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_PIPELINED: the observations of one SM do not fit in shared memory at this n");
             }
@@ -1388,7 +1390,8 @@ static int run_persistent(bcfgpu_handle* h, int total)
             // run by the batched kernel, then the pipelined one resumes
             int* dn = h->d_done;
             CK(cudaMemsetAsync(dn, 0, 4, h->stream));
-            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl, (void*)&dn};
+            int pntl = h->pipe_ntl;
+            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&pntl, (void*)&dn};
             CK(cudaLaunchCooperativeKernel((const void*)k_pipe, dim3(h->coop_grid), dim3(PIPE_THREADS), args, h->pipe_smem, h->stream));
             h->launches++;
             int ndone = 0;

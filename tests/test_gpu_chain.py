@@ -207,3 +207,20 @@ def test_shared_covariate_matrix_is_copied_once_and_changes_nothing():
     assert a.sigma().tobytes() == b.sigma().tobytes()
     for t in range(a.T):
         assert tree_signature(*a.get_tree(t)[:3]) == tree_signature(*b.get_tree(t)[:3])
+
+
+@pytest.mark.parametrize("max_ctas,n", [(3, 22000), (2, 12000)])
+def test_pipelined_engine_with_several_tiles_per_warp(monkeypatch, max_ctas, n):
+    """More than 27 tiles per CTA (here forced with BCFGPU_MAX_CTAS; at full grid: n > 1.02e6): the tile warps take several
+    tiles each, rebuild the previous batch's columns from the stored keys, and the batched kernel behind k_pipe keeps its
+    state in HBM.  Same chain as the batched engine, bit for bit."""
+    monkeypatch.setenv("BCFGPU_MAX_CTAS", str(max_ctas))
+    pr = make_problem(n=n, p=8, seed=31)
+    out = {}
+    for engine in (5, 4):
+        g = gpu_sampler(pr, engine=engine, seed=3, ntree_con=20, ntree_mod=8)
+        g.run(4, 4)
+        assert g.verify_leaf_cache() == 0
+        out[engine] = (g.trace()[0].tobytes(), g.tau_mean().tobytes(), g.sigma().tobytes(), g.engine_in_use)
+    assert out[5][3][0] == 4                      # k_pipe really ran
+    assert out[5][:3] == out[4][:3]
