@@ -81,3 +81,41 @@ def test_chains_are_repeatable_run_to_run(inputs):
             if ref is None:
                 ref = got
             assert got == ref
+
+
+def test_all_candidate_histogram_at_headline_size(inputs):
+    """K2' on the full matrix (1e6 x 100 two-valued columns + the 10 000-cutpoint pihat column): per leaf and column the
+    bins add up to the leaf's count and residual sum, and a few columns agree with a direct NumPy evaluation."""
+    w = inputs
+    n = len(w["y"])
+    s = _lib.Sampler(lambda_=w["lambda_"], sigma_init=w["sigma_init"], seed=1)
+    s.set_data(w["y"], w["z"], w["x_con"], w["x_mod"], w["cuts_con"], w["off_con"], w["cuts_mod"], w["off_mod"])
+    rng = np.random.default_rng(5)
+    r = rng.standard_normal(n)
+    for forest, off in ((1, w["off_mod"]), (0, w["off_con"])):
+        for nleaf in (1, 3):
+            slot = rng.integers(0, nleaf, n).astype(np.int32)
+            cnt, sm, ms = s.op_hist_all(forest, slot, nleaf, r)
+            p = len(off) - 1
+            nbt = int(off[p]) + p
+            cnt = cnt.reshape(nleaf, nbt); sm = sm.reshape(nleaf, nbt)
+            tol = 1e-10 * np.abs(r).sum()
+            for l in range(nleaf):
+                m = slot == l
+                for v in range(p):
+                    lo, hi = int(off[v]) + v, int(off[v + 1]) + v + 1
+                    assert cnt[l, lo:hi].sum() == m.sum()
+                    assert abs(sm[l, lo:hi].sum() - r[m].sum()) <= tol
+            X = w["x_mod"] if forest == 1 else w["x_con"]
+            cuts = w["cuts_mod"] if forest == 1 else w["cuts_con"]
+            for v in (0, 1, p // 2, p - 1):
+                c = cuts[int(off[v]):int(off[v + 1])]
+                b = np.searchsorted(c, X[:, v], side="right")          # bin = #cutpoints <= x
+                lo = int(off[v]) + v
+                for l in range(nleaf):
+                    m = slot == l
+                    want_c = np.bincount(b[m], minlength=len(c) + 1)
+                    want_s = np.bincount(b[m], weights=r[m], minlength=len(c) + 1)
+                    assert np.array_equal(cnt[l, lo:lo + len(c) + 1], want_c)
+                    assert np.allclose(sm[l, lo:lo + len(c) + 1], want_s, rtol=0, atol=tol)
+    s.close()
