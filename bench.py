@@ -226,6 +226,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (libbcfgpu has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
