@@ -381,19 +381,21 @@ static int setup_forest(bcfgpu_handle* h, int f, int p, const double* cuts, cons
 
 constexpr size_t MAX_STAGE = (size_t)1 << 28;   // fp64 staging buffer of K0: 256 Mi doubles = 2 GiB
 
-// K0 over a column-major host matrix, chunked by columns so the fp64 staging buffer stays bounded
-static int bin_forest(bcfgpu_handle* h, int f, const double* x)
+// K0 over a column-major host matrix, chunked by columns so the fp64 staging buffer stays bounded.
+// pre: the whole matrix is already on its way into this buffer on h->stream (set_data starts that copy before its
+// host-side work); the buffer is the caller's.
+static int bin_forest(bcfgpu_handle* h, int f, const double* x, double* pre = nullptr)
 {
     ForestHost& F = h->fh[f];
     if (F.p == 0) return BCFGPU_OK;
     const int64_t n = h->n;
-    int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(F.p, (int64_t)(MAX_STAGE / (size_t)n)));
-    double* stage = nullptr;
-    CK(cudaMalloc((void**)&stage, (size_t)chunk * n * 8));
+    int chunk = pre ? F.p : (int)std::max<int64_t>(1, std::min<int64_t>(F.p, (int64_t)(MAX_STAGE / (size_t)n)));
+    double* stage = pre;
+    if (!pre) CK(cudaMalloc((void**)&stage, (size_t)chunk * n * 8));
     int rc = BCFGPU_OK;
     for (int c0 = 0; c0 < F.p && rc == BCFGPU_OK; c0 += chunk) {
         const int nc = std::min(chunk, F.p - c0);
-        cudaError_t e = cudaMemcpyAsync(stage, x + (size_t)c0 * n, (size_t)nc * n * 8, cudaMemcpyHostToDevice, h->stream);
+        cudaError_t e = pre ? cudaSuccess : cudaMemcpyAsync(stage, x + (size_t)c0 * n, (size_t)nc * n * 8, cudaMemcpyHostToDevice, h->stream);
         if (e != cudaSuccess) { rc = fail(BCFGPU_ERR_CUDA, std::string("H2D of X: ") + cudaGetErrorString(e)); break; }
         h->h2d_bytes += (int64_t)nc * n * 8;
         dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 4096), (unsigned)nc);
@@ -403,7 +405,7 @@ static int bin_forest(bcfgpu_handle* h, int f, const double* x)
         e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(BCFGPU_ERR_CUDA, std::string("k_bin: ") + cudaGetErrorString(e));
     }
-    cudaFree(stage);
+    if (!pre) cudaFree(stage);
     return rc;
 }
 
@@ -472,13 +474,6 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     h->ntrt = (int)ntrt;
     h->n_pad = trt_pad + ctl_pad;
     const int64_t n_pad = h->n_pad;
-    // bcf: perm = order(z, decreasing = TRUE): treated rows first, ties in original order
-    h->pos.resize(n);
-    std::vector<int32_t> orig(n_pad, -1);
-    {
-        int64_t kt = 0, kc = trt_pad;
-        for (int64_t i = 0; i < n; ++i) { const int64_t q = z[i] ? kt++ : kc++; h->pos[i] = (int32_t)q; orig[q] = (int32_t)i; }
-    }
     Dev& d = h->dev;
     memset(&d, 0, sizeof(Dev));
     d.pr.rank = h->rank; d.pr.nranks = h->peer_ok ? h->nranks : 1; d.pr.seq0 = 0; d.pr.mine = h->d_mail;
@@ -492,11 +487,8 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     }
     d.nu = c.nu; d.lambda = c.lambda; d.con_sd = c.con_sd; d.mod_sd = c.mod_sd;
 
-    sd_mark("permutation (host)");
     DM(h, &h->d_pos, (size_t)n);
     DM(h, &h->d_orig, (size_t)n_pad);
-    CK(cudaMemcpyAsync(h->d_pos, h->pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_orig, orig.data(), (size_t)n_pad * 4, cudaMemcpyHostToDevice, h->stream));
     double* dy = nullptr;
     DM(h, &dy, (size_t)n_pad);
     DM(h, &d.rfx, (size_t)n_pad); DM(h, &d.Gc, (size_t)n_pad); DM(h, &d.Gm, (size_t)n_pad);
@@ -526,14 +518,6 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     CK(cudaMemsetAsync(d.trace_logr, 0, (size_t)h->T * 8, h->stream));
     CK(cudaMemsetAsync(d.counters, 0, 32, h->stream));
     CK(cudaMemsetAsync(h->d_bar, 0, 64 * 4, h->stream));
-    {
-        std::vector<double> yi((size_t)n_pad, 0.0);
-        for (int64_t i = 0; i < n; ++i) yi[h->pos[i]] = y[i];
-        CK(cudaMemcpyAsync(dy, yi.data(), (size_t)n_pad * 8, cudaMemcpyHostToDevice, h->stream));
-        h->h2d_bytes += (int64_t)n_pad * 8 + (int64_t)n * 4 + (int64_t)n_pad * 4;   // y, pos, orig
-        CK(cudaStreamSynchronize(h->stream));
-    }
-    sd_mark("clears + y (host scatter, H2D)");
     int rc;
     // x_moderate = the leading columns of x_control (same buffer, column-major, same cutpoints)?  Then bin once.
     bool shared_x = p_mod > 0 && xmod == xcon && p_mod <= p_con && cut_off_mod[0] == 0 && cut_off_con[0] == 0;
@@ -544,12 +528,23 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     }
     if ((rc = setup_forest(h, 0, p_con, cuts_con, cut_off_con))) return rc;
     if ((rc = setup_forest(h, 1, p_mod, cuts_mod, cut_off_mod, shared_x ? &h->fh[0] : nullptr))) return rc;
-    if ((rc = bin_forest(h, 0, xcon))) return rc;
-    if (!shared_x && (rc = bin_forest(h, 1, xmod))) return rc;
-    sd_mark("X: H2D + binning");
-    fill_forest_dev(h, 0, d.f[0]);
-    fill_forest_dev(h, 1, d.f[1]);
-
+    sd_mark("allocations, clears, cutpoints");
+    // Every allocation is made: X_control starts crossing the bus now (async from pinned memory), UNDER the host-side
+    // work below (permutation, y, ybar: ~10 ms at n = 1e6); the small copies and the binning kernel queue behind it.
+    struct StageGuard { double* p = nullptr; ~StageGuard() { if (p) cudaFree(p); } } pre_stage;
+    if ((size_t)p_con * (size_t)n <= MAX_STAGE) {
+        CK(cudaMalloc((void**)&pre_stage.p, (size_t)p_con * n * 8));
+        CK(cudaMemcpyAsync(pre_stage.p, xcon, (size_t)p_con * n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    // bcf: perm = order(z, decreasing = TRUE): treated rows first, ties in original order
+    h->pos.resize(n);
+    std::vector<int32_t> orig(n_pad, -1);
+    {
+        int64_t kt = 0, kc = trt_pad;
+        for (int64_t i = 0; i < n; ++i) { const int64_t q = z[i] ? kt++ : kc++; h->pos[i] = (int32_t)q; orig[q] = (int32_t)i; }
+    }
+    std::vector<double> yi((size_t)n_pad, 0.0);
+    for (int64_t i = 0; i < n; ++i) yi[h->pos[i]] = y[i];
     // ybar from an order-independent fixed-point sum, so any sharding starts from identical bits
     long long ysum[5] = {0, 0, 0, 0, (long long)ntrt};   // count, limb0, limb1, limb2, treated count
     for (int64_t i = 0; i < n; ++i) {
@@ -557,6 +552,17 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
         const long long v = std::llrint(y[i] * 17592186044416.0);
         ysum[0] += 1; ysum[1] += v & 0x1FFFFF; ysum[2] += (v >> LIMB_BITS) & 0x1FFFFF; ysum[3] += v >> (2 * LIMB_BITS);
     }
+    sd_mark("permutation, y, ybar (host)");
+    CK(cudaMemcpyAsync(h->d_pos, h->pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_orig, orig.data(), (size_t)n_pad * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dy, yi.data(), (size_t)n_pad * 8, cudaMemcpyHostToDevice, h->stream));
+    h->h2d_bytes += (int64_t)n_pad * 8 + (int64_t)n * 4 + (int64_t)n_pad * 4;   // y, pos, orig
+    if ((rc = bin_forest(h, 0, xcon, pre_stage.p))) return rc;
+    if (!shared_x && (rc = bin_forest(h, 1, xmod))) return rc;
+    sd_mark("X: H2D + binning");
+    fill_forest_dev(h, 0, d.f[0]);
+    fill_forest_dev(h, 1, d.f[1]);
+
     if (h->nranks > 1) {
         long long* dq = (long long*)h->d_tmp;
         CK(cudaMemcpyAsync(dq, ysum, 40, cudaMemcpyHostToDevice, h->stream));
