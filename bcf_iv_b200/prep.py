@@ -58,13 +58,21 @@ def pack_cuts(cut_list):
 
 
 def lm_sigma(yscale: np.ndarray, z: np.ndarray, x_c: np.ndarray) -> float:
-    """summary(lm(yscale ~ z + x_c))$sigma via the normal equations (rank-aware)."""
+    """summary(lm(yscale ~ z + x_c))$sigma via the normal equations (rank-aware).  The Gram matrix of (1, z, x_c) is
+    assembled from its blocks, so the n x (p + 2) design matrix is never materialised (400 MB at n = 5e5, p = 100)."""
     n = yscale.size
-    A = np.column_stack([np.ones(n), np.asarray(z, dtype=np.float64), np.asarray(x_c, dtype=np.float64)])
-    G = A.T @ A
-    b = A.T @ yscale
+    X = np.asarray(x_c, dtype=np.float64)
+    zf = np.asarray(z, dtype=np.float64)
+    p = X.shape[1]
+    G = np.empty((p + 2, p + 2))
+    sx, zx = X.sum(axis=0), zf @ X
+    G[0, 0], G[0, 1], G[1, 1] = n, zf.sum(), zf @ zf
+    G[0, 2:], G[1, 2:], G[2:, 2:] = sx, zx, X.T @ X
+    G[1, 0] = G[0, 1]; G[2:, 0] = sx; G[2:, 1] = zx
+    b = np.concatenate([[yscale.sum(), zf @ yscale], yscale @ X])
     beta, _, rank, _ = np.linalg.lstsq(G, b, rcond=None)
-    rss = float(np.sum((yscale - A @ beta) ** 2))
+    resid = yscale - (beta[0] + beta[1] * zf + X @ beta[2:])
+    rss = float(resid @ resid)
     dof = max(n - int(rank), 1)
     return float(np.sqrt(rss / dof))
 
