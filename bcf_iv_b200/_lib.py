@@ -36,6 +36,9 @@ class BcfGpuError(RuntimeError):
         self.code = code
 
 
+B200_SMS = 148          # the library is written for B200 (sm_100a) only
+
+
 class Config(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("ntree_con", C.c_int32), ("ntree_mod", C.c_int32),
@@ -43,7 +46,8 @@ class Config(C.Structure):
         ("con_sd", C.c_double), ("mod_sd", C.c_double), ("nu", C.c_double), ("lambda_", C.c_double),
         ("sigma_init", C.c_double), ("use_muscale", C.c_int32), ("use_tauscale", C.c_int32),
         ("min_leaf", C.c_int32), ("max_leaves", C.c_int32), ("seed", C.c_uint64), ("chain", C.c_uint32),
-        ("device", C.c_int32), ("engine", C.c_int32), ("keep_draws", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("device", C.c_int32), ("engine", C.c_int32), ("keep_draws", C.c_int32), ("max_ctas", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -264,9 +264,12 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     pihat = logit_link(z[disc], Xd)
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)
-    # the two fits are independent: run them side by side (small samples leave most of the GPU idle -- the sampler's
-    # grid is one CTA per 256-row tile -- and at any size one fit's host-side preamble hides under the other's sweeps)
+    # the two fits are independent: run them side by side.  While a discovery sample fits in half of a B200's shared
+    # memory (27 tiles of 256 rows on each of 74 SMs) each fit gets half of the SMs; at any size one fit's host-side
+    # preamble hides under the other's sweeps.
     from concurrent.futures import ThreadPoolExecutor
+    if "max_ctas" not in fit_args and len(disc) <= 27 * 256 * (_bcf._lib.B200_SMS // 2) - 512:
+        fit_args["max_ctas"] = _bcf._lib.B200_SMS // 2
     with ThreadPoolExecutor(max_workers=2) as pool:
         f_pic = pool.submit(_bcf.bcf, w[disc], z[disc], Xd, Xd, pihat, **fit_args)          # P(complier | x)
         f_itt = pool.submit(_bcf.bcf, y[disc], z[disc], Xd, Xd, pihat, **fit_args)          # R/bcf_iv.R:89-91

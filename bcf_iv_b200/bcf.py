@@ -42,7 +42,7 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
         nu=3.0, lambda_=None, sigq=0.9, sighat=None, include_pi="control", use_muscale=True, use_tauscale=True,
         w=None, random_seed=None, n_chains=1, n_cores=None, n_threads=None, no_output=True,
         save_tree_directory=None, log_file=None, verbose=False,
-        devices=None, keep_draws=None, engine=_lib.ENGINE_AUTO):
+        devices=None, keep_draws=None, engine=_lib.ENGINE_AUTO, max_ctas=0):
     """Fit the Bayesian Causal Forest  y = mu(x, pihat) + tau(x) z + eps  on the GPU.
 
     Returns a dict with bcf's fields: `sigma` (nsim*n_chains), `yhat`, `mu`, `tau` (nsim*n_chains x n, original row
@@ -51,7 +51,7 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
 
     Extras beyond bcf's signature: `devices` (CUDA ordinals, chains are dealt round-robin: one independent chain per
     GPU), `keep_draws` (None = keep the three nsim x n matrices only while they fit DRAW_BYTES_CAP),
-    `engine`.  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
+    `engine`, `max_ctas` (0 = the whole GPU; k > 0 = at most k CTAs, so that several fits can run side by side on one GPU).  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
     no_output, verbose, update_interval) are accepted and ignored; observation weights `w` are not implemented.
     """
     if nburn is None or nsim is None:
@@ -82,7 +82,7 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
                beta_con=float(power_control), alpha_mod=float(base_moderate), beta_mod=float(power_moderate),
                con_sd=P.con_sd, mod_sd=P.mod_sd, nu=float(nu), lambda_=P.lambda_, sigma_init=P.sigma_init,
                use_muscale=int(bool(use_muscale)), use_tauscale=int(bool(use_tauscale)), seed=seed,
-               keep_draws=7 if keep_draws else 0, engine=int(engine))
+               keep_draws=7 if keep_draws else 0, engine=int(engine), max_ctas=int(max_ctas))
     res = [None] * int(n_chains)
     threads = []
     for c in range(int(n_chains)):

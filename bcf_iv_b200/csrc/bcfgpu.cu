@@ -1330,6 +1330,7 @@ static int select_kernel(bcfgpu_handle* h)
         // per-tree work that is dealt by CTA (proposals, tree write-back).  Measured (k_pipe): n = 500: 930 -> 1530
         // sweeps/s, n = 5e4: 1275 -> 1543 against a grid of one CTA per tile.
         int grid = h->num_sms * PERSIST_CTAS_PER_SM;
+        if (h->cfg.max_ctas > 0) grid = std::min<int>(grid, h->cfg.max_ctas);      // a share of the GPU (fits running side by side)
         if (getenv("BCFGPU_GRID_BY_TILES")) grid = std::min<int>(grid, std::max(1, h->dev.n_tiles));
         if (const char* mc = getenv("BCFGPU_MAX_CTAS")) grid = std::max(1, std::min(grid, atoi(mc)));   // tests: many tiles per CTA at small n
         const int ntl_max = (h->dev.n_tiles + grid - 1) / grid;

@@ -82,7 +82,9 @@ typedef struct bcfgpu_config {
     int32_t device;               /* CUDA ordinal; -1 = current device */
     int32_t engine;               /* bcfgpu_engine */
     int32_t keep_draws;           /* bit0 tau, bit1 mu, bit2 yhat: keep nsim x n draws on device */
-    int32_t reserved[7];
+    int32_t max_ctas;             /* 0: one CTA per SM.  > 0: at most that many CTAs, so that several fits can share one GPU
+                                   * side by side (bcf_iv fits the complier proportion and the ITT at the same time) */
+    int32_t reserved[6];
 } bcfgpu_config;
 
 typedef struct bcfgpu_handle bcfgpu_handle;
