@@ -81,6 +81,7 @@ SEXP bcfgpu_R_fit(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off_c, SEX
     cfg.seed = (uint64_t)num(cfg_list, "seed", 42);
     cfg.chain = (uint32_t)num(cfg_list, "chain", 0);
     cfg.device = (int32_t)num(cfg_list, "device", -1);
+    cfg.max_ctas = (int32_t)num(cfg_list, "max_ctas", 0);
     cfg.keep_draws = keep ? 7 : 0;
 
     bcfgpu_handle *h = NULL;

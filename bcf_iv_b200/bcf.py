@@ -85,14 +85,21 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
                keep_draws=7 if keep_draws else 0, engine=int(engine), max_ctas=int(max_ctas))
     res = [None] * int(n_chains)
     threads = []
+    # chains that share a GPU: side by side on a share of its SMs each while an SM's 27 tiles of 256 rows hold the share's
+    # observations, else one after the other (each launch then fills the device)
+    per_dev = -(-int(n_chains) // len(devs))
+    share = _lib.B200_SMS // per_dev if per_dev > 1 else 0
+    side_by_side = per_dev > 1 and int(max_ctas) == 0 and share >= 1 and n <= 27 * 256 * share - 512
+    if side_by_side:
+        cfg["max_ctas"] = share
     for c in range(int(n_chains)):
         ccfg = dict(cfg, chain=c)
         th = threading.Thread(target=_run_chain, args=(res, c, P, (cc, oc, cm, om), ccfg, int(nburn), int(nsim),
                                                        int(nthin), keep_draws, devs[c % len(devs)]))
         th.start()
         threads.append(th)
-        if len(devs) == 1:
-            th.join()           # chains that share a GPU run one after the other (each launch fills the device)
+        if per_dev > 1 and not side_by_side:
+            th.join()
     for th in threads:
         th.join()
     for r in res:
