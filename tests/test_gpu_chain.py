@@ -224,3 +224,15 @@ def test_pipelined_engine_with_several_tiles_per_warp(monkeypatch, max_ctas, n):
         out[engine] = (g.trace()[0].tobytes(), g.tau_mean().tobytes(), g.sigma().tobytes(), g.engine_in_use)
     assert out[5][3][0] == 4                      # k_pipe really ran
     assert out[5][:3] == out[4][:3]
+
+
+def test_a_share_of_the_gpu_walks_the_same_chain():
+    """config.max_ctas (several fits side by side on one GPU): the chain does not depend on how many CTAs replay it."""
+    pr = make_problem(n=9000, p=8, seed=41)
+    out = []
+    for max_ctas in (0, 74, 5):
+        g = gpu_sampler(pr, seed=6, ntree_con=24, ntree_mod=8, max_ctas=max_ctas)
+        g.run(4, 4)
+        assert g.verify_leaf_cache() == 0
+        out.append((g.trace()[0].tobytes(), g.tau_mean().tobytes(), g.sigma().tobytes()))
+    assert out[0] == out[1] == out[2]
