@@ -186,7 +186,9 @@ __device__ inline void sweep_scalars(const Dev& d, const TreeRec* newtrees, cons
         Scalars sc = *scs;
         const Rng rng{d.key0, d.key1};
         double tssq = 0.0, tcnt = 0.0;
-        for (int i = 0; i < (int)blockDim.x; ++i) { tssq += red[i]; tcnt += red[blockDim.x + i]; }
+        // fixed order; the entries behind the last tree are zeros (adding them changes no bit): stop there
+        const int nred = min((int)blockDim.x, d.f[0].ntree);
+        for (int i = 0; i < nred; ++i) { tssq += red[i]; tcnt += red[blockDim.x + i]; }
         double M[2][NMOM];
         for (int g = 0; g < 2; ++g)
             for (int m = 0; m < NMOM; ++m) {

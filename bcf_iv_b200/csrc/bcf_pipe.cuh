@@ -787,6 +787,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
         }
 #undef PTRACE
         __syncthreads();
+#ifdef BCF_PROF
+        long long te = clock64();
+#define EPROF(k) do { if (d.prof != nullptr && t == 0) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&d.prof[1024 + 2048 + blockIdx.x * 8 + (k)], (unsigned long long)(now_ - te)); te = now_; } } while (0)
+#else
+#define EPROF(k) do { } while (0)
+#endif
         // ---- epilogue: moments of (y, Gc, Gm) ----
         if (is_pass) {
             long long* tb = reinterpret_cast<long long*>(&sm.p.tab);
@@ -814,10 +820,16 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
             const long long v = table_word(sm.p.tab, PIPE_THREADS / 32, m, g, q);
             if (v != 0) atomicAdd((unsigned long long*)&mom[(g * NMOM + m) * 3 + (q - 1)], (unsigned long long)v);
         }
+        EPROF(3);
         grid_all();
-        if (!grid_all_wait()) return;
-        sweep_scalars(d, d.trees[par ^ 1], mom, sm.p.red, &scs, writer0);
+        // the next sweep's proposals need only the new trees (each is proposed by the CTA that wrote it) and the Philox
+        // counters: they are made while the moments cross the grid barrier
         if (sw + 1 < nsweeps) pipe_propose_all(sm, d, d.trees[par ^ 1], sc.sweep + 1u);
+        EPROF(6);
+        if (!grid_all_wait()) return;
+        EPROF(4);
+        sweep_scalars(d, d.trees[par ^ 1], mom, sm.p.red, &scs, writer0);
+        EPROF(5);
         grid_all();   // proposals visible before the next sweep reads them (wait: below)
         // ---- finishing pass ----
         {
@@ -863,8 +875,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
             for (int64_t i = gtid; i < 2 * NMOM * 3; i += gstride) mom_next[i] = 0;
         }
         if (!grid_all_wait()) return;
+        EPROF(7);
         ++done;
     }
+#undef EPROF
     // exit: park the state in HBM in the form every engine understands (Gm was stored by the finishing pass)
     if (is_pass)
         for (int lt = pw; lt < ntl; lt += PP_WARPS) {

@@ -756,7 +756,7 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
             CK(cudaMemcpy(pcx.data(), d.prof + 1024, pcx.size() * 8, cudaMemcpyDeviceToHost));
             CK(cudaMemset(d.prof + 1024, 0, pcx.size() * 8));
             const double nbat = (double)total * ((h->cfg.ntree_con + 3) / 4 + (h->cfg.ntree_mod + 3) / 4);
-            for (int k = 0; k < 11; ++k) {   // 8..10: utility warp (wait for the flush, plan, stage)
+            for (int k = 0; k < 16; ++k) {   // 8..10: utility warp (wait for the flush, plan, stage); 11..15: sweep epilogue (moments, barrier, scalars, proposals, finishing pass + barrier)
                 std::vector<double> v;
                 for (int c = 0; c < h->coop_grid && c < 256; ++c) v.push_back((double)pcx[(k < 8 ? c * 8 + k : 2048 + c * 8 + k - 8)] / nbat);
                 if (v.empty()) break;
