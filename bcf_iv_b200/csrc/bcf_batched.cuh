@@ -1067,6 +1067,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
             }
         }
         grid_arrive(bar, target);
+        // the next sweep's proposals need only the new trees (each is proposed by the CTA that wrote it) and the Philox
+        // counters: they are made while the moments cross the grid barrier
+        if (sw + 1 < nsweeps) propose_all_b(sm, d, d.trees[par ^ 1], sc.sweep + 1u);
         if (!grid_wait(bar, target, d.err, &bar_ok)) return;
         if (d.pr.nranks > 1) {   // the sweep's moments, summed over the shards
             ++mev;
@@ -1089,7 +1092,6 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
             sweep_scalars(d, d.trees[par ^ 1], sm.momsum, sm.p.red, &scs, writer0, true);
         } else
             sweep_scalars(d, d.trees[par ^ 1], mom, sm.p.red, &scs, writer0);
-        if (sw + 1 < nsweeps) propose_all_b(sm, d, d.trees[par ^ 1], sc.sweep + 1u);   // every tree record is visible now
         grid_arrive(bar, target);   // the proposals must be visible before the next sweep stages them (wait: below)
         // ---- finishing pass: posterior accumulation, residual re-derived with the new scales, back to the mu forest ----
         {
