@@ -493,6 +493,12 @@ __global__ void __launch_bounds__(256) k_hist(Dev d, int forest, const uint8_t* 
 #ifndef HISTB_CELLS_N
 #define HISTB_CELLS_N 12
 #endif
+// bit o of `bits` as the double 0.0 or 1.0 (its high word is 0 or 0x3FF00000): acc = fma(bit, r, acc) is then the
+// predicated add `if (bit) acc += r` in three instructions (fma(1, r, acc) and acc + r round identically)
+__device__ __forceinline__ double bit_as_double(uint32_t bits, int o)
+{
+    return __hiloint2double((int)(((bits >> o) & 1u) * 0x3FF00000u), 0);
+}
 constexpr int HISTB_CELLS = HISTB_CELLS_N;   // (column, leaf) cells per CTA: that many sums + counts in registers (two CTAs per SM)
 template <int NLEAF>
 __global__ void __launch_bounds__(256, 2) k_hist_bits(Dev d, int forest, const uint8_t* __restrict__ label,
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(256, 2) k_hist_bits(Dev d, int forest, const u
             lb[l] = bytes_to_bits(__vcmpeq4(lab.x, lv), __vcmpeq4(lab.y, lv));
             if (totals) {
 #pragma unroll
-                for (int o = 0; o < 8; ++o) tot[l] += ((lb[l] >> o) & 1u) ? rd[o] : 0.0;
+                for (int o = 0; o < 8; ++o) tot[l] = fma(bit_as_double(lb[l], o), rd[o], tot[l]);
                 tcnt[l] += __popc(lb[l]);
             }
         }
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(256, 2) k_hist_bits(Dev d, int forest, const u
                 for (int l = 0; l < NLEAF; ++l) {
                     const uint32_t bits = one & lb[l];
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) acc[c][l] += ((bits >> o) & 1u) ? rd[o] : 0.0;
+                    for (int o = 0; o < 8; ++o) acc[c][l] = fma(bit_as_double(bits, o), rd[o], acc[c][l]);
                     cnt[c][l] += __popc(bits);
                 }
             }
