@@ -12,7 +12,13 @@ bcf <- function(y, z, x_control, x_moderate = x_control, pihat, nburn, nsim, nth
                 use_muscale = TRUE, use_tauscale = TRUE,
                 w = NULL, random_seed = sample.int(.Machine$integer.max, 1), n_chains = 1, n_cores = NULL,
                 n_threads = NULL, no_output = TRUE, save_tree_directory = NULL, log_file = NULL, verbose = FALSE,
-                device = -1L, keep_draws = TRUE) {
+                device = -1L, devices = NULL, first_chain = 0L,
+                keep_draws = 3 * 8 * as.double(length(y)) * nsim * n_chains <= 8 * 2^30) {
+  # keep_draws: the three nsim x n matrices bcf returns (tau, mu, yhat) are kept only while they fit 8 GiB (the Python
+  # twin's DRAW_BYTES_CAP); tau_mean / mu_mean / yhat_mean / tau_var -- what BayesIV consumes -- are always returned.
+  # devices: CUDA ordinals the n_chains chains are dealt over, all running at the same time (one host thread per chain
+  # inside the library: bcfgpu_run_chains); NULL = every visible device.  first_chain: index of the first chain's
+  # Philox stream (bcf_iv gives the complier-proportion fit its own stream).
   if (!is.null(w)) stop("observation weights are not implemented")
   x_control <- as.matrix(x_control); x_moderate <- as.matrix(x_moderate); pihat <- as.matrix(pihat)
   n <- length(y)
@@ -38,25 +44,32 @@ bcf <- function(y, z, x_control, x_moderate = x_control, pihat, nburn, nsim, nth
   mod_sd <- (if (isTRUE(all.equal(sd_moderate, sdy))) 1 else sd_moderate / sdy) / (if (use_tauscale) 0.674 else 1)
   perm <- order(z, decreasing = TRUE)           # reported only: the library permutes and un-permutes internally
 
-  chains <- lapply(seq_len(n_chains) - 1L, function(ch) {
-    cfg <- list(ntree_control = ntree_control, ntree_moderate = ntree_moderate, base_control = base_control,
-                power_control = power_control, base_moderate = base_moderate, power_moderate = power_moderate,
-                con_sd = con_sd, mod_sd = mod_sd, nu = nu, lambda = lambda, sigma_init = sd(yscale),
-                use_muscale = as.integer(use_muscale), use_tauscale = as.integer(use_tauscale),
-                seed = random_seed, chain = ch, device = device)
-    .Call("bcfgpu_R_fit", as.double(yscale), as.integer(z), x_c, x_m,
-          as.double(unlist(cut_c)), as.integer(c(0L, cumsum(lengths(cut_c)))),
-          as.double(unlist(cut_m)), as.integer(c(0L, cumsum(lengths(cut_m)))),
-          cfg, as.integer(nburn), as.integer(nsim), as.integer(nthin), isTRUE(keep_draws))
-  })
+  cfg <- list(ntree_control = ntree_control, ntree_moderate = ntree_moderate, base_control = base_control,
+              power_control = power_control, base_moderate = base_moderate, power_moderate = power_moderate,
+              con_sd = con_sd, mod_sd = mod_sd, nu = nu, lambda = lambda, sigma_init = sd(yscale),
+              use_muscale = as.integer(use_muscale), use_tauscale = as.integer(use_tauscale),
+              seed = random_seed, chain = as.integer(first_chain), device = device)
+  if (is.null(devices)) devices <- if (n_chains > 1) seq_len(.Call("bcfgpu_R_device_count")) - 1L else as.integer(device)
+  # all chains in ONE native call: the library runs them concurrently, chain c on devices[c mod length(devices)]
+  chains <- .Call("bcfgpu_R_fit_chains", as.double(yscale), as.integer(z), x_c, x_m,
+                  as.double(unlist(cut_c)), as.integer(c(0L, cumsum(lengths(cut_c)))),
+                  as.double(unlist(cut_m)), as.integer(c(0L, cumsum(lengths(cut_m)))),
+                  cfg, as.integer(nburn), as.integer(nsim), as.integer(nthin), isTRUE(keep_draws),
+                  as.integer(n_chains), as.integer(devices))
   bind <- function(f) do.call(rbind, lapply(chains, function(r) t(r[[f]])))      # n x nsim -> nsim x n, chains stacked
   avg <- function(f) Reduce(`+`, lapply(chains, `[[`, f)) / length(chains)
+  # variance of the STACKED draws (what fit$tau holds): within-chain sums of squares plus the spread of the chain means
+  pooled_var <- function() {
+    ns <- length(chains[[1]]$sigma); N <- ns * length(chains); m <- avg("tau_mean")
+    if (N < 2) return(0 * m)
+    Reduce(`+`, lapply(chains, function(r) (ns - 1) * r$tau_var + ns * (r$tau_mean - m)^2)) / (N - 1)
+  }
   fit <- list(sigma = sdy * unlist(lapply(chains, `[[`, "sigma")),
               mu_scale = sdy * unlist(lapply(chains, `[[`, "mu_scale")),
               tau_scale = sdy * unlist(lapply(chains, `[[`, "tau_scale")),
               perm = perm,
               tau_mean = sdy * avg("tau_mean"), mu_mean = muy + sdy * avg("mu_mean"),
-              yhat_mean = muy + sdy * avg("yhat_mean"), tau_var = sdy^2 * avg("tau_var"))
+              yhat_mean = muy + sdy * avg("yhat_mean"), tau_var = sdy^2 * pooled_var())
   if (isTRUE(keep_draws)) {
     fit$tau <- sdy * bind("tau"); fit$mu <- muy + sdy * bind("mu"); fit$yhat <- muy + sdy * bind("yhat")
   }

@@ -3,7 +3,7 @@
 #' Drop-in for BayesIV::bcf_itt (reference R/bcf_itt.R:33): same arguments; prints the node effects and returns
 #' NULL invisibly, as the reference does.
 #' @export
-bcf_itt <- function(y, w, z, x, binary = FALSE, n_burn = 500, n_sim = 500, inference_ratio = 0.5, max_depth = 2,
+bcf_itt <- function(y, w, z, x, binary = FALSE, max_depth = 2, n_burn = 500, n_sim = 500, inference_ratio = 0.5,
                     seed = 42) {
   # binary = TRUE: the reference fits the ITT with bartCause::bartc (probit BART) here; this build fits it with the same
   # GPU sampler on the 0/1 outcome (its tau is the ITT on the probability scale, as for the complier proportion)

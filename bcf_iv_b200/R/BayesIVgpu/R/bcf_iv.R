@@ -17,29 +17,38 @@ bcf_iv <- function(y, w, z, x, binary = FALSE, n_burn = 500, n_sim = 500, infere
   xd <- x[-index, , drop = FALSE]
   pihat <- .logit_pihat(z[-index], xd)
 
-  fit <- function(outcome) bcf(outcome, z[-index], xd, xd, pihat, nburn = n_burn, nsim = n_sim,
-                               random_seed = seed, keep_draws = FALSE)$tau_mean
-  pic <- fit(w[-index])                       # posterior mean share of compliers given x
-  itt <- fit(y[-index])                       # posterior mean intention-to-treat effect given x  (the hot path)
+  # the two fits are independent samplers in the reference (bartc for pic, bcf for the ITT): distinct Philox streams
+  # (chain 1 / chain 0 of the same seed), so that the Monte Carlo noise of itt and pic is not shared
+  fit <- function(outcome, chain) bcf(outcome, z[-index], xd, xd, pihat, nburn = n_burn, nsim = n_sim,
+                                      random_seed = seed, keep_draws = FALSE, first_chain = chain)$tau_mean
+  pic <- fit(w[-index], 1L)                   # posterior mean share of compliers given x
+  itt <- fit(y[-index], 0L)                   # posterior mean intention-to-treat effect given x  (the hot path)
   tauhat <- itt / pic
 
   tree <- rpart::rpart(tauhat ~ ., data = data.frame(tauhat = tauhat, xd), maxdepth = max_depth, cp = cp,
                        minsplit = minsplit)
   nodes <- as.numeric(row.names(tree$frame))
-  is_leaf <- tree$frame$var == "<leaf>"
+  # Rows are indexed by rpart NODE NUMBER, as the reference does (bcfivMat[i, ] with i the node number, R/bcf_iv.R:174;
+  # root in row 1, R/bcf_iv.R:138): the table starts with length(nodes) rows and grows (NA rows in between) when a
+  # node number exceeds that, exactly like the reference's data.frame assignment.
   out <- data.frame(node = rep(NA_character_, length(nodes)), CCACE = NA, pvalue = NA, Weak_IV_test = NA,
                     Pi_obs = NA, ITT = NA, Pi_compliers = NA)
-  for (k in seq_along(nodes)) {
-    rule <- if (nodes[k] == 1) NA_character_ else .node_rule(tree, nodes[k])
-    sub <- if (nodes[k] == 1) inference else inference[which(eval(parse(text = rule), inference)), ]
-    if (nodes[k] != 1 && length(unique(sub$w)) == 1 && length(unique(sub$z)) == 1) next
+  leaves <- numeric(length(nodes))
+  leaves[nodes[tree$frame$var == "<leaf>"]] <- 1                        # R/bcf_iv.R:118-120
+  for (i in nodes) {
+    rule <- if (i == 1) NA_character_ else .node_rule(tree, i)
+    sub <- if (i == 1) inference else inference[which(eval(parse(text = rule), inference)), ]
+    if (i != 1 && length(unique(sub$w)) == 1 && length(unique(sub$z)) == 1) next      # R/bcf_iv.R:157
     r <- .node_iv(sub)
-    out[k, ] <- list(rule, round(r[["effect"]], 4), round(r[["p"]], 4), round(r[["weak"]], 4),
+    out[i, ] <- list(rule, round(r[["effect"]], 4), round(r[["p"]], 4), round(r[["weak"]], 4),
                      round(nrow(sub) / nrow(inference), 4), round(r[["effect"]] * r[["compliers"]], 4),
                      round(r[["compliers"]], 4))
   }
-  row.names(out) <- nodes
+  nr <- max(nrow(out), length(leaves))
+  if (nrow(out) < nr) out[nr, ] <- NA
+  length(leaves) <- nr
+  is_leaf <- which(leaves == 1)
   out$Adj_pvalue <- NA
-  out$Adj_pvalue[is_leaf] <- round(p.adjust(as.numeric(out$pvalue[is_leaf]), adj_method), 5)
+  out$Adj_pvalue[is_leaf] <- round(p.adjust(as.numeric(out$pvalue[is_leaf]), adj_method), 5)     # R/bcf_iv.R:182-185
   out
 }

@@ -8,6 +8,11 @@
  * stay in their order (the library applies and undoes bcf's treated-first permutation), outputs are allocated here
  * with allocVector/allocMatrix and filled by the library, errors become R errors carrying bcfgpu_last_error().
  *
+ * Interrupts: the chains run on the library's own host threads (bcfgpu_fit_chains); this thread polls
+ * R_CheckUserInterrupt() under R_ToplevelExec, so a Ctrl-C never longjmps past live handles: the library stops the
+ * chains, destroys their handles and only then the shim raises the R error.  The whole run is ONE logical bcfgpu_run
+ * per chain (nburn, nsim, nthin together), so thinning follows bcf's `iIter % thin` rule whatever nburn is.
+ *
  * Not compiled in this repository's CI (no R in the image): tests/test_r_package.py syntax-checks it against a stub
  * of Rinternals.h; INTEGRATION.md shows the build line.
  */
@@ -15,17 +20,25 @@
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
 #include <R_ext/Utils.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "bcfgpu.h"
 
-static void check(int rc, bcfgpu_handle *h)
+static void destroy_all(bcfgpu_handle **hs, int nh)
+{
+    for (int c = 0; hs && c < nh; ++c) { if (hs[c]) bcfgpu_destroy(hs[c]); hs[c] = NULL; }
+}
+
+/* non-zero status -> R error, after every live handle is destroyed (Rf_error does not return) */
+static void check(int rc, bcfgpu_handle **hs, int nh)
 {
     if (rc != BCFGPU_OK) {
         char msg[512];
         strncpy(msg, bcfgpu_last_error(), sizeof(msg) - 1);
         msg[sizeof(msg) - 1] = 0;
-        if (h) bcfgpu_destroy(h);
+        destroy_all(hs, nh);
+        free(hs);
         Rf_error("libbcfgpu: %s", msg);
     }
 }
@@ -38,30 +51,77 @@ static double num(SEXP list, const char *name, double dflt)
     return dflt;
 }
 
+/* R_CheckUserInterrupt() longjmps on Ctrl-C: under R_ToplevelExec the jump is caught and reported as FALSE */
+static void check_interrupt(void *unused) { (void)unused; R_CheckUserInterrupt(); }
+static int interrupt_pending(void *unused) { (void)unused; return R_ToplevelExec(check_interrupt, NULL) == FALSE; }
+
 /* .Call("bcfgpu_R_device_count") */
 SEXP bcfgpu_R_device_count(void) { return Rf_ScalarInteger(bcfgpu_device_count()); }
 
+/* results of one finished chain -> list(tau_mean, tau_var, mu_mean, yhat_mean, sigma, mu_scale, tau_scale, tau, mu, yhat,
+ * device_ms) on the standardised scale; tau / mu / yhat are n x nsaved matrices when keep, else NULL */
+static SEXP chain_result(bcfgpu_handle **hs, int nh, int c, R_xlen_t n, int keep)
+{
+    bcfgpu_handle *h = hs[c];
+    double ms = 0;
+    bcfgpu_last_run_ms(h, &ms);
+    int32_t ns = 0;
+    check(bcfgpu_num_saved(h, &ns), hs, nh);
+    const char *nm[] = {"tau_mean", "tau_var", "mu_mean", "yhat_mean", "sigma", "mu_scale", "tau_scale", "tau", "mu",
+                        "yhat", "device_ms", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+    SEXP v;
+    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_tau_mean(h, REAL(v)), hs, nh); SET_VECTOR_ELT(out, 0, v); UNPROTECT(1);
+    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_tau_var(h, REAL(v)), hs, nh); SET_VECTOR_ELT(out, 1, v); UNPROTECT(1);
+    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_mu_mean(h, REAL(v)), hs, nh); SET_VECTOR_ELT(out, 2, v); UNPROTECT(1);
+    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_yhat_mean(h, REAL(v)), hs, nh); SET_VECTOR_ELT(out, 3, v); UNPROTECT(1);
+    v = PROTECT(Rf_allocVector(REALSXP, ns)); check(bcfgpu_get_sigma(h, REAL(v)), hs, nh); SET_VECTOR_ELT(out, 4, v); UNPROTECT(1);
+    {
+        SEXP a = PROTECT(Rf_allocVector(REALSXP, ns)), b = PROTECT(Rf_allocVector(REALSXP, ns));
+        check(bcfgpu_get_scales(h, REAL(a), REAL(b)), hs, nh);
+        SET_VECTOR_ELT(out, 5, a); SET_VECTOR_ELT(out, 6, b);
+        UNPROTECT(2);
+    }
+    if (keep) {
+        /* the library returns draw-major rows (nsaved x n, row-major) = an n x nsaved column-major R matrix: the R
+         * wrapper transposes to bcf's nsim x n */
+        for (int which = 0; which < 3; ++which) {
+            v = PROTECT(Rf_allocMatrix(REALSXP, (int)n, ns));
+            check(bcfgpu_get_draws(h, which, REAL(v)), hs, nh);
+            SET_VECTOR_ELT(out, 7 + which, v);
+            UNPROTECT(1);
+        }
+    }
+    SET_VECTOR_ELT(out, 10, Rf_ScalarReal(ms));
+    UNPROTECT(1);
+    return out;
+}
+
 /*
- * .Call("bcfgpu_R_fit", yscale, z, x_c, x_m, cuts_c, off_c, cuts_m, off_m, cfg, nburn, nsim, nthin, keep_draws)
+ * .Call("bcfgpu_R_fit_chains", yscale, z, x_c, x_m, cuts_c, off_c, cuts_m, off_m, cfg, nburn, nsim, nthin, keep_draws,
+ *       n_chains, devices)
  *   yscale  numeric n      standardised outcome            z       integer n (0/1)
  *   x_c/x_m numeric matrices n x p_con / n x p_mod (column-major, as R stores them)
  *   cuts_*  numeric        concatenated cutpoints          off_*   integer p+1 offsets
- *   cfg     named list     the bcfgpu_config fields that differ from bcf's defaults
- * Runs nburn + nsim*nthin sweeps in batches of 256 with R_CheckUserInterrupt() between batches.
- * Returns list(tau_mean, tau_var, mu_mean, yhat_mean, sigma, mu_scale, tau_scale, tau, mu, yhat, device_ms)
- * on the standardised scale; tau/mu/yhat are nsim x n matrices when keep_draws, else NULL.
+ *   cfg     named list     the bcfgpu_config fields that differ from bcf's defaults (chain = first Philox stream)
+ *   devices integer        CUDA ordinals the chains are dealt over (chain c on devices[c %% length]); they run at once
+ * Returns a list of n_chains per-chain results (see chain_result).
  */
-SEXP bcfgpu_R_fit(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off_c, SEXP cuts_m, SEXP off_m, SEXP cfg_list,
-                  SEXP nburn_, SEXP nsim_, SEXP nthin_, SEXP keep_)
+SEXP bcfgpu_R_fit_chains(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off_c, SEXP cuts_m, SEXP off_m, SEXP cfg_list,
+                         SEXP nburn_, SEXP nsim_, SEXP nthin_, SEXP keep_, SEXP nchains_, SEXP devices_)
 {
     const R_xlen_t n = Rf_xlength(y);
     if (!Rf_isReal(y) || !Rf_isInteger(z) || !Rf_isMatrix(xc) || !Rf_isReal(xc) || !Rf_isMatrix(xm) || !Rf_isReal(xm))
-        Rf_error("bcfgpu_R_fit: y, x_control, x_moderate must be double, z integer");
-    if (Rf_xlength(z) != n || Rf_nrows(xc) != n || Rf_nrows(xm) != n) Rf_error("bcfgpu_R_fit: row counts differ");
+        Rf_error("bcfgpu_R_fit_chains: y, x_control, x_moderate must be double, z integer");
+    if (Rf_xlength(z) != n || Rf_nrows(xc) != n || Rf_nrows(xm) != n) Rf_error("bcfgpu_R_fit_chains: row counts differ");
     const int p_con = Rf_ncols(xc), p_mod = Rf_ncols(xm);
-    if (Rf_xlength(off_c) != p_con + 1 || Rf_xlength(off_m) != p_mod + 1) Rf_error("bcfgpu_R_fit: bad cutpoint offsets");
+    if (Rf_xlength(off_c) != p_con + 1 || Rf_xlength(off_m) != p_mod + 1) Rf_error("bcfgpu_R_fit_chains: bad cutpoint offsets");
     const int nburn = Rf_asInteger(nburn_), nsim = Rf_asInteger(nsim_), nthin = Rf_asInteger(nthin_);
     const int keep = Rf_asLogical(keep_);
+    const int nch = Rf_asInteger(nchains_);
+    if (nch < 1 || !Rf_isInteger(devices_)) Rf_error("bcfgpu_R_fit_chains: need n_chains >= 1 and integer devices");
+    int ndev = (int)Rf_xlength(devices_);
+    if (ndev == 1 && INTEGER(devices_)[0] < 0) ndev = 0;      /* -1: the current device */
 
     bcfgpu_config cfg;
     bcfgpu_config_init(&cfg);
@@ -84,55 +144,23 @@ SEXP bcfgpu_R_fit(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off_c, SEX
     cfg.max_ctas = (int32_t)num(cfg_list, "max_ctas", 0);
     cfg.keep_draws = keep ? 7 : 0;
 
-    bcfgpu_handle *h = NULL;
-    check(bcfgpu_create(&cfg, &h), NULL);
-    check(bcfgpu_set_data(h, (int64_t)n, p_con, p_mod, REAL(y), INTEGER(z), REAL(xc), REAL(xm), REAL(cuts_c),
-                          INTEGER(off_c), REAL(cuts_m), INTEGER(off_m)), h);
-    /* burn-in in interruptible batches, then the saved part in one call (it owns the posterior accumulators) */
-    for (int done = 0; done < nburn; done += 256) {
-        check(bcfgpu_run(h, nburn - done < 256 ? nburn - done : 256, 0, 1), h);
-        R_CheckUserInterrupt();
-    }
-    check(bcfgpu_run(h, 0, nsim, nthin), h);
-    double ms = 0;
-    bcfgpu_last_run_ms(h, &ms);
-    int32_t ns = 0;
-    check(bcfgpu_num_saved(h, &ns), h);
-
-    const char *nm[] = {"tau_mean", "tau_var", "mu_mean", "yhat_mean", "sigma", "mu_scale", "tau_scale", "tau", "mu",
-                        "yhat", "device_ms", ""};
-    SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
-    SEXP v;
-    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_tau_mean(h, REAL(v)), h); SET_VECTOR_ELT(out, 0, v); UNPROTECT(1);
-    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_tau_var(h, REAL(v)), h); SET_VECTOR_ELT(out, 1, v); UNPROTECT(1);
-    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_mu_mean(h, REAL(v)), h); SET_VECTOR_ELT(out, 2, v); UNPROTECT(1);
-    v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_yhat_mean(h, REAL(v)), h); SET_VECTOR_ELT(out, 3, v); UNPROTECT(1);
-    v = PROTECT(Rf_allocVector(REALSXP, ns)); check(bcfgpu_get_sigma(h, REAL(v)), h); SET_VECTOR_ELT(out, 4, v); UNPROTECT(1);
-    {
-        SEXP a = PROTECT(Rf_allocVector(REALSXP, ns)), b = PROTECT(Rf_allocVector(REALSXP, ns));
-        check(bcfgpu_get_scales(h, REAL(a), REAL(b)), h);
-        SET_VECTOR_ELT(out, 5, a); SET_VECTOR_ELT(out, 6, b);
-        UNPROTECT(2);
-    }
-    if (keep) {
-        /* the library returns draw-major rows (nsaved x n, row-major) = an n x nsaved column-major R matrix: the R
-         * wrapper transposes to bcf's nsim x n */
-        for (int which = 0; which < 3; ++which) {
-            v = PROTECT(Rf_allocMatrix(REALSXP, (int)n, ns));
-            check(bcfgpu_get_draws(h, which, REAL(v)), h);
-            SET_VECTOR_ELT(out, 7 + which, v);
-            UNPROTECT(1);
-        }
-    }
-    SET_VECTOR_ELT(out, 10, Rf_ScalarReal(ms));
-    bcfgpu_destroy(h);
+    bcfgpu_handle **hs = (bcfgpu_handle **)calloc((size_t)nch, sizeof(bcfgpu_handle *));
+    if (!hs) Rf_error("bcfgpu_R_fit_chains: out of memory");
+    /* on failure (or interrupt) the library has already destroyed every handle */
+    check(bcfgpu_fit_chains(&cfg, nch, ndev ? INTEGER(devices_) : NULL, ndev, (int64_t)n, p_con, p_mod, REAL(y), INTEGER(z),
+                            REAL(xc), REAL(xm), REAL(cuts_c), INTEGER(off_c), REAL(cuts_m), INTEGER(off_m), nburn, nsim,
+                            nthin, interrupt_pending, NULL, hs), hs, nch);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, nch));
+    for (int c = 0; c < nch; ++c) SET_VECTOR_ELT(out, c, chain_result(hs, nch, c, n, keep));
+    destroy_all(hs, nch);
+    free(hs);
     UNPROTECT(1);
     return out;
 }
 
 static const R_CallMethodDef call_methods[] = {
     {"bcfgpu_R_device_count", (DL_FUNC)&bcfgpu_R_device_count, 0},
-    {"bcfgpu_R_fit", (DL_FUNC)&bcfgpu_R_fit, 13},
+    {"bcfgpu_R_fit_chains", (DL_FUNC)&bcfgpu_R_fit_chains, 15},
     {NULL, NULL, 0}};
 
 void R_init_BayesIVgpu(DllInfo *dll)

@@ -1,6 +1,6 @@
 """ctypes binding of libbcfgpu.so -- exactly the entry points declared in include/bcfgpu.h.
 
-This is the Python stand-in for the R shim (bcf_iv_b200/R/src/r_shim.c): same C-ABI, host buffers in, host
+This is the Python stand-in for the R shim (bcf_iv_b200/R/BayesIVgpu/src/r_shim.c): same C-ABI, host buffers in, host
 buffers out.  There is no CPU fallback: if the library is missing it is an ImportError-like failure, and if
 there is no CUDA device every compute call raises BcfGpuError.
 """
@@ -15,13 +15,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbcfgpu.so")
 
 MAX_LEAVES = 128
-STATUS = {0: "OK", 1: "BAD_ARG", 2: "CUDA", 3: "NCCL", 4: "NUMERIC", 5: "OOM", 6: "STATE"}
+STATUS = {0: "OK", 1: "BAD_ARG", 2: "CUDA", 3: "NCCL", 4: "NUMERIC", 5: "OOM", 6: "STATE", 7: "INTERRUPTED"}
 ENGINE_AUTO, ENGINE_GRAPH, ENGINE_PERSISTENT, ENGINE_PERSISTENT_HBM, ENGINE_BATCHED, ENGINE_PIPELINED = 0, 1, 2, 3, 4, 5
 
 # every symbol include/bcfgpu.h declares (tests check the library exports each of them)
 SYMBOLS = [
     "bcfgpu_abi_version", "bcfgpu_device_count", "bcfgpu_last_error", "bcfgpu_config_init", "bcfgpu_create",
-    "bcfgpu_destroy", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_data", "bcfgpu_run",
+    "bcfgpu_destroy", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_data", "bcfgpu_run", "bcfgpu_request_stop",
+    "bcfgpu_fit_chains",
     "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_h2d_bytes", "bcfgpu_engine_in_use", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
     "bcfgpu_get_mu_mean", "bcfgpu_get_yhat_mean", "bcfgpu_get_sigma", "bcfgpu_get_scales", "bcfgpu_get_draws",
     "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
@@ -51,6 +52,8 @@ class Config(C.Structure):
     ]
 
 
+POLL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)    # bcfgpu_fit_chains' interrupt hook
+
 _lib = None
 
 
@@ -78,6 +81,9 @@ def load():
     L.bcfgpu_set_shard.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.bcfgpu_set_data.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, dp, ip, dp, dp, dp, ip, dp, ip]
     L.bcfgpu_run.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    L.bcfgpu_request_stop.argtypes = [vp]
+    L.bcfgpu_fit_chains.argtypes = [C.POINTER(Config), C.c_int32, ip, C.c_int32, C.c_int64, C.c_int32, C.c_int32, dp, ip, dp,
+                                    dp, dp, ip, dp, ip, C.c_int32, C.c_int32, C.c_int32, POLL_FN, vp, C.POINTER(vp)]
     L.bcfgpu_last_run_ms.argtypes = [vp, dp]
     L.bcfgpu_kernel_launches.argtypes = [vp, lp]
     L.bcfgpu_h2d_bytes.argtypes = [vp, lp]
@@ -164,6 +170,24 @@ class Sampler:
         check(L.bcfgpu_create(C.byref(c), C.byref(self._h)))
         self.n = 0
         self._keep = []
+
+    @classmethod
+    def _adopt(cls, handle, cfg, n, off_con, off_mod, p_con, p_mod):
+        """wrap a handle made by the library (bcfgpu_fit_chains)"""
+        s = cls.__new__(cls)
+        s.cfg, s.T, s._h, s.n, s._keep = cfg, cfg.ntree_con + cfg.ntree_mod, C.c_void_p(handle), n, []
+        s.off_con, s.off_mod, s.p_con, s.p_mod = off_con, off_mod, p_con, p_mod
+        return s
+
+    def request_stop(self):
+        """thread-safe: the bcfgpu_run in progress on another thread returns INTERRUPTED at its next launch boundary"""
+        check(load().bcfgpu_request_stop(self._h))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -353,3 +377,42 @@ def op_rng_probe(seed, chain, sweep, tree, purpose, idx):
     o = np.zeros(3)
     check(load().bcfgpu_op_rng_probe(seed, chain, sweep, tree, purpose, idx, _dp(o)))
     return o
+
+
+def fit_chains(cfg_kw, n_chains, devices, y, z, x_con, x_mod, cuts_con, off_con, cuts_mod, off_mod, nburn, nsim, nthin=1,
+               poll=None):
+    """bcfgpu_fit_chains: n_chains chains in one native call (one host thread per device inside the library).
+    Returns a list of Sampler objects wrapping the finished chains (close them)."""
+    L = load()
+    c = default_config()
+    for k, v in cfg_kw.items():
+        if k == "lambda":
+            k = "lambda_"
+        if not hasattr(c, k):
+            raise TypeError(f"unknown config field {k}")
+        setattr(c, k, v)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    z = np.ascontiguousarray(z, dtype=np.int32)
+    xc = np.asfortranarray(x_con, dtype=np.float64)
+    n = y.size
+    if c.ntree_mod > 0:
+        xm = np.asfortranarray(x_mod, dtype=np.float64)
+        cm = np.ascontiguousarray(cuts_mod, dtype=np.float64); om = np.ascontiguousarray(off_mod, dtype=np.int32)
+        p_mod = xm.shape[1]
+    else:
+        xm = cm = om = None
+        p_mod = 0
+    cc = np.ascontiguousarray(cuts_con, dtype=np.float64); oc = np.ascontiguousarray(off_con, dtype=np.int32)
+    if xc.shape[0] != n or z.size != n or (xm is not None and xm.shape[0] != n):
+        raise ValueError("row count mismatch")
+    dv = np.ascontiguousarray(devices if devices is not None else [], dtype=np.int32)
+    hs = (C.c_void_p * n_chains)()
+    cb = POLL_FN(lambda _ctx: int(bool(poll()))) if poll is not None else C.cast(None, POLL_FN)
+    check(L.bcfgpu_fit_chains(C.byref(c), n_chains, _ip(dv) if dv.size else None, dv.size, n, xc.shape[1], p_mod, _dp(y),
+                              _ip(z), _dp(xc), _dp(xm), _dp(cc), _ip(oc), _dp(cm), _ip(om), nburn, nsim, nthin, cb, None, hs))
+    out = []
+    for k in range(n_chains):
+        ck = Config.from_buffer_copy(c)
+        ck.chain = c.chain + k
+        out.append(Sampler._adopt(hs[k], ck, n, oc, om, xc.shape[1], p_mod))
+    return out

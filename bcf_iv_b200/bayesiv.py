@@ -161,6 +161,8 @@ def tsls(y, w, z):
     summary.ivreg), and the weak-instrument test (first-stage F of z, on (1, n - 2) df)."""
     y, w, z = (np.asarray(a, dtype=np.float64) for a in (y, w, z))
     n = len(y)
+    if n <= 2:                                               # no residual degrees of freedom
+        return float("nan"), float("nan"), float("nan")
     zc, wc, yc = z - z.mean(), w - w.mean(), y - y.mean()
     szw, szz = float(zc @ wc), float(zc @ zc)
     if szz == 0 or szw == 0:
@@ -188,6 +190,11 @@ def tsls(y, w, z):
 # ---------------------------------------------------------------------------------------------------------------
 def p_adjust(p, method="holm"):
     p = np.asarray(p, dtype=np.float64)
+    ok = np.isfinite(p)
+    if not ok.all():                                         # R: NAs are left out, n = number of non-NA p-values
+        out = np.full(len(p), np.nan)
+        out[ok] = p_adjust(p[ok], method)
+        return out
     n = len(p)
     if n == 0 or method == "none":
         return p.copy()
@@ -271,28 +278,34 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     if "max_ctas" not in fit_args and len(disc) <= 27 * 256 * (_bcf._lib.B200_SMS // 2) - 512:
         fit_args["max_ctas"] = _bcf._lib.B200_SMS // 2
     with ThreadPoolExecutor(max_workers=2) as pool:
-        f_pic = pool.submit(_bcf.bcf, w[disc], z[disc], Xd, Xd, pihat, **fit_args)          # P(complier | x)
+        # the reference's two samplers are independent (bartc / bcf): the complier-proportion fit gets its own Philox
+        # stream (chain 1 of the seed), so itt and pic do not share their Monte Carlo noise
+        f_pic = pool.submit(_bcf.bcf, w[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, first_chain=1))   # P(complier | x)
         f_itt = pool.submit(_bcf.bcf, y[disc], z[disc], Xd, Xd, pihat, **fit_args)          # R/bcf_iv.R:89-91
         pic, itt = f_pic.result()["tau_mean"], f_itt.result()["tau_mean"]
     tauhat = itt / pic                                                                      # R/bcf_iv.R:94
     nodes, where = cart(Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
     ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
     leaves = {nid for nid in ids if nodes[nid].left is None}
-    tab = pd.DataFrame([rows[n] if rows[n] is not None else {c: None for c in COLUMNS[:-1]} for n in ids],
-                       index=ids, columns=COLUMNS[:-1])
-    adj = pd.Series([None] * len(ids), index=ids, dtype=object)
+    # rows are indexed by rpart NODE NUMBER as in the reference (bcfivMat[i, ], R/bcf_iv.R:174): the table starts with
+    # one row per node and grows, NA rows in between, when a node number exceeds that count
+    nrow = max(len(ids), max(nid for nid in ids if rows[nid] is not None or nid in leaves))
+    index = list(range(1, nrow + 1))
+    blank = {c: None for c in COLUMNS[:-1]}
+    tab = pd.DataFrame([rows[n] if rows.get(n) is not None else blank for n in index], index=index, columns=COLUMNS[:-1])
+    adj = pd.Series([None] * nrow, index=index, dtype=object)
     lv = [n for n in ids if n in leaves and rows[n] is not None]
     if lv:
         a = np.round(p_adjust([rows[n]["pvalue"] for n in lv], adj_method), 5)
         for n_, v in zip(lv, a):
-            adj[n_] = float(v)
+            adj[n_] = None if not np.isfinite(v) else float(v)
     tab["Adj_pvalue"] = adj
     return tab
 
 
-def bcf_itt(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5, max_depth=2, seed=42, **bcf_args):
-    """Heterogeneity in the intention-to-treat effect (R/bcf_itt.R:33): prints the node effects and returns None,
-    as the reference does."""
+def bcf_itt(y, w, z, x, binary=False, max_depth=2, n_burn=500, n_sim=500, inference_ratio=0.5, seed=42, **bcf_args):
+    """Heterogeneity in the intention-to-treat effect (R/bcf_itt.R:33; same positional order of the arguments): prints the
+    node effects and returns None, as the reference does."""
     y, w, z = (np.asarray(a, dtype=np.float64).ravel() for a in (y, w, z))
     if binary and not np.all((y == 0) | (y == 1)):
         raise ValueError("binary = TRUE needs a 0/1 outcome")

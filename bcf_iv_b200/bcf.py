@@ -11,7 +11,6 @@ CUDA device the call raises.  The R twin of this file is bcf_iv_b200/R/BayesIVgp
 """
 from __future__ import annotations
 
-import threading
 import warnings
 
 import numpy as np
@@ -21,19 +20,16 @@ from . import _lib, prep
 DRAW_BYTES_CAP = 8 << 30   # keep nsim x n draws on the device only below this (3 matrices of doubles)
 
 
-def _run_chain(out, idx, P, cuts, cfg, nburn, nsim, nthin, keep, device):
+def _collect(s, keep):
+    """what bcf() returns from one finished chain (a _lib.Sampler); always closes it"""
     try:
-        s = _lib.Sampler(device=device, **cfg)
-        s.set_data(P.yscale, P.z, P.x_c, P.x_m, *cuts)
-        s.run(nburn, nsim, nthin)
         r = {"sigma": s.sigma(), "scales": s.scales(), "tau_mean": s.tau_mean(), "mu_mean": s.mu_mean(),
              "yhat_mean": s.yhat_mean(), "tau_var": s.tau_var(), "ms": s.last_run_ms, "moves": s.counters()}
         if keep:
             r["tau"], r["mu"], r["yhat"] = s.draws("tau"), s.draws("mu"), s.draws("yhat")
+        return r
+    finally:
         s.close()
-        out[idx] = r
-    except BaseException as e:     # re-raised on the calling thread
-        out[idx] = e
 
 
 def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nthin=1, update_interval=100,
@@ -42,7 +38,7 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
         nu=3.0, lambda_=None, sigq=0.9, sighat=None, include_pi="control", use_muscale=True, use_tauscale=True,
         w=None, random_seed=None, n_chains=1, n_cores=None, n_threads=None, no_output=True,
         save_tree_directory=None, log_file=None, verbose=False,
-        devices=None, keep_draws=None, engine=_lib.ENGINE_AUTO, max_ctas=0):
+        devices=None, keep_draws=None, engine=_lib.ENGINE_AUTO, max_ctas=0, first_chain=0):
     """Fit the Bayesian Causal Forest  y = mu(x, pihat) + tau(x) z + eps  on the GPU.
 
     Returns a dict with bcf's fields: `sigma` (nsim*n_chains), `yhat`, `mu`, `tau` (nsim*n_chains x n, original row
@@ -51,7 +47,8 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
 
     Extras beyond bcf's signature: `devices` (CUDA ordinals, chains are dealt round-robin: one independent chain per
     GPU), `keep_draws` (None = keep the three nsim x n matrices only while they fit DRAW_BYTES_CAP),
-    `engine`, `max_ctas` (0 = the whole GPU; k > 0 = at most k CTAs, so that several fits can run side by side on one GPU).  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
+    `engine`, `max_ctas` (0 = the whole GPU; k > 0 = at most k CTAs, so that several fits can run side by side on one GPU),
+    `first_chain` (Philox stream of the first chain; chain c uses first_chain + c).  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
     no_output, verbose, update_interval) are accepted and ignored; observation weights `w` are not implemented.
     """
     if nburn is None or nsim is None:
@@ -83,38 +80,40 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
                con_sd=P.con_sd, mod_sd=P.mod_sd, nu=float(nu), lambda_=P.lambda_, sigma_init=P.sigma_init,
                use_muscale=int(bool(use_muscale)), use_tauscale=int(bool(use_tauscale)), seed=seed,
                keep_draws=7 if keep_draws else 0, engine=int(engine), max_ctas=int(max_ctas))
-    res = [None] * int(n_chains)
-    threads = []
     # chains that share a GPU: side by side on a share of its SMs each while an SM's 27 tiles of 256 rows hold the share's
-    # observations, else one after the other (each launch then fills the device)
+    # observations, else one after the other (each launch then fills the device).  All chains run inside ONE native call
+    # (bcfgpu_fit_chains: one host thread per device, or per chain when they run side by side).
     per_dev = -(-int(n_chains) // len(devs))
     share = _lib.B200_SMS // per_dev if per_dev > 1 else 0
-    side_by_side = per_dev > 1 and int(max_ctas) == 0 and share >= 1 and n <= 27 * 256 * share - 512
-    if side_by_side:
+    if per_dev > 1 and int(max_ctas) == 0 and share >= 1 and n <= 27 * 256 * share - 512:
         cfg["max_ctas"] = share
-    for c in range(int(n_chains)):
-        ccfg = dict(cfg, chain=c)
-        th = threading.Thread(target=_run_chain, args=(res, c, P, (cc, oc, cm, om), ccfg, int(nburn), int(nsim),
-                                                       int(nthin), keep_draws, devs[c % len(devs)]))
-        th.start()
-        threads.append(th)
-        if per_dev > 1 and not side_by_side:
-            th.join()
-    for th in threads:
-        th.join()
-    for r in res:
-        if isinstance(r, BaseException):
-            raise r
+    cfg["chain"] = int(first_chain)
+    samplers = _lib.fit_chains(cfg, int(n_chains), devs, P.yscale, P.z, P.x_c, P.x_m, cc, oc, cm, om, int(nburn), int(nsim),
+                               int(nthin))
+    res, err = [], None
+    for smp in samplers:                                      # every handle is closed even if one read-back fails
+        try:
+            res.append(_collect(smp, keep_draws))
+        except BaseException as e:
+            err = err or e
+    if err is not None:
+        raise err
+    ns = len(res[0]["sigma"])
+    ntot = ns * len(res)
+    tau_mean = np.mean([r["tau_mean"] for r in res], axis=0)
+    # variance of the stacked draws (what out["tau"] holds): within-chain sums of squares + spread of the chain means
+    tau_var = (sum((ns - 1) * r["tau_var"] + ns * (r["tau_mean"] - tau_mean) ** 2 for r in res) / (ntot - 1)
+               if ntot > 1 else np.zeros_like(tau_mean))
     sdy, muy = P.sdy, P.muy
     out = {
         "sigma": sdy * np.concatenate([r["sigma"] for r in res]),
         "mu_scale": sdy * np.concatenate([r["scales"][0] for r in res]),
         "tau_scale": sdy * np.concatenate([r["scales"][1] for r in res]),
         "perm": P.perm + 1,                                   # R's 1-based order(z, decreasing = TRUE)
-        "tau_mean": sdy * np.mean([r["tau_mean"] for r in res], axis=0),
+        "tau_mean": sdy * tau_mean,
         "mu_mean": muy + sdy * np.mean([r["mu_mean"] for r in res], axis=0),
         "yhat_mean": muy + sdy * np.mean([r["yhat_mean"] for r in res], axis=0),
-        "tau_var": sdy ** 2 * np.mean([r["tau_var"] for r in res], axis=0),
+        "tau_var": sdy ** 2 * tau_var,
         "device_ms": [r["ms"] for r in res],
         "moves": [r["moves"] for r in res],
     }

@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <chrono>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace bcf;
@@ -87,7 +89,7 @@ struct ForestHost {
 
 struct bcfgpu_handle {
     bcfgpu_config cfg;
-    int device = 0, num_sms = 148;
+    int device = 0, num_sms = 148, max_optin = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int rank = 0, nranks = 1;
@@ -128,6 +130,7 @@ struct bcfgpu_handle {
     double last_ms = 0.0;
     int32_t nsaved = 0, post_cap = 0;
     int keep = 0;
+    std::atomic<int> stop{0};         // bcfgpu_request_stop: the run in progress ends at its next launch boundary
 };
 
 template <typename Tp>
@@ -231,6 +234,15 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_sweep_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_batched<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM_BYTES);
+    // The kernels that keep an SM's observations in shared memory: the attribute is per function and per DEVICE, not per
+    // handle, so it is raised once to the device's opt-in maximum (handles with different n on one GPU would otherwise
+    // lower each other's limit between select_kernel() and the launch); select_kernel() only checks its own need.
+    if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&h->max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    for (const void* fn : {(const void*)k_batched<true>, (const void*)k_pipe, (const void*)k_resident}) {
+        cudaFuncAttributes fa;
+        if (e2 == cudaSuccess) e2 = cudaFuncGetAttributes(&fa, fn);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin - (int)fa.sharedSizeBytes);
+    }
     if (e2 != cudaSuccess) { delete h; return fail(BCFGPU_ERR_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(e2)); }
     if (cfg->engine < BCFGPU_ENGINE_AUTO || cfg->engine > BCFGPU_ENGINE_PIPELINED) { delete h; return fail(BCFGPU_ERR_BAD_ARG, "unknown engine"); }
     h->engine = cfg->engine == BCFGPU_ENGINE_AUTO ? BCFGPU_ENGINE_PIPELINED : cfg->engine;
@@ -656,9 +668,22 @@ static int check_device_err(bcfgpu_handle* h)
     return BCFGPU_OK;
 }
 
+static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin);
 extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin)
 {
     USE(h); NEED_DATA(h);
+    const int rc = run_impl(h, nburn, nsim, nthin);
+    h->stop.store(0);                 // a stop request ends ONE run
+    return rc;
+}
+extern "C" int bcfgpu_request_stop(bcfgpu_handle* h)
+{
+    if (!h) return fail(BCFGPU_ERR_BAD_ARG, "null handle");
+    h->stop.store(1);                 // no CUDA call, no lock: safe from any thread
+    return BCFGPU_OK;
+}
+static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin)
+{
     if (nburn < 0 || nsim < 0 || nthin < 1) return fail(BCFGPU_ERR_BAD_ARG, "need nburn >= 0, nsim >= 0, nthin >= 1");
     const int64_t total64 = (int64_t)nburn + (int64_t)nsim * nthin;
     if (total64 > 2000000000ll) return fail(BCFGPU_ERR_BAD_ARG, "too many sweeps");
@@ -713,7 +738,10 @@ extern "C" int bcfgpu_run(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t
         rc = run_persistent(h, total);
         h->last_kernel = h->kernel;
     } else if (h->nranks == 1) {
-        for (int it = 0; it < total; ++it) CK(cudaGraphLaunch(h->gexec, h->stream));
+        for (int it = 0; it < total; ++it) {
+            if ((it & 63) == 0 && h->stop.load(std::memory_order_relaxed)) { cudaStreamSynchronize(h->stream); return fail(BCFGPU_ERR_INTERRUPTED, "run stopped by bcfgpu_request_stop"); }
+            CK(cudaGraphLaunch(h->gexec, h->stream));
+        }
         h->launches += (int64_t)total * (h->T + 4);
     } else {
         for (int it = 0; it < total && rc == BCFGPU_OK; ++it) rc = enqueue_sweep(h);
@@ -1249,7 +1277,7 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
         int tpc = std::max(1, std::min(48, (tiles + h->num_sms * 2 - 1) / (h->num_sms * 2)));
         const int gridx = (tiles + tpc - 1) / tpc;
         const size_t smem = per_obs ? (size_t)ncells * 32 : (size_t)(ncells + nleaf) * 16;
-        CK(cudaFuncSetAttribute(k_hist_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        CK(cudaFuncSetAttribute(k_hist_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));   // one value for every handle (the attribute is per device)
         k_hist_small<<<gridx, 256, smem, h->stream>>>(h->dev, forest, dlab, h->d_tmp2, nleaf, F.d_off, dsmall, (int)small.size(), dbase,
                                                        ncells, tpc, dout, per_obs ? 1 : 0);
     }
@@ -1324,8 +1352,7 @@ static int select_kernel(bcfgpu_handle* h)
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
         if (!coop) return fail(BCFGPU_ERR_CUDA, "device does not support cooperative launch");
-        int max_optin = 0;
-        CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        const int max_optin = h->max_optin;
         // One CTA per SM whatever n: a CTA without observation tiles still replays the decisions and takes its share of the
         // per-tree work that is dealt by CTA (proposals, tree write-back).  Measured (k_pipe): n = 500: 930 -> 1530
         // sweeps/s, n = 5e4: 1275 -> 1543 against a grid of one CTA per tile.
@@ -1342,8 +1369,7 @@ static int select_kernel(bcfgpu_handle* h)
         auto fits = [&](const void* fn, size_t need, int threads = PTHREADS) -> int {
             cudaFuncAttributes fa;
             if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) return 0;
-            if (need + fa.sharedSizeBytes + 1024 > (size_t)max_optin) return 0;
-            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) return 0;
+            if (need + fa.sharedSizeBytes > (size_t)max_optin) return 0;   // (the attribute was raised to the maximum in bcfgpu_create)
             int per_sm = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, need) != cudaSuccess) return 0;
             return per_sm >= 1;
@@ -1390,6 +1416,10 @@ static int run_persistent(bcfgpu_handle* h, int total)
     // keep launches short enough to stay interruptible (R_CheckUserInterrupt between batches)
     const int batch = 256;
     for (int done = 0; done < total;) {
+        if (h->stop.load(std::memory_order_relaxed)) {
+            cudaStreamSynchronize(h->stream);
+            return fail(BCFGPU_ERR_INTERRUPTED, "run stopped by bcfgpu_request_stop");
+        }
         int nsw = std::min(batch, total - done);
         Dev d = h->dev;
         d.pr.seq0 = (++h->launch_id) << 32;
@@ -1435,6 +1465,59 @@ static int run_persistent(bcfgpu_handle* h, int total)
         }
         h->launches++;
         done += nsw;
+    }
+    return BCFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// several chains in one call (bcf 2.x's n_chains): one host thread per chain, chain c on devices[c % n_devices]
+// ------------------------------------------------------------------------------------------------
+extern "C" int bcfgpu_fit_chains(const bcfgpu_config* cfg, int32_t n_chains, const int32_t* devices, int32_t n_devices,
+                                 int64_t n, int32_t p_con, int32_t p_mod, const double* y, const int32_t* z,
+                                 const double* xcon, const double* xmod, const double* cuts_con, const int32_t* cut_off_con,
+                                 const double* cuts_mod, const int32_t* cut_off_mod, int32_t nburn, int32_t nsim, int32_t nthin,
+                                 int (*poll)(void*), void* poll_ctx, bcfgpu_handle** handles_out)
+{
+    if (!cfg || !handles_out || n_chains < 1 || n_chains > 4096) return fail(BCFGPU_ERR_BAD_ARG, "bad argument");
+    if (n_devices < 0 || (n_devices > 0 && !devices)) return fail(BCFGPU_ERR_BAD_ARG, "bad device list");
+    for (int c = 0; c < n_chains; ++c) handles_out[c] = nullptr;
+    std::vector<int> rc((size_t)n_chains, BCFGPU_OK);
+    std::vector<std::string> msg((size_t)n_chains);
+    std::vector<std::thread> th;
+    std::atomic<int> running{n_chains};
+    // chains that share a device run one after the other on it (each launch fills the GPU) unless the caller gave them a
+    // share of the SMs (cfg.max_ctas): one worker per device walks its chains in order
+    const int nd = n_devices > 0 ? n_devices : 1;
+    const bool side_by_side = cfg->max_ctas > 0;
+    auto one_chain = [&](int c) {
+        bcfgpu_config cc = *cfg;
+        cc.chain = cfg->chain + (uint32_t)c;
+        if (n_devices > 0) cc.device = devices[c % n_devices];
+        int r = bcfgpu_create(&cc, &handles_out[c]);
+        if (!r) r = bcfgpu_set_data(handles_out[c], n, p_con, p_mod, y, z, xcon, xmod, cuts_con, cut_off_con, cuts_mod, cut_off_mod);
+        if (!r) r = bcfgpu_run(handles_out[c], nburn, nsim, nthin);
+        rc[c] = r;
+        if (r) msg[c] = g_err;
+        running.fetch_sub(1);
+    };
+    if (side_by_side) for (int c = 0; c < n_chains; ++c) th.emplace_back(one_chain, c);
+    else for (int dv = 0; dv < std::min(nd, n_chains); ++dv) th.emplace_back([&, dv]() { for (int c = dv; c < n_chains; c += nd) one_chain(c); });
+    bool stopped = false;
+    while (running.load() > 0) {      // the calling thread polls the caller's interrupt hook (R_CheckUserInterrupt, ...)
+        std::this_thread::sleep_for(std::chrono::milliseconds(poll ? 20 : 50));
+        if (poll && !stopped && poll(poll_ctx)) {
+            stopped = true;
+            for (int c = 0; c < n_chains; ++c) if (handles_out[c]) handles_out[c]->stop.store(1);
+        }
+        if (stopped) for (int c = 0; c < n_chains; ++c) if (handles_out[c]) handles_out[c]->stop.store(1);   // chains created since
+    }
+    for (auto& t : th) t.join();
+    int first = -1;
+    for (int c = 0; c < n_chains; ++c) if (rc[c] && first < 0) first = c;
+    if (first >= 0 || stopped) {
+        for (int c = 0; c < n_chains; ++c) { if (handles_out[c]) bcfgpu_destroy(handles_out[c]); handles_out[c] = nullptr; }
+        if (stopped) return fail(BCFGPU_ERR_INTERRUPTED, "interrupted");
+        return fail(rc[first], "chain " + std::to_string(first) + ": " + msg[first]);
     }
     return BCFGPU_OK;
 }

@@ -9,7 +9,7 @@
  *   .Call("_bcf_bcfoverparRcppClean", y, z, t(x_c), t(x_m), cutpoint lists, nburn, nsim, nthin, ...)
  * (third-party package `bcf`, imported un-pinned at DESCRIPTION:23 / NAMESPACE:9; source not vendored,
  * see SURVEY.md 8b/8c).  The R shim that binds these entry points with .Call is
- * bcf_iv_b200/R/src/r_shim.c; INTEGRATION.md shows the wiring.
+ * bcf_iv_b200/R/BayesIVgpu/src/r_shim.c; INTEGRATION.md shows the wiring.
  *
  * Conventions
  *   - plain C, no R / torch / CUDA types in any signature; every pointer is a HOST pointer unless the
@@ -45,7 +45,8 @@ typedef enum bcfgpu_status {
     BCFGPU_ERR_NCCL = 3,
     BCFGPU_ERR_NUMERIC = 4,     /* NaN / fixed-point range guard tripped on device (bcf stop()s on NaN too) */
     BCFGPU_ERR_OOM = 5,
-    BCFGPU_ERR_STATE = 6        /* call order (e.g. run before set_data) */
+    BCFGPU_ERR_STATE = 6,       /* call order (e.g. run before set_data) */
+    BCFGPU_ERR_INTERRUPTED = 7  /* bcfgpu_request_stop / the poll hook of bcfgpu_fit_chains ended the run */
 } bcfgpu_status;
 
 typedef enum bcfgpu_engine {
@@ -56,11 +57,12 @@ typedef enum bcfgpu_engine {
     BCFGPU_ENGINE_PERSISTENT_HBM = 3, /* same schedule, observation state kept in HBM/L2 (any n) */
     BCFGPU_ENGINE_BATCHED = 4      /* cooperative kernel, up to 8 trees per observation pass and per grid barrier (exact
                                       integer cross-count correction), state in shared memory */
-    , BCFGPU_ENGINE_PIPELINED = 5  /* BATCHED with the decisions off the pass's critical path: 16 warps stream the
-                                      observations while 8 warps decide the previous batch (cross-batch counts keep it
-                                      exact); sweeps that hold a tree with more than 8 keys fall back to BATCHED.
-                                      AUTO = PIPELINED when the observations of an SM fit in shared memory, else BATCHED,
-                                      else PERSISTENT */
+    , BCFGPU_ENGINE_PIPELINED = 5  /* BATCHED with the decisions off the pass's critical path: the CTA is split in 27 tile
+                                      warps that stream the observations, 4 chain warps that decide the previous batch of
+                                      4 trees (cross-batch counts keep it exact) and 1 utility warp that plans and stages
+                                      two batches ahead; sweeps that hold a tree with more than 8 keys fall back to BATCHED.
+                                      AUTO = PIPELINED when the observations of an SM fit in shared memory, else BATCHED
+                                      (state in shared memory, else in HBM), else PERSISTENT */
 } bcfgpu_engine;
 
 /* Hyper-parameters of the sampler: bcf()'s arguments after the R wrapper's rescaling. */
@@ -117,6 +119,22 @@ BCFGPU_API int bcfgpu_set_data(bcfgpu_handle *h, int64_t n, int32_t p_con, int32
  * Runs nburn + nsim*nthin Gibbs sweeps (continuing the chain if called again); sweep it is saved when
  * it >= nburn and it % nthin == 0, as bcf does.  Blocking. */
 BCFGPU_API int bcfgpu_run(bcfgpu_handle *h, int32_t nburn, int32_t nsim, int32_t nthin);
+/* Asks the run in progress on `h` (another thread is inside bcfgpu_run) to end at its next launch boundary (at most 256
+ * sweeps away); that bcfgpu_run returns BCFGPU_ERR_INTERRUPTED and the chain stays valid.  Callable from any thread. */
+BCFGPU_API int bcfgpu_request_stop(bcfgpu_handle *h);
+/* bcf 2.x's n_chains in ONE call: n_chains independent chains (Philox stream cfg->chain + c), chain c on CUDA device
+ * devices[c % n_devices] (n_devices = 0: cfg->device for all), one host thread per device inside the library, chains
+ * that share a device one after the other -- or side by side when cfg->max_ctas > 0 gives each a share of the SMs.
+ * The same host buffers serve every chain.  `poll` (may be NULL) is called on the CALLING thread about every 20 ms
+ * while the chains run; a non-zero return stops them (R shim: R_CheckUserInterrupt under R_ToplevelExec).
+ * On success handles_out[0..n_chains) hold the finished chains: read them with the bcfgpu_get_* calls, then
+ * bcfgpu_destroy each.  On failure every handle is destroyed and handles_out is all NULL. */
+BCFGPU_API int bcfgpu_fit_chains(const bcfgpu_config *cfg, int32_t n_chains, const int32_t *devices, int32_t n_devices,
+                                 int64_t n, int32_t p_con, int32_t p_mod, const double *y, const int32_t *z,
+                                 const double *xcon, const double *xmod, const double *cuts_con,
+                                 const int32_t *cut_off_con, const double *cuts_mod, const int32_t *cut_off_mod,
+                                 int32_t nburn, int32_t nsim, int32_t nthin, int (*poll)(void *), void *poll_ctx,
+                                 bcfgpu_handle **handles_out);
 BCFGPU_API int bcfgpu_last_run_ms(bcfgpu_handle *h, double *device_ms);  /* CUDA-event time of the last run */
 BCFGPU_API int bcfgpu_kernel_launches(bcfgpu_handle *h, int64_t *count); /* kernels launched since create */
 /* bytes set_data copied host -> device.  When x_moderate IS the leading columns of x_control (same pointer, same

@@ -36,4 +36,6 @@ void Rf_unprotect(int);
 #define PROTECT(s) Rf_protect(s)
 #define UNPROTECT(n) Rf_unprotect(n)
 void Rf_error(const char *, ...) __attribute__((noreturn));
+Rboolean R_ToplevelExec(void (*fun)(void *), void *data);
+void R_CheckUserInterrupt(void);
 #endif

@@ -36,7 +36,7 @@ def test_r_functions_keep_the_reference_signatures():
     assert _formals(os.path.join(PKG, "R", "bcf_iv.R"), "bcf_iv") == [
         "y", "w", "z", "x", "binary", "n_burn", "n_sim", "inference_ratio", "max_depth", "cp", "minsplit", "adj_method", "seed"]
     assert _formals(os.path.join(PKG, "R", "bcf_itt.R"), "bcf_itt") == [
-        "y", "w", "z", "x", "binary", "n_burn", "n_sim", "inference_ratio", "max_depth", "seed"]
+        "y", "w", "z", "x", "binary", "max_depth", "n_burn", "n_sim", "inference_ratio", "seed"]      # R/bcf_itt.R:33-34
     assert _formals(os.path.join(PKG, "R", "generate_dataset.R"), "generate_dataset")[:6] == [
         "n", "p", "rho", "null", "effect_size", "compliance"]
     b = _formals(os.path.join(PKG, "R", "bcf.R"), "bcf")
