@@ -21,7 +21,7 @@ ENGINE_AUTO, ENGINE_GRAPH, ENGINE_PERSISTENT, ENGINE_PERSISTENT_HBM, ENGINE_BATC
 # every symbol include/bcfgpu.h declares (tests check the library exports each of them)
 SYMBOLS = [
     "bcfgpu_abi_version", "bcfgpu_device_count", "bcfgpu_last_error", "bcfgpu_config_init", "bcfgpu_create",
-    "bcfgpu_destroy", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_data", "bcfgpu_run", "bcfgpu_request_stop",
+    "bcfgpu_destroy", "bcfgpu_release_cached_memory", "bcfgpu_cache_stats", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_data", "bcfgpu_run", "bcfgpu_request_stop",
     "bcfgpu_fit_chains",
     "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_h2d_bytes", "bcfgpu_engine_in_use", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
     "bcfgpu_get_mu_mean", "bcfgpu_get_yhat_mean", "bcfgpu_get_sigma", "bcfgpu_get_scales", "bcfgpu_get_draws",
@@ -77,6 +77,8 @@ def load():
     L.bcfgpu_config_init.restype = None
     L.bcfgpu_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     L.bcfgpu_destroy.argtypes = [vp]
+    L.bcfgpu_release_cached_memory.argtypes = []
+    L.bcfgpu_cache_stats.argtypes = [lp]
     L.bcfgpu_nccl_unique_id.argtypes = [C.c_char_p]
     L.bcfgpu_set_shard.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.bcfgpu_set_data.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, dp, ip, dp, dp, dp, ip, dp, ip]
@@ -144,6 +146,16 @@ def default_config() -> Config:
     c = Config()
     load().bcfgpu_config_init(C.byref(c))
     return c
+
+
+def release_cached_memory():
+    check(load().bcfgpu_release_cached_memory())
+
+
+def cache_stats():
+    o = np.zeros(2, dtype=np.int64)
+    check(load().bcfgpu_cache_stats(_lp(o)))
+    return {"device_bytes": int(o[0]), "pinned_bytes": int(o[1])}
 
 
 def nccl_unique_id() -> bytes:

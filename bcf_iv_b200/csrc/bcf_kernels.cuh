@@ -24,27 +24,145 @@ __device__ __forceinline__ int upper_bound_cut(const double* __restrict__ cuts, 
     }
     return lo;
 }
-// grid.y = column within the chunk
+// grid = (blocks of BIN_ROWS rows, columns of the chunk).  The rows of a block land in two runs of the internal order --
+// its treated rows and its control rows, each contiguous because bcf's permutation is stable -- so the bins are compacted
+// per run in shared memory and leave as aligned 32-bit words: x is read once with coalesced 8-byte loads and every
+// 32-byte sector of the binned column is written once (the scattered byte stores of the first version made the kernel
+// run at a third of the copy bandwidth).
+constexpr int BIN_ROWS = 2048;
+template <typename B>
+__device__ __forceinline__ void bin_flush_run(B* __restrict__ dst, int64_t g0, int len, const B* __restrict__ src, int t)
+{
+    constexpr int PER = 4 / (int)sizeof(B);                       // elements per 32-bit word
+    const int head = min(len, (int)((PER - (g0 & (PER - 1))) & (PER - 1)));
+    if (t < head) dst[g0 + t] = src[t];
+    const int nwords = (len - head) / PER;
+    uint32_t* out = reinterpret_cast<uint32_t*>(dst + g0 + head);
+    for (int w = t; w < nwords; w += 256) {
+        const B* q = src + head + PER * w;
+        uint32_t v = 0;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) v |= (uint32_t)q[e] << (8 * (int)sizeof(B) * e);
+        out[w] = v;
+    }
+    const int tail0 = head + PER * nwords;
+    if (t < len - tail0) dst[g0 + tail0 + t] = src[tail0 + t];
+}
 __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ x, int64_t n, int ncols, int col0,
                                              const double* __restrict__ cuts, const int32_t* __restrict__ off,
                                              const int32_t* __restrict__ col_index, const uint8_t* __restrict__ col_is16,
-                                             const int32_t* __restrict__ pos, int64_t n_pad, uint8_t* bins8,
+                                             const int32_t* __restrict__ pos, int64_t n_pad, int trt_pad, uint8_t* bins8,
                                              uint16_t* bins16)
 {
+    __shared__ __align__(16) uint16_t sb[BIN_ROWS];               // the block's bins in run order (uint8 columns: as bytes)
+    __shared__ int s_min[2], s_cnt[2];
     const int c = blockIdx.y;
     if (c >= ncols) return;
-    const int v = col0 + c;
+    const int v = col0 + c, t = threadIdx.x;
     const double* xc = x + (int64_t)c * n;
     const double* cv = cuts + off[v];
     const int nc = off[v + 1] - off[v];
     const int ci = col_index[v];
     const bool w16 = col_is16[v] != 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int b = upper_bound_cut(cv, nc, xc[i]);
-        const int64_t q = pos ? (int64_t)pos[i] : i;
-        if (w16) bins16[(int64_t)ci * n_pad + q] = (uint16_t)b;
-        else bins8[(int64_t)ci * n_pad + q] = (uint8_t)b;
+    for (int64_t r0 = (int64_t)blockIdx.x * BIN_ROWS; r0 < n; r0 += (int64_t)gridDim.x * BIN_ROWS) {
+        const int rows = (int)min((int64_t)BIN_ROWS, n - r0);
+        if (t < 2) { s_min[t] = 0x7fffffff; s_cnt[t] = 0; }
+        __syncthreads();
+        int q[BIN_ROWS / 256], bn[BIN_ROWS / 256];
+        int mn[2] = {0x7fffffff, 0x7fffffff}, cnt_t = 0;
+#pragma unroll
+        for (int k = 0; k < BIN_ROWS / 256; ++k) {
+            const int r = k * 256 + t;
+            q[k] = -1; bn[k] = 0;
+            if (r < rows) {
+                q[k] = pos[r0 + r];
+                bn[k] = upper_bound_cut(cv, nc, xc[r0 + r]);
+                const int g = q[k] < trt_pad ? 1 : 0;               // treated positions lie below trt_pad
+                mn[g] = min(mn[g], q[k]);
+                cnt_t += g;
+            }
+        }
+        cnt_t = __reduce_add_sync(0xffffffffu, cnt_t);
+        mn[0] = __reduce_min_sync(0xffffffffu, mn[0]);
+        mn[1] = __reduce_min_sync(0xffffffffu, mn[1]);
+        if ((t & 31) == 0) { atomicAdd(&s_cnt[1], cnt_t); atomicMin(&s_min[0], mn[0]); atomicMin(&s_min[1], mn[1]); }
+        __syncthreads();
+        // the block's treated rows form the run [p0, p0 + n_same), its control rows [o0, o0 + n_other): positions of one
+        // group increase with the row
+        const int n_same = s_cnt[1], n_other = rows - n_same, p0 = s_min[1], o0 = s_min[0];
+        uint8_t* sb8 = reinterpret_cast<uint8_t*>(sb);
+#pragma unroll
+        for (int k = 0; k < BIN_ROWS / 256; ++k)
+            if (q[k] >= 0) {
+                const int li = q[k] < trt_pad ? q[k] - p0 : n_same + (q[k] - o0);
+                if (w16) sb[li] = (uint16_t)bn[k]; else sb8[li] = (uint8_t)bn[k];
+            }
+        __syncthreads();
+        if (w16) {
+            uint16_t* dst = bins16 + (int64_t)ci * n_pad;
+            if (n_same > 0) bin_flush_run<uint16_t>(dst, p0, n_same, sb, t);
+            if (n_other > 0) bin_flush_run<uint16_t>(dst, o0, n_other, sb + n_same, t);
+        } else {
+            uint8_t* dst = bins8 + (int64_t)ci * n_pad;
+            if (n_same > 0) bin_flush_run<uint8_t>(dst, p0, n_same, sb8, t);
+            if (n_other > 0) bin_flush_run<uint8_t>(dst, o0, n_other, sb8 + n_same, t);
+        }
+        __syncthreads();
     }
+}
+// bcf's perm = order(z, decreasing = TRUE), applied on the device: one CTA per chunk of PLACE_CHUNK rows, whose count of
+// treated rows BEFORE the chunk comes from the host's validation pass.  Treated rows go to [0, ntrt) in row order, control
+// rows to [trt_pad, trt_pad + nctl) (each group is padded to whole warp tiles).  Writes pos (row -> position), orig
+// (position -> row; the padding stays -1) and y in internal order.
+__global__ void __launch_bounds__(256) k_place(const double* __restrict__ yraw, const int32_t* __restrict__ zraw,
+                                               const int32_t* __restrict__ chunk_trt, int64_t n, int64_t trt_pad,
+                                               int32_t* __restrict__ pos, int32_t* __restrict__ orig, double* __restrict__ y)
+{
+    __shared__ int wsum[8];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 4096;
+    int64_t trt_base = chunk_trt[blockIdx.x];
+    int64_t ctl_base = trt_pad + (r0 - trt_base);
+    for (int it = 0; it < 4096 / 256 && r0 + it * 256 < n; ++it) {
+        const int64_t i = r0 + it * 256 + t;
+        const bool valid = i < n;
+        const int zi = valid ? zraw[i] : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, zi != 0);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int sv = wsum[w]; total += sv; if (w < warp) before += sv; }
+        const int rank_t = before + __popc(bal & ((1u << lane) - 1u));
+        if (valid) {
+            const int64_t q = zi ? trt_base + rank_t : ctl_base + (t - rank_t);
+            pos[i] = (int32_t)q;
+            orig[q] = (int32_t)i;
+            y[q] = yraw[i];
+        }
+        trt_base += total; ctl_base += 256 - total;
+        __syncthreads();
+    }
+}
+// every tree a root [SURVEY A.2]: the mu trees' leaf ybar / ntree_con, the tau trees' trt_init / ntree_mod
+__global__ void __launch_bounds__(256) k_init_trees(TreeRec* t0, TreeRec* t1, int ntree_con, double mu_con, double mu_mod,
+                                                    int32_t ntrt, int32_t nctl)
+{
+    __shared__ TreeRec tr;
+    const int t = threadIdx.x, j = blockIdx.x;
+    for (int i = t; i < (int)(sizeof(TreeRec) / 16); i += blockDim.x) reinterpret_cast<uint4*>(&tr)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    for (int i = t; i < MAXN; i += blockDim.x) { tr.parent[i] = tr.left[i] = tr.right[i] = -1; tr.var[i] = tr.cut[i] = 0xFFFF; }
+    __syncthreads();
+    if (t == 0) {
+        tr.nnodes = 1; tr.nleaves = 1;
+        tr.node_slot[0] = 0; tr.depth[0] = 0; tr.heap[0] = 1; tr.slot_node[0] = 0;
+        tr.mu[0] = j < ntree_con ? mu_con : mu_mod;
+        tr.cnt1[0] = ntrt; tr.cnt0[0] = nctl;
+    }
+    __syncthreads();
+    store_tree(&t0[j], &tr);
+    store_tree(&t1[j], &tr);
 }
 __global__ void k_bin_simple(const double* __restrict__ x, int64_t n, const double* __restrict__ cuts, int ncut,
                              uint16_t* out)

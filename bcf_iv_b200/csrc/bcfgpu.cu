@@ -13,6 +13,8 @@
 #include <chrono>
 #include <cstring>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -78,6 +80,7 @@ constexpr int NCCL_INT8 = 0, NCCL_INT64 = 4, NCCL_SUM = 0, NCCL_MIN = 3;
 // ------------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------------
+struct Block { void* p; size_t bytes; };   // a block of the caching allocator (below)
 struct ForestHost {
     int p = 0, p8 = 0, p16 = 0;
     std::vector<int32_t> off, ncut, col_index;
@@ -90,8 +93,10 @@ struct ForestHost {
 struct bcfgpu_handle {
     bcfgpu_config cfg;
     int device = 0, num_sms = 148, max_optin = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_binned[2] = {nullptr, nullptr};   // set_data: chunks of X in flight
+    bool have_pos = false;            // h->pos mirrors d_pos
     int rank = 0, nranks = 1;
     void* comm = nullptr;
     Mailbox* d_mail = nullptr;        // [nranks] this rank's mailboxes (peer-memory exchange of the sharded mode)
@@ -103,8 +108,8 @@ struct bcfgpu_handle {
     int64_t n = 0, n_pad = 0, n_global = 0;
     int ntrt = 0, T = 0;
     bool has_data = false;
-    std::vector<void*> allocs;        // data-lifetime allocations
-    std::vector<void*> run_allocs;    // run-lifetime allocations (posterior buffers)
+    std::vector<Block> allocs;        // data-lifetime allocations (blocks of the caching allocator)
+    std::vector<Block> run_allocs;    // run-lifetime allocations (posterior buffers)
     ForestHost fh[2];
     std::vector<int32_t> pos;
     int32_t *d_pos = nullptr, *d_orig = nullptr;
@@ -133,23 +138,114 @@ struct bcfgpu_handle {
     std::atomic<int> stop{0};         // bcfgpu_request_stop: the run in progress ends at its next launch boundary
 };
 
+// ------------------------------------------------------------------------------------------------
+// Caching allocator.  cudaMalloc / cudaFree of the sampler's buffers (1.2 GB at n = 1e6, p = 100) cost 5 - 35 ms per
+// fit and vary from call to call; bcf_iv() fits twice per call and bcf(n_chains) many times, always with the same sizes.
+// Freed blocks are therefore parked per device (exact size classes: multiples of 2 MiB above 1 MiB, of 512 B below) and
+// handed out again; the cache is bounded (BCFGPU_CACHE_MB, default 4096 per device; 0 = off) and
+// bcfgpu_release_cached_memory() empties it.  The same for the pinned host staging of pageable inputs.
+// ------------------------------------------------------------------------------------------------
+struct MemCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_;
+    size_t bytes = 0;
+};
+constexpr int MAX_DEVICES = 64;
+static MemCache g_dev_cache[MAX_DEVICES];
+static MemCache g_pin_cache;
+static size_t cache_cap_bytes()
+{
+    static const size_t cap = [] { const char* e = getenv("BCFGPU_CACHE_MB"); return (size_t)(e ? std::max(0, atoi(e)) : 4096) << 20; }();
+    return cap;
+}
+static size_t size_class(size_t bytes)
+{
+    bytes = std::max<size_t>(bytes, 16);
+    const size_t g = bytes >= ((size_t)1 << 20) ? ((size_t)2 << 20) : 512;
+    return (bytes + g - 1) / g * g;
+}
+static void* cache_take(MemCache& c, size_t cls)
+{
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.free_.find(cls);
+    if (it == c.free_.end()) return nullptr;
+    void* p = it->second;
+    c.free_.erase(it);
+    c.bytes -= cls;
+    return p;
+}
+static bool cache_put(MemCache& c, void* p, size_t cls)
+{
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.bytes + cls > cache_cap_bytes()) return false;
+    c.free_.emplace(cls, p);
+    c.bytes += cls;
+    return true;
+}
+static void cache_drain(MemCache& c, bool pinned)
+{
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (auto& kv : c.free_) { if (pinned) cudaFreeHost(kv.second); else cudaFree(kv.second); }
+    c.free_.clear();
+    c.bytes = 0;
+}
+// device memory of the CURRENT device
+static cudaError_t dev_alloc(int device, size_t bytes, Block* out)
+{
+    const size_t cls = size_class(bytes);
+    void* p = (device >= 0 && device < MAX_DEVICES) ? cache_take(g_dev_cache[device], cls) : nullptr;
+    if (!p) {
+        cudaError_t e = cudaMalloc(&p, cls);
+        if (e != cudaSuccess && device >= 0 && device < MAX_DEVICES) {   // out of memory: give the parked blocks back and retry
+            cudaGetLastError();
+            cache_drain(g_dev_cache[device], false);
+            e = cudaMalloc(&p, cls);
+        }
+        if (e != cudaSuccess) { out->p = nullptr; out->bytes = 0; return e; }
+    }
+    out->p = p; out->bytes = cls;
+    return cudaSuccess;
+}
+static void dev_free(int device, Block b)
+{
+    if (!b.p) return;
+    if (device < 0 || device >= MAX_DEVICES || !cache_put(g_dev_cache[device], b.p, b.bytes)) cudaFree(b.p);
+}
+static cudaError_t pin_alloc(size_t bytes, Block* out)
+{
+    const size_t cls = size_class(bytes);
+    void* p = cache_take(g_pin_cache, cls);
+    if (!p) {
+        cudaError_t e = cudaHostAlloc(&p, cls, cudaHostAllocPortable);
+        if (e != cudaSuccess) { out->p = nullptr; out->bytes = 0; return e; }
+    }
+    out->p = p; out->bytes = cls;
+    return cudaSuccess;
+}
+static void pin_free(Block b)
+{
+    if (b.p && !cache_put(g_pin_cache, b.p, b.bytes)) cudaFreeHost(b.p);
+}
+
 template <typename Tp>
 static int dmalloc(bcfgpu_handle* h, Tp** p, size_t count, bool run_scope = false)
 {
-    void* q = nullptr;
+    Block b;
     const size_t bytes = std::max<size_t>(count * sizeof(Tp), 16);
-    cudaError_t e = cudaMalloc(&q, bytes);
+    cudaError_t e = dev_alloc(h->device, bytes, &b);
     if (e != cudaSuccess) {
         *p = nullptr;
+        cudaGetLastError();
         return fail(BCFGPU_ERR_OOM, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes: " + cudaGetErrorString(e));
     }
-    (run_scope ? h->run_allocs : h->allocs).push_back(q);
-    *p = (Tp*)q;
+    (run_scope ? h->run_allocs : h->allocs).push_back(b);
+    *p = (Tp*)b.p;
     return BCFGPU_OK;
 }
 #define DM(...) do { int r_ = dmalloc(__VA_ARGS__); if (r_) return r_; } while (0)
 
-static void free_list(std::vector<void*>& v) { for (void* p : v) cudaFree(p); v.clear(); }
+// (the owner has synchronised its stream: nothing in flight touches these blocks)
+static void free_list(bcfgpu_handle* h, std::vector<Block>& v) { for (Block b : v) dev_free(h->device, b); v.clear(); }
 static void drop_graph(bcfgpu_handle* h)
 {
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
@@ -194,6 +290,30 @@ void bcfgpu_config_init(bcfgpu_config* c)
     c->seed = 42; c->chain = 0; c->device = -1; c->engine = BCFGPU_ENGINE_AUTO; c->keep_draws = 0;
 }
 
+int bcfgpu_release_cached_memory(void)
+{
+    int cur = 0;
+    const bool have = cudaGetDevice(&cur) == cudaSuccess;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
+    for (int dv = 0; dv < std::min(ndev, MAX_DEVICES); ++dv) {
+        { std::lock_guard<std::mutex> lk(g_dev_cache[dv].mu); if (g_dev_cache[dv].free_.empty()) continue; }
+        cudaSetDevice(dv);
+        cache_drain(g_dev_cache[dv], false);
+    }
+    cache_drain(g_pin_cache, true);
+    if (have) cudaSetDevice(cur);
+    return BCFGPU_OK;
+}
+int bcfgpu_cache_stats(int64_t out2[2])
+{
+    if (!out2) return fail(BCFGPU_ERR_BAD_ARG, "null output");
+    out2[0] = out2[1] = 0;
+    for (int dv = 0; dv < MAX_DEVICES; ++dv) { std::lock_guard<std::mutex> lk(g_dev_cache[dv].mu); out2[0] += (int64_t)g_dev_cache[dv].bytes; }
+    { std::lock_guard<std::mutex> lk(g_pin_cache.mu); out2[1] = (int64_t)g_pin_cache.bytes; }
+    return BCFGPU_OK;
+}
+
 int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
 {
     if (!cfg || !out) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
@@ -225,6 +345,11 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     memset(&h->graph_dev, 0, sizeof(Dev));
     cudaError_t e2 = cudaSetDevice(dev);
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (int b = 0; b < 2; ++b) {
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_binned[b], cudaEventDisableTiming);
+    }
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev1);
     if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -256,11 +381,13 @@ int bcfgpu_destroy(bcfgpu_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_graph(h);
-    free_list(h->allocs);
-    free_list(h->run_allocs);
+    free_list(h, h->allocs);
+    free_list(h, h->run_allocs);
     for (int p = 0; p < MAX_RANKS; ++p) if (h->peer_mail[p]) cudaIpcCloseMemHandle(h->peer_mail[p]);
     if (h->d_mail) cudaFree(h->d_mail);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int b = 0; b < 2; ++b) { if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]); if (h->ev_binned[b]) cudaEventDestroy(h->ev_binned[b]); }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -391,33 +518,86 @@ static int setup_forest(bcfgpu_handle* h, int f, int p, const double* cuts, cons
     return BCFGPU_OK;
 }
 
-constexpr size_t MAX_STAGE = (size_t)1 << 28;   // fp64 staging buffer of K0: 256 Mi doubles = 2 GiB
+// ------------------------------------------------------------------------------------------------
+// host-side helpers of set_data: a few threads over row ranges (the R process calling us is single-threaded)
+// ------------------------------------------------------------------------------------------------
+static int host_threads()
+{
+    static const int nt = [] {
+        if (const char* e = getenv("BCFGPU_HOST_THREADS")) return std::max(1, std::min(64, atoi(e)));
+        return (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    }();
+    return nt;
+}
+// f(part, lo, hi) over [0, n) cut into `parts` ranges whose bounds are multiples of `align`
+template <class F>
+static void parallel_ranges(int64_t n, int64_t align, int parts, F f)
+{
+    const int64_t units = (n + align - 1) / align;
+    parts = (int)std::max<int64_t>(1, std::min<int64_t>(parts, units));
+    auto bound = [&](int t) { return std::min<int64_t>(n, units * t / parts * align); };
+    std::vector<std::thread> th;
+    for (int t = 1; t < parts; ++t) th.emplace_back([&, t] { f(t, bound(t), bound(t + 1)); });
+    f(0, bound(0), bound(1));
+    for (auto& x : th) x.join();
+}
 
-// K0 over a column-major host matrix, chunked by columns so the fp64 staging buffer stays bounded.
-// pre: the whole matrix is already on its way into this buffer on h->stream (set_data starts that copy before its
-// host-side work); the buffer is the caller's.
-static int bin_forest(bcfgpu_handle* h, int f, const double* x, double* pre = nullptr)
+constexpr int PLACE_CHUNK = 4096;                 // rows per CTA of k_place (the host hands over one prefix count per chunk)
+constexpr size_t STAGE_BYTES = (size_t)64 << 20;  // fp64 staging buffer of K0, two of them: copy of chunk k+1 under the binning of chunk k
+
+// K0 over a column-major host matrix: column chunks cross the bus on the copy stream (straight from the caller's buffer
+// when it is pinned; through two pinned staging buffers filled by host threads when it is pageable, as R's memory is)
+// while the previous chunk is binned on the compute stream.  No n x p fp64 copy ever exists on the device.
+static int bin_forest(bcfgpu_handle* h, int f, const double* x)
 {
     ForestHost& F = h->fh[f];
     if (F.p == 0) return BCFGPU_OK;
     const int64_t n = h->n;
-    int chunk = pre ? F.p : (int)std::max<int64_t>(1, std::min<int64_t>(F.p, (int64_t)(MAX_STAGE / (size_t)n)));
-    double* stage = pre;
-    if (!pre) CK(cudaMalloc((void**)&stage, (size_t)chunk * n * 8));
+    const size_t colb = (size_t)n * 8;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)F.p, STAGE_BYTES / colb));
+    const size_t stage_bytes = (size_t)chunk * colb;
+    cudaPointerAttributes pa;
+    bool pinned = cudaPointerGetAttributes(&pa, x) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (getenv("BCFGPU_FORCE_PAGEABLE")) pinned = false;
+    const int nbuf = ((size_t)F.p > (size_t)chunk) ? 2 : 1;
+    Block stage[2] = {{nullptr, 0}, {nullptr, 0}}, pin[2] = {{nullptr, 0}, {nullptr, 0}};
     int rc = BCFGPU_OK;
-    for (int c0 = 0; c0 < F.p && rc == BCFGPU_OK; c0 += chunk) {
-        const int nc = std::min(chunk, F.p - c0);
-        cudaError_t e = pre ? cudaSuccess : cudaMemcpyAsync(stage, x + (size_t)c0 * n, (size_t)nc * n * 8, cudaMemcpyHostToDevice, h->stream);
-        if (e != cudaSuccess) { rc = fail(BCFGPU_ERR_CUDA, std::string("H2D of X: ") + cudaGetErrorString(e)); break; }
-        h->h2d_bytes += (int64_t)nc * n * 8;
-        dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 4096), (unsigned)nc);
-        k_bin<<<grid, 256, 0, h->stream>>>(stage, n, nc, c0, F.d_cuts, F.d_off, F.d_col_index, F.d_is16, h->d_pos,
-                                            h->n_pad, F.d_bins8, F.d_bins16);
-        h->launches++;
-        e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail(BCFGPU_ERR_CUDA, std::string("k_bin: ") + cudaGetErrorString(e));
+    for (int b = 0; b < nbuf && rc == BCFGPU_OK; ++b) {
+        if (dev_alloc(h->device, stage_bytes, &stage[b]) != cudaSuccess) rc = fail(BCFGPU_ERR_OOM, "staging buffer of the binning kernel");
+        else if (!pinned && pin_alloc(stage_bytes, &pin[b]) != cudaSuccess) rc = fail(BCFGPU_ERR_OOM, "pinned staging buffer");
     }
-    if (!pre) cudaFree(stage);
+    cudaError_t e = cudaSuccess;
+    for (int c0 = 0, k = 0; c0 < F.p && rc == BCFGPU_OK && e == cudaSuccess; c0 += chunk, ++k) {
+        const int b = k & (nbuf - 1);
+        const int nc = std::min(chunk, F.p - c0);
+        const size_t bytes = (size_t)nc * colb;
+        const double* src = x + (size_t)c0 * n;
+        if (k >= nbuf) e = cudaStreamWaitEvent(h->copy_stream, h->ev_binned[b], 0);       // the staging buffer is free again
+        if (!pinned && e == cudaSuccess) {
+            if (k >= nbuf) e = cudaEventSynchronize(h->ev_copied[b]);                     // ... and so is the pinned one
+            char* dst = (char*)pin[b].p;
+            parallel_ranges((int64_t)bytes, 1 << 16, host_threads(), [&](int, int64_t lo, int64_t hi) { memcpy(dst + lo, (const char*)src + lo, (size_t)(hi - lo)); });
+            src = (const double*)pin[b].p;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(stage[b].p, src, bytes, cudaMemcpyHostToDevice, h->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied[b], h->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0);
+        if (e != cudaSuccess) break;
+        h->h2d_bytes += (int64_t)bytes;
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + BIN_ROWS - 1) / BIN_ROWS, 65535)), (unsigned)nc);
+        k_bin<<<grid, 256, 0, h->stream>>>((const double*)stage[b].p, n, nc, c0, F.d_cuts, F.d_off, F.d_col_index, F.d_is16, h->d_pos,
+                                            h->n_pad, (int)((int64_t)h->dev.trt_tiles * TILE), F.d_bins8, F.d_bins16);
+        h->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_binned[b], h->stream);
+    }
+    if (rc == BCFGPU_OK && e != cudaSuccess) rc = fail(BCFGPU_ERR_CUDA, std::string("H2D / binning of X: ") + cudaGetErrorString(e));
+    // the buffers go back to the cache only when nothing in flight uses them (and the caller's X may be freed on return)
+    cudaStreamSynchronize(h->copy_stream);
+    e = cudaStreamSynchronize(h->stream);
+    if (rc == BCFGPU_OK && e != cudaSuccess) rc = fail(BCFGPU_ERR_CUDA, std::string("k_bin: ") + cudaGetErrorString(e));
+    for (int b = 0; b < 2; ++b) { dev_free(h->device, stage[b]); pin_free(pin[b]); }
     return rc;
 }
 
@@ -452,11 +632,11 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     const bcfgpu_config& c = h->cfg;
     const bool sdprof = getenv("BCFGPU_SETDATA_PROFILE") != nullptr;
     auto sd_t0 = std::chrono::steady_clock::now();
-    auto sd_mark = [&](const char* what) {
+    auto sd_mark = [&](const char* what, bool sync = false) {
         if (!sdprof) return;
-        cudaStreamSynchronize(h->stream);
+        if (sync) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->stream); }
         const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[bcfgpu set_data] %-28s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - sd_t0).count());
+        fprintf(stderr, "[bcfgpu set_data] %-34s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - sd_t0).count());
         sd_t0 = now;
     };
     if (n < 1 || n > 2000000000ll) return fail(BCFGPU_ERR_BAD_ARG, "n must be in [1, 2e9]");
@@ -465,22 +645,52 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     if (c.ntree_mod > 0 && (p_mod < 1 || p_mod > 65535 || !xmod || !cuts_mod || !cut_off_mod))
         return fail(BCFGPU_ERR_BAD_ARG, "moderate forest needs x_moderate and its cutpoints");
     if (c.ntree_mod == 0) p_mod = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        if (z[i] != 0 && z[i] != 1) return fail(BCFGPU_ERR_BAD_ARG, "z must be 0/1");
-        if (!std::isfinite(y[i])) return fail(BCFGPU_ERR_BAD_ARG, "y must be finite");
-    }
-    sd_mark("argument checks");
+    // ---- one threaded pass over (y, z): validation, treated rows per chunk of PLACE_CHUNK rows (what the device needs
+    // to apply bcf's perm = order(z, decreasing = TRUE) itself), and ybar's order-independent fixed-point sum, so that any
+    // sharding starts from identical bits
+    const int64_t nchunk = (n + PLACE_CHUNK - 1) / PLACE_CHUNK;
+    std::vector<int32_t> chunk_trt((size_t)nchunk + 1, 0);
+    const int nth = n >= 65536 ? host_threads() : 1;
+    struct Part { long long s[4] = {0, 0, 0, 0}; int bad = 0; char pad_[28]; };
+    std::vector<Part> part((size_t)nth);
+    parallel_ranges(n, PLACE_CHUNK, nth, [&](int t, int64_t lo, int64_t hi) {
+        Part P;
+        for (int64_t c0 = lo; c0 < hi; c0 += PLACE_CHUNK) {
+            const int64_t c1 = std::min(hi, c0 + PLACE_CHUNK);
+            int32_t k = 0;
+            for (int64_t i = c0; i < c1; ++i) {
+                const int32_t zi = z[i];
+                const double yi = y[i];
+                if (zi != 0 && zi != 1) P.bad |= 1;
+                if (!(std::fabs(yi) < 32768.0)) { P.bad |= std::isfinite(yi) ? 4 : 2; continue; }
+                k += zi;
+                const long long v = std::llrint(yi * 17592186044416.0);
+                P.s[1] += v & 0x1FFFFF; P.s[2] += (v >> LIMB_BITS) & 0x1FFFFF; P.s[3] += v >> (2 * LIMB_BITS);
+            }
+            chunk_trt[(size_t)(c0 / PLACE_CHUNK) + 1] = k;
+        }
+        part[(size_t)t] = P;
+    });
+    long long ysum[5] = {(long long)n, 0, 0, 0, 0};   // count, limb0, limb1, limb2, treated count
+    int badbits = 0;
+    for (const Part& P : part) { badbits |= P.bad; ysum[1] += P.s[1]; ysum[2] += P.s[2]; ysum[3] += P.s[3]; }
+    if (badbits & 1) return fail(BCFGPU_ERR_BAD_ARG, "z must be 0/1");
+    if (badbits & 2) return fail(BCFGPU_ERR_BAD_ARG, "y must be finite");
+    if (badbits & 4) return fail(BCFGPU_ERR_BAD_ARG, "|y| too large: pass the standardised outcome");
+    for (int64_t k = 0; k < nchunk; ++k) chunk_trt[(size_t)k + 1] += chunk_trt[(size_t)k];     // exclusive prefix: treated rows before chunk k
+    const int64_t ntrt = chunk_trt[(size_t)nchunk];
+    ysum[4] = ntrt;
+    sd_mark("checks, counts, ybar (host threads)");
     CK(cudaStreamSynchronize(h->stream));
     drop_graph(h);
-    free_list(h->allocs);
-    free_list(h->run_allocs);
+    free_list(h, h->allocs);
+    free_list(h, h->run_allocs);
     h->has_data = false;
     h->h2d_bytes = 0;
     h->coop_grid = 0;
     h->shard_decided = false;
+    h->have_pos = false;
     h->n = n;
-    int64_t ntrt = 0;
-    for (int64_t i = 0; i < n; ++i) ntrt += z[i];
     const int64_t trt_pad = (ntrt + TILE - 1) / TILE * TILE;
     const int64_t ctl_pad = (n - ntrt + TILE - 1) / TILE * TILE;
     h->ntrt = (int)ntrt;
@@ -519,9 +729,23 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     DM(h, &d.counters, 4);
     DM(h, &h->d_bar, 64);
     DM(h, &h->d_done, 4);
+    int32_t* d_chunk = nullptr;
+    DM(h, &d_chunk, (size_t)nchunk + 1);
     if (getenv("BCFGPU_PROFILE")) { DM(h, &d.prof, 1024 + 512 * 8); CK(cudaMemsetAsync(d.prof, 0, (1024 + 512 * 8) * 8, h->stream)); }
     d.y = dy;
     sd_mark("device allocations");
+    // ---- y, z and the chunk counts cross first (12 B per row), then the device permutes: pos, orig, y in internal order
+    double* d_yraw = h->d_tmp;                         // scratch until the first fetch
+    int32_t* d_zraw = (int32_t*)h->d_tmp2;
+    CK(cudaMemcpyAsync(d_yraw, y, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_zraw, z, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_chunk, chunk_trt.data(), ((size_t)nchunk + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    h->h2d_bytes += (int64_t)n * 12 + (nchunk + 1) * 4;
+    CK(cudaMemsetAsync(h->d_orig, 0xFF, (size_t)n_pad * 4, h->stream));       // padding rows: orig = -1, y = 0
+    CK(cudaMemsetAsync(dy, 0, (size_t)n_pad * 8, h->stream));
+    k_place<<<(unsigned)nchunk, 256, 0, h->stream>>>(d_yraw, d_zraw, d_chunk, n, trt_pad, h->d_pos, h->d_orig, dy);
+    h->launches++;
+    CK(cudaGetLastError());
     CK(cudaMemsetAsync(d.totals, 0, (size_t)2 * h->T * KEYS * 8 * 8, h->stream));
     CK(cudaMemsetAsync(d.cross, 0, (size_t)2 * h->T * PIPE_XSTRIDE * 8, h->stream));
     CK(cudaMemsetAsync(d.mom, 0, 2 * 2 * NMOM * 3 * 8, h->stream));
@@ -540,38 +764,10 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     }
     if ((rc = setup_forest(h, 0, p_con, cuts_con, cut_off_con))) return rc;
     if ((rc = setup_forest(h, 1, p_mod, cuts_mod, cut_off_mod, shared_x ? &h->fh[0] : nullptr))) return rc;
-    sd_mark("allocations, clears, cutpoints");
-    // Every allocation is made: X_control starts crossing the bus now (async from pinned memory), UNDER the host-side
-    // work below (permutation, y, ybar: ~10 ms at n = 1e6); the small copies and the binning kernel queue behind it.
-    struct StageGuard { double* p = nullptr; ~StageGuard() { if (p) cudaFree(p); } } pre_stage;
-    if ((size_t)p_con * (size_t)n <= MAX_STAGE) {
-        CK(cudaMalloc((void**)&pre_stage.p, (size_t)p_con * n * 8));
-        CK(cudaMemcpyAsync(pre_stage.p, xcon, (size_t)p_con * n * 8, cudaMemcpyHostToDevice, h->stream));
-    }
-    // bcf: perm = order(z, decreasing = TRUE): treated rows first, ties in original order
-    h->pos.resize(n);
-    std::vector<int32_t> orig(n_pad, -1);
-    {
-        int64_t kt = 0, kc = trt_pad;
-        for (int64_t i = 0; i < n; ++i) { const int64_t q = z[i] ? kt++ : kc++; h->pos[i] = (int32_t)q; orig[q] = (int32_t)i; }
-    }
-    std::vector<double> yi((size_t)n_pad, 0.0);
-    for (int64_t i = 0; i < n; ++i) yi[h->pos[i]] = y[i];
-    // ybar from an order-independent fixed-point sum, so any sharding starts from identical bits
-    long long ysum[5] = {0, 0, 0, 0, (long long)ntrt};   // count, limb0, limb1, limb2, treated count
-    for (int64_t i = 0; i < n; ++i) {
-        if (!(std::fabs(y[i]) < 32768.0)) return fail(BCFGPU_ERR_BAD_ARG, "|y| too large: pass the standardised outcome");
-        const long long v = std::llrint(y[i] * 17592186044416.0);
-        ysum[0] += 1; ysum[1] += v & 0x1FFFFF; ysum[2] += (v >> LIMB_BITS) & 0x1FFFFF; ysum[3] += v >> (2 * LIMB_BITS);
-    }
-    sd_mark("permutation, y, ybar (host)");
-    CK(cudaMemcpyAsync(h->d_pos, h->pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_orig, orig.data(), (size_t)n_pad * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(dy, yi.data(), (size_t)n_pad * 8, cudaMemcpyHostToDevice, h->stream));
-    h->h2d_bytes += (int64_t)n_pad * 8 + (int64_t)n * 4 + (int64_t)n_pad * 4;   // y, pos, orig
-    if ((rc = bin_forest(h, 0, xcon, pre_stage.p))) return rc;
+    sd_mark("y, z, cutpoints queued");
+    if ((rc = bin_forest(h, 0, xcon))) return rc;
     if (!shared_x && (rc = bin_forest(h, 1, xmod))) return rc;
-    sd_mark("X: H2D + binning");
+    sd_mark("X: H2D + binning (overlapped)");
     fill_forest_dev(h, 0, d.f[0]);
     fill_forest_dev(h, 1, d.f[1]);
 
@@ -582,7 +778,6 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
         CK(cudaMemcpyAsync(ysum, dq, 40, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
-    sd_mark("ybar (host)");
     h->n_global = ysum[0];
     d.n_global = h->n_global;
     if (h->n_global > 2000000000ll) return fail(BCFGPU_ERR_BAD_ARG, "more than 2e9 observations over all shards");
@@ -591,12 +786,11 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
 
     // trees, scalars [SURVEY A.2]
     {
-        std::vector<TreeRec> trees((size_t)h->T);
         const double trt_init = 1.0;
-        for (int j = 0; j < h->T; ++j)
-            root_tree(trees[j], j < c.ntree_con ? ybar / c.ntree_con : trt_init / c.ntree_mod, ntrt_g, nctl_g);
-        CK(cudaMemcpyAsync(d.trees[0], trees.data(), sizeof(TreeRec) * h->T, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(d.trees[1], trees.data(), sizeof(TreeRec) * h->T, cudaMemcpyHostToDevice, h->stream));
+        k_init_trees<<<h->T, 256, 0, h->stream>>>(d.trees[0], d.trees[1], c.ntree_con, ybar / c.ntree_con,
+                                                  c.ntree_mod > 0 ? trt_init / c.ntree_mod : 0.0, ntrt_g, nctl_g);
+        h->launches++;
+        CK(cudaGetLastError());
         Scalars sc;
         memset(&sc, 0, sizeof(sc));
         sc.sigma = c.sigma_init; sc.mscale = 1.0; sc.bscale1 = 0.5; sc.bscale0 = -0.5;
@@ -616,6 +810,17 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     sd_mark("trees + initial state");
     h->has_data = true;
     h->nsaved = 0;
+    return BCFGPU_OK;
+}
+
+// the host copy of the row permutation (only the stand-alone operators need it)
+static int ensure_host_pos(bcfgpu_handle* h)
+{
+    if (h->have_pos) return BCFGPU_OK;
+    h->pos.resize((size_t)h->n);
+    CK(cudaMemcpyAsync(h->pos.data(), h->d_pos, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_pos = true;
     return BCFGPU_OK;
 }
 
@@ -691,7 +896,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
     Dev& d = h->dev;
     CK(cudaStreamSynchronize(h->stream));
     // posterior buffers of this run
-    free_list(h->run_allocs);
+    free_list(h, h->run_allocs);
     d.draws_tau = d.draws_mu = d.draws_yhat = nullptr;
     const int cap = std::max(nsim, 1);
     DM(h, &d.sigma_post, (size_t)cap, true); DM(h, &d.msd_post, (size_t)cap, true); DM(h, &d.bsd_post, (size_t)cap, true);
@@ -1211,6 +1416,7 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
     if (F.p == 0) return fail(BCFGPU_ERR_BAD_ARG, "forest has no covariates");
     const int64_t nbt = (int64_t)F.off[F.p] + F.p;
     // labels -> internal order, uint8, padding = 255
+    { int rcp = ensure_host_pos(h); if (rcp) return rcp; }
     std::vector<uint8_t> lab((size_t)h->n_pad, 255);
     for (int64_t i = 0; i < h->n; ++i) lab[h->pos[i]] = (slot[i] >= 0 && slot[i] < nleaf) ? (uint8_t)slot[i] : 255;
     uint8_t* dlab = nullptr; long long* dout = nullptr;

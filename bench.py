@@ -319,18 +319,27 @@ def run_ours(args):
     s.close()
 
     # ---- end-to-end leg through the C-ABI with host buffers ----
-    barrier()
-    e0 = time.perf_counter()
-    s2 = make_sampler()
-    set_data(s2)
-    s2.run(0, K)
-    tau = s2.tau_mean()
-    torch.cuda.synchronize()
-    e1 = time.perf_counter()
-    h2d = s2.h2d_bytes
+    # The call a user makes: create + set_data (H2D of y, z, X from pinned host memory, binning) + run(K) + colMeans(tau)
+    # back to the host.  Timed twice: `cold` right after the library's cached device blocks were released (every buffer
+    # comes from cudaMalloc), then again in the state every fit but a process's first one sees (bcf_iv() makes two fits
+    # per call, bcf(n_chains) many): blocks of the previous fit are reused.  `e2e.value` is the second; both are reported.
+    def e2e_once():
+        barrier()
+        a = time.perf_counter()
+        s2 = make_sampler()
+        set_data(s2)
+        s2.run(0, K)
+        tau_ = s2.tau_mean()
+        torch.cuda.synchronize()
+        b_ = time.perf_counter()
+        h2d_ = s2.h2d_bytes
+        s2.close()
+        return max_over_ranks(b_ - a), tau_, h2d_
+
+    _lib.release_cached_memory()
+    e2e_cold_s, _, _ = e2e_once()
+    e2e_s, tau, h2d = e2e_once()
     d2h = tau.nbytes
-    s2.close()
-    e2e_s = max_over_ranks(e1 - e0)
     e2e_val = units / e2e_s
     if not np.all(np.isfinite(tau)):
         raise SystemExit("bench.py: non-finite posterior mean")
@@ -365,8 +374,10 @@ def run_ours(args):
                      "launch_ms": launch_ms},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                 "call": "bcfgpu_create + set_data(pinned host y, z, X_control, X_moderate: H2D + binning) + "
-                        f"run({K} sweeps) + get_tau_mean (D2H), wall clock; bytes amortised over the {K} sweeps",
-                "seconds": e2e_s},
+                        f"run({K} sweeps) + get_tau_mean (D2H), wall clock; bytes amortised over the {K} sweeps; device "
+                        "blocks reused from the library's caching allocator (second fit of the process); `cold`: the same "
+                        "call with the cache emptied first (all buffers from cudaMalloc)",
+                "seconds": e2e_s, "cold": {"value": units / e2e_cold_s, "seconds": e2e_cold_s}},
         "gpu_launches": total_launches,
         "clocks": clocks.summary(t0, t1),
     }

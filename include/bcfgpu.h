@@ -98,6 +98,12 @@ BCFGPU_API const char *bcfgpu_last_error(void);
 BCFGPU_API void bcfgpu_config_init(bcfgpu_config *cfg);     /* bcf()'s defaults */
 BCFGPU_API int bcfgpu_create(const bcfgpu_config *cfg, bcfgpu_handle **out);
 BCFGPU_API int bcfgpu_destroy(bcfgpu_handle *h);
+/* The library parks the device (and pinned staging) blocks of destroyed handles, per device, and hands them to the next
+ * fit of the same shape: cudaMalloc / cudaFree of a fit's buffers cost 5 - 35 ms per call at n = 1e6 and bcf_iv() fits
+ * twice per call.  Bounded by BCFGPU_CACHE_MB per device (default 4096; 0 disables).  This empties the cache;
+ * cache_stats: out2 = {device bytes parked over all devices, pinned host bytes parked}. */
+BCFGPU_API int bcfgpu_release_cached_memory(void);
+BCFGPU_API int bcfgpu_cache_stats(int64_t out2[2]);
 
 /* ---- observation-sharded mode: call before set_data on every rank ------------------
  * nccl_unique_id: the 128 bytes of an ncclUniqueId made on rank 0 (bcfgpu_nccl_unique_id) and broadcast by

@@ -133,3 +133,62 @@ def test_philox_stream_matches_oracle():
         o = orc.rng_probe(*args)
         assert g[0] == o[0] and g[1] == o[1]                 # uniforms: integer arithmetic, bit-exact
         assert g[2] == pytest.approx(o[2], rel=1e-13, abs=1e-15)   # Box-Muller: device vs glibc log/cos
+
+
+@pytest.mark.parametrize("pattern", ["random", "treated_first", "control_first", "all_control", "all_treated", "blocks"])
+@pytest.mark.parametrize("pageable", [False, True])
+def test_set_data_permutation_and_binning_layouts(pattern, pageable, monkeypatch):
+    """set_data's device-side treated-first permutation (k_place) and the run-compacting binning kernel (k_bin), for the
+    z patterns that stress them: sorted either way (a block's treated and control runs touch), a single group, long
+    blocks; rows not a multiple of the 4096-row chunk / 2048-row block / 256-row tile; pinned-style direct copies and the
+    pageable path through the pinned staging buffers.  Checked through K1: the leaf of every row under a deep random
+    tree (it reads the binned columns at the permuted positions) against the oracle's walk over the raw doubles."""
+    if pageable:
+        monkeypatch.setenv("BCFGPU_FORCE_PAGEABLE", "1")
+    n = 2 * 4096 + 2048 + 300 + 7
+    pr = make_problem(n=n, p=9, seed=17, continuous=True)
+    rng = np.random.default_rng(3)
+    z = {"random": pr.P.z,
+         "treated_first": (np.arange(n) < n // 3).astype(np.int32),
+         "control_first": (np.arange(n) >= n // 3).astype(np.int32),
+         "all_control": np.zeros(n, np.int32), "all_treated": np.ones(n, np.int32),
+         "blocks": ((np.arange(n) // 1500) % 2).astype(np.int32)}[pattern]
+    P = pr.P
+    perm = np.argsort(-z, kind="stable")
+    inv = np.empty(n, np.int64); inv[perm] = np.arange(n)
+    from oracle import orc
+    o = orc.OracleSampler(P.yscale[perm], int(z.sum()), P.x_c[perm], P.x_m[perm], P.cuts_c, P.cuts_m, lambda_=P.lambda_,
+                          sigma_init=P.sigma_init, ntree_con=2, ntree_mod=1)
+    g = _lib.Sampler(lambda_=P.lambda_, sigma_init=P.sigma_init, ntree_con=2, ntree_mod=1)
+    g.set_data(P.yscale, z, P.x_c, P.x_m, pr.cuts_c_flat, pr.off_c, pr.cuts_m_flat, pr.off_m)
+    for tid, cuts in ((0, P.cuts_c), (2, P.cuts_m)):
+        heap, var, cut, mu = _random_tree(rng, [len(c) for c in cuts], 60)
+        g.set_tree(tid, heap, var, cut, mu)
+        o.set_tree(tid, heap, var, cut, mu)
+        assert np.array_equal(g.leaf_ids(tid), o.assign_leaves(tid)[inv])
+    assert g.verify_leaf_cache() == 0
+    # y went through the same permutation: the residual the sweeps start from is built on it
+    o.refit()
+    for _ in range(3):
+        g.run(1, 0)
+        o.sweeps(1)
+        assert np.array_equal(g.trace()[0], o.trace()[0])
+    assert abs(g.scalars()["sigma"] - o.scalars()["sigma"]) <= 1e-9 * o.scalars()["sigma"]
+    g.close(); o.close()
+
+
+def test_caching_allocator_reuses_blocks_and_releases_them():
+    """A second fit of the same shape takes its device blocks from the library's cache (no new cudaMalloc), and
+    bcfgpu_release_cached_memory hands everything back."""
+    pr = make_problem(n=3000, p=10, seed=2)
+    _lib.release_cached_memory()
+    s = gpu_sampler(pr); s.run(1, 0); s.close()
+    st0 = _lib.cache_stats()
+    assert st0["device_bytes"] > 0
+    s = gpu_sampler(pr); s.run(1, 0)
+    st1 = _lib.cache_stats()
+    assert st1["device_bytes"] < st0["device_bytes"]          # blocks were taken out of the cache
+    s.close()
+    assert _lib.cache_stats()["device_bytes"] >= st0["device_bytes"]
+    _lib.release_cached_memory()
+    assert _lib.cache_stats()["device_bytes"] == 0
