@@ -7,8 +7,11 @@
 A STEP is one Gibbs sweep: one birth/death + leaf-redraw update of every one of the 250 trees, the
 parameter-expansion scale draws and the sigma draw.  N > 1 (torchrun, one process per GPU)
 runs ONE INDEPENDENT CHAIN PER GPU on the replicated data with no data-path collective (SURVEY 8e "chains"):
-weak scaling, value = sweeps of all chains / max-over-ranks time.  `--mode sharded` instead shards the
-observations over the ranks with one NCCL all-reduce of the leaf statistics per tree.
+weak scaling, value = sweeps of all chains / max-over-ranks time.  The same run then ALSO measures the other way the
+path partitions (BASELINE config 5): ONE chain with the observations sharded over the N GPUs (n = 1e7, p = 200), the
+leaf statistics exchanged inside the sweep kernel over NVLink; it is attached to the JSON line as `"sharded": {...}`
+together with an in-line proof that the N-shard chain equals the 1-GPU chain bit for bit (`shard_parity`).
+`--mode sharded` makes the sharded chain (at --nobs / --ncov) the main line instead.
 
 Timed region of `value`: inputs binned and resident in HBM, chain burnt in (tree sizes stationary), W warm-up
 sweeps, then exactly K sweeps bracketed by barrier + synchronize, timed with CUDA events on the library's stream,
@@ -212,6 +215,125 @@ def workload_config(args, world, where):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Observation shards (BASELINE config 5): ONE chain over all ranks, every rank holds a contiguous row range,
+# the leaf statistics of a batch of trees are exchanged inside the sweep kernel through peer memory over NVLink.
+# ------------------------------------------------------------------------------------------------------------------
+def sharded_record(args, torch, dist, rank, local_rank, world, n, p, K, W, burnin, engine):
+    """Runs on every rank; rank 0 gets the record.  (1) bit-parity of the N-shard chain with the same chain on one GPU
+    at a small n; (2) sweeps/s of the N-shard chain at (n, p), device-timed, max over ranks; (3) the same rows per GPU
+    run WITHOUT the exchange (each rank an independent chain on its rows) -- the difference is what the exchange costs."""
+    from bcf_iv_b200 import _lib, multi, workload
+    dev = torch.device("cuda", local_rank)
+    T = T_CON + T_MOD
+
+    def maxr(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def shard_sampler(lam, sig0, seed):
+        s = _lib.Sampler(engine=engine, lambda_=lam, sigma_init=sig0, seed=seed, chain=0, device=local_rank)
+        s.set_shard(rank, world, multi.exchange_unique_id(_lib.nccl_unique_id))
+        return s
+
+    # ---- (1) parity: decisions, sigma and the posterior mean of tau bit for bit, shards vs one GPU ----
+    n_par, p_par, sweeps_par = args.shard_parity_n, 20, 12
+    wp = workload.synthetic_sampler_inputs(n_par, p_par, seed=args.data_seed + 1)
+    lo, hi = multi.shard_range(n_par, rank, world)
+    s = shard_sampler(wp["lambda_"], wp["sigma_init"], args.seed)
+    s.set_data(wp["y"][lo:hi], wp["z"][lo:hi], wp["x_con"][lo:hi], wp["x_mod"][lo:hi], wp["cuts_con"], wp["off_con"],
+               wp["cuts_mod"], wp["off_mod"])
+    s.run(0, sweeps_par)
+    tau_sh = multi.gather_rows(s.tau_mean())
+    tr_sh, lr_sh = s.trace()
+    sc_sh, cnt_sh, eng_par = s.scalars(), s.counters(), s.engine_in_use
+    s.close()
+    parity = None
+    if rank == 0:
+        s1 = _lib.Sampler(lambda_=wp["lambda_"], sigma_init=wp["sigma_init"], seed=args.seed, chain=0, device=local_rank)
+        s1.set_data(wp["y"], wp["z"], wp["x_con"], wp["x_mod"], wp["cuts_con"], wp["off_con"], wp["cuts_mod"], wp["off_mod"])
+        s1.run(0, sweeps_par)
+        tr1, lr1 = s1.trace()
+        sc1 = s1.scalars()
+        parity = {"n": n_par, "p": p_par, "sweeps": sweeps_par,
+                  "moves_identical": bool(np.array_equal(tr1, tr_sh)) and s1.counters() == cnt_sh,
+                  "log_ratios_identical": bool(np.array_equal(lr1, lr_sh, equal_nan=True)),
+                  "scalars_identical": all(sc1[k] == sc_sh[k] for k in ("sigma", "mscale", "bscale1", "bscale0", "tau_con")),
+                  "tau_mean_identical": bool(np.array_equal(s1.tau_mean(), tau_sh)),
+                  "exchange": {0: "none", 1: "ncclAllReduce per tree", 2: "in-kernel peer-memory mailboxes (NVLink)"}[eng_par[1]]}
+        s1.close()
+    # ---- (2) the timed shape ----
+    def gather_sum(v):
+        parts = [None] * world
+        dist.all_gather_object(parts, np.asarray(v))
+        return np.sum(parts, axis=0)                          # same order on every rank: identical bits
+    lo, hi = multi.shard_range(n, rank, world)
+    t0 = time.perf_counter()
+    w = workload.synthetic_shard_inputs(n, p, lo, hi, seed=args.data_seed, allreduce=gather_sum)
+    gen_s = time.perf_counter() - t0
+    s = shard_sampler(w["lambda_"], w["sigma_init"], args.seed)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s.set_data(w["y"], w["z"], w["x_con"], w["x_mod"], w["cuts_con"], w["off_con"], w["cuts_mod"], w["off_mod"])
+    set_s = maxr(time.perf_counter() - t0)
+    s.run(burnin, 0)
+    s.run(W, 0)
+    l0 = s.kernel_launches
+    dist.barrier(); torch.cuda.synchronize()
+    s.run(0, K)
+    torch.cuda.synchronize()
+    ms = maxr(s.last_run_ms)
+    launches = s.kernel_launches - l0
+    in_use = s.engine_in_use
+    sizes = [len(s.get_tree(t)[0]) for t in range(0, T, 5)]
+    sig = s.scalars()["sigma"]
+    s.close()
+    # ---- (3) the same rows per GPU without the exchange ----
+    s = _lib.Sampler(engine=engine, lambda_=w["lambda_"], sigma_init=w["sigma_init"], seed=args.seed, chain=1 + rank, device=local_rank)
+    s.set_data(w["y"], w["z"], w["x_con"], w["x_mod"], w["cuts_con"], w["off_con"], w["cuts_mod"], w["off_mod"])
+    s.run(burnin, 0)
+    s.run(W, 0)
+    dist.barrier(); torch.cuda.synchronize()
+    s.run(0, K)
+    ms_local = maxr(s.last_run_ms)
+    eng_local = s.engine_in_use
+    s.close()
+    _lib.release_cached_memory()
+    if rank != 0:
+        return None
+    value = K / (ms * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    b_sweep = algorithmic_bytes_per_sweep(n, T)
+    achieved = b_sweep * value / 1e9
+    names = {0: "graph", 1: "persistent_hbm", 2: "persistent", 3: "batched", 4: "pipelined", 5: "batched_hbm"}
+    kern = {"pipelined": "k_pipe", "batched": "k_batched<resident>", "batched_hbm": "k_batched<hbm>", "persistent": "k_resident",
+            "persistent_hbm": "k_persistent", "graph": "k_tree_step x T + ncclAllReduce per tree"}
+    exch = {0: "none", 1: "ncclAllReduce per tree", 2: "in-kernel peer-memory mailboxes (NVLink)"}[in_use[1]]
+    ok = bool(parity and parity["moves_identical"] and parity["log_ratios_identical"] and parity["scalars_identical"]
+              and parity["tau_mean_identical"])
+    return {
+        "workload": f"ONE chain, observations sharded over {world} GPUs: n_s={n} rows in all ({hi - lo} per GPU), p={p} binary "
+                    f"covariates + pihat, {T_CON} mu + {T_MOD} tau trees (BASELINE.json config 5 shape)",
+        "n": n, "p": p, "n_gpus": world, "rows_per_gpu": hi - lo, "value": value, "unit": UNIT, "ms_per_step": ms / K,
+        "steps": K, "warmup": W, "burnin_sweeps": burnin, "scaling": "strong",
+        "engine": names[in_use[0]], "kernel": kern[names[in_use[0]]], "shard_exchange": exch,
+        "exchange_detail": "per batch of trees: every rank stores its reduced leaf statistics and cross counts (<= 6 KB of "
+                           "int64 words) into its mailbox on every peer over NVLink, releases a sequence number, and "
+                           "waits for the peers'; one more exchange per sweep for the scale / sigma moments",
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                     "algorithmic_bytes_per_sweep": b_sweep, "peak_source": peak_src + f" x {world} GPUs"},
+        "same_rows_without_exchange": {"value": K / (ms_local * 1e-3), "ms_per_step": ms_local / K, "engine": names[eng_local[0]],
+                                       "note": "each GPU an independent chain on its own rows: what the shard costs per "
+                                               "sweep with no exchange; the difference to ms_per_step is the exchange "
+                                               "(stores + wait for the slowest rank)"},
+        "exchange_ms_per_step": ms / K - ms_local / K,
+        "shard_parity": ok, "parity": parity,
+        "gpu_launches": int(launches), "mean_nodes_per_tree": float(np.mean(sizes)), "sigma": sig,
+        "set_data_s": set_s, "data_generation_s": gen_s,
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -344,12 +466,17 @@ def run_ours(args):
     if not np.all(np.isfinite(tau)):
         raise SystemExit("bench.py: non-finite posterior mean")
 
+    shard_rec = None
+    if world > 1 and not sharded and not args.no_sharded:
+        host.clear(); keep.clear()                  # the pinned copies of the chains legs (0.8 GB per rank)
+        shard_rec = sharded_record(args, torch, dist, rank, local_rank, world, args.shard_n, args.shard_p,
+                                   min(K, args.shard_steps), min(W, 5), args.burnin, engine)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    n_local = host["y"].shape[0]
+    n_local = n if not sharded else (hi - lo)
     b_sweep = algorithmic_bytes_per_sweep(n_local, T)
     peak, peak_src = measured_peak_gbs()
     sweeps_per_launch = K / max(launches, 1)
@@ -381,6 +508,8 @@ def run_ours(args):
         "gpu_launches": total_launches,
         "clocks": clocks.summary(t0, t1),
     }
+    if shard_rec is not None:
+        line["sharded"] = shard_rec
     if world == 1 and not args.no_cpu_baseline:
         from oracle import orc
         orc.build()
@@ -414,6 +543,11 @@ def main():
     ap.add_argument("--cpu-sweeps", type=int, default=8)
     ap.add_argument("--cpu-budget", type=float, default=120.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the observation-sharded record")
+    ap.add_argument("--shard-n", type=int, default=10_000_000, help="rows of the observation-sharded record (config 5)")
+    ap.add_argument("--shard-p", type=int, default=200)
+    ap.add_argument("--shard-steps", type=int, default=50)
+    ap.add_argument("--shard-parity-n", type=int, default=60_000)
     args = ap.parse_args()
     if args.steps < 1 or args.warmup < 0:
         raise SystemExit("need --steps >= 1 and --warmup >= 0")
