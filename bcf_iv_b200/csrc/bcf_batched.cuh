@@ -1079,9 +1079,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, uns
                     for (int p = 0; p < d.pr.nranks; ++p)
                         if (p != d.pr.rank) d.pr.peer[p][d.pr.rank].mom[i] = v;
                 }
-                peer_release(d, 2, d.pr.seq0 + mev);
+                peer_release(d, MAIL_FLAG_MOM, d.pr.seq0 + mev);
             }
-            if (!peer_wait(d, 2, d.pr.seq0 + mev, &bar_ok)) return;
+            if (!peer_wait(d, MAIL_FLAG_MOM, d.pr.seq0 + mev, &bar_ok)) return;
             for (int i = t; i < MAIL_MOM_WORDS; i += blockDim.x) {
                 long long v = __ldcg(&mom[i]);
                 for (int p = 0; p < d.pr.nranks; ++p)

@@ -109,16 +109,26 @@ struct ForestDev {
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_RANKS = 8;
 constexpr int MAIL_TOT_WORDS = KEYS * 8;            // totals words of a batch (a big tree: KEYS * 8; 8 small trees: 512)
-constexpr int MAIL_X_WORDS = 256;                   // cross-count words of a batch
+constexpr int MAIL_X_WORDS = 512;                   // cross-count words of a batch (batched engine: 256; pipelined: 2 * 216)
 constexpr int MAIL_MOM_WORDS = 2 * NMOM * 3;
+constexpr int MAIL_SLOTS = 4;                       // batch slots of the pipelined engine (the batched engine alternates between
+                                                    // two): its statistics pass runs up to two batches ahead of the decisions,
+                                                    // so a rank may push batch b + 3 while a peer still reads batch b
+constexpr int MAIL_FLAG_MOM = MAIL_SLOTS;           // flag index of the moments exchange
+constexpr int MAIL_LL_WORDS = 4 * 8 * 8 + 2 * 216;  // a batch of the pipelined engine: PNB * KB * 8 totals words + 2 * PXCAP cross counts
 struct __align__(16) Mailbox {
-    unsigned long long flag[4];                     // [0], [1]: batch slots, [2]: moments -- sequence number of the last complete push
+    unsigned long long flag[MAIL_SLOTS + 4];        // [0..1]: batch slots of the batched engine, [4]: moments -- sequence number of the last complete push
     long long batch[2][MAIL_TOT_WORDS + MAIL_X_WORDS];
     long long mom[MAIL_MOM_WORDS + 4];
+    // Pipelined engine: self-validating words, (value << 16) | tag -- a 48-bit value and the low 16 bits of the batch's
+    // global number in ONE 8-byte store (single-copy atomic), so a push needs no fence and no flag and a reader that
+    // sees the tag it expects has the value: one NVLink crossing per batch instead of store + fence + flag + poll.
+    unsigned long long ll[MAIL_SLOTS][MAIL_LL_WORDS];
 };
 struct PeerDev {
     int32_t rank, nranks;
     unsigned long long seq0;                        // launch id << 32: sequence numbers never repeat across launches
+    unsigned long long batch0;                      // batches of the pipelined engine exchanged before this launch (tags and slots go on)
     Mailbox* mine;                                  // [nranks] my mailboxes, indexed by SOURCE rank (local HBM)
     Mailbox* peer[MAX_RANKS];                       // peer[p]: rank p's mailbox array, mapped here (cudaIpc)
 };

@@ -50,11 +50,9 @@ constexpr int H1_THREADS = 32 + PR_THREADS;          // tile warp 0 arrives, cha
 constexpr int PT_THREADS = PT_WARPS * 32;
 constexpr int H2_THREADS = PT_THREADS + PR_THREADS;  // chain warps arrive, tile warps wait
 
-struct __align__(16) TMeta {                         // what the pass needs to know about a tree, per sweep
-    const void* bins;                                // column of the proposed variable
+struct __align__(8) TMeta {                          // what the pass needs to know about a tree, per sweep (8 bytes: the
+    uint16_t var, cut;                               // column pointer of the proposed variable is formed by the utility warp)
     uint8_t K, L, birth, sx;
-    uint16_t cut;
-    uint8_t is16, pad_;
 };
 
 struct PipePlan {
@@ -99,7 +97,7 @@ struct PipeSmem {
     PreKey pre[PNB * (KB + 1)];
     PipeConsts cons[2];                               // per forest, per sweep
     union { PipeAcc acc[2]; StatTabT<32> tab; double red[2 * PIPE_THREADS]; } p;
-    alignas(16) uint8_t colb[PP_WARPS][2 * PMAXC][32];   // read 16 bytes at a time
+    alignas(16) uint8_t colb[PT_WARPS][2 * PMAXC][32];   // per tile warp; read 16 bytes at a time
 };
 constexpr size_t PIPE_SMEM_BYTES = (sizeof(PipeSmem) + 15) / 16 * 16;
 
@@ -149,7 +147,7 @@ __device__ inline void pipe_plan(PipePlan& P, const PipePlan* prev, const Dev& d
         const int fend = f ? d.T : (d.f[1].ntree > 0 ? d.f[1].tree0 : d.T);
         const int ncand = min(PNB, fend - first);
         TMeta m;
-        m.K = 1; m.L = 1; m.birth = 0; m.sx = 0; m.cut = 0; m.is16 = 0; m.pad_ = 0; m.bins = nullptr;
+        m.K = 1; m.L = 1; m.birth = 0; m.sx = 0; m.cut = 0; m.var = 0;
         if (l < ncand) m = meta[first + l];
         const int c = (l < ncand) ? (int)m.K - 1 : 0;            // own columns
         int cb = c;                                                 // inclusive prefix of the columns
@@ -180,7 +178,9 @@ __device__ inline void pipe_plan(PipePlan& P, const PipePlan* prev, const Dev& d
             P.Kp[l] = (l < np) ? prev->K[l] : 1;
             P.colbasep[l] = (l < np) ? prev->colbase[l] : 0;
             CurInfo& ci = P.ci[l];
-            ci.active = 1; ci.K = m.K; ci.birth = m.birth; ci.sx = m.sx; ci.cut = m.cut; ci.bins = m.bins; ci.is16 = m.is16;
+            int is16 = 0;
+            const void* bins = (l < ncand && m.birth) ? bin_column(d.f[f], (int)m.var, d.n_pad, is16) : nullptr;
+            ci.active = 1; ci.K = m.K; ci.birth = m.birth; ci.sx = m.sx; ci.cut = m.cut; ci.bins = bins; ci.is16 = is16;
             ci.forest = f; ci.new_slot = m.L;
         }
         if (l == 0) {
@@ -431,9 +431,52 @@ __device__ inline void pipe_stage_trees(SmallStage* st, const Dev& d, const Tree
     __syncwarp();
 }
 
+// ---- observation shards (see PeerDev, Mailbox::ll): the exchange of a batch's reduced words ----
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// index of word i of the batch's message: totals words of the trees' live keys first (i < nb * KB * 8), then the cross counts
+__device__ __forceinline__ bool pipe_word_live(const PipePlan& P, int i)
+{
+    return i >= P.nb * KB * 8 || ((i >> 3) & (KB - 1)) < P.K[i / (KB * 8)];
+}
+// ONE warp (the utility warp of the first CTAs: CTA c serves the c-th peer), after this rank's grid barrier of the batch: this
+// rank's reduced words, tagged with the batch's global number g, go into its mailbox on that peer (posted stores over NVLink).
+__device__ inline void pipe_peer_push(const PipePlan& P, const Dev& d, const long long* totals, const long long* cross, int peer,
+                                      unsigned long long g, int lane)
+{
+    const int nt = P.nb * KB * 8, nx = 2 * P.ncell;
+    unsigned long long* dst = d.pr.peer[peer][d.pr.rank].ll[g & (MAIL_SLOTS - 1)];
+    const unsigned long long tag = g & 0xFFFFull;
+    for (int i0 = 0; i0 < nt + nx; i0 += 32 * 4) {
+        long long v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                                 // loads first: one L2 round trip per 128 words
+            const int i = i0 + u * 32 + lane;
+            v[u] = 0;
+            if (i < nt) { if (pipe_word_live(P, i)) v[u] = __ldcg(&totals[(size_t)(P.first + i / (KB * 8)) * KEYS * 8 + (i & (KB * 8 - 1))]); }
+            else if (i < nt + nx) v[u] = __ldcg(&cross[(size_t)P.first * PIPE_XSTRIDE + (i - nt)]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            if (i < nt + nx && pipe_word_live(P, i)) st_relaxed_sys_u64(dst + i, ((unsigned long long)v[u] << 16) | tag);
+        }
+    }
+}
+
 // everything of a batch's decisions (resolve role, PR_THREADS threads; rt = thread within the role)
+// gtag != 0: observation shards -- the batch's global number: the peers' words (Mailbox::ll) are added to this rank's
 __device__ inline void pipe_resolve(PipeSmem& sm, SmallStage* st, const PipePlan& P, int b, const Dev& d, const Scalars& sc,
-                                    TreeRec* newtrees, const long long* totals, const long long* cross, int rt, long long* trc = nullptr)
+                                    TreeRec* newtrees, const long long* totals, const long long* cross, int rt,
+                                    unsigned long long gtag, long long* trc = nullptr)
 {
     const int nb = P.nb;
     PipeRS& rs = sm.rs;
@@ -459,6 +502,38 @@ __device__ inline void pipe_resolve(PipeSmem& sm, SmallStage* st, const PipePlan
         for (int it = 0; it < NX_IT; ++it) {
             const int i = rt + it * PR_THREADS;
             xv[it] = i < nx ? __ldcg(xg + i) : 0ll;
+        }
+        if (gtag != 0ull) {   // observation shards: add the peers' words (integers: any order gives the same bits)
+            const unsigned long long tag = gtag & 0xFFFFull;
+            const long long t0 = clock64();
+            for (int p = 0; p < d.pr.nranks; ++p) {
+                if (p == d.pr.rank) continue;
+                const unsigned long long* mb = d.pr.mine[p].ll[gtag & (MAIL_SLOTS - 1)];
+                unsigned long long pv[NT_IT + NX_IT];
+                bool need[NT_IT + NX_IT];
+#pragma unroll
+                for (int it = 0; it < NT_IT + NX_IT; ++it) {
+                    const int i = it < NT_IT ? rt + it * PR_THREADS : nb * KB * 8 + rt + (it - NT_IT) * PR_THREADS;
+                    need[it] = it < NT_IT ? (i < nb * KB * 8 && pipe_word_live(P, i)) : (i - nb * KB * 8 < nx);
+                    pv[it] = 0ull;
+                }
+                for (bool all = false; !all;) {        // every word carries its batch's tag: poll until each has arrived
+                    all = true;
+#pragma unroll
+                    for (int it = 0; it < NT_IT + NX_IT; ++it) {
+                        const int i = it < NT_IT ? rt + it * PR_THREADS : nb * KB * 8 + rt + (it - NT_IT) * PR_THREADS;
+                        if (need[it]) pv[it] = ld_relaxed_sys_u64(mb + i);
+                    }
+#pragma unroll
+                    for (int it = 0; it < NT_IT + NX_IT; ++it)
+                        if (need[it]) { if ((pv[it] & 0xFFFFull) == tag) need[it] = false; else all = false; }
+                    if (!all && clock64() - t0 > 120000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); __trap(); }
+                }
+#pragma unroll
+                for (int it = 0; it < NT_IT; ++it) tv[it] += (long long)pv[it] >> 16;       // (words not needed stayed 0)
+#pragma unroll
+                for (int it = 0; it < NX_IT; ++it) xv[it] += (long long)pv[NT_IT + it] >> 16;
+            }
         }
 #pragma unroll
         for (int it = 0; it < NT_IT; ++it) {
@@ -581,6 +656,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
     // (it only waits for b-1's decisions), so consecutive batches must not share a counter; it cannot reach b+2
     // before b has completed, so two counters are enough.
     unsigned int target = 0, tbatch[2] = {0u, 0u};
+    unsigned long long gbatch = d.pr.batch0, mev = 0;   // observation shards: global batch number (tags, slots) / moment exchanges of this launch
+    unsigned int ubatch[2] = {0u, 0u};                  // the utility warp's own count of the batch barriers ...
+    unsigned long long ugbatch = d.pr.batch0;           // ... and of the global batch number
+    const bool sharded = d.pr.nranks > 1;
     int bad = 0;
     PipePtrs rs;
     rs.R = (uint32_t)__cvta_generic_to_shared(dyn);
@@ -634,8 +713,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
             const int L = __ldcg(&tr->nleaves), mv = __ldcg(&P->move);
             TMeta m;
             m.L = (uint8_t)L; m.birth = mv == 1; m.K = (uint8_t)min(255, L + (mv == 1 ? 1 : 0));
-            m.sx = (uint8_t)__ldcg(&P->slot); m.cut = (uint16_t)__ldcg(&P->cut); m.is16 = (uint8_t)__ldcg(&P->is16); m.pad_ = 0;
-            m.bins = (const void*)__ldcg(reinterpret_cast<const unsigned long long*>(&P->bins));
+            m.sx = (uint8_t)__ldcg(&P->slot); m.cut = (uint16_t)__ldcg(&P->cut); m.var = (uint16_t)__ldcg(&P->var);
             meta[j] = m;
             if (m.K > KB || L > KB) sm.anybig = 1;
         }
@@ -714,6 +792,22 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                     for (int i = lane; i < (int)(2 * sizeof(PipeAcc) / 4); i += 32) tb[i] = 0u;
                 }
                 int pfirst = 0, pb = 0;
+                // CTA c (c < nranks - 1) pushes to the c-th peer of this rank
+                const bool pusher = sharded && (int)blockIdx.x < d.pr.nranks - 1;
+                const int push_peer = (int)blockIdx.x < d.pr.rank ? (int)blockIdx.x : (int)blockIdx.x + 1;
+                auto push_batch = [&](int ub) {
+                    ubatch[ub & 1] += gridDim.x;
+                    ++ugbatch;
+                    if (lane == 0) {
+                        const long long t0 = clock64();
+                        while (ld_acquire_u32(bar + (ub & 1)) < ubatch[ub & 1]) {
+                            __nanosleep(100);
+                            if (clock64() - t0 > 8000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); __trap(); }
+                        }
+                    }
+                    __syncwarp();
+                    pipe_peer_push(sm.plan[ub & 3], d, totals, cross, push_peer, ugbatch, lane);
+                };
                 [[maybe_unused]] long long up = BCF_PROF_CLOCK();
                 [[maybe_unused]] const bool uprof = d.prof != nullptr && lane == 0;
 #ifndef BCF_PROF
@@ -723,8 +817,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
 #endif
                 while (pfirst < T) {
                     if (pb >= 2) {
-                        if (lane == 0) pipe_wait_flag(&sm.flushed, pb - 1, d.err, 200);
+                        if (lane == 0) pipe_wait_flag(&sm.flushed, pb - 1, d.err, pusher ? 40 : 200);
                         __syncwarp();
+                        // observation shards: batch pb - 2 is flushed by this CTA; once every CTA of this rank has flushed
+                        // it, its reduced words go to the peer this CTA serves -- first thing, before the planning: the
+                        // peers' chain warps are about to look for them
+                        if (pusher) push_batch(pb - 2);
                     }
                     UPROF(0);
                     PipePlan& NP = sm.plan[pb & 3];
@@ -736,6 +834,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                     if (lane == 0) st_release_cta_s32(&sm.plan_ready, pb + 1);
                     pfirst += NP.nb; ++pb;
                 }
+                if (pusher)
+                    for (int ub = max(pb - 2, 0); ub < pb; ++ub) {               // the sweep's last two batches
+                        if (lane == 0) pipe_wait_flag(&sm.flushed, ub + 1, d.err, 40);
+                        __syncwarp();
+                        push_batch(ub);
+                    }
 #undef UPROF
             }
             asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_REGS_BASE));
@@ -767,6 +871,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                 QPROF(4); PTRACE(5);
                 const PipePlan& P = sm.plan[b & 3];
                 tbatch[b & 1] += gridDim.x;
+                ++gbatch;                                                        // global number of the batch (observation shards: tag and slot)
                 if (rt == 0) {
                     const long long t0 = clock64();
                     while (ld_acquire_u32(bar + (b & 1)) < tbatch[b & 1]) {
@@ -776,7 +881,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                 }
                 named_sync(BAR_RES, PR_THREADS);
                 QPROF(6); PTRACE(6);
-                pipe_resolve(sm, sm.st[b & 3], P, b, d, sc, d.trees[par ^ 1], totals, cross, rt,
+                pipe_resolve(sm, sm.st[b & 3], P, b, d, sc, d.trees[par ^ 1], totals, cross, rt, sharded ? gbatch : 0ull,
                              (d.prof != nullptr && blockIdx.x == 0 && sw == 0 && b >= 8 && b < 16) ? d.prof + 16 + 512 + (b - 8) * 32 : nullptr);
                 named_arrive(BAR_H2 + (b & 1), H2_THREADS);                      // H2(b)
                 QPROF(7); PTRACE(7);
@@ -828,7 +933,28 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
         EPROF(6);
         if (!grid_all_wait()) return;
         EPROF(4);
-        sweep_scalars(d, d.trees[par ^ 1], mom, sm.p.red, &scs, writer0);
+        if (sharded) {   // the sweep's moments, summed over the shards (as in k_batched)
+            ++mev;
+            if (blockIdx.x == 0) {
+                for (int i = t; i < MAIL_MOM_WORDS; i += PIPE_THREADS) {
+                    const long long v = __ldcg(&mom[i]);
+                    for (int p = 0; p < d.pr.nranks; ++p)
+                        if (p != d.pr.rank) d.pr.peer[p][d.pr.rank].mom[i] = v;
+                }
+                peer_release(d, MAIL_FLAG_MOM, d.pr.seq0 + mev);
+            }
+            if (!peer_wait(d, MAIL_FLAG_MOM, d.pr.seq0 + mev, &bar_ok)) return;
+            long long* momsum = &sm.rs.tot[0][0][0][0];      // (the resolve staging is idle between the role sections)
+            for (int i = t; i < MAIL_MOM_WORDS; i += PIPE_THREADS) {
+                long long v = __ldcg(&mom[i]);
+                for (int p = 0; p < d.pr.nranks; ++p)
+                    if (p != d.pr.rank) v += __ldcg(&d.pr.mine[p].mom[i]);
+                momsum[i] = v;
+            }
+            __syncthreads();
+            sweep_scalars(d, d.trees[par ^ 1], momsum, sm.p.red, &scs, writer0, true);
+        } else
+            sweep_scalars(d, d.trees[par ^ 1], mom, sm.p.red, &scs, writer0);
         EPROF(5);
         grid_all();   // proposals visible before the next sweep reads them (wait: below)
         // ---- finishing pass ----
@@ -891,7 +1017,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
             st8_f64(d.Gc + gb, G);
             st8_i64(d.rfx + gb, R);
         }
-    if (writer0 && t == 0) *done_out = done;
+    if (writer0 && t == 0) done_out[0] = done;
+    if (writer0 && !is_pass && rt == 0) done_out[1] = (int)(gbatch - d.pr.batch0);   // batches exchanged (observation shards: tags go on)
     if (bad) atomicOr(d.err, ERR_FX_RANGE);
     if (t == 0 && sm.bad) atomicOr(d.err, sm.bad);
 }

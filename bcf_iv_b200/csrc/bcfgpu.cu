@@ -103,6 +103,7 @@ struct bcfgpu_handle {
     Mailbox* peer_mail[MAX_RANKS] = {nullptr};   // the peers' mailbox arrays, mapped with cudaIpc
     bool peer_ok = false;             // every rank mapped every peer: the sweep kernel exchanges through NVLink itself
     unsigned long long launch_id = 0;
+    unsigned long long pipe_batches = 0;   // batches the pipelined kernel has exchanged with the peers so far (tags of Mailbox::ll)
     bool shard_decided = false, shard_persistent = false;
     int last_kernel = 0;
     int64_t n = 0, n_pad = 0, n_global = 0;
@@ -924,12 +925,16 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
         // take the same path (the shards differ by a row, so "does it fit in shared memory" is agreed on, not assumed)
         if (!h->shard_decided) {
             if ((rc = select_kernel(h))) return rc;
-            long long ok = (h->kernel == 3 || h->kernel == 5) ? 1 : 0;
+            // level 2: the pipelined kernel (batches of 4, four mailbox slots); level 1: the batched kernel (batches of 8,
+            // two slots; its shared-memory and HBM variants speak the same protocol); 0: neither.  Every rank runs the
+            // lowest level any rank has.
+            long long ok = h->kernel == 4 ? 2 : (h->kernel == 3 || h->kernel == 5) ? 1 : 0;
             long long* dq = (long long*)h->d_tmp;
             CK(cudaMemcpyAsync(dq, &ok, 8, cudaMemcpyHostToDevice, h->stream));
             NK(g_nccl.AllReduce(dq, dq, 1, NCCL_INT64, NCCL_MIN, h->comm, h->stream));
             CK(cudaMemcpyAsync(&ok, dq, 8, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
+            if (ok == 1 && h->kernel == 4) h->kernel = h->fallback_kernel;     // a peer's shard does not fit the pipelined kernel
             h->shard_persistent = ok != 0;
             h->shard_decided = true;
             if (!h->shard_persistent) d.pr.nranks = 1;
@@ -1591,7 +1596,7 @@ static int select_kernel(bcfgpu_handle* h)
                 }
             }
             // the pipelined kernel on top of it (the batched one then serves the sweeps that hold a wide tree)
-            if ((h->kernel == 3 || h->kernel == 5) && may_reside && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && h->nranks == 1) {
+            if ((h->kernel == 3 || h->kernel == 5) && may_reside && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && (h->nranks == 1 || h->peer_ok)) {
                 h->fallback_kernel = h->kernel;
                 const size_t needp = PIPE_SMEM_BYTES + (size_t)ntl_max * PIPE_BYTES_PER_TILE + (size_t)h->T * sizeof(TMeta) + 16;
                 if (fits((const void*)k_pipe, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; h->pipe_ntl = ntl_max; }
@@ -1636,17 +1641,21 @@ static int run_persistent(bcfgpu_handle* h, int total)
             // pipelined kernel; it returns early at a sweep that holds a tree wider than KB keys: that one sweep is
             // run by the batched kernel, then the pipelined one resumes
             int* dn = h->d_done;
-            CK(cudaMemsetAsync(dn, 0, 4, h->stream));
+            CK(cudaMemsetAsync(dn, 0, 8, h->stream));
+            d.pr.batch0 = h->pipe_batches;
             int pntl = h->pipe_ntl;
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&pntl, (void*)&dn};
             CK(cudaLaunchCooperativeKernel((const void*)k_pipe, dim3(h->coop_grid), dim3(PIPE_THREADS), args, h->pipe_smem, h->stream));
             h->launches++;
-            int ndone = 0;
-            CK(cudaMemcpyAsync(&ndone, dn, 4, cudaMemcpyDeviceToHost, h->stream));
+            int dn_host[2] = {0, 0};
+            CK(cudaMemcpyAsync(dn_host, dn, 8, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
+            const int ndone = dn_host[0];
+            h->pipe_batches += (unsigned long long)dn_host[1];
             done += ndone;
             if (ndone < nsw) {
                 int one = 1;
+                d.pr.seq0 = (++h->launch_id) << 32;                  // (its own launch: the mailbox sequence numbers restart)
                 CK(cudaMemsetAsync(bar, 0, 16, h->stream));
                 void* a2[] = {(void*)&d, (void*)&one, (void*)&bar, (void*)&ntl};
                 CK(cudaLaunchCooperativeKernel(h->fallback_kernel == 3 ? (const void*)k_batched<true> : (const void*)k_batched<false>, dim3(h->coop_grid),
