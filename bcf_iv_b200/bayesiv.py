@@ -257,9 +257,12 @@ def _node_rows(nodes, where, names, inf_y, inf_w, inf_z, inf_X):
 
 
 def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5, max_depth=2, cp=0.01, minsplit=10,
-           adj_method="holm", seed=42, **bcf_args):
+           adj_method="holm", seed=42, bcf_fn=None, details=None, **bcf_args):
     """Discovery and estimation of heterogeneity in the complier average causal effect (R/bcf_iv.R:47).
-    Returns a pandas DataFrame with the reference's columns (COLUMNS), one row per CART node."""
+    Returns a pandas DataFrame with the reference's columns (COLUMNS), one row per CART node.
+    `bcf_fn`: the fitting function (default: bcf_iv_b200.bcf.bcf, the GPU sampler) -- the parity tests pass a twin that
+    drives the CPU oracle through the identical pipeline.  `details`: a dict that receives the intermediate estimands
+    (discovery rows, pic, itt, tauhat, the CART's split variables)."""
     import pandas as pd
     y, w, z = (np.asarray(a, dtype=np.float64).ravel() for a in (y, w, z))
     if binary and not np.all((y == 0) | (y == 1)):
@@ -277,14 +280,18 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     from concurrent.futures import ThreadPoolExecutor
     if "max_ctas" not in fit_args and len(disc) <= 27 * 256 * (_bcf._lib.B200_SMS // 2) - 512:
         fit_args["max_ctas"] = _bcf._lib.B200_SMS // 2
+    fit = bcf_fn or _bcf.bcf
     with ThreadPoolExecutor(max_workers=2) as pool:
         # the reference's two samplers are independent (bartc / bcf): the complier-proportion fit gets its own Philox
         # stream (chain 1 of the seed), so itt and pic do not share their Monte Carlo noise
-        f_pic = pool.submit(_bcf.bcf, w[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, first_chain=1))   # P(complier | x)
-        f_itt = pool.submit(_bcf.bcf, y[disc], z[disc], Xd, Xd, pihat, **fit_args)          # R/bcf_iv.R:89-91
+        f_pic = pool.submit(fit, w[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, first_chain=1))   # P(complier | x)
+        f_itt = pool.submit(fit, y[disc], z[disc], Xd, Xd, pihat, **fit_args)               # R/bcf_iv.R:89-91
         pic, itt = f_pic.result()["tau_mean"], f_itt.result()["tau_mean"]
     tauhat = itt / pic                                                                      # R/bcf_iv.R:94
     nodes, where = cart(Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
+    if details is not None:
+        details.update(disc=disc, index=index, pic=pic, itt=itt, tauhat=tauhat,
+                       split_vars=sorted({nd.var for nd in nodes.values() if nd.var is not None}))
     ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
     leaves = {nid for nid in ids if nodes[nid].left is None}
     # rows are indexed by rpart NODE NUMBER as in the reference (bcfivMat[i, ], R/bcf_iv.R:174): the table starts with

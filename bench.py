@@ -130,6 +130,30 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process (and so the first touch of its pinned buffers and the library's host threads) to the CPUs next to
+    its GPU: with one rank per GPU on a two-socket box the host-to-device copies otherwise cross the socket link.
+    Best effort: returns the cpulist used or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpulist
+    except Exception:
+        return None
+
+
 def pinned_like(a):
     """copy of a numpy array in pinned host memory (what the e2e leg hands to the C-ABI), keeping Fortran order"""
     import torch
@@ -347,6 +371,7 @@ def run_ours(args):
     if _lib.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (libbcfgpu has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -492,7 +517,7 @@ def run_ours(args):
         "config": dict(workload_config(args, world, "B200"), engine=eng_name, shard_exchange=exchange, burnin_sweeps=args.burnin,
                        l2="no flush: per-sweep working set (250 MB leaf-slot cache + 101 MB bins + 40 MB state) "
                           "exceeds the 126 MB L2",
-                       mean_nodes_per_tree=float(np.mean(sizes)), sigma=sig, moves=acc,
+                       mean_nodes_per_tree=float(np.mean(sizes)), sigma=sig, moves=acc, cpu_binding=numa_cpus,
                        wall_ms_per_step=wall_ms / K),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic_sweep * sweeps_per_launch if traffic_sweep is not None else None),

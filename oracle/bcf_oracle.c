@@ -325,6 +325,66 @@ static void allsuff(orc_sampler *s, node *t, const nvec *bots, const double *x, 
 
 static double pgrow_at_depth(double alpha, double beta, int depth) { return alpha / pow(1.0 + (double)depth, beta); }
 
+/* Structural part of the MH ratio (alpha1) of a BIRTH at leaf nx with rule (v, c) [bcf-recall, SURVEY A.3 step 2]:
+ * PGnx (1-PGly)(1-PGry) PDy Pnogy / ((1-PGnx) PBx Pbotx). */
+static double birth_alpha1(const orc_sampler *s, node *t, node *nx, int v, int c, const xinfo *xi, double alpha, double beta)
+{
+    nvec bots = {0}, good = {0}, nogs = {0};
+    tree_bots(t, &bots);
+    for (int b = 0; b < bots.n; ++b) if (cansplit(bots.a[b], xi)) nvec_push(&good, bots.a[b]);
+    tree_nogs(t, &nogs);
+    const int single = (t->l == NULL);
+    const double PBx = single ? 1.0 : 0.5;          /* a birth is only proposed when some leaf can split */
+    const int ngv = goodvars(nx, xi, NULL);
+    int lo, hi; node_rg(nx, v, xi, &lo, &hi);
+    const int dnx = node_depth(nx);
+    const double PGnx = pgrow_at_depth(alpha, beta, dnx);
+    double PGly, PGry;
+    const int y_capped = (s->cfg.max_leaves > 0 && bots.n + 1 >= s->cfg.max_leaves);
+    const int child_depth_ok = (dnx + 1 < ORC_MAX_DEPTH) && !y_capped;
+    if (!child_depth_ok) { PGly = PGry = 0.0; }
+    else if (ngv > 1) { PGly = PGry = pgrow_at_depth(alpha, beta, dnx + 1); }
+    else {
+        PGly = (c - 1 < lo) ? 0.0 : pgrow_at_depth(alpha, beta, dnx + 1);
+        PGry = (hi < c + 1) ? 0.0 : pgrow_at_depth(alpha, beta, dnx + 1);
+    }
+    double PDy;
+    if (y_capped) PDy = 1.0;
+    else if (good.n > 1) PDy = 0.5;
+    else PDy = (PGly == 0.0 && PGry == 0.0) ? 1.0 : 0.5;
+    double Pnogy;
+    if (!nx->p) Pnogy = 1.0;
+    else Pnogy = node_is_nog(nx->p) ? 1.0 / nogs.n : 1.0 / (nogs.n + 1.0);
+    const double Pbotx = 1.0 / good.n;
+    free(bots.a); free(good.a); free(nogs.a);
+    return (PGnx * (1.0 - PGly) * (1.0 - PGry) * PDy * Pnogy) / ((1.0 - PGnx) * PBx * Pbotx);
+}
+/* ... and of the DEATH of nog node nx: (1-PGny) PBy Pboty / (PGny (1-PGlx)(1-PGrx) PDx Pnogx). */
+static double death_alpha1(const orc_sampler *s, node *t, node *nx, const xinfo *xi, double alpha, double beta)
+{
+    nvec bots = {0}, good = {0}, nogs = {0};
+    tree_bots(t, &bots);
+    for (int b = 0; b < bots.n; ++b) if (cansplit(bots.a[b], xi)) nvec_push(&good, bots.a[b]);
+    tree_nogs(t, &nogs);
+    const int capped = (s->cfg.max_leaves > 0 && bots.n >= s->cfg.max_leaves);
+    const int ngood_x = capped ? 0 : good.n;
+    const double PBx = (ngood_x == 0) ? 0.0 : 0.5;  /* the tree has a nog node, so it is not a single leaf */
+    const int dny = node_depth(nx);
+    const double PGny = pgrow_at_depth(alpha, beta, dny);
+    /* pgrow of the two children as they stand in the current tree */
+    const int rl = cansplit(nx->l, xi), rr = cansplit(nx->r, xi);
+    const double PGlx = (rl && !capped) ? pgrow_at_depth(alpha, beta, dny + 1) : 0.0;
+    const double PGrx = (rr && !capped) ? pgrow_at_depth(alpha, beta, dny + 1) : 0.0;
+    const double PBy = nx->p ? 0.5 : 1.0;
+    /* goodbots of the proposed tree: lose the children, gain nx (it splits on v, so v is usable there) */
+    const int ngood = good.n - rl - rr + 1;
+    const double Pboty = 1.0 / ngood;
+    const double PDx = 1.0 - PBx;
+    const double Pnogx = 1.0 / nogs.n;
+    free(bots.a); free(good.a); free(nogs.a);
+    return ((1.0 - PGny) * PBy * Pboty) / (PGny * (1.0 - PGlx) * (1.0 - PGrx) * PDx * Pnogx);
+}
+
 /* One birth/death Metropolis-Hastings step on tree *tp (bcf's bd/bdhet) [bcf-recall, SURVEY A.3 step 2] */
 static void bd(orc_sampler *s, node **tp, uint32_t tree_id, const double *x, int p, const xinfo *xi,
                double alpha, double beta, double tau, const double *phi, const double *R)
@@ -361,26 +421,7 @@ static void bd(orc_sampler *s, node **tp, uint32_t tree_id, const double *x, int
         rng_u2(&s->rng, s->sweep, tree_id, PUR_CUT, 0, &ua, &ub);
         int c = lo + (int)floor(ua * (hi - lo + 1)); if (c > hi) c = hi;
 
-        const int dnx = node_depth(nx);
-        const double PGnx = pgrow_at_depth(alpha, beta, dnx);
-        double PGly, PGry;
-        const int y_capped = (s->cfg.max_leaves > 0 && bots.n + 1 >= s->cfg.max_leaves);
-        const int child_depth_ok = (dnx + 1 < ORC_MAX_DEPTH) && !y_capped;
-        if (!child_depth_ok) { PGly = PGry = 0.0; }
-        else if (ngv > 1) { PGly = PGry = pgrow_at_depth(alpha, beta, dnx + 1); }
-        else {
-            PGly = (c - 1 < lo) ? 0.0 : pgrow_at_depth(alpha, beta, dnx + 1);
-            PGry = (hi < c + 1) ? 0.0 : pgrow_at_depth(alpha, beta, dnx + 1);
-        }
-        double PDy;
-        if (y_capped) PDy = 1.0;
-        else if (good.n > 1) PDy = 0.5;
-        else PDy = (PGly == 0.0 && PGry == 0.0) ? 1.0 : 0.5;
-        tree_nogs(t, &nogs);
-        double Pnogy;
-        if (!nx->p) Pnogy = 1.0;
-        else Pnogy = node_is_nog(nx->p) ? 1.0 / nogs.n : 1.0 / (nogs.n + 1.0);
-        const double Pbotx = 1.0 / good.n;
+        const double alpha1 = birth_alpha1(s, t, nx, v, c, xi, alpha, beta);
 
         sinfo sl, sr;
         getsuff_birth(s, t, nx, v, c, x, p, xi, phi, R, &sl, &sr);
@@ -389,7 +430,6 @@ static void bd(orc_sampler *s, node **tp, uint32_t tree_id, const double *x, int
         if (sl.n0 >= s->cfg.min_leaf && sr.n0 >= s->cfg.min_leaf) {
             const double lill = lil(sl.n, sl.sy, tau), lilr = lil(sr.n, sr.sy, tau);
             const double lilt = lil(sl.n + sr.n, sl.sy + sr.sy, tau);
-            const double alpha1 = (PGnx * (1.0 - PGly) * (1.0 - PGry) * PDy * Pnogy) / ((1.0 - PGnx) * PBx * Pbotx);
             const double logr = log(alpha1) + (lill + lilr - lilt);
             s->trace_logr[tree_id] = logr;
             const double a = logr >= 0 ? 1.0 : exp(logr);
@@ -406,25 +446,13 @@ static void bd(orc_sampler *s, node **tp, uint32_t tree_id, const double *x, int
         rng_u2(&s->rng, s->sweep, tree_id, PUR_NODE, 0, &ua, &ub);
         int ni = (int)floor(ua * nogs.n); if (ni >= nogs.n) ni = nogs.n - 1;
         node *nx = nogs.a[ni];
-        const int dny = node_depth(nx);
-        const double PGny = pgrow_at_depth(alpha, beta, dny);
-        /* pgrow of the two children as they stand in the current tree */
-        const int rl = cansplit(nx->l, xi), rr = cansplit(nx->r, xi);
-        const double PGlx = (rl && !capped) ? pgrow_at_depth(alpha, beta, dny + 1) : 0.0;
-        const double PGrx = (rr && !capped) ? pgrow_at_depth(alpha, beta, dny + 1) : 0.0;
-        const double PBy = nx->p ? 0.5 : 1.0;
-        /* goodbots of the proposed tree: lose the children, gain nx (it splits on v, so v is usable there) */
-        const int ngood = good.n - rl - rr + 1;
-        const double Pboty = 1.0 / ngood;
-        const double PDx = 1.0 - PBx;
-        const double Pnogx = 1.0 / nogs.n;
+        const double alpha1 = death_alpha1(s, t, nx, xi, alpha, beta);
         sinfo sl, sr;
         getsuff_death(s, t, nx->l, nx->r, x, p, xi, phi, R, &sl, &sr);
         s->n_death_prop++;
         tr[0] = 2; tr[2] = (int32_t)node_heap_id(nx); tr[3] = nx->v; tr[4] = nx->c;
         const double lill = lil(sl.n, sl.sy, tau), lilr = lil(sr.n, sr.sy, tau);
         const double lilt = lil(sl.n + sr.n, sl.sy + sr.sy, tau);
-        const double alpha1 = ((1.0 - PGny) * PBy * Pboty) / (PGny * (1.0 - PGlx) * (1.0 - PGrx) * PDx * Pnogx);
         const double logr = log(alpha1) + (lilt - lill - lilr);
         s->trace_logr[tree_id] = logr;
         const double a = logr >= 0 ? 1.0 : exp(logr);
@@ -778,6 +806,48 @@ ORC_API int orc_getsuff_birth(orc_sampler *s, int tree_id, uint32_t leaf_heap, i
     return 0;
 }
 ORC_API double orc_lil(double sum_phi, double sum_phi_r, double tau) { return lil(sum_phi, sum_phi_r, tau); }
+
+/* log MH ratio of a NAMED move on the tree as it stands, for caller-supplied weights phi and partial residual R
+ * (tests: reversibility, birth o death = 1).  move 1: birth at the leaf with heap id `heap` under rule (v, c);
+ * move 2: death of the nog node `heap`.  out2 = {log alpha1 (structure), log likelihood ratio}.  Returns 0, or -1 when the
+ * node does not exist / is not a leaf (birth) / not a nog (death). */
+static node *find_heap(node *n, uint32_t id, uint32_t heap)
+{
+    if (!n) return NULL;
+    if (id == heap) return n;
+    node *f = find_heap(n->l, 2 * id, heap);
+    return f ? f : find_heap(n->r, 2 * id + 1, heap);
+}
+ORC_API int orc_mh_logratio(orc_sampler *s, int tree_id, int move, uint32_t heap, int v, int c, const double *phi,
+                            const double *R, double out2[2])
+{
+    const int con = tree_id < s->cfg.ntree_con;
+    const double *x = con ? s->xc : s->xm; const int p = con ? s->p_con : s->p_mod;
+    const xinfo *xi = con ? &s->xi_c : &s->xi_m;
+    const double alpha = con ? s->cfg.alpha_con : s->cfg.alpha_mod, beta = con ? s->cfg.beta_con : s->cfg.beta_mod;
+    const double tau = con ? s->tau_con : s->tau_mod;
+    node *t = get_tree(s, tree_id);
+    node *nx = find_heap(t, 1u, heap);
+    if (!nx) return -1;
+    sinfo sl, sr;
+    const int keep = s->cfg.nthreads; s->cfg.nthreads = 1;
+    if (move == 1) {
+        if (nx->l) { s->cfg.nthreads = keep; return -1; }
+        getsuff_birth(s, t, nx, v, c, x, p, xi, phi, R, &sl, &sr);
+        out2[0] = log(birth_alpha1(s, t, nx, v, c, xi, alpha, beta));
+        out2[1] = lil(sl.n, sl.sy, tau) + lil(sr.n, sr.sy, tau) - lil(sl.n + sr.n, sl.sy + sr.sy, tau);
+    } else {
+        if (!node_is_nog(nx)) { s->cfg.nthreads = keep; return -1; }
+        getsuff_death(s, t, nx->l, nx->r, x, p, xi, phi, R, &sl, &sr);
+        out2[0] = log(death_alpha1(s, t, nx, xi, alpha, beta));
+        out2[1] = lil(sl.n + sr.n, sl.sy + sr.sy, tau) - lil(sl.n, sl.sy, tau) - lil(sr.n, sr.sy, tau);
+    }
+    s->cfg.nthreads = keep;
+    return 0;
+}
+/* replace the outcome vector (joint-distribution tests redraw y given the parameters); the fits are untouched */
+ORC_API void orc_set_y(orc_sampler *s, const double *y) { memcpy(s->y, y, sizeof(double) * (size_t)s->n); }
+ORC_API void orc_get_allfit(const orc_sampler *s, double *allfit) { memcpy(allfit, s->allfit, sizeof(double) * (size_t)s->n); }
 
 /* homoskedastic lil of BART/bcf 1.x (n, sum y, sum y^2, sigma, tau), for the lil == lilhet identity test */
 ORC_API double orc_lil_homosked(double n, double sy, double sy2, double sigma, double tau)

@@ -74,6 +74,10 @@ def lib():
         L.orc_allsuff.argtypes = [C.c_void_p, C.c_int, dp, dp, up, dp, dp, dp]
         L.orc_getsuff_birth.restype = C.c_int
         L.orc_getsuff_birth.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_int, dp, dp, dp]
+        L.orc_mh_logratio.restype = C.c_int
+        L.orc_mh_logratio.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, dp, dp, dp]
+        L.orc_set_y.argtypes = [C.c_void_p, dp]
+        L.orc_get_allfit.argtypes = [C.c_void_p, dp]
         L.orc_lil.restype = C.c_double
         L.orc_lil.argtypes = [C.c_double] * 3
         L.orc_lil_homosked.restype = C.c_double
@@ -236,6 +240,25 @@ class OracleSampler:
         rc = lib().orc_getsuff_birth(self.h, tid, int(leaf_heap), int(v), int(c), _dp(phi), _dp(R), _dp(o))
         if rc != 0:
             raise ValueError("no such leaf")
+        return o
+
+    def mh_logratio(self, tid, move, heap, v, c, phi, R):
+        """(log alpha1, log likelihood ratio) of a named move on the tree as it stands: move 1 = birth at leaf `heap`
+        under rule (v, c), move 2 = death of nog node `heap`"""
+        o = np.zeros(2)
+        phi = np.ascontiguousarray(phi, dtype=np.float64); R = np.ascontiguousarray(R, dtype=np.float64)
+        if lib().orc_mh_logratio(self.h, tid, int(move), int(heap), int(v), int(c), _dp(phi), _dp(R), _dp(o)) != 0:
+            raise ValueError("no such move")
+        return o
+
+    def set_y(self, y):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        assert y.size == self.n
+        lib().orc_set_y(self.h, _dp(y))
+
+    def allfit(self):
+        o = np.zeros(self.n)
+        lib().orc_get_allfit(self.h, _dp(o))
         return o
 
     def hist_all(self, forest, slot, nleaf, r):

@@ -46,3 +46,55 @@ def gpu_sampler(pr, **kw):
 def tree_signature(heap, var, cut):
     """structure of a serialised tree as a sorted tuple (order-free)"""
     return tuple(sorted((int(h), int(v), int(c)) for h, v, c in zip(heap, var, cut)))
+
+
+def random_tree(rng, ncut, nleaves, max_depth=12, with_ranges=False):
+    """random full binary tree as (heap, var, cut, mu) with valid (var, cut) given ancestors (bcf's rg rule);
+    with_ranges: also the usable cutpoint range {var: (lo, hi)} of every leaf (variables not listed: all cutpoints)"""
+    p = len(ncut)
+    leaves = {1: {}}          # heap id -> {var: (lo, hi)}
+    internal = {}
+    while len(leaves) < nleaves:
+        cand = [h for h in leaves if h.bit_length() - 1 < max_depth]
+        if not cand:
+            break
+        h = cand[rng.integers(len(cand))]
+        rngs = leaves[h]
+        ok = [v for v in range(p) if rngs.get(v, (0, ncut[v] - 1))[1] >= rngs.get(v, (0, ncut[v] - 1))[0]]
+        if not ok:
+            break
+        v = ok[rng.integers(len(ok))]
+        lo, hi = rngs.get(v, (0, ncut[v] - 1))
+        c = int(rng.integers(lo, hi + 1))
+        del leaves[h]
+        internal[h] = (v, c)
+        l = dict(rngs); l[v] = (lo, c - 1)
+        r = dict(rngs); r[v] = (c + 1, hi)
+        leaves[2 * h] = l
+        leaves[2 * h + 1] = r
+    heap, var, cut, mu = [], [], [], []
+    for h, (v, c) in internal.items():
+        heap.append(h); var.append(v); cut.append(c); mu.append(0.0)
+    for h in leaves:
+        heap.append(h); var.append(-1); cut.append(-1); mu.append(float(rng.standard_normal()))
+    out = (np.array(heap, np.uint32), np.array(var, np.int32), np.array(cut, np.int32), np.array(mu))
+    return out + (leaves,) if with_ranges else out
+
+
+def oracle_bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nthin=1, random_seed=None,
+               first_chain=0, keep_draws=False, max_leaves=0, nthreads=1, **ignored):
+    """bcf() with the CPU ORACLE as the sampler: the same R-side preamble (prep.prepare), the same Philox stream
+    (seed, chain), the same outputs as bcf_iv_b200.bcf.bcf -- the oracle-driven twin of the end-to-end parity tests."""
+    from oracle import orc
+    if x_moderate is None:
+        x_moderate = x_control
+    P = prep.prepare(y, z, x_control, x_moderate, pihat)
+    perm = P.perm
+    o = orc.OracleSampler(P.yscale[perm], P.ntrt, P.x_c[perm], P.x_m[perm], P.cuts_c, P.cuts_m, lambda_=P.lambda_,
+                          sigma_init=P.sigma_init, con_sd=P.con_sd, mod_sd=P.mod_sd, seed=int(random_seed),
+                          chain=int(first_chain), max_leaves=max_leaves, nthreads=nthreads)
+    out = o.run(int(nburn), int(nsim), int(nthin))
+    o.close()
+    inv = P.inv_perm
+    return {"tau_mean": P.sdy * out["tau_mean"][inv], "mu_mean": P.muy + P.sdy * out["mu_mean"][inv],
+            "yhat_mean": P.muy + P.sdy * out["yhat_mean"][inv], "sigma": P.sdy * out["sigma"]}

@@ -12,35 +12,7 @@ from helpers import gpu_sampler, make_problem, oracle_sampler
 pytestmark = pytest.mark.gpu
 
 
-def _random_tree(rng, ncut, nleaves, max_depth=12):
-    """random full binary tree as (heap, var, cut, mu) with valid (var, cut) given ancestors (bcf's rg rule)"""
-    p = len(ncut)
-    leaves = {1: {}}          # heap id -> {var: (lo, hi)}
-    internal = {}
-    while len(leaves) < nleaves:
-        cand = [h for h in leaves if h.bit_length() - 1 < max_depth]
-        if not cand:
-            break
-        h = cand[rng.integers(len(cand))]
-        rngs = leaves[h]
-        ok = [v for v in range(p) if rngs.get(v, (0, ncut[v] - 1))[1] >= rngs.get(v, (0, ncut[v] - 1))[0]]
-        if not ok:
-            break
-        v = ok[rng.integers(len(ok))]
-        lo, hi = rngs.get(v, (0, ncut[v] - 1))
-        c = int(rng.integers(lo, hi + 1))
-        del leaves[h]
-        internal[h] = (v, c)
-        l = dict(rngs); l[v] = (lo, c - 1)
-        r = dict(rngs); r[v] = (c + 1, hi)
-        leaves[2 * h] = l
-        leaves[2 * h + 1] = r
-    heap, var, cut, mu = [], [], [], []
-    for h, (v, c) in internal.items():
-        heap.append(h); var.append(v); cut.append(c); mu.append(0.0)
-    for h in leaves:
-        heap.append(h); var.append(-1); cut.append(-1); mu.append(float(rng.standard_normal()))
-    return np.array(heap, np.uint32), np.array(var, np.int32), np.array(cut, np.int32), np.array(mu)
+from helpers import random_tree as _random_tree  # noqa: E402
 
 
 def test_k0_bins_match_definition():
