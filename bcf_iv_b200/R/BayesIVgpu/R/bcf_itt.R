@@ -5,16 +5,16 @@
 #' @export
 bcf_itt <- function(y, w, z, x, binary = FALSE, max_depth = 2, n_burn = 500, n_sim = 500, inference_ratio = 0.5,
                     seed = 42) {
-  # binary = TRUE: the reference fits the ITT with bartCause::bartc (probit BART) here; this build fits it with the same
-  # GPU sampler on the 0/1 outcome (its tau is the ITT on the probability scale, as for the complier proportion)
+  # binary = TRUE: the reference fits the ITT with bartCause::bartc (probit BART, R/bcf_itt.R:166-170): bartc_ite()
   if (binary && !all(y %in% c(0, 1))) stop("binary = TRUE needs a 0/1 outcome")
   x <- as.matrix(x)
   index <- .honest_split(nrow(x), inference_ratio, seed)
   inference <- data.frame(y = y, w = w, z = z, x)[index, ]
   xd <- x[-index, , drop = FALSE]
   pihat <- .logit_pihat(z[-index], xd)
-  tauhat <- bcf(y[-index], z[-index], xd, xd, pihat, nburn = n_burn, nsim = n_sim, random_seed = seed,
-                keep_draws = FALSE)$tau_mean
+  tauhat <- if (binary) bartc_ite(y[-index], z[-index], xd, n.samples = n_sim, n.burn = n_burn, n.chains = 2L, seed = seed)
+            else bcf(y[-index], z[-index], xd, xd, pihat, nburn = n_burn, nsim = n_sim, random_seed = seed,
+                     keep_draws = FALSE)$tau_mean
   tree <- rpart::rpart(tauhat ~ ., data = data.frame(tauhat = tauhat, xd), maxdepth = max_depth)
   for (i in as.numeric(row.names(tree$frame))) {
     rule <- if (i == 1) NULL else .node_rule(tree, i)

@@ -2,13 +2,13 @@
 #'
 #' Drop-in for BayesIV::bcf_iv (reference R/bcf_iv.R:47): same arguments, same returned data.frame
 #' (node, CCACE, pvalue, Weak_IV_test, Pi_obs, ITT, Pi_compliers, Adj_pvalue; one row per rpart node number).
-#' The ITT forest is fitted by bcf() of this package, i.e. on the GPU; the complier-proportion forest too
-#' (the reference uses bartCause::bartc for it), everything else is unchanged CPU code.
+#' The ITT forest is fitted by bcf() of this package and the complier proportion (and, with binary = TRUE, the ITT) by
+#' bartc_ite() -- both on the GPU; everything else is unchanged CPU code.
 #' @export
 bcf_iv <- function(y, w, z, x, binary = FALSE, n_burn = 500, n_sim = 500, inference_ratio = 0.5, max_depth = 2,
                    cp = 0.01, minsplit = 10, adj_method = "holm", seed = 42) {
-  # binary = TRUE: the reference fits the ITT with bartCause::bartc (probit BART) here; this build fits it with the same
-  # GPU sampler on the 0/1 outcome (its tau is the ITT on the probability scale, as for the complier proportion)
+  # the reference's second sampler, bartCause::bartc (probit BART S-learner), is bartc_ite() of this package: the complier
+  # proportion of every call (R/bcf_iv.R:78-80) and, with binary = TRUE, the ITT itself (R/bcf_iv.R:198-202)
   if (binary && !all(y %in% c(0, 1))) stop("binary = TRUE needs a 0/1 outcome")
   x <- as.matrix(x)
   index <- .honest_split(nrow(x), inference_ratio, seed)
@@ -17,12 +17,13 @@ bcf_iv <- function(y, w, z, x, binary = FALSE, n_burn = 500, n_sim = 500, infere
   xd <- x[-index, , drop = FALSE]
   pihat <- .logit_pihat(z[-index], xd)
 
-  # the two fits are independent samplers in the reference (bartc for pic, bcf for the ITT): distinct Philox streams
-  # (chain 1 / chain 0 of the same seed), so that the Monte Carlo noise of itt and pic is not shared
+  # the fits are independent samplers, as in the reference (bartc for pic, bcf for the ITT): each has its own Philox
+  # streams, so the Monte Carlo noise of itt and pic is not shared
   fit <- function(outcome, chain) bcf(outcome, z[-index], xd, xd, pihat, nburn = n_burn, nsim = n_sim,
                                       random_seed = seed, keep_draws = FALSE, first_chain = chain)$tau_mean
-  pic <- fit(w[-index], 1L)                   # posterior mean share of compliers given x
-  itt <- fit(y[-index], 0L)                   # posterior mean intention-to-treat effect given x  (the hot path)
+  pic <- bartc_ite(w[-index], z[-index], xd, n.samples = n_sim, n.burn = n_burn, n.chains = 2L, seed = seed)
+  itt <- if (binary) bartc_ite(y[-index], z[-index], xd, n.samples = n_sim, n.burn = n_burn, n.chains = 2L, seed = seed + 1L)
+         else fit(y[-index], 0L)              # posterior mean intention-to-treat effect given x  (the hot path, R/bcf_iv.R:89)
   tauhat <- itt / pic
 
   tree <- rpart::rpart(tauhat ~ ., data = data.frame(tauhat = tauhat, xd), maxdepth = max_depth, cp = cp,

@@ -142,6 +142,9 @@ SEXP bcfgpu_R_fit_chains(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off
     cfg.chain = (uint32_t)num(cfg_list, "chain", 0);
     cfg.device = (int32_t)num(cfg_list, "device", -1);
     cfg.max_ctas = (int32_t)num(cfg_list, "max_ctas", 0);
+    cfg.model = (int32_t)num(cfg_list, "model", BCFGPU_MODEL_BCF);            /* 1: probit BART (R/bartc.R) */
+    cfg.treatment_col = (int32_t)num(cfg_list, "treatment_col", -1);
+    cfg.probit_offset = num(cfg_list, "probit_offset", 0.0);
     cfg.keep_draws = keep ? 7 : 0;
 
     bcfgpu_handle **hs = (bcfgpu_handle **)calloc((size_t)nch, sizeof(bcfgpu_handle *));

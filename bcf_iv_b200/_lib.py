@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "libbcfgpu.so")
 MAX_LEAVES = 128
 STATUS = {0: "OK", 1: "BAD_ARG", 2: "CUDA", 3: "NCCL", 4: "NUMERIC", 5: "OOM", 6: "STATE", 7: "INTERRUPTED"}
 ENGINE_AUTO, ENGINE_GRAPH, ENGINE_PERSISTENT, ENGINE_PERSISTENT_HBM, ENGINE_BATCHED, ENGINE_PIPELINED = 0, 1, 2, 3, 4, 5
+MODEL_BCF, MODEL_PROBIT_BART = 0, 1
 
 # every symbol include/bcfgpu.h declares (tests check the library exports each of them)
 SYMBOLS = [
@@ -27,7 +28,7 @@ SYMBOLS = [
     "bcfgpu_get_mu_mean", "bcfgpu_get_yhat_mean", "bcfgpu_get_sigma", "bcfgpu_get_scales", "bcfgpu_get_draws",
     "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
     "bcfgpu_get_tree", "bcfgpu_set_tree", "bcfgpu_get_leaf_ids", "bcfgpu_verify_leaf_cache", "bcfgpu_op_bin_column",
-    "bcfgpu_op_suffstats", "bcfgpu_op_hist_all", "bcfgpu_op_lil", "bcfgpu_op_rng_probe",
+    "bcfgpu_op_suffstats", "bcfgpu_op_hist_all", "bcfgpu_op_lil", "bcfgpu_op_rng_probe", "bcfgpu_op_probit_latent",
 ]
 
 
@@ -48,7 +49,8 @@ class Config(C.Structure):
         ("sigma_init", C.c_double), ("use_muscale", C.c_int32), ("use_tauscale", C.c_int32),
         ("min_leaf", C.c_int32), ("max_leaves", C.c_int32), ("seed", C.c_uint64), ("chain", C.c_uint32),
         ("device", C.c_int32), ("engine", C.c_int32), ("keep_draws", C.c_int32), ("max_ctas", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("model", C.c_int32), ("treatment_col", C.c_int32), ("reserved0", C.c_int32), ("probit_offset", C.c_double),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -109,6 +111,7 @@ def load():
     L.bcfgpu_op_hist_all.argtypes = [vp, C.c_int32, ip, C.c_int32, dp, lp, dp, dp]
     L.bcfgpu_op_lil.argtypes = [dp, dp, dp, C.c_int32, dp]
     L.bcfgpu_op_rng_probe.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp]
+    L.bcfgpu_op_probit_latent.argtypes = [dp, ip, dp, C.c_int32, dp]
     for nm in SYMBOLS:
         f = getattr(L, nm)
         if nm not in ("bcfgpu_last_error", "bcfgpu_config_init"):
@@ -428,3 +431,10 @@ def fit_chains(cfg_kw, n_chains, devices, y, z, x_con, x_mod, cuts_con, off_con,
         ck.chain = c.chain + k
         out.append(Sampler._adopt(hs[k], ck, n, oc, om, xc.shape[1], p_mod))
     return out
+
+
+def op_probit_latent(m, y, u):
+    m = np.ascontiguousarray(m, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.int32)
+    u = np.ascontiguousarray(u, dtype=np.float64); o = np.zeros(m.size)
+    check(load().bcfgpu_op_probit_latent(_dp(m), _ip(y), _dp(u), m.size, _dp(o)))
+    return o

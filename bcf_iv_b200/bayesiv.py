@@ -6,15 +6,13 @@ complier proportion -> ITT by Bayesian Causal Forest (THE HOT PATH, R/bcf_iv.R:8
 -> tauhat = itt / pic -> depth-limited CART on tauhat -> per-node 2SLS and weak-instrument test on the inference
 sample -> p-value adjustment on the leaves.  The R version of the same glue is bcf_iv_b200/R/BayesIVgpu/R/.
 
-Everything except the sampler stays on the CPU (north_star): the pieces R takes from rpart / AER / stats are restated
-here in closed form (`cart`, `tsls`, `p_adjust`, `logit_link`).  Deviations, all forced by what is not in scope:
-  * the complier proportion `pic` comes from the same GPU sampler run on the treatment received (tau of  w ~ z  is
-    P(complier | x)) instead of bartCause::bartc (a different third-party sampler, SURVEY 8f-1);
-  * binary = TRUE: the reference switches to bartc (probit BART, S-learner) for the ITT and never reaches bcf
-    (R/bcf_iv.R:198-202).  Here the ITT on the probability scale, P(y=1 | z=1, x) - P(y=1 | z=0, x) -- the estimand
-    bartc's "ite" reports for a binary response -- is the tau of the same GPU sampler run on the 0/1 outcome (a linear
-    probability BCF, exactly what is done for `pic`); y must be 0/1.  A substitution, not a restatement: say so when
-    comparing numbers with the reference on config C4;
+Everything except the samplers stays on the CPU (north_star): the pieces R takes from rpart / AER / stats are restated
+here in closed form (`cart`, `tsls`, `p_adjust`, `logit_link`).  The reference's second sampler, bartCause::bartc
+(probit BART S-learner: the complier proportion of every call, R/bcf_iv.R:78-80, and the whole model when binary = TRUE,
+R/bcf_iv.R:198-202, R/bcf_itt.R:166-170), is bcf_iv_b200.bart.bartc: the same library's probit-BART model on the GPU.
+Deviations:
+  * `pic_model="bcf"` (not the default) keeps round 1's stand-in for bartc: the complier proportion as the tau of a
+    linear-probability BCF of w on z, and with binary = TRUE the ITT as the tau of a BCF on the 0/1 outcome;
   * the honest split uses NumPy's generator: the same seed gives a different split than R's sample().
 """
 from __future__ import annotations
@@ -23,6 +21,7 @@ import math
 
 import numpy as np
 
+from . import bart as _bart
 from . import bcf as _bcf
 
 COLUMNS = ["node", "CCACE", "pvalue", "Weak_IV_test", "Pi_obs", "ITT", "Pi_compliers", "Adj_pvalue"]
@@ -257,11 +256,13 @@ def _node_rows(nodes, where, names, inf_y, inf_w, inf_z, inf_X):
 
 
 def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5, max_depth=2, cp=0.01, minsplit=10,
-           adj_method="holm", seed=42, bcf_fn=None, details=None, **bcf_args):
+           adj_method="holm", seed=42, bcf_fn=None, bartc_fn=None, pic_model="bartc", details=None, **bcf_args):
     """Discovery and estimation of heterogeneity in the complier average causal effect (R/bcf_iv.R:47).
     Returns a pandas DataFrame with the reference's columns (COLUMNS), one row per CART node.
-    `bcf_fn`: the fitting function (default: bcf_iv_b200.bcf.bcf, the GPU sampler) -- the parity tests pass a twin that
-    drives the CPU oracle through the identical pipeline.  `details`: a dict that receives the intermediate estimands
+    `bcf_fn` / `bartc_fn`: the fitting functions (default: bcf_iv_b200.bcf.bcf and bcf_iv_b200.bart.bartc, the GPU
+    samplers) -- the parity tests pass twins that drive the CPU oracle through the identical pipeline.
+    `pic_model`: "bartc" (the reference: probit BART for the complier proportion and, with binary = TRUE, for the ITT) or
+    "bcf" (both from the BCF sampler on the 0/1 vectors: a linear-probability stand-in).  `details`: a dict that receives the intermediate estimands
     (discovery rows, pic, itt, tauhat, the CART's split variables)."""
     import pandas as pd
     y, w, z = (np.asarray(a, dtype=np.float64).ravel() for a in (y, w, z))
@@ -278,15 +279,27 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     # memory (27 tiles of 256 rows on each of 74 SMs) each fit gets half of the SMs; at any size one fit's host-side
     # preamble hides under the other's sweeps.
     from concurrent.futures import ThreadPoolExecutor
-    if "max_ctas" not in fit_args and len(disc) <= 27 * 256 * (_bcf._lib.B200_SMS // 2) - 512:
+    if pic_model == "bcf" and "max_ctas" not in fit_args and len(disc) <= 27 * 256 * (_bcf._lib.B200_SMS // 2) - 512:
         fit_args["max_ctas"] = _bcf._lib.B200_SMS // 2
     fit = bcf_fn or _bcf.bcf
+    fit_bartc = bartc_fn or _bart.bartc
+    if pic_model not in ("bartc", "bcf"):
+        raise ValueError("pic_model must be 'bartc' or 'bcf'")
     with ThreadPoolExecutor(max_workers=2) as pool:
-        # the reference's two samplers are independent (bartc / bcf): the complier-proportion fit gets its own Philox
-        # stream (chain 1 of the seed), so itt and pic do not share their Monte Carlo noise
-        f_pic = pool.submit(fit, w[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, first_chain=1))   # P(complier | x)
-        f_itt = pool.submit(fit, y[disc], z[disc], Xd, Xd, pihat, **fit_args)               # R/bcf_iv.R:89-91
-        pic, itt = f_pic.result()["tau_mean"], f_itt.result()["tau_mean"]
+        # the reference's two samplers are independent (bartc / bcf): each fit has its own Philox streams, so itt and pic
+        # do not share their Monte Carlo noise
+        if pic_model == "bartc":
+            f_pic = pool.submit(lambda: fit_bartc(w[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2,
+                                                  seed=seed)["ite_mean"])                    # R/bcf_iv.R:78-80
+            if binary:                                                                          # R/bcf_iv.R:198-202
+                f_itt = pool.submit(lambda: fit_bartc(y[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2,
+                                                      seed=seed + 1)["ite_mean"])
+            else:
+                f_itt = pool.submit(lambda: fit(y[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"])   # R/bcf_iv.R:89-91
+        else:
+            f_pic = pool.submit(lambda: fit(w[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, first_chain=1))["tau_mean"])
+            f_itt = pool.submit(lambda: fit(y[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"])
+        pic, itt = f_pic.result(), f_itt.result()
     tauhat = itt / pic                                                                      # R/bcf_iv.R:94
     nodes, where = cart(Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
     if details is not None:
@@ -310,7 +323,8 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     return tab
 
 
-def bcf_itt(y, w, z, x, binary=False, max_depth=2, n_burn=500, n_sim=500, inference_ratio=0.5, seed=42, **bcf_args):
+def bcf_itt(y, w, z, x, binary=False, max_depth=2, n_burn=500, n_sim=500, inference_ratio=0.5, seed=42, bcf_fn=None,
+            bartc_fn=None, **bcf_args):
     """Heterogeneity in the intention-to-treat effect (R/bcf_itt.R:33; same positional order of the arguments): prints the
     node effects and returns None, as the reference does."""
     y, w, z = (np.asarray(a, dtype=np.float64).ravel() for a in (y, w, z))
@@ -323,7 +337,10 @@ def bcf_itt(y, w, z, x, binary=False, max_depth=2, n_burn=500, n_sim=500, infere
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)
     Xd = X[disc]
-    tauhat = _bcf.bcf(y[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"]             # R/bcf_itt.R:71-75
+    if binary:                                                                              # R/bcf_itt.R:166-170
+        tauhat = (bartc_fn or _bart.bartc)(y[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2, seed=seed)["ite_mean"]
+    else:
+        tauhat = (bcf_fn or _bcf.bcf)(y[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"]         # R/bcf_itt.R:71-75
     nodes, where = cart(Xd, tauhat, maxdepth=max_depth)                                     # rpart defaults (R/bcf_itt.R:82)
     ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
     for nid in ids:

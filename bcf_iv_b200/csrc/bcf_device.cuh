@@ -140,6 +140,7 @@ struct Dev {
     int32_t n_tiles, trt_tiles;  // tiles [0, trt_tiles) are treated, the rest control
     int32_t T, max_leaves, min_leaf;
     int32_t use_muscale, use_tauscale;
+    int32_t fix_sigma, pad_;   // probit BART: the latent's variance is 1, sigma is not drawn
     uint32_t key0, key1;       // Philox key
     double nu, lambda, con_sd, mod_sd;
     ForestDev f[2];

@@ -336,8 +336,10 @@ __device__ inline void sweep_scalars(const Dev& d, const TreeRec* newtrees, cons
             const double b = g ? b1 : b0;
             rss += M[g][0] + ms * ms * M[g][3] + b * b * M[g][5] - 2.0 * ms * M[g][1] - 2.0 * b * M[g][2] + 2.0 * ms * b * M[g][4];
         }
-        const double chi2 = 2.0 * rng_gamma(rng, sc.sweep, PUR_SIGMA, 0.5 * (d.nu + (double)d.n_global));
-        sc.sigma = sqrt((d.nu * d.lambda + rss) / chi2);
+        if (!d.fix_sigma) {
+            const double chi2 = 2.0 * rng_gamma(rng, sc.sweep, PUR_SIGMA, 0.5 * (d.nu + (double)d.n_global));
+            sc.sigma = sqrt((d.nu * d.lambda + rss) / chi2);
+        }
         sc.mscale = ms; sc.bscale1 = b1; sc.bscale0 = b0;
         if (!(sc.sigma == sc.sigma) || !(ms == ms) || !(b1 == b1) || !(b0 == b0)) atomicOr(d.err, ERR_NAN);
         // bcf saves iteration i when i >= burn and i % thin == 0
@@ -860,6 +862,162 @@ __global__ void __launch_bounds__(256) k_hist_small(Dev d, int forest, const uin
         for (int q = 0; q < 4; ++q) if (rest[q] != 0) atomicAdd((unsigned long long*)&o0[q], (unsigned long long)rest[q]);
     }
     if (bad) atomicOr(d.err, ERR_FX_RANGE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Probit BART: the sampler behind bartCause::bartc for a 0/1 response, which the reference calls at
+// R/bcf_iv.R:78-80 (complier proportion) and R/bcf_iv.R:198-202, R/bcf_itt.R:166-170 (binary = TRUE).  Chipman-George-
+// McCulloch BART with Albert & Chib's latent Gaussian: the forest machinery is the mu forest of the sweep kernels run
+// alone (no tau forest, no scales, sigma = 1); what is added is the latent draw that opens every sweep and, per saved
+// sweep, the S-learner's individual effect  Phi(offset + f(x, z = 1)) - Phi(offset + f(x, z = 0)).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double norm_cdf_d(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+// Wichura's AS 241 (PPND16): the expression of the oracle's norm_inv, term for term
+__device__ inline double norm_inv_d(double p)
+{
+    const double q = p - 0.5;
+    if (fabs(q) <= 0.425) {
+        const double r = 0.180625 - q * q;
+        return q * (((((((2.5090809287301226727e3 * r + 3.3430575583588128105e4) * r + 6.7265770927008700853e4) * r +
+                        4.5921953931549871457e4) * r + 1.3731693765509461125e4) * r + 1.9715909503065514427e3) * r +
+                      1.3314166789178437745e2) * r + 3.3871328727963666080e0) /
+               (((((((5.2264952788528545610e3 * r + 2.8729085735721942674e4) * r + 3.9307895800092710610e4) * r +
+                    2.1213794301586595867e4) * r + 5.3941960214247511077e3) * r + 6.8718700749205790830e2) * r +
+                  4.2313330701600911252e1) * r + 1.0);
+    }
+    double r = q < 0 ? p : 1.0 - p;
+    r = sqrt(-log(r));
+    double v;
+    if (r <= 5.0) {
+        r -= 1.6;
+        v = (((((((7.74545014278341407640e-4 * r + 2.27238449892691845833e-2) * r + 2.41780725177450611770e-1) * r +
+                 1.27045825245236838258e0) * r + 3.64784832476320460504e0) * r + 5.76949722146069140550e0) * r +
+               4.63033784615654529590e0) * r + 1.42343711074968357734e0) /
+            (((((((1.05075007164441684324e-9 * r + 5.47593808499534494600e-4) * r + 1.51986665636164571966e-2) * r +
+                 1.48103976427480074590e-1) * r + 6.89767334985100004550e-1) * r + 1.67638483018380384940e0) * r +
+               2.05319162663775882187e0) * r + 1.0);
+    } else {
+        r -= 5.0;
+        v = (((((((2.01033439929228813265e-7 * r + 2.71155556874348757815e-5) * r + 1.24266094738807843860e-3) * r +
+                 2.65321895265761230930e-2) * r + 2.96560571828504891230e-1) * r + 1.78482653991729133580e0) * r +
+               5.46378491116411436990e0) * r + 6.65790464350110377720e0) /
+            (((((((2.04426310338993978564e-15 * r + 1.42151175831644588870e-7) * r + 1.84631831751005468180e-5) * r +
+                 7.86869131145613259100e-4) * r + 1.48753612908506148525e-2) * r + 1.36929880922735805310e-1) * r +
+               5.99832206555887937690e-1) * r + 1.0);
+    }
+    return q < 0 ? -v : v;
+}
+// ystar ~ N(m, 1) truncated to (0, inf) when y = 1, to (-inf, 0] when y = 0, by inversion of one uniform on the side
+// where the cdf is small
+__device__ __forceinline__ double probit_latent_d(double m, int y, double u)
+{
+    return y ? m - norm_inv_d(u * norm_cdf_d(m)) : m + norm_inv_d(u * norm_cdf_d(-m));
+}
+constexpr uint32_t PUR_LATENT = 20;       // idx = the caller's row number
+// after k_place: the permuted outcome is the 0/1 response; keep it as bytes, the working response starts at 0
+__global__ void k_probit_prepare(double* __restrict__ y, uint8_t* __restrict__ ybin, int64_t n_pad)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        ybin[i] = y[i] != 0.0 ? 1 : 0;
+        y[i] = 0.0;
+    }
+}
+// the latent draw that opens a sweep: working response y = ystar - offset, full residual re-derived from it
+__global__ void __launch_bounds__(256) k_probit_latent(Dev d, const uint8_t* __restrict__ ybin, const int32_t* __restrict__ orig,
+                                                       int64_t row0, double offset, double* __restrict__ y)
+{
+    const Scalars sc = *d.sc;
+    const Rng rng{d.key0, d.key1};
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t o = orig[i];
+        if (o < 0) continue;                                    // padding: y = 0, residual 0
+        double ua, ub;
+        rng_u2(rng, sc.sweep, TREE_SWEEP_LEVEL, PUR_LATENT, (uint32_t)(row0 + o), ua, ub);
+        const double gc = d.Gc[i];
+        const double ys = probit_latent_d(offset + sc.mscale * gc, ybin[i], ua) - offset;
+        if (!(ys == ys)) bad = 1;
+        y[i] = ys;
+        d.rfx[i] = resync_fx(ys, sc.mscale, gc, 0.0, 0.0, bad);
+    }
+    if (bad) atomicOr(d.err, ERR_FX_RANGE);
+}
+// which trees split on the treatment column?  one CTA per tree; list[0] = count, list[1..] = tree ids (any order)
+__global__ void k_cf_collect(Dev d, const TreeRec* __restrict__ trees, int trt_var, int* list)
+{
+    const TreeRec& tr = trees[blockIdx.x];
+    const int nn = __ldcg(&tr.nnodes);
+    int hit = 0;
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) hit |= (__ldcg(&tr.left[i]) >= 0 && (int)__ldcg(&tr.var[i]) == trt_var) ? 1 : 0;
+    if (__syncthreads_or(hit) && threadIdx.x == 0) list[1 + atomicAdd(&list[0], 1)] = (int)blockIdx.x;
+}
+// One saved sweep of the S-learner: f with the treatment flipped differs from the fitted f only through the trees that
+// split on the treatment; those are walked again with the flipped bin.  Accumulates (internal order)
+//   tau_sum / tau_sq : Phi(offset + f(x, 1)) - Phi(offset + f(x, 0))  and its square,
+//   mu_sum           : Phi(offset + f(x)) at the observed treatment,   yhat_sum: f(x) itself.
+constexpr int CF_OBS_PER_THREAD = 4;
+__global__ void __launch_bounds__(256) k_cf_accumulate(Dev d, const TreeRec* __restrict__ trees, const int* __restrict__ list,
+                                                       int trt_var, double offset, const int32_t* __restrict__ orig)
+{
+    __shared__ TreeRec tr;
+    const ForestDev& F = d.f[0];
+    const int nlist = trt_var >= 0 ? list[0] : 0;
+    const int64_t base = (int64_t)blockIdx.x * (256 * CF_OBS_PER_THREAD) + threadIdx.x;
+    double diff[CF_OBS_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < CF_OBS_PER_THREAD; ++k) diff[k] = 0.0;
+    int tb[CF_OBS_PER_THREAD];                                   // observed treatment (bin of the treatment column: 0 / 1)
+#pragma unroll
+    for (int k = 0; k < CF_OBS_PER_THREAD; ++k) {
+        const int64_t i = base + (int64_t)k * 256;
+        tb[k] = 0;
+        if (trt_var >= 0 && i < d.n_pad) {
+            const int ci = F.col_index[trt_var];
+            tb[k] = F.col_is16[trt_var] ? (int)F.bins16[(int64_t)ci * d.n_pad + i] : (int)F.bins8[(int64_t)ci * d.n_pad + i];
+        }
+    }
+    for (int q = 0; q < nlist; ++q) {
+        const int t = list[1 + q];
+        __syncthreads();
+        load_tree(&tr, &trees[t]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CF_OBS_PER_THREAD; ++k) {
+            const int64_t i = base + (int64_t)k * 256;
+            if (i >= d.n_pad || orig[i] < 0) continue;
+            int node = 0;
+            while (tr.left[node] >= 0) {
+                const int v = tr.var[node];
+                int b;
+                if (v == trt_var) b = tb[k] ? 0 : 1;             // the other arm
+                else {
+                    const int ci = F.col_index[v];
+                    b = F.col_is16[v] ? (int)F.bins16[(int64_t)ci * d.n_pad + i] : (int)F.bins8[(int64_t)ci * d.n_pad + i];
+                }
+                node = (b <= (int)tr.cut[node]) ? tr.left[node] : tr.right[node];
+            }
+            const int s_fact = d.slots[(int64_t)t * d.n_pad + i];
+            diff[k] += tr.mu[tr.node_slot[node]] - tr.mu[s_fact];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CF_OBS_PER_THREAD; ++k) {
+        const int64_t i = base + (int64_t)k * 256;
+        if (i >= d.n_pad || orig[i] < 0) continue;
+        const double f = d.Gc[i], fcf = f + diff[k];
+        const double pf = norm_cdf_d(offset + f);
+        double ite = 0.0;
+        if (trt_var >= 0) {
+            const double pcf = norm_cdf_d(offset + fcf);
+            ite = tb[k] ? pf - pcf : pcf - pf;
+        }
+        d.tau_sum[i] += ite; d.tau_sq[i] += ite * ite; d.mu_sum[i] += pf; d.yhat_sum[i] += f;
+    }
+}
+__global__ void k_probit_probe(const double* m, const int* y, const double* u, int n, double* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = probit_latent_d(m[i], y[i], u[i]);
 }
 
 __global__ void k_lil(const double* a, const double* b, const double* tau, int m, double* out)

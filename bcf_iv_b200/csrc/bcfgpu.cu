@@ -136,6 +136,8 @@ struct bcfgpu_handle {
     double last_ms = 0.0;
     int32_t nsaved = 0, post_cap = 0;
     int keep = 0;
+    uint8_t* d_ybin = nullptr;        // probit BART: the observed 0/1 response, internal order
+    int* d_cflist = nullptr;          // probit BART: trees that split on the treatment (k_cf_collect)
     std::atomic<int> stop{0};         // bcfgpu_request_stop: the run in progress ends at its next launch boundary
 };
 
@@ -289,6 +291,7 @@ void bcfgpu_config_init(bcfgpu_config* c)
     c->use_muscale = 1; c->use_tauscale = 1;
     c->min_leaf = 5; c->max_leaves = 0;
     c->seed = 42; c->chain = 0; c->device = -1; c->engine = BCFGPU_ENGINE_AUTO; c->keep_draws = 0;
+    c->model = BCFGPU_MODEL_BCF; c->treatment_col = -1; c->probit_offset = 0.0;
 }
 
 int bcfgpu_release_cached_memory(void)
@@ -328,6 +331,9 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
         return fail(BCFGPU_ERR_BAD_ARG, "con_sd, mod_sd, nu, lambda, sigma_init must be positive");
     if (cfg->max_leaves < 0 || cfg->max_leaves > MAXL || cfg->max_leaves == 1) return fail(BCFGPU_ERR_BAD_ARG, "max_leaves must be 0 or in [2,128]");
     if (cfg->min_leaf < 1) return fail(BCFGPU_ERR_BAD_ARG, "min_leaf must be >= 1");
+    if (cfg->model != BCFGPU_MODEL_BCF && cfg->model != BCFGPU_MODEL_PROBIT_BART) return fail(BCFGPU_ERR_BAD_ARG, "unknown model");
+    if (cfg->model == BCFGPU_MODEL_PROBIT_BART && (cfg->ntree_mod != 0 || cfg->use_muscale != 0))
+        return fail(BCFGPU_ERR_BAD_ARG, "probit BART is one forest without scales: set ntree_mod = 0 and use_muscale = 0");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -652,6 +658,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     const int64_t nchunk = (n + PLACE_CHUNK - 1) / PLACE_CHUNK;
     std::vector<int32_t> chunk_trt((size_t)nchunk + 1, 0);
     const int nth = n >= 65536 ? host_threads() : 1;
+    const bool probit01 = c.model == BCFGPU_MODEL_PROBIT_BART;
     struct Part { long long s[4] = {0, 0, 0, 0}; int bad = 0; char pad_[28]; };
     std::vector<Part> part((size_t)nth);
     parallel_ranges(n, PLACE_CHUNK, nth, [&](int t, int64_t lo, int64_t hi) {
@@ -663,6 +670,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
                 const int32_t zi = z[i];
                 const double yi = y[i];
                 if (zi != 0 && zi != 1) P.bad |= 1;
+                if (probit01 && yi != 0.0 && yi != 1.0) P.bad |= 8;
                 if (!(std::fabs(yi) < 32768.0)) { P.bad |= std::isfinite(yi) ? 4 : 2; continue; }
                 k += zi;
                 const long long v = std::llrint(yi * 17592186044416.0);
@@ -678,6 +686,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     if (badbits & 1) return fail(BCFGPU_ERR_BAD_ARG, "z must be 0/1");
     if (badbits & 2) return fail(BCFGPU_ERR_BAD_ARG, "y must be finite");
     if (badbits & 4) return fail(BCFGPU_ERR_BAD_ARG, "|y| too large: pass the standardised outcome");
+    if (badbits & 8) return fail(BCFGPU_ERR_BAD_ARG, "probit BART needs a 0/1 response");
     for (int64_t k = 0; k < nchunk; ++k) chunk_trt[(size_t)k + 1] += chunk_trt[(size_t)k];     // exclusive prefix: treated rows before chunk k
     const int64_t ntrt = chunk_trt[(size_t)nchunk];
     ysum[4] = ntrt;
@@ -704,6 +713,15 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     d.n_pad = n_pad; d.n_tiles = (int32_t)(n_pad / TILE); d.trt_tiles = (int32_t)(trt_pad / TILE);
     d.T = h->T; d.max_leaves = c.max_leaves; d.min_leaf = c.min_leaf;
     d.use_muscale = c.use_muscale; d.use_tauscale = c.use_tauscale;
+    const bool probit = c.model == BCFGPU_MODEL_PROBIT_BART;
+    d.fix_sigma = probit ? 1 : 0;
+    if (probit) {
+        if (h->nranks > 1) return fail(BCFGPU_ERR_BAD_ARG, "probit BART does not run sharded");
+        if (c.treatment_col >= p_con) return fail(BCFGPU_ERR_BAD_ARG, "treatment_col is not a column of x_control");
+        if (c.treatment_col >= 0 && cut_off_con[c.treatment_col + 1] - cut_off_con[c.treatment_col] != 1)
+            return fail(BCFGPU_ERR_BAD_ARG, "the treatment column must be 0/1 with one cutpoint");
+        ysum[1] = ysum[2] = ysum[3] = 0;       // the working response starts at 0: every leaf starts at 0
+    }
     {
         const uint64_t s = c.seed + (uint64_t)c.chain * 0x9E3779B97F4A7C15ull;
         d.key0 = (uint32_t)s; d.key1 = (uint32_t)(s >> 32);
@@ -747,6 +765,13 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     k_place<<<(unsigned)nchunk, 256, 0, h->stream>>>(d_yraw, d_zraw, d_chunk, n, trt_pad, h->d_pos, h->d_orig, dy);
     h->launches++;
     CK(cudaGetLastError());
+    if (probit) {
+        DM(h, &h->d_ybin, (size_t)n_pad);
+        DM(h, &h->d_cflist, (size_t)h->T + 1);
+        k_probit_prepare<<<(unsigned)std::min<int64_t>((n_pad + 255) / 256, 4096), 256, 0, h->stream>>>(dy, h->d_ybin, n_pad);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     CK(cudaMemsetAsync(d.totals, 0, (size_t)2 * h->T * KEYS * 8 * 8, h->stream));
     CK(cudaMemsetAsync(d.cross, 0, (size_t)2 * h->T * PIPE_XSTRIDE * 8, h->stream));
     CK(cudaMemsetAsync(d.mom, 0, 2 * 2 * NMOM * 3 * 8, h->stream));
@@ -916,6 +941,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
     CK(cudaMemcpyAsync(&sc, d.sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     sc.run_it = 0; sc.nburn = nburn; sc.nthin = nthin; sc.nsim = nsim; sc.save_ctr = 0; sc.save_row = -1;
+    if (h->cfg.model == BCFGPU_MODEL_PROBIT_BART) { sc.nburn = total; sc.nsim = 0; }      // (saved by the counterfactual pass instead)
     CK(cudaMemcpyAsync(d.sc, &sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
     h->nsaved = 0;
     int rc = BCFGPU_OK;
@@ -944,19 +970,54 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
     if (!persistent && h->nranks == 1) { if ((rc = build_graph(h))) return rc; }
     CK(cudaEventRecord(h->ev0, h->stream));
     h->last_kernel = 0;
-    if (persistent) {
-        rc = run_persistent(h, total);
-        h->last_kernel = h->kernel;
-    } else if (h->nranks == 1) {
-        for (int it = 0; it < total; ++it) {
-            if ((it & 63) == 0 && h->stop.load(std::memory_order_relaxed)) { cudaStreamSynchronize(h->stream); return fail(BCFGPU_ERR_INTERRUPTED, "run stopped by bcfgpu_request_stop"); }
-            CK(cudaGraphLaunch(h->gexec, h->stream));
+    auto launch_sweeps = [&](int k) -> int {
+        if (persistent) {
+            int r = run_persistent(h, k);
+            h->last_kernel = h->kernel;
+            return r;
         }
-        h->launches += (int64_t)total * (h->T + 4);
-    } else {
-        for (int it = 0; it < total && rc == BCFGPU_OK; ++it) rc = enqueue_sweep(h);
-        h->launches += (int64_t)total * (h->T + 4);
-    }
+        if (h->nranks == 1) {
+            for (int it = 0; it < k; ++it) {
+                if ((it & 63) == 0 && h->stop.load(std::memory_order_relaxed)) { cudaStreamSynchronize(h->stream); return fail(BCFGPU_ERR_INTERRUPTED, "run stopped by bcfgpu_request_stop"); }
+                CK(cudaGraphLaunch(h->gexec, h->stream));
+            }
+            h->launches += (int64_t)k * (h->T + 4);
+            return BCFGPU_OK;
+        }
+        int r = BCFGPU_OK;
+        for (int it = 0; it < k && r == BCFGPU_OK; ++it) r = enqueue_sweep(h);
+        h->launches += (int64_t)k * (h->T + 4);
+        return r;
+    };
+    int probit_saved = 0;
+    if (h->cfg.model == BCFGPU_MODEL_PROBIT_BART) {
+        // One sweep per launch: the latent draw opens it (its own kernel: every engine parks the chain state in HBM between
+        // launches), the sweep kernel runs it as a burn-in sweep (the engines' own posterior accumulation stays off), and a
+        // saved sweep ends with the counterfactual pass.
+        const int grid = h->grid_fin;
+        const int cfgrid = (int)((d.n_pad + 256 * CF_OBS_PER_THREAD - 1) / (256 * CF_OBS_PER_THREAD));
+        for (int it = 0; it < total && rc == BCFGPU_OK; ++it) {
+            if (h->stop.load(std::memory_order_relaxed)) { rc = fail(BCFGPU_ERR_INTERRUPTED, "run stopped by bcfgpu_request_stop"); break; }
+            k_probit_latent<<<grid, 256, 0, h->stream>>>(d, h->d_ybin, h->d_orig, 0, h->cfg.probit_offset, const_cast<double*>(d.y));
+            h->launches++;
+            rc = launch_sweeps(1);
+            if (rc == BCFGPU_OK && it >= nburn && (it % nthin) == 0 && probit_saved < nsim) {
+                // (the sweep flipped the tree parity: the current trees are in trees[parity]; read it back lazily -- it
+                // simply alternates from the value fetched above)
+                const int par = (sc.parity + it + 1) & 1;
+                if (h->cfg.treatment_col >= 0) {
+                    CK(cudaMemsetAsync(h->d_cflist, 0, 4, h->stream));
+                    k_cf_collect<<<h->T, 64, 0, h->stream>>>(d, d.trees[par], h->cfg.treatment_col, h->d_cflist);
+                }
+                k_cf_accumulate<<<cfgrid, 256, 0, h->stream>>>(d, d.trees[par], h->d_cflist, h->cfg.treatment_col,
+                                                               h->cfg.probit_offset, h->d_orig);
+                h->launches += 2;
+                ++probit_saved;
+            }
+        }
+        if (rc == BCFGPU_OK) CK(cudaGetLastError());
+    } else
+        rc = launch_sweeps(total);
     if (rc) { cudaStreamSynchronize(h->stream); return rc; }
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -965,7 +1026,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
     h->last_ms = ms;
     if ((rc = check_device_err(h))) return rc;
     CK(cudaMemcpy(&sc, d.sc, sizeof(sc), cudaMemcpyDeviceToHost));
-    h->nsaved = sc.save_ctr;
+    h->nsaved = h->cfg.model == BCFGPU_MODEL_PROBIT_BART ? probit_saved : sc.save_ctr;
 #ifndef BCF_PROF
     if (d.prof) {
         static bool told = false;
@@ -1534,6 +1595,23 @@ int bcfgpu_op_lil(const double* sum_phi, const double* sum_phi_r, const double* 
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, d + 3 * m, (size_t)m * 8, cudaMemcpyDeviceToHost));
     cudaFree(d);
+    return BCFGPU_OK;
+}
+
+int bcfgpu_op_probit_latent(const double* m, const int32_t* y, const double* u, int32_t n, double* out)
+{
+    if (!m || !y || !u || !out || n < 1) return fail(BCFGPU_ERR_BAD_ARG, "bad argument");
+    if (bcfgpu_device_count() == 0) return fail(BCFGPU_ERR_CUDA, "no CUDA device available (libbcfgpu has no CPU fallback)");
+    double* dm = nullptr; int* dyv = nullptr;
+    CK(cudaMalloc((void**)&dm, (size_t)n * 8 * 3));
+    CK(cudaMalloc((void**)&dyv, (size_t)n * 4));
+    CK(cudaMemcpy(dm, m, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dm + n, u, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dyv, y, (size_t)n * 4, cudaMemcpyHostToDevice));
+    k_probit_probe<<<(n + 127) / 128, 128>>>(dm, dyv, dm + n, n, dm + 2 * (size_t)n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dm + 2 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dm); cudaFree(dyv);
     return BCFGPU_OK;
 }
 

@@ -86,8 +86,23 @@ typedef struct bcfgpu_config {
     int32_t keep_draws;           /* bit0 tau, bit1 mu, bit2 yhat: keep nsim x n draws on device */
     int32_t max_ctas;             /* 0: one CTA per SM.  > 0: at most that many CTAs, so that several fits can share one GPU
                                    * side by side (bcf_iv fits the complier proportion and the ITT at the same time) */
-    int32_t reserved[6];
+    int32_t model;                /* bcfgpu_model: 0 = Bayesian Causal Forest (bcf), 1 = probit BART (bartCause::bartc's sampler) */
+    int32_t treatment_col;        /* probit BART: column of x_control that holds the 0/1 treatment (S-learner: tau = the
+                                   * individual effect Phi(f(x,1)) - Phi(f(x,0))), or -1: no treatment, only P(y = 1 | x) */
+    int32_t reserved0;
+    double probit_offset;         /* probit BART: P(y = 1 | x) = Phi(probit_offset + f(x))  (dbarts' binaryOffset, 0) */
+    int32_t reserved[2];
 } bcfgpu_config;
+
+/* BCFGPU_MODEL_PROBIT_BART: the sampler behind bartCause::bartc(response, treatment, confounders) for a 0/1 response --
+ * the reference's complier-proportion fit (R/bcf_iv.R:78-80) and its whole model when binary = TRUE (R/bcf_iv.R:198-202,
+ * R/bcf_itt.R:166-170).  One forest (ntree_con trees; set ntree_mod = 0, use_muscale = 0, con_sd = 3 / k), sigma = 1,
+ * Albert-Chib latent redrawn before every sweep.  set_data: y = the 0/1 response, z = the treatment (any 0/1 vector when
+ * there is none), xcon = (confounders, ..., treatment) with treatment_col naming the treatment's column.  Results:
+ * get_tau_mean / get_tau_var = posterior mean / variance of Phi(off + f(x, 1)) - Phi(off + f(x, 0)) per observation
+ * (bartc's individual effects on the probability scale), get_mu_mean = posterior mean of P(y = 1 | x, z observed),
+ * get_yhat_mean = posterior mean of f(x). */
+typedef enum bcfgpu_model { BCFGPU_MODEL_BCF = 0, BCFGPU_MODEL_PROBIT_BART = 1 } bcfgpu_model;
 
 typedef struct bcfgpu_handle bcfgpu_handle;
 
@@ -202,6 +217,8 @@ BCFGPU_API int bcfgpu_op_lil(const double *sum_phi, const double *sum_phi_r, con
 /* Philox stream probe: {ua, ub, normal} for (seed, chain, sweep, tree, purpose, idx), computed on device */
 BCFGPU_API int bcfgpu_op_rng_probe(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t tree, uint32_t purpose,
                                    uint32_t idx, double out3[3]);
+/* probit BART's latent draw: out[i] = ystar ~ N(m[i], 1) truncated by y[i] (1: > 0, 0: <= 0), from the uniform u[i] */
+BCFGPU_API int bcfgpu_op_probit_latent(const double *m, const int32_t *y, const double *u, int32_t n, double *out);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,8 @@ enum {
     PUR_CUT = 2,    /* ua: cutpoint choice                                       */
     PUR_LEAF = 3,   /* idx = heap id of the leaf: normal for the leaf mean draw */
     PUR_BSCALE1 = 10, PUR_BSCALE0 = 11, PUR_MSCALE = 12,
-    PUR_DELTA_CON = 13, PUR_DELTA_MOD = 14, PUR_SIGMA = 15
+    PUR_DELTA_CON = 13, PUR_DELTA_MOD = 14, PUR_SIGMA = 15,
+    PUR_LATENT = 20 /* idx = the caller's row number: the uniform behind that row's truncated-normal latent */
 };
 #define TREE_SWEEP_LEVEL 0xFFFFFFFFu
 
@@ -251,6 +252,12 @@ typedef struct orc_sampler {
     /* last-move trace (for parity tests) */
     int32_t *trace;  /* per tree: [move(0 none,1 birth,2 death), accepted, nodeheap, var, cut] */
     double *trace_logr; /* per tree: log MH ratio (log alpha1 + lil difference), NaN if not evaluated */
+    /* probit BART (the bartc replacement, see "Probit BART" below): 0/1 response behind a latent Gaussian */
+    int probit;          /* 1: y is the latent, redrawn before every sweep; sigma stays 1 */
+    uint8_t *ybin;       /* the observed 0/1 response, internal order */
+    int32_t *rowid;      /* caller's row number of every internal row: the Philox index of its latent draw */
+    double offset;       /* binaryOffset: P(y = 1 | x) = Phi(offset + f(x)) */
+    int trt_col;         /* column of the treatment in x_con (S-learner), or -1 */
 } orc_sampler;
 
 static void fit_tree(orc_sampler *s, node *t, const double *x, int p, const xinfo *xi, double *out)
@@ -540,7 +547,7 @@ ORC_API void orc_destroy(orc_sampler *s)
     for (int j = 0; j < s->cfg.ntree_mod; ++j) tree_free(s->t_mod[j]);
     free(s->t_con); free(s->t_mod); free(s->y); free(s->xc); free(s->xm); free(s->cuts_c); free(s->cuts_m);
     free(s->off_c); free(s->off_m); free(s->allfit); free(s->allfit_con); free(s->allfit_mod); free(s->ftemp);
-    free(s->rtemp); free(s->weight); free(s->trace); free(s->trace_logr); free(s);
+    free(s->rtemp); free(s->weight); free(s->trace); free(s->trace_logr); free(s->ybin); free(s->rowid); free(s);
 }
 
 /* One full Gibbs sweep [bcf-recall: the body of the outer loop of bcfoverparRcppClean; SURVEY 3.3, A.3, A.4] */
@@ -636,8 +643,10 @@ static void sweep_once(orc_sampler *s)
         const double e = s->y[k] - s->allfit[k];
         rss += e * e;
     }
-    const double chi2 = 2.0 * rng_gamma(&s->rng, s->sweep, PUR_SIGMA, 0.5 * (c->nu + n));
-    s->sigma = sqrt((c->nu * c->lambda + rss) / chi2);
+    if (!s->probit) {   /* probit BART: the latent has unit variance by construction */
+        const double chi2 = 2.0 * rng_gamma(&s->rng, s->sweep, PUR_SIGMA, 0.5 * (c->nu + n));
+        s->sigma = sqrt((c->nu * c->lambda + rss) / chi2);
+    }
     s->sweep++;
 }
 
@@ -877,6 +886,132 @@ ORC_API void orc_hist_all(orc_sampler *s, int forest, const int32_t *slot, int n
         }
     }
 }
+
+/* ------------------------------------------------------------------------- */
+/* Probit BART: the sampler behind bartCause::bartc for a 0/1 response, which the   */
+/* reference calls at R/bcf_iv.R:78-80 (complier proportion: response w) and at      */
+/* R/bcf_iv.R:198-202, R/bcf_itt.R:166-170 (binary = TRUE: response y).  bartCause   */
+/* and dbarts are third-party, un-vendored and un-pinned like bcf (DESCRIPTION:22-24)*/
+/* -> PARITY UNPINNED.  Restated: the published algorithm -- Chipman, George &       */
+/* McCulloch (2010) BART with the Albert & Chib (1993) data augmentation:            */
+/*   y_i = 1{ystar_i > 0},  ystar_i = offset + f(x_i) + eps_i,  eps ~ N(0, 1),       */
+/*   f = sum of T trees, leaf values N(0, (3 / (k sqrt T))^2), k = 2,                */
+/*   tree prior alpha (1 + d)^-beta = .95, 2;  sigma = 1 is not drawn.               */
+/* One sweep = redraw every latent from its truncated normal given f, then the usual */
+/* backfitting pass (birth/death + leaf draws: the SAME bd()/drmu() as above with     */
+/* one forest, no scales).  bartc is an S-learner: the forest sees (x, pscore, z) and */
+/* the individual effect of a draw is  Phi(offset + f(x, 1)) - Phi(offset + f(x, 0)).*/
+/* ------------------------------------------------------------------------- */
+/* standard normal cdf, accurate in both tails */
+static double norm_cdf(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+/* its inverse: Wichura's AS 241 (PPND16), relative error ~1e-16 */
+static double norm_inv(double p)
+{
+    const double q = p - 0.5;
+    if (fabs(q) <= 0.425) {
+        const double r = 0.180625 - q * q;
+        return q * (((((((2.5090809287301226727e3 * r + 3.3430575583588128105e4) * r + 6.7265770927008700853e4) * r +
+                        4.5921953931549871457e4) * r + 1.3731693765509461125e4) * r + 1.9715909503065514427e3) * r +
+                      1.3314166789178437745e2) * r + 3.3871328727963666080e0) /
+               (((((((5.2264952788528545610e3 * r + 2.8729085735721942674e4) * r + 3.9307895800092710610e4) * r +
+                    2.1213794301586595867e4) * r + 5.3941960214247511077e3) * r + 6.8718700749205790830e2) * r +
+                  4.2313330701600911252e1) * r + 1.0);
+    }
+    double r = q < 0 ? p : 1.0 - p;
+    r = sqrt(-log(r));
+    double v;
+    if (r <= 5.0) {
+        r -= 1.6;
+        v = (((((((7.74545014278341407640e-4 * r + 2.27238449892691845833e-2) * r + 2.41780725177450611770e-1) * r +
+                 1.27045825245236838258e0) * r + 3.64784832476320460504e0) * r + 5.76949722146069140550e0) * r +
+               4.63033784615654529590e0) * r + 1.42343711074968357734e0) /
+            (((((((1.05075007164441684324e-9 * r + 5.47593808499534494600e-4) * r + 1.51986665636164571966e-2) * r +
+                 1.48103976427480074590e-1) * r + 6.89767334985100004550e-1) * r + 1.67638483018380384940e0) * r +
+               2.05319162663775882187e0) * r + 1.0);
+    } else {
+        r -= 5.0;
+        v = (((((((2.01033439929228813265e-7 * r + 2.71155556874348757815e-5) * r + 1.24266094738807843860e-3) * r +
+                 2.65321895265761230930e-2) * r + 2.96560571828504891230e-1) * r + 1.78482653991729133580e0) * r +
+               5.46378491116411436990e0) * r + 6.65790464350110377720e0) /
+            (((((((2.04426310338993978564e-15 * r + 1.42151175831644588870e-7) * r + 1.84631831751005468180e-5) * r +
+                 7.86869131145613259100e-4) * r + 1.48753612908506148525e-2) * r + 1.36929880922735805310e-1) * r +
+               5.99832206555887937690e-1) * r + 1.0);
+    }
+    return q < 0 ? -v : v;
+}
+ORC_API double orc_norm_cdf(double x) { return norm_cdf(x); }
+ORC_API double orc_norm_inv(double p) { return norm_inv(p); }
+/* one latent: ystar ~ N(m, 1) truncated to (0, inf) when y = 1, to (-inf, 0] when y = 0, by inversion of ONE uniform
+ * (written on the side where the cdf is small, so it stays accurate however improbable the observed response is) */
+static double probit_latent(double m, int y, double u)
+{
+    if (y) return m - norm_inv(u * norm_cdf(m));     /* eps = -eps', eps' < m */
+    return m + norm_inv(u * norm_cdf(-m));           /* eps < -m */
+}
+ORC_API double orc_probit_latent_probe(double m, int y, double u) { return probit_latent(m, y, u); }
+
+/* Switch a sampler (created with ntree_mod = 0, use_muscale = 0 and y = 0) to probit BART.  ybin / rowid: the 0/1
+ * response and the caller's row number of every row, internal order. */
+ORC_API void orc_probit_enable(orc_sampler *s, const uint8_t *ybin, const int32_t *rowid, double offset, int trt_col)
+{
+    s->probit = 1; s->offset = offset; s->trt_col = trt_col;
+    s->ybin = (uint8_t *)malloc((size_t)s->n); memcpy(s->ybin, ybin, (size_t)s->n);
+    s->rowid = (int32_t *)malloc(sizeof(int32_t) * (size_t)s->n); memcpy(s->rowid, rowid, sizeof(int32_t) * (size_t)s->n);
+    s->sigma = 1.0;
+}
+/* the latent draw that opens sweep s->sweep: the working response is ystar - offset */
+static void probit_draw_latents(orc_sampler *s)
+{
+    for (int i = 0; i < s->n; ++i) {
+        double ua, ub;
+        rng_u2(&s->rng, s->sweep, TREE_SWEEP_LEVEL, PUR_LATENT, (uint32_t)s->rowid[i], &ua, &ub);
+        s->y[i] = probit_latent(s->offset + s->allfit[i], s->ybin[i], ua) - s->offset;
+    }
+}
+/* f(x) of every row with the treatment column set to `trt` (0 / 1), by walking every tree over the raw doubles */
+static void probit_fit_with_treatment(orc_sampler *s, double trt, double *out)
+{
+    const int p = s->p_con;
+    double *xx = (double *)malloc(sizeof(double) * (size_t)p);
+    for (int i = 0; i < s->n; ++i) {
+        memcpy(xx, s->xc + (size_t)i * p, sizeof(double) * (size_t)p);
+        if (s->trt_col >= 0) xx[s->trt_col] = trt;
+        double f = 0;
+        for (int j = 0; j < s->cfg.ntree_con; ++j) f += tree_bn(s->t_con[j], xx, &s->xi_c)->mu;
+        out[i] = f;
+    }
+    free(xx);
+}
+/* nburn + nsim * nthin sweeps; saved sweeps accumulate, per row (internal order):
+ *   ite_mean  = mean of Phi(offset + f(x, 1)) - Phi(offset + f(x, 0))   (NULL or trt_col < 0: skipped)
+ *   prob_mean = mean of Phi(offset + f(x)) at the observed covariates */
+ORC_API int orc_probit_run(orc_sampler *s, int nburn, int nsim, int nthin, double *ite_mean, double *prob_mean)
+{
+    const int n = s->n, total = nburn + nsim * nthin;
+    int saved = 0;
+    double *f1 = (double *)malloc(sizeof(double) * (size_t)n), *f0 = (double *)malloc(sizeof(double) * (size_t)n);
+    if (ite_mean) memset(ite_mean, 0, sizeof(double) * (size_t)n);
+    if (prob_mean) memset(prob_mean, 0, sizeof(double) * (size_t)n);
+    for (int it = 0; it < total; ++it) {
+        probit_draw_latents(s);
+        sweep_once(s);
+        if (it >= nburn && it % nthin == 0 && saved < nsim) {
+            if (ite_mean && s->trt_col >= 0) {
+                probit_fit_with_treatment(s, 1.0, f1);
+                probit_fit_with_treatment(s, 0.0, f0);
+                for (int i = 0; i < n; ++i) ite_mean[i] += norm_cdf(s->offset + f1[i]) - norm_cdf(s->offset + f0[i]);
+            }
+            if (prob_mean) for (int i = 0; i < n; ++i) prob_mean[i] += norm_cdf(s->offset + s->allfit[i]);
+            ++saved;
+        }
+    }
+    if (saved > 0) for (int i = 0; i < n; ++i) { if (ite_mean) ite_mean[i] /= saved; if (prob_mean) prob_mean[i] /= saved; }
+    free(f1); free(f0);
+    return saved;
+}
+/* one sweep (latent draw + backfitting), for move-by-move parity */
+ORC_API void orc_probit_sweeps(orc_sampler *s, int k) { for (int i = 0; i < k; ++i) { probit_draw_latents(s); sweep_once(s); } }
+ORC_API void orc_get_y(const orc_sampler *s, double *y) { memcpy(y, s->y, sizeof(double) * (size_t)s->n); }
 
 ORC_API int orc_max_threads(void)
 {

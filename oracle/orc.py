@@ -78,6 +78,14 @@ def lib():
         L.orc_mh_logratio.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, dp, dp, dp]
         L.orc_set_y.argtypes = [C.c_void_p, dp]
         L.orc_get_allfit.argtypes = [C.c_void_p, dp]
+        u8 = C.POINTER(C.c_uint8)
+        L.orc_probit_enable.argtypes = [C.c_void_p, u8, ip, C.c_double, C.c_int]
+        L.orc_probit_run.restype = C.c_int
+        L.orc_probit_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp]
+        L.orc_probit_sweeps.argtypes = [C.c_void_p, C.c_int]
+        L.orc_get_y.argtypes = [C.c_void_p, dp]
+        L.orc_probit_latent_probe.restype = C.c_double
+        L.orc_probit_latent_probe.argtypes = [C.c_double, C.c_int, C.c_double]
         L.orc_lil.restype = C.c_double
         L.orc_lil.argtypes = [C.c_double] * 3
         L.orc_lil_homosked.restype = C.c_double
@@ -261,6 +269,25 @@ class OracleSampler:
         lib().orc_get_allfit(self.h, _dp(o))
         return o
 
+    # ---- probit BART (create with ntree_mod = 0, use_muscale = False, y = zeros) ----
+    def probit_enable(self, ybin, rowid, offset=0.0, trt_col=-1):
+        yb = np.ascontiguousarray(ybin, dtype=np.uint8); ri = np.ascontiguousarray(rowid, dtype=np.int32)
+        assert yb.size == self.n and ri.size == self.n
+        lib().orc_probit_enable(self.h, yb.ctypes.data_as(C.POINTER(C.c_uint8)), _ip(ri), float(offset), int(trt_col))
+
+    def probit_sweeps(self, k=1):
+        lib().orc_probit_sweeps(self.h, int(k))
+
+    def probit_run(self, nburn, nsim, nthin=1):
+        ite = np.zeros(self.n); prob = np.zeros(self.n)
+        saved = lib().orc_probit_run(self.h, int(nburn), int(nsim), int(nthin), _dp(ite), _dp(prob))
+        return dict(ite_mean=ite, prob_mean=prob, saved=saved)
+
+    def get_y(self):
+        o = np.zeros(self.n)
+        lib().orc_get_y(self.h, _dp(o))
+        return o
+
     def hist_all(self, forest, slot, nleaf, r):
         off = self.oc if forest == 0 else self.om
         p = self.p_con if forest == 0 else self.p_mod
@@ -281,3 +308,7 @@ def lil_homosked(n, sy, sy2, sigma, tau):
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def probit_latent(m, y, u):
+    return lib().orc_probit_latent_probe(float(m), int(y), float(u))

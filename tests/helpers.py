@@ -98,3 +98,44 @@ def oracle_bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=No
     inv = P.inv_perm
     return {"tau_mean": P.sdy * out["tau_mean"][inv], "mu_mean": P.muy + P.sdy * out["mu_mean"][inv],
             "yhat_mean": P.muy + P.sdy * out["yhat_mean"][inv], "sigma": P.sdy * out["sigma"]}
+
+
+def oracle_probit_sampler(y01, X, treatment=None, seed=0, chain=0, n_trees=75, k=2.0, **kw):
+    """the CPU oracle set up as bcf_iv_b200.bart.probit_bart sets up the GPU sampler (same cutpoints, same Philox stream)"""
+    from oracle import orc
+    from bcf_iv_b200 import bart
+    y01 = np.asarray(y01, dtype=np.float64).ravel()
+    X = np.asarray(X, dtype=np.float64)
+    n = y01.size
+    if treatment is not None:
+        z = np.asarray(treatment).ravel().astype(np.int32)
+        xc = np.column_stack([X, z.astype(np.float64)])
+        trt_col = X.shape[1]
+    else:
+        z = np.zeros(n, dtype=np.int32)
+        xc = X
+        trt_col = -1
+    cuts = [bart.bart_cutpoints(xc[:, v]) for v in range(xc.shape[1])]
+    perm = np.argsort(-z, kind="stable")
+    o = orc.OracleSampler(np.zeros(n), int(z.sum()), xc[perm], np.zeros((n, 0)), cuts, [], ntree_con=n_trees, ntree_mod=0,
+                          con_sd=3.0 / k, use_muscale=False, use_tauscale=False, sigma_init=1.0, lambda_=1.0, seed=seed,
+                          chain=chain, **kw)
+    o.probit_enable(y01[perm], perm.astype(np.int32), 0.0, trt_col)
+    return o, perm
+
+
+def oracle_probit_bart(y01, X, treatment=None, n_samples=500, n_burn=500, n_thin=1, n_chains=2, seed=0, first_chain=0,
+                       devices=None, **bart_args):
+    """bart.probit_bart with the CPU oracle as the sampler (chains pooled the same way)"""
+    res = []
+    for c in range(n_chains):
+        o, perm = oracle_probit_sampler(y01, X, treatment, seed=seed, chain=first_chain + c, max_leaves=128, **bart_args)
+        out = o.probit_run(n_burn, n_samples, n_thin)
+        o.close()
+        inv = np.empty(perm.size, np.int64); inv[perm] = np.arange(perm.size)
+        res.append((out["prob_mean"][inv], out["ite_mean"][inv]))
+    r = {"prob_mean": np.mean([a for a, _ in res], axis=0)}
+    if treatment is not None:
+        r["ite_mean"] = np.mean([b for _, b in res], axis=0)
+        r["ite_var"] = np.zeros_like(r["ite_mean"])
+    return r

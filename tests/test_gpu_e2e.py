@@ -59,14 +59,19 @@ def test_bcf_iv_recovers_the_readme_subgroups():
     assert (leaves["Adj_pvalue"].astype(float) < 0.05).sum() >= 2
 
 
-def test_bcf_iv_binary_outcome_runs_through_the_gpu_sampler():
-    """BASELINE config 4 in small: binary outcome, low compliance, correlated covariates.  The reference uses bartc there
-    (R/bcf_iv.R:198); here the ITT on the probability scale is the tau of the GPU sampler on the 0/1 outcome.  The
-    effect cells (x1 = x2 = 0: y more often 1 under assignment; x1 = x2 = 1: less often) keep their signs."""
+@pytest.mark.parametrize("pic_model", ["bartc", "bcf"])
+def test_bcf_iv_binary_outcome_runs_through_the_gpu_sampler(pic_model):
+    """BASELINE config 4 in small: binary outcome, low compliance, correlated covariates.  The reference fits both the
+    complier proportion and the ITT with bartc there (R/bcf_iv.R:78, 198): probit BART on the GPU (pic_model = "bartc",
+    the default); "bcf" keeps the linear-probability stand-in.  The effect cells (x1 = x2 = 0: y more often 1 under
+    assignment; x1 = x2 = 1: less often) keep their signs."""
+    import warnings
     d = datasets.generate_dataset_wide(n=4000, p=10, rho=0.5, compliance=0.6, seed=3, binary_outcome=True)
     assert set(np.unique(d["y"])) <= {0.0, 1.0}
-    with pytest.warns(UserWarning, match="discrete"):
-        tab = bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], binary=True, n_burn=300, n_sim=300, max_depth=2, seed=42)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)               # ("y appears to be discrete": the bcf stand-in's preamble)
+        tab = bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], binary=True, n_burn=300, n_sim=300, max_depth=2, seed=42,
+                             pic_model=pic_model)
     assert list(tab.columns) == bayesiv.COLUMNS
     rules = " ".join(str(r) for r in tab["node"].dropna())
     assert "x1" in rules or "x2" in rules

@@ -1,14 +1,22 @@
 """Level-2 parity of BASELINE.json's north_star: "posterior mean CATE/ITT per observation, together with the bcf_iv CCACE,
 CITT, complier proportion and discovered subgroups on the README's generate_dataset workloads, agree with the reference
 within Monte Carlo standard error across seeds" -- the reference here being the CPU oracle (bcf itself cannot run:
-SURVEY 8c), driven through the IDENTICAL bcf_iv pipeline (tests/helpers.oracle_bcf), seeds 0..9; and level-1 parity at the
+SURVEY 8c), driven through the IDENTICAL bcf_iv pipeline (tests/helpers.oracle_bcf for the ITT forest, the oracle's probit
+BART behind bartc for the complier proportion), seeds 0..9; and level-1 parity at the
 sizes the first round left to engine-vs-engine checks: the headline shape (n = 1e6, p = 100) and continuous covariates at
 n = 1e5, move by move against the oracle; the oracle WITHOUT the GPU's structural cap of 128 leaves."""
 import numpy as np
 import pytest
 
 from bcf_iv_b200 import _lib, bayesiv, datasets, workload
-from helpers import gpu_sampler, make_problem, oracle_bcf, oracle_sampler
+from bcf_iv_b200 import bart
+from helpers import gpu_sampler, make_problem, oracle_bcf, oracle_probit_bart, oracle_sampler
+
+
+def oracle_bartc(*a, **k):
+    """bartc() with the CPU oracle's probit BART behind it"""
+    return bart.bartc(*a, fit=oracle_probit_bart, **k)
+
 
 pytestmark = pytest.mark.gpu
 
@@ -29,9 +37,10 @@ def test_readme_workload_gpu_twin_vs_oracle_twin_seeds_0_to_9():
     for seed in SEEDS:
         d = datasets.generate_dataset(n=1000, p=10, compliance=0.75, seed=100 + seed)
         row = {}
-        for who, fn in (("gpu", None), ("orc", oracle_bcf)):
+        for who, fn, bfn in (("gpu", None, None), ("orc", oracle_bcf, oracle_bartc)):
             det = {}
-            tab = bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], n_burn=nb, n_sim=ns, max_depth=2, seed=seed, bcf_fn=fn, details=det)
+            tab = bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], n_burn=nb, n_sim=ns, max_depth=2, seed=seed, bcf_fn=fn,
+                                 bartc_fn=bfn, details=det)
             cells = _cells(d["X"][det["disc"]])
             row[who] = dict(itt=np.array([det["itt"][c].mean() for c in cells]), pic=float(det["pic"].mean()),
                             pic_cells=np.array([det["pic"][c].mean() for c in cells]),
