@@ -41,7 +41,8 @@ bartc_ite <- function(response, treatment, confounders, n.samples = 500L, n.burn
   empty <- matrix(0, n, 0)
   chains <- .Call("bcfgpu_R_fit_chains", as.double(y01), z, xc, empty,
                   as.double(unlist(cuts)), as.integer(c(0L, cumsum(lengths(cuts)))), double(0), 0L,
-                  cfg, as.integer(n.burn), as.integer(n.samples), 1L, FALSE, as.integer(n.chains), as.integer(devices))
+                  cfg, as.integer(n.burn), as.integer(n.samples), 1L, FALSE, as.integer(n.chains), as.integer(devices),
+                  matrix(0, 0, 0), matrix(0, 0, 0))
   avg <- function(f) Reduce(`+`, lapply(chains, `[[`, f)) / length(chains)
   list(prob_mean = avg("mu_mean"), ite_mean = avg("tau_mean"))
 }

@@ -13,6 +13,7 @@ bcf <- function(y, z, x_control, x_moderate = x_control, pihat, nburn, nsim, nth
                 w = NULL, random_seed = sample.int(.Machine$integer.max, 1), n_chains = 1, n_cores = NULL,
                 n_threads = NULL, no_output = TRUE, save_tree_directory = NULL, log_file = NULL, verbose = FALSE,
                 device = -1L, devices = NULL, first_chain = 0L,
+                x_predict_control = NULL, x_predict_moderate = x_predict_control, pihat_predict = NULL,
                 keep_draws = 3 * 8 * as.double(length(y)) * nsim * n_chains <= 8 * 2^30) {
   # keep_draws: the three nsim x n matrices bcf returns (tau, mu, yhat) are kept only while they fit 8 GiB (the Python
   # twin's DRAW_BYTES_CAP); tau_mean / mu_mean / yhat_mean / tau_var -- what BayesIV consumes -- are always returned.
@@ -50,12 +51,21 @@ bcf <- function(y, z, x_control, x_moderate = x_control, pihat, nburn, nsim, nth
               use_muscale = as.integer(use_muscale), use_tauscale = as.integer(use_tauscale),
               seed = random_seed, chain = as.integer(first_chain), device = device)
   if (is.null(devices)) devices <- if (n_chains > 1) seq_len(.Call("bcfgpu_R_device_count")) - 1L else as.integer(device)
+  # bcf 2.x's predict() in the same call: new rows at which every saved sweep's forests are evaluated on the device
+  xp_c <- xp_m <- matrix(0, 0, 0)
+  if (!is.null(x_predict_control)) {
+    php <- if (is.null(pihat_predict)) NULL else as.matrix(pihat_predict)
+    if (include_pi != "none" && is.null(php)) stop("predicting needs pihat_predict")
+    xp_c <- if (include_pi %in% c("control", "both")) cbind(as.matrix(x_predict_control), php) else as.matrix(x_predict_control)
+    xp_m <- if (include_pi %in% c("moderate", "both")) cbind(as.matrix(x_predict_moderate), php) else as.matrix(x_predict_moderate)
+    storage.mode(xp_c) <- "double"; storage.mode(xp_m) <- "double"
+  }
   # all chains in ONE native call: the library runs them concurrently, chain c on devices[c mod length(devices)]
   chains <- .Call("bcfgpu_R_fit_chains", as.double(yscale), as.integer(z), x_c, x_m,
                   as.double(unlist(cut_c)), as.integer(c(0L, cumsum(lengths(cut_c)))),
                   as.double(unlist(cut_m)), as.integer(c(0L, cumsum(lengths(cut_m)))),
                   cfg, as.integer(nburn), as.integer(nsim), as.integer(nthin), isTRUE(keep_draws),
-                  as.integer(n_chains), as.integer(devices))
+                  as.integer(n_chains), as.integer(devices), xp_c, xp_m)
   bind <- function(f) do.call(rbind, lapply(chains, function(r) t(r[[f]])))      # n x nsim -> nsim x n, chains stacked
   avg <- function(f) Reduce(`+`, lapply(chains, `[[`, f)) / length(chains)
   # variance of the STACKED draws (what fit$tau holds): within-chain sums of squares plus the spread of the chain means
@@ -70,6 +80,9 @@ bcf <- function(y, z, x_control, x_moderate = x_control, pihat, nburn, nsim, nth
               perm = perm,
               tau_mean = sdy * avg("tau_mean"), mu_mean = muy + sdy * avg("mu_mean"),
               yhat_mean = muy + sdy * avg("yhat_mean"), tau_var = sdy^2 * pooled_var())
+  if (nrow(xp_c) > 0) {
+    fit$tau_predict_mean <- sdy * avg("tau_predict_mean"); fit$mu_predict_mean <- muy + sdy * avg("mu_predict_mean")
+  }
   if (isTRUE(keep_draws)) {
     fit$tau <- sdy * bind("tau"); fit$mu <- muy + sdy * bind("mu"); fit$yhat <- muy + sdy * bind("yhat")
   }

@@ -60,7 +60,7 @@ SEXP bcfgpu_R_device_count(void) { return Rf_ScalarInteger(bcfgpu_device_count()
 
 /* results of one finished chain -> list(tau_mean, tau_var, mu_mean, yhat_mean, sigma, mu_scale, tau_scale, tau, mu, yhat,
  * device_ms) on the standardised scale; tau / mu / yhat are n x nsaved matrices when keep, else NULL */
-static SEXP chain_result(bcfgpu_handle **hs, int nh, int c, R_xlen_t n, int keep)
+static SEXP chain_result(bcfgpu_handle **hs, int nh, int c, R_xlen_t n, int keep, SEXP xpc, SEXP xpm)
 {
     bcfgpu_handle *h = hs[c];
     double ms = 0;
@@ -68,7 +68,7 @@ static SEXP chain_result(bcfgpu_handle **hs, int nh, int c, R_xlen_t n, int keep
     int32_t ns = 0;
     check(bcfgpu_num_saved(h, &ns), hs, nh);
     const char *nm[] = {"tau_mean", "tau_var", "mu_mean", "yhat_mean", "sigma", "mu_scale", "tau_scale", "tau", "mu",
-                        "yhat", "device_ms", ""};
+                        "yhat", "device_ms", "tau_predict_mean", "tau_predict_var", "mu_predict_mean", ""};
     SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
     SEXP v;
     v = PROTECT(Rf_allocVector(REALSXP, n)); check(bcfgpu_get_tau_mean(h, REAL(v)), hs, nh); SET_VECTOR_ELT(out, 0, v); UNPROTECT(1);
@@ -93,22 +93,31 @@ static SEXP chain_result(bcfgpu_handle **hs, int nh, int c, R_xlen_t n, int keep
         }
     }
     SET_VECTOR_ELT(out, 10, Rf_ScalarReal(ms));
+    if (Rf_isMatrix(xpc) && Rf_nrows(xpc) > 0) {   /* bcf 2.x's predict(): the saved forests at new rows (keep_draws bit 3) */
+        const int m = Rf_nrows(xpc);
+        SEXP a = PROTECT(Rf_allocVector(REALSXP, m)), b = PROTECT(Rf_allocVector(REALSXP, m)), d = PROTECT(Rf_allocVector(REALSXP, m));
+        check(bcfgpu_predict(h, (int64_t)m, REAL(xpc), Rf_isMatrix(xpm) && Rf_ncols(xpm) > 0 ? REAL(xpm) : NULL, REAL(a), REAL(b),
+                             REAL(d), NULL, NULL), hs, nh);
+        SET_VECTOR_ELT(out, 11, a); SET_VECTOR_ELT(out, 12, b); SET_VECTOR_ELT(out, 13, d);
+        UNPROTECT(3);
+    }
     UNPROTECT(1);
     return out;
 }
 
 /*
  * .Call("bcfgpu_R_fit_chains", yscale, z, x_c, x_m, cuts_c, off_c, cuts_m, off_m, cfg, nburn, nsim, nthin, keep_draws,
- *       n_chains, devices)
+ *       n_chains, devices, x_predict_control, x_predict_moderate)
  *   yscale  numeric n      standardised outcome            z       integer n (0/1)
  *   x_c/x_m numeric matrices n x p_con / n x p_mod (column-major, as R stores them)
  *   cuts_*  numeric        concatenated cutpoints          off_*   integer p+1 offsets
  *   cfg     named list     the bcfgpu_config fields that differ from bcf's defaults (chain = first Philox stream)
  *   devices integer        CUDA ordinals the chains are dealt over (chain c on devices[c %% length]); they run at once
+ *   x_predict_*  numeric matrices (0 rows: none): new rows at which the saved forests are evaluated (bcf 2.x's predict())
  * Returns a list of n_chains per-chain results (see chain_result).
  */
 SEXP bcfgpu_R_fit_chains(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off_c, SEXP cuts_m, SEXP off_m, SEXP cfg_list,
-                         SEXP nburn_, SEXP nsim_, SEXP nthin_, SEXP keep_, SEXP nchains_, SEXP devices_)
+                         SEXP nburn_, SEXP nsim_, SEXP nthin_, SEXP keep_, SEXP nchains_, SEXP devices_, SEXP xpc, SEXP xpm)
 {
     const R_xlen_t n = Rf_xlength(y);
     if (!Rf_isReal(y) || !Rf_isInteger(z) || !Rf_isMatrix(xc) || !Rf_isReal(xc) || !Rf_isMatrix(xm) || !Rf_isReal(xm))
@@ -146,6 +155,12 @@ SEXP bcfgpu_R_fit_chains(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off
     cfg.treatment_col = (int32_t)num(cfg_list, "treatment_col", -1);
     cfg.probit_offset = num(cfg_list, "probit_offset", 0.0);
     cfg.keep_draws = keep ? 7 : 0;
+    const int predict = Rf_isMatrix(xpc) && Rf_nrows(xpc) > 0;
+    if (predict) {
+        if (Rf_ncols(xpc) != p_con || (p_mod > 0 && (!Rf_isMatrix(xpm) || Rf_ncols(xpm) != p_mod || Rf_nrows(xpm) != Rf_nrows(xpc))))
+            Rf_error("bcfgpu_R_fit_chains: the rows to predict at must have the training columns");
+        cfg.keep_draws |= 8;
+    }
 
     bcfgpu_handle **hs = (bcfgpu_handle **)calloc((size_t)nch, sizeof(bcfgpu_handle *));
     if (!hs) Rf_error("bcfgpu_R_fit_chains: out of memory");
@@ -154,7 +169,7 @@ SEXP bcfgpu_R_fit_chains(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off
                             REAL(xc), REAL(xm), REAL(cuts_c), INTEGER(off_c), REAL(cuts_m), INTEGER(off_m), nburn, nsim,
                             nthin, interrupt_pending, NULL, hs), hs, nch);
     SEXP out = PROTECT(Rf_allocVector(VECSXP, nch));
-    for (int c = 0; c < nch; ++c) SET_VECTOR_ELT(out, c, chain_result(hs, nch, c, n, keep));
+    for (int c = 0; c < nch; ++c) SET_VECTOR_ELT(out, c, chain_result(hs, nch, c, n, keep, xpc, xpm));
     destroy_all(hs, nch);
     free(hs);
     UNPROTECT(1);
@@ -163,7 +178,7 @@ SEXP bcfgpu_R_fit_chains(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off
 
 static const R_CallMethodDef call_methods[] = {
     {"bcfgpu_R_device_count", (DL_FUNC)&bcfgpu_R_device_count, 0},
-    {"bcfgpu_R_fit_chains", (DL_FUNC)&bcfgpu_R_fit_chains, 15},
+    {"bcfgpu_R_fit_chains", (DL_FUNC)&bcfgpu_R_fit_chains, 17},
     {NULL, NULL, 0}};
 
 void R_init_BayesIVgpu(DllInfo *dll)

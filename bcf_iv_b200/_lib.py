@@ -26,7 +26,7 @@ SYMBOLS = [
     "bcfgpu_fit_chains",
     "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_h2d_bytes", "bcfgpu_engine_in_use", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
     "bcfgpu_get_mu_mean", "bcfgpu_get_yhat_mean", "bcfgpu_get_sigma", "bcfgpu_get_scales", "bcfgpu_get_draws",
-    "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
+    "bcfgpu_num_saved_forests", "bcfgpu_predict", "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
     "bcfgpu_get_tree", "bcfgpu_set_tree", "bcfgpu_get_leaf_ids", "bcfgpu_verify_leaf_cache", "bcfgpu_op_bin_column",
     "bcfgpu_op_suffstats", "bcfgpu_op_hist_all", "bcfgpu_op_lil", "bcfgpu_op_rng_probe", "bcfgpu_op_probit_latent",
 ]
@@ -97,6 +97,8 @@ def load():
         getattr(L, "bcfgpu_get_" + nm).argtypes = [vp, dp]
     L.bcfgpu_get_scales.argtypes = [vp, dp, dp]
     L.bcfgpu_get_draws.argtypes = [vp, C.c_int32, dp]
+    L.bcfgpu_num_saved_forests.argtypes = [vp, ip, lp]
+    L.bcfgpu_predict.argtypes = [vp, C.c_int64, dp, dp, dp, dp, dp, dp, dp]
     L.bcfgpu_get_scalars.argtypes = [vp, dp]
     L.bcfgpu_get_fits.argtypes = [vp, dp, dp]
     L.bcfgpu_get_counters.argtypes = [vp, lp]
@@ -307,6 +309,30 @@ class Sampler:
         o = np.zeros((self.num_saved, self.n))
         check(load().bcfgpu_get_draws(self._h, idx, _dp(o)))
         return o
+
+    @property
+    def saved_forests(self):
+        """(draws whose forests are kept on the device, nodes they hold)"""
+        a = C.c_int32(); b = C.c_int64()
+        check(load().bcfgpu_num_saved_forests(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def predict(self, x_con_new, x_mod_new=None, draws=False):
+        """tau(x), mu(x) of the saved forests at new rows (standardised scale): dict(tau_mean, tau_var, mu_mean[, tau, mu])"""
+        xc = np.asfortranarray(x_con_new, dtype=np.float64)
+        xm = np.asfortranarray(x_mod_new, dtype=np.float64) if x_mod_new is not None else None
+        m = xc.shape[0]
+        if xc.shape[1] != self.p_con or (self.p_mod > 0 and (xm is None or xm.shape != (m, self.p_mod))):
+            raise ValueError("new rows must have the training columns")
+        out = {k: np.zeros(m) for k in ("tau_mean", "tau_var", "mu_mean")}
+        td = md = None
+        if draws:
+            ns = self.saved_forests[0]
+            td = np.zeros((ns, m)); md = np.zeros((ns, m))
+            out.update(tau=td, mu=md)
+        check(load().bcfgpu_predict(self._h, m, _dp(xc), _dp(xm), _dp(out["tau_mean"]), _dp(out["tau_var"]), _dp(out["mu_mean"]),
+                                    _dp(td), _dp(md)))
+        return out
 
     def scalars(self):
         o = np.zeros(8)

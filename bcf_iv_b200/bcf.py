@@ -20,13 +20,15 @@ from . import _lib, prep
 DRAW_BYTES_CAP = 8 << 30   # keep nsim x n draws on the device only below this (3 matrices of doubles)
 
 
-def _collect(s, keep):
+def _collect(s, keep, pred=None):
     """what bcf() returns from one finished chain (a _lib.Sampler); always closes it"""
     try:
         r = {"sigma": s.sigma(), "scales": s.scales(), "tau_mean": s.tau_mean(), "mu_mean": s.mu_mean(),
              "yhat_mean": s.yhat_mean(), "tau_var": s.tau_var(), "ms": s.last_run_ms, "moves": s.counters()}
         if keep:
             r["tau"], r["mu"], r["yhat"] = s.draws("tau"), s.draws("mu"), s.draws("yhat")
+        if pred is not None:
+            r["pred"] = s.predict(pred[0], pred[1], draws=pred[2])
         return r
     finally:
         s.close()
@@ -38,7 +40,8 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
         nu=3.0, lambda_=None, sigq=0.9, sighat=None, include_pi="control", use_muscale=True, use_tauscale=True,
         w=None, random_seed=None, n_chains=1, n_cores=None, n_threads=None, no_output=True,
         save_tree_directory=None, log_file=None, verbose=False,
-        devices=None, keep_draws=None, engine=_lib.ENGINE_AUTO, max_ctas=0, first_chain=0):
+        devices=None, keep_draws=None, engine=_lib.ENGINE_AUTO, max_ctas=0, first_chain=0,
+        x_predict_control=None, x_predict_moderate=None, pihat_predict=None, predict_draws=False):
     """Fit the Bayesian Causal Forest  y = mu(x, pihat) + tau(x) z + eps  on the GPU.
 
     Returns a dict with bcf's fields: `sigma` (nsim*n_chains), `yhat`, `mu`, `tau` (nsim*n_chains x n, original row
@@ -48,7 +51,10 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
     Extras beyond bcf's signature: `devices` (CUDA ordinals, chains are dealt round-robin: one independent chain per
     GPU), `keep_draws` (None = keep the three nsim x n matrices only while they fit DRAW_BYTES_CAP),
     `engine`, `max_ctas` (0 = the whole GPU; k > 0 = at most k CTAs, so that several fits can run side by side on one GPU),
-    `first_chain` (Philox stream of the first chain; chain c uses first_chain + c).  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
+    `first_chain` (Philox stream of the first chain; chain c uses first_chain + c);
+    `x_predict_control` / `x_predict_moderate` / `pihat_predict` (bcf 2.x's predict() in the same call): new covariate rows at
+    which every saved sweep's forests are evaluated on the device -> `tau_predict_mean`, `tau_predict_var`,
+    `mu_predict_mean` (and `tau_predict`, `mu_predict`: nsim*n_chains x n_new with predict_draws=True), original y units.  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
     no_output, verbose, update_interval) are accepted and ignored; observation weights `w` are not implemented.
     """
     if nburn is None or nsim is None:
@@ -88,12 +94,23 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
     if per_dev > 1 and int(max_ctas) == 0 and share >= 1 and n <= 27 * 256 * share - 512:
         cfg["max_ctas"] = share
     cfg["chain"] = int(first_chain)
+    pred = None
+    if x_predict_control is not None:
+        xpc = np.asarray(x_predict_control, dtype=np.float64)
+        xpm = np.asarray(x_predict_moderate if x_predict_moderate is not None else x_predict_control, dtype=np.float64)
+        php = np.asarray(pihat_predict, dtype=np.float64).reshape(xpc.shape[0], -1) if pihat_predict is not None else None
+        if include_pi != "none" and php is None:
+            raise TypeError("predicting needs pihat_predict (include_pi != 'none')")
+        xc_new = np.column_stack([xpc, php]) if include_pi in ("control", "both") else xpc
+        xm_new = np.column_stack([xpm, php]) if include_pi in ("moderate", "both") else xpm
+        pred = (xc_new, xm_new, bool(predict_draws))
+        cfg["keep_draws"] |= 8                                # keep every saved sweep's forests on the device
     samplers = _lib.fit_chains(cfg, int(n_chains), devs, P.yscale, P.z, P.x_c, P.x_m, cc, oc, cm, om, int(nburn), int(nsim),
                                int(nthin))
     res, err = [], None
     for smp in samplers:                                      # every handle is closed even if one read-back fails
         try:
-            res.append(_collect(smp, keep_draws))
+            res.append(_collect(smp, keep_draws, pred))
         except BaseException as e:
             err = err or e
     if err is not None:
@@ -117,6 +134,15 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
         "device_ms": [r["ms"] for r in res],
         "moves": [r["moves"] for r in res],
     }
+    if pred is not None:
+        pm = np.mean([r["pred"]["tau_mean"] for r in res], axis=0)
+        out["tau_predict_mean"] = sdy * pm
+        out["mu_predict_mean"] = muy + sdy * np.mean([r["pred"]["mu_mean"] for r in res], axis=0)
+        out["tau_predict_var"] = sdy ** 2 * (sum((ns - 1) * r["pred"]["tau_var"] + ns * (r["pred"]["tau_mean"] - pm) ** 2
+                                                 for r in res) / (ntot - 1) if ntot > 1 else np.zeros_like(pm))
+        if predict_draws:
+            out["tau_predict"] = sdy * np.concatenate([r["pred"]["tau"] for r in res], axis=0)
+            out["mu_predict"] = muy + sdy * np.concatenate([r["pred"]["mu"] for r in res], axis=0)
     if keep_draws:                                            # chains rbind-ed, as bcf 2.x does
         out["tau"] = sdy * np.concatenate([r["tau"] for r in res], axis=0)
         out["mu"] = muy + sdy * np.concatenate([r["mu"] for r in res], axis=0)

@@ -1020,6 +1020,83 @@ __global__ void k_probit_probe(const double* m, const int* y, const double* u, i
     if (i < n) out[i] = probit_latent_d(m[i], y[i], u[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Saved forests and out-of-sample evaluation (bcf's `$tau` contract beyond colMeans, and predict()).
+// keep_draws bit 3: after every saved sweep its trees are compacted into a node pool on the device (16 bytes per node:
+// split rule or leaf value, children as node indices), together with the sweep's signed scales; bcfgpu_predict() bins new
+// covariate rows with the training cutpoints (K0) and walks every saved forest over them.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) SavedNode { uint16_t var, cut; int16_t left, right; double mu; };    // leaf: left = -1, mu = leaf value
+struct SavedDraw { double mscale, bscale1, bscale0, pad_; };
+// one CTA per tree: the draw's tree `blockIdx.x` -> pool (bump allocation: the order of the trees in the pool is arbitrary,
+// their offsets are recorded).  off[draw * (T + 1) + tree] = first node, count in cnt[...].
+__global__ void k_save_trees(Dev d, const TreeRec* __restrict__ trees, int draw, SavedNode* pool, long long pool_cap,
+                             unsigned long long* pool_used, long long* off, int32_t* cnt, SavedDraw* scal)
+{
+    __shared__ long long base;
+    const TreeRec& tr = trees[blockIdx.x];
+    const int nn = __ldcg(&tr.nnodes);
+    if (threadIdx.x == 0) {
+        const unsigned long long b = atomicAdd(pool_used, (unsigned long long)nn);
+        base = (b + (unsigned long long)nn <= (unsigned long long)pool_cap) ? (long long)b : -1;
+        off[(size_t)draw * d.T + blockIdx.x] = base;
+        cnt[(size_t)draw * d.T + blockIdx.x] = nn;
+        if (blockIdx.x == 0) { const Scalars sc = *d.sc; scal[draw] = SavedDraw{sc.mscale, sc.bscale1, sc.bscale0, 0.0}; }
+    }
+    __syncthreads();
+    if (base < 0) return;                                          // pool exhausted: predict reports it
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+        SavedNode nd;
+        nd.left = __ldcg(&tr.left[i]); nd.right = __ldcg(&tr.right[i]);
+        nd.var = __ldcg(&tr.var[i]); nd.cut = __ldcg(&tr.cut[i]);
+        nd.mu = nd.left < 0 ? __ldcg(&tr.mu[__ldcg(&tr.node_slot[i])]) : 0.0;
+        pool[base + i] = nd;
+    }
+}
+// K0 for new rows: no permutation, every column as uint16, [col][n]
+__global__ void k_bin_plain(const double* __restrict__ x, int64_t n, int p, const double* __restrict__ cuts,
+                            const int32_t* __restrict__ off, uint16_t* __restrict__ out)
+{
+    const int v = blockIdx.y;
+    if (v >= p) return;
+    const double* cv = cuts + off[v];
+    const int nc = off[v + 1] - off[v];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)v * n + i] = (uint16_t)upper_bound_cut(cv, nc, x[(int64_t)v * n + i]);
+}
+// one thread per new row, draws [d0, d1): sum over the draw's trees of the leaf the row falls in, per forest; accumulates
+// mean / second moment of tau = (bscale1 - bscale0) * g_mod and of mu = mscale * g_con, optionally every draw
+__global__ void __launch_bounds__(128) k_predict(int64_t n, int T, int ntree_con, int d0, int d1, const SavedNode* __restrict__ pool,
+                                                 const long long* __restrict__ off, const SavedDraw* __restrict__ scal,
+                                                 const uint16_t* __restrict__ bc, const uint16_t* __restrict__ bm,
+                                                 double* tau_sum, double* tau_sq, double* mu_sum, double* tau_draws, double* mu_draws)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ts = 0.0, tq = 0.0, ms = 0.0;
+    for (int dr = d0; dr < d1; ++dr) {
+        double g[2] = {0.0, 0.0};
+        for (int t = 0; t < T; ++t) {
+            const long long b = off[(size_t)dr * T + t];
+            const int f = t >= ntree_con ? 1 : 0;
+            const uint16_t* bins = f ? bm : bc;
+            int node = 0;
+            SavedNode nd = pool[b];
+            while (nd.left >= 0) {
+                node = ((int)bins[(int64_t)nd.var * n + i] <= (int)nd.cut) ? nd.left : nd.right;
+                nd = pool[b + node];
+            }
+            g[f] += nd.mu;
+        }
+        const SavedDraw sd = scal[dr];
+        const double tau = (sd.bscale1 - sd.bscale0) * g[1], mu = sd.mscale * g[0];
+        ts += tau; tq += tau * tau; ms += mu;
+        if (tau_draws) tau_draws[(int64_t)dr * n + i] = tau;
+        if (mu_draws) mu_draws[(int64_t)dr * n + i] = mu;
+    }
+    tau_sum[i] += ts; tau_sq[i] += tq; mu_sum[i] += ms;
+}
+
 __global__ void k_lil(const double* a, const double* b, const double* tau, int m, double* out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -136,6 +136,10 @@ struct bcfgpu_handle {
     double last_ms = 0.0;
     int32_t nsaved = 0, post_cap = 0;
     int keep = 0;
+    // saved forests (keep_draws bit 3): node pool of the last run, per (draw, tree) offsets, per-draw scales
+    SavedNode* d_pool = nullptr; long long pool_cap = 0; unsigned long long* d_pool_used = nullptr;
+    long long* d_tree_off = nullptr; int32_t* d_tree_cnt = nullptr; SavedDraw* d_draw_scal = nullptr;
+    int32_t forests_saved = 0;
     uint8_t* d_ybin = nullptr;        // probit BART: the observed 0/1 response, internal order
     int* d_cflist = nullptr;          // probit BART: trees that split on the treatment (k_cf_collect)
     std::atomic<int> stop{0};         // bcfgpu_request_stop: the run in progress ends at its next launch boundary
@@ -933,6 +937,19 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
         if (h->keep & 2) DM(h, &d.draws_mu, (size_t)nsim * d.n_pad, true);
         if (h->keep & 4) DM(h, &d.draws_yhat, (size_t)nsim * d.n_pad, true);
     }
+    h->d_pool = nullptr; h->forests_saved = 0; h->pool_cap = 0;
+    const bool keep_trees = (h->keep & 8) && nsim > 0 && h->cfg.model == BCFGPU_MODEL_BCF;
+    if (keep_trees) {
+        if (h->nranks > 1) return fail(BCFGPU_ERR_BAD_ARG, "saved forests (keep_draws bit 3) are not available in the sharded mode");
+        // trees average 2 - 3 nodes at stationarity: room for 12 per tree and draw, at most 4 GiB
+        h->pool_cap = std::min<long long>((long long)nsim * h->T * 12, ((long long)4 << 30) / (long long)sizeof(SavedNode));
+        DM(h, &h->d_pool, (size_t)h->pool_cap, true);
+        DM(h, &h->d_pool_used, 2, true);
+        DM(h, &h->d_tree_off, (size_t)nsim * h->T, true);
+        DM(h, &h->d_tree_cnt, (size_t)nsim * h->T, true);
+        DM(h, &h->d_draw_scal, (size_t)nsim, true);
+        CK(cudaMemsetAsync(h->d_pool_used, 0, 16, h->stream));
+    }
     CK(cudaMemsetAsync(d.tau_sum, 0, (size_t)d.n_pad * 8, h->stream));
     CK(cudaMemsetAsync(d.tau_sq, 0, (size_t)d.n_pad * 8, h->stream));
     CK(cudaMemsetAsync(d.mu_sum, 0, (size_t)d.n_pad * 8, h->stream));
@@ -1016,6 +1033,23 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
             }
         }
         if (rc == BCFGPU_OK) CK(cudaGetLastError());
+    } else if (keep_trees) {
+        // the sampling part runs one sweep per launch so that the trees of every saved sweep can be copied out between
+        // launches (the engines keep only the current forest)
+        rc = launch_sweeps(nburn);
+        int saved = 0;
+        for (int it = nburn; it < total && rc == BCFGPU_OK; ++it) {
+            rc = launch_sweeps(1);
+            if (rc == BCFGPU_OK && (it % nthin) == 0 && saved < nsim) {
+                const int par = (sc.parity + it + 1) & 1;
+                k_save_trees<<<h->T, 64, 0, h->stream>>>(d, d.trees[par], saved, h->d_pool, h->pool_cap, h->d_pool_used,
+                                                         h->d_tree_off, h->d_tree_cnt, h->d_draw_scal);
+                h->launches++;
+                ++saved;
+            }
+        }
+        if (rc == BCFGPU_OK) CK(cudaGetLastError());
+        h->forests_saved = saved;
     } else
         rc = launch_sweeps(total);
     if (rc) { cudaStreamSynchronize(h->stream); return rc; }
@@ -1758,6 +1792,96 @@ static int run_persistent(bcfgpu_handle* h, int total)
         }
         h->launches++;
         done += nsw;
+    }
+    return BCFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out-of-sample evaluation of the saved forests (bcf 2.x's predict(): tau(x), mu(x) at new covariate rows)
+// ------------------------------------------------------------------------------------------------
+static int bin_new_rows(bcfgpu_handle* h, const ForestHost& F, const double* x, int64_t n, uint16_t* d_out)
+{
+    const size_t colb = (size_t)n * 8;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)F.p, STAGE_BYTES / colb));
+    Block stage;
+    if (dev_alloc(h->device, (size_t)chunk * colb, &stage) != cudaSuccess) return fail(BCFGPU_ERR_OOM, "staging buffer of predict");
+    cudaError_t e = cudaSuccess;
+    for (int c0 = 0; c0 < F.p && e == cudaSuccess; c0 += chunk) {
+        const int nc = std::min(chunk, F.p - c0);
+        e = cudaMemcpyAsync(stage.p, x + (size_t)c0 * n, (size_t)nc * colb, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) break;
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 4096)), (unsigned)nc);
+        k_bin_plain<<<grid, 256, 0, h->stream>>>((const double*)stage.p, n, nc, F.d_cuts, F.d_off + c0, d_out + (size_t)c0 * n);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    dev_free(h->device, stage);
+    if (e != cudaSuccess) return fail(BCFGPU_ERR_CUDA, std::string("predict: binning the new rows: ") + cudaGetErrorString(e));
+    return BCFGPU_OK;
+}
+
+extern "C" int bcfgpu_num_saved_forests(bcfgpu_handle* h, int32_t* ndraws, int64_t* nnodes)
+{
+    USE(h); NEED_DATA(h);
+    if (ndraws) *ndraws = h->forests_saved;
+    if (nnodes) {
+        unsigned long long used = 0;
+        if (h->d_pool_used) CK(cudaMemcpy(&used, h->d_pool_used, 8, cudaMemcpyDeviceToHost));
+        *nnodes = (int64_t)used;
+    }
+    return BCFGPU_OK;
+}
+
+extern "C" int bcfgpu_predict(bcfgpu_handle* h, int64_t n_new, const double* xcon_new, const double* xmod_new, double* tau_mean,
+                              double* tau_var, double* mu_mean, double* tau_draws, double* mu_draws)
+{
+    USE(h); NEED_DATA(h);
+    if (n_new < 1 || !xcon_new) return fail(BCFGPU_ERR_BAD_ARG, "bad argument");
+    if (h->forests_saved < 1 || !h->d_pool) return fail(BCFGPU_ERR_STATE, "no saved forests: run with keep_draws bit 3 (8) set and nsim >= 1");
+    const ForestHost &Fc = h->fh[0], &Fm = h->fh[1];
+    if (Fm.p > 0 && !xmod_new) return fail(BCFGPU_ERR_BAD_ARG, "the moderate forest needs x_moderate rows");
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long used = 0;
+    CK(cudaMemcpy(&used, h->d_pool_used, 8, cudaMemcpyDeviceToHost));
+    if ((long long)used > h->pool_cap) return fail(BCFGPU_ERR_OOM, "the saved forests outgrew their node pool (trees much larger than expected)");
+    const int ns = h->forests_saved;
+    Block bc{nullptr, 0}, bm{nullptr, 0}, acc{nullptr, 0}, dr{nullptr, 0};
+    int rc = BCFGPU_OK;
+    auto cleanup = [&]() { dev_free(h->device, bc); dev_free(h->device, bm); dev_free(h->device, acc); dev_free(h->device, dr); };
+    if (dev_alloc(h->device, (size_t)Fc.p * n_new * 2, &bc) != cudaSuccess || dev_alloc(h->device, (size_t)std::max(Fm.p, 1) * n_new * 2, &bm) != cudaSuccess ||
+        dev_alloc(h->device, (size_t)n_new * 8 * 3, &acc) != cudaSuccess) { cleanup(); return fail(BCFGPU_ERR_OOM, "predict: device buffers"); }
+    if ((rc = bin_new_rows(h, Fc, xcon_new, n_new, (uint16_t*)bc.p)) || (Fm.p > 0 && (rc = bin_new_rows(h, Fm, xmod_new, n_new, (uint16_t*)bm.p)))) { cleanup(); return rc; }
+    double* a = (double*)acc.p;
+    cudaError_t e = cudaMemsetAsync(a, 0, (size_t)n_new * 8 * 3, h->stream);
+    // draws leave in chunks, so that the device never holds more than ~512 MB of them
+    const bool want_draws = tau_draws || mu_draws;
+    const int per = want_draws ? (int)std::max<int64_t>(1, std::min<int64_t>(ns, ((int64_t)256 << 20) / (n_new * 8))) : ns;
+    if (want_draws && dev_alloc(h->device, (size_t)per * n_new * 8 * 2, &dr) != cudaSuccess) { cleanup(); return fail(BCFGPU_ERR_OOM, "predict: draw buffers"); }
+    double* dt = (double*)dr.p;
+    double* dm = dt ? dt + (size_t)per * n_new : nullptr;
+    const unsigned grid = (unsigned)((n_new + 127) / 128);
+    for (int d0 = 0; d0 < ns && e == cudaSuccess; d0 += per) {
+        const int d1 = std::min(ns, d0 + per);
+        k_predict<<<grid, 128, 0, h->stream>>>(n_new, h->T, h->cfg.ntree_con, d0, d1, h->d_pool, h->d_tree_off, h->d_draw_scal,
+                                               (const uint16_t*)bc.p, (const uint16_t*)bm.p, a, a + n_new, a + 2 * n_new,
+                                               tau_draws ? dt - (size_t)d0 * n_new : nullptr, mu_draws ? dm - (size_t)d0 * n_new : nullptr);
+        h->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess && tau_draws) e = cudaMemcpyAsync(tau_draws + (size_t)d0 * n_new, dt, (size_t)(d1 - d0) * n_new * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && mu_draws) e = cudaMemcpyAsync(mu_draws + (size_t)d0 * n_new, dm, (size_t)(d1 - d0) * n_new * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && want_draws) e = cudaStreamSynchronize(h->stream);
+    }
+    std::vector<double> host((size_t)n_new * 3);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), a, (size_t)n_new * 8 * 3, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(BCFGPU_ERR_CUDA, std::string("predict: ") + cudaGetErrorString(e));
+    for (int64_t i = 0; i < n_new; ++i) {
+        const double m = host[(size_t)i] / ns;
+        if (tau_mean) tau_mean[i] = m;
+        if (tau_var) tau_var[i] = ns > 1 ? std::max(0.0, (host[(size_t)n_new + i] - ns * m * m) / (ns - 1)) : 0.0;
+        if (mu_mean) mu_mean[i] = host[(size_t)2 * n_new + i] / ns;
     }
     return BCFGPU_OK;
 }

@@ -83,7 +83,8 @@ typedef struct bcfgpu_config {
     uint32_t chain;               /* chain index: mixes into the key (one chain per GPU in chains mode) */
     int32_t device;               /* CUDA ordinal; -1 = current device */
     int32_t engine;               /* bcfgpu_engine */
-    int32_t keep_draws;           /* bit0 tau, bit1 mu, bit2 yhat: keep nsim x n draws on device */
+    int32_t keep_draws;           /* bit0 tau, bit1 mu, bit2 yhat: keep nsim x n draws on device; bit3 (8): keep the FORESTS of
+                                   * every saved sweep on the device (bcfgpu_predict) */
     int32_t max_ctas;             /* 0: one CTA per SM.  > 0: at most that many CTAs, so that several fits can share one GPU
                                    * side by side (bcf_iv fits the complier proportion and the ITT at the same time) */
     int32_t model;                /* bcfgpu_model: 0 = Bayesian Causal Forest (bcf), 1 = probit BART (bartCause::bartc's sampler) */
@@ -176,6 +177,16 @@ BCFGPU_API int bcfgpu_get_sigma(bcfgpu_handle *h, double *out_nsaved);
 BCFGPU_API int bcfgpu_get_scales(bcfgpu_handle *h, double *mu_scale_nsaved, double *tau_scale_nsaved);
 /* which: 0 tau, 1 mu, 2 yhat; out is nsaved x n ROW-major per draw (draw-major), needs keep_draws */
 BCFGPU_API int bcfgpu_get_draws(bcfgpu_handle *h, int32_t which, double *out_nsaved_by_n);
+
+/* ---- saved forests and out-of-sample evaluation (bcf 2.x's predict(); needs keep_draws bit 3 in the run) ----------
+ * For every saved sweep s and every new row: mu(x) = mscale_s * sum of the mu trees' leaves, tau(x) = (bscale1_s -
+ * bscale0_s) * sum of the tau trees' leaves, on the standardised scale (the R wrapper rescales as for the fit).
+ * xcon_new / xmod_new: column-major n_new x p_con / n_new x p_mod, binned with the training cutpoints (K0).
+ * Any output may be NULL; *_draws are nsaved x n_new, draw-major.  With keep_draws bit 3 the sampling part of the run is
+ * launched sweep by sweep (the forest of each saved sweep is copied into a node pool between launches). */
+BCFGPU_API int bcfgpu_num_saved_forests(bcfgpu_handle *h, int32_t *ndraws, int64_t *nnodes);
+BCFGPU_API int bcfgpu_predict(bcfgpu_handle *h, int64_t n_new, const double *xcon_new, const double *xmod_new,
+                              double *tau_mean, double *tau_var, double *mu_mean, double *tau_draws, double *mu_draws);
 
 /* ---- chain state (parity tests, checkpoints, predict) ------------------------------------------ */
 /* scalars: {sigma, mscale, bscale1, bscale0, delta_con, tau_con, tau_mod, sweeps_done} */

@@ -691,6 +691,33 @@ ORC_API int orc_run(orc_sampler *s, int nburn, int nsim, int nthin, double *tau_
     return saved;
 }
 
+/* The same run, evaluated at NEW covariate rows (bcf 2.x's predict()): per saved sweep mu(x) = mscale * sum of the mu
+ * trees' leaves, tau(x) = (bscale1 - bscale0) * sum of the tau trees' leaves, by walking the pointer trees over the raw
+ * doubles.  xcon_new / xmod_new row-major n_new x p; outputs: means over the saved sweeps, optional draws (nsim x n_new). */
+ORC_API int orc_run_predict(orc_sampler *s, int nburn, int nsim, int nthin, int n_new, const double *xcon_new,
+                            const double *xmod_new, double *tau_mean, double *mu_mean, double *tau_draws)
+{
+    const int total = nsim * nthin + nburn;
+    int saved = 0;
+    memset(tau_mean, 0, sizeof(double) * (size_t)n_new); memset(mu_mean, 0, sizeof(double) * (size_t)n_new);
+    for (int it = 0; it < total; ++it) {
+        sweep_once(s);
+        if (it >= nburn && it % nthin == 0 && saved < nsim) {
+            for (int i = 0; i < n_new; ++i) {
+                double gc = 0, gm = 0;
+                for (int j = 0; j < s->cfg.ntree_con; ++j) gc += tree_bn(s->t_con[j], xcon_new + (size_t)i * s->p_con, &s->xi_c)->mu;
+                for (int j = 0; j < s->cfg.ntree_mod; ++j) gm += tree_bn(s->t_mod[j], xmod_new + (size_t)i * s->p_mod, &s->xi_m)->mu;
+                const double tau = (s->bscale1 - s->bscale0) * gm, mu = s->mscale * gc;
+                tau_mean[i] += tau; mu_mean[i] += mu;
+                if (tau_draws) tau_draws[(size_t)saved * n_new + i] = tau;
+            }
+            ++saved;
+        }
+    }
+    if (saved > 0) for (int i = 0; i < n_new; ++i) { tau_mean[i] /= saved; mu_mean[i] /= saved; }
+    return saved;
+}
+
 /* ---- state getters (parity tests) ---- */
 ORC_API void orc_get_scalars(const orc_sampler *s, double out[8])
 {

@@ -86,6 +86,8 @@ def lib():
         L.orc_get_y.argtypes = [C.c_void_p, dp]
         L.orc_probit_latent_probe.restype = C.c_double
         L.orc_probit_latent_probe.argtypes = [C.c_double, C.c_int, C.c_double]
+        L.orc_run_predict.restype = C.c_int
+        L.orc_run_predict.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp]
         L.orc_lil.restype = C.c_double
         L.orc_lil.argtypes = [C.c_double] * 3
         L.orc_lil_homosked.restype = C.c_double
@@ -190,6 +192,18 @@ class OracleSampler:
                               _dp(out["mu_mean"]), _dp(out["yhat_mean"]), _dp(out["sigma"]), _dp(out["msd"]),
                               _dp(out["bsd"]))
         out["saved"] = saved
+        return out
+
+    def run_predict(self, nburn, nsim, nthin, x_con_new, x_mod_new, draws=False):
+        """run the chain and evaluate every saved sweep's forests at new rows (row-major n_new x p)"""
+        xc = np.ascontiguousarray(x_con_new, dtype=np.float64); xm = np.ascontiguousarray(x_mod_new, dtype=np.float64)
+        m = xc.shape[0]
+        out = {"tau_mean": np.zeros(m), "mu_mean": np.zeros(m)}
+        td = np.zeros((nsim, m)) if draws else None
+        out["saved"] = lib().orc_run_predict(self.h, int(nburn), int(nsim), int(nthin), m, _dp(xc), _dp(xm), _dp(out["tau_mean"]),
+                                             _dp(out["mu_mean"]), _dp(td))
+        if draws:
+            out["tau"] = td
         return out
 
     def scalars(self):

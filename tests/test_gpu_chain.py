@@ -236,3 +236,54 @@ def test_a_share_of_the_gpu_walks_the_same_chain():
         assert g.verify_leaf_cache() == 0
         out.append((g.trace()[0].tobytes(), g.tau_mean().tobytes(), g.sigma().tobytes()))
     assert out[0] == out[1] == out[2]
+
+
+def test_saved_forests_predict_in_and_out_of_sample():
+    """keep_draws bit 3: every saved sweep's forests stay on the device; bcfgpu_predict walks them over new rows binned with
+    the training cutpoints.  In sample the predictions ARE the fit's tau / mu draws; out of sample they equal
+    the oracle's pointer-tree walk over the raw doubles of the same chain, draw by draw."""
+    pr = make_problem(n=900, p=8, seed=14, continuous=True)
+    kw = dict(seed=8, ntree_con=40, ntree_mod=15)
+    g = gpu_sampler(pr, keep_draws=7 | 8, **kw)
+    g.run(12, 9, 2)
+    nd, nn = g.saved_forests
+    assert nd == 9 and nn >= 9 * 55
+    P = pr.P
+    ins = g.predict(P.x_c, P.x_m, draws=True)
+    assert np.allclose(ins["tau"], g.draws("tau"), rtol=1e-12, atol=1e-12)
+    assert np.allclose(ins["mu"], g.draws("mu"), rtol=1e-12, atol=1e-12)
+    assert np.allclose(ins["tau_mean"], g.tau_mean(), rtol=1e-12, atol=1e-12)
+    assert np.allclose(ins["tau_var"], g.tau_var(), rtol=1e-8, atol=1e-12)
+    # new rows: some inside the training range, some outside it (bins clamp at the end cutpoints, as x < cut comparisons do)
+    rng = np.random.default_rng(4)
+    m = 333
+    xn = np.column_stack([rng.integers(0, 2, (m, 2)).astype(float), rng.uniform(-0.3, 1.3, (m, P.x_m.shape[1] - 2))])
+    xcn = np.column_stack([xn, 0.2 * rng.standard_normal(m)])
+    out = g.predict(xcn, xn, draws=True)
+    o = oracle_sampler(pr, max_leaves=128, **kw)
+    ref = o.run_predict(12, 9, 2, xcn, xn, draws=True)
+    assert ref["saved"] == 9
+    assert np.allclose(out["tau"], ref["tau"], rtol=TOL, atol=TOL)
+    assert np.allclose(out["tau_mean"], ref["tau_mean"], rtol=TOL, atol=TOL)
+    assert np.allclose(out["mu_mean"], ref["mu_mean"], rtol=TOL, atol=TOL)
+    # a run without the bit has nothing to predict from
+    g2 = gpu_sampler(pr, **kw)
+    g2.run(3, 2)
+    import pytest as _pt
+    from bcf_iv_b200 import _lib
+    with _pt.raises(_lib.BcfGpuError, match="no saved forests"):
+        g2.predict(xcn, xn)
+    g.close(); g2.close(); o.close()
+
+
+def test_bcf_front_end_predicts_at_new_rows():
+    from bcf_iv_b200 import bcf, datasets
+    d = datasets.generate_dataset_wide(n=700, p=6, seed=6)
+    pihat = 0.05 * np.random.default_rng(1).standard_normal(700)
+    fit = bcf.bcf(d["y"], d["z"], d["X"], d["X"], pihat, nburn=120, nsim=40, random_seed=5, n_chains=2,
+                  x_predict_control=d["X"][:50], pihat_predict=pihat[:50], predict_draws=True)
+    assert fit["tau_predict"].shape == (80, 50)
+    # predicting at training rows reproduces their fitted draws (chains stacked the same way)
+    assert np.allclose(fit["tau_predict"], fit["tau"][:, :50], rtol=1e-10, atol=1e-10)
+    assert np.allclose(fit["tau_predict_mean"], fit["tau_mean"][:50], rtol=1e-10, atol=1e-10)
+    assert np.allclose(fit["mu_predict_mean"], fit["mu_mean"][:50], rtol=1e-10, atol=1e-10)
