@@ -189,12 +189,17 @@ class Sampler:
         self._keep = []
 
     @classmethod
-    def _adopt(cls, handle, cfg, n, off_con, off_mod, p_con, p_mod):
+    def _adopt(cls, handle, cfg, n, off_con, off_mod, p_con, p_mod, cuts_con=None, cuts_mod=None):
         """wrap a handle made by the library (bcfgpu_fit_chains)"""
         s = cls.__new__(cls)
         s.cfg, s.T, s._h, s.n, s._keep = cfg, cfg.ntree_con + cfg.ntree_mod, C.c_void_p(handle), n, []
         s.off_con, s.off_mod, s.p_con, s.p_mod = off_con, off_mod, p_con, p_mod
+        s.cuts_con, s.cuts_mod = cuts_con, cuts_mod
         return s
+
+    def cutpoints(self, forest):
+        """the flat cutpoint vector the forest's columns were binned with (offsets: off_con / off_mod)"""
+        return self.cuts_con if forest == 0 else self.cuts_mod
 
     def request_stop(self):
         """thread-safe: the bcfgpu_run in progress on another thread returns INTERRUPTED at its next launch boundary"""
@@ -243,6 +248,7 @@ class Sampler:
                                      _ip(oc), _dp(cm), _ip(om)))
         self.n = n
         self.off_con, self.off_mod = oc, om
+        self.cuts_con, self.cuts_mod = cc, cm
         self.p_con, self.p_mod = xc.shape[1], p_mod
         v = C.c_int64()
         check(load().bcfgpu_h2d_bytes(self._h, C.byref(v)))
@@ -455,7 +461,7 @@ def fit_chains(cfg_kw, n_chains, devices, y, z, x_con, x_mod, cuts_con, off_con,
     for k in range(n_chains):
         ck = Config.from_buffer_copy(c)
         ck.chain = c.chain + k
-        out.append(Sampler._adopt(hs[k], ck, n, oc, om, xc.shape[1], p_mod))
+        out.append(Sampler._adopt(hs[k], ck, n, oc, om, xc.shape[1], p_mod, cc, cm))
     return out
 
 

@@ -25,6 +25,9 @@ N_TREES, K_SD, BASE, POWER, NUMCUT = 75, 2.0, 0.95, 2.0, 100
 
 def bart_cutpoints(x, numcut=NUMCUT, cat_levels=prep.CP_CAT_LEVELS):
     x = np.asarray(x, dtype=np.float64)
+    lo, hi = x.min(), x.max()
+    if lo != hi and np.all((x == lo) | (x == hi)):
+        return np.array([lo + (hi - lo) / 2.0])       # two-valued column: no sort needed
     ux = np.unique(x)
     if ux.size == 1:
         return ux.copy()

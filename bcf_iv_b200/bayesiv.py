@@ -135,9 +135,72 @@ def cart(X, y, maxdepth=2, cp=0.01, minsplit=20, minbucket=None):
     return nodes, where
 
 
+def cart_device(sampler, X, y, maxdepth=2, cp=0.01, minsplit=20, minbucket=None, forest=1):
+    """`cart` with the split search on the GPU: the candidate statistics of EVERY (node, variable, cutpoint)
+    of a tree level come from one pass of the all-candidate histogram kernel (K2', bcfgpu_op_hist_all) over the binned
+    covariates the sampler already holds on the device; prefix sums over the bins give each split's left child, the
+    arg-max and the rpart stopping rules are a few hundred numbers on the host.  Same result as `cart` when every column's
+    candidate splits are the sampler's cutpoints, i.e. for columns with fewer than 8 distinct values (midpoints between
+    them: rpart's own candidates) -- the reference's designs; the caller falls back to `cart` otherwise."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = len(y)
+    if minbucket is None:
+        minbucket = int(round(minsplit / 3.0))
+    off = sampler.off_mod if forest == 1 else sampler.off_con
+    p = X.shape[1]
+    ncut = np.diff(off)[:p]
+    cuts_all = sampler.cutpoints(forest)
+    root = CartNode(1, np.arange(n), y, [])
+    nodes, where = {1: root}, np.ones(n, dtype=np.int64)
+    frontier = [root]
+    for depth in range(maxdepth):
+        live = [nd for nd in frontier if nd.n >= minsplit and nd.dev > 0]
+        if not live:
+            break
+        lab = np.full(n, -1, dtype=np.int32)
+        for k, nd in enumerate(live):
+            lab[where == nd.id] = k
+        cnt, sm, _ = sampler.op_hist_all(forest, lab, len(live), y)
+        nxt = []
+        for k, nd in enumerate(live):
+            tot, base = nd.mean * nd.n, (nd.mean * nd.n) ** 2 / nd.n
+            best = (0.0, None, None)
+            for v in range(p):
+                b0 = int(off[v]) + v
+                c_ = np.cumsum(cnt[k, b0:b0 + ncut[v]])            # rows with bin <= c  <=>  x < cut[c]: the left child of cut c
+                s_ = np.cumsum(sm[k, b0:b0 + ncut[v]])
+                ok = (c_ >= minbucket) & (nd.n - c_ >= minbucket)
+                if not ok.any():
+                    continue
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    gain = np.where(ok, s_ ** 2 / c_ + (tot - s_) ** 2 / (nd.n - c_) - base, -np.inf)
+                j = int(np.argmax(gain))
+                if gain[j] > best[0] * (1 + 1e-12):
+                    best = (float(gain[j]), v, float(cuts_all[int(off[v]) + j]))
+            gain, v, cut = best
+            if v is None or gain < cp * root.dev:
+                continue
+            idx = np.nonzero(where == nd.id)[0]
+            li, ri = idx[X[idx, v] < cut], idx[X[idx, v] >= cut]
+            nd.var, nd.cut = v, cut
+            nd.left = CartNode(2 * nd.id, li, y, nd.rule + [(v, "<", cut)])
+            nd.right = CartNode(2 * nd.id + 1, ri, y, nd.rule + [(v, ">=", cut)])
+            nodes[nd.left.id], nodes[nd.right.id] = nd.left, nd.right
+            where[li], where[ri] = nd.left.id, nd.right.id
+            nxt += [nd.left, nd.right]
+        frontier = nxt
+    return nodes, where
+
+
 def rule_text(rule, names):
     """the node's path as the reference prints it: 'x1< 0.5 & x2>=0.5' (path.rpart's format)"""
     return " & ".join(f"{names[v]}{'< ' if op == '<' else '>='}{cut:.4g}" for v, op, cut in rule)
+
+
+def prep_cat_levels():
+    from . import prep
+    return prep.CP_CAT_LEVELS
 
 
 def rule_mask(rule, X):
@@ -283,6 +346,7 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
         fit_args["max_ctas"] = _bcf._lib.B200_SMS // 2
     fit = bcf_fn or _bcf.bcf
     fit_bartc = bartc_fn or _bart.bartc
+    live = []                                       # the ITT fit's sampler, kept open for the CART on the device
     if pic_model not in ("bartc", "bcf"):
         raise ValueError("pic_model must be 'bartc' or 'bcf'")
     with ThreadPoolExecutor(max_workers=2) as pool:
@@ -295,15 +359,31 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
                 f_itt = pool.submit(lambda: fit_bartc(y[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2,
                                                       seed=seed + 1)["ite_mean"])
             else:
-                f_itt = pool.submit(lambda: fit(y[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"])   # R/bcf_iv.R:89-91
+                def _itt():
+                    r = fit(y[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, keep_sampler=bcf_fn is None))   # R/bcf_iv.R:89-91
+                    live.append(r.get("sampler"))
+                    return r["tau_mean"]
+                f_itt = pool.submit(_itt)
         else:
             f_pic = pool.submit(lambda: fit(w[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, first_chain=1))["tau_mean"])
             f_itt = pool.submit(lambda: fit(y[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"])
         pic, itt = f_pic.result(), f_itt.result()
     tauhat = itt / pic                                                                      # R/bcf_iv.R:94
-    nodes, where = cart(Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
+    smp = live[0] if live and live[0] is not None else None
+    try:
+        # the CART on tauhat: on the device when the sampler's cutpoints ARE rpart's candidate splits (columns with fewer
+        # than 8 distinct values) and tauhat fits the kernel's fixed-point range; on the host otherwise
+        on_device = (smp is not None and np.all(np.diff(smp.off_mod) < prep_cat_levels() - 1)
+                     and np.all(np.isfinite(tauhat)) and np.max(np.abs(tauhat)) < 16384.0)
+        if on_device:
+            nodes, where = cart_device(smp, Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
+        else:
+            nodes, where = cart(Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
+    finally:
+        if smp is not None:
+            smp.close()
     if details is not None:
-        details.update(disc=disc, index=index, pic=pic, itt=itt, tauhat=tauhat,
+        details.update(disc=disc, index=index, pic=pic, itt=itt, tauhat=tauhat, cart_on_device=bool(on_device),
                        split_vars=sorted({nd.var for nd in nodes.values() if nd.var is not None}))
     ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
     leaves = {nid for nid in ids if nodes[nid].left is None}

@@ -20,8 +20,8 @@ from . import _lib, prep
 DRAW_BYTES_CAP = 8 << 30   # keep nsim x n draws on the device only below this (3 matrices of doubles)
 
 
-def _collect(s, keep, pred=None):
-    """what bcf() returns from one finished chain (a _lib.Sampler); always closes it"""
+def _collect(s, keep, pred=None, close=True):
+    """what bcf() returns from one finished chain (a _lib.Sampler); closes it unless the caller keeps the handle"""
     try:
         r = {"sigma": s.sigma(), "scales": s.scales(), "tau_mean": s.tau_mean(), "mu_mean": s.mu_mean(),
              "yhat_mean": s.yhat_mean(), "tau_var": s.tau_var(), "ms": s.last_run_ms, "moves": s.counters()}
@@ -30,8 +30,12 @@ def _collect(s, keep, pred=None):
         if pred is not None:
             r["pred"] = s.predict(pred[0], pred[1], draws=pred[2])
         return r
+    except BaseException:
+        close = True
+        raise
     finally:
-        s.close()
+        if close:
+            s.close()
 
 
 def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nthin=1, update_interval=100,
@@ -41,7 +45,7 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
         w=None, random_seed=None, n_chains=1, n_cores=None, n_threads=None, no_output=True,
         save_tree_directory=None, log_file=None, verbose=False,
         devices=None, keep_draws=None, engine=_lib.ENGINE_AUTO, max_ctas=0, first_chain=0,
-        x_predict_control=None, x_predict_moderate=None, pihat_predict=None, predict_draws=False):
+        x_predict_control=None, x_predict_moderate=None, pihat_predict=None, predict_draws=False, keep_sampler=False):
     """Fit the Bayesian Causal Forest  y = mu(x, pihat) + tau(x) z + eps  on the GPU.
 
     Returns a dict with bcf's fields: `sigma` (nsim*n_chains), `yhat`, `mu`, `tau` (nsim*n_chains x n, original row
@@ -54,7 +58,9 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
     `first_chain` (Philox stream of the first chain; chain c uses first_chain + c);
     `x_predict_control` / `x_predict_moderate` / `pihat_predict` (bcf 2.x's predict() in the same call): new covariate rows at
     which every saved sweep's forests are evaluated on the device -> `tau_predict_mean`, `tau_predict_var`,
-    `mu_predict_mean` (and `tau_predict`, `mu_predict`: nsim*n_chains x n_new with predict_draws=True), original y units.  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
+    `mu_predict_mean` (and `tau_predict`, `mu_predict`: nsim*n_chains x n_new with predict_draws=True), original y units;
+    `keep_sampler` (the first chain's _lib.Sampler is returned open as out["sampler"]: bcf_iv grows its CART on the binned
+    covariates that are already on the device; the caller closes it).  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
     no_output, verbose, update_interval) are accepted and ignored; observation weights `w` are not implemented.
     """
     if nburn is None or nsim is None:
@@ -108,12 +114,14 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
     samplers = _lib.fit_chains(cfg, int(n_chains), devs, P.yscale, P.z, P.x_c, P.x_m, cc, oc, cm, om, int(nburn), int(nsim),
                                int(nthin))
     res, err = [], None
-    for smp in samplers:                                      # every handle is closed even if one read-back fails
+    for k, smp in enumerate(samplers):                         # every handle is closed even if one read-back fails
         try:
-            res.append(_collect(smp, keep_draws, pred))
+            res.append(_collect(smp, keep_draws, pred, close=not (keep_sampler and k == 0)))
         except BaseException as e:
             err = err or e
     if err is not None:
+        if keep_sampler:
+            samplers[0].close()
         raise err
     ns = len(res[0]["sigma"])
     ntot = ns * len(res)
@@ -134,6 +142,8 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
         "device_ms": [r["ms"] for r in res],
         "moves": [r["moves"] for r in res],
     }
+    if keep_sampler:
+        out["sampler"] = samplers[0]                          # the first chain's live handle (binned X still on the device): close() it
     if pred is not None:
         pm = np.mean([r["pred"]["tau_mean"] for r in res], axis=0)
         out["tau_predict_mean"] = sdy * pm

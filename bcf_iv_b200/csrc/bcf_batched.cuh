@@ -928,9 +928,13 @@ __device__ __forceinline__ void propose_all_b(BatchSmem& sm, const Dev& d, const
 #define PROF(k) do { if (prof) { const long long now_ = clock64(); pc[k] += now_ - tp; tp = now_; } } while (0)
 #endif
 
+// done_in (may be null): sweeps of this request the pipelined kernel has already run (device memory): the launch queued
+// behind k_pipe to take over a sweep that holds a wide tree returns at once when there is nothing left for it
 template <bool RES>
-__global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, unsigned int* bar, int ntl_max)
+__global__ void __launch_bounds__(PTHREADS, 1) k_batched(Dev d, int nsweeps, unsigned int* bar, int ntl_max, const int* done_in)
 {
+    if (done_in != nullptr) nsweeps -= __ldcg(done_in);
+    if (nsweeps <= 0) return;
     extern __shared__ __align__(16) unsigned char bcf_dyn_smem[];
     BatchSmem& sm = *reinterpret_cast<BatchSmem*>(bcf_dyn_smem);
     unsigned char* dyn = bcf_dyn_smem + BATCH_SMEM_BYTES;

@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(256, 2) k_hist_bits(Dev d, int forest, const u
         if (lane == 0) { ssum[wib][HISTB_CELLS + l] = v; scnt[wib][HISTB_CELLS + l] = k; }
     }
     __syncthreads();
-    if (t < HISTB_CELLS + NLEAF) {
+    if (t < CPC * NLEAF || (t >= HISTB_CELLS && t < HISTB_CELLS + NLEAF)) {   // (cells CPC * NLEAF .. HISTB_CELLS - 1 do not exist when NLEAF does not divide HISTB_CELLS)
         double v = 0.0;
         long long k = 0;
         for (int w = 0; w < 8; ++w) { v += ssum[w][t]; k += scnt[w][t]; }

@@ -889,7 +889,7 @@ static int build_graph(bcfgpu_handle* h)
     return BCFGPU_OK;
 }
 
-static int run_persistent(bcfgpu_handle* h, int total);
+static int run_persistent(bcfgpu_handle* h, int total, bool no_sync = false);
 static int select_kernel(bcfgpu_handle* h);
 
 static int check_device_err(bcfgpu_handle* h)
@@ -987,9 +987,9 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
     if (!persistent && h->nranks == 1) { if ((rc = build_graph(h))) return rc; }
     CK(cudaEventRecord(h->ev0, h->stream));
     h->last_kernel = 0;
-    auto launch_sweeps = [&](int k) -> int {
+    auto launch_sweeps = [&](int k, bool no_sync = false) -> int {
         if (persistent) {
-            int r = run_persistent(h, k);
+            int r = run_persistent(h, k, no_sync);
             h->last_kernel = h->kernel;
             return r;
         }
@@ -1017,7 +1017,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
             if (h->stop.load(std::memory_order_relaxed)) { rc = fail(BCFGPU_ERR_INTERRUPTED, "run stopped by bcfgpu_request_stop"); break; }
             k_probit_latent<<<grid, 256, 0, h->stream>>>(d, h->d_ybin, h->d_orig, 0, h->cfg.probit_offset, const_cast<double*>(d.y));
             h->launches++;
-            rc = launch_sweeps(1);
+            rc = launch_sweeps(1, true);
             if (rc == BCFGPU_OK && it >= nburn && (it % nthin) == 0 && probit_saved < nsim) {
                 // (the sweep flipped the tree parity: the current trees are in trees[parity]; read it back lazily -- it
                 // simply alternates from the value fetched above)
@@ -1039,7 +1039,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
         rc = launch_sweeps(nburn);
         int saved = 0;
         for (int it = nburn; it < total && rc == BCFGPU_OK; ++it) {
-            rc = launch_sweeps(1);
+            rc = launch_sweeps(1, true);
             if (rc == BCFGPU_OK && (it % nthin) == 0 && saved < nsim) {
                 const int par = (sc.parity + it + 1) & 1;
                 k_save_trees<<<h->T, 64, 0, h->stream>>>(d, d.trees[par], saved, h->d_pool, h->pool_cap, h->d_pool_used,
@@ -1732,7 +1732,7 @@ static int select_kernel(bcfgpu_handle* h)
     return BCFGPU_OK;
 }
 
-static int run_persistent(bcfgpu_handle* h, int total)
+static int run_persistent(bcfgpu_handle* h, int total, bool no_sync)
 {
     if (total <= 0) return BCFGPU_OK;
     { int rc = select_kernel(h); if (rc) return rc; }
@@ -1747,7 +1747,7 @@ static int run_persistent(bcfgpu_handle* h, int total)
         Dev d = h->dev;
         d.pr.seq0 = (++h->launch_id) << 32;
         unsigned int* bar = h->d_bar;
-        CK(cudaMemsetAsync(bar, 0, 16, h->stream));
+        CK(cudaMemsetAsync(bar, 0, 64, h->stream));
         int ntl = h->res_ntl;
         if (h->kernel == 4) {
             // pipelined kernel; it returns early at a sweep that holds a tree wider than KB keys: that one sweep is
@@ -1759,6 +1759,18 @@ static int run_persistent(bcfgpu_handle* h, int total)
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&pntl, (void*)&dn};
             CK(cudaLaunchCooperativeKernel((const void*)k_pipe, dim3(h->coop_grid), dim3(PIPE_THREADS), args, h->pipe_smem, h->stream));
             h->launches++;
+            if (no_sync && nsw == 1 && h->nranks == 1) {
+                // sweep-by-sweep callers (probit BART, saved forests): no host round trip per sweep -- the batched kernel is
+                // queued behind k_pipe unconditionally and returns at once unless k_pipe left the sweep to it
+                unsigned int* bar2 = bar + 8;                       // its own barrier counters (zeroed with the others)
+                const int* din = dn;
+                void* a2[] = {(void*)&d, (void*)&nsw, (void*)&bar2, (void*)&ntl, (void*)&din};
+                CK(cudaLaunchCooperativeKernel(h->fallback_kernel == 3 ? (const void*)k_batched<true> : (const void*)k_batched<false>, dim3(h->coop_grid),
+                                               dim3(PTHREADS), a2, h->res_smem, h->stream));
+                h->launches++;
+                done += 1;
+                continue;
+            }
             int dn_host[2] = {0, 0};
             CK(cudaMemcpyAsync(dn_host, dn, 8, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -1769,7 +1781,8 @@ static int run_persistent(bcfgpu_handle* h, int total)
                 int one = 1;
                 d.pr.seq0 = (++h->launch_id) << 32;                  // (its own launch: the mailbox sequence numbers restart)
                 CK(cudaMemsetAsync(bar, 0, 16, h->stream));
-                void* a2[] = {(void*)&d, (void*)&one, (void*)&bar, (void*)&ntl};
+                const int* none = nullptr;
+                void* a2[] = {(void*)&d, (void*)&one, (void*)&bar, (void*)&ntl, (void*)&none};
                 CK(cudaLaunchCooperativeKernel(h->fallback_kernel == 3 ? (const void*)k_batched<true> : (const void*)k_batched<false>, dim3(h->coop_grid),
                                                dim3(PTHREADS), a2, h->res_smem, h->stream));
                 h->launches++;
@@ -1777,11 +1790,12 @@ static int run_persistent(bcfgpu_handle* h, int total)
             }
             continue;
         }
+        const int* none = nullptr;
         if (h->kernel == 3) {
-            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};
+            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl, (void*)&none};
             CK(cudaLaunchCooperativeKernel((const void*)k_batched<true>, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
         } else if (h->kernel == 5) {
-            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};
+            void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl, (void*)&none};
             CK(cudaLaunchCooperativeKernel((const void*)k_batched<false>, dim3(h->coop_grid), dim3(PTHREADS), args, h->res_smem, h->stream));
         } else if (h->kernel == 2) {
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl};

@@ -22,6 +22,9 @@ def cp_quantile(x: np.ndarray, num: int = CP_NUM, cat_levels: int = CP_CAT_LEVEL
     evaluated on seq(min, max, length.out=num).
     """
     x = np.asarray(x, dtype=np.float64)
+    lo, hi = x.min(), x.max()
+    if lo != hi and np.all((x == lo) | (x == hi)):
+        return np.array([lo + (hi - lo) / 2.0])       # two-valued column (the reference's covariates): no sort needed
     ux = np.unique(x)
     if ux.size == 1:
         warnings.warn("A supplied covariate contains a single distinct value.")

@@ -1,48 +1,59 @@
-"""Wall time of whole bcf_iv() / bcf_itt() calls on BASELINE.json's shapes (one GPU), with the share spent in the sampler.
+"""Wall time of whole bcf_iv() / bcf_itt() calls on BASELINE.json's shapes (one GPU), by phase: the host-side steps of the
+reference's pipeline (logistic propensity, bcf's R-side preamble, CART, per-node 2SLS) and the two GPU samplers (bcf for
+the ITT, bartc's probit BART for the complier proportion / binary outcomes).
 
-usage: python scripts/bcf_iv_walltime.py [c1] [c2] [c3]     (default: all three)
+usage: python scripts/bcf_iv_walltime.py [c1] [c2] [c3] [c4]     (default: all four)
 """
 import contextlib
 import io
 import json
 import os
 import sys
+import threading
 import time
 
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bcf_iv_b200 import bayesiv, bcf as bcfmod, datasets  # noqa: E402
+from bcf_iv_b200 import bart as bartmod, bayesiv, bcf as bcfmod, datasets, prep  # noqa: E402
 
-which = [a for a in sys.argv[1:]] or ["c1", "c2", "c3"]
-calls = []
-_orig = bcfmod.bcf
-
-
-def _timed_bcf(*a, **k):
-    t0 = time.perf_counter()
-    r = _orig(*a, **k)
-    calls.append((time.perf_counter() - t0, sum(r["device_ms"]) * 1e-3, len(a[0])))
-    return r
+which = [a for a in sys.argv[1:]] or ["c1", "c2", "c3", "c4"]
+phase = {}
+lock = threading.Lock()
 
 
-bayesiv._bcf.bcf = _timed_bcf
+def timed(name, fn):
+    def f(*a, **k):
+        t0 = time.perf_counter()
+        try:
+            return fn(*a, **k)
+        finally:
+            with lock:
+                phase.setdefault(name, []).append(round(time.perf_counter() - t0, 3))
+    return f
+
+
+bayesiv.logit_link = timed("logit_link (glm z ~ x)", bayesiv.logit_link)
+bayesiv.cart = timed("cart (rpart)", bayesiv.cart)
+bayesiv._node_rows = timed("per-node 2SLS (ivreg)", bayesiv._node_rows)
+bcfmod.prep.prepare = timed("bcf preamble (cutpoints, lm sighat)", prep.prepare)
+_fit_chains = bcfmod._lib.fit_chains
+bcfmod._lib.fit_chains = timed("GPU: fit_chains (set_data + sweeps)", _fit_chains)     # (bart.py goes through the same module object)
+bayesiv._bcf.bcf = timed("bcf() ITT fit, whole call", bcfmod.bcf)
+bayesiv._bart.bartc = timed("bartc() probit BART, whole call", bartmod.bartc)
 
 
 def run(name, fn, gen, **kw):
     t0 = time.perf_counter()
     d = gen()
     t_gen = time.perf_counter() - t0
-    calls.clear()
+    phase.clear()
     t0 = time.perf_counter()
     with contextlib.redirect_stdout(io.StringIO()):
         out = fn(d["y"], d["w"], d["z"], d["X"], **kw)
     wall = time.perf_counter() - t0
-    sweeps = kw.get("n_burn", 500) + kw.get("n_sim", 500)
-    print(json.dumps({"config": name, "wall_s": round(wall, 3), "data_gen_s": round(t_gen, 2), "sampler_calls": len(calls),
-                      "n_s": calls[0][2], "sweeps_per_call": sweeps, "bcf_call_s": [round(c[0], 3) for c in calls],
-                      "sampler_device_s": [round(c[1], 3) for c in calls],
-                      "sweeps_per_s_device": [round(sweeps / c[1], 1) for c in calls],
+    print(json.dumps({"config": name, "wall_s": round(wall, 3), "data_gen_s": round(t_gen, 2), "n": int(len(d["y"])),
+                      "sweeps_per_fit": kw.get("n_burn", 500) + kw.get("n_sim", 500), "phases_s": dict(phase),
                       "rows": (None if out is None else int(len(out)))}), flush=True)
 
 
@@ -55,3 +66,7 @@ if "c2" in which:
 if "c3" in which:
     run("C3 bcf_iv n=1e6 p=100 (one chain)", bayesiv.bcf_iv,
         lambda: datasets.generate_dataset_wide(n=1000000, p=100, compliance=0.75, seed=1), n_burn=500, n_sim=500)
+if "c4" in which:
+    run("C4 bcf_iv binary outcome n=1e6 p=100 compliance=.3 rho=.5", bayesiv.bcf_iv,
+        lambda: datasets.generate_dataset_wide(n=1000000, p=100, compliance=0.3, rho=0.5, seed=1, binary_outcome=True),
+        binary=True, n_burn=500, n_sim=500)

@@ -137,3 +137,32 @@ def test_observation_shards_walk_the_single_gpu_chain(engine, world):
         assert np.array_equal(tau, ref)
         assert all(scal[k] == sc[k] for k in ("sigma", "mscale", "bscale1", "bscale0", "tau_con", "sweep"))
         assert scal["engine_in_use"][1] == (1 if engine == _lib.ENGINE_GRAPH else 2)    # NCCL per tree / in-kernel mailboxes
+
+
+def test_cart_on_the_device_equals_the_host_cart():
+    """the subgroup tree on tauhat grown from the all-candidate histogram kernel (K2') over the sampler's binned
+    covariates == the host restatement of rpart (same candidates: midpoints of few-valued columns, same stopping rules)."""
+    rng = np.random.default_rng(5)
+    n, p = 6000, 12
+    X = rng.integers(0, 2, (n, p)).astype(float)
+    X[:, 5] = rng.integers(0, 4, n)                              # a four-valued column: three candidate cutpoints
+    tau = 1.5 * (X[:, 0] == 0) * (X[:, 1] == 0) - 1.5 * (X[:, 0] == 1) * (X[:, 1] == 1) + 0.4 * (X[:, 5] >= 2) + 0.3 * rng.standard_normal(n)
+    pr_y = rng.standard_normal(n)
+    z = rng.integers(0, 2, n)
+    fit = bcf.bcf(pr_y, z, X, X, 0.05 * rng.standard_normal(n), nburn=2, nsim=1, random_seed=1, keep_sampler=True)
+    s = fit["sampler"]
+    try:
+        for depth, cp, minsplit in ((2, 0.01, 10), (3, 0.001, 20), (1, 0.01, 10), (4, 0.0, 40)):
+            nd_h, wh_h = bayesiv.cart(X, tau, maxdepth=depth, cp=cp, minsplit=minsplit)
+            nd_d, wh_d = bayesiv.cart_device(s, X, tau, maxdepth=depth, cp=cp, minsplit=minsplit)
+            assert sorted(nd_h) == sorted(nd_d)
+            assert np.array_equal(wh_h, wh_d)
+            for k in nd_h:
+                assert (nd_h[k].var, nd_h[k].cut, nd_h[k].n) == (nd_d[k].var, nd_d[k].cut, nd_d[k].n)
+    finally:
+        s.close()
+    # and bcf_iv takes that path on the reference's binary designs
+    d = datasets.generate_dataset(n=1000, p=10, compliance=0.75, seed=7)
+    det = {}
+    bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], n_burn=100, n_sim=100, max_depth=2, seed=42, details=det)
+    assert det["cart_on_device"] is True and det["split_vars"] == [0, 1]
