@@ -24,7 +24,7 @@ SYMBOLS = [
     "bcfgpu_abi_version", "bcfgpu_device_count", "bcfgpu_last_error", "bcfgpu_config_init", "bcfgpu_create",
     "bcfgpu_destroy", "bcfgpu_release_cached_memory", "bcfgpu_cache_stats", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_data", "bcfgpu_run", "bcfgpu_request_stop",
     "bcfgpu_fit_chains",
-    "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_h2d_bytes", "bcfgpu_engine_in_use", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
+    "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_h2d_bytes", "bcfgpu_engine_in_use", "bcfgpu_engine_stats", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
     "bcfgpu_get_mu_mean", "bcfgpu_get_yhat_mean", "bcfgpu_get_sigma", "bcfgpu_get_scales", "bcfgpu_get_draws",
     "bcfgpu_num_saved_forests", "bcfgpu_predict", "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
     "bcfgpu_get_tree", "bcfgpu_set_tree", "bcfgpu_get_leaf_ids", "bcfgpu_verify_leaf_cache", "bcfgpu_op_bin_column",
@@ -92,6 +92,7 @@ def load():
     L.bcfgpu_kernel_launches.argtypes = [vp, lp]
     L.bcfgpu_h2d_bytes.argtypes = [vp, lp]
     L.bcfgpu_engine_in_use.argtypes = [vp, ip]
+    L.bcfgpu_engine_stats.argtypes = [vp, lp]
     L.bcfgpu_num_saved.argtypes = [vp, ip]
     for nm in ("tau_mean", "tau_var", "mu_mean", "yhat_mean", "sigma"):
         getattr(L, "bcfgpu_get_" + nm).argtypes = [vp, dp]
@@ -276,6 +277,13 @@ class Sampler:
         o = np.zeros(2, dtype=np.int32)
         check(load().bcfgpu_engine_in_use(self._h, _ip(o)))
         return int(o[0]), int(o[1])
+
+    @property
+    def engine_stats(self):
+        """sweeps run by the pipelined kernel / handed to the batched kernel (a tree wider than 8 keys), since create"""
+        o = np.zeros(2, dtype=np.int64)
+        check(load().bcfgpu_engine_stats(self._h, _lp(o)))
+        return {"pipelined_sweeps": int(o[0]), "fallback_sweeps": int(o[1])}
 
     @property
     def num_saved(self):

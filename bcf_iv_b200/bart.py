@@ -97,14 +97,16 @@ def probit_bart(y01, X, treatment=None, n_samples=500, n_burn=500, n_thin=1, n_c
     return out
 
 
-def bartc(response, treatment, confounders, n_samples=500, n_burn=500, n_chains=2, seed=0, devices=None, fit=probit_bart):
+def bartc(response, treatment, confounders, n_samples=500, n_burn=500, n_chains=2, seed=0, devices=None, fit=probit_bart,
+          **fit_args):
     """bartCause::bartc(response, treatment, confounders, n.samples, n.burn, n.chains) for a 0/1 response, then
     extract(type = "ite") averaged over the draws: dict(ite_mean, ite_var, p_score, prob_mean).  `fit`: the probit-BART
-    fitting function (the parity tests pass the CPU oracle's)."""
+    fitting function (the parity tests pass the CPU oracle's); fit_args (e.g. max_ctas: a share of the GPU per chain, the
+    chains then run side by side) go to it."""
     trt = fit(treatment, confounders, None, n_samples=n_samples, n_burn=n_burn, n_chains=n_chains, seed=seed, first_chain=100,
-              devices=devices)
+              devices=devices, **fit_args)
     ps = trt["prob_mean"]
     Xr = np.column_stack([np.asarray(confounders, dtype=np.float64), ps])
     rsp = fit(response, Xr, treatment, n_samples=n_samples, n_burn=n_burn, n_chains=n_chains, seed=seed, first_chain=200,
-              devices=devices)
+              devices=devices, **fit_args)
     return {"ite_mean": rsp["ite_mean"], "ite_var": rsp["ite_var"], "p_score": ps, "prob_mean": rsp["prob_mean"]}

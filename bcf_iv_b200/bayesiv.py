@@ -342,8 +342,15 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     # memory (27 tiles of 256 rows on each of 74 SMs) each fit gets half of the SMs; at any size one fit's host-side
     # preamble hides under the other's sweeps.
     from concurrent.futures import ThreadPoolExecutor
-    if pic_model == "bcf" and "max_ctas" not in fit_args and len(disc) <= 27 * 256 * (_bcf._lib.B200_SMS // 2) - 512:
-        fit_args["max_ctas"] = _bcf._lib.B200_SMS // 2
+    # At these sizes a sweep is bound by the latency of its decision chain, not by the SMs it has: the fits run side by side
+    # on shares of the GPU while an SM's 27 tiles of 256 rows hold a share's observations -- the ITT forest on half of the
+    # SMs, bartc's two chains on a quarter each (or on the other half, one after the other, when a quarter is too small).
+    sms = _bcf._lib.B200_SMS
+    fits_in = lambda ctas: len(disc) <= 27 * 256 * ctas - 512
+    bart_ctas = 0
+    if "max_ctas" not in fit_args and fits_in(sms // 2):
+        fit_args["max_ctas"] = sms // 2
+        bart_ctas = sms // 4 if fits_in(sms // 4) else sms // 2
     fit = bcf_fn or _bcf.bcf
     fit_bartc = bartc_fn or _bart.bartc
     live = []                                       # the ITT fit's sampler, kept open for the CART on the device
@@ -353,11 +360,12 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
         # the reference's two samplers are independent (bartc / bcf): each fit has its own Philox streams, so itt and pic
         # do not share their Monte Carlo noise
         if pic_model == "bartc":
+            bkw = dict(max_ctas=bart_ctas) if (bartc_fn is None and bart_ctas) else {}
             f_pic = pool.submit(lambda: fit_bartc(w[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2,
-                                                  seed=seed)["ite_mean"])                    # R/bcf_iv.R:78-80
+                                                  seed=seed, **bkw)["ite_mean"])             # R/bcf_iv.R:78-80
             if binary:                                                                          # R/bcf_iv.R:198-202
                 f_itt = pool.submit(lambda: fit_bartc(y[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2,
-                                                      seed=seed + 1)["ite_mean"])
+                                                      seed=seed + 1, **bkw)["ite_mean"])
             else:
                 def _itt():
                     r = fit(y[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, keep_sampler=bcf_fn is None))   # R/bcf_iv.R:89-91

@@ -923,9 +923,11 @@ __global__ void k_probit_prepare(double* __restrict__ y, uint8_t* __restrict__ y
     }
 }
 // the latent draw that opens a sweep: working response y = ystar - offset, full residual re-derived from it
+// stall (here and below, may be null): set when a queued sweep kernel left its sweep undone -- everything queued behind it returns
 __global__ void __launch_bounds__(256) k_probit_latent(Dev d, const uint8_t* __restrict__ ybin, const int32_t* __restrict__ orig,
-                                                       int64_t row0, double offset, double* __restrict__ y)
+                                                       int64_t row0, double offset, double* __restrict__ y, const int* stall)
 {
+    if (stall != nullptr && __ldcg(stall) != 0) return;
     const Scalars sc = *d.sc;
     const Rng rng{d.key0, d.key1};
     int bad = 0;
@@ -943,8 +945,9 @@ __global__ void __launch_bounds__(256) k_probit_latent(Dev d, const uint8_t* __r
     if (bad) atomicOr(d.err, ERR_FX_RANGE);
 }
 // which trees split on the treatment column?  one CTA per tree; list[0] = count, list[1..] = tree ids (any order)
-__global__ void k_cf_collect(Dev d, const TreeRec* __restrict__ trees, int trt_var, int* list)
+__global__ void k_cf_collect(Dev d, const TreeRec* __restrict__ trees, int trt_var, int* list, const int* stall)
 {
+    if (stall != nullptr && __ldcg(stall) != 0) return;
     const TreeRec& tr = trees[blockIdx.x];
     const int nn = __ldcg(&tr.nnodes);
     int hit = 0;
@@ -957,9 +960,10 @@ __global__ void k_cf_collect(Dev d, const TreeRec* __restrict__ trees, int trt_v
 //   mu_sum           : Phi(offset + f(x)) at the observed treatment,   yhat_sum: f(x) itself.
 constexpr int CF_OBS_PER_THREAD = 4;
 __global__ void __launch_bounds__(256) k_cf_accumulate(Dev d, const TreeRec* __restrict__ trees, const int* __restrict__ list,
-                                                       int trt_var, double offset, const int32_t* __restrict__ orig)
+                                                       int trt_var, double offset, const int32_t* __restrict__ orig, const int* stall)
 {
     __shared__ TreeRec tr;
+    if (stall != nullptr && __ldcg(stall) != 0) return;
     const ForestDev& F = d.f[0];
     const int nlist = trt_var >= 0 ? list[0] : 0;
     const int64_t base = (int64_t)blockIdx.x * (256 * CF_OBS_PER_THREAD) + threadIdx.x;
@@ -1031,9 +1035,10 @@ struct SavedDraw { double mscale, bscale1, bscale0, pad_; };
 // one CTA per tree: the draw's tree `blockIdx.x` -> pool (bump allocation: the order of the trees in the pool is arbitrary,
 // their offsets are recorded).  off[draw * (T + 1) + tree] = first node, count in cnt[...].
 __global__ void k_save_trees(Dev d, const TreeRec* __restrict__ trees, int draw, SavedNode* pool, long long pool_cap,
-                             unsigned long long* pool_used, long long* off, int32_t* cnt, SavedDraw* scal)
+                             unsigned long long* pool_used, long long* off, int32_t* cnt, SavedDraw* scal, const int* stall)
 {
     __shared__ long long base;
+    if (stall != nullptr && __ldcg(stall) != 0) return;
     const TreeRec& tr = trees[blockIdx.x];
     const int nn = __ldcg(&tr.nnodes);
     if (threadIdx.x == 0) {

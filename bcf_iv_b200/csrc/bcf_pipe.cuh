@@ -630,6 +630,7 @@ __device__ inline void pipe_propose_all(PipeSmem& sm, const Dev& d, const TreeRe
 __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, unsigned int* bar, int ntl_max, int* done_out)
 {
     extern __shared__ __align__(16) unsigned char bcf_dyn_smem[];
+    if (__ldcg(&done_out[2]) != 0) return;            // queued behind a launch that handed its sweep to the batched kernel: the host reruns from there
     PipeSmem& sm = *reinterpret_cast<PipeSmem*>(bcf_dyn_smem);
     unsigned char* dyn = bcf_dyn_smem + PIPE_SMEM_BYTES;
     __shared__ Scalars scs;
@@ -1017,7 +1018,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
             st8_f64(d.Gc + gb, G);
             st8_i64(d.rfx + gb, R);
         }
-    if (writer0 && t == 0) done_out[0] = done;
+    if (writer0 && t == 0) {
+        done_out[0] += done;                          // (the host zeroes it per request; sweep-by-sweep callers queue several launches)
+        if (done < nsweeps) done_out[2] = 1;          // a sweep was left to the batched kernel: later queued work must not run ahead of it
+    }
     if (writer0 && !is_pass && rt == 0) done_out[1] = (int)(gbatch - d.pr.batch0);   // batches exchanged (observation shards: tags go on)
     if (bad) atomicOr(d.err, ERR_FX_RANGE);
     if (t == 0 && sm.bad) atomicOr(d.err, sm.bad);

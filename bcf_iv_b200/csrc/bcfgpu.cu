@@ -103,6 +103,7 @@ struct bcfgpu_handle {
     Mailbox* peer_mail[MAX_RANKS] = {nullptr};   // the peers' mailbox arrays, mapped with cudaIpc
     bool peer_ok = false;             // every rank mapped every peer: the sweep kernel exchanges through NVLink itself
     unsigned long long launch_id = 0;
+    int64_t pipe_sweeps = 0, fallback_sweeps = 0;   // sweeps the pipelined kernel ran / handed to the batched kernel (a tree wider than 8 keys)
     unsigned long long pipe_batches = 0;   // batches the pipelined kernel has exchanged with the peers so far (tags of Mailbox::ll)
     bool shard_decided = false, shard_persistent = false;
     int last_kernel = 0;
@@ -941,8 +942,8 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
     const bool keep_trees = (h->keep & 8) && nsim > 0 && h->cfg.model == BCFGPU_MODEL_BCF;
     if (keep_trees) {
         if (h->nranks > 1) return fail(BCFGPU_ERR_BAD_ARG, "saved forests (keep_draws bit 3) are not available in the sharded mode");
-        // trees average 2 - 3 nodes at stationarity: room for 12 per tree and draw, at most 4 GiB
-        h->pool_cap = std::min<long long>((long long)nsim * h->T * 12, ((long long)4 << 30) / (long long)sizeof(SavedNode));
+        // trees average 2 - 3 nodes at stationarity: room for 12 per tree and draw (+ 512 per draw: forests of a few wide trees), at most 4 GiB
+        h->pool_cap = std::min<long long>((long long)nsim * ((long long)h->T * 12 + 512), ((long long)4 << 30) / (long long)sizeof(SavedNode));
         DM(h, &h->d_pool, (size_t)h->pool_cap, true);
         DM(h, &h->d_pool_used, 2, true);
         DM(h, &h->d_tree_off, (size_t)nsim * h->T, true);
@@ -1007,48 +1008,98 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
         return r;
     };
     int probit_saved = 0;
+    // Sweep-by-sweep running (probit BART: a latent draw before and a counterfactual pass after the sweep; saved forests: a
+    // copy of the trees after it).  pre(it, stall) / post(it, stall) queue the kernels around sweep `it`.  With the
+    // pipelined kernel the sweeps of a group are queued WITHOUT asking after each one whether it ran: k_pipe refuses a sweep
+    // that holds a tree wider than 8 keys and raises a device flag that makes everything queued behind it return at once;
+    // the host looks at the group's count, runs the refused sweep with the batched kernel and goes on behind it.
+    auto stepwise = [&](int it0, int it1, auto pre, auto post) -> int {
+        int r = BCFGPU_OK;
+        const bool spec = persistent && h->nranks == 1 && (select_kernel(h) == BCFGPU_OK) && h->kernel == 4;
+        int* stall = h->d_done + 2;
+        for (int it = it0; it < it1 && r == BCFGPU_OK;) {
+            if (h->stop.load(std::memory_order_relaxed)) return fail(BCFGPU_ERR_INTERRUPTED, "run stopped by bcfgpu_request_stop");
+            if (!spec) {
+                pre(it, nullptr);
+                r = launch_sweeps(1);
+                if (r == BCFGPU_OK) post(it, nullptr);
+                ++it;
+                continue;
+            }
+            const int m = std::min(32, it1 - it);
+            CK(cudaMemsetAsync(h->d_done, 0, 12, h->stream));
+            for (int j = 0; j < m && r == BCFGPU_OK; ++j) {
+                pre(it + j, stall);
+                r = run_persistent(h, 1, true);
+                post(it + j, stall);
+            }
+            if (r) break;
+            int dn_host[3] = {0, 0, 0};
+            CK(cudaMemcpyAsync(dn_host, h->d_done, 12, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            h->last_kernel = 4;
+            h->pipe_sweeps += dn_host[0];
+            if (dn_host[0] >= m) { it += m; continue; }
+            // sweep it + c was refused (its pre() had run): the batched kernel takes it
+            const int c = dn_host[0];
+            h->fallback_sweeps++;
+            CK(cudaMemsetAsync(h->d_done, 0, 12, h->stream));
+            const int keep_kernel = h->kernel;
+            h->kernel = h->fallback_kernel;
+            r = run_persistent(h, 1);
+            h->kernel = keep_kernel;
+            if (r == BCFGPU_OK) post(it + c, nullptr);
+            it += c + 1;
+        }
+        return r;
+    };
+    auto save_index = [&](int it) -> int {   // bcf: sweep it is saved when it >= nburn and it % nthin == 0; which saved sweep is it?
+        if (it < nburn || (it % nthin) != 0) return -1;
+        const int first = (nburn + nthin - 1) / nthin * nthin;
+        const int k = (it - first) / nthin;
+        return k < nsim ? k : -1;
+    };
     if (h->cfg.model == BCFGPU_MODEL_PROBIT_BART) {
         // One sweep per launch: the latent draw opens it (its own kernel: every engine parks the chain state in HBM between
         // launches), the sweep kernel runs it as a burn-in sweep (the engines' own posterior accumulation stays off), and a
         // saved sweep ends with the counterfactual pass.
         const int grid = h->grid_fin;
         const int cfgrid = (int)((d.n_pad + 256 * CF_OBS_PER_THREAD - 1) / (256 * CF_OBS_PER_THREAD));
-        for (int it = 0; it < total && rc == BCFGPU_OK; ++it) {
-            if (h->stop.load(std::memory_order_relaxed)) { rc = fail(BCFGPU_ERR_INTERRUPTED, "run stopped by bcfgpu_request_stop"); break; }
-            k_probit_latent<<<grid, 256, 0, h->stream>>>(d, h->d_ybin, h->d_orig, 0, h->cfg.probit_offset, const_cast<double*>(d.y));
-            h->launches++;
-            rc = launch_sweeps(1, true);
-            if (rc == BCFGPU_OK && it >= nburn && (it % nthin) == 0 && probit_saved < nsim) {
-                // (the sweep flipped the tree parity: the current trees are in trees[parity]; read it back lazily -- it
-                // simply alternates from the value fetched above)
-                const int par = (sc.parity + it + 1) & 1;
+        rc = stepwise(0, total,
+            [&](int, const int* stall) {
+                k_probit_latent<<<grid, 256, 0, h->stream>>>(d, h->d_ybin, h->d_orig, 0, h->cfg.probit_offset, const_cast<double*>(d.y), stall);
+                h->launches++;
+            },
+            [&](int it, const int* stall) {
+                if (save_index(it) < 0) return;
+                const int par = (sc.parity + it + 1) & 1;     // the sweep flipped the tree parity
                 if (h->cfg.treatment_col >= 0) {
-                    CK(cudaMemsetAsync(h->d_cflist, 0, 4, h->stream));
-                    k_cf_collect<<<h->T, 64, 0, h->stream>>>(d, d.trees[par], h->cfg.treatment_col, h->d_cflist);
+                    cudaMemsetAsync(h->d_cflist, 0, 4, h->stream);
+                    k_cf_collect<<<h->T, 64, 0, h->stream>>>(d, d.trees[par], h->cfg.treatment_col, h->d_cflist, stall);
                 }
                 k_cf_accumulate<<<cfgrid, 256, 0, h->stream>>>(d, d.trees[par], h->d_cflist, h->cfg.treatment_col,
-                                                               h->cfg.probit_offset, h->d_orig);
+                                                               h->cfg.probit_offset, h->d_orig, stall);
                 h->launches += 2;
-                ++probit_saved;
-            }
-        }
+            });
         if (rc == BCFGPU_OK) CK(cudaGetLastError());
+        for (int it = 0; it < total; ++it) probit_saved += save_index(it) >= 0 ? 1 : 0;
     } else if (keep_trees) {
         // the sampling part runs one sweep per launch so that the trees of every saved sweep can be copied out between
         // launches (the engines keep only the current forest)
         rc = launch_sweeps(nburn);
-        int saved = 0;
-        for (int it = nburn; it < total && rc == BCFGPU_OK; ++it) {
-            rc = launch_sweeps(1, true);
-            if (rc == BCFGPU_OK && (it % nthin) == 0 && saved < nsim) {
-                const int par = (sc.parity + it + 1) & 1;
-                k_save_trees<<<h->T, 64, 0, h->stream>>>(d, d.trees[par], saved, h->d_pool, h->pool_cap, h->d_pool_used,
-                                                         h->d_tree_off, h->d_tree_cnt, h->d_draw_scal);
-                h->launches++;
-                ++saved;
-            }
-        }
+        if (rc == BCFGPU_OK)
+            rc = stepwise(nburn, total, [&](int, const int*) {},
+                [&](int it, const int* stall) {
+                    const int k = save_index(it);
+                    if (k < 0) return;
+                    const int par = (sc.parity + it + 1) & 1;
+                    k_save_trees<<<h->T, 64, 0, h->stream>>>(d, d.trees[par], k, h->d_pool, h->pool_cap, h->d_pool_used,
+                                                             h->d_tree_off, h->d_tree_cnt, h->d_draw_scal, stall);
+                    h->launches++;
+                });
         if (rc == BCFGPU_OK) CK(cudaGetLastError());
+        int saved = 0;
+        for (int it = nburn; it < total; ++it) saved += save_index(it) >= 0 ? 1 : 0;
         h->forests_saved = saved;
     } else
         rc = launch_sweeps(total);
@@ -1150,6 +1201,12 @@ int bcfgpu_engine_in_use(bcfgpu_handle* h, int32_t out2[2])
     if (!h || !out2) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
     out2[0] = h->last_kernel;
     out2[1] = h->nranks <= 1 ? 0 : (h->last_kernel == 0 ? 1 : 2);
+    return BCFGPU_OK;
+}
+int bcfgpu_engine_stats(bcfgpu_handle* h, int64_t out2[2])
+{
+    if (!h || !out2) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
+    out2[0] = h->pipe_sweeps; out2[1] = h->fallback_sweeps;
     return BCFGPU_OK;
 }
 int bcfgpu_num_saved(bcfgpu_handle* h, int32_t* ns)
@@ -1753,22 +1810,14 @@ static int run_persistent(bcfgpu_handle* h, int total, bool no_sync)
             // pipelined kernel; it returns early at a sweep that holds a tree wider than KB keys: that one sweep is
             // run by the batched kernel, then the pipelined one resumes
             int* dn = h->d_done;
-            CK(cudaMemsetAsync(dn, 0, 8, h->stream));
+            if (!no_sync) CK(cudaMemsetAsync(dn, 0, 12, h->stream));
             d.pr.batch0 = h->pipe_batches;
             int pntl = h->pipe_ntl;
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&pntl, (void*)&dn};
             CK(cudaLaunchCooperativeKernel((const void*)k_pipe, dim3(h->coop_grid), dim3(PIPE_THREADS), args, h->pipe_smem, h->stream));
             h->launches++;
-            if (no_sync && nsw == 1 && h->nranks == 1) {
-                // sweep-by-sweep callers (probit BART, saved forests): no host round trip per sweep -- the batched kernel is
-                // queued behind k_pipe unconditionally and returns at once unless k_pipe left the sweep to it
-                unsigned int* bar2 = bar + 8;                       // its own barrier counters (zeroed with the others)
-                const int* din = dn;
-                void* a2[] = {(void*)&d, (void*)&nsw, (void*)&bar2, (void*)&ntl, (void*)&din};
-                CK(cudaLaunchCooperativeKernel(h->fallback_kernel == 3 ? (const void*)k_batched<true> : (const void*)k_batched<false>, dim3(h->coop_grid),
-                                               dim3(PTHREADS), a2, h->res_smem, h->stream));
-                h->launches++;
-                done += 1;
+            if (no_sync) {   // speculative (stepwise()): the caller zeroed d_done, checks it later and reruns what was refused
+                done += nsw;
                 continue;
             }
             int dn_host[2] = {0, 0};
@@ -1776,8 +1825,10 @@ static int run_persistent(bcfgpu_handle* h, int total, bool no_sync)
             CK(cudaStreamSynchronize(h->stream));
             const int ndone = dn_host[0];
             h->pipe_batches += (unsigned long long)dn_host[1];
+            h->pipe_sweeps += ndone;
             done += ndone;
             if (ndone < nsw) {
+                h->fallback_sweeps++;
                 int one = 1;
                 d.pr.seq0 = (++h->launch_id) << 32;                  // (its own launch: the mailbox sequence numbers restart)
                 CK(cudaMemsetAsync(bar, 0, 16, h->stream));

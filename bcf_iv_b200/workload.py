@@ -11,7 +11,9 @@ import numpy as np
 from . import prep
 
 
-def synthetic_sampler_inputs(n, p, seed=0, rho=0.0, compliance=0.75, effect_size=2.0, continuous=False):
+def synthetic_sampler_inputs(n, p, seed=0, rho=0.0, compliance=0.75, effect_size=2.0, continuous=False, analytic_cuts=False):
+    """continuous: columns 3.. are X = Phi(raw) ~ U(0, 1) -> 10 000-cutpoint grids (uint16 bins), SURVEY 8d's stress variant;
+    analytic_cuts: their cutpoints are the quantiles of U(0, 1) instead of the sample's (no sort of n values per column)."""
     rng = np.random.default_rng(seed)
     X = np.empty((n, p), dtype=np.float64, order="F")
     common = rng.standard_normal(n) * np.sqrt(rho) if rho > 0 else None
@@ -38,7 +40,12 @@ def synthetic_sampler_inputs(n, p, seed=0, rho=0.0, compliance=0.75, effect_size
     x_con[:, p] = pihat
     cuts_x = []
     for v in range(p):
-        cuts_x.append(np.array([0.5]) if not (continuous and v >= 2) else prep.cp_quantile(X[:, v]))
+        if not (continuous and v >= 2):
+            cuts_x.append(np.array([0.5]))
+        elif analytic_cuts:
+            cuts_x.append(np.linspace(0.0, 1.0, prep.CP_NUM + 2)[1:-1])
+        else:
+            cuts_x.append(prep.cp_quantile(X[:, v]))
     cuts_c = cuts_x + [prep.cp_quantile(pihat)]
     cc, oc = prep.pack_cuts(cuts_c)
     cm, om = prep.pack_cuts(cuts_x)

@@ -463,7 +463,38 @@ def run_ours(args):
     sizes = [len(s.get_tree(t)[0]) for t in range(0, T, 5)]
     acc = s.counters()
     sig = s.scalars()["sigma"]
+    stats0 = s.engine_stats
+    # ---- other regimes of the same shape (N = 1 only; extra keys of the line, not the headline) ----
+    regimes = None
+    if world == 1 and not args.no_regimes:
+        peak_gbs, _ = measured_peak_gbs()
+
+        def timed(smp, bx):
+            smp.run(W, 0)
+            torch.cuda.synchronize()
+            smp.run(0, K)
+            v = K / (smp.last_run_ms * 1e-3)
+            nodes = [len(smp.get_tree(t)[0]) for t in range(T)]
+            return {"value": v, "unit": UNIT, "ms_per_step": smp.last_run_ms / K, "steps": K,
+                    "mean_nodes_per_tree": float(np.mean(nodes)), "max_nodes_in_a_tree": int(np.max(nodes)),
+                    "engine_stats_since_create": smp.engine_stats,
+                    "roofline_frac": algorithmic_bytes_per_sweep(n, T, bx) * v / 1e9 / peak_gbs}
+        regimes = {}
+        # (1) the chain far into burn-in: trees at their stationary sizes (the headline burns in args.burnin sweeps)
+        s.run(args.long_burnin - args.burnin - W - K, 0)
+        regimes[f"after_{args.long_burnin}_burnin_sweeps"] = dict(timed(s, 1), note="same chain, same data as the headline")
     s.close()
+    if regimes is not None:
+        # (2) SURVEY 8d's stress variant: continuous covariates -> 10 000-cutpoint grids, uint16 bin columns
+        wc = workload.synthetic_sampler_inputs(n, p, seed=args.data_seed, continuous=True, analytic_cuts=True)
+        sc_ = _lib.Sampler(engine=engine, lambda_=wc["lambda_"], sigma_init=wc["sigma_init"], seed=args.seed, device=local_rank)
+        sc_.set_data(wc["y"], wc["z"], wc["x_con"], wc["x_mod"], wc["cuts_con"], wc["off_con"], wc["cuts_mod"], wc["off_mod"])
+        sc_.run(args.burnin, 0)
+        regimes["continuous_x"] = dict(timed(sc_, 2), burnin_sweeps=args.burnin,
+                                       note=f"X = Phi(raw) on {p - 2} of the {p} covariates: 10 000 cutpoints each, uint16 bins; "
+                                            "roofline_frac on SURVEY 8d's b_x = 2 bytes")
+        sc_.close()
+        del wc
 
     # ---- end-to-end leg through the C-ABI with host buffers ----
     # The call a user makes: create + set_data (H2D of y, z, X from pinned host memory, binning) + run(K) + colMeans(tau)
@@ -535,6 +566,9 @@ def run_ours(args):
     }
     if shard_rec is not None:
         line["sharded"] = shard_rec
+    if regimes is not None:
+        line["regimes"] = regimes
+    line["config"]["engine_stats"] = stats0
     if world == 1 and not args.no_cpu_baseline:
         from oracle import orc
         orc.build()
@@ -568,6 +602,8 @@ def main():
     ap.add_argument("--cpu-sweeps", type=int, default=8)
     ap.add_argument("--cpu-budget", type=float, default=120.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-regimes", action="store_true", help="N = 1: skip the long-burn-in and continuous-X records")
+    ap.add_argument("--long-burnin", type=int, default=2000)
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the observation-sharded record")
     ap.add_argument("--shard-n", type=int, default=10_000_000, help="rows of the observation-sharded record (config 5)")
     ap.add_argument("--shard-p", type=int, default=200)

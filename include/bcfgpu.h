@@ -166,6 +166,9 @@ BCFGPU_API int bcfgpu_h2d_bytes(bcfgpu_handle *h, int64_t *bytes);
 /* what the last run used: out[0] sweep kernel (0 graph of per-tree kernels, 1 k_persistent, 2 k_resident, 3 k_batched,
  * 4 k_pipe, 5 k_batched with the state in HBM), out[1] shards exchange (0 none, 1 ncclAllReduce per tree, 2 in-kernel peer-memory mailboxes) */
 BCFGPU_API int bcfgpu_engine_in_use(bcfgpu_handle *h, int32_t out2[2]);
+/* since create: out2 = {sweeps run by the pipelined kernel, sweeps it handed to the batched kernel because a tree had more
+ * than 8 keys} (counted for multi-sweep launches; sweep-by-sweep callers queue the batched kernel without asking) */
+BCFGPU_API int bcfgpu_engine_stats(bcfgpu_handle *h, int64_t out2[2]);
 
 /* ---- results (standardised scale, original row order; the R wrapper rescales by sd(y)/mean(y)) ---- */
 BCFGPU_API int bcfgpu_num_saved(bcfgpu_handle *h, int32_t *nsaved);

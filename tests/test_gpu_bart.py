@@ -99,3 +99,26 @@ def test_probit_needs_a_binary_response():
         _gpu_sampler(y + 0.5, X, z)
     with pytest.raises(_lib.BcfGpuError):
         _lib.Sampler(model=_lib.MODEL_PROBIT_BART)               # two forests / scales are not a probit BART
+
+
+def test_sweeps_with_wide_trees_are_rerun_by_the_batched_kernel():
+    """Sweep-by-sweep running queues its launches without asking after each: the pipelined kernel refuses a sweep that holds
+    a tree with more than 8 keys and everything queued behind it returns; the host reruns from there with the batched
+    kernel.  Few trees + a strong continuous signal grow such trees: the chain must still be the oracle's, move by move."""
+    rng = np.random.default_rng(2)
+    n = 4000
+    X = rng.random((n, 3))
+    z = (rng.random(n) < 0.5).astype(np.int32)
+    pr = 0.5 + 0.45 * np.sin(9 * X[:, 0]) * np.cos(7 * X[:, 1])
+    y = (rng.random(n) < pr).astype(np.float64)
+    g = _gpu_sampler(y, X, z, seed=3, n_trees=4)
+    o, perm = oracle_probit_sampler(y, X, z, seed=3, n_trees=4, max_leaves=128)
+    g.run(150, 40)
+    out = o.probit_run(150, 40, 1)
+    inv = np.empty(perm.size, np.int64); inv[perm] = np.arange(perm.size)
+    assert np.array_equal(g.trace()[0], o.trace()[0]) and g.counters() == o.counters()
+    assert np.allclose(g.tau_mean(), out["ite_mean"][inv], rtol=1e-8, atol=1e-8)
+    assert max((len(g.get_tree(t)[0]) + 1) // 2 for t in range(4)) > 8        # a tree wider than the pipelined kernel takes
+    st = g.engine_stats
+    assert st["fallback_sweeps"] > 0 and st["pipelined_sweeps"] > 0, st
+    g.close(); o.close()

@@ -287,3 +287,28 @@ def test_bcf_front_end_predicts_at_new_rows():
     assert np.allclose(fit["tau_predict"], fit["tau"][:, :50], rtol=1e-10, atol=1e-10)
     assert np.allclose(fit["tau_predict_mean"], fit["tau_mean"][:50], rtol=1e-10, atol=1e-10)
     assert np.allclose(fit["mu_predict_mean"], fit["mu_mean"][:50], rtol=1e-10, atol=1e-10)
+
+
+def test_saved_forests_with_wide_trees():
+    """keep_draws bit 3 runs the sampling part sweep by sweep; sweeps the pipelined kernel refuses (a tree with more than 8
+    keys) are rerun by the batched kernel: the saved forests still reproduce the fit's draws."""
+    pr = make_problem(n=5000, p=4, seed=33, continuous=True)
+    # a strong smooth signal on a continuous covariate and only three mu trees: they must grow wide
+    from bcf_iv_b200 import prep
+    d = pr.data
+    ywide = 3.0 * np.sin(9.0 * d["X"][:, 2]) + d["y"]
+    pr.P = prep.prepare(ywide, d["z"], d["X"], d["X"], 0.05 * np.random.default_rng(1).standard_normal(pr.n))
+    pr.cuts_c_flat, pr.off_c = prep.pack_cuts(pr.P.cuts_c)
+    pr.cuts_m_flat, pr.off_m = prep.pack_cuts(pr.P.cuts_m)
+    kw = dict(seed=12, ntree_con=3, ntree_mod=2)
+    g = gpu_sampler(pr, keep_draws=7 | 8, **kw)
+    g.run(120, 30)
+    assert max((len(g.get_tree(t)[0]) + 1) // 2 for t in range(5)) > 8
+    assert g.engine_stats["fallback_sweeps"] > 0
+    ins = g.predict(pr.P.x_c, pr.P.x_m, draws=True)
+    assert np.allclose(ins["tau"], g.draws("tau"), rtol=1e-12, atol=1e-12)
+    assert np.allclose(ins["mu"], g.draws("mu"), rtol=1e-12, atol=1e-12)
+    o = oracle_sampler(pr, max_leaves=128, **kw)
+    out = o.run(120, 30, 1)
+    assert np.allclose(g.tau_mean(), out["tau_mean"][pr.P.inv_perm], rtol=1e-7, atol=1e-7)
+    g.close(); o.close()
