@@ -22,7 +22,7 @@ MODEL_BCF, MODEL_PROBIT_BART = 0, 1
 # every symbol include/bcfgpu.h declares (tests check the library exports each of them)
 SYMBOLS = [
     "bcfgpu_abi_version", "bcfgpu_device_count", "bcfgpu_last_error", "bcfgpu_config_init", "bcfgpu_create",
-    "bcfgpu_destroy", "bcfgpu_release_cached_memory", "bcfgpu_cache_stats", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_data", "bcfgpu_run", "bcfgpu_request_stop",
+    "bcfgpu_destroy", "bcfgpu_release_cached_memory", "bcfgpu_cache_stats", "bcfgpu_nccl_unique_id", "bcfgpu_set_shard", "bcfgpu_set_shard_local", "bcfgpu_set_data", "bcfgpu_run", "bcfgpu_request_stop",
     "bcfgpu_fit_chains",
     "bcfgpu_last_run_ms", "bcfgpu_kernel_launches", "bcfgpu_h2d_bytes", "bcfgpu_engine_in_use", "bcfgpu_engine_stats", "bcfgpu_num_saved", "bcfgpu_get_tau_mean", "bcfgpu_get_tau_var",
     "bcfgpu_get_mu_mean", "bcfgpu_get_yhat_mean", "bcfgpu_get_sigma", "bcfgpu_get_scales", "bcfgpu_get_draws",
@@ -83,6 +83,7 @@ def load():
     L.bcfgpu_cache_stats.argtypes = [lp]
     L.bcfgpu_nccl_unique_id.argtypes = [C.c_char_p]
     L.bcfgpu_set_shard.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.bcfgpu_set_shard_local.argtypes = [C.POINTER(vp), C.c_int]
     L.bcfgpu_set_data.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, dp, ip, dp, dp, dp, ip, dp, ip]
     L.bcfgpu_run.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.bcfgpu_request_stop.argtypes = [vp]
@@ -162,6 +163,12 @@ def cache_stats():
     o = np.zeros(2, dtype=np.int64)
     check(load().bcfgpu_cache_stats(_lp(o)))
     return {"device_bytes": int(o[0]), "pinned_bytes": int(o[1])}
+
+
+def set_shard_local(samplers):
+    """make the samplers (one per shard, same process) the shards of one chain; then drive each from its own thread"""
+    hs = (C.c_void_p * len(samplers))(*[s._h for s in samplers])
+    check(load().bcfgpu_set_shard_local(hs, len(samplers)))
 
 
 def nccl_unique_id() -> bytes:

@@ -40,6 +40,16 @@ enum { PUR_MOVE = 0, PUR_NODE = 1, PUR_CUT = 2, PUR_LEAF = 3, PUR_BSCALE1 = 10, 
 constexpr uint32_t TREE_SWEEP_LEVEL = 0xFFFFFFFFu;
 
 enum { ERR_NAN = 1, ERR_FX_RANGE = 2, ERR_BARRIER_TIMEOUT = 4 };
+// a wait gave up: leave a note the host can still read (code, CTA, two details), then trap
+__device__ __noinline__ void give_up(int* dbg, int code, int a, int b)
+{
+    if (dbg != nullptr) {
+        volatile int* q = dbg;
+        q[1] = code; q[2] = (int)blockIdx.x; q[3] = a; q[4] = b; q[0] = 1;
+        __threadfence_system();
+    }
+    __trap();
+}
 
 // ---------------------------------------------------------------------------------------------
 // Flat tree.  Node 0 is the root; nodes are kept compact (swap-with-last on death).
@@ -164,6 +174,7 @@ struct Dev {
     double *sigma_post, *msd_post, *bsd_post;    // [cap]
     int32_t post_cap;
     long long* prof;           // optional [16] cycle counters of CTA 0 (persistent engine), null = off
+    int* dbg;                  // host-mapped pinned words: where a kernel gave up before it trapped (survives the context's death)
 };
 
 // The persistent engines alternate between two statistics buffers by sweep parity: every sweep zeroes the buffer it

@@ -24,12 +24,14 @@ __device__ __forceinline__ int upper_bound_cut(const double* __restrict__ cuts, 
     }
     return lo;
 }
-// grid = (blocks of BIN_ROWS rows, columns of the chunk).  The rows of a block land in two runs of the internal order --
-// its treated rows and its control rows, each contiguous because bcf's permutation is stable -- so the bins are compacted
-// per run in shared memory and leave as aligned 32-bit words: x is read once with coalesced 8-byte loads and every
-// 32-byte sector of the binned column is written once (the scattered byte stores of the first version made the kernel
-// run at a third of the copy bandwidth).
-constexpr int BIN_ROWS = 2048;
+// grid = (blocks of BIN_ROWS rows, groups of BIN_COLS columns of the chunk).  The rows of a block land in two runs of
+// the internal order -- its treated rows and its control rows, each contiguous because bcf's permutation is stable -- so the
+// block works out ONCE where each of its rows goes, then per column compacts the bins per run in shared memory and writes
+// them as aligned 32-bit words; the next column's values are already in flight while one is flushed.  x is read once with
+// coalesced 8-byte loads and every 32-byte sector of a binned column is written once.  (The first versions -- scattered byte
+// stores, then one column per block with a binary search even for one-cutpoint columns -- ran at a third of the copy
+// bandwidth: instruction-bound, 66 % issue utilisation for 72 MB.)
+constexpr int BIN_ROWS = 2048, BIN_COLS = 4;
 template <typename B>
 __device__ __forceinline__ void bin_flush_run(B* __restrict__ dst, int64_t g0, int len, const B* __restrict__ src, int t)
 {
@@ -54,50 +56,64 @@ __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ x, int64
                                              const int32_t* __restrict__ pos, int64_t n_pad, int trt_pad, uint8_t* bins8,
                                              uint16_t* bins16)
 {
-    __shared__ __align__(16) uint16_t sb[BIN_ROWS];               // the block's bins in run order (uint8 columns: as bytes)
-    __shared__ int s_min[2], s_cnt[2];
-    const int c = blockIdx.y;
-    if (c >= ncols) return;
-    const int v = col0 + c, t = threadIdx.x;
-    const double* xc = x + (int64_t)c * n;
-    const double* cv = cuts + off[v];
-    const int nc = off[v + 1] - off[v];
-    const int ci = col_index[v];
-    const bool w16 = col_is16[v] != 0;
-    for (int64_t r0 = (int64_t)blockIdx.x * BIN_ROWS; r0 < n; r0 += (int64_t)gridDim.x * BIN_ROWS) {
-        const int rows = (int)min((int64_t)BIN_ROWS, n - r0);
-        if (t < 2) { s_min[t] = 0x7fffffff; s_cnt[t] = 0; }
-        __syncthreads();
-        int q[BIN_ROWS / 256], bn[BIN_ROWS / 256];
-        int mn[2] = {0x7fffffff, 0x7fffffff}, cnt_t = 0;
+    constexpr int PT = BIN_ROWS / 256;                            // rows per thread
+    __shared__ __align__(16) uint16_t sb[BIN_ROWS];               // the block's bins of one column in run order (uint8 columns: as bytes)
+    __shared__ int s_min[2], s_cnt;
+    const int t = threadIdx.x;
+    const int cg0 = blockIdx.y * BIN_COLS, ncg = min(BIN_COLS, ncols - cg0);
+    const int64_t r0 = (int64_t)blockIdx.x * BIN_ROWS;
+    if (ncg <= 0 || r0 >= n) return;
+    const int rows = (int)min((int64_t)BIN_ROWS, n - r0);
+    // ---- where the block's rows go: treated positions lie below trt_pad and increase with the row, control ones above ----
+    if (t == 0) { s_min[0] = s_min[1] = 0x7fffffff; s_cnt = 0; }
+    __syncthreads();
+    int li[PT];
+    {
+        int q[PT], mn[2] = {0x7fffffff, 0x7fffffff}, cnt_t = 0;
 #pragma unroll
-        for (int k = 0; k < BIN_ROWS / 256; ++k) {
+        for (int k = 0; k < PT; ++k) {
             const int r = k * 256 + t;
-            q[k] = -1; bn[k] = 0;
-            if (r < rows) {
-                q[k] = pos[r0 + r];
-                bn[k] = upper_bound_cut(cv, nc, xc[r0 + r]);
-                const int g = q[k] < trt_pad ? 1 : 0;               // treated positions lie below trt_pad
-                mn[g] = min(mn[g], q[k]);
-                cnt_t += g;
-            }
+            q[k] = r < rows ? pos[r0 + r] : -1;
+            if (q[k] >= 0) { const int g = q[k] < trt_pad ? 1 : 0; mn[g] = min(mn[g], q[k]); cnt_t += g; }
         }
         cnt_t = __reduce_add_sync(0xffffffffu, cnt_t);
         mn[0] = __reduce_min_sync(0xffffffffu, mn[0]);
         mn[1] = __reduce_min_sync(0xffffffffu, mn[1]);
-        if ((t & 31) == 0) { atomicAdd(&s_cnt[1], cnt_t); atomicMin(&s_min[0], mn[0]); atomicMin(&s_min[1], mn[1]); }
+        if ((t & 31) == 0) { atomicAdd(&s_cnt, cnt_t); atomicMin(&s_min[0], mn[0]); atomicMin(&s_min[1], mn[1]); }
         __syncthreads();
-        // the block's treated rows form the run [p0, p0 + n_same), its control rows [o0, o0 + n_other): positions of one
-        // group increase with the row
-        const int n_same = s_cnt[1], n_other = rows - n_same, p0 = s_min[1], o0 = s_min[0];
-        uint8_t* sb8 = reinterpret_cast<uint8_t*>(sb);
 #pragma unroll
-        for (int k = 0; k < BIN_ROWS / 256; ++k)
-            if (q[k] >= 0) {
-                const int li = q[k] < trt_pad ? q[k] - p0 : n_same + (q[k] - o0);
-                if (w16) sb[li] = (uint16_t)bn[k]; else sb8[li] = (uint8_t)bn[k];
-            }
+        for (int k = 0; k < PT; ++k) li[k] = q[k] < 0 ? -1 : (q[k] < trt_pad ? q[k] - s_min[1] : s_cnt + (q[k] - s_min[0]));
+    }
+    // the block's treated rows form the run [p0, p0 + n_same) of every column, its control rows [o0, o0 + n_other)
+    const int n_same = s_cnt, n_other = rows - n_same, p0 = s_min[1], o0 = s_min[0];
+    uint8_t* sb8 = reinterpret_cast<uint8_t*>(sb);
+    double xv[PT];
+#pragma unroll
+    for (int k = 0; k < PT; ++k) { const int r = k * 256 + t; xv[k] = r < rows ? x[(int64_t)cg0 * n + r0 + r] : 0.0; }
+    for (int cc = 0; cc < ncg; ++cc) {
+        const int c = cg0 + cc, v = col0 + c;
+        double xn[PT];
+        if (cc + 1 < ncg) {                                        // the next column's values fly while this one is binned and flushed
+#pragma unroll
+            for (int k = 0; k < PT; ++k) { const int r = k * 256 + t; xn[k] = r < rows ? x[(int64_t)(c + 1) * n + r0 + r] : 0.0; }
+        }
+        const double* cv = cuts + off[v];
+        const int nc = off[v + 1] - off[v];
+        const bool w16 = col_is16[v] != 0;
+        if (nc == 1) {                                             // two-valued columns (the reference's covariates): one compare
+            const double c0v = cv[0];
+#pragma unroll
+            for (int k = 0; k < PT; ++k) if (li[k] >= 0) sb8[li[k]] = (uint8_t)(c0v <= xv[k] ? 1 : 0);
+        } else {
+#pragma unroll
+            for (int k = 0; k < PT; ++k)
+                if (li[k] >= 0) {
+                    const int b = upper_bound_cut(cv, nc, xv[k]);
+                    if (w16) sb[li[k]] = (uint16_t)b; else sb8[li[k]] = (uint8_t)b;
+                }
+        }
         __syncthreads();
+        const int ci = col_index[v];
         if (w16) {
             uint16_t* dst = bins16 + (int64_t)ci * n_pad;
             if (n_same > 0) bin_flush_run<uint16_t>(dst, p0, n_same, sb, t);
@@ -108,6 +124,10 @@ __global__ void __launch_bounds__(256) k_bin(const double* __restrict__ x, int64
             if (n_other > 0) bin_flush_run<uint8_t>(dst, o0, n_other, sb8 + n_same, t);
         }
         __syncthreads();
+        if (cc + 1 < ncg) {
+#pragma unroll
+            for (int k = 0; k < PT; ++k) xv[k] = xn[k];
+        }
     }
 }
 // bcf's perm = order(z, decreasing = TRUE), applied on the device: one CTA per chunk of PLACE_CHUNK rows, whose count of

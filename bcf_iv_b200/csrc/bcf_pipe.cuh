@@ -120,12 +120,12 @@ __device__ __forceinline__ void st_release_cta_s32(int* p, int v)
 }
 
 // one lane waits for a CTA-local progress counter to reach `target` (bounded: a logic error traps instead of hanging)
-__device__ __forceinline__ void pipe_wait_flag(const int* p, int target, int32_t* err, unsigned ns)
+__device__ __forceinline__ void pipe_wait_flag(const int* p, int target, int32_t* err, unsigned ns, int* dbg = nullptr, int what = 0)
 {
     const long long t0 = clock64();
     while (ld_acquire_cta_s32(p) < target) {
         __nanosleep(ns);
-        if (clock64() - t0 > 8000000000ll) { atomicOr(err, ERR_BARRIER_TIMEOUT); __trap(); }
+        if (clock64() - t0 > 8000000000ll) { atomicOr(err, ERR_BARRIER_TIMEOUT); give_up(dbg, 10 + what, target, ld_acquire_cta_s32(p)); }
     }
 }
 
@@ -431,6 +431,9 @@ __device__ inline void pipe_stage_trees(SmallStage* st, const Dev& d, const Tree
     __syncwarp();
 }
 
+#ifndef LL_TIMEOUT
+#define LL_TIMEOUT 120000000000ll
+#endif
 // ---- observation shards (see PeerDev, Mailbox::ll): the exchange of a batch's reduced words ----
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p)
 {
@@ -527,7 +530,7 @@ __device__ inline void pipe_resolve(PipeSmem& sm, SmallStage* st, const PipePlan
 #pragma unroll
                     for (int it = 0; it < NT_IT + NX_IT; ++it)
                         if (need[it]) { if ((pv[it] & 0xFFFFull) == tag) need[it] = false; else all = false; }
-                    if (!all && clock64() - t0 > 120000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); __trap(); }
+                    if (!all && clock64() - t0 > LL_TIMEOUT) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); give_up(d.dbg, 20, p, (int)gtag); }
                 }
 #pragma unroll
                 for (int it = 0; it < NT_IT; ++it) tv[it] += (long long)pv[it] >> 16;       // (words not needed stayed 0)
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
 #define PPROF(k) do { if (cprof) { const long long now_ = clock64(); if (prof) atomicAdd((unsigned long long*)&d.prof[k], (unsigned long long)(now_ - tp)); atomicAdd((unsigned long long*)&d.prof[1024 + blockIdx.x * 8 + (k)], (unsigned long long)(now_ - tp)); tp = now_; } } while (0)
 #endif
                 int first = 0, b = 0;
-                if (lane == 0) pipe_wait_flag(&sm.plan_ready, 1, d.err, 20);     // the first plan
+                if (lane == 0) pipe_wait_flag(&sm.plan_ready, 1, d.err, 20, d.dbg, 1);     // the first plan
                 __syncwarp();
                 while (first < T) {
                     const PipePlan& P = sm.plan[b & 3];
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                     for (int lt = tw; lt < ntl; lt += PT_WARPS) pipe_stats_tile(sm, sm.p.acc[b & 1], P, d, rs, tile0, lt, lane, pw, b & 1, ntl <= PT_WARPS);
                     // the next plan is made two batches ahead: warp 0 checks it (an acquire load: kept off the other
                     // warps, and away from the apply's stores) and the barrier hands the knowledge to everybody
-                    if (tw == 0 && lane == 0 && first + P.nb < T) pipe_wait_flag(&sm.plan_ready, b + 2, d.err, 20);
+                    if (tw == 0 && lane == 0 && first + P.nb < T) pipe_wait_flag(&sm.plan_ready, b + 2, d.err, 20, d.dbg, 2);
                     named_sync(BAR_S, PT_THREADS);                               // every tile warp is through STATS(b)
                     PPROF(0); PTRACE(1);
                     pipe_flush(sm.p.acc[b & 1], P, totals, cross, tw * 32 + lane);
@@ -803,7 +806,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                         const long long t0 = clock64();
                         while (ld_acquire_u32(bar + (ub & 1)) < ubatch[ub & 1]) {
                             __nanosleep(100);
-                            if (clock64() - t0 > 8000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); __trap(); }
+                            if (clock64() - t0 > 8000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); give_up(d.dbg, 30, ub, (int)ubatch[ub & 1]); }
                         }
                     }
                     __syncwarp();
@@ -818,7 +821,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
 #endif
                 while (pfirst < T) {
                     if (pb >= 2) {
-                        if (lane == 0) pipe_wait_flag(&sm.flushed, pb - 1, d.err, pusher ? 40 : 200);
+                        if (lane == 0) pipe_wait_flag(&sm.flushed, pb - 1, d.err, pusher ? 40 : 200, d.dbg, 3);
                         __syncwarp();
                         // observation shards: batch pb - 2 is flushed by this CTA; once every CTA of this rank has flushed
                         // it, its reduced words go to the peer this CTA serves -- first thing, before the planning: the
@@ -837,7 +840,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                 }
                 if (pusher)
                     for (int ub = max(pb - 2, 0); ub < pb; ++ub) {               // the sweep's last two batches
-                        if (lane == 0) pipe_wait_flag(&sm.flushed, ub + 1, d.err, 40);
+                        if (lane == 0) pipe_wait_flag(&sm.flushed, ub + 1, d.err, 40, d.dbg, 4);
                         __syncwarp();
                         push_batch(ub);
                     }
@@ -877,7 +880,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                     const long long t0 = clock64();
                     while (ld_acquire_u32(bar + (b & 1)) < tbatch[b & 1]) {
                         __nanosleep(40);   // the pass warps of this SM need the issue slots
-                        if (clock64() - t0 > 8000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); __trap(); }
+                        if (clock64() - t0 > 8000000000ll) { atomicOr(d.err, ERR_BARRIER_TIMEOUT); give_up(d.dbg, 40, b, (int)tbatch[b & 1]); }
                     }
                 }
                 named_sync(BAR_RES, PR_THREADS);

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <string>
@@ -81,6 +82,7 @@ constexpr int NCCL_INT8 = 0, NCCL_INT64 = 4, NCCL_SUM = 0, NCCL_MIN = 3;
 // handle
 // ------------------------------------------------------------------------------------------------
 struct Block { void* p; size_t bytes; };   // a block of the caching allocator (below)
+struct LocalGroup;
 struct ForestHost {
     int p = 0, p8 = 0, p16 = 0;
     std::vector<int32_t> off, ncut, col_index;
@@ -101,6 +103,8 @@ struct bcfgpu_handle {
     void* comm = nullptr;
     Mailbox* d_mail = nullptr;        // [nranks] this rank's mailboxes (peer-memory exchange of the sharded mode)
     Mailbox* peer_mail[MAX_RANKS] = {nullptr};   // the peers' mailbox arrays, mapped with cudaIpc
+    LocalGroup* local = nullptr;      // shards inside one process (bcfgpu_set_shard_local)
+    bool no_pipe = false;             // ... three or more of them on this device: the batched kernel only
     bool peer_ok = false;             // every rank mapped every peer: the sweep kernel exchanges through NVLink itself
     unsigned long long launch_id = 0;
     int64_t pipe_sweeps = 0, fallback_sweeps = 0;   // sweeps the pipelined kernel ran / handed to the batched kernel (a tree wider than 8 keys)
@@ -141,6 +145,7 @@ struct bcfgpu_handle {
     SavedNode* d_pool = nullptr; long long pool_cap = 0; unsigned long long* d_pool_used = nullptr;
     long long* d_tree_off = nullptr; int32_t* d_tree_cnt = nullptr; SavedDraw* d_draw_scal = nullptr;
     int32_t forests_saved = 0;
+    int* dbg_host = nullptr;          // mapped pinned words the kernels write before they trap (Dev::dbg)
     uint8_t* d_ybin = nullptr;        // probit BART: the observed 0/1 response, internal order
     int* d_cflist = nullptr;          // probit BART: trees that split on the treatment (k_cf_collect)
     std::atomic<int> stop{0};         // bcfgpu_request_stop: the run in progress ends at its next launch boundary
@@ -362,6 +367,8 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming);
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_binned[b], cudaEventDisableTiming);
     }
+    if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&h->dbg_host, 64, cudaHostAllocMapped);
+    if (e2 == cudaSuccess) memset(h->dbg_host, 0, 64);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev1);
     if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -387,6 +394,7 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     return BCFGPU_OK;
 }
 
+static void release_local_group(LocalGroup* g);
 int bcfgpu_destroy(bcfgpu_handle* h)
 {
     if (!h) return BCFGPU_OK;
@@ -395,11 +403,13 @@ int bcfgpu_destroy(bcfgpu_handle* h)
     drop_graph(h);
     free_list(h, h->allocs);
     free_list(h, h->run_allocs);
-    for (int p = 0; p < MAX_RANKS; ++p) if (h->peer_mail[p]) cudaIpcCloseMemHandle(h->peer_mail[p]);
+    if (!h->local) for (int p = 0; p < MAX_RANKS; ++p) if (h->peer_mail[p]) cudaIpcCloseMemHandle(h->peer_mail[p]);
     if (h->d_mail) cudaFree(h->d_mail);
+    if (h->local) release_local_group(h->local);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int b = 0; b < 2; ++b) { if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]); if (h->ev_binned[b]) cudaEventDestroy(h->ev_binned[b]); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->dbg_host) cudaFreeHost(h->dbg_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -475,11 +485,99 @@ int bcfgpu_set_shard(bcfgpu_handle* h, int rank, int nranks, const char nccl_uni
 
 }  // extern "C"
 
-// all-reduce (sum) of int64 words across shards; no-op on one rank
-static int shard_allreduce(bcfgpu_handle* h, long long* buf, size_t count)
+// Shards that live in ONE process (bcfgpu_set_shard_local: one handle per shard, each driven by its own host thread;
+// the shards may even share a GPU, each on a share of its SMs): the few host-side reductions go through this object
+// instead of NCCL, the in-kernel exchange through mailboxes the handles reach directly (same address space).
+struct LocalGroup {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n = 0, arrived = 0, refs = 0;
+    long long gen = 0;
+    std::vector<long long> acc, res;
+};
+static int local_allreduce(bcfgpu_handle* h, long long* dbuf, size_t count, bool take_min)
+{
+    LocalGroup* g = h->local;
+    std::vector<long long> v(count);
+    CK(cudaMemcpyAsync(v.data(), dbuf, count * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    {
+        std::unique_lock<std::mutex> lk(g->mu);
+        if (g->arrived == 0) g->acc = v;
+        else for (size_t i = 0; i < count; ++i) g->acc[i] = take_min ? std::min(g->acc[i], v[i]) : g->acc[i] + v[i];
+        if (++g->arrived == g->n) { g->res = g->acc; g->arrived = 0; ++g->gen; g->cv.notify_all(); }
+        else { const long long my = g->gen; g->cv.wait(lk, [&] { return g->gen != my; }); }
+        v = g->res;
+    }
+    CK(cudaMemcpyAsync(dbuf, v.data(), count * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BCFGPU_OK;
+}
+static void release_local_group(LocalGroup* g)
+{
+    bool last;
+    { std::lock_guard<std::mutex> lk(g->mu); last = --g->refs == 0; }
+    if (last) delete g;
+}
+// all-reduce of int64 words across shards (sum, or min); no-op on one rank
+static int shard_allreduce(bcfgpu_handle* h, long long* buf, size_t count, bool take_min = false)
 {
     if (h->nranks <= 1) return BCFGPU_OK;
-    NK(g_nccl.AllReduce(buf, buf, count, NCCL_INT64, NCCL_SUM, h->comm, h->stream));
+    if (h->local) return local_allreduce(h, buf, count, take_min);
+    NK(g_nccl.AllReduce(buf, buf, count, NCCL_INT64, take_min ? NCCL_MIN : NCCL_SUM, h->comm, h->stream));
+    return BCFGPU_OK;
+}
+
+extern "C" int bcfgpu_set_shard_local(bcfgpu_handle** hs, int nranks)
+{
+    if (!hs || nranks < 1 || nranks > MAX_RANKS) return fail(BCFGPU_ERR_BAD_ARG, "need 1 .. 8 handles");
+    for (int r = 0; r < nranks; ++r) {
+        if (!hs[r]) return fail(BCFGPU_ERR_BAD_ARG, "null handle");
+        if (hs[r]->has_data || hs[r]->nranks > 1) return fail(BCFGPU_ERR_STATE, "set_shard_local must come before set_data, once");
+        if (hs[r]->cfg.engine == BCFGPU_ENGINE_GRAPH) return fail(BCFGPU_ERR_BAD_ARG, "in-process shards need a sweep kernel with the in-kernel exchange (not ENGINE_GRAPH)");
+    }
+    if (nranks == 1) { hs[0]->rank = 0; hs[0]->nranks = 1; return BCFGPU_OK; }
+    LocalGroup* g = new LocalGroup();
+    g->n = nranks; g->refs = nranks;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int r = 0; r < nranks; ++r) {
+        bcfgpu_handle* h = hs[r];
+        // Shards that share a device run side by side, each spinning on the others' words: together they must leave a few
+        // SMs free, or the small kernels (memsets, permutations) of a shard that is not in its sweep kernel yet would wait
+        // for an SM that never comes.
+        int same = 0;
+        for (int q = 0; q < nranks; ++q) same += hs[q]->device == h->device ? 1 : 0;
+        if (same > 1) {
+            const int share = std::max(1, (h->num_sms - 4) / same);
+            h->cfg.max_ctas = h->cfg.max_ctas > 0 ? std::min(h->cfg.max_ctas, share) : share;
+        }
+        // Observed on B200: a third pipelined sweep kernel (1024-thread CTAs, the whole register file and ~200 KB of shared
+        // memory per CTA) is not scheduled while two others spin on the same device, whatever their grid sizes; four batched
+        // kernels are.  Three or more shards of one device therefore run the batched kernel.
+        h->no_pipe = same > 2;
+        CK(cudaSetDevice(h->device));
+        CK(cudaMalloc((void**)&h->d_mail, sizeof(Mailbox) * nranks));
+        CK(cudaMemset(h->d_mail, 0, sizeof(Mailbox) * nranks));
+        h->rank = r; h->nranks = nranks; h->local = g;
+    }
+    for (int r = 0; r < nranks; ++r) {
+        CK(cudaSetDevice(hs[r]->device));
+        for (int p = 0; p < nranks; ++p) {
+            if (p == r) continue;
+            if (hs[p]->device != hs[r]->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, hs[r]->device, hs[p]->device));
+                if (!can) return fail(BCFGPU_ERR_CUDA, "no peer access between the shards' devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess(hs[p]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(BCFGPU_ERR_CUDA, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            hs[r]->peer_mail[p] = hs[p]->d_mail;
+        }
+        hs[r]->peer_ok = true;
+    }
+    cudaSetDevice(cur);
     return BCFGPU_OK;
 }
 
@@ -597,7 +695,7 @@ static int bin_forest(bcfgpu_handle* h, int f, const double* x)
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0);
         if (e != cudaSuccess) break;
         h->h2d_bytes += (int64_t)bytes;
-        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + BIN_ROWS - 1) / BIN_ROWS, 65535)), (unsigned)nc);
+        dim3 grid((unsigned)((n + BIN_ROWS - 1) / BIN_ROWS), (unsigned)((nc + BIN_COLS - 1) / BIN_COLS));
         k_bin<<<grid, 256, 0, h->stream>>>((const double*)stage[b].p, n, nc, c0, F.d_cuts, F.d_off, F.d_col_index, F.d_is16, h->d_pos,
                                             h->n_pad, (int)((int64_t)h->dev.trt_tiles * TILE), F.d_bins8, F.d_bins16);
         h->launches++;
@@ -715,6 +813,7 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
     memset(&d, 0, sizeof(Dev));
     d.pr.rank = h->rank; d.pr.nranks = h->peer_ok ? h->nranks : 1; d.pr.seq0 = 0; d.pr.mine = h->d_mail;
     for (int p = 0; p < MAX_RANKS; ++p) d.pr.peer[p] = h->peer_mail[p];
+    d.dbg = h->dbg_host;       // (unified addressing: the mapped host pointer is valid on the device)
     d.n_pad = n_pad; d.n_tiles = (int32_t)(n_pad / TILE); d.trt_tiles = (int32_t)(trt_pad / TILE);
     d.T = h->T; d.max_leaves = c.max_leaves; d.min_leaf = c.min_leaf;
     d.use_muscale = c.use_muscale; d.use_tauscale = c.use_tauscale;
@@ -975,7 +1074,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
             long long ok = h->kernel == 4 ? 2 : (h->kernel == 3 || h->kernel == 5) ? 1 : 0;
             long long* dq = (long long*)h->d_tmp;
             CK(cudaMemcpyAsync(dq, &ok, 8, cudaMemcpyHostToDevice, h->stream));
-            NK(g_nccl.AllReduce(dq, dq, 1, NCCL_INT64, NCCL_MIN, h->comm, h->stream));
+            if ((rc = shard_allreduce(h, dq, 1, true))) return rc;
             CK(cudaMemcpyAsync(&ok, dq, 8, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             if (ok == 1 && h->kernel == 4) h->kernel = h->fallback_kernel;     // a peer's shard does not fit the pipelined kernel
@@ -1103,7 +1202,16 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
         h->forests_saved = saved;
     } else
         rc = launch_sweeps(total);
-    if (rc) { cudaStreamSynchronize(h->stream); return rc; }
+    if (rc) {
+        cudaStreamSynchronize(h->stream);
+        if (h->dbg_host && h->dbg_host[0]) {
+            char note[160];
+            snprintf(note, sizeof(note), " [kernel gave up: code %d (1x: flag wait, 20: peer words, 30: utility warp's grid barrier, 40: chain's grid barrier), CTA %d, %d, %d; rank %d]",
+                     h->dbg_host[1], h->dbg_host[2], h->dbg_host[3], h->dbg_host[4], h->rank);
+            g_err += note;
+        }
+        return rc;
+    }
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     float ms = 0.f;
@@ -1765,7 +1873,7 @@ static int select_kernel(bcfgpu_handle* h)
                 }
             }
             // the pipelined kernel on top of it (the batched one then serves the sweeps that hold a wide tree)
-            if ((h->kernel == 3 || h->kernel == 5) && may_reside && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && (h->nranks == 1 || h->peer_ok)) {
+            if ((h->kernel == 3 || h->kernel == 5) && may_reside && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && (h->nranks == 1 || h->peer_ok) && !h->no_pipe) {
                 h->fallback_kernel = h->kernel;
                 const size_t needp = PIPE_SMEM_BYTES + (size_t)ntl_max * PIPE_BYTES_PER_TILE + (size_t)h->T * sizeof(TMeta) + 16;
                 if (fits((const void*)k_pipe, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; h->pipe_ntl = ntl_max; }

@@ -126,6 +126,12 @@ BCFGPU_API int bcfgpu_cache_stats(int64_t out2[2]);
  * the caller (torch.distributed, MPI, ...).  Each rank then passes only ITS rows to set_data. */
 BCFGPU_API int bcfgpu_nccl_unique_id(char id_out[128]);
 BCFGPU_API int bcfgpu_set_shard(bcfgpu_handle *h, int rank, int nranks, const char nccl_unique_id[128]);
+/* The same mode with every shard in ONE process: handles[r] becomes shard r of nranks (1 .. 8).  No NCCL, no IPC: the
+ * handles reach each other's mailboxes directly (peer access is enabled between their devices); the few host-side
+ * reductions meet in a barrier, so set_data / run / set_tree must then be called for all shards CONCURRENTLY, one host
+ * thread per handle.  The shards may share a GPU: each then gets an equal share of its SMs (a few are left free for the
+ * small kernels around the sweeps), so the whole sharded path, exchange included, runs on a single device. */
+BCFGPU_API int bcfgpu_set_shard_local(bcfgpu_handle **handles, int nranks);
 
 /* ---- data ------------------------------------------------------------------------------------
  * y: standardised outcome (n); z: 0/1 treatment = BayesIV's instrument (n);
