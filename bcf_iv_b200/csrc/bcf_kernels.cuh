@@ -50,7 +50,7 @@ __device__ __forceinline__ void bin_flush_run(B* __restrict__ dst, int64_t g0, i
     const int tail0 = head + PER * nwords;
     if (t < len - tail0) dst[g0 + tail0 + t] = src[tail0 + t];
 }
-__global__ void __launch_bounds__(256) k_bin(const double* __restrict__ x, int64_t n, int ncols, int col0,
+__global__ void __launch_bounds__(256, 4) k_bin(const double* __restrict__ x, int64_t n, int ncols, int col0,
                                              const double* __restrict__ cuts, const int32_t* __restrict__ off,
                                              const int32_t* __restrict__ col_index, const uint8_t* __restrict__ col_is16,
                                              const int32_t* __restrict__ pos, int64_t n_pad, int trt_pad, uint8_t* bins8,

@@ -697,9 +697,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
             res_st8(rs.G + toff, lane, gc);
         }
     __syncthreads();
+    if (d.dbg != nullptr && t == 0 && blockIdx.x == 0) ((volatile int*)d.dbg)[8] += 1;      // launches of this kernel that started running
     pipe_propose_all(sm, d, d.trees[scs.parity], scs.sweep);
     grid_all();
     if (!grid_all_wait()) return;
+    if (d.dbg != nullptr && t == 0 && blockIdx.x == 0) ((volatile int*)d.dbg)[9] += 1;      // ... and got through their first grid barrier
 
     int done = 0;
     for (int sw = 0; sw < nsweeps; ++sw) {

@@ -427,7 +427,8 @@ static int setup_peers(bcfgpu_handle* h)
     h->peer_ok = false;
     if (h->nranks > MAX_RANKS || !g_nccl.AllGather || getenv("BCFGPU_NO_PEER")) return BCFGPU_OK;
     CK(cudaMalloc((void**)&h->d_mail, sizeof(Mailbox) * h->nranks));
-    CK(cudaMemset(h->d_mail, 0, sizeof(Mailbox) * h->nranks));
+    CK(cudaMemsetAsync(h->d_mail, 0, sizeof(Mailbox) * h->nranks, h->stream));   // (ordered on the handle's stream, see set_shard_local)
+    CK(cudaStreamSynchronize(h->stream));
     cudaIpcMemHandle_t mine;
     CK(cudaIpcGetMemHandle(&mine, h->d_mail));
     char *d_send = nullptr, *d_recv = nullptr;
@@ -558,7 +559,11 @@ extern "C" int bcfgpu_set_shard_local(bcfgpu_handle** hs, int nranks)
         h->no_pipe = same > 2;
         CK(cudaSetDevice(h->device));
         CK(cudaMalloc((void**)&h->d_mail, sizeof(Mailbox) * nranks));
-        CK(cudaMemset(h->d_mail, 0, sizeof(Mailbox) * nranks));
+        // (on the handle's own stream and waited for: a memset on the legacy stream is not ordered before the sweep kernels
+        // of the non-blocking streams, and one that ran late would wipe words a peer has already pushed)
+        CK(cudaMemsetAsync(h->d_mail, 0, sizeof(Mailbox) * nranks, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaDeviceSynchronize());
         h->rank = r; h->nranks = nranks; h->local = g;
     }
     for (int r = 0; r < nranks; ++r) {
@@ -1204,10 +1209,15 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
         rc = launch_sweeps(total);
     if (rc) {
         cudaStreamSynchronize(h->stream);
-        if (h->dbg_host && h->dbg_host[0]) {
+        if (h->dbg_host && !h->dbg_host[0] && h->nranks > 1) {
             char note[160];
-            snprintf(note, sizeof(note), " [kernel gave up: code %d (1x: flag wait, 20: peer words, 30: utility warp's grid barrier, 40: chain's grid barrier), CTA %d, %d, %d; rank %d]",
-                     h->dbg_host[1], h->dbg_host[2], h->dbg_host[3], h->dbg_host[4], h->rank);
+            snprintf(note, sizeof(note), " [rank %d: k_pipe launches started %d, past their first barrier %d]", h->rank, h->dbg_host[8], h->dbg_host[9]);
+            g_err += note;
+        }
+        if (h->dbg_host && h->dbg_host[0]) {
+            char note[320];
+            snprintf(note, sizeof(note), " [kernel gave up: code %d (1x: flag wait, 20: peer words, 30: utility warp's grid barrier, 40: chain's grid barrier), CTA %d, %d, %d; rank %d; k_pipe launches started %d, past their first barrier %d]",
+                     h->dbg_host[1], h->dbg_host[2], h->dbg_host[3], h->dbg_host[4], h->rank, h->dbg_host[8], h->dbg_host[9]);
             g_err += note;
         }
         return rc;

@@ -22,3 +22,4 @@ for engine in (5, 4, 2):
             bad += 1
             print(f"engine {engine} rep {rep}: DIFFERENT sigma {got[0]!r} vs {ref[0]!r} counters {got[1]} vs {ref[1]} cache mismatches {mism}", flush=True)
     print(f"engine {engine}: {bad} of {reps} runs differ", flush=True)
+
