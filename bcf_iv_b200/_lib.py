@@ -29,6 +29,7 @@ SYMBOLS = [
     "bcfgpu_num_saved_forests", "bcfgpu_predict", "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
     "bcfgpu_get_tree", "bcfgpu_set_tree", "bcfgpu_get_leaf_ids", "bcfgpu_verify_leaf_cache", "bcfgpu_op_bin_column",
     "bcfgpu_op_suffstats", "bcfgpu_op_hist_all", "bcfgpu_op_lil", "bcfgpu_op_rng_probe", "bcfgpu_op_probit_latent",
+    "bcfgpu_glm_logit", "bcfgpu_lm_sigma",
 ]
 
 
@@ -116,6 +117,8 @@ def load():
     L.bcfgpu_op_lil.argtypes = [dp, dp, dp, C.c_int32, dp]
     L.bcfgpu_op_rng_probe.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp]
     L.bcfgpu_op_probit_latent.argtypes = [dp, ip, dp, C.c_int32, dp]
+    L.bcfgpu_glm_logit.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, C.c_int32, ip, C.c_int32, C.c_double, dp, dp, dp, ip]
+    L.bcfgpu_lm_sigma.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, C.c_int32, ip, dp, dp, dp, ip]
     for nm in SYMBOLS:
         f = getattr(L, nm)
         if nm not in ("bcfgpu_last_error", "bcfgpu_config_init"):
@@ -485,3 +488,49 @@ def op_probit_latent(m, y, u):
     u = np.ascontiguousarray(u, dtype=np.float64); o = np.zeros(m.size)
     check(load().bcfgpu_op_probit_latent(_dp(m), _ip(y), _dp(u), m.size, _dp(o)))
     return o
+
+
+def _matrix_arg(X):
+    """(array kept alive, row_major flag) of an n x p float64 matrix handed over without a host-side transpose"""
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 1:
+        X = X[:, None]
+    if X.flags.f_contiguous:
+        return X, 0
+    return np.ascontiguousarray(X), 1
+
+
+def glm_logit(z, X, device=0, max_iter=25, epsilon=1e-8, full=False):
+    """stats::glm(z ~ X, family = binomial) + predict(type = "link") on the device (R/bcf_iv.R:72-75, R/bcf_itt.R:58-61):
+    the linear predictor (log-odds) of every row.  full=True also returns coefficients (NaN = aliased), deviance, info."""
+    Xa, rm = _matrix_arg(X)
+    n, p = Xa.shape
+    zi = np.ascontiguousarray(np.asarray(z).ravel(), dtype=np.int32)
+    if zi.size != n:
+        raise ValueError("z and X must have the same number of rows")
+    eta = np.empty(n)
+    beta = np.empty(p + 1)
+    dev = np.zeros(1)
+    info = np.zeros(4, dtype=np.int32)
+    check(load().bcfgpu_glm_logit(device, n, p, _dp(Xa), rm, _ip(zi), max_iter, epsilon, _dp(eta), _dp(beta), _dp(dev), _ip(info)))
+    if full:
+        return eta, {"beta": beta, "deviance": float(dev[0]), "iterations": int(info[0]), "converged": bool(info[1]),
+                     "rank": int(info[2]), "launches": int(info[3])}
+    return eta
+
+
+def lm_sigma(y, z, X, device=0, full=False):
+    """summary(lm(y ~ z + X))$sigma on the device (bcf's default sighat); z may be None."""
+    Xa, rm = _matrix_arg(X)
+    n, p = Xa.shape
+    ya = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+    zi = None if z is None else np.ascontiguousarray(np.asarray(z).ravel(), dtype=np.int32)
+    if ya.size != n or (zi is not None and zi.size != n):
+        raise ValueError("y, z and X must have the same number of rows")
+    sig = np.zeros(1)
+    beta = np.empty(1 + (zi is not None) + p)
+    info = np.zeros(2, dtype=np.int32)
+    check(load().bcfgpu_lm_sigma(device, n, p, _dp(Xa), rm, _ip(zi), _dp(ya), _dp(sig), _dp(beta), _ip(info)))
+    if full:
+        return float(sig[0]), {"beta": beta, "rank": int(info[0]), "launches": int(info[1])}
+    return float(sig[0])

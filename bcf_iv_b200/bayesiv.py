@@ -7,7 +7,7 @@ complier proportion -> ITT by Bayesian Causal Forest (THE HOT PATH, R/bcf_iv.R:8
 sample -> p-value adjustment on the leaves.  The R version of the same glue is bcf_iv_b200/R/BayesIVgpu/R/.
 
 Everything except the samplers stays on the CPU (north_star): the pieces R takes from rpart / AER / stats are restated
-here in closed form (`cart`, `tsls`, `p_adjust`, `logit_link`).  The reference's second sampler, bartCause::bartc
+here in closed form (`cart`, `tsls`, `p_adjust`); the logistic propensity model (`logit_link`) runs on the device.  The reference's second sampler, bartCause::bartc
 (probit BART S-learner: the complier proportion of every call, R/bcf_iv.R:78-80, and the whole model when binary = TRUE,
 R/bcf_iv.R:198-202, R/bcf_itt.R:166-170), is bcf_iv_b200.bart.bartc: the same library's probit-BART model on the GPU.
 Deviations:
@@ -30,33 +30,10 @@ COLUMNS = ["node", "CCACE", "pvalue", "Weak_IV_test", "Pi_obs", "ITT", "Pi_compl
 # ---------------------------------------------------------------------------------------------------------------
 # stats::glm(z ~ x, binomial) + predict(type = "link")   (R/bcf_iv.R:72-75)
 # ---------------------------------------------------------------------------------------------------------------
-def logit_link(z, X, iters=25, tol=1e-8):
-    """IRLS logistic regression of z on (1, X); returns the linear predictor (log-odds), as predict.glm does by default."""
-    z = np.asarray(z, dtype=np.float64)
-    A = np.column_stack([np.ones(len(z)), np.asarray(X, dtype=np.float64)])
-    # drop aliased columns the way glm does (their coefficient is NA and they do not enter the prediction): a column
-    # depends on the ones to its left exactly when the same holds in the Gram matrix, whose QR costs O(p^3), not O(n p^2)
-    # in LAPACK's unblocked tall QR (3 s at n = 2e5, p = 100)
-    r = np.linalg.qr(A.T @ A, mode="r")
-    dr = np.abs(np.diag(r))
-    keep = dr > 1e-12 * max(1.0, dr.max())
-    A = A[:, keep]
-    beta = np.zeros(A.shape[1])
-    eta = np.zeros(len(z))
-    dev_old = np.inf
-    for _ in range(iters):
-        mu = 1.0 / (1.0 + np.exp(-eta))
-        wgt = np.clip(mu * (1.0 - mu), 1e-10, None)
-        zz = eta + (z - mu) / wgt
-        AtW = A.T * wgt
-        beta = np.linalg.solve(AtW @ A, AtW @ zz)
-        eta = A @ beta
-        mu = np.clip(1.0 / (1.0 + np.exp(-eta)), 1e-12, 1 - 1e-12)
-        dev = -2.0 * np.sum(z * np.log(mu) + (1 - z) * np.log(1 - mu))
-        if abs(dev - dev_old) / (abs(dev) + 0.1) < tol:
-            break
-        dev_old = dev
-    return eta
+def logit_link(z, X, device=0):
+    """glm(z ~ X, family = binomial) followed by predict(): the linear predictor (log-odds), predict.glm's default scale.
+    IRLS on the device (bcfgpu_glm_logit: weighted Gram matrix + streaming passes in CUDA); no host path."""
+    return _bcf._lib.glm_logit(z, X, device=device)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -319,11 +296,11 @@ def _node_rows(nodes, where, names, inf_y, inf_w, inf_z, inf_X):
 
 
 def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5, max_depth=2, cp=0.01, minsplit=10,
-           adj_method="holm", seed=42, bcf_fn=None, bartc_fn=None, pic_model="bartc", details=None, **bcf_args):
+           adj_method="holm", seed=42, bcf_fn=None, bartc_fn=None, logit_fn=None, pic_model="bartc", details=None, **bcf_args):
     """Discovery and estimation of heterogeneity in the complier average causal effect (R/bcf_iv.R:47).
     Returns a pandas DataFrame with the reference's columns (COLUMNS), one row per CART node.
-    `bcf_fn` / `bartc_fn`: the fitting functions (default: bcf_iv_b200.bcf.bcf and bcf_iv_b200.bart.bartc, the GPU
-    samplers) -- the parity tests pass twins that drive the CPU oracle through the identical pipeline.
+    `bcf_fn` / `bartc_fn` / `logit_fn`: the fitting functions (default: bcf_iv_b200.bcf.bcf, bcf_iv_b200.bart.bartc and
+    logit_link, all on the GPU) -- the parity tests pass twins that drive the CPU oracle through the identical pipeline.
     `pic_model`: "bartc" (the reference: probit BART for the complier proportion and, with binary = TRUE, for the ITT) or
     "bcf" (both from the BCF sampler on the 0/1 vectors: a linear-probability stand-in).  `details`: a dict that receives the intermediate estimands
     (discovery rows, pic, itt, tauhat, the CART's split variables)."""
@@ -335,7 +312,7 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
     disc, index = _split(len(y), inference_ratio, seed)
     Xd = X[disc]                                    # the same matrix twice, as the reference passes it: copied to the GPU once
-    pihat = logit_link(z[disc], Xd)
+    pihat = (logit_fn or logit_link)(z[disc], Xd)                                          # R/bcf_iv.R:72-75
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)
     # the two fits are independent: run them side by side.  While a discovery sample fits in half of a B200's shared
@@ -412,7 +389,7 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
 
 
 def bcf_itt(y, w, z, x, binary=False, max_depth=2, n_burn=500, n_sim=500, inference_ratio=0.5, seed=42, bcf_fn=None,
-            bartc_fn=None, **bcf_args):
+            bartc_fn=None, logit_fn=None, **bcf_args):
     """Heterogeneity in the intention-to-treat effect (R/bcf_itt.R:33; same positional order of the arguments): prints the
     node effects and returns None, as the reference does."""
     y, w, z = (np.asarray(a, dtype=np.float64).ravel() for a in (y, w, z))
@@ -421,10 +398,10 @@ def bcf_itt(y, w, z, x, binary=False, max_depth=2, n_burn=500, n_sim=500, infere
     X = np.asarray(x, dtype=np.float64)
     names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
     disc, index = _split(len(y), inference_ratio, seed)
-    pihat = logit_link(z[disc], X[disc])
+    Xd = X[disc]
+    pihat = (logit_fn or logit_link)(z[disc], Xd)                                          # R/bcf_itt.R:58-61
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)
-    Xd = X[disc]
     if binary:                                                                              # R/bcf_itt.R:166-170
         tauhat = (bartc_fn or _bart.bartc)(y[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2, seed=seed)["ite_mean"]
     else:

@@ -2121,3 +2121,8 @@ extern "C" int bcfgpu_fit_chains(const bcfgpu_config* cfg, int32_t n_chains, con
     }
     return BCFGPU_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// dense pre-steps of bcf_iv() / bcf()
+// ------------------------------------------------------------------------------------------------
+#include "bcfgpu_glm.inl"

@@ -1,8 +1,8 @@
 """Host-side preprocessing that bcf's R wrapper does before and after the native call.
 
 Restates the R code of `bcf::bcf` [bcf-recall; the package is imported
-by the reference at NAMESPACE:9 and called at R/bcf_iv.R:89, R/bcf_itt.R:71].  Plain NumPy: this is
-O(n p) once per call and stays on the CPU (SURVEY 8f-3 lists it as a later row).
+by the reference at NAMESPACE:9 and called at R/bcf_iv.R:89, R/bcf_itt.R:71].  The O(n p) bookkeeping (standardisation,
+cutpoint grids, permutation) is NumPy on the host; the O(n p^2) step -- `lm` for sighat -- runs on the device.
 """
 from __future__ import annotations
 
@@ -60,24 +60,11 @@ def pack_cuts(cut_list):
     return np.ascontiguousarray(flat), off
 
 
-def lm_sigma(yscale: np.ndarray, z: np.ndarray, x_c: np.ndarray) -> float:
-    """summary(lm(yscale ~ z + x_c))$sigma via the normal equations (rank-aware).  The Gram matrix of (1, z, x_c) is
-    assembled from its blocks, so the n x (p + 2) design matrix is never materialised (400 MB at n = 5e5, p = 100)."""
-    n = yscale.size
-    X = np.asarray(x_c, dtype=np.float64)
-    zf = np.asarray(z, dtype=np.float64)
-    p = X.shape[1]
-    G = np.empty((p + 2, p + 2))
-    sx, zx = X.sum(axis=0), zf @ X
-    G[0, 0], G[0, 1], G[1, 1] = n, zf.sum(), zf @ zf
-    G[0, 2:], G[1, 2:], G[2:, 2:] = sx, zx, X.T @ X
-    G[1, 0] = G[0, 1]; G[2:, 0] = sx; G[2:, 1] = zx
-    b = np.concatenate([[yscale.sum(), zf @ yscale], yscale @ X])
-    beta, _, rank, _ = np.linalg.lstsq(G, b, rcond=None)
-    resid = yscale - (beta[0] + beta[1] * zf + X @ beta[2:])
-    rss = float(resid @ resid)
-    dof = max(n - int(rank), 1)
-    return float(np.sqrt(rss / dof))
+def lm_sigma(yscale: np.ndarray, z: np.ndarray, x_c: np.ndarray, device: int = 0) -> float:
+    """summary(lm(yscale ~ z + x_c))$sigma: bcf's default `sighat`.  Runs on the device (bcfgpu_lm_sigma: Gram matrix of
+    (1, z, x_c, y) + residual pass in CUDA, rank-aware solve of the normal equations); no host path."""
+    from . import _lib
+    return _lib.lm_sigma(yscale, z, x_c, device=device)
 
 
 def qchisq(p: float, df: float) -> float:
@@ -93,9 +80,11 @@ class Prepared:
 
 
 def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_control=None, sd_moderate=None,
-            nu=3.0, lambda_=None, sigq=0.9, sighat=None, use_tauscale=True) -> Prepared:
+            nu=3.0, lambda_=None, sigq=0.9, sighat=None, use_tauscale=True, sigma_fn=None, device=0) -> Prepared:
     """bcf's R-side preamble [bcf-recall, SURVEY A.1].  Returns arrays in the ORIGINAL row order plus `perm`
-    (treated rows first, stable: R's order(z, decreasing=TRUE)); the native library applies the permutation."""
+    (treated rows first, stable: R's order(z, decreasing=TRUE)); the native library applies the permutation.
+    `sigma_fn(yscale, z, x_c)`: what computes the default sighat (the device's lm_sigma; the parity tests hand in the
+    CPU oracle's so that problems can be prepared without a GPU)."""
     same_x = x_moderate is x_control            # bcf(y, z, x, x, pihat): what BayesIV calls (R/bcf_iv.R:89)
     y = np.asarray(y, dtype=np.float64).ravel()
     z = np.asarray(z).ravel()
@@ -140,7 +129,7 @@ def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_cont
     P.x_c, P.x_m = x_c, x_m
     P.cuts_c = make_cutpoints(x_c)
     P.cuts_m = P.cuts_c[:x_m.shape[1]] if x_m.base is x_c else make_cutpoints(x_m)
-    P.sighat = float(sighat) if sighat is not None else lm_sigma(P.yscale, z, x_c)
+    P.sighat = float(sighat) if sighat is not None else float(sigma_fn(P.yscale, z, x_c) if sigma_fn else lm_sigma(P.yscale, z, x_c, device))
     P.lambda_ = float(lambda_) if lambda_ is not None else P.sighat ** 2 * qchisq(1.0 - sigq, nu) / nu
     P.perm = np.argsort(-P.z, kind="stable")          # treated first, ties in original order
     P.inv_perm = np.empty(n, dtype=np.int64)

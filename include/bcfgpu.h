@@ -240,6 +240,28 @@ BCFGPU_API int bcfgpu_op_rng_probe(uint64_t seed, uint32_t chain, uint32_t sweep
 /* probit BART's latent draw: out[i] = ystar ~ N(m[i], 1) truncated by y[i] (1: > 0, 0: <= 0), from the uniform u[i] */
 BCFGPU_API int bcfgpu_op_probit_latent(const double *m, const int32_t *y, const double *u, int32_t n, double *out);
 
+
+/* ---- the dense pre-steps of bcf_iv() / bcf(): no handle, one call each ----------------------------
+ * X is n x p doubles, column-major (row_major = 0: R's layout) or row-major (row_major = 1: NumPy's default; it is
+ * transposed on the device, not on the host).  The n-sized passes and the weighted Gram matrix A' W A run on the
+ * device in fp64 with block-ordered (deterministic) sums; the (p + 2)-square solve runs on the host.  Columns are
+ * taken left to right as R's dqrdc2 does: a column that is a linear combination of the ones before it is ALIASED --
+ * its coefficient is NaN (R's NA) and it does not enter the fit.
+ *
+ * bcfgpu_glm_logit replaces   p.score <- glm(z ~ x[-index,], family = binomial); pihat <- predict(p.score, ...)
+ *   (R/bcf_iv.R:72-75, R/bcf_itt.R:58-61): stats::glm.fit's IRLS for binomial(logit) -- start mu = (z + 0.5) / 2,
+ *   working weights max(mu (1 - mu), DBL_EPSILON), convergence |dev - dev_old| / (|dev| + 0.1) < epsilon (1e-8), at
+ *   most max_iter (25) iterations.  eta_out[n] = the linear predictor (predict.glm's default type = "link");
+ *   beta_out[p + 1] (intercept first; may be NULL); info[4] = {iterations, converged, rank, kernel launches}. */
+BCFGPU_API int bcfgpu_glm_logit(int32_t device, int64_t n, int32_t p, const double *X, int32_t row_major,
+                                const int32_t *z, int32_t max_iter, double epsilon, double *eta_out, double *beta_out,
+                                double *deviance_out, int32_t *info);
+/* bcfgpu_lm_sigma replaces    sighat <- summary(lm(yscale ~ z + x_c))$sigma   (bcf's R wrapper):
+ *   sqrt(RSS / (n - rank)) of the least-squares fit of y on (1, z, X); z may be NULL (no such column).
+ *   beta_out[1 + (z != NULL) + p] may be NULL; info[2] = {rank, kernel launches}. */
+BCFGPU_API int bcfgpu_lm_sigma(int32_t device, int64_t n, int32_t p, const double *X, int32_t row_major,
+                               const int32_t *z, const double *y, double *sigma_out, double *beta_out, int32_t *info);
+
 #ifdef __cplusplus
 }
 #endif

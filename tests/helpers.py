@@ -6,6 +6,14 @@ import numpy as np
 from bcf_iv_b200 import datasets, prep
 
 
+def prepare(*a, **kw):
+    """prep.prepare with the default sighat taken from the CPU oracle's lm (oracle/glm_oracle.py): the parity problems are
+    prepared without a GPU, and the oracle and the GPU sampler receive the identical prior"""
+    from oracle import glm_oracle
+    kw.setdefault("sigma_fn", glm_oracle.lm_sigma)
+    return prep.prepare(*a, **kw)
+
+
 class Problem:
     pass
 
@@ -16,7 +24,7 @@ def make_problem(n=500, p=10, seed=1, continuous=False, rho=0.0, compliance=0.75
     d = datasets.generate_dataset_wide(n=n, p=p, rho=rho, compliance=compliance, seed=seed, continuous=continuous)
     rng = np.random.default_rng(seed + 1000)
     pihat = pihat_noise * rng.standard_normal(n)          # logit of a randomised instrument is ~0
-    P = prep.prepare(d["y"], d["z"], d["X"], d["X"], pihat)
+    P = prepare(d["y"], d["z"], d["X"], d["X"], pihat)
     pr = Problem()
     pr.data, pr.P, pr.n, pr.p = d, P, n, p
     pr.cuts_c_flat, pr.off_c = prep.pack_cuts(P.cuts_c)
@@ -88,7 +96,7 @@ def oracle_bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=No
     from oracle import orc
     if x_moderate is None:
         x_moderate = x_control
-    P = prep.prepare(y, z, x_control, x_moderate, pihat)
+    P = prepare(y, z, x_control, x_moderate, pihat)
     perm = P.perm
     o = orc.OracleSampler(P.yscale[perm], P.ntrt, P.x_c[perm], P.x_m[perm], P.cuts_c, P.cuts_m, lambda_=P.lambda_,
                           sigma_init=P.sigma_init, con_sd=P.con_sd, mod_sd=P.mod_sd, seed=int(random_seed),

@@ -4,6 +4,8 @@ Reference call sites: R/bcf_iv.R:89-91, R/bcf_itt.R:71-75 (bcf(...)$tau -> colMe
 oracle restates the un-vendored `bcf` package; agreement is with that restatement.
 """
 import numpy as np
+
+import helpers
 import pytest
 
 from helpers import gpu_sampler, make_problem, oracle_sampler, tree_signature
@@ -297,7 +299,7 @@ def test_saved_forests_with_wide_trees():
     from bcf_iv_b200 import prep
     d = pr.data
     ywide = 3.0 * np.sin(9.0 * d["X"][:, 2]) + d["y"]
-    pr.P = prep.prepare(ywide, d["z"], d["X"], d["X"], 0.05 * np.random.default_rng(1).standard_normal(pr.n))
+    pr.P = helpers.prepare(ywide, d["z"], d["X"], d["X"], 0.05 * np.random.default_rng(1).standard_normal(pr.n))
     pr.cuts_c_flat, pr.off_c = prep.pack_cuts(pr.P.cuts_c)
     pr.cuts_m_flat, pr.off_m = prep.pack_cuts(pr.P.cuts_m)
     kw = dict(seed=12, ntree_con=3, ntree_mod=2)

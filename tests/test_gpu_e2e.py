@@ -6,6 +6,8 @@ import socket
 import sys
 
 import numpy as np
+
+import helpers
 import pytest
 
 from bcf_iv_b200 import _lib, bayesiv, bcf, datasets
@@ -22,7 +24,7 @@ def test_bcf_front_end_matches_oracle_posterior_means():
     assert fit["tau"].shape == (60, 600) and fit["sigma"].shape == (60,)
     assert np.allclose(fit["tau"].mean(axis=0), fit["tau_mean"], rtol=1e-9, atol=1e-9)
     from bcf_iv_b200 import prep
-    P = prep.prepare(d["y"], d["z"], d["X"], d["X"], pihat)
+    P = helpers.prepare(d["y"], d["z"], d["X"], d["X"], pihat)
     class Pr: pass
     pr = Pr(); pr.P = P
     o = oracle_sampler(pr, seed=17, max_leaves=128)

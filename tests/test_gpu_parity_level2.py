@@ -10,6 +10,7 @@ import pytest
 
 from bcf_iv_b200 import _lib, bayesiv, datasets, workload
 from bcf_iv_b200 import bart
+from oracle import glm_oracle
 from helpers import gpu_sampler, make_problem, oracle_bcf, oracle_probit_bart, oracle_sampler
 
 
@@ -37,10 +38,10 @@ def test_readme_workload_gpu_twin_vs_oracle_twin_seeds_0_to_9():
     for seed in SEEDS:
         d = datasets.generate_dataset(n=1000, p=10, compliance=0.75, seed=100 + seed)
         row = {}
-        for who, fn, bfn in (("gpu", None, None), ("orc", oracle_bcf, oracle_bartc)):
+        for who, fn, bfn, lfn in (("gpu", None, None, None), ("orc", oracle_bcf, oracle_bartc, glm_oracle.glm_logit)):
             det = {}
             tab = bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], n_burn=nb, n_sim=ns, max_depth=2, seed=seed, bcf_fn=fn,
-                                 bartc_fn=bfn, details=det)
+                                 bartc_fn=bfn, logit_fn=lfn, details=det)
             cells = _cells(d["X"][det["disc"]])
             row[who] = dict(itt=np.array([det["itt"][c].mean() for c in cells]), pic=float(det["pic"].mean()),
                             pic_cells=np.array([det["pic"][c].mean() for c in cells]),

@@ -1,6 +1,8 @@
 """Host-side pieces that stay on the CPU: bcf's R-wrapper preamble (prep), the workload generator (datasets) and the
 closed forms the bcf_iv / bcf_itt twins use in place of rpart / AER / stats (bayesiv).  No GPU needed."""
 import numpy as np
+
+import helpers
 import pytest
 
 from bcf_iv_b200 import bayesiv, datasets, prep
@@ -22,7 +24,7 @@ def test_cutpoints_binary_few_valued_and_continuous():
 def test_prepare_follows_bcf_conventions():
     d = datasets.generate_dataset_wide(n=300, p=4, seed=1)
     pihat = np.linspace(-1, 1, 300)
-    P = prep.prepare(d["y"], d["z"], d["X"], d["X"], pihat)
+    P = helpers.prepare(d["y"], d["z"], d["X"], d["X"], pihat)
     assert P.x_c.shape == (300, 5) and P.x_m.shape == (300, 4)           # include_pi = "control"
     assert np.isclose(P.yscale.mean(), 0, atol=1e-12) and np.isclose(P.yscale.std(ddof=1), 1)
     z = P.z[P.perm]
@@ -35,9 +37,9 @@ def test_prepare_follows_bcf_conventions():
     res = P.yscale - A @ np.linalg.lstsq(A, P.yscale, rcond=None)[0]
     assert P.sighat == pytest.approx(np.sqrt(res @ res / (300 - np.linalg.matrix_rank(A))))
     with pytest.raises(ValueError):
-        prep.prepare(d["y"], d["z"] + 2, d["X"], d["X"], pihat)
+        helpers.prepare(d["y"], d["z"] + 2, d["X"], d["X"], pihat)
     with pytest.raises(ValueError):
-        prep.prepare(np.r_[d["y"][:-1], np.nan], d["z"], d["X"], d["X"], pihat)
+        helpers.prepare(np.r_[d["y"][:-1], np.nan], d["z"], d["X"], d["X"], pihat)
 
 
 # ---- generate_dataset (R/generate_dataset.R:22-68) ---------------------------------------------------------------
@@ -64,20 +66,37 @@ def test_wide_generator_correlation_and_variants():
 
 
 # ---- closed forms of the twins ------------------------------------------------------------------------------------
-def test_logit_link_matches_newton_on_the_likelihood():
+def test_oracle_glm_solves_the_score_equations_and_drops_aliased_columns():
     rng = np.random.default_rng(2)
     X = rng.standard_normal((800, 3))
     eta_true = 0.3 + X @ np.array([1.0, -0.5, 0.0])
     z = (rng.random(800) < 1 / (1 + np.exp(-eta_true))).astype(float)
-    eta = bayesiv.logit_link(z, X)
+    from oracle import glm_oracle
+    eta, inf = glm_oracle.glm_logit(z, X, full=True)
+    assert inf["converged"] and inf["rank"] == 4
     A = np.column_stack([np.ones(800), X])
     beta = np.linalg.lstsq(A, eta, rcond=None)[0]
     mu = 1 / (1 + np.exp(-eta))
     assert np.allclose(A.T @ (z - mu), 0, atol=1e-6)     # score equations of the MLE
     assert np.allclose(beta, [0.3, 1.0, -0.5, 0.0], atol=0.35)
     # an aliased column is dropped, as glm does
-    eta2 = bayesiv.logit_link(z, np.column_stack([X, X[:, 0]]))
-    assert np.allclose(eta, eta2, atol=1e-6)
+    eta2, inf2 = glm_oracle.glm_logit(z, np.column_stack([X, X[:, 0]]), full=True)
+    assert np.allclose(eta, eta2, atol=1e-9) and inf2["rank"] == 4 and np.isnan(inf2["beta"][-1])
+
+
+def test_oracle_lm_sigma_matches_lstsq_and_counts_the_rank():
+    from oracle import glm_oracle
+    rng = np.random.default_rng(3)
+    X = (rng.random((600, 6)) < 0.5).astype(float)
+    z = (rng.random(600) < 0.5).astype(int)
+    y = 0.5 * z + X[:, 0] - X[:, 1] + rng.standard_normal(600)
+    A = np.column_stack([np.ones(600), z, X])
+    res = y - A @ np.linalg.lstsq(A, y, rcond=None)[0]
+    assert np.isclose(glm_oracle.lm_sigma(y, z, X), np.sqrt(res @ res / (600 - 8)), rtol=1e-12)
+    # pihat = a linear predictor of (1, X) is aliased in lm(y ~ z + [X | pihat]): the rank, and so sigma, do not change
+    pihat = 0.2 + X @ np.arange(6.0)
+    s2, inf = glm_oracle.lm_sigma(y, z, np.column_stack([X, pihat]), full=True)
+    assert inf["rank"] == 8 and np.isnan(inf["beta"][-1]) and np.isclose(s2, np.sqrt(res @ res / (600 - 8)), rtol=1e-10)
 
 
 def test_cart_matches_sklearn_and_rpart_rules():
@@ -155,13 +174,13 @@ def test_prepare_shares_the_matrix_when_bcf_is_called_with_the_same_x_twice():
     X = (rng.random((n, p)) < 0.4).astype(float)
     X[:, 3] = rng.standard_normal(n)
     y, z, pihat = rng.standard_normal(n), (rng.random(n) < 0.5).astype(int), 0.1 * rng.standard_normal(n)
-    a = prep.prepare(y, z, X, X, pihat)
-    b = prep.prepare(y, z, X, X.copy(), pihat)
+    a = helpers.prepare(y, z, X, X, pihat)
+    b = helpers.prepare(y, z, X, X.copy(), pihat)
     assert np.shares_memory(a.x_m, a.x_c) and a.x_c.flags.f_contiguous and a.x_m.flags.f_contiguous
     assert not np.shares_memory(b.x_m, b.x_c)
     assert np.array_equal(a.x_c, b.x_c) and np.array_equal(a.x_m, b.x_m)
     assert len(a.cuts_m) == len(b.cuts_m) == p
     for u, v in zip(a.cuts_m, b.cuts_m):
         assert np.array_equal(u, v)
-    c = prep.prepare(y, z, X, X, pihat, include_pi="both")      # pihat in both: two matrices again
+    c = helpers.prepare(y, z, X, X, pihat, include_pi="both")      # pihat in both: two matrices again
     assert not np.shares_memory(c.x_m, c.x_c) and c.x_m.shape[1] == p + 1
