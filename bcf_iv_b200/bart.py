@@ -47,10 +47,11 @@ def bart_config(n_trees=N_TREES, k=K_SD, base=BASE, power=POWER, seed=0, chain=0
 
 
 def probit_bart(y01, X, treatment=None, n_samples=500, n_burn=500, n_thin=1, n_chains=2, seed=0, first_chain=0, devices=None,
-                **bart_args):
+                keep_sampler=False, **bart_args):
     """Probit BART of the 0/1 vector y01 on the columns of X (and, S-learner, on `treatment` appended as the last column).
     Returns dict(prob_mean = posterior mean of P(y = 1 | x[, z observed]); with a treatment also ite_mean / ite_var = posterior
-    mean / variance of Phi(f(x, 1)) - Phi(f(x, 0)) per row), chains pooled."""
+    mean / variance of Phi(f(x, 1)) - Phi(f(x, 0)) per row), chains pooled.  keep_sampler: the first chain's _lib.Sampler is
+    returned open as out["sampler"] (bcf_iv grows its CART on the covariates it holds binned on the device; the caller closes it)."""
     y01 = np.asarray(y01, dtype=np.float64).ravel()
     if not np.all((y01 == 0) | (y01 == 1)):
         raise ValueError("probit BART needs a 0/1 response")
@@ -78,18 +79,23 @@ def probit_bart(y01, X, treatment=None, n_samples=500, n_burn=500, n_thin=1, n_c
     samplers = _lib.fit_chains(cfg, int(n_chains), devs, y01, z.astype(np.int32), xc, None, cuts, off, None, None,
                                int(n_burn), int(n_samples), int(n_thin))
     res, err = [], None
-    for s in samplers:
+    for i, s in enumerate(samplers):
         try:
             res.append((s.mu_mean(), s.tau_mean(), s.tau_var(), s.num_saved, s.last_run_ms))
         except BaseException as e:
             err = err or e
         finally:
-            s.close()
+            if not (keep_sampler and i == 0):
+                s.close()
     if err is not None:
+        if keep_sampler:
+            samplers[0].close()
         raise err
     ns = res[0][3]
     ntot = ns * len(res)
     out = {"prob_mean": np.mean([r[0] for r in res], axis=0), "device_ms": [r[4] for r in res]}
+    if keep_sampler:
+        out["sampler"] = samplers[0]
     if treatment is not None:
         m = np.mean([r[1] for r in res], axis=0)
         out["ite_mean"] = m
@@ -98,7 +104,7 @@ def probit_bart(y01, X, treatment=None, n_samples=500, n_burn=500, n_thin=1, n_c
 
 
 def bartc(response, treatment, confounders, n_samples=500, n_burn=500, n_chains=2, seed=0, devices=None, fit=probit_bart,
-          **fit_args):
+          keep_sampler=False, **fit_args):
     """bartCause::bartc(response, treatment, confounders, n.samples, n.burn, n.chains) for a 0/1 response, then
     extract(type = "ite") averaged over the draws: dict(ite_mean, ite_var, p_score, prob_mean).  `fit`: the probit-BART
     fitting function (the parity tests pass the CPU oracle's); fit_args (e.g. max_ctas: a share of the GPU per chain, the
@@ -107,6 +113,11 @@ def bartc(response, treatment, confounders, n_samples=500, n_burn=500, n_chains=
               devices=devices, **fit_args)
     ps = trt["prob_mean"]
     Xr = np.column_stack([np.asarray(confounders, dtype=np.float64), ps])
+    if keep_sampler:
+        fit_args = dict(fit_args, keep_sampler=True)       # the response model's: its leading columns are the confounders
     rsp = fit(response, Xr, treatment, n_samples=n_samples, n_burn=n_burn, n_chains=n_chains, seed=seed, first_chain=200,
               devices=devices, **fit_args)
-    return {"ite_mean": rsp["ite_mean"], "ite_var": rsp["ite_var"], "p_score": ps, "prob_mean": rsp["prob_mean"]}
+    out = {"ite_mean": rsp["ite_mean"], "ite_var": rsp["ite_var"], "p_score": ps, "prob_mean": rsp["prob_mean"]}
+    if keep_sampler:
+        out["sampler"] = rsp.get("sampler")
+    return out

@@ -341,8 +341,12 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
             f_pic = pool.submit(lambda: fit_bartc(w[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2,
                                                   seed=seed, **bkw)["ite_mean"])             # R/bcf_iv.R:78-80
             if binary:                                                                          # R/bcf_iv.R:198-202
-                f_itt = pool.submit(lambda: fit_bartc(y[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2,
-                                                      seed=seed + 1, **bkw)["ite_mean"])
+                def _itt_b():
+                    r = fit_bartc(y[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2, seed=seed + 1,
+                                  **dict(bkw, **({"keep_sampler": True} if bartc_fn is None else {})))
+                    live.append(r.get("sampler"))
+                    return r["ite_mean"]
+                f_itt = pool.submit(_itt_b)
             else:
                 def _itt():
                     r = fit(y[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, keep_sampler=bcf_fn is None))   # R/bcf_iv.R:89-91
@@ -358,10 +362,13 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     try:
         # the CART on tauhat: on the device when the sampler's cutpoints ARE rpart's candidate splits (columns with fewer
         # than 8 distinct values) and tauhat fits the kernel's fixed-point range; on the host otherwise
-        on_device = (smp is not None and np.all(np.diff(smp.off_mod) < prep_cat_levels() - 1)
+        # (binary = TRUE: the sampler is bartc's response model, one forest whose leading columns are the covariates)
+        cforest = 0 if binary else 1
+        on_device = (smp is not None
+                     and np.all(np.diff(smp.off_con if binary else smp.off_mod)[:Xd.shape[1]] < prep_cat_levels() - 1)
                      and np.all(np.isfinite(tauhat)) and np.max(np.abs(tauhat)) < 16384.0)
         if on_device:
-            nodes, where = cart_device(smp, Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
+            nodes, where = cart_device(smp, Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit, forest=cforest)
         else:
             nodes, where = cart(Xd, tauhat, maxdepth=max_depth, cp=cp, minsplit=minsplit)
     finally:

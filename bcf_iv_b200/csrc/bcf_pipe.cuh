@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
                 while (first < T) {
                     const PipePlan& P = sm.plan[b & 3];
                     PPROF(5); PTRACE(0);
-                    for (int lt = tw; lt < ntl; lt += PT_WARPS) pipe_stats_tile(sm, sm.p.acc[b & 1], P, d, rs, tile0, lt, lane, pw, b & 1, ntl <= PT_WARPS);
+                    for (int lt = tw; lt < ntl; lt += PT_WARPS) pipe_stats_tile(sm, sm.p.acc[b & 1], P, d, rs, tile0, lt, lane, tw, b & 1, ntl <= PT_WARPS);
                     // the next plan is made two batches ahead: warp 0 checks it (an acquire load: kept off the other
                     // warps, and away from the apply's stores) and the barrier hands the knowledge to everybody
                     if (tw == 0 && lane == 0 && first + P.nb < T) pipe_wait_flag(&sm.plan_ready, b + 2, d.err, 20, d.dbg, 2);

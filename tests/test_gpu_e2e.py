@@ -72,9 +72,17 @@ def test_bcf_iv_binary_outcome_runs_through_the_gpu_sampler(pic_model):
     assert set(np.unique(d["y"])) <= {0.0, 1.0}
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", UserWarning)               # ("y appears to be discrete": the bcf stand-in's preamble)
+        det = {}
         tab = bayesiv.bcf_iv(d["y"], d["w"], d["z"], d["X"], binary=True, n_burn=300, n_sim=300, max_depth=2, seed=42,
-                             pic_model=pic_model)
+                             pic_model=pic_model, details=det)
     assert list(tab.columns) == bayesiv.COLUMNS
+    if pic_model == "bartc":
+        # the subgroup CART grew on the device, over the covariates bartc's response model holds binned there (its leading
+        # columns), and is the host restatement of rpart's tree
+        assert det["cart_on_device"] is True
+        nd_h, wh_h = bayesiv.cart(d["X"][det["disc"]], det["tauhat"], maxdepth=2, cp=0.01, minsplit=10)
+        assert sorted(nd_h) == sorted(int(i) for i in tab.index if tab.loc[i, "node"] is not None)
+        assert sorted({nd.var for nd in nd_h.values() if nd.var is not None}) == det["split_vars"]
     rules = " ".join(str(r) for r in tab["node"].dropna())
     assert "x1" in rules or "x2" in rules
     eff = tab.dropna(subset=["Adj_pvalue"])["CCACE"].astype(float)
