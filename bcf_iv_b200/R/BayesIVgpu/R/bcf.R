@@ -39,7 +39,10 @@ bcf <- function(y, z, x_control, x_moderate = x_control, pihat, nburn, nsim, nth
   cut_c <- lapply(seq_len(ncol(x_c)), function(j) .cutpoints(x_c[, j]))
   cut_m <- lapply(seq_len(ncol(x_m)), function(j) .cutpoints(x_m[, j]))
   muy <- mean(y); sdy <- sd(y); yscale <- (y - muy) / sdy
-  if (is.null(sighat)) sighat <- summary(lm(yscale ~ z + x_c))$sigma
+  if (is.null(sighat)) {   # summary(lm(yscale ~ z + x_c))$sigma, on the device (bcfgpu_lm_sigma)
+    xs <- as.matrix(x_c); storage.mode(xs) <- "double"
+    sighat <- .Call("bcfgpu_R_lm_sigma", as.double(yscale), as.integer(z), xs, 0L, PACKAGE = "BayesIVgpu")
+  }
   if (is.null(lambda)) lambda <- sighat^2 * qchisq(1 - sigq, nu) / nu
   con_sd <- if (isTRUE(all.equal(sd_control, 2 * sdy))) 2 else sd_control / sdy
   mod_sd <- (if (isTRUE(all.equal(sd_moderate, sdy))) 1 else sd_moderate / sdy) / (if (use_tauscale) 0.674 else 1)

@@ -176,9 +176,41 @@ SEXP bcfgpu_R_fit_chains(SEXP y, SEXP z, SEXP xc, SEXP xm, SEXP cuts_c, SEXP off
     return out;
 }
 
+/* .Call("bcfgpu_R_glm_logit", z, x, device): the linear predictor of glm(z ~ x, family = binomial) -- what the reference
+ * computes with stats::glm + predict (R/bcf_iv.R:72-75, R/bcf_itt.R:58-61) -- by IRLS on the device.  x: numeric matrix
+ * (column-major, handed over as it is). */
+SEXP bcfgpu_R_glm_logit(SEXP z, SEXP x, SEXP device)
+{
+    if (!Rf_isReal(x) || !Rf_isMatrix(x) || !Rf_isInteger(z)) Rf_error("bcfgpu_R_glm_logit: x must be a double matrix, z an integer vector");
+    const R_xlen_t n = Rf_nrows(x);
+    const int p = Rf_ncols(x);
+    if (Rf_xlength(z) != n) Rf_error("bcfgpu_R_glm_logit: z and x differ in length");
+    SEXP eta = PROTECT(Rf_allocVector(REALSXP, n));
+    int info[4] = {0, 0, 0, 0};
+    const int rc = bcfgpu_glm_logit(Rf_asInteger(device), (int64_t)n, p, REAL(x), 0, INTEGER(z), 25, 1e-8, REAL(eta), NULL, NULL, info);
+    if (rc != BCFGPU_OK) { UNPROTECT(1); Rf_error("libbcfgpu: %s", bcfgpu_last_error()); }
+    if (!info[1]) Rf_warning("glm.fit: algorithm did not converge");
+    UNPROTECT(1);
+    return eta;
+}
+
+/* .Call("bcfgpu_R_lm_sigma", y, z, x, device): summary(lm(y ~ z + x))$sigma, bcf's default sighat, on the device */
+SEXP bcfgpu_R_lm_sigma(SEXP y, SEXP z, SEXP x, SEXP device)
+{
+    if (!Rf_isReal(x) || !Rf_isMatrix(x) || !Rf_isReal(y) || !Rf_isInteger(z)) Rf_error("bcfgpu_R_lm_sigma: bad argument types");
+    const R_xlen_t n = Rf_nrows(x);
+    if (Rf_xlength(y) != n || Rf_xlength(z) != n) Rf_error("bcfgpu_R_lm_sigma: y, z and x differ in length");
+    double sigma = 0.0;
+    const int rc = bcfgpu_lm_sigma(Rf_asInteger(device), (int64_t)n, Rf_ncols(x), REAL(x), 0, INTEGER(z), REAL(y), &sigma, NULL, NULL);
+    if (rc != BCFGPU_OK) Rf_error("libbcfgpu: %s", bcfgpu_last_error());
+    return Rf_ScalarReal(sigma);
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"bcfgpu_R_device_count", (DL_FUNC)&bcfgpu_R_device_count, 0},
     {"bcfgpu_R_fit_chains", (DL_FUNC)&bcfgpu_R_fit_chains, 17},
+    {"bcfgpu_R_glm_logit", (DL_FUNC)&bcfgpu_R_glm_logit, 3},
+    {"bcfgpu_R_lm_sigma", (DL_FUNC)&bcfgpu_R_lm_sigma, 4},
     {NULL, NULL, 0}};
 
 void R_init_BayesIVgpu(DllInfo *dll)

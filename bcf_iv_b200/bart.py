@@ -46,37 +46,33 @@ def bart_config(n_trees=N_TREES, k=K_SD, base=BASE, power=POWER, seed=0, chain=0
     return cfg
 
 
-def probit_bart(y01, X, treatment=None, n_samples=500, n_burn=500, n_thin=1, n_chains=2, seed=0, first_chain=0, devices=None,
-                keep_sampler=False, **bart_args):
-    """Probit BART of the 0/1 vector y01 on the columns of X (and, S-learner, on `treatment` appended as the last column).
-    Returns dict(prob_mean = posterior mean of P(y = 1 | x[, z observed]); with a treatment also ite_mean / ite_var = posterior
-    mean / variance of Phi(f(x, 1)) - Phi(f(x, 0)) per row), chains pooled.  keep_sampler: the first chain's _lib.Sampler is
-    returned open as out["sampler"] (bcf_iv grows its CART on the covariates it holds binned on the device; the caller closes it)."""
-    y01 = np.asarray(y01, dtype=np.float64).ravel()
-    if not np.all((y01 == 0) | (y01 == 1)):
-        raise ValueError("probit BART needs a 0/1 response")
+def _as_design(X, extra_cols=0):
+    """n x (p + extra_cols) column-major matrix whose leading columns are X (row-major input: transposed in cache-sized
+    blocks, 1.5x a plain assignment; column-major input: a column-wise memcpy)"""
     X = np.asarray(X, dtype=np.float64)
     if X.ndim == 1:
         X = X[:, None]
-    n = y01.size
-    if treatment is not None:
-        z = np.asarray(treatment).ravel()
-        if not np.all((z == 0) | (z == 1)):
-            raise ValueError("treatment must be a vector of 0's and 1's")
-        xc = np.empty((n, X.shape[1] + 1), dtype=np.float64, order="F")
-        xc[:, :-1] = X
-        xc[:, -1] = z
-        trt_col = X.shape[1]
+    n, p = X.shape
+    xc = np.empty((n, p + extra_cols), dtype=np.float64, order="F")
+    if X.flags.c_contiguous and p > 1:
+        for r0 in range(0, n, 8192):
+            xc[r0:r0 + 8192, :p] = X[r0:r0 + 8192]
     else:
-        z = np.zeros(n, dtype=np.int32)
-        xc = np.asfortranarray(X)
-        trt_col = -1
+        xc[:, :p] = X
+    return xc
+
+
+def _fit_design(y01, xc, cuts_list, trt_col, n_samples, n_burn, n_thin, n_chains, seed, first_chain, devices, keep_sampler,
+                bart_args):
+    """the probit-BART chains of one model on the column-major design xc (treatment in column trt_col, or -1)"""
+    n = y01.size
+    z = xc[:, trt_col].astype(np.int32) if trt_col >= 0 else np.zeros(n, dtype=np.int32)
     if _lib.device_count() < 1:
         raise _lib.BcfGpuError(2, "no CUDA device available (libbcfgpu has no CPU fallback)")
-    cuts, off = prep.pack_cuts([bart_cutpoints(xc[:, v]) for v in range(xc.shape[1])])
+    cuts, off = prep.pack_cuts(cuts_list)
     cfg = bart_config(seed=seed, chain=first_chain, treatment_col=trt_col, **bart_args)
     devs = list(devices) if devices is not None else list(range(min(_lib.device_count(), max(1, int(n_chains)))))
-    samplers = _lib.fit_chains(cfg, int(n_chains), devs, y01, z.astype(np.int32), xc, None, cuts, off, None, None,
+    samplers = _lib.fit_chains(cfg, int(n_chains), devs, y01, z, xc, None, cuts, off, None, None,
                                int(n_burn), int(n_samples), int(n_thin))
     res, err = [], None
     for i, s in enumerate(samplers):
@@ -96,11 +92,35 @@ def probit_bart(y01, X, treatment=None, n_samples=500, n_burn=500, n_thin=1, n_c
     out = {"prob_mean": np.mean([r[0] for r in res], axis=0), "device_ms": [r[4] for r in res]}
     if keep_sampler:
         out["sampler"] = samplers[0]
-    if treatment is not None:
+    if trt_col >= 0:
         m = np.mean([r[1] for r in res], axis=0)
         out["ite_mean"] = m
         out["ite_var"] = (sum((ns - 1) * r[2] + ns * (r[1] - m) ** 2 for r in res) / (ntot - 1)) if ntot > 1 else np.zeros_like(m)
     return out
+
+
+def probit_bart(y01, X, treatment=None, n_samples=500, n_burn=500, n_thin=1, n_chains=2, seed=0, first_chain=0, devices=None,
+                keep_sampler=False, **bart_args):
+    """Probit BART of the 0/1 vector y01 on the columns of X (and, S-learner, on `treatment` appended as the last column).
+    Returns dict(prob_mean = posterior mean of P(y = 1 | x[, z observed]); with a treatment also ite_mean / ite_var = posterior
+    mean / variance of Phi(f(x, 1)) - Phi(f(x, 0)) per row), chains pooled.  keep_sampler: the first chain's _lib.Sampler is
+    returned open as out["sampler"] (bcf_iv grows its CART on the covariates it holds binned on the device; the caller closes it)."""
+    y01 = np.asarray(y01, dtype=np.float64).ravel()
+    if not np.all((y01 == 0) | (y01 == 1)):
+        raise ValueError("probit BART needs a 0/1 response")
+    if treatment is not None:
+        z = np.asarray(treatment).ravel()
+        if not np.all((z == 0) | (z == 1)):
+            raise ValueError("treatment must be a vector of 0's and 1's")
+        xc = _as_design(X, 1)
+        xc[:, -1] = z
+        trt_col = xc.shape[1] - 1
+    else:
+        xc = _as_design(X)
+        trt_col = -1
+    cuts_list = [bart_cutpoints(xc[:, v]) for v in range(xc.shape[1])]
+    return _fit_design(y01, xc, cuts_list, trt_col, n_samples, n_burn, n_thin, n_chains, seed, first_chain, devices,
+                       keep_sampler, bart_args)
 
 
 def bartc(response, treatment, confounders, n_samples=500, n_burn=500, n_chains=2, seed=0, devices=None, fit=probit_bart,
@@ -108,15 +128,34 @@ def bartc(response, treatment, confounders, n_samples=500, n_burn=500, n_chains=
     """bartCause::bartc(response, treatment, confounders, n.samples, n.burn, n.chains) for a 0/1 response, then
     extract(type = "ite") averaged over the draws: dict(ite_mean, ite_var, p_score, prob_mean).  `fit`: the probit-BART
     fitting function (the parity tests pass the CPU oracle's); fit_args (e.g. max_ctas: a share of the GPU per chain, the
-    chains then run side by side) go to it."""
-    trt = fit(treatment, confounders, None, n_samples=n_samples, n_burn=n_burn, n_chains=n_chains, seed=seed, first_chain=100,
-              devices=devices, **fit_args)
+    chains then run side by side) go to it.  keep_sampler: the response model's first sampler comes back open as
+    out["sampler"] (its leading columns are the confounders)."""
+    if fit is not probit_bart:
+        trt = fit(treatment, confounders, None, n_samples=n_samples, n_burn=n_burn, n_chains=n_chains, seed=seed,
+                  first_chain=100, devices=devices, **fit_args)
+        ps = trt["prob_mean"]
+        Xr = np.column_stack([np.asarray(confounders, dtype=np.float64), ps])
+        rsp = fit(response, Xr, treatment, n_samples=n_samples, n_burn=n_burn, n_chains=n_chains, seed=seed, first_chain=200,
+                  devices=devices, **fit_args)
+        return {"ite_mean": rsp["ite_mean"], "ite_var": rsp["ite_var"], "p_score": ps, "prob_mean": rsp["prob_mean"]}
+    # One column-major design [confounders | p.score | treatment] serves both models (the treatment model reads its leading
+    # columns), and the confounders' cutpoints are made once: at n = 5e5, p = 100 the copies and column scans of two
+    # separate set-ups cost more than the chains themselves.
+    resp = np.asarray(response, dtype=np.float64).ravel()
+    trt01 = np.asarray(treatment, dtype=np.float64).ravel()
+    for v, what in ((resp, "probit BART needs a 0/1 response"), (trt01, "treatment must be a vector of 0's and 1's")):
+        if not np.all((v == 0) | (v == 1)):
+            raise ValueError(what)
+    xr = _as_design(confounders, 2)
+    p = xr.shape[1] - 2
+    cuts_x = [bart_cutpoints(xr[:, v]) for v in range(p)]
+    common = dict(n_samples=n_samples, n_burn=n_burn, n_thin=1, n_chains=n_chains, seed=seed, devices=devices)
+    trt = _fit_design(trt01, xr[:, :p], cuts_x, -1, first_chain=100, keep_sampler=False, bart_args=fit_args, **common)
     ps = trt["prob_mean"]
-    Xr = np.column_stack([np.asarray(confounders, dtype=np.float64), ps])
-    if keep_sampler:
-        fit_args = dict(fit_args, keep_sampler=True)       # the response model's: its leading columns are the confounders
-    rsp = fit(response, Xr, treatment, n_samples=n_samples, n_burn=n_burn, n_chains=n_chains, seed=seed, first_chain=200,
-              devices=devices, **fit_args)
+    xr[:, p] = ps
+    xr[:, p + 1] = trt01
+    cuts = cuts_x + [bart_cutpoints(xr[:, p]), bart_cutpoints(xr[:, p + 1])]
+    rsp = _fit_design(resp, xr, cuts, p + 1, first_chain=200, keep_sampler=keep_sampler, bart_args=fit_args, **common)
     out = {"ite_mean": rsp["ite_mean"], "ite_var": rsp["ite_var"], "p_score": ps, "prob_mean": rsp["prob_mean"]}
     if keep_sampler:
         out["sampler"] = rsp.get("sampler")

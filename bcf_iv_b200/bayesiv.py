@@ -311,7 +311,8 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     X = np.asarray(x, dtype=np.float64)
     names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
     disc, index = _split(len(y), inference_ratio, seed)
-    Xd = X[disc]                                    # the same matrix twice, as the reference passes it: copied to the GPU once
+    Xd = _bart._as_design(X[disc])                  # the same matrix twice, as the reference passes it: copied to the GPU once;
+                                                    # column-major from here on (what every native entry streams: ONE transposition per call)
     pihat = (logit_fn or logit_link)(z[disc], Xd)                                          # R/bcf_iv.R:72-75
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)
@@ -405,7 +406,7 @@ def bcf_itt(y, w, z, x, binary=False, max_depth=2, n_burn=500, n_sim=500, infere
     X = np.asarray(x, dtype=np.float64)
     names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
     disc, index = _split(len(y), inference_ratio, seed)
-    Xd = X[disc]
+    Xd = _bart._as_design(X[disc])
     pihat = (logit_fn or logit_link)(z[disc], Xd)                                          # R/bcf_itt.R:58-61
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)

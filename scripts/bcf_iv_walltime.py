@@ -35,6 +35,7 @@ def timed(name, fn):
 
 bayesiv.logit_link = timed("logit_link (glm z ~ x)", bayesiv.logit_link)
 bayesiv.cart = timed("cart (rpart)", bayesiv.cart)
+bayesiv.cart_device = timed("cart on the device (K2')", bayesiv.cart_device)
 bayesiv._node_rows = timed("per-node 2SLS (ivreg)", bayesiv._node_rows)
 bcfmod.prep.prepare = timed("bcf preamble (cutpoints, lm sighat)", prep.prepare)
 _fit_chains = bcfmod._lib.fit_chains
@@ -43,17 +44,32 @@ bayesiv._bcf.bcf = timed("bcf() ITT fit, whole call", bcfmod.bcf)
 bayesiv._bart.bartc = timed("bartc() probit BART, whole call", bartmod.bartc)
 
 
+# the process's first CUDA call creates the context and loads the library's kernels: a fixed cost per process, timed apart
+_t0 = time.perf_counter()
+bcfmod._lib.glm_logit(np.array([0, 1, 0, 1], dtype=np.int32), np.array([[0.0], [1.0], [1.0], [0.0]]))
+CUDA_INIT_S = round(time.perf_counter() - _t0, 3)
+REPEATS = int(os.environ.get("WALLTIME_REPEATS", "2"))
+
+
 def run(name, fn, gen, **kw):
     t0 = time.perf_counter()
     d = gen()
     t_gen = time.perf_counter() - t0
-    phase.clear()
-    t0 = time.perf_counter()
-    with contextlib.redirect_stdout(io.StringIO()):
-        out = fn(d["y"], d["w"], d["z"], d["X"], **kw)
-    wall = time.perf_counter() - t0
-    print(json.dumps({"config": name, "wall_s": round(wall, 3), "data_gen_s": round(t_gen, 2), "n": int(len(d["y"])),
-                      "sweeps_per_fit": kw.get("n_burn", 500) + kw.get("n_sim", 500), "phases_s": dict(phase),
+    best = None
+    walls = []
+    for _ in range(REPEATS):       # the boxes' host cores are shared: the host-side phases vary by 2x between runs; best of REPEATS
+        phase.clear()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = fn(d["y"], d["w"], d["z"], d["X"], **kw)
+        wall = time.perf_counter() - t0
+        walls.append(round(wall, 3))
+        if best is None or wall < best[0]:
+            best = (wall, dict(phase), out)
+    wall, ph, out = best
+    print(json.dumps({"config": name, "wall_s": round(wall, 3), "wall_s_runs": walls, "cuda_init_s (once per process, not in wall_s)": CUDA_INIT_S,
+                      "data_gen_s": round(t_gen, 2), "n": int(len(d["y"])),
+                      "sweeps_per_fit": kw.get("n_burn", 500) + kw.get("n_sim", 500), "phases_s": ph,
                       "rows": (None if out is None else int(len(out)))}), flush=True)
 
 
