@@ -50,7 +50,10 @@ __device__ __forceinline__ void bin_flush_run(B* __restrict__ dst, int64_t g0, i
     const int tail0 = head + PER * nwords;
     if (t < len - tail0) dst[g0 + tail0 + t] = src[tail0 + t];
 }
-__global__ void __launch_bounds__(256, 4) k_bin(const double* __restrict__ x, int64_t n, int ncols, int col0,
+// XT = double: the caller's values; XT = uint8_t: a run of ONE-cutpoint columns that crossed the bus already compared with
+// their cutpoint (bin = (cut <= x) as a byte: set_data's host staging pass writes that instead of copying 8 bytes).
+template <typename XT>
+__global__ void __launch_bounds__(256, 4) k_bin(const XT* __restrict__ x, int64_t n, int ncols, int col0,
                                              const double* __restrict__ cuts, const int32_t* __restrict__ off,
                                              const int32_t* __restrict__ col_index, const uint8_t* __restrict__ col_is16,
                                              const int32_t* __restrict__ pos, int64_t n_pad, int trt_pad, uint8_t* bins8,
@@ -87,28 +90,32 @@ __global__ void __launch_bounds__(256, 4) k_bin(const double* __restrict__ x, in
     // the block's treated rows form the run [p0, p0 + n_same) of every column, its control rows [o0, o0 + n_other)
     const int n_same = s_cnt, n_other = rows - n_same, p0 = s_min[1], o0 = s_min[0];
     uint8_t* sb8 = reinterpret_cast<uint8_t*>(sb);
-    double xv[PT];
+    constexpr bool PREBINNED = sizeof(XT) == 1;
+    XT xv[PT];
 #pragma unroll
-    for (int k = 0; k < PT; ++k) { const int r = k * 256 + t; xv[k] = r < rows ? x[(int64_t)cg0 * n + r0 + r] : 0.0; }
+    for (int k = 0; k < PT; ++k) { const int r = k * 256 + t; xv[k] = r < rows ? x[(int64_t)cg0 * n + r0 + r] : (XT)0; }
     for (int cc = 0; cc < ncg; ++cc) {
         const int c = cg0 + cc, v = col0 + c;
-        double xn[PT];
+        XT xn[PT];
         if (cc + 1 < ncg) {                                        // the next column's values fly while this one is binned and flushed
 #pragma unroll
-            for (int k = 0; k < PT; ++k) { const int r = k * 256 + t; xn[k] = r < rows ? x[(int64_t)(c + 1) * n + r0 + r] : 0.0; }
+            for (int k = 0; k < PT; ++k) { const int r = k * 256 + t; xn[k] = r < rows ? x[(int64_t)(c + 1) * n + r0 + r] : (XT)0; }
         }
         const double* cv = cuts + off[v];
         const int nc = off[v + 1] - off[v];
         const bool w16 = col_is16[v] != 0;
-        if (nc == 1) {                                             // two-valued columns (the reference's covariates): one compare
+        if (PREBINNED) {
+#pragma unroll
+            for (int k = 0; k < PT; ++k) if (li[k] >= 0) sb8[li[k]] = (uint8_t)xv[k];
+        } else if (nc == 1) {                                      // two-valued columns (the reference's covariates): one compare
             const double c0v = cv[0];
 #pragma unroll
-            for (int k = 0; k < PT; ++k) if (li[k] >= 0) sb8[li[k]] = (uint8_t)(c0v <= xv[k] ? 1 : 0);
+            for (int k = 0; k < PT; ++k) if (li[k] >= 0) sb8[li[k]] = (uint8_t)(c0v <= (double)xv[k] ? 1 : 0);
         } else {
 #pragma unroll
             for (int k = 0; k < PT; ++k)
                 if (li[k] >= 0) {
-                    const int b = upper_bound_cut(cv, nc, xv[k]);
+                    const int b = upper_bound_cut(cv, nc, (double)xv[k]);
                     if (w16) sb[li[k]] = (uint16_t)b; else sb8[li[k]] = (uint8_t)b;
                 }
         }

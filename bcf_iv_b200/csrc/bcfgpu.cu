@@ -663,46 +663,73 @@ constexpr size_t STAGE_BYTES = (size_t)64 << 20;  // fp64 staging buffer of K0, 
 // K0 over a column-major host matrix: column chunks cross the bus on the copy stream (straight from the caller's buffer
 // when it is pinned; through two pinned staging buffers filled by host threads when it is pageable, as R's memory is)
 // while the previous chunk is binned on the compute stream.  No n x p fp64 copy ever exists on the device.
-static int bin_forest(bcfgpu_handle* h, int f, const double* x)
+// Runs of ONE-cutpoint columns (the reference's two-valued covariates) cross as BYTES: the host threads that fill the pinned
+// staging buffer write (cut <= x) instead of copying 8 bytes -- the same pass over the caller's memory, an eighth of the
+// traffic over PCIe (which is what bounds set_data: 820 MB at 50 GB/s at n = 1e6, p = 100) -- and k_bin only places them.
+// BCFGPU_NO_HOST_PACK=1 sends every column as doubles (the tests run both ways).
+// o[i] = (cut <= x[i]) for i in [i0, i1): the staging pass of a one-cutpoint column (memory-bound; the AVX2 clone keeps a
+// single thread near its streaming bandwidth)
+__attribute__((target_clones("avx2", "default")))
+static void pack_column(const double* __restrict__ xs, double cut, int64_t i0, int64_t i1, uint8_t* __restrict__ o)
 {
-    ForestHost& F = h->fh[f];
-    if (F.p == 0) return BCFGPU_OK;
+    for (int64_t i = i0; i < i1; ++i) o[i] = (uint8_t)(cut <= xs[i]);
+}
+static int bin_columns(bcfgpu_handle* h, ForestHost& F, const double* x, int v0, int v1, bool as_bytes, bool pinned)
+{
     const int64_t n = h->n;
-    const size_t colb = (size_t)n * 8;
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)F.p, STAGE_BYTES / colb));
+    const size_t es = as_bytes ? 1 : 8, colb = (size_t)n * es;
+    const int ncol = v1 - v0;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)ncol, STAGE_BYTES / colb));
     const size_t stage_bytes = (size_t)chunk * colb;
-    cudaPointerAttributes pa;
-    bool pinned = cudaPointerGetAttributes(&pa, x) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
-    cudaGetLastError();
-    if (getenv("BCFGPU_FORCE_PAGEABLE")) pinned = false;
-    const int nbuf = ((size_t)F.p > (size_t)chunk) ? 2 : 1;
+    const bool staged = as_bytes || !pinned;
+    const int nbuf = (ncol > chunk) ? 2 : 1;
     Block stage[2] = {{nullptr, 0}, {nullptr, 0}}, pin[2] = {{nullptr, 0}, {nullptr, 0}};
     int rc = BCFGPU_OK;
     for (int b = 0; b < nbuf && rc == BCFGPU_OK; ++b) {
         if (dev_alloc(h->device, stage_bytes, &stage[b]) != cudaSuccess) rc = fail(BCFGPU_ERR_OOM, "staging buffer of the binning kernel");
-        else if (!pinned && pin_alloc(stage_bytes, &pin[b]) != cudaSuccess) rc = fail(BCFGPU_ERR_OOM, "pinned staging buffer");
+        else if (staged && pin_alloc(stage_bytes, &pin[b]) != cudaSuccess) rc = fail(BCFGPU_ERR_OOM, "pinned staging buffer");
     }
     cudaError_t e = cudaSuccess;
-    for (int c0 = 0, k = 0; c0 < F.p && rc == BCFGPU_OK && e == cudaSuccess; c0 += chunk, ++k) {
+    for (int c0 = v0, k = 0; c0 < v1 && rc == BCFGPU_OK && e == cudaSuccess; c0 += chunk, ++k) {
         const int b = k & (nbuf - 1);
-        const int nc = std::min(chunk, F.p - c0);
+        const int nc = std::min(chunk, v1 - c0);
         const size_t bytes = (size_t)nc * colb;
         const double* src = x + (size_t)c0 * n;
+        const void* from = src;
         if (k >= nbuf) e = cudaStreamWaitEvent(h->copy_stream, h->ev_binned[b], 0);       // the staging buffer is free again
-        if (!pinned && e == cudaSuccess) {
+        if (staged && e == cudaSuccess) {
             if (k >= nbuf) e = cudaEventSynchronize(h->ev_copied[b]);                     // ... and so is the pinned one
-            char* dst = (char*)pin[b].p;
-            parallel_ranges((int64_t)bytes, 1 << 16, host_threads(), [&](int, int64_t lo, int64_t hi) { memcpy(dst + lo, (const char*)src + lo, (size_t)(hi - lo)); });
-            src = (const double*)pin[b].p;
+            if (as_bytes) {
+                uint8_t* dst = (uint8_t*)pin[b].p;
+                const double* cuts = F.cuts.data();
+                const int32_t* off = F.off.data();
+                parallel_ranges((int64_t)nc * n, 1 << 14, host_threads(), [&](int, int64_t lo, int64_t hi) {
+                    while (lo < hi) {                                                     // (a range may span columns)
+                        const int64_t c = lo / n, i0 = lo - c * n, i1 = std::min<int64_t>(n, i0 + (hi - lo));
+                        const double cut = cuts[off[c0 + c]];
+                        pack_column(src + c * n, cut, i0, i1, dst + c * n);
+                        lo += i1 - i0;
+                    }
+                });
+            } else {
+                char* dst = (char*)pin[b].p;
+                parallel_ranges((int64_t)bytes, 1 << 16, host_threads(), [&](int, int64_t lo, int64_t hi) { memcpy(dst + lo, (const char*)src + lo, (size_t)(hi - lo)); });
+            }
+            from = pin[b].p;
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(stage[b].p, src, bytes, cudaMemcpyHostToDevice, h->copy_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(stage[b].p, from, bytes, cudaMemcpyHostToDevice, h->copy_stream);
         if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied[b], h->copy_stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0);
         if (e != cudaSuccess) break;
         h->h2d_bytes += (int64_t)bytes;
         dim3 grid((unsigned)((n + BIN_ROWS - 1) / BIN_ROWS), (unsigned)((nc + BIN_COLS - 1) / BIN_COLS));
-        k_bin<<<grid, 256, 0, h->stream>>>((const double*)stage[b].p, n, nc, c0, F.d_cuts, F.d_off, F.d_col_index, F.d_is16, h->d_pos,
-                                            h->n_pad, (int)((int64_t)h->dev.trt_tiles * TILE), F.d_bins8, F.d_bins16);
+        const int trt_pad = (int)((int64_t)h->dev.trt_tiles * TILE);
+        if (as_bytes)
+            k_bin<uint8_t><<<grid, 256, 0, h->stream>>>((const uint8_t*)stage[b].p, n, nc, c0, F.d_cuts, F.d_off, F.d_col_index, F.d_is16, h->d_pos,
+                                                         h->n_pad, trt_pad, F.d_bins8, F.d_bins16);
+        else
+            k_bin<double><<<grid, 256, 0, h->stream>>>((const double*)stage[b].p, n, nc, c0, F.d_cuts, F.d_off, F.d_col_index, F.d_is16, h->d_pos,
+                                                        h->n_pad, trt_pad, F.d_bins8, F.d_bins16);
         h->launches++;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaEventRecord(h->ev_binned[b], h->stream);
@@ -714,6 +741,26 @@ static int bin_forest(bcfgpu_handle* h, int f, const double* x)
     if (rc == BCFGPU_OK && e != cudaSuccess) rc = fail(BCFGPU_ERR_CUDA, std::string("k_bin: ") + cudaGetErrorString(e));
     for (int b = 0; b < 2; ++b) { dev_free(h->device, stage[b]); pin_free(pin[b]); }
     return rc;
+}
+static int bin_forest(bcfgpu_handle* h, int f, const double* x)
+{
+    ForestHost& F = h->fh[f];
+    if (F.p == 0) return BCFGPU_OK;
+    cudaPointerAttributes pa;
+    bool pinned = cudaPointerGetAttributes(&pa, x) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (getenv("BCFGPU_FORCE_PAGEABLE")) pinned = false;
+    const bool pack = !getenv("BCFGPU_NO_HOST_PACK");
+    auto byteable = [&](int v) { return pack && F.ncut[v] == 1 && !F.is16[v]; };
+    for (int v0 = 0; v0 < F.p;) {                      // maximal runs of columns of one kind
+        const bool bts = byteable(v0);
+        int v1 = v0 + 1;
+        while (v1 < F.p && byteable(v1) == bts) ++v1;
+        const int rc = bin_columns(h, F, x, v0, v1, bts, pinned);
+        if (rc) return rc;
+        v0 = v1;
+    }
+    return BCFGPU_OK;
 }
 
 static void fill_forest_dev(const bcfgpu_handle* h, int f, ForestDev& D)

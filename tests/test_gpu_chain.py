@@ -3,6 +3,8 @@
 Reference call sites: R/bcf_iv.R:89-91, R/bcf_itt.R:71-75 (bcf(...)$tau -> colMeans).  PARITY UNPINNED: the
 oracle restates the un-vendored `bcf` package; agreement is with that restatement.
 """
+import os
+
 import numpy as np
 
 import helpers
@@ -202,7 +204,8 @@ def test_shared_covariate_matrix_is_copied_once_and_changes_nothing():
     from bcf_iv_b200 import _lib
     b = _lib.Sampler(lambda_=P.lambda_, sigma_init=P.sigma_init, con_sd=P.con_sd, mod_sd=P.mod_sd, seed=4)
     b.set_data(P.yscale, P.z, P.x_c, np.array(P.x_m, order="F"), pr.cuts_c_flat, pr.off_c, pr.cuts_m_flat, pr.off_m)
-    assert b.h2d_bytes - shared_bytes == P.x_m.size * 8
+    # (the second copy of these two-valued columns crosses the bus as bytes: set_data's staging pass compares on the way)
+    assert b.h2d_bytes - shared_bytes == P.x_m.size * (8 if os.environ.get("BCFGPU_NO_HOST_PACK") else 1)
     b.run(3, 4)
     assert a.trace()[0].tobytes() == b.trace()[0].tobytes()
     assert a.tau_mean().tobytes() == b.tau_mean().tobytes()

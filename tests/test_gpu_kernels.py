@@ -164,3 +164,31 @@ def test_caching_allocator_reuses_blocks_and_releases_them():
     assert _lib.cache_stats()["device_bytes"] >= st0["device_bytes"]
     _lib.release_cached_memory()
     assert _lib.cache_stats()["device_bytes"] == 0
+
+
+@pytest.mark.parametrize("pageable", [False, True])
+def test_one_cutpoint_columns_cross_the_bus_as_bytes(monkeypatch, pageable):
+    """set_data's staging pass writes (cut <= x) as a byte for every run of one-cutpoint columns (the reference's two-valued
+    covariates) instead of copying the double: same bins -- the leaf assignment of a random tree equals the oracle's walk
+    over the raw doubles either way -- and an eighth of the bytes over PCIe for those columns."""
+    if pageable:
+        monkeypatch.setenv("BCFGPU_FORCE_PAGEABLE", "1")
+    pr = make_problem(n=6007, p=12, seed=21)                       # 12 binary columns + the 10 000-cutpoint pihat column
+    o = oracle_sampler(pr, ntree_con=2, ntree_mod=1)
+    rng = np.random.default_rng(8)
+    heap, var, cut, mu = _random_tree(rng, [len(c) for c in pr.P.cuts_c], 24)
+    o.set_tree(0, heap, var, cut, mu)
+    want = o.assign_leaves(0)[pr.P.inv_perm]
+    moved = {}
+    for packed in (True, False):
+        if packed:
+            monkeypatch.delenv("BCFGPU_NO_HOST_PACK", raising=False)
+        else:
+            monkeypatch.setenv("BCFGPU_NO_HOST_PACK", "1")
+        g = gpu_sampler(pr, ntree_con=2, ntree_mod=1)
+        g.set_tree(0, heap, var, cut, mu)
+        assert np.array_equal(g.leaf_ids(0), want)
+        assert g.verify_leaf_cache() == 0
+        moved[packed] = g.h2d_bytes
+        g.close()
+    assert moved[False] - moved[True] == 12 * 6007 * 7            # 12 columns x n rows x (8 - 1) bytes
