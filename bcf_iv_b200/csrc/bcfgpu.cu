@@ -5,6 +5,7 @@
 #include "bcf_persistent.cuh"
 #include "bcf_batched.cuh"
 #include "bcf_pipe.cuh"
+#include "bcf_hist_mma.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -382,7 +383,7 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     // handle, so it is raised once to the device's opt-in maximum (handles with different n on one GPU would otherwise
     // lower each other's limit between select_kernel() and the launch); select_kernel() only checks its own need.
     if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&h->max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    for (const void* fn : {(const void*)k_batched<true>, (const void*)k_pipe, (const void*)k_resident}) {
+    for (const void* fn : {(const void*)k_batched<true>, (const void*)k_pipe, (const void*)k_resident, (const void*)k_hist_mma}) {
         cudaFuncAttributes fa;
         if (e2 == cudaSuccess) e2 = cudaFuncGetAttributes(&fa, fn);
         if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin - (int)fa.sharedSizeBytes);
@@ -666,7 +667,7 @@ constexpr size_t STAGE_BYTES = (size_t)64 << 20;  // fp64 staging buffer of K0, 
 // Runs of ONE-cutpoint columns (the reference's two-valued covariates) cross as BYTES: the host threads that fill the pinned
 // staging buffer write (cut <= x) instead of copying 8 bytes -- the same pass over the caller's memory, an eighth of the
 // traffic over PCIe (which is what bounds set_data: 820 MB at 50 GB/s at n = 1e6, p = 100) -- and k_bin only places them.
-// BCFGPU_NO_HOST_PACK=1 sends every column as doubles (the tests run both ways).
+// BCFGPU_NO_HOST_PACK=1 sends every column as doubles (the tests run both ways); BCFGPU_HOST_PACK=1 skips the probe below.
 // o[i] = (cut <= x[i]) for i in [i0, i1): the staging pass of a one-cutpoint column (memory-bound; the AVX2 clone keeps a
 // single thread near its streaming bandwidth)
 __attribute__((target_clones("avx2", "default")))
@@ -674,12 +675,14 @@ static void pack_column(const double* __restrict__ xs, double cut, int64_t i0, i
 {
     for (int64_t i = i0; i < i1; ++i) o[i] = (uint8_t)(cut <= xs[i]);
 }
-static int bin_columns(bcfgpu_handle* h, ForestHost& F, const double* x, int v0, int v1, bool as_bytes, bool pinned)
+static int bin_columns(bcfgpu_handle* h, ForestHost& F, const double* x, int v0, int v1, bool as_bytes, bool pinned, double* pack_s = nullptr)
 {
     const int64_t n = h->n;
     const size_t es = as_bytes ? 1 : 8, colb = (size_t)n * es;
     const int ncol = v1 - v0;
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)ncol, STAGE_BYTES / colb));
+    // (bytes: smaller chunks -- the pinned staging buffers are allocated on a process's first fit, and the host pass of the next
+    // chunk runs under the copy and the placement of this one)
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)ncol, (as_bytes ? STAGE_BYTES / 2 : STAGE_BYTES) / colb));
     const size_t stage_bytes = (size_t)chunk * colb;
     const bool staged = as_bytes || !pinned;
     const int nbuf = (ncol > chunk) ? 2 : 1;
@@ -703,6 +706,7 @@ static int bin_columns(bcfgpu_handle* h, ForestHost& F, const double* x, int v0,
                 uint8_t* dst = (uint8_t*)pin[b].p;
                 const double* cuts = F.cuts.data();
                 const int32_t* off = F.off.data();
+                const auto tp0 = std::chrono::steady_clock::now();
                 parallel_ranges((int64_t)nc * n, 1 << 14, host_threads(), [&](int, int64_t lo, int64_t hi) {
                     while (lo < hi) {                                                     // (a range may span columns)
                         const int64_t c = lo / n, i0 = lo - c * n, i1 = std::min<int64_t>(n, i0 + (hi - lo));
@@ -711,6 +715,7 @@ static int bin_columns(bcfgpu_handle* h, ForestHost& F, const double* x, int v0,
                         lo += i1 - i0;
                     }
                 });
+                if (pack_s) *pack_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count();
             } else {
                 char* dst = (char*)pin[b].p;
                 parallel_ranges((int64_t)bytes, 1 << 16, host_threads(), [&](int, int64_t lo, int64_t hi) { memcpy(dst + lo, (const char*)src + lo, (size_t)(hi - lo)); });
@@ -742,6 +747,7 @@ static int bin_columns(bcfgpu_handle* h, ForestHost& F, const double* x, int v0,
     for (int b = 0; b < 2; ++b) { dev_free(h->device, stage[b]); pin_free(pin[b]); }
     return rc;
 }
+constexpr double HOST_PACK_MIN_RATE = 36e9;   // bytes / s of the probe below which pinned one-cutpoint columns cross by DMA as doubles
 static int bin_forest(bcfgpu_handle* h, int f, const double* x)
 {
     ForestHost& F = h->fh[f];
@@ -756,7 +762,19 @@ static int bin_forest(bcfgpu_handle* h, int f, const double* x)
         const bool bts = byteable(v0);
         int v1 = v0 + 1;
         while (v1 < F.p && byteable(v1) == bts) ++v1;
-        const int rc = bin_columns(h, F, x, v0, v1, bts, pinned);
+        int rc;
+        if (bts && pinned && !getenv("BCFGPU_HOST_PACK") && v1 - v0 > 8) {
+            // Pinned input could also cross by DMA without a host pass (50 GB/s over PCIe gen5): the byte path only pays when
+            // the host threads read faster than that -- they do on an idle box (85 GB/s on 16 cores), they may not when
+            // several ranks share few cores.  The first columns are the probe; it reads low (thread wake-up inside 64 MB:
+            // a box whose probe said 47-52 GB/s moved X in 11.8 ms as bytes, 16.5 ms as doubles), hence the margin.
+            double pack_s = 0.0;
+            rc = bin_columns(h, F, x, v0, v0 + 8, true, pinned, &pack_s);
+            const double rate = 8.0 * (double)h->n * 8.0 / std::max(pack_s, 1e-9);
+            if (getenv("BCFGPU_SETDATA_PROFILE")) fprintf(stderr, "[bcfgpu set_data] host pass of one-cutpoint columns: %.1f GB/s -> %s\n", rate * 1e-9, rate >= HOST_PACK_MIN_RATE ? "bytes" : "doubles by DMA");
+            if (!rc) rc = bin_columns(h, F, x, v0 + 8, v1, rate >= HOST_PACK_MIN_RATE, pinned);
+        } else
+            rc = bin_columns(h, F, x, v0, v1, bts, pinned);
         if (rc) return rc;
         v0 = v1;
     }
@@ -1729,6 +1747,24 @@ int bcfgpu_op_suffstats(bcfgpu_handle* h, int32_t tree, const double* r, uint32_
     return BCFGPU_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime (the library links cudart only): the TMA descriptor of K2''s B operand
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
 int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, int32_t nleaf, const double* r,
                        int64_t* cnt, double* sum, double* device_ms)
 {
@@ -1760,9 +1796,12 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
     std::vector<int32_t> small, large, cellbase, twoval;
     int ncells = 0;
     const int nl2 = nleaf <= 1 ? 1 : nleaf <= 2 ? 2 : nleaf <= 4 ? 4 : 8;     // k_hist_bits is instantiated for 1, 2, 4, 8 leaves
-    const bool use_bits = nleaf <= 8 && !getenv("BCFGPU_NO_HIST_BITS");
+    // two-valued columns, up to 12 leaves: the int8 tensor-core contraction (k_hist_mma: exact, HBM-bound, independent of the
+    // number of leaves); BCFGPU_NO_HIST_MMA=1: the CUDA-core kernel of round 1 (k_hist_bits, up to 8 leaves)
+    const bool use_mma = nleaf <= HM_MAX_LEAF && F.p8 > 0 && !getenv("BCFGPU_NO_HIST_MMA") && tensor_map_encoder() != nullptr;
+    const bool use_bits = !use_mma && nleaf <= 8 && !getenv("BCFGPU_NO_HIST_BITS");
     for (int v = 0; v < F.p; ++v) {
-        if (use_bits && !F.is16[v] && F.ncut[v] == 1) { twoval.push_back(v); continue; }   // two-valued: register accumulators
+        if ((use_mma || use_bits) && !F.is16[v] && F.ncut[v] == 1) { twoval.push_back(v); continue; }   // two-valued: register / tensor-memory accumulators
         const int add = per_obs ? nleaf * (F.ncut[v] + 1) : nleaf * F.ncut[v];
         const size_t need = per_obs ? (size_t)(ncells + add) * 32 : (size_t)(ncells + add + nleaf) * 16;
         if (!F.is16[v] && F.ncut[v] + 1 <= HIST2_MAX_BINS && nleaf <= HIST2_MAX_LEAF && need <= smem_cap) {
@@ -1770,13 +1809,21 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
         } else large.push_back(v);
     }
     int32_t* dcols = nullptr;
-    CK(cudaMalloc((void**)&dcols, (size_t)(small.size() * 2 + large.size() + twoval.size() + 4) * 4 + 8 * 32));
+    constexpr int LEAF_TOT = 16;                                              // leaf totals kept for up to 16 leaves x 4 words
+    const size_t ncolw = small.size() * 2 + large.size() + twoval.size() + (size_t)F.p8;
+    CK(cudaMalloc((void**)&dcols, (ncolw + 4) * 4 + LEAF_TOT * 32));
     int32_t* dsmall = dcols; int32_t* dbase = dcols + small.size(); int32_t* dlarge = dcols + 2 * small.size();
     int32_t* dtwo = dlarge + large.size();
-    long long* dleaf = reinterpret_cast<long long*>(dcols + ((small.size() * 2 + large.size() + twoval.size() + 2) & ~(size_t)1));   // 8 leaves x 4 words
+    int32_t* dcolvar = dtwo + twoval.size();                                  // [p8] variable of a uint8 column if it is two-valued, else -1
+    long long* dleaf = reinterpret_cast<long long*>(dcols + ((ncolw + 2) & ~(size_t)1));
     if (!twoval.empty()) {
         CK(cudaMemcpyAsync(dtwo, twoval.data(), twoval.size() * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemsetAsync(dleaf, 0, 8 * 32, h->stream));
+        CK(cudaMemsetAsync(dleaf, 0, LEAF_TOT * 32, h->stream));
+    }
+    std::vector<int32_t> colvar((size_t)std::max(F.p8, 1), -1);
+    if (use_mma && !twoval.empty()) {
+        for (int v : twoval) colvar[(size_t)F.col_index[v]] = v;
+        CK(cudaMemcpyAsync(dcolvar, colvar.data(), (size_t)F.p8 * 4, cudaMemcpyHostToDevice, h->stream));
     }
     if (!small.empty()) {
         CK(cudaMemcpyAsync(dsmall, small.data(), small.size() * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1784,7 +1831,47 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
     }
     if (!large.empty()) CK(cudaMemcpyAsync(dlarge, large.data(), large.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
-    if (!twoval.empty()) {
+    if (!twoval.empty() && use_mma) {
+        // B operand = the forest's uint8 bins as they lie in HBM: [p8 columns][n_pad observations], one byte each
+        const int ncb = std::min(F.p8, HM_MAX_COLS), gy = (F.p8 + ncb - 1) / ncb;
+        const int ktiles = (int)(h->n_pad / HM_KT);
+        const int gx0 = std::max(1, std::min(ktiles, std::max(1, h->num_sms / gy)));
+        const int tpc = (ktiles + gx0 - 1) / gx0;
+        CUtensorMap tm;
+        const cuuint64_t gdim[2] = {(cuuint64_t)h->n_pad, (cuuint64_t)F.p8}, gstr[1] = {(cuuint64_t)h->n_pad};
+        const cuuint32_t box[2] = {(cuuint32_t)HM_KT, (cuuint32_t)ncb}, estr[2] = {1u, 1u};
+        const CUresult cr = tensor_map_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)F.d_bins8, gdim, gstr, box, estr,
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { cudaFree(dlab); cudaFree(dout); cudaFree(dcols); return fail(BCFGPU_ERR_CUDA, "op_hist_all: cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"); }
+        // as many ring stages as shared memory holds, up to 8 (8 stages up to 8 leaves at 100 columns; 4 at 240 columns); the
+        // epilogue's tile of the accumulator needs three
+        // (an EVEN number: a stage is then always served by the same producer and the same MMA issuer -- the tiles' parity --,
+        // which the parity waits on its barriers rely on)
+        int nst = HM_MAX_STAGES;
+        while (nst > 4 && hm_smem_bytes(ncb, nst, nleaf) > (size_t)h->max_optin) nst -= 2;
+        const size_t smem = hm_smem_bytes(ncb, nst, nleaf);
+        if (smem > (size_t)h->max_optin) { cudaFree(dlab); cudaFree(dout); cudaFree(dcols); return fail(BCFGPU_ERR_CUDA, "op_hist_all: k_hist_mma does not fit in shared memory"); }
+        dim3 grid((unsigned)((ktiles + tpc - 1) / tpc), (unsigned)gy);
+        const int probe = getenv("BCFGPU_HIST_PROBE") ? atoi(getenv("BCFGPU_HIST_PROBE")) : 0;   // timing experiments only
+        long long* dtrace = nullptr;
+        if (getenv("BCFGPU_HIST_TRACE")) { CK(cudaMalloc((void**)&dtrace, 6 * 64 * 8)); CK(cudaMemsetAsync(dtrace, 0, 6 * 64 * 8, h->stream)); }
+        k_hist_mma<<<grid, HM_THREADS, smem, h->stream>>>(tm, dlab, h->d_tmp2, nleaf, ncb, F.p8, ktiles, tpc, nst, dcolvar, F.d_off,
+                                                          (long long)nbt, dout, dleaf, h->dev.err, h->dev.dbg, probe, dtrace);
+        if (dtrace) {   // the timeline of CTA 0, in cycles since its start (a debugging aid: synchronises)
+            long long tr[6 * 64];
+            CK(cudaMemcpyAsync(tr, dtrace, sizeof(tr), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(dtrace);
+            const long long t0 = tr[5 * 64];
+            fprintf(stderr, "[k_hist_mma trace] nst %d tiles/CTA %d: set-up %lld, accumulator complete %lld, in smem %lld, end %lld\n", nst, tpc,
+                    tr[5 * 64 + 1] - t0, tr[5 * 64 + 2] - t0, tr[5 * 64 + 3] - t0, tr[5 * 64 + 4] - t0);
+            for (int i = 0; i < std::min(tpc, 64); ++i)
+                fprintf(stderr, "  tile %2d: issued %7lld landed(builder) %7lld built %7lld mma-ready %7lld committed %7lld\n", i, tr[i] - t0,
+                        tr[64 + i] - t0, tr[128 + i] - t0, tr[192 + i] - t0, tr[256 + i] - t0);
+        }
+        h->launches++;
+    } else if (!twoval.empty()) {
         const int cpc = HISTB_CELLS / nl2, gy = ((int)twoval.size() + cpc - 1) / cpc;
         const int tiles = h->dev.n_tiles;
         const int waves = getenv("BCFGPU_HIST_WAVES") ? std::max(1, atoi(getenv("BCFGPU_HIST_WAVES"))) : 4;
@@ -1817,7 +1904,7 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
     CK(cudaEventRecord(h->ev1, h->stream));
     h->launches += 2;
     std::vector<long long> tot((size_t)nleaf * nbt * 4);
-    long long leaf_tot[8 * 4] = {0};
+    long long leaf_tot[LEAF_TOT * 4] = {0};
     e = cudaMemcpyAsync(tot.data(), dout, tot.size() * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && !twoval.empty()) e = cudaMemcpyAsync(leaf_tot, dleaf, sizeof(leaf_tot), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

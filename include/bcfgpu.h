@@ -229,7 +229,10 @@ BCFGPU_API int bcfgpu_op_suffstats(bcfgpu_handle *h, int32_t tree, const double 
                                    int32_t var, int32_t cut, int32_t *nleaves, uint32_t *heap, int64_t *cnt_trt,
                                    int64_t *cnt_ctl, double *sum_trt, double *sum_ctl, double out_birth[8]);
 /* K2': all-candidate histogram: for leaf labels slot[i] in [0,nleaf) (or <0 = skip) and forest (0 con, 1 mod):
- * cnt/sum[leaf][cut_off[v] + v + b] over bins b = 0..ncut_v.  (count, residual sum) for every (var, cutpoint). */
+ * cnt/sum[leaf][cut_off[v] + v + b] over bins b = 0..ncut_v.  (count, residual sum) for every (var, cutpoint).
+ * Two-valued columns with nleaf <= 12 go through k_hist_mma (tcgen05 int8 contraction over TMA-fed bins, int32
+ * accumulators in tensor memory: sums exact in the 2^-44 fixed point, |r| < 2^15); BCFGPU_NO_HIST_MMA=1 selects the
+ * CUDA-core kernels of round 1 instead. */
 BCFGPU_API int bcfgpu_op_hist_all(bcfgpu_handle *h, int32_t forest, const int32_t *slot_n, int32_t nleaf,
                                   const double *r_n, int64_t *cnt, double *sum, double *device_ms);
 /* K3: integrated log-likelihood of a leaf, weighted form (bcf's lilhet without the cancelling term) */

@@ -90,6 +90,58 @@ def test_k2prime_all_candidate_histogram():
             assert ms > 0
 
 
+def _exact_hist_two_valued(X, cuts, slot, nleaf, r):
+    """per (leaf, column): exact counts and the exact sum of the 2^-44 fixed-point residuals (Python integers), bins 0 / 1"""
+    fx = np.rint(r * 2.0 ** 44).astype(np.int64)
+    cnt = np.zeros((nleaf, X.shape[1], 2), dtype=np.int64)
+    sm = np.zeros((nleaf, X.shape[1], 2), dtype=np.float64)
+    for l in range(nleaf):
+        m = slot == l
+        for v in range(X.shape[1]):
+            one = m & (X[:, v] >= cuts[v])
+            zero = m & ~(X[:, v] >= cuts[v])
+            cnt[l, v, 0], cnt[l, v, 1] = zero.sum(), one.sum()
+            sm[l, v, 0] = int(fx[zero].sum(dtype=object) if zero.any() else 0) / 2 ** 44      # (int / int: correctly rounded)
+            sm[l, v, 1] = int(fx[one].sum(dtype=object) if one.any() else 0) / 2 ** 44
+    return cnt, sm
+
+
+@pytest.mark.parametrize("n,p", [(5000, 12), (70001, 33), (3000, 300), (600000, 20)])
+def test_k2prime_on_the_tensor_cores_is_exact(n, p, monkeypatch):
+    """K2' for two-valued columns as an int8 contraction on tcgen05 (k_hist_mma: TMA-fed bins, 7-bit limbs of the fixed-point
+    residual, int32 accumulators in tensor memory): counts exact and sums BIT-EXACT against integer arithmetic on the host,
+    for 1..12 leaves, skipped labels, more than 240 columns (two column
+    passes); and equal to the CUDA-core kernel it replaces (k_hist_bits, fp64 lane sums rounded once) within that kernel's 1e-13."""
+    rng = np.random.default_rng(n + p)
+    X = rng.integers(0, 2, (n, p)).astype(np.float64)
+    z = rng.integers(0, 2, n).astype(np.int32)
+    y = rng.standard_normal(n)
+    cuts = [np.array([0.5])] * p
+    flat, off = prep.pack_cuts(cuts)
+    s = _lib.Sampler(lambda_=1.0, sigma_init=1.0, seed=1, ntree_con=2, ntree_mod=2)
+    s.set_data(y, z, X, X, flat, off, flat, off)
+    r = rng.standard_normal(n) * 3.0
+    r[::97] = 0.0
+    r[5] = 32767.99                                                      # the edge of the fixed-point range, both signs
+    r[6] = -32767.99
+    for nleaf in ((1, 2, 5, 8, 12) if n < 100000 else (3, 12)):
+        slot = rng.integers(-1, nleaf, n).astype(np.int32)
+        monkeypatch.delenv("BCFGPU_NO_HIST_MMA", raising=False)
+        want_c, want_s = _exact_hist_two_valued(X, np.full(p, 0.5), slot, nleaf, r)
+        cg, sg, ms = s.op_hist_all(1, slot, nleaf, r)
+        cg = cg.reshape(nleaf, p, 2); sg = sg.reshape(nleaf, p, 2)
+        assert np.array_equal(cg, want_c)
+        assert np.array_equal(sg, want_s)                               # bit-exact: integer sums, one rounding
+        if nleaf <= 8:   # (k_hist_bits rounds a CTA's fp64 SUM to fixed point: it needs |sum| < 2^15, so a smaller r for the pair)
+            rs = r / 1024.0
+            cm, smm, _ = s.op_hist_all(1, slot, nleaf, rs)
+            monkeypatch.setenv("BCFGPU_NO_HIST_MMA", "1")
+            cb, sb, _ = s.op_hist_all(1, slot, nleaf, rs)
+            assert np.array_equal(cb, cm) and np.array_equal(cm.reshape(nleaf, p, 2), cg)
+            assert np.allclose(sb, smm, rtol=0, atol=1e-13 * np.abs(rs).sum())
+    s.close()
+
+
 def test_k3_integrated_likelihood():
     from oracle import orc
     rng = np.random.default_rng(1)
