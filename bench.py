@@ -483,6 +483,18 @@ def run_ours(args):
         # (1) the chain far into burn-in: trees at their stationary sizes (the headline burns in args.burnin sweeps)
         s.run(args.long_burnin - args.burnin - W - K, 0)
         regimes[f"after_{args.long_burnin}_burnin_sweeps"] = dict(timed(s, 1), note="same chain, same data as the headline")
+        # (3) K2' (SURVEY 8a-4), the all-candidate histogram over the same binned covariates: what bcf_iv's subgroup CART calls
+        # once per tree level; for two-valued columns an exact int8 contraction on tcgen05 (k_hist_mma).  Device time of the
+        # kernel (events inside the library), algorithmic bytes n * (9 + p); not part of the sweeps/s figures.
+        rr = np.random.default_rng(args.data_seed + 7).standard_normal(n)
+        k2 = {}
+        for nleaf in (1, 4, 8):
+            slot = (np.arange(n) % nleaf).astype(np.int32)
+            us = min(s.op_hist_all(1, slot, nleaf, rr)[2] for _ in range(3)) * 1e3
+            gbs = n * (9 + p) / 1e9 / (us * 1e-6)
+            k2[f"leaves_{nleaf}"] = {"us": us, "GBps": gbs, "roofline_frac": gbs / peak_gbs}
+        regimes["k2prime_all_candidate_histogram"] = dict(k2, kernel="k_hist_mma (tcgen05.mma.kind::i8, TMA, tensor memory)",
+                                                          algorithmic_bytes=n * (9 + p), columns=p)
     s.close()
     if regimes is not None:
         # (2) SURVEY 8d's stress variant: continuous covariates -> 10 000-cutpoint grids, uint16 bin columns
