@@ -29,7 +29,7 @@ SYMBOLS = [
     "bcfgpu_num_saved_forests", "bcfgpu_predict", "bcfgpu_get_scalars", "bcfgpu_get_fits", "bcfgpu_get_counters", "bcfgpu_get_trace", "bcfgpu_tree_size",
     "bcfgpu_get_tree", "bcfgpu_set_tree", "bcfgpu_get_leaf_ids", "bcfgpu_verify_leaf_cache", "bcfgpu_op_bin_column",
     "bcfgpu_op_suffstats", "bcfgpu_op_hist_all", "bcfgpu_op_lil", "bcfgpu_op_rng_probe", "bcfgpu_op_probit_latent",
-    "bcfgpu_glm_logit", "bcfgpu_lm_sigma",
+    "bcfgpu_glm_logit", "bcfgpu_lm_sigma", "bcfgpu_scan_columns",
 ]
 
 
@@ -119,6 +119,7 @@ def load():
     L.bcfgpu_op_probit_latent.argtypes = [dp, ip, dp, C.c_int32, dp]
     L.bcfgpu_glm_logit.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, C.c_int32, ip, C.c_int32, C.c_double, dp, dp, dp, ip]
     L.bcfgpu_lm_sigma.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, C.c_int32, ip, dp, dp, dp, ip]
+    L.bcfgpu_scan_columns.argtypes = [dp, C.c_int64, C.c_int32, C.c_int64, dp, dp, C.POINTER(C.c_uint8)]
     for nm in SYMBOLS:
         f = getattr(L, nm)
         if nm not in ("bcfgpu_last_error", "bcfgpu_config_init"):
@@ -517,6 +518,21 @@ def glm_logit(z, X, device=0, max_iter=25, epsilon=1e-8, full=False):
         return eta, {"beta": beta, "deviance": float(dev[0]), "iterations": int(info[0]), "converged": bool(info[1]),
                      "rank": int(info[2]), "launches": int(info[3])}
     return eta
+
+
+def scan_columns(X):
+    """(lo, hi, flags) per column of a column-major float64 matrix in one threaded host pass (bcfgpu_scan_columns):
+    flags bit 0 = two-valued or constant column, bit 1 = NaN / Inf present.  Any column stride >= n rows is taken as it is."""
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim != 2 or X.shape[1] == 0 or X.shape[0] == 0:
+        raise ValueError("scan_columns needs a non-empty matrix")
+    n, p = X.shape
+    if not (X.strides[0] == 8 and (p == 1 or (X.strides[1] % 8 == 0 and X.strides[1] >= 8 * n))):
+        X = np.asfortranarray(X)
+    ld = n if p == 1 else X.strides[1] // 8
+    lo = np.empty(p); hi = np.empty(p); fl = np.zeros(p, dtype=np.uint8)
+    check(load().bcfgpu_scan_columns(_dp(X), n, p, ld, _dp(lo), _dp(hi), fl.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return lo, hi, fl
 
 
 def lm_sigma(y, z, X, device=0, full=False):

@@ -46,15 +46,20 @@ def bart_config(n_trees=N_TREES, k=K_SD, base=BASE, power=POWER, seed=0, chain=0
     return cfg
 
 
-def _as_design(X, extra_cols=0):
+def _as_design(X, extra_cols=0, rows=None):
     """n x (p + extra_cols) column-major matrix whose leading columns are X (row-major input: transposed in cache-sized
-    blocks, 1.5x a plain assignment; column-major input: a column-wise memcpy)"""
+    blocks, 1.5x a plain assignment; column-major input: a column-wise memcpy).  rows: an index vector -- the matrix of
+    X[rows] without the row-major intermediate (gathered block by block, straight into the column-major result)."""
     X = np.asarray(X, dtype=np.float64)
     if X.ndim == 1:
         X = X[:, None]
-    n, p = X.shape
+    p = X.shape[1]
+    n = X.shape[0] if rows is None else len(rows)
     xc = np.empty((n, p + extra_cols), dtype=np.float64, order="F")
-    if X.flags.c_contiguous and p > 1:
+    if rows is not None:
+        for r0 in range(0, n, 8192):
+            xc[r0:r0 + 8192, :p] = X[rows[r0:r0 + 8192]]
+    elif X.flags.c_contiguous and p > 1:
         for r0 in range(0, n, 8192):
             xc[r0:r0 + 8192, :p] = X[r0:r0 + 8192]
     else:

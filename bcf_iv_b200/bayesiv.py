@@ -180,6 +180,22 @@ def prep_cat_levels():
     return prep.CP_CAT_LEVELS
 
 
+class _Rows:
+    """X[rows] as far as the node rules need it: one column at a time (the inference sample is only ever looked at through
+    the few split variables, so its n x p row gather is never made)"""
+
+    def __init__(self, X, rows):
+        self.X, self.rows, self.shape, self._col = X, rows, (len(rows), X.shape[1]), {}
+
+    def __getitem__(self, key):
+        sl, v = key
+        if not (isinstance(sl, slice) and sl == slice(None)):
+            raise IndexError("_Rows serves whole columns only")
+        if v not in self._col:
+            self._col[v] = self.X[self.rows, v]
+        return self._col[v]
+
+
 def rule_mask(rule, X):
     m = np.ones(X.shape[0], dtype=bool)
     for v, op, cut in rule:
@@ -311,8 +327,10 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     X = np.asarray(x, dtype=np.float64)
     names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
     disc, index = _split(len(y), inference_ratio, seed)
-    Xd = _bart._as_design(X[disc])                  # the same matrix twice, as the reference passes it: copied to the GPU once;
-                                                    # column-major from here on (what every native entry streams: ONE transposition per call)
+    # the same matrix twice, as the reference passes it: copied to the GPU once; column-major from here on (what every native
+    # entry streams): ONE pass over the discovery rows per call, gathered straight into a buffer with a spare trailing column
+    # where bcf() puts pihat (its design [x | pihat] then needs no copy of its own)
+    Xd = _bart._as_design(X, 1, rows=disc)[:, :X.shape[1]]
     pihat = (logit_fn or logit_link)(z[disc], Xd)                                          # R/bcf_iv.R:72-75
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)
@@ -350,7 +368,8 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
                 f_itt = pool.submit(_itt_b)
             else:
                 def _itt():
-                    r = fit(y[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, keep_sampler=bcf_fn is None))   # R/bcf_iv.R:89-91
+                    own = dict(keep_sampler=True, x_spare_column=True) if bcf_fn is None else dict(keep_sampler=False)
+                    r = fit(y[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, **own))              # R/bcf_iv.R:89-91
                     live.append(r.get("sampler"))
                     return r["tau_mean"]
                 f_itt = pool.submit(_itt)
@@ -378,7 +397,7 @@ def bcf_iv(y, w, z, x, binary=False, n_burn=500, n_sim=500, inference_ratio=0.5,
     if details is not None:
         details.update(disc=disc, index=index, pic=pic, itt=itt, tauhat=tauhat, cart_on_device=bool(on_device),
                        split_vars=sorted({nd.var for nd in nodes.values() if nd.var is not None}))
-    ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
+    ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], _Rows(X, index))
     leaves = {nid for nid in ids if nodes[nid].left is None}
     # rows are indexed by rpart NODE NUMBER as in the reference (bcfivMat[i, ], R/bcf_iv.R:174): the table starts with
     # one row per node and grows, NA rows in between, when a node number exceeds that count
@@ -406,16 +425,17 @@ def bcf_itt(y, w, z, x, binary=False, max_depth=2, n_burn=500, n_sim=500, infere
     X = np.asarray(x, dtype=np.float64)
     names = list(getattr(x, "columns", [f"x{j + 1}" for j in range(X.shape[1])]))
     disc, index = _split(len(y), inference_ratio, seed)
-    Xd = _bart._as_design(X[disc])
+    Xd = _bart._as_design(X, 1, rows=disc)[:, :X.shape[1]]          # (as in bcf_iv: one gather, a spare column for pihat)
     pihat = (logit_fn or logit_link)(z[disc], Xd)                                          # R/bcf_itt.R:58-61
     fit_args = dict(nburn=n_burn, nsim=n_sim, random_seed=seed, keep_draws=False)
     fit_args.update(bcf_args)
     if binary:                                                                              # R/bcf_itt.R:166-170
         tauhat = (bartc_fn or _bart.bartc)(y[disc], z[disc], Xd, n_samples=n_sim, n_burn=n_burn, n_chains=2, seed=seed)["ite_mean"]
     else:
-        tauhat = (bcf_fn or _bcf.bcf)(y[disc], z[disc], Xd, Xd, pihat, **fit_args)["tau_mean"]         # R/bcf_itt.R:71-75
+        own = dict(x_spare_column=True) if bcf_fn is None else {}
+        tauhat = (bcf_fn or _bcf.bcf)(y[disc], z[disc], Xd, Xd, pihat, **dict(fit_args, **own))["tau_mean"]   # R/bcf_itt.R:71-75
     nodes, where = cart(Xd, tauhat, maxdepth=max_depth)                                     # rpart defaults (R/bcf_itt.R:82)
-    ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], X[index])
+    ids, rows = _node_rows(nodes, where, names, y[index], w[index], z[index], _Rows(X, index))
     for nid in ids:
         r = rows[nid]
         if r is None:

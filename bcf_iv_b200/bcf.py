@@ -45,7 +45,8 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
         w=None, random_seed=None, n_chains=1, n_cores=None, n_threads=None, no_output=True,
         save_tree_directory=None, log_file=None, verbose=False,
         devices=None, keep_draws=None, engine=_lib.ENGINE_AUTO, max_ctas=0, first_chain=0,
-        x_predict_control=None, x_predict_moderate=None, pihat_predict=None, predict_draws=False, keep_sampler=False):
+        x_predict_control=None, x_predict_moderate=None, pihat_predict=None, predict_draws=False, keep_sampler=False,
+        x_spare_column=False):
     """Fit the Bayesian Causal Forest  y = mu(x, pihat) + tau(x) z + eps  on the GPU.
 
     Returns a dict with bcf's fields: `sigma` (nsim*n_chains), `yhat`, `mu`, `tau` (nsim*n_chains x n, original row
@@ -60,7 +61,9 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
     which every saved sweep's forests are evaluated on the device -> `tau_predict_mean`, `tau_predict_var`,
     `mu_predict_mean` (and `tau_predict`, `mu_predict`: nsim*n_chains x n_new with predict_draws=True), original y units;
     `keep_sampler` (the first chain's _lib.Sampler is returned open as out["sampler"]: bcf_iv grows its CART on the binned
-    covariates that are already on the device; the caller closes it).  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
+    covariates that are already on the device; the caller closes it); `x_spare_column` (the caller states that x_control --
+    passed for x_moderate as well -- is the leading columns of a column-major buffer of its own with one spare trailing
+    column, which bcf may overwrite with pihat: saves the n x p copy into [x | pihat]).  bcf 2.x arguments that have no meaning here (n_cores, n_threads, save_tree_directory, log_file,
     no_output, verbose, update_interval) are accepted and ignored; observation weights `w` are not implemented.
     """
     if nburn is None or nsim is None:
@@ -79,7 +82,7 @@ def bcf(y, z, x_control, x_moderate=None, pihat=None, nburn=None, nsim=None, nth
         raise _lib.BcfGpuError(2, "no CUDA device available (libbcfgpu has no CPU fallback)")
     P = prep.prepare(y, z, x_control, x_moderate, pihat, include_pi=include_pi, sd_control=sd_control,
                      sd_moderate=sd_moderate, nu=nu, lambda_=lambda_, sigq=sigq, sighat=sighat,
-                     use_tauscale=use_tauscale)
+                     use_tauscale=use_tauscale, spare_column=bool(x_spare_column))
     cc, oc = prep.pack_cuts(P.cuts_c)
     cm, om = prep.pack_cuts(P.cuts_m)
     n = P.n

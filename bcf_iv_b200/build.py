@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbcfgpu.so")
-SOURCES = ["bcfgpu.cu"]
-HEADERS = ["bcf_device.cuh", "bcf_step.cuh", "bcf_kernels.cuh", "bcf_persistent.cuh", "bcf_batched.cuh", "bcf_pipe.cuh", "bcf_hist_mma.cuh", "bcf_glm.cuh", "bcfgpu_glm.inl", os.path.join("..", "..", "include", "bcfgpu.h")]
+SOURCES = ["bcfgpu.cu", "bcf_host.cpp"]
+HEADERS = ["bcf_device.cuh", "bcf_step.cuh", "bcf_kernels.cuh", "bcf_persistent.cuh", "bcf_batched.cuh", "bcf_pipe.cuh", "bcf_hist_mma.cuh", "bcf_host.h", "bcf_glm.cuh", "bcfgpu_glm.inl", os.path.join("..", "..", "include", "bcfgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               # no FMA contraction: every kernel (and both engines, and any sharding) rounds identically
               "-fmad=false",

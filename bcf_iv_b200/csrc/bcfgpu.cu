@@ -6,6 +6,7 @@
 #include "bcf_batched.cuh"
 #include "bcf_pipe.cuh"
 #include "bcf_hist_mma.cuh"
+#include "bcf_host.h"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -656,6 +657,22 @@ static void parallel_ranges(int64_t n, int64_t align, int parts, F f)
     for (int t = 1; t < parts; ++t) th.emplace_back([&, t] { f(t, bound(t), bound(t + 1)); });
     f(0, bound(0), bound(1));
     for (auto& x : th) x.join();
+}
+
+// ------------------------------------------------------------------------------------------------
+// host pre-pass of bcf's R wrapper over the covariates (no device needed)
+// ------------------------------------------------------------------------------------------------
+extern "C" int bcfgpu_scan_columns(const double* X, int64_t n, int32_t p, int64_t ld, double* lo, double* hi, uint8_t* flags)
+{
+    if (!X || !lo || !hi || !flags || n < 1 || p < 1 || ld < n) return fail(BCFGPU_ERR_BAD_ARG, "bad argument");
+    std::atomic<int> next{0};
+    auto work = [&] { for (int v; (v = next.fetch_add(1)) < p;) scan_column(X + (int64_t)v * ld, n, lo + v, hi + v, flags + v); };
+    const int nth = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)host_threads(), (int64_t)p, n * (int64_t)p / 65536 + 1}));
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return BCFGPU_OK;
 }
 
 constexpr int PLACE_CHUNK = 4096;                 // rows per CTA of k_place (the host hands over one prefix count per chunk)

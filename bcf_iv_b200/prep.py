@@ -45,10 +45,22 @@ def cp_quantile(x: np.ndarray, num: int = CP_NUM, cat_levels: int = CP_CAT_LEVEL
     return np.interp(grid, uxs, mq)
 
 
-def make_cutpoints(X: np.ndarray):
-    """Per-column cutpoints of an n x p matrix -> list of p sorted float64 vectors."""
+def scan_columns(X: np.ndarray):
+    """(lo, hi, flags) per column in one threaded host pass of the native library (bcfgpu_scan_columns; no device needed):
+    flags bit 0 = two-valued or constant column, bit 1 = a NaN / Inf is present."""
+    from . import _lib
+    return _lib.scan_columns(X)
+
+
+def make_cutpoints(X: np.ndarray, scan=None):
+    """Per-column cutpoints of an n x p matrix -> list of p sorted float64 vectors.  `scan`: scan_columns(X) if the caller has
+    it already; two-valued columns (the reference's covariates) then cost nothing more."""
     X = np.asarray(X, dtype=np.float64)
-    return [cp_quantile(X[:, v]) for v in range(X.shape[1])]
+    if X.shape[1] == 0:
+        return []
+    lo, hi, fl = scan if scan is not None else scan_columns(X)
+    return [np.array([lo[v] + (hi[v] - lo[v]) / 2.0]) if (fl[v] & 1) and lo[v] != hi[v] else cp_quantile(X[:, v])
+            for v in range(X.shape[1])]
 
 
 def pack_cuts(cut_list):
@@ -84,12 +96,25 @@ class Prepared:
                  "sighat", "lambda_", "con_sd", "mod_sd", "sigma_init")
 
 
+def _spare_column_buffer(x: np.ndarray, extra: int):
+    """x as the leading columns of its own column-major base buffer with `extra` spare trailing columns, or None"""
+    b = x.base
+    if (isinstance(b, np.ndarray) and b.ndim == 2 and b.dtype == np.float64 and b.flags.f_contiguous and b.flags.writeable
+            and x.ndim == 2 and b.shape[0] == x.shape[0] and b.shape[1] >= x.shape[1] + extra and x.strides == b.strides
+            and x.ctypes.data == b.ctypes.data):
+        return b
+    return None
+
+
 def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_control=None, sd_moderate=None,
-            nu=3.0, lambda_=None, sigq=0.9, sighat=None, use_tauscale=True, sigma_fn=None, device=0) -> Prepared:
+            nu=3.0, lambda_=None, sigq=0.9, sighat=None, use_tauscale=True, sigma_fn=None, device=0,
+            spare_column=False) -> Prepared:
     """bcf's R-side preamble [bcf-recall, SURVEY A.1].  Returns arrays in the ORIGINAL row order plus `perm`
     (treated rows first, stable: R's order(z, decreasing=TRUE)); the native library applies the permutation.
     `sigma_fn(yscale, z, x_c)`: what computes the default sighat (the device's lm_sigma; the parity tests hand in the
-    CPU oracle's so that problems can be prepared without a GPU)."""
+    CPU oracle's so that problems can be prepared without a GPU).  `spare_column`: the caller states that x_control is the
+    leading columns of a column-major buffer of its own with a spare trailing column that may be overwritten: pihat goes
+    there and the n x p copy into [x | pihat] is saved (what bcf_iv does with its discovery sample)."""
     same_x = x_moderate is x_control            # bcf(y, z, x, x, pihat): what BayesIV calls (R/bcf_iv.R:89)
     y = np.asarray(y, dtype=np.float64).ravel()
     z = np.asarray(z).ravel()
@@ -105,7 +130,7 @@ def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_cont
     n = y.size
     if not (z.size == n and x_control.shape[0] == n and x_moderate.shape[0] == n and pihat.shape[0] == n):
         raise ValueError("y, z, x_control, x_moderate and pihat must have the same number of rows")
-    if not (_all_finite(y) and _all_finite(x_control) and (same_x or _all_finite(x_moderate)) and _all_finite(pihat)):
+    if not (_all_finite(y) and _all_finite(pihat)):
         raise ValueError("Missing or non-finite values in y, x_control, x_moderate or pihat")
     if not np.all((z == 0) | (z == 1)):
         raise ValueError("z must be a vector of 0's and 1's")
@@ -117,17 +142,28 @@ def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_cont
     if same_x and include_pi == "control":
         # one column-major matrix [x | pihat]; x_moderate is its leading columns (the library then bins and copies it once)
         pc = x_control.shape[1]
-        x_c = np.empty((n, pc + pihat.shape[1]), dtype=np.float64, order="F")
-        if x_control.flags.c_contiguous and pc > 1:
-            for r0 in range(0, n, 8192):              # row-major -> column-major in cache-sized blocks (1.5x a plain assignment)
-                x_c[r0:r0 + 8192, :pc] = x_control[r0:r0 + 8192]
+        buf = _spare_column_buffer(x_control, pihat.shape[1]) if spare_column else None
+        if buf is not None:
+            x_c = buf[:, :pc + pihat.shape[1]]        # in place: no n x p copy
         else:
-            x_c[:, :pc] = x_control
+            x_c = np.empty((n, pc + pihat.shape[1]), dtype=np.float64, order="F")
+            if x_control.flags.c_contiguous and pc > 1:
+                for r0 in range(0, n, 8192):          # row-major -> column-major in cache-sized blocks (1.5x a plain assignment)
+                    x_c[r0:r0 + 8192, :pc] = x_control[r0:r0 + 8192]
+            else:
+                x_c[:, :pc] = x_control
         x_c[:, pc:] = pihat
         x_m = x_c[:, :x_control.shape[1]]
+        m_is_prefix = True
     else:
+        m_is_prefix = False
         x_c = np.column_stack([x_control, pihat]) if include_pi in ("control", "both") else x_control
         x_m = np.column_stack([x_moderate, pihat]) if include_pi in ("moderate", "both") else x_moderate
+    # one threaded pass over the covariates: the NA check and what .cp_quantile needs to know about every column
+    scan_c = scan_columns(x_c)
+    scan_m = None if m_is_prefix else scan_columns(x_m)
+    if np.any(scan_c[2] & 2) or (scan_m is not None and np.any(scan_m[2] & 2)):
+        raise ValueError("Missing or non-finite values in y, x_control, x_moderate or pihat")
 
     P = Prepared()
     P.n = n
@@ -136,8 +172,8 @@ def prepare(y, z, x_control, x_moderate, pihat, *, include_pi="control", sd_cont
     P.yscale = (y - P.muy) / P.sdy
     P.z = z.astype(np.int32)
     P.x_c, P.x_m = x_c, x_m
-    P.cuts_c = make_cutpoints(x_c)
-    P.cuts_m = P.cuts_c[:x_m.shape[1]] if x_m.base is x_c else make_cutpoints(x_m)
+    P.cuts_c = make_cutpoints(x_c, scan_c)
+    P.cuts_m = P.cuts_c[:x_m.shape[1]] if m_is_prefix else make_cutpoints(x_m, scan_m)
     P.sighat = float(sighat) if sighat is not None else float(sigma_fn(P.yscale, z, x_c) if sigma_fn else lm_sigma(P.yscale, z, x_c, device))
     P.lambda_ = float(lambda_) if lambda_ is not None else P.sighat ** 2 * qchisq(1.0 - sigq, nu) / nu
     P.perm = np.argsort(-P.z, kind="stable")          # treated first, ties in original order

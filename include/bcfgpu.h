@@ -265,6 +265,13 @@ BCFGPU_API int bcfgpu_glm_logit(int32_t device, int64_t n, int32_t p, const doub
 BCFGPU_API int bcfgpu_lm_sigma(int32_t device, int64_t n, int32_t p, const double *X, int32_t row_major,
                                const int32_t *z, const double *y, double *sigma_out, double *beta_out, int32_t *info);
 
+/* The pass over the covariates that bcf's R wrapper makes before the native call (the NA check, and
+ * .cp_quantile's look at every column), on the library's host threads; needs no device.  Per column v of the
+ * column-major n x p matrix X (leading dimension ld >= n): lo[v] = min, hi[v] = max, flags[v] bit 0 = every value equals
+ * lo or hi (a two-valued or constant column: its cutpoint grid is lo + (hi - lo) / 2, no sort), bit 1 = NaN / Inf present. */
+BCFGPU_API int bcfgpu_scan_columns(const double *X, int64_t n, int32_t p, int64_t ld, double *lo, double *hi,
+                                   uint8_t *flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,3 +184,53 @@ def test_prepare_shares_the_matrix_when_bcf_is_called_with_the_same_x_twice():
         assert np.array_equal(u, v)
     c = helpers.prepare(y, z, X, X, pihat, include_pi="both")      # pihat in both: two matrices again
     assert not np.shares_memory(c.x_m, c.x_c) and c.x_m.shape[1] == p + 1
+
+
+def test_scan_columns_is_the_numpy_answer_for_every_kind_of_column():
+    """bcfgpu_scan_columns (one threaded host pass of the library, no device): min, max, "two-valued" and "non-finite" per
+    column, on a column-major matrix, on a view with a larger column stride, and on a row-major one"""
+    from bcf_iv_b200 import _lib
+    rng = np.random.default_rng(4)
+    n = 10007
+    cols = [rng.integers(0, 2, n).astype(float), np.full(n, 3.0), rng.standard_normal(n), rng.integers(0, 3, n).astype(float),
+            np.where(rng.random(n) < 0.5, -1.5, 2.25), rng.standard_normal(n), rng.standard_normal(n)]
+    cols[5][n - 1] = np.nan
+    cols[6][17] = -np.inf
+    X = np.asfortranarray(np.column_stack(cols))
+    want_two = [1, 1, 0, 0, 1, 0, 0]
+    want_bad = [0, 0, 0, 0, 0, 1, 1]
+    for M in (X, np.asfortranarray(np.column_stack(cols + [np.zeros(n)] * 3))[:, :7], np.ascontiguousarray(X)):
+        lo, hi, fl = _lib.scan_columns(M)
+        assert list(fl & 1) == want_two and list((fl >> 1) & 1) == want_bad
+        for v in range(5):
+            assert lo[v] == X[:, v].min() and hi[v] == X[:, v].max()
+    cuts = prep.make_cutpoints(X[:, :5])
+    assert np.array_equal(cuts[0], [0.5]) and np.array_equal(cuts[4], [0.375])
+    assert all(np.array_equal(a, prep.cp_quantile(X[:, v])) for v, a in enumerate(cuts) if v != 1)
+
+
+def test_prepare_with_a_spare_column_builds_the_design_in_place():
+    """bcf(x_spare_column=True): x_control is the leading columns of the caller's column-major buffer with one spare column;
+    prepare() puts pihat there instead of copying n x p numbers -- same Prepared as the copying path"""
+    from bcf_iv_b200 import bart
+    rng = np.random.default_rng(9)
+    n, p = 3001, 6
+    Xall = np.column_stack([rng.integers(0, 2, (2 * n, p - 1)).astype(float), rng.standard_normal(2 * n)])
+    rows = np.sort(rng.choice(2 * n, n, replace=False))
+    y, z, pihat = rng.standard_normal(n), rng.integers(0, 2, n), 0.1 * rng.standard_normal(n)
+    Xd = bart._as_design(Xall, 1, rows=rows)[:, :p]
+    assert np.array_equal(Xd, Xall[rows]) and Xd.flags.f_contiguous
+    P0 = helpers.prepare(y, z, Xall[rows], Xall[rows], pihat)
+    P1 = helpers.prepare(y, z, Xd, Xd, pihat, spare_column=True)
+    assert P1.x_c.ctypes.data == Xd.ctypes.data and P1.x_m.ctypes.data == Xd.ctypes.data      # in place
+    assert np.array_equal(P0.x_c, P1.x_c) and np.array_equal(P0.x_m, P1.x_m)
+    assert all(np.array_equal(a, b) for a, b in zip(P0.cuts_c, P1.cuts_c)) and len(P1.cuts_m) == p
+    assert P0.sighat == P1.sighat and P0.lambda_ == P1.lambda_
+    # not a leading-columns view of a buffer with room: the copying path, the caller's matrix untouched
+    V = np.asfortranarray(Xall[rows])
+    keep = V.copy()
+    P2 = helpers.prepare(y, z, V, V, pihat, spare_column=True)
+    assert np.array_equal(V, keep) and np.array_equal(P2.x_c, P0.x_c)
+    with pytest.raises(ValueError):
+        bad = Xd.copy(order="F"); bad[5, 2] = np.nan
+        helpers.prepare(y, z, bad, bad, pihat)
