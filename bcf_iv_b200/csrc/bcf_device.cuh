@@ -175,6 +175,11 @@ struct Dev {
     int32_t post_cap;
     long long* prof;           // optional [16] cycle counters of CTA 0 (persistent engine), null = off
     int* dbg;                  // host-mapped pinned words: where a kernel gave up before it trapped (survives the context's death)
+    // probit BART (null / 0 otherwise): the observed 0/1 response and the caller's row numbers in internal order, the offset
+    const uint8_t* ybin;
+    const int32_t* orig;
+    double probit_offset;
+    int32_t probit, pad2_;
 };
 
 // The persistent engines alternate between two statistics buffers by sweep parity: every sweep zeroes the buffer it

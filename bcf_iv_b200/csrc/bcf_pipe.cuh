@@ -600,7 +600,7 @@ __device__ inline void pipe_resolve(PipeSmem& sm, SmallStage* st, const PipePlan
 }
 
 // proposals of sweep `sweep` (all threads of the CTA)
-__device__ inline void pipe_propose_all(PipeSmem& sm, const Dev& d, const TreeRec* trees, uint32_t sweep)
+__device__ __forceinline__ void pipe_propose_all(PipeSmem& sm, const Dev& d, const TreeRec* trees, uint32_t sweep)
 {
     const int t = threadIdx.x;
     for (int j = blockIdx.x; j < d.T; j += gridDim.x) {
@@ -630,6 +630,31 @@ __device__ inline void pipe_propose_all(PipeSmem& sm, const Dev& d, const TreeRe
     }
 }
 
+// probit BART: the latent draw that opens the NEXT sweep, for a lane's 8 observations of a tile, made in the finishing pass of
+// the sweep before (k_probit_latent's arithmetic and Philox addresses, term for term; its own function so that the
+// double-precision inverse normal does not weigh on the register allocation of the sweep itself)
+__device__ __noinline__ void pipe_probit_latent8(Rng rng, const uint8_t* ybin, const int32_t* orig, double* yout, double offset, uint32_t sweep,
+                                                   double ms, const double (&gc)[8], double (&y)[8], int* bad)
+{
+    // (scalars, not the Dev: a reference to the kernel's parameter block would make the kernel copy it to its stack)
+    const uint2 yb = *reinterpret_cast<const uint2*>(ybin);
+    const int4 o0 = *reinterpret_cast<const int4*>(orig), o1 = *reinterpret_cast<const int4*>(orig + 4);
+    const int32_t og[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll 1
+    for (int o = 0; o < 8; ++o) {
+        if (og[o] < 0) { y[o] = 0.0; continue; }                // padding: y = 0, residual 0
+        double ua, ub;
+        rng_u2(rng, sweep, TREE_SWEEP_LEVEL, PUR_LATENT, (uint32_t)og[o], ua, ub);
+        const int yo = (int)(((o < 4 ? yb.x : yb.y) >> (8 * (o & 3))) & 0xFFu);
+        const double ys = probit_latent_d(offset + ms * gc[o], yo, ua) - offset;
+        if (!(ys == ys)) *bad = 1;
+        y[o] = ys;
+    }
+    st8_f64(yout, y);
+}
+
+// PROBIT: probit BART (the instantiation that draws the latent in its finishing pass; the BCF one carries none of that code)
+template <bool PROBIT>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, unsigned int* bar, int ntl_max, int* done_out)
 {
     extern __shared__ __align__(16) unsigned char bcf_dyn_smem[];
@@ -983,6 +1008,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pipe(Dev d, int nsweeps, un
 #pragma unroll
                         for (int o = 0; o < 8; ++o) gm[o] = 0.0;
                     }
+                    if (PROBIT)                                                                  // (one forest: gc is the fit)
+                        pipe_probit_latent8(Rng{d.key0, d.key1}, d.ybin + gb, d.orig + gb, const_cast<double*>(d.y) + gb, d.probit_offset, sn.sweep, ms, gc, y, &bad);
 #pragma unroll
                     for (int o = 0; o < 8; ++o) R[o] = resync_fx(y[o], ms, gc[o], bb, gm[o], bad);
                     res_st8i(rs.R + toff, lane, R);

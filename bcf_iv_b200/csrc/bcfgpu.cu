@@ -149,6 +149,8 @@ struct bcfgpu_handle {
     int32_t forests_saved = 0;
     int* dbg_host = nullptr;          // mapped pinned words the kernels write before they trap (Dev::dbg)
     uint8_t* d_ybin = nullptr;        // probit BART: the observed 0/1 response, internal order
+    bool latent_drawn = false;        // probit BART: the latent of the next sweep exists (k_pipe draws it in its finishing pass)
+    bool fuse_latent = false;         // probit BART: k_pipe<true> is in use (BCFGPU_NO_FUSED_LATENT=1: k_probit_latent before every sweep)
     int* d_cflist = nullptr;          // probit BART: trees that split on the treatment (k_cf_collect)
     std::atomic<int> stop{0};         // bcfgpu_request_stop: the run in progress ends at its next launch boundary
 };
@@ -384,7 +386,7 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
     // handle, so it is raised once to the device's opt-in maximum (handles with different n on one GPU would otherwise
     // lower each other's limit between select_kernel() and the launch); select_kernel() only checks its own need.
     if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&h->max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    for (const void* fn : {(const void*)k_batched<true>, (const void*)k_pipe, (const void*)k_resident, (const void*)k_hist_mma}) {
+    for (const void* fn : {(const void*)k_batched<true>, (const void*)k_pipe<false>, (const void*)k_pipe<true>, (const void*)k_resident, (const void*)k_hist_mma}) {
         cudaFuncAttributes fa;
         if (e2 == cudaSuccess) e2 = cudaFuncGetAttributes(&fa, fn);
         if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin - (int)fa.sharedSizeBytes);
@@ -960,6 +962,8 @@ extern "C" int bcfgpu_set_data(bcfgpu_handle* h, int64_t n, int32_t p_con, int32
         DM(h, &h->d_ybin, (size_t)n_pad);
         DM(h, &h->d_cflist, (size_t)h->T + 1);
         k_probit_prepare<<<(unsigned)std::min<int64_t>((n_pad + 255) / 256, 4096), 256, 0, h->stream>>>(dy, h->d_ybin, n_pad);
+        d.ybin = h->d_ybin; d.orig = h->d_orig; d.probit_offset = c.probit_offset; d.probit = 1;
+        h->fuse_latent = !getenv("BCFGPU_NO_FUSED_LATENT");
         h->launches++;
         CK(cudaGetLastError());
     }
@@ -1208,6 +1212,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
             if (!spec) {
                 pre(it, nullptr);
                 r = launch_sweeps(1);
+                if (!persistent) h->latent_drawn = false;
                 if (r == BCFGPU_OK) post(it, nullptr);
                 ++it;
                 continue;
@@ -1216,7 +1221,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
             CK(cudaMemsetAsync(h->d_done, 0, 12, h->stream));
             for (int j = 0; j < m && r == BCFGPU_OK; ++j) {
                 pre(it + j, stall);
-                r = run_persistent(h, 1, true);
+                r = run_persistent(h, 1, true);      // (probit BART: the sweeps queued behind it find their latent drawn by this one)
                 post(it + j, stall);
             }
             if (r) break;
@@ -1232,7 +1237,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
             CK(cudaMemsetAsync(h->d_done, 0, 12, h->stream));
             const int keep_kernel = h->kernel;
             h->kernel = h->fallback_kernel;
-            r = run_persistent(h, 1);
+            r = run_persistent(h, 1);                // (the batched kernel draws no latent: latent_drawn is false behind it)
             h->kernel = keep_kernel;
             if (r == BCFGPU_OK) post(it + c, nullptr);
             it += c + 1;
@@ -1246,16 +1251,30 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
         return k < nsim ? k : -1;
     };
     if (h->cfg.model == BCFGPU_MODEL_PROBIT_BART) {
-        // One sweep per launch: the latent draw opens it (its own kernel: every engine parks the chain state in HBM between
-        // launches), the sweep kernel runs it as a burn-in sweep (the engines' own posterior accumulation stays off), and a
-        // saved sweep ends with the counterfactual pass.
+        // A latent draw opens every sweep, the sweep kernel runs it as a burn-in sweep (the engines' own posterior accumulation
+        // stays off), and a saved sweep ends with the counterfactual pass.  The pipelined kernel makes the next sweep's draw in
+        // its own finishing pass (h->latent_drawn: run_persistent keeps it), so burn-in runs many sweeps per launch and a saved
+        // sweep costs one launch + the counterfactual pass; the other engines get the draw from k_probit_latent before every
+        // sweep, one sweep per launch (every engine parks the chain state in HBM between launches).
         const int grid = h->grid_fin;
         const int cfgrid = (int)((d.n_pad + 256 * CF_OBS_PER_THREAD - 1) / (256 * CF_OBS_PER_THREAD));
-        rc = stepwise(0, total,
-            [&](int, const int* stall) {
-                k_probit_latent<<<grid, 256, 0, h->stream>>>(d, h->d_ybin, h->d_orig, 0, h->cfg.probit_offset, const_cast<double*>(d.y), stall);
-                h->launches++;
-            },
+        h->latent_drawn = false;                       // (a run's first sweep: drawn here; redrawing an existing draw gives the same numbers)
+        auto draw = [&](int, const int* stall) {
+            if (h->latent_drawn) return;
+            k_probit_latent<<<grid, 256, 0, h->stream>>>(d, h->d_ybin, h->d_orig, 0, h->cfg.probit_offset, const_cast<double*>(d.y), stall);
+            h->launches++;
+        };
+        int it0 = 0;
+        if (h->fuse_latent && persistent && h->nranks == 1 && select_kernel(h) == BCFGPU_OK && h->kernel == 4) {
+            int first_saved = total;
+            for (int it = 0; it < total; ++it) if (save_index(it) >= 0) { first_saved = it; break; }
+            if (first_saved > 0) {
+                draw(0, nullptr);
+                rc = launch_sweeps(first_saved);
+                it0 = first_saved;
+            }
+        }
+        if (rc == BCFGPU_OK) rc = stepwise(it0, total, draw,
             [&](int it, const int* stall) {
                 if (save_index(it) < 0) return;
                 const int par = (sc.parity + it + 1) & 1;     // the sweep flipped the tree parity
@@ -2037,7 +2056,7 @@ static int select_kernel(bcfgpu_handle* h)
             if ((h->kernel == 3 || h->kernel == 5) && may_reside && h->engine == BCFGPU_ENGINE_PIPELINED && h->T <= 4096 && (h->nranks == 1 || h->peer_ok) && !h->no_pipe) {
                 h->fallback_kernel = h->kernel;
                 const size_t needp = PIPE_SMEM_BYTES + (size_t)ntl_max * PIPE_BYTES_PER_TILE + (size_t)h->T * sizeof(TMeta) + 16;
-                if (fits((const void*)k_pipe, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; h->pipe_ntl = ntl_max; }
+                if (fits(h->fuse_latent ? (const void*)k_pipe<true> : (const void*)k_pipe<false>, needp, PIPE_THREADS)) { h->kernel = 4; h->pipe_smem = needp; h->pipe_ntl = ntl_max; }
                 else if (h->cfg.engine == BCFGPU_ENGINE_PIPELINED)
                     return fail(BCFGPU_ERR_BAD_ARG, "BCFGPU_ENGINE_PIPELINED: the observations of one SM do not fit in shared memory at this n");
             }
@@ -2083,8 +2102,9 @@ static int run_persistent(bcfgpu_handle* h, int total, bool no_sync)
             d.pr.batch0 = h->pipe_batches;
             int pntl = h->pipe_ntl;
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&pntl, (void*)&dn};
-            CK(cudaLaunchCooperativeKernel((const void*)k_pipe, dim3(h->coop_grid), dim3(PIPE_THREADS), args, h->pipe_smem, h->stream));
+            CK(cudaLaunchCooperativeKernel(h->fuse_latent ? (const void*)k_pipe<true> : (const void*)k_pipe<false>, dim3(h->coop_grid), dim3(PIPE_THREADS), args, h->pipe_smem, h->stream));
             h->launches++;
+            h->latent_drawn = h->fuse_latent;         // probit BART: k_pipe<true>'s finishing pass draws the next sweep's latent
             if (no_sync) {   // speculative (stepwise()): the caller zeroed d_done, checks it later and reruns what was refused
                 done += nsw;
                 continue;
@@ -2107,9 +2127,14 @@ static int run_persistent(bcfgpu_handle* h, int total, bool no_sync)
                                                dim3(PTHREADS), a2, h->res_smem, h->stream));
                 h->launches++;
                 done += 1;
+                if (h->fuse_latent) {   // (the batched kernel does not draw: the sweep behind it gets its latent from the stand-alone kernel)
+                    k_probit_latent<<<h->grid_fin, 256, 0, h->stream>>>(d, h->d_ybin, h->d_orig, 0, h->cfg.probit_offset, const_cast<double*>(d.y), nullptr);
+                    h->launches++;
+                }
             }
             continue;
         }
+        h->latent_drawn = false;                      // (the other sweep kernels leave the draw to k_probit_latent)
         const int* none = nullptr;
         if (h->kernel == 3) {
             void* args[] = {(void*)&d, (void*)&nsw, (void*)&bar, (void*)&ntl, (void*)&none};

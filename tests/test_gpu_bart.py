@@ -122,3 +122,34 @@ def test_sweeps_with_wide_trees_are_rerun_by_the_batched_kernel():
     st = g.engine_stats
     assert st["fallback_sweeps"] > 0 and st["pipelined_sweeps"] > 0, st
     g.close(); o.close()
+
+
+def test_latent_drawn_inside_the_sweep_kernel_is_the_stand_alone_draw(monkeypatch):
+    """k_pipe<true> draws the next sweep's latent in its finishing pass (burn-in then runs many sweeps per launch);
+    BCFGPU_NO_FUSED_LATENT=1 keeps round 2's form, k_probit_latent before every sweep.  Both walk the oracle's chain, through
+    wide-tree fallbacks as well, and give bit-identical posterior means."""
+    res = []
+    for n, ntree, nb, ns in ((3000, 75, 40, 25), (4000, 4, 120, 30)):
+        rng = np.random.default_rng(n)
+        X = rng.random((n, 3))
+        z = (rng.random(n) < 0.5).astype(np.int32)
+        pr = 0.5 + 0.45 * np.sin(9 * X[:, 0]) * np.cos(7 * X[:, 1])
+        y = (rng.random(n) < pr).astype(np.float64)
+        o, perm = oracle_probit_sampler(y, X, z, seed=11, n_trees=ntree, max_leaves=128)
+        out = o.probit_run(nb, ns, 1)
+        inv = np.empty(perm.size, np.int64); inv[perm] = np.arange(perm.size)
+        for fused in (True, False):
+            if fused:
+                monkeypatch.delenv("BCFGPU_NO_FUSED_LATENT", raising=False)
+            else:
+                monkeypatch.setenv("BCFGPU_NO_FUSED_LATENT", "1")
+            g = _gpu_sampler(y, X, z, seed=11, n_trees=ntree)
+            g.run(nb, ns)
+            assert np.array_equal(g.trace()[0], o.trace()[0]) and g.counters() == o.counters(), (n, fused)
+            assert np.allclose(g.tau_mean(), out["ite_mean"][inv], rtol=1e-8, atol=1e-8)
+            res.append((g.tau_mean().copy(), g.fits()[0].copy(), g.kernel_launches))
+            g.close()
+        o.close()
+        (ta, fa, la), (tb, fb, lb) = res[-2], res[-1]
+        assert np.array_equal(ta, tb) and np.array_equal(fa, fb)
+        assert la < lb                                            # fewer launches: no latent kernels, burn-in in few launches
