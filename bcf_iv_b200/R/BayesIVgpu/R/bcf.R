@@ -36,8 +36,8 @@ bcf <- function(y, z, x_control, x_moderate = x_control, pihat, nburn, nsim, nth
   x_c <- if (include_pi %in% c("control", "both")) cbind(x_control, pihat) else x_control
   x_m <- if (include_pi %in% c("moderate", "both")) cbind(x_moderate, pihat) else x_moderate
   storage.mode(x_c) <- "double"; storage.mode(x_m) <- "double"
-  cut_c <- lapply(seq_len(ncol(x_c)), function(j) .cutpoints(x_c[, j]))
-  cut_m <- lapply(seq_len(ncol(x_m)), function(j) .cutpoints(x_m[, j]))
+  cut_c <- .cutpoints_matrix(x_c)
+  cut_m <- .cutpoints_matrix(x_m)
   muy <- mean(y); sdy <- sd(y); yscale <- (y - muy) / sdy
   if (is.null(sighat)) {   # summary(lm(yscale ~ z + x_c))$sigma, on the device (bcfgpu_lm_sigma)
     xs <- as.matrix(x_c); storage.mode(xs) <- "double"
@@ -90,6 +90,15 @@ bcf <- function(y, z, x_control, x_moderate = x_control, pihat, nburn, nsim, nth
     fit$tau <- sdy * bind("tau"); fit$mu <- muy + sdy * bind("mu"); fit$yhat <- muy + sdy * bind("yhat")
   }
   fit
+}
+
+# every column's grid after ONE threaded pass of the library over the matrix (bcfgpu_scan_columns: min, max, two-valued,
+# non-finite): a two-valued column -- the reference's covariates -- needs no sort, the others go through .cutpoints
+.cutpoints_matrix <- function(x) {
+  s <- .Call("bcfgpu_R_scan_columns", x, PACKAGE = "BayesIVgpu")
+  if (any(s[3, ] >= 2)) stop("Missing or non-finite values in x_control, x_moderate or pihat")
+  lapply(seq_len(ncol(x)), function(j)
+    if (s[3, j] == 1 && s[1, j] != s[2, j]) s[1, j] + (s[2, j] - s[1, j]) / 2 else .cutpoints(x[, j]))
 }
 
 # bcf's .cp_quantile: one value -> itself; fewer than 8 distinct -> midpoints; else 10000 points of the empirical

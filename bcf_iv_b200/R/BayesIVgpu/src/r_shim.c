@@ -206,11 +206,31 @@ SEXP bcfgpu_R_lm_sigma(SEXP y, SEXP z, SEXP x, SEXP device)
     return Rf_ScalarReal(sigma);
 }
 
+/* .Call("bcfgpu_R_scan_columns", x): 3 x p matrix (min, max, flags) of the columns of x in one threaded pass of the library:
+ * flags 1 = two-valued or constant column (its cutpoint grid needs no sort), 2 = a NaN / Inf is present -- what bcf's R
+ * preamble asks of every column before the native call (the NA check and .cp_quantile's first look) */
+SEXP bcfgpu_R_scan_columns(SEXP x)
+{
+    if (!Rf_isReal(x) || !Rf_isMatrix(x)) Rf_error("bcfgpu_R_scan_columns: x must be a double matrix");
+    const R_xlen_t n = Rf_nrows(x);
+    const int p = Rf_ncols(x);
+    if (n < 1 || p < 1) Rf_error("bcfgpu_R_scan_columns: empty matrix");
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, 3, p));
+    double *lo = (double *)R_alloc((size_t)p, sizeof(double)), *hi = (double *)R_alloc((size_t)p, sizeof(double));
+    uint8_t *fl = (uint8_t *)R_alloc((size_t)p, 1);
+    const int rc = bcfgpu_scan_columns(REAL(x), (int64_t)n, p, (int64_t)n, lo, hi, fl);
+    if (rc != BCFGPU_OK) { UNPROTECT(1); Rf_error("libbcfgpu: %s", bcfgpu_last_error()); }
+    for (int j = 0; j < p; ++j) { REAL(out)[3 * j] = lo[j]; REAL(out)[3 * j + 1] = hi[j]; REAL(out)[3 * j + 2] = (double)fl[j]; }
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"bcfgpu_R_device_count", (DL_FUNC)&bcfgpu_R_device_count, 0},
     {"bcfgpu_R_fit_chains", (DL_FUNC)&bcfgpu_R_fit_chains, 17},
     {"bcfgpu_R_glm_logit", (DL_FUNC)&bcfgpu_R_glm_logit, 3},
     {"bcfgpu_R_lm_sigma", (DL_FUNC)&bcfgpu_R_lm_sigma, 4},
+    {"bcfgpu_R_scan_columns", (DL_FUNC)&bcfgpu_R_scan_columns, 1},
     {NULL, NULL, 0}};
 
 void R_init_BayesIVgpu(DllInfo *dll)

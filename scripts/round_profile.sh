@@ -11,6 +11,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 20 --warmup 5 > $O/${P}_ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_pipe -s 1 -c 1 -f -o $O/${P}_k_pipe \
     python bench.py --steps 20 --warmup 5 > $O/${P}_ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_bin -s 2 -c 1 -f -o $O/${P}_k_bin \
+[ "${SKIP_BIN:-0}" = 1 ] || ncu --set full --clock-control none --import-source on -k regex:k_bin -s 2 -c 1 -f -o $O/${P}_k_bin \
     python bench.py --steps 20 --warmup 5 > $O/${P}_ncu_full_bin.log 2>&1
 tail -1 $O/${P}_bench_n1.json | cut -c1-400

@@ -2,4 +2,5 @@
 #ifndef R_STUB_H
 #define R_STUB_H
 #include <stddef.h>
+char *R_alloc(size_t, int);            /* R_ext/Memory.h: transient storage, freed at the end of the .Call */
 #endif

@@ -28,6 +28,7 @@ double *REAL(SEXP);
 int *INTEGER(SEXP);
 SEXP Rf_ScalarInteger(int);
 SEXP Rf_ScalarReal(double);
+void Rf_warning(const char *, ...);
 SEXP Rf_allocVector(unsigned int, R_xlen_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);
 SEXP Rf_mkNamed(unsigned int, const char **);
