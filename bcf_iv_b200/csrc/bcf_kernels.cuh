@@ -971,7 +971,8 @@ __global__ void __launch_bounds__(256) k_probit_latent(Dev d, const uint8_t* __r
     }
     if (bad) atomicOr(d.err, ERR_FX_RANGE);
 }
-// which trees split on the treatment column?  one CTA per tree; list[0] = count, list[1..] = tree ids (any order)
+// which trees split on the treatment column?  one CTA per tree; list[1 + t] = 1 if tree t does (a flag per tree, not a list
+// in arrival order: the pass below then adds the trees' contributions in tree order, so the effects are reproducible bit for bit)
 __global__ void k_cf_collect(Dev d, const TreeRec* __restrict__ trees, int trt_var, int* list, const int* stall)
 {
     if (stall != nullptr && __ldcg(stall) != 0) return;
@@ -979,7 +980,8 @@ __global__ void k_cf_collect(Dev d, const TreeRec* __restrict__ trees, int trt_v
     const int nn = __ldcg(&tr.nnodes);
     int hit = 0;
     for (int i = threadIdx.x; i < nn; i += blockDim.x) hit |= (__ldcg(&tr.left[i]) >= 0 && (int)__ldcg(&tr.var[i]) == trt_var) ? 1 : 0;
-    if (__syncthreads_or(hit) && threadIdx.x == 0) list[1 + atomicAdd(&list[0], 1)] = (int)blockIdx.x;
+    hit = __syncthreads_or(hit);
+    if (threadIdx.x == 0) list[1 + blockIdx.x] = hit ? 1 : 0;
 }
 // One saved sweep of the S-learner: f with the treatment flipped differs from the fitted f only through the trees that
 // split on the treatment; those are walked again with the flipped bin.  Accumulates (internal order)
@@ -992,7 +994,7 @@ __global__ void __launch_bounds__(256) k_cf_accumulate(Dev d, const TreeRec* __r
     __shared__ TreeRec tr;
     if (stall != nullptr && __ldcg(stall) != 0) return;
     const ForestDev& F = d.f[0];
-    const int nlist = trt_var >= 0 ? list[0] : 0;
+    const int nlist = trt_var >= 0 ? d.T : 0;
     const int64_t base = (int64_t)blockIdx.x * (256 * CF_OBS_PER_THREAD) + threadIdx.x;
     double diff[CF_OBS_PER_THREAD];
 #pragma unroll
@@ -1007,8 +1009,8 @@ __global__ void __launch_bounds__(256) k_cf_accumulate(Dev d, const TreeRec* __r
             tb[k] = F.col_is16[trt_var] ? (int)F.bins16[(int64_t)ci * d.n_pad + i] : (int)F.bins8[(int64_t)ci * d.n_pad + i];
         }
     }
-    for (int q = 0; q < nlist; ++q) {
-        const int t = list[1 + q];
+    for (int t = 0; t < nlist; ++t) {
+        if (list[1 + t] == 0) continue;                          // (the same for the whole CTA)
         __syncthreads();
         load_tree(&tr, &trees[t]);
         __syncthreads();

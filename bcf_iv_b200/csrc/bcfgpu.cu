@@ -1279,7 +1279,6 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
                 if (save_index(it) < 0) return;
                 const int par = (sc.parity + it + 1) & 1;     // the sweep flipped the tree parity
                 if (h->cfg.treatment_col >= 0) {
-                    cudaMemsetAsync(h->d_cflist, 0, 4, h->stream);
                     k_cf_collect<<<h->T, 64, 0, h->stream>>>(d, d.trees[par], h->cfg.treatment_col, h->d_cflist, stall);
                 }
                 k_cf_accumulate<<<cfgrid, 256, 0, h->stream>>>(d, d.trees[par], h->d_cflist, h->cfg.treatment_col,
