@@ -49,6 +49,9 @@ def scan_columns(X: np.ndarray):
     """(lo, hi, flags) per column in one threaded host pass of the native library (bcfgpu_scan_columns; no device needed):
     flags bit 0 = two-valued or constant column, bit 1 = a NaN / Inf is present."""
     from . import _lib
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 2 and X.shape[1] == 0:
+        return np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.uint8)
     return _lib.scan_columns(X)
 
 
