@@ -23,3 +23,27 @@ for engine in (5, 4, 2):
             print(f"engine {engine} rep {rep}: DIFFERENT sigma {got[0]!r} vs {ref[0]!r} counters {got[1]} vs {ref[1]} cache mismatches {mism}", flush=True)
     print(f"engine {engine}: {bad} of {reps} runs differ", flush=True)
 
+
+# probit BART (latent drawn inside k_pipe<true>, counterfactual pass in tree order) and K2' on the tensor cores: run to run, bit for bit
+from bcf_iv_b200 import bart, prep
+rng = np.random.default_rng(2)
+nb_ = min(n, 300_000)
+X = rng.integers(0, 2, (nb_, 30)).astype(np.float64)
+zb = rng.integers(0, 2, nb_).astype(np.int32)
+yb = (rng.random(nb_) < 0.3 + 0.3 * X[:, 0] * zb).astype(np.float64)
+xc = np.asfortranarray(np.column_stack([X, zb.astype(np.float64)]))
+cuts, off = prep.pack_cuts([bart.bart_cutpoints(xc[:, v]) for v in range(xc.shape[1])])
+refb, bad = None, 0
+for rep in range(reps):
+    b = _lib.Sampler(**bart.bart_config(seed=4, treatment_col=30))
+    b.set_data(yb, zb, xc, None, cuts, off)
+    b.run(12, 8)
+    slot = (np.arange(nb_) % 5).astype(np.int32)
+    cnt, sm, _ = b.op_hist_all(0, slot, 5, rng.standard_normal(nb_) if rep < 0 else np.sin(np.arange(nb_) * 0.37))
+    got = (b.trace()[0].tobytes(), b.tau_mean().tobytes(), b.fits()[0].tobytes(), cnt.tobytes(), sm.tobytes(), tuple(b.engine_stats.values()))
+    b.close()
+    if refb is None: refb = got
+    if got != refb:
+        bad += 1
+        print(f"probit BART / K2' rep {rep}: DIFFERENT", [a == c for a, c in zip(got, refb)], flush=True)
+print(f"probit BART + K2' (k_hist_mma): {bad} of {reps} runs differ; engine stats {refb[5]}", flush=True)
