@@ -1869,7 +1869,7 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
     if (!twoval.empty() && use_mma) {
         // B operand = the forest's uint8 bins as they lie in HBM: [p8 columns][n_pad observations], one byte each
         const int ncb = std::min(F.p8, HM_MAX_COLS), gy = (F.p8 + ncb - 1) / ncb;
-        const int ktiles = (int)(h->n_pad / HM_KT);
+        const int ktiles = (int)(h->n_pad / HM_TILE);             // (n_pad is a multiple of 256)
         const int gx0 = std::max(1, std::min(ktiles, std::max(1, h->num_sms / gy)));
         const int tpc = (ktiles + gx0 - 1) / gx0;
         CUtensorMap tm;
@@ -1879,19 +1879,25 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) { cudaFree(dlab); cudaFree(dout); cudaFree(dcols); return fail(BCFGPU_ERR_CUDA, "op_hist_all: cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"); }
-        // as many ring stages as shared memory holds, up to 8 (8 stages up to 8 leaves at 100 columns; 4 at 240 columns); the
-        // epilogue's tile of the accumulator needs three
-        // (an EVEN number: a stage is then always served by the same producer and the same MMA issuer -- the tiles' parity --,
-        // which the parity waits on its barriers rely on)
-        int nst = HM_MAX_STAGES;
-        while (nst > 4 && hm_smem_bytes(ncb, nst, nleaf) > (size_t)h->max_optin) nst -= 2;
-        const size_t smem = hm_smem_bytes(ncb, nst, nleaf);
+        // three rings (bcf_hist_mma.cuh): 4 stages for A whenever two B stages still fit beside them (measured at 8 and 12
+        // leaves: the A ring matters more than the B ring), and as many B stages as the rest of shared memory holds (6 at 100
+        // columns and 1-4 leaves).  EVEN numbers: a stage is then always served by the same producer and the same MMA issuer
+        // -- the tiles' parity --, which the parity waits on its barriers rely on.
+        int na = hm_smem_bytes(ncb, nleaf, HM_MAX_A_STAGES, 2) <= (size_t)h->max_optin ? HM_MAX_A_STAGES : 2;
+        int nb = HM_MAX_B_STAGES;
+        while (nb > 2 && hm_smem_bytes(ncb, nleaf, na, nb) > (size_t)h->max_optin) nb -= 2;
+        if (const char* e = getenv("BCFGPU_HIST_RINGS")) {   // experiments: "na,nb"
+            int a_ = 0, b_ = 0;
+            if (sscanf(e, "%d,%d", &a_, &b_) == 2 && (a_ == 2 || a_ == 4) && b_ >= 2 && b_ <= HM_MAX_B_STAGES && b_ % 2 == 0 &&
+                hm_smem_bytes(ncb, nleaf, a_, b_) <= (size_t)h->max_optin) { na = a_; nb = b_; }
+        }
+        const size_t smem = hm_smem_bytes(ncb, nleaf, na, nb);
         if (smem > (size_t)h->max_optin) { cudaFree(dlab); cudaFree(dout); cudaFree(dcols); return fail(BCFGPU_ERR_CUDA, "op_hist_all: k_hist_mma does not fit in shared memory"); }
         dim3 grid((unsigned)((ktiles + tpc - 1) / tpc), (unsigned)gy);
         const int probe = getenv("BCFGPU_HIST_PROBE") ? atoi(getenv("BCFGPU_HIST_PROBE")) : 0;   // timing experiments only
         long long* dtrace = nullptr;
         if (getenv("BCFGPU_HIST_TRACE")) { CK(cudaMalloc((void**)&dtrace, 6 * 64 * 8)); CK(cudaMemsetAsync(dtrace, 0, 6 * 64 * 8, h->stream)); }
-        k_hist_mma<<<grid, HM_THREADS, smem, h->stream>>>(tm, dlab, h->d_tmp2, nleaf, ncb, F.p8, ktiles, tpc, nst, dcolvar, F.d_off,
+        k_hist_mma<<<grid, HM_THREADS, smem, h->stream>>>(tm, dlab, h->d_tmp2, nleaf, ncb, F.p8, ktiles, tpc, na, nb, dcolvar, F.d_off,
                                                           (long long)nbt, dout, dleaf, h->dev.err, h->dev.dbg, probe, dtrace);
         if (dtrace) {   // the timeline of CTA 0, in cycles since its start (a debugging aid: synchronises)
             long long tr[6 * 64];
@@ -1899,10 +1905,10 @@ int bcfgpu_op_hist_all(bcfgpu_handle* h, int32_t forest, const int32_t* slot, in
             CK(cudaStreamSynchronize(h->stream));
             cudaFree(dtrace);
             const long long t0 = tr[5 * 64];
-            fprintf(stderr, "[k_hist_mma trace] nst %d tiles/CTA %d: set-up %lld, accumulator complete %lld, in smem %lld, end %lld\n", nst, tpc,
+            fprintf(stderr, "[k_hist_mma trace] A stages %d, B stages %d, K-tiles of 256 observations per CTA %d: set-up %lld, accumulator complete %lld, in smem %lld, end %lld\n", na, nb, tpc,
                     tr[5 * 64 + 1] - t0, tr[5 * 64 + 2] - t0, tr[5 * 64 + 3] - t0, tr[5 * 64 + 4] - t0);
             for (int i = 0; i < std::min(tpc, 64); ++i)
-                fprintf(stderr, "  tile %2d: issued %7lld landed(builder) %7lld built %7lld mma-ready %7lld committed %7lld\n", i, tr[i] - t0,
+                fprintf(stderr, "  tile %2d: bins issued %7lld inputs landed %7lld built %7lld mma-ready %7lld committed %7lld\n", i, tr[i] - t0,
                         tr[64 + i] - t0, tr[128 + i] - t0, tr[192 + i] - t0, tr[256 + i] - t0);
         }
         h->launches++;
