@@ -332,6 +332,24 @@ int bcfgpu_cache_stats(int64_t out2[2])
     return BCFGPU_OK;
 }
 
+// The 64 mapped pinned bytes a handle's kernels leave their give-up note in: pinned allocations cost about a millisecond
+// (a twentieth of a 20-sweep fit), so handles that are destroyed hand theirs to the next one (a few words per process).
+static std::mutex g_dbg_mu;
+static std::vector<int*> g_dbg_free;
+static cudaError_t dbg_words_take(int** out)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_dbg_mu);
+        if (!g_dbg_free.empty()) { *out = g_dbg_free.back(); g_dbg_free.pop_back(); return cudaSuccess; }
+    }
+    return cudaHostAlloc((void**)out, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+}
+static void dbg_words_give(int* p)
+{
+    std::lock_guard<std::mutex> lk(g_dbg_mu);
+    if (g_dbg_free.size() < 64) g_dbg_free.push_back(p); else cudaFreeHost(p);
+}
+
 int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
 {
     if (!cfg || !out) return fail(BCFGPU_ERR_BAD_ARG, "null argument");
@@ -371,7 +389,7 @@ int bcfgpu_create(const bcfgpu_config* cfg, bcfgpu_handle** out)
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming);
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_binned[b], cudaEventDisableTiming);
     }
-    if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&h->dbg_host, 64, cudaHostAllocMapped);
+    if (e2 == cudaSuccess) e2 = dbg_words_take(&h->dbg_host);
     if (e2 == cudaSuccess) memset(h->dbg_host, 0, 64);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&h->ev1);
@@ -413,7 +431,7 @@ int bcfgpu_destroy(bcfgpu_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int b = 0; b < 2; ++b) { if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]); if (h->ev_binned[b]) cudaEventDestroy(h->ev_binned[b]); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    if (h->dbg_host) cudaFreeHost(h->dbg_host);
+    if (h->dbg_host) dbg_words_give(h->dbg_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
