@@ -1334,7 +1334,7 @@ static int run_impl(bcfgpu_handle* h, int32_t nburn, int32_t nsim, int32_t nthin
         }
         if (h->dbg_host && h->dbg_host[0]) {
             char note[320];
-            snprintf(note, sizeof(note), " [kernel gave up: code %d (1x: flag wait, 20: peer words, 30: utility warp's grid barrier, 40: chain's grid barrier), CTA %d, %d, %d; rank %d; k_pipe launches started %d, past their first barrier %d]",
+            snprintf(note, sizeof(note), " [kernel gave up: code %d (20: peer words, 30: utility warp's grid barrier; 5x: k_hist_mma), CTA %d, %d, %d; rank %d; k_pipe launches started %d, past their first barrier %d]",
                      h->dbg_host[1], h->dbg_host[2], h->dbg_host[3], h->dbg_host[4], h->rank, h->dbg_host[8], h->dbg_host[9]);
             g_err += note;
         }
