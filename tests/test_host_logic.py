@@ -234,3 +234,18 @@ def test_prepare_with_a_spare_column_builds_the_design_in_place():
     with pytest.raises(ValueError):
         bad = Xd.copy(order="F"); bad[5, 2] = np.nan
         helpers.prepare(y, z, bad, bad, pihat)
+
+
+def test_inference_rows_are_read_through_their_split_columns_only():
+    """bcf_iv's per-node 2SLS looks at the inference sample only through the node rules: `_Rows` serves X[rows][:, v] one column
+    at a time (no n x p row gather), and rule_mask over it equals rule_mask over the gathered matrix"""
+    rng = np.random.default_rng(12)
+    X = rng.random((500, 7))
+    rows = rng.choice(500, 240, replace=False)
+    view = bayesiv._Rows(X, rows)
+    assert view.shape == (240, 7)
+    rule = [(2, "<", 0.6), (5, ">=", 0.3), (2, ">=", 0.1)]
+    assert np.array_equal(bayesiv.rule_mask(rule, view), bayesiv.rule_mask(rule, X[rows]))
+    assert set(view._col) == {2, 5}                                  # only the split columns were ever gathered
+    with pytest.raises(IndexError):
+        view[3:5, 1]
